@@ -1,0 +1,185 @@
+/* raxtax_b200.h -- C ABI of the B200 (sm_100a) query-classification library.
+ *
+ * Drop-in boundary for the per-query body of raxtax's driver loop: reference src/raxtax.rs:41-84
+ * (`intersect_buffer.fill(0)` ... the one-exact-match override), i.e. everything between "a parsed query"
+ * and "a Vec<EvaluationResult>" (src/lineage.rs:7-14).  FASTA parsing, Tree construction, the exact-match
+ * hash map, string formatting, logging and checkpointing stay on the host side of this boundary
+ * (see include/raxtax_host.h for the C++ host that mirrors the reference's `raxtax()` signature and
+ * INTEGRATION.md for the Rust `extern "C"` block a maintainer would add in src/raxtax.rs).
+ *
+ * Conventions: plain pointers and sizes, little-endian, caller owns every host buffer, the library owns
+ * every device allocation.  Every call returns 0 on success and a negative rtx_status on failure;
+ * rtx_last_error() gives the message.  One rtx_ctx per GPU, used from one host thread at a time; contexts
+ * are independent, so N GPUs = N contexts driven by N threads or N processes.  There is no CPU fallback:
+ * without a usable CUDA device rtx_ctx_create fails.
+ */
+#ifndef RAXTAX_B200_H
+#define RAXTAX_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RTX_ABI_VERSION 1
+#define RTX_MAX_LEVELS 32 /* deepest lineage (comma-separated ranks) the device tree walk supports */
+#define RTX_MAX_RESULTS_PER_QUERY 256 /* >= the 200 lines a query can produce with the 0.01 cutoff */
+
+typedef enum {
+    RTX_OK = 0,
+    RTX_ERR_INVALID = -1,     /* bad argument / violated input contract */
+    RTX_ERR_CUDA = -2,        /* CUDA runtime error (message has the CUDA string) */
+    RTX_ERR_NO_DEVICE = -3,   /* no CUDA device: the library has no CPU path */
+    RTX_ERR_NO_INDEX = -4,    /* classify before rtx_index_upload */
+    RTX_ERR_UNSUPPORTED = -5, /* input outside the supported envelope (e.g. > 8191 unique 8-mers in one query) */
+    RTX_ERR_ASSERT = -6       /* an invariant the reference asserts on failed (raxtax.rs:72, prob.rs:98) */
+} rtx_status;
+
+typedef struct rtx_ctx rtx_ctx;
+
+/* flags of rtx_batch.flags -- the two switches that reach the hot path (raxtax.rs:17-18) */
+#define RTX_SKIP_EXACT_MATCHES 1u /* --skip-exact-matches: zero the counters of exact matches (raxtax.rs:65-68) */
+#define RTX_RAW_CONFIDENCE 2u     /* --raw-confidence: disable the one-exact-match override (raxtax.rs:73-84) */
+
+/* hit-count kernel variants (rtx_ctx_set_option(RTX_OPT_HITCOUNT_VARIANT)) */
+#define RTX_HITCOUNT_BITROWS 0 /* bit-row positional popcount (default) */
+#define RTX_HITCOUNT_CSR 1     /* CSR postings + shared-memory counters (the reference's data structure) */
+
+typedef enum {
+    RTX_OPT_HITCOUNT_VARIANT = 1,
+    RTX_OPT_SUB_BATCH = 2,      /* queries per device sub-batch (0 = auto) */
+    RTX_OPT_KEEP_CSR = 3,       /* keep the CSR postings resident after building bit rows (needed for variant CSR) */
+    RTX_OPT_PROFILE = 4         /* record a CUDA event pair around every kernel launch (rtx_profile_get) */
+} rtx_option;
+
+/* ---- context ------------------------------------------------------------------------------------------- */
+int rtx_abi_version(void);
+int rtx_ctx_create(int device_ordinal, rtx_ctx** out);
+void rtx_ctx_destroy(rtx_ctx* ctx);
+const char* rtx_last_error(const rtx_ctx* ctx); /* ctx may be NULL: error of the last failed rtx_ctx_create */
+int rtx_ctx_set_option(rtx_ctx* ctx, int option, int64_t value);
+/* the CUDA stream (cudaStream_t) all of this context's work is issued on; lets a caller record its own events */
+void* rtx_ctx_stream(rtx_ctx* ctx);
+int rtx_ctx_synchronize(rtx_ctx* ctx);
+
+/* ---- reference index ("Tree", src/tree.rs:36-43) --------------------------------------------------------
+ * Flattened form of what Tree::new (tree.rs:47-140) builds:
+ *  - reference ids are positions in the lineage-sorted order (tree.rs:53-54), n_refs = Tree.num_tips;
+ *  - k_mer_map (tree.rs:41,134-137) as CSR: csr_offsets[65537], csr_ids ascending and unique per list;
+ *  - the Node tree (tree.rs:189-194) without its childless Sequence leaves (they never influence
+ *    Lineage::evaluate, lineage.rs:119-179, because their parent is never Inner), numbered so that the children of node i are the consecutive
+ *    nodes child_first[i] .. child_first[i]+child_count[i]-1 in the reference's child order; node 0 = root;
+ *    node_lo/node_hi = confidence_range (global reference ids);
+ *  - ref_levels[r] = number of comma-separated ranks of lineages[r] (used by the override, raxtax.rs:79).
+ * Reference sharding: this context holds the postings of references [ref_shard_begin, ref_shard_end) only;
+ * csr_ids outside that range are ignored.  The node tree and ref_levels are always the full ones.
+ */
+typedef struct {
+    uint64_t n_refs;
+    const uint64_t* csr_offsets;
+    const uint32_t* csr_ids;
+    uint32_t n_nodes;
+    const uint32_t* node_lo;
+    const uint32_t* node_hi;
+    const uint8_t* node_type; /* 0 = Inner, 1 = Taxon, 2 = Sequence node that has children (degenerate lineages only) (tree.rs:181-186) */
+    const uint32_t* child_first;
+    const uint32_t* child_count;
+    const uint8_t* ref_levels;
+    uint64_t ref_shard_begin;
+    uint64_t ref_shard_end; /* 0 = n_refs */
+} rtx_index_desc;
+
+int rtx_index_upload(rtx_ctx* ctx, const rtx_index_desc* desc);
+/* sizes a caller needs to allocate tap buffers */
+uint64_t rtx_index_n_refs(const rtx_ctx* ctx);       /* global N */
+uint64_t rtx_index_shard_refs(const rtx_ctx* ctx);   /* references held by this context */
+uint32_t rtx_index_max_levels(const rtx_ctx* ctx);   /* stride of rtx_results.confidence */
+uint64_t rtx_index_device_bytes(const rtx_ctx* ctx); /* HBM held by the index */
+
+/* ---- query batch (src/raxtax.rs:14-22: `queries: &[(String, Vec<u8>)]` minus the labels) ----------------
+ * seq_codes are the 4-bit one-hot codes of parser.rs:11-34.  exact_ids[exact_offsets[q]..exact_offsets[q+1])
+ * is `tree.sequences.get(query_sequence)` (raxtax.rs:42) looked up by the host; exact_offsets may be NULL
+ * when no query has an exact match.
+ */
+typedef struct {
+    uint32_t n_queries;
+    const uint64_t* seq_offsets; /* [n_queries + 1] */
+    const uint8_t* seq_codes;
+    const uint32_t* exact_offsets; /* [n_queries + 1] or NULL */
+    const uint32_t* exact_ids;
+    uint32_t flags;
+} rtx_batch;
+
+/* ---- results (`Vec<EvaluationResult>` per query, src/lineage.rs:7-14, in the reference's order) ----------
+ * Results of query q are entries [result_begin[q], result_begin[q+1]) of the per-result arrays.
+ * confidence has row stride rtx_index_max_levels(); values are already rounded to 0.01 (lineage.rs:129)
+ * or 1.0 for the override.  Tap buffers are optional (NULL = skip) and exist for parity tests:
+ *   tap_counts[q * shard_refs + r]  = intersect_buffer after the skip-zeroing (raxtax.rs:58-68), u16
+ *   tap_hist[q * tap_hist_stride + m] = number of references with count m (prob.rs:13-19), this shard only
+ *   tap_kmers[q * tap_kmer_stride + i] = sorted unique 8-mers (utils.rs:27-40)
+ */
+typedef struct {
+    uint16_t* n_kmers;       /* [n_queries] */
+    uint32_t* result_begin;  /* [n_queries + 1] */
+    double* global_signal;   /* [n_queries] */
+    uint64_t result_capacity;
+    uint32_t* first_ref;     /* [result_capacity] index into Tree.lineages */
+    uint8_t* n_levels;       /* [result_capacity] */
+    double* confidence;      /* [result_capacity * max_levels] */
+    double* local_signal;    /* [result_capacity] */
+    uint64_t n_results;      /* out: total results written (if > result_capacity nothing past capacity is written
+                                and the call returns RTX_ERR_INVALID with the needed size here) */
+    uint16_t* tap_counts;
+    uint32_t* tap_hist;
+    uint64_t tap_hist_stride;
+    uint16_t* tap_kmers;
+    uint64_t tap_kmer_stride;
+} rtx_results;
+
+/* One call = H2D of the batch, all kernels, D2H of the results (the end-to-end path). */
+int rtx_classify_batch(rtx_ctx* ctx, const rtx_batch* batch, rtx_results* results);
+
+/* The same path split so that a caller can keep a batch resident in HBM and time the device part alone:
+ * upload (H2D) -> run (kernels only, asynchronous on rtx_ctx_stream) -> download (D2H + host-side ordering). */
+int rtx_batch_upload(rtx_ctx* ctx, const rtx_batch* batch);
+int rtx_batch_run(rtx_ctx* ctx);
+int rtx_batch_download(rtx_ctx* ctx, rtx_results* results);
+
+/* ---- reference-sharded mode (north_star: NCCL all-reduce of the per-query count histograms) -------------
+ * rtx_batch_run == rtx_shard_phase1 ; [all-reduce hist] ; rtx_shard_phase2 ; [all-reduce partial] ; rtx_shard_phase3.
+ * The buffers are device pointers owned by the library, valid until the next rtx_batch_upload:
+ *   hist:    uint32 [n_queries * hist_stride]          summed over ranks -> global histograms
+ *   partial: double [n_queries * partial_stride]       summed over ranks -> per-shard probability mass
+ */
+int rtx_shard_phase1(rtx_ctx* ctx);
+int rtx_shard_hist_buffer(rtx_ctx* ctx, void** dev_ptr, uint64_t* n_elems);
+int rtx_shard_phase2(rtx_ctx* ctx);
+int rtx_shard_partial_buffer(rtx_ctx* ctx, void** dev_ptr, uint64_t* n_elems);
+int rtx_shard_phase3(rtx_ctx* ctx);
+
+/* ---- measurement ---------------------------------------------------------------------------------------- */
+typedef struct {
+    uint64_t launches;   /* kernel launches since the last reset */
+    double total_ms;     /* sum of CUDA-event durations (only with RTX_OPT_PROFILE) */
+} rtx_kernel_stat;
+
+enum { RTX_K_KMERS = 0, RTX_K_HITCOUNT = 1, RTX_K_FIXUP = 2, RTX_K_PROB = 3, RTX_K_INDEX = 4, RTX_K_COUNT = 5 };
+
+typedef struct {
+    rtx_kernel_stat kernel[RTX_K_COUNT];
+    uint64_t queries;          /* queries run since the last reset */
+    uint64_t hits;             /* sum over queries of sum_r count[r] = postings a CSR walk would touch */
+    uint64_t bitrow_bytes;     /* bytes of bit rows + count vectors the hit-count launches had to move */
+    uint64_t csr_equiv_bytes;  /* 4*hits + 2*N per query: the reference data structure's traffic */
+    uint64_t h2d_bytes, d2h_bytes;
+} rtx_profile;
+
+int rtx_profile_reset(rtx_ctx* ctx);
+int rtx_profile_get(rtx_ctx* ctx, rtx_profile* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RAXTAX_B200_H */

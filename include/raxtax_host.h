@@ -1,0 +1,77 @@
+/* raxtax_host.h -- C ABI of the C++ host library (libraxtax_host.so) that sits above include/raxtax_b200.h.
+ *
+ * The reference's host is Rust; no Rust toolchain exists in the build image, so the host side of the hot path
+ * is C++17 with the same names, argument meaning and error behaviour as the reference:
+ *   rxh_tree_from_fasta   = parser::parse_reference_fasta_str   (src/parser.rs:46-105) -> Tree::new (src/tree.rs:47-140)
+ *   rxh_tree_new          = Tree::new                            (src/tree.rs:47-140)
+ *   rxh_queries_from_fasta= parser::parse_query_fasta_str        (src/parser.rs:117-154)
+ *   rxh_raxtax            = raxtax::raxtax                       (src/raxtax.rs:14-97)
+ *   rxh_sender            = crossbeam Sender<(String,String,Option<String>)> (src/raxtax.rs:20, src/main.rs:126-134)
+ * Functions returning int give 0 on success, negative on failure with the message in rxh_last_error();
+ * constructors return NULL on failure.  Errors the reference reports with bail!/panic! surface as failures
+ * with the same message text where one exists.
+ */
+#ifndef RAXTAX_HOST_H
+#define RAXTAX_HOST_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#include "raxtax_b200.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct rxh_tree rxh_tree;       /* raxtax::tree::Tree */
+typedef struct rxh_queries rxh_queries; /* Vec<(String, Vec<u8>)> */
+
+const char* rxh_last_error(void);
+
+/* ---- Tree ------------------------------------------------------------------------------------------------ */
+rxh_tree* rxh_tree_from_fasta(const char* text, size_t len);
+/* lineages: n strings joined by '\n'; sequences: 4-bit codes (parser.rs:11-34) with offsets[n+1] */
+rxh_tree* rxh_tree_new(size_t n, const char* lineage_blob, size_t blob_len, const uint64_t* seq_offsets, const uint8_t* seq_codes);
+void rxh_tree_free(rxh_tree* t);
+size_t rxh_tree_num_tips(const rxh_tree* t);
+const char* rxh_tree_lineage(const rxh_tree* t, size_t i); /* Tree.lineages[i] (sorted order) */
+/* Tree.k_mer_map as CSR (pointers stay valid for the life of the tree) */
+void rxh_tree_csr(const rxh_tree* t, const uint64_t** offsets, const uint32_t** ids);
+/* Tree.sequences.get(seq): number of matches; up to cap ascending ids are written */
+size_t rxh_tree_exact(const rxh_tree* t, const uint8_t* seq, size_t len, uint32_t* out, size_t cap);
+/* flattened Inner/Taxon node arrays + everything rtx_index_upload needs; pointers owned by the tree */
+int rxh_tree_index_desc(const rxh_tree* t, rtx_index_desc* out);
+/* convenience: rtx_index_upload(ctx, desc of t) restricted to references [shard_begin, shard_end) (0,0 = all) */
+int rxh_tree_upload(const rxh_tree* t, rtx_ctx* ctx, uint64_t shard_begin, uint64_t shard_end);
+
+/* ---- queries ----------------------------------------------------------------------------------------------- */
+rxh_queries* rxh_queries_from_fasta(const char* text, size_t len);
+rxh_queries* rxh_queries_new(size_t n, const char* label_blob, size_t blob_len, const uint64_t* seq_offsets, const uint8_t* seq_codes);
+void rxh_queries_free(rxh_queries* q);
+size_t rxh_queries_len(const rxh_queries* q);
+const char* rxh_queries_label(const rxh_queries* q, size_t i);
+void rxh_queries_arrays(const rxh_queries* q, const uint64_t** seq_offsets, const uint8_t** seq_codes);
+
+/* ---- driver ------------------------------------------------------------------------------------------------
+ * sender(user, query_label, primary_results, tsv_results_or_NULL) is called once per query, in query order,
+ * from the calling thread; a non-zero return aborts the run like a failed channel send (raxtax.rs:87).
+ * logger(user, level, message) receives the Info / Warn lines the reference writes to raxtax.log
+ * (raxtax.rs:46-52): level 2 = Warn, 3 = Info.  chunk_size = queries per device batch (0 = all at once).
+ * Returns 0, or -1 on error; *warnings (may be NULL) is set when exact matches disagreed above the leaf level
+ * (raxtax.rs:49-52, 93-95).
+ */
+typedef int (*rxh_sender)(void* user, const char* query_label, const char* primary_results, const char* tsv_results);
+typedef void (*rxh_logger)(void* user, int level, const char* message);
+
+int rxh_raxtax(rtx_ctx* ctx, const rxh_queries* queries, const rxh_tree* tree, int skip_exact_matches, int raw_confidence,
+               size_t chunk_size, rxh_sender sender, void* sender_user, int tsv, rxh_logger logger, void* logger_user, int* warnings);
+
+/* exact-match lookup for a whole batch (the host half of raxtax.rs:42): fills exact_offsets[n+1]; returns the
+ * total number of ids; writes at most cap ids */
+uint64_t rxh_exact_batch(const rxh_tree* t, size_t n, const uint64_t* seq_offsets, const uint8_t* seq_codes, uint32_t* exact_offsets,
+                         uint32_t* exact_ids, uint64_t cap);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RAXTAX_HOST_H */

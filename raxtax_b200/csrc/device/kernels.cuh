@@ -1,0 +1,894 @@
+// kernels.cuh -- hand-written sm_100a kernels of the raxtax query-classification path.
+//
+//   K0 build_bitrows_kernel    CSR postings (Tree.k_mer_map, tree.rs:41,134-137) -> bit rows in HBM
+//   K1 kmers_kernel            2-bit packing + unique sorted 8-mers per query (utils.rs:17-40)
+//   K2 hitcount_bitrows_kernel per-query hit counts (raxtax.rs:58-64) by positional popcount over bit rows,
+//                              fused count histogram (prob.rs:13-19)
+//   K2' fixup_exact_kernel     --skip-exact-matches zeroing (raxtax.rs:65-68) applied to counts + histogram
+//   K3-5 prob_lineage_kernel   highest-hit probabilities (prob.rs:20-102), prefix sums at node boundaries
+//                              (lineage.rs:61-77,114-117), tree walk with the 0.01 cutoff / fallback
+//                              (lineage.rs:119-179), signals and ordering (lineage.rs:86-111), override
+//                              (raxtax.rs:73-84)
+#pragma once
+
+#include <math_constants.h>
+
+#include "common.cuh"
+
+namespace rtx {
+
+// =========================================================================================================
+// small helpers
+// =========================================================================================================
+__device__ __forceinline__ uint4 ldg_stream(const uint4* p) {
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                 : "l"(p));
+    return r;
+}
+__device__ __forceinline__ uint2 ldg_stream(const uint2* p) {
+    uint2 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
+    return r;
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFullMask, v, o);
+    return v;
+}
+
+// inclusive warp scan
+__device__ __forceinline__ double warp_scan_incl(double v, int lane) {
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        double y = __shfl_up_sync(kFullMask, v, o);
+        if (lane >= o) v += y;
+    }
+    return v;
+}
+__device__ __forceinline__ u32 warp_scan_incl(u32 v, int lane) {
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        u32 y = __shfl_up_sync(kFullMask, v, o);
+        if (lane >= o) v += y;
+    }
+    return v;
+}
+
+// Deterministic block-wide sum, result broadcast to every thread.  red must hold >= 33 doubles.
+__device__ __forceinline__ double block_sum(double v, double* red, int tid, int nwarps) {
+    int lane = tid & 31, warp = tid >> 5;
+    v = warp_sum(v);
+    __syncthreads();
+    if (lane == 0) red[warp] = v;
+    __syncthreads();
+    if (warp == 0) {
+        double s = 0.0;
+        if (lane == 0) {
+            for (int w = 0; w < nwarps; ++w) s += red[w];
+            red[32] = s;
+        }
+    }
+    __syncthreads();
+    return red[32];
+}
+
+// Block-wide exclusive scan of one u32 per thread; returns the exclusive prefix, *total gets the block sum.
+__device__ __forceinline__ u32 block_scan_excl(u32 v, u32* wsum, int tid, int nwarps, u32* total) {
+    int lane = tid & 31, warp = tid >> 5;
+    u32 inc = warp_scan_incl(v, lane);
+    __syncthreads();
+    if (lane == 31) wsum[warp] = inc;
+    __syncthreads();
+    u32 base = 0, tot = 0;
+    for (int w = 0; w < nwarps; ++w) {
+        u32 x = wsum[w];
+        if (w < warp) base += x;
+        tot += x;
+    }
+    *total = tot;
+    return base + inc - v;
+}
+
+// =========================================================================================================
+// K0: CSR -> bit rows.  One thread per posting (grid-stride); the k-mer of posting p is found by binary
+// search in csr_off.  Row 0 stays all-zero (the padding row).
+// =========================================================================================================
+__global__ void __launch_bounds__(256) build_bitrows_kernel(const u64* __restrict__ csr_off, const u32* __restrict__ csr_ids,
+                                                            u64 nnz, const u32* __restrict__ rowmap, u32* __restrict__ bitrows,
+                                                            u32 row_words, u64 s0, u64 s1) {
+    for (u64 p = (u64)blockIdx.x * blockDim.x + threadIdx.x; p < nnz; p += (u64)gridDim.x * blockDim.x) {
+        u32 id = csr_ids[p];
+        if (id < s0 || id >= s1) continue;
+        u32 lo = 0, hi = 65536;  // largest k with csr_off[k] <= p
+        while (hi - lo > 1) {
+            u32 mid = (lo + hi) >> 1;
+            if (csr_off[mid] <= p) lo = mid;
+            else hi = mid;
+        }
+        u32 row = rowmap[lo];
+        u32 local = (u32)(id - s0);
+        atomicOr(&bitrows[(size_t)row * row_words + (local >> 5)], 1u << (local & 31));
+    }
+}
+
+// =========================================================================================================
+// K1: one CTA (128 threads) per query.  A 65 536-bit bitmap in shared memory is both the dedup set and the
+// sort: scanning it in word order emits the unique k-mers ascending (utils.rs:39).
+// =========================================================================================================
+constexpr int kKmerThreads = 128;
+
+__global__ void __launch_bounds__(kKmerThreads) kmers_kernel(IndexView ix, BatchView b) {
+    __shared__ u32 bitmap[2048];
+    __shared__ u32 wsum[kKmerThreads / 32];
+    const int q = blockIdx.x, tid = threadIdx.x;
+    const u64 base = b.seq_off[q];
+    const u32 L = (u32)(b.seq_off[q + 1] - base);
+    for (int i = tid; i < 2048; i += kKmerThreads) bitmap[i] = 0;
+    __syncthreads();
+    if (L >= 8) {
+        for (u32 i = tid; i + 8 <= L; i += kKmerThreads) {  // sequence.windows(8)
+            u32 k = 0;
+            bool ok = true;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                u32 c = b.codes[base + i + j];
+                ok &= (c == 1u) | (c == 2u) | (c == 4u) | (c == 8u);  // map_four_to_two_bit_repr -> Some
+                k |= ((u32)(__ffs(c) - 1) & 3u) << (14 - 2 * j);      // first base in bits 15..14
+            }
+            if (ok) atomicOr(&bitmap[k >> 5], 1u << (k & 31));
+        }
+    }
+    __syncthreads();
+    // ordered compaction; thread t owns bitmap words [16t, 16t+16)
+    u32 cnt = 0, cnt_present = 0;
+#pragma unroll
+    for (int w = 0; w < 16; ++w) {
+        u32 x = bitmap[tid * 16 + w];
+        cnt += __popc(x);
+        cnt_present += __popc(x & ix.present[tid * 16 + w]);
+    }
+    u32 total, total_present;
+    u32 pos = block_scan_excl(cnt, wsum, tid, kKmerThreads / 32, &total);
+    u32 pos2 = block_scan_excl(cnt_present, wsum, tid, kKmerThreads / 32, &total_present);
+    u16* kout = b.kmers + (size_t)q * b.kstride;
+    u32* rout = b.rows + (size_t)q * b.kstride;
+    for (int w = 0; w < 16; ++w) {
+        u32 x = bitmap[tid * 16 + w];
+        while (x) {
+            u32 bit = __ffs(x) - 1;
+            x &= x - 1;
+            u32 kmer = (u32)(tid * 16 + w) * 32 + bit;
+            kout[pos++] = (u16)kmer;
+            u32 r = ix.rowmap[kmer];
+            if (r) rout[pos2++] = r;
+        }
+    }
+    u32 padded = (total_present + 15u) & ~15u;
+    if (tid < 16 && total_present + tid < padded) rout[total_present + tid] = 0;  // zero row
+    if (tid == 0) {
+        b.K[q] = (u16)total;
+        b.nrows[q] = padded;
+    }
+}
+
+// =========================================================================================================
+// K2: hit counting by positional popcount.
+//
+// count[r] = |kmers(q) ∩ kmers(ref r)| = column sum over the query's bit rows.  Each lane owns V consecutive
+// 32-bit words of the row (32·V references) and keeps the column sums bit-sliced: plane p of a word holds bit p
+// of the 32 counters.  16 rows are folded per step with a carry-save adder tree (15 full adders = 30 LOP3)
+// whose single weight-16 carry ripples into the high planes.  The epilogue transposes the planes into 32 u16
+// counters with a 16x16 bit-matrix transpose done on both half-words at once, stores them and feeds the
+// shared-memory histogram.
+// =========================================================================================================
+constexpr int kHitThreads = 256;
+constexpr int kHitWarps = kHitThreads / 32;
+constexpr int kRowListCap = 4096;  // row ids staged in shared memory per chunk
+
+__device__ __forceinline__ void csa(u32& s, u32& c, u32 a, u32 b, u32 d) {
+    u32 x = a ^ b;
+    c = (a & b) | (x & d);
+    s = x ^ d;
+}
+
+template <int NP>
+__device__ __forceinline__ void add16(u32 (&pl)[NP], const u32 (&x)[16]) {
+    u32 a[8], b4[4], d2[2], e;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) csa(pl[0], a[i], pl[0], x[2 * i], x[2 * i + 1]);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) csa(pl[1], b4[i], pl[1], a[2 * i], a[2 * i + 1]);
+#pragma unroll
+    for (int i = 0; i < 2; ++i) csa(pl[2], d2[i], pl[2], b4[2 * i], b4[2 * i + 1]);
+    csa(pl[3], e, pl[3], d2[0], d2[1]);
+#pragma unroll
+    for (int p = 4; p < NP; ++p) {
+        u32 t = pl[p] & e;
+        pl[p] ^= e;
+        e = t;
+    }
+}
+
+// planes -> 32 u16 counters packed as 16 words: out[i] = count[2i] | count[2i+1] << 16
+template <int NP>
+__device__ __forceinline__ void planes_to_counts(const u32 (&pl)[NP], u32 (&out)[16]) {
+    u32 A[16];
+#pragma unroll
+    for (int p = 0; p < 16; ++p) A[p] = (p < NP) ? pl[p] : 0u;
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
+        const int j = 8 >> s;
+        const u32 m = (s == 0) ? 0x00FF00FFu : (s == 1) ? 0x0F0F0F0Fu : (s == 2) ? 0x33333333u : 0x55555555u;
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            if (k & j) continue;
+            u32 t = ((A[k] >> j) ^ A[k + j]) & m;
+            A[k + j] ^= t;
+            A[k] ^= t << j;
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        out[i] = __byte_perm(A[2 * i], A[2 * i + 1], 0x5410);      // references 2i, 2i+1
+        out[8 + i] = __byte_perm(A[2 * i], A[2 * i + 1], 0x7632);  // references 16+2i, 16+2i+1
+    }
+}
+
+template <int V>
+struct RowVec;
+template <>
+struct RowVec<2> {
+    typedef uint2 T;
+};
+template <>
+struct RowVec<4> {
+    typedef uint4 T;
+};
+__device__ __forceinline__ u32 vec_get(const uint2& v, int i) { return i == 0 ? v.x : v.y; }
+__device__ __forceinline__ u32 vec_get(const uint4& v, int i) { return i == 0 ? v.x : i == 1 ? v.y : i == 2 ? v.z : v.w; }
+
+// grid: x = query within the sub-batch, y = tile group.  block: kHitThreads.
+// dynamic shared memory: u32 srow[kRowListCap] + u32 shist[hstride]
+template <int V, int NP>
+__global__ void __launch_bounds__(kHitThreads)
+    hitcount_bitrows_kernel(IndexView ix, BatchView b, u16* __restrict__ counts, int q_base, int tiles_per_cta, int n_tiles) {
+    extern __shared__ __align__(16) u32 hsm[];
+    u32* srow = hsm;
+    u32* shist = hsm + kRowListCap;
+    typedef typename RowVec<V>::T vec_t;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int ql = blockIdx.x;
+    const int q = q_base + ql;
+    const u32 n = b.nrows[q];
+    const u32* __restrict__ qrows = b.rows + (size_t)q * b.kstride;
+    const int tile_begin = blockIdx.y * tiles_per_cta;
+    const int tile_end = min(n_tiles, tile_begin + tiles_per_cta);
+    const int rounds = (tile_end - tile_begin + kHitWarps - 1) / kHitWarps;
+    const u32 nbins = (u32)b.K[q] + 1u;
+
+    for (u32 i = tid; i < nbins; i += kHitThreads) shist[i] = 0;
+    const bool single = n <= (u32)kRowListCap;
+    if (single) {
+        for (u32 i = tid; i < n; i += kHitThreads) srow[i] = qrows[i];
+    }
+    __syncthreads();
+
+    u16* __restrict__ qcounts = counts + (size_t)ql * ix.n_pad;
+    for (int r = 0; r < rounds; ++r) {
+        const int tile = tile_begin + r * kHitWarps + warp;
+        const bool active = tile < tile_end;
+        const u32 word0 = (u32)tile * (32 * V) + lane * V;  // first word of this lane
+        u32 pl[V][NP];
+#pragma unroll
+        for (int v = 0; v < V; ++v)
+#pragma unroll
+            for (int p = 0; p < NP; ++p) pl[v][p] = 0;
+
+        for (u32 c0 = 0; c0 < n; c0 += kRowListCap) {
+            const u32 cn = min((u32)kRowListCap, n - c0);
+            if (!single) {
+                __syncthreads();
+                for (u32 i = tid; i < cn; i += kHitThreads) srow[i] = qrows[c0 + i];
+                __syncthreads();
+            }
+            if (active) {
+                const u32* __restrict__ colbase = ix.bitrows + word0;
+                for (u32 j = 0; j < cn; j += 16) {
+                    vec_t x[16];
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        const u32 rid = srow[j + i];
+                        x[i] = ldg_stream(reinterpret_cast<const vec_t*>(colbase + (size_t)rid * ix.row_words));
+                    }
+#pragma unroll
+                    for (int v = 0; v < V; ++v) {
+                        u32 xv[16];
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) xv[i] = vec_get(x[i], v);
+                        add16<NP>(pl[v], xv);
+                    }
+                }
+            }
+        }
+        if (active) {
+#pragma unroll
+            for (int v = 0; v < V; ++v) {
+                u32 out[16];
+                planes_to_counts<NP>(pl[v], out);
+                const u64 ref0 = (u64)(word0 + v) * 32;
+                uint4* dst = reinterpret_cast<uint4*>(qcounts + ref0);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) dst[i] = make_uint4(out[4 * i], out[4 * i + 1], out[4 * i + 2], out[4 * i + 3]);
+                if (ref0 + 32 <= ix.shard_refs) {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        atomicAdd(&shist[out[i] & 0xFFFFu], 1u);
+                        atomicAdd(&shist[out[i] >> 16], 1u);
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        if (ref0 + 2 * i < ix.shard_refs) atomicAdd(&shist[out[i] & 0xFFFFu], 1u);
+                        if (ref0 + 2 * i + 1 < ix.shard_refs) atomicAdd(&shist[out[i] >> 16], 1u);
+                    }
+                }
+            }
+        }
+    }
+    __syncthreads();
+    u32* __restrict__ ghist = b.hist + (size_t)q * b.hstride;
+    for (u32 i = tid; i < nbins; i += kHitThreads) {
+        u32 h = shist[i];
+        if (h) atomicAdd(&ghist[i], h);
+    }
+}
+
+// =========================================================================================================
+// K2 (variant): the reference's own data structure -- CSR postings with u32 ids (tree.rs:22,41) walked per
+// query k-mer, counters in shared memory.  One CTA per (query, reference tile of kCsrTileRefs references);
+// u16 counters are packed two per 32-bit word so that neighbouring ids hit neighbouring banks.
+// =========================================================================================================
+constexpr int kCsrThreads = 256;
+constexpr int kCsrTileRefs = 65536;  // 128 KB of packed u16 counters
+
+__global__ void __launch_bounds__(kCsrThreads)
+    hitcount_csr_kernel(IndexView ix, BatchView b, u16* __restrict__ counts, int q_base) {
+    extern __shared__ __align__(16) u32 csm[];
+    u32* cnt = csm;                          // [kCsrTileRefs / 2]
+    u32* shist = csm + kCsrTileRefs / 2;     // [hstride]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int ql = blockIdx.x, q = q_base + ql;
+    const u64 tile0 = ix.shard_begin + (u64)blockIdx.y * kCsrTileRefs;  // global id range of this tile
+    const u64 tile1 = min(ix.shard_begin + ix.shard_refs, tile0 + kCsrTileRefs);
+    const u32 K = b.K[q];
+    const u32 nbins = K + 1u;
+    for (u32 i = tid; i < kCsrTileRefs / 2; i += kCsrThreads) cnt[i] = 0;
+    for (u32 i = tid; i < nbins; i += kCsrThreads) shist[i] = 0;
+    __syncthreads();
+    const u16* __restrict__ kmers = b.kmers + (size_t)q * b.kstride;
+    // one warp per posting list; the sub-range falling into the tile is found by binary search (lists ascend)
+    for (u32 ki = warp; ki < K; ki += kCsrThreads / 32) {
+        const u32 kmer = kmers[ki];
+        u64 o0 = ix.csr_off[kmer], o1 = ix.csr_off[kmer + 1];
+        u64 lo = o0, hi = o1;  // first posting >= tile0
+        while (lo < hi) {
+            u64 mid = (lo + hi) >> 1;
+            if (ix.csr_ids[mid] < tile0) lo = mid + 1;
+            else hi = mid;
+        }
+        const u64 a = lo;
+        hi = o1;  // first posting >= tile1
+        while (lo < hi) {
+            u64 mid = (lo + hi) >> 1;
+            if (ix.csr_ids[mid] < tile1) lo = mid + 1;
+            else hi = mid;
+        }
+        const u64 e = lo;
+        for (u64 p = a + lane; p < e; p += 32) {
+            u32 local = (u32)(ix.csr_ids[p] - tile0);
+            atomicAdd(&cnt[local >> 1], (local & 1u) ? 0x10000u : 1u);
+        }
+    }
+    __syncthreads();
+    u16* __restrict__ qcounts = counts + (size_t)ql * ix.n_pad + (tile0 - ix.shard_begin);
+    const u32 nref = (u32)(tile1 - tile0);
+    u32* qc32 = reinterpret_cast<u32*>(qcounts);
+    for (u32 i = tid; i < (nref + 1) / 2; i += kCsrThreads) {
+        u32 w = cnt[i];
+        qc32[i] = w;
+        atomicAdd(&shist[w & 0xFFFFu], 1u);
+        if (2 * i + 1 < nref) atomicAdd(&shist[w >> 16], 1u);
+    }
+    __syncthreads();
+    u32* __restrict__ ghist = b.hist + (size_t)q * b.hstride;
+    for (u32 i = tid; i < nbins; i += kCsrThreads) {
+        u32 h = shist[i];
+        if (h) atomicAdd(&ghist[i], h);
+    }
+}
+
+// =========================================================================================================
+// K2': --skip-exact-matches (raxtax.rs:65-68): counter of every exact match := 0, histogram adjusted.
+// One thread per query of the sub-batch.
+// =========================================================================================================
+__global__ void fixup_exact_kernel(IndexView ix, BatchView b, u16* __restrict__ counts, int q_base, int q_count) {
+    int ql = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ql >= q_count || b.exact_off == nullptr) return;
+    int q = q_base + ql;
+    u32* hist = b.hist + (size_t)q * b.hstride;
+    for (u32 e = b.exact_off[q]; e < b.exact_off[q + 1]; ++e) {
+        u64 id = b.exact_ids[e];
+        if (id < ix.shard_begin || id >= ix.shard_begin + ix.shard_refs) continue;
+        u16* c = counts + (size_t)ql * ix.n_pad + (id - ix.shard_begin);
+        u16 old = *c;
+        if (old != 0) {
+            *c = 0;
+            atomicSub(&hist[old], 1u);
+            atomicAdd(&hist[0], 1u);
+        }
+    }
+}
+
+// =========================================================================================================
+// K3-K5: probabilities, lineage aggregation, selection.  Persistent CTAs (256 threads), one query at a time.
+// =========================================================================================================
+constexpr int kProbThreads = 256;
+constexpr int kProbWarps = kProbThreads / 32;
+
+struct ProbScratch {
+    double* cbuf;        // [slots][cbuf_stride] log-CMFs of the slow branch, row d = distinct count d
+    size_t cbuf_stride;  // = hstride * tstride doubles
+    u32 tstride;         // doubles per cbuf row ( >= max t + 1 )
+    double* preb;        // [slots][preb_stride] prefix sums of normalised probabilities at node boundaries
+    size_t preb_stride;
+    u32* st_first;       // [slots][RTX_MAX_RESULTS_PER_QUERY] staged results (DFS order)
+    u8* st_nlev;
+    double* st_conf;     // [slots][RTX_MAX_RESULTS_PER_QUERY][max_levels]
+    double* st_local;
+};
+
+__device__ __forceinline__ double round_conf(double x) {
+    return round(x * 100.0) / 100.0;  // f64::round = half away from zero (lineage.rs:129)
+}
+
+// dynamic smem carve-up (all sizes depend on H = hstride, T1 = H/2 + 1)
+struct ProbSmem {
+    double* Ptab;   // [H]   P(m) then P(m)/S, direct-indexed by count
+    double* dval;   // [H]   per distinct count: scan carry (pass 1) / P (pass 2)
+    double* g;      // [T1]  ln i! + ln (t-i)!
+    double* prod;   // [T1]  sum_m h[m] * c_m[i]
+    u32* hist;      // [H]
+    u32* dh;        // [H]   multiplicity of distinct count d
+    u16* dm;        // [H]   distinct counts ascending
+    __device__ ProbSmem(unsigned char* base, u32 H, u32 T1) {
+        Ptab = reinterpret_cast<double*>(base);
+        dval = Ptab + H;
+        g = dval + H;
+        prod = g + T1;
+        hist = reinterpret_cast<u32*>(prod + T1);
+        dh = hist + H;
+        dm = reinterpret_cast<u16*>(dh + H);
+    }
+    static size_t bytes(u32 H, u32 T1) { return (size_t)H * (8 + 8 + 4 + 4 + 2) + (size_t)T1 * 16 + 16; }
+};
+
+__global__ void __launch_bounds__(kProbThreads)
+    prob_lineage_kernel(IndexView ix, BatchView b, ResultPool pool, ProbScratch sc, const u16* __restrict__ counts, int q_base,
+                        int q_count, unsigned long long* __restrict__ hits_total) {
+    extern __shared__ __align__(16) unsigned char psm_raw[];
+    __shared__ double red[40];
+    __shared__ double part[kProbWarps][32];
+    __shared__ u32 wsum[kProbWarps];
+    __shared__ double wtot[kProbWarps];
+    __shared__ u32 sh_D;
+    __shared__ double sh_S;
+    // tree-walk state (warp 0)
+    __shared__ u32 st_node[RTX_MAX_LEVELS + 1];
+    __shared__ u32 st_next[RTX_MAX_LEVELS + 1];
+    __shared__ u8 st_any[RTX_MAX_LEVELS + 1];
+    __shared__ double path_conf[RTX_MAX_LEVELS + 1];
+    __shared__ double path_exp[RTX_MAX_LEVELS + 1];
+    __shared__ u16 order[RTX_MAX_RESULTS_PER_QUERY];
+
+    const u32 H = b.hstride;
+    const u32 T1 = H / 2 + 1;
+    ProbSmem sm(psm_raw, H, T1);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const double* __restrict__ lf = ix.lnfact;
+    const double NEG_INF = -CUDART_INF;
+    const u32 ML = ix.max_levels;
+    const double Nd = (double)ix.n_refs;
+
+    double* cbuf = sc.cbuf + (size_t)blockIdx.x * sc.cbuf_stride;
+    double* preb = sc.preb + (size_t)blockIdx.x * sc.preb_stride;
+    u32* stg_first = sc.st_first + (size_t)blockIdx.x * RTX_MAX_RESULTS_PER_QUERY;
+    u8* stg_nlev = sc.st_nlev + (size_t)blockIdx.x * RTX_MAX_RESULTS_PER_QUERY;
+    double* stg_conf = sc.st_conf + (size_t)blockIdx.x * RTX_MAX_RESULTS_PER_QUERY * ML;
+    double* stg_local = sc.st_local + (size_t)blockIdx.x * RTX_MAX_RESULTS_PER_QUERY;
+
+    for (int ql = blockIdx.x; ql < q_count; ql += gridDim.x) {
+        const int q = q_base + ql;
+        const u32 K = b.K[q];
+        const u32 t = K / 2;  // raxtax.rs:57
+        const u32* __restrict__ ghist = b.hist + (size_t)q * H;
+        const u16* __restrict__ qcounts = counts + (size_t)ql * ix.n_pad;
+        __syncthreads();  // smem reuse across queries
+
+        // ---- histogram -> distinct counts (ascending), prob.rs:13-19 ------------------------------------
+        const u32 per = (K + 1 + kProbThreads - 1) / kProbThreads;
+        const u32 m_lo = min(K + 1, (u32)tid * per), m_hi = min(K + 1, m_lo + per);
+        u32 nz = 0;
+        for (u32 m = m_lo; m < m_hi; ++m) {
+            u32 h = ghist[m];
+            sm.hist[m] = h;
+            nz += (h != 0);
+        }
+        u32 D;
+        u32 dpos = block_scan_excl(nz, wsum, tid, kProbWarps, &D);
+        for (u32 m = m_lo; m < m_hi; ++m) {
+            u32 h = sm.hist[m];
+            if (h) {
+                sm.dm[dpos] = (u16)m;
+                sm.dh[dpos] = h;
+                sm.dval[dpos] = 0.0;
+                ++dpos;
+            }
+            sm.Ptab[m] = 0.0;
+        }
+        __syncthreads();
+        // postings a CSR walk would have touched for this query = sum_r count[r]
+        {
+            unsigned long long hsum = 0;
+            for (u32 d = tid; d < D; d += kProbThreads) hsum += (unsigned long long)sm.dm[d] * sm.dh[d];
+            for (int o = 16; o > 0; o >>= 1) hsum += __shfl_xor_sync(kFullMask, hsum, o);
+            if (lane == 0 && hsum) atomicAdd(hits_total, hsum);
+        }
+
+        // ---- P(m) per distinct count -------------------------------------------------------------------
+        const bool any_full = sm.hist[K] > 0;  // prob.rs:24-26 (K == 0: every count equals K)
+        // T = ln C(K+t-1, t); for K == 0 the reference's u64 arithmetic wraps and yields 0.0, never used then
+        const double T = (K == 0) ? 0.0 : lf[K + t - 1] - lf[t] - lf[K - 1];
+        if (any_full) {  // fast branch, only_last_pmf (prob.rs:105-119)
+            for (u32 d = tid; d < D; d += kProbThreads) {
+                u32 m = sm.dm[d];
+                double P;
+                if (m == K) P = 1.0;
+                else if (m == 0) P = 0.0;
+                else P = exp(lf[m + t - 1] - lf[t] - lf[m - 1] - T);
+                sm.dval[d] = P;
+            }
+        } else {  // slow branch (prob.rs:43-91); here 0 <= m < K for every distinct count
+            for (u32 i = tid; i <= t; i += kProbThreads) sm.g[i] = lf[i] + lf[t - i];
+            __syncthreads();
+            const u32 nchunks = (t + 1 + 31) / 32;
+            double* __restrict__ crow_base = cbuf;
+            // pass 1: log-CMFs c_m[i] and prod[i] = sum_m h[m] c_m[i]
+            for (u32 ch = 0; ch < nchunks; ++ch) {
+                const u32 i = ch * 32 + lane;
+                const bool valid = i <= t;
+                double acc = 0.0;
+                for (u32 d = warp; d < D; d += kProbWarps) {
+                    const u32 m = sm.dm[d];
+                    if (m == 0) continue;  // pmf = [1,0,0,..] => cmf == 1 => ln cmf == 0 for every i
+                    const double cm = lf[m - 1] + lf[K - m - 1] + T;
+                    double e = 0.0;
+                    if (valid) {
+                        // ln pmf_m(i) = ln C(m+i-1,i) + ln C(K-m+t-i-1,t-i) - T   (closed form of prob.rs:136-166)
+                        double p = lf[m + i - 1] + lf[K - m + t - i - 1] - sm.g[i] - cm;
+                        e = exp(p);
+                    }
+                    double s = warp_scan_incl(e, lane) + sm.dval[d];
+                    __syncwarp();
+                    if (lane == 31) sm.dval[d] = s;
+                    double c = log(s);  // s == 0 -> -inf, as the reference's sum.ln()
+                    if (valid) {
+                        crow_base[(size_t)d * sc.tstride + i] = c;
+                        acc += (double)sm.dh[d] * c;
+                    }
+                }
+                part[warp][lane] = acc;
+                __syncthreads();
+                if (warp == 0) {
+                    double s = 0.0;
+#pragma unroll
+                    for (int w = 0; w < kProbWarps; ++w) s += part[w][lane];
+                    if (valid) sm.prod[i] = s;
+                }
+                __syncthreads();
+            }
+            // pass 2: P(m) = sum_i exp(p_m[i] + prod[i] - c_m[i])   (prob.rs:74-90)
+            for (u32 d = warp; d < D; d += kProbWarps) {
+                const u32 m = sm.dm[d];
+                double val;
+                if (m == 0) {
+                    double pr = sm.prod[0];
+                    val = (pr == NEG_INF) ? 0.0 : exp(pr);
+                } else {
+                    const double cm = lf[m - 1] + lf[K - m - 1] + T;
+                    double s = 0.0;
+                    for (u32 i = lane; i <= t; i += 32) {
+                        double p = lf[m + i - 1] + lf[K - m + t - i - 1] - sm.g[i] - cm;
+                        double c = crow_base[(size_t)d * sc.tstride + i];
+                        double pr = sm.prod[i];
+                        s += (c == NEG_INF || pr == NEG_INF) ? 0.0 : exp(p + pr - c);
+                    }
+                    val = warp_sum(s);
+                }
+                if (lane == 0) sm.dval[d] = val;
+            }
+        }
+        __syncthreads();
+        // ---- normalise (prob.rs:97-102) and global signal (lineage.rs:86-90) ---------------------------
+        double sl = 0.0;
+        for (u32 d = tid; d < D; d += kProbThreads) sl += (double)sm.dh[d] * sm.dval[d];
+        const double S = block_sum(sl, red, tid, kProbWarps);
+        const bool bad_sum = !(S > 0.0);  // assert!(probs_sum > 0.0)
+        double gl = 0.0;
+        for (u32 d = tid; d < D; d += kProbThreads) {
+            double pn = sm.dval[d] / S;
+            sm.Ptab[sm.dm[d]] = pn;
+            double df = pn - 1.0 / Nd;
+            gl += (double)sm.dh[d] * (df * df);
+        }
+        const double gsum = block_sum(gl, red, tid, kProbWarps);
+        const double global_signal = sqrt(gsum);
+
+        // ---- prefix sums of the normalised probabilities at node boundaries (lineage.rs:61-77) ---------
+        {
+            double carry = 0.0;
+            const u64 Ns = ix.shard_refs;
+            for (u64 base = 0; base < Ns; base += (u64)kProbThreads * 8) {
+                const u64 r0 = base + (u64)tid * 8;
+                double v[8];
+                if (r0 < Ns) {
+                    uint4 cw = *reinterpret_cast<const uint4*>(qcounts + r0);
+                    u32 w[4] = {cw.x, cw.y, cw.z, cw.w};
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        v[2 * k] = (r0 + 2 * k < Ns) ? sm.Ptab[w[k] & 0xFFFFu] : 0.0;
+                        v[2 * k + 1] = (r0 + 2 * k + 1 < Ns) ? sm.Ptab[w[k] >> 16] : 0.0;
+                    }
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) v[k] = 0.0;
+                }
+#pragma unroll
+                for (int k = 1; k < 8; ++k) v[k] += v[k - 1];
+                double inc = warp_scan_incl(v[7], lane);
+                if (lane == 31) wtot[warp] = inc;
+                __syncthreads();
+                double offs = carry + inc - v[7];
+                double tot = 0.0;
+#pragma unroll
+                for (int w = 0; w < kProbWarps; ++w) {
+                    double x = wtot[w];
+                    if (w < warp) offs += x;
+                    tot += x;
+                }
+                if (r0 < Ns) {
+                    const u32 word = ix.bnd_after[r0 >> 5];
+                    const u32 sh = (u32)(r0 & 31);
+                    u32 byte = (word >> sh) & 0xFFu;
+                    if (byte) {
+                        u32 idx = 1u + ix.bnd_rank[r0 >> 5] + __popc(word & ((1u << sh) - 1u));
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) {
+                            if (byte & (1u << k)) preb[idx++] = offs + v[k];
+                        }
+                    }
+                }
+                carry += tot;
+                __syncthreads();
+            }
+            if (tid == 0) preb[0] = 0.0;
+            __syncthreads();
+        }
+
+        // ---- tree walk (lineage.rs:119-179), warp 0 ----------------------------------------------------
+        if (warp == 0) {
+            u32 n_res = 0;
+            bool overflow = false;
+            int depth = 0;
+            if (lane == 0) {
+                st_node[0] = 0;
+                st_next[0] = 0;
+                st_any[0] = 0;
+            }
+            __syncwarp();
+            while (depth >= 0 && !bad_sum) {
+                const u32 node = st_node[depth];
+                const u32 cf = ix.child_first[node], cc = ix.child_count[node];
+                u32 nxt = st_next[depth];
+                bool found = false;
+                u32 child = 0;
+                double cconf = 0.0;
+                for (u32 cb = nxt; cb < cc; cb += 32) {
+                    const u32 ci = cb + lane;
+                    double rc = 0.0;
+                    if (ci < cc) {
+                        const u32 c = cf + ci;
+                        rc = round_conf(preb[ix.node_bhi[c]] - preb[ix.node_blo[c]]);
+                    }
+                    const u32 mask = __ballot_sync(kFullMask, rc != 0.0);
+                    if (mask) {
+                        const int j = __ffs(mask) - 1;
+                        child = cf + cb + j;
+                        cconf = __shfl_sync(kFullMask, rc, j);
+                        nxt = cb + j + 1;
+                        found = true;
+                        break;
+                    }
+                }
+                if (found) {
+                    if (lane == 0) {
+                        st_next[depth] = nxt;
+                        st_any[depth] = 1;
+                        path_conf[depth] = cconf;
+                        path_exp[depth] = (double)(ix.node_hi[child] - ix.node_lo[child]) / Nd;
+                        st_node[depth + 1] = child;
+                        st_next[depth + 1] = 0;
+                        st_any[depth + 1] = 0;
+                    }
+                    __syncwarp();
+                    ++depth;  // depth <= max_levels by construction of the tree
+                    continue;
+                }
+                // children exhausted
+                if (!st_any[depth]) {
+                    int d = depth;
+                    u32 cur = node;
+                    bool emit = true;
+                    if (ix.node_type[node] == 0) {  // Inner with no significant child: follow the best children
+                        while (ix.node_type[cur] == 0) {
+                            const u32 f = ix.child_first[cur], n_c = ix.child_count[cur];
+                            // max_by(partial_cmp): the LAST maximal child wins (lineage.rs:156-164)
+                            double best = -CUDART_INF;
+                            u32 besti = 0;
+                            for (u32 cb = 0; cb < n_c; cb += 32) {
+                                const u32 ci = cb + lane;
+                                double cv = -CUDART_INF;
+                                if (ci < n_c) cv = preb[ix.node_bhi[f + ci]] - preb[ix.node_blo[f + ci]];
+                                if (ci < n_c && cv >= best) {
+                                    best = cv;
+                                    besti = ci;
+                                }
+                            }
+#pragma unroll
+                            for (int o = 16; o > 0; o >>= 1) {
+                                double ob = __shfl_xor_sync(kFullMask, best, o);
+                                u32 oi = __shfl_xor_sync(kFullMask, besti, o);
+                                if (ob > best || (ob == best && oi > besti)) {
+                                    best = ob;
+                                    besti = oi;
+                                }
+                            }
+                            cur = f + besti;
+                            if (lane == 0) {
+                                path_conf[d] = 1.0 / 100.0;
+                                path_exp[d] = (double)(ix.node_hi[cur] - ix.node_lo[cur]) / Nd;
+                            }
+                            ++d;
+                        }
+                    } else if (ix.node_type[node] != 1 || depth == 0) {
+                        emit = false;  // only Taxon nodes are emitted (lineage.rs:143); Sequence-typed pass-through nodes are not
+                    }
+                    __syncwarp();
+                    if (emit) {
+                        if (n_res >= RTX_MAX_RESULTS_PER_QUERY) overflow = true;
+                        else {
+                            // local signal (lineage.rs:95-102, utils.rs:91-105), sequential like the reference
+                            if (lane == 0) {
+                                int start = d - 1;
+                                for (int i = 0; i < d; ++i)
+                                    if (1.0 > path_exp[i]) {
+                                        start = i;
+                                        break;
+                                    }
+                                double a_sum = 0.0, b_sum = 0.0;
+                                for (int i = start; i < d; ++i) a_sum += path_conf[i];
+                                for (int i = start; i < d; ++i) b_sum += path_exp[i];
+                                double s2 = 0.0;
+                                for (int i = start; i < d; ++i) {
+                                    double df = path_conf[i] / a_sum - path_exp[i] / b_sum;
+                                    s2 += df * df;
+                                }
+                                stg_local[n_res] = (d > 0) ? sqrt(s2) : 0.0;
+                                stg_first[n_res] = ix.node_lo[cur];
+                                stg_nlev[n_res] = (u8)d;
+                            }
+                            for (int i = lane; i < d; i += 32) stg_conf[(size_t)n_res * ML + i] = path_conf[i];
+                            ++n_res;
+                        }
+                    }
+                }
+                --depth;
+                __syncwarp();
+            }
+            __syncwarp();
+            // ---- order: stable sort, descending lexicographic on the confidence vectors (lineage.rs:93)
+            int status = kQOk;
+            if (bad_sum) status = kQProbSumZero;
+            else if (overflow) status = kQTooManyResults;
+            else if (n_res == 0) status = kQEmptyResult;  // assert!(!eval_res.is_empty()) raxtax.rs:72
+            if (lane == 0) {
+                for (u32 i = 0; i < n_res; ++i) {
+                    int j = (int)i - 1;
+                    const double* ci = stg_conf + (size_t)i * ML;
+                    const u32 li = stg_nlev[i];
+                    while (j >= 0) {
+                        const u32 oj = order[j];
+                        const double* cj = stg_conf + (size_t)oj * ML;
+                        const u32 lj = stg_nlev[oj];
+                        // does i sort strictly before order[j]?  <=> conf_i > conf_j lexicographically
+                        bool before = false, decided = false;
+                        for (u32 l = 0; l < min(li, lj); ++l) {
+                            if (ci[l] > cj[l]) {
+                                before = true;
+                                decided = true;
+                                break;
+                            }
+                            if (ci[l] < cj[l]) {
+                                decided = true;
+                                break;
+                            }
+                        }
+                        if (!decided) before = li > lj;
+                        if (!before) break;
+                        order[j + 1] = order[j];
+                        --j;
+                    }
+                    order[j + 1] = (u16)i;
+                }
+            }
+            __syncwarp();
+            // ---- override (raxtax.rs:73-84) and emission into the result pool ---------------------------
+            u32 n_out = n_res;
+            bool ovr = false;
+            u32 ovr_idx = 0;
+            if (status == kQOk && !(b.flags & RTX_RAW_CONFIDENCE) && !(b.flags & RTX_SKIP_EXACT_MATCHES) && b.exact_off) {
+                if (b.exact_off[q + 1] - b.exact_off[q] == 1) {
+                    ovr = true;
+                    ovr_idx = b.exact_ids[b.exact_off[q]];
+                    n_out = 1;
+                }
+            }
+            if (status != kQOk) n_out = 0;
+            unsigned long long base = 0;
+            if (lane == 0) base = atomicAdd(pool.used, (unsigned long long)n_out);
+            base = __shfl_sync(kFullMask, base, 0);
+            if (base + n_out > pool.cap) {
+                if (status == kQOk) status = kQPoolOverflow;
+            } else if (ovr) {
+                const u32 nl = ix.ref_levels[ovr_idx];
+                if (lane == 0) {
+                    pool.first_ref[base] = ovr_idx;
+                    pool.n_levels[base] = (u8)nl;
+                    pool.local[base] = stg_local[order[0]];
+                }
+                for (u32 l = lane; l < ML; l += 32) pool.conf[base * ML + l] = (l < nl) ? 1.0 : 0.0;
+            } else {
+                for (u32 i = 0; i < n_out; ++i) {
+                    const u32 src = order[i];
+                    if (lane == 0) {
+                        pool.first_ref[base + i] = stg_first[src];
+                        pool.n_levels[base + i] = stg_nlev[src];
+                        pool.local[base + i] = stg_local[src];
+                    }
+                    const u32 nl = stg_nlev[src];
+                    for (u32 l = lane; l < ML; l += 32) pool.conf[(base + i) * ML + l] = (l < nl) ? stg_conf[(size_t)src * ML + l] : 0.0;
+                }
+            }
+            if (lane == 0) {
+                pool.res_off[q] = (u32)base;
+                pool.res_cnt[q] = n_out;
+                pool.global_sig[q] = global_signal;
+                pool.status[q] = status;
+            }
+        }
+    }
+}
+
+}  // namespace rtx

@@ -1,0 +1,836 @@
+// rtx_api.cu -- C ABI (include/raxtax_b200.h) of the sm_100a query-classification library.
+// Host-side orchestration only: validation, HBM layout, kernel launches, result ordering.  No CPU compute path.
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <mutex>
+
+#include "kernels.cuh"
+
+using namespace rtx;
+
+// ---------------------------------------------------------------------------------------------------------
+struct EventPair {
+    cudaEvent_t a, b;
+    int kernel;
+};
+
+struct rtx_ctx {
+    int device = 0;
+    int n_sms = 148;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    // options
+    int variant = RTX_HITCOUNT_BITROWS;
+    int64_t sub_batch_opt = 0;
+    bool keep_csr = false;
+    bool profile = false;
+    // index
+    bool has_index = false;
+    IndexView ix{};
+    u32 n_rows = 0;
+    u64 index_bytes = 0;
+    DevBuf d_bitrows, d_rowmap, d_present, d_csr_off, d_csr_ids, d_node_lo, d_node_hi, d_node_type, d_child_first, d_child_count,
+        d_node_blo, d_node_bhi, d_bnd_after, d_bnd_rank, d_ref_levels, d_lnfact;
+    // batch
+    bool has_batch = false;
+    bool ran = false;
+    BatchView bv{};
+    u32 max_len = 0;
+    u64 total_codes = 0, total_exact = 0;
+    DevBuf d_seq_off, d_codes, d_exact_off, d_exact_ids, d_K, d_kmers, d_rows, d_nrows, d_hist;
+    DevBuf d_counts;
+    u32 sub_batch = 0;
+    // results
+    ResultPool pool{};
+    DevBuf d_pool_first, d_pool_nlev, d_pool_conf, d_pool_local, d_pool_used, d_res_off, d_res_cnt, d_global, d_status, d_hits;
+    // prob scratch
+    ProbScratch sc{};
+    int prob_slots = 0;
+    size_t prob_smem = 0;
+    DevBuf d_cbuf, d_preb, d_st_first, d_st_nlev, d_st_conf, d_st_local;
+    // host staging
+    std::vector<u32> h_res_off, h_res_cnt, h_nrows, h_pool_first;
+    std::vector<int> h_status;
+    std::vector<u8> h_pool_nlev;
+    std::vector<double> h_pool_conf, h_pool_local;
+    // taps wired by rtx_classify_batch for sub-batched runs
+    u16* tap_counts_host = nullptr;
+    // profile
+    rtx_profile prof{};
+    std::vector<EventPair> events;
+};
+
+static std::string g_create_err;
+static std::mutex g_create_mtx;
+
+static int set_err(rtx_ctx* c, int code, const std::string& msg) {
+    if (c) c->err = msg;
+    else {
+        std::lock_guard<std::mutex> g(g_create_mtx);
+        g_create_err = msg;
+    }
+    return code;
+}
+
+#define CU(call)                                                                                              \
+    do {                                                                                                      \
+        cudaError_t e__ = (call);                                                                             \
+        if (e__ != cudaSuccess)                                                                               \
+            return set_err(ctx, RTX_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__));           \
+    } while (0)
+
+#define REQUIRE(cond, msg)                                                \
+    do {                                                                  \
+        if (!(cond)) return set_err(ctx, RTX_ERR_INVALID, std::string(msg)); \
+    } while (0)
+
+static inline u32 round_up(u32 x, u32 a) { return (x + a - 1) / a * a; }
+
+// ---- launch bookkeeping -------------------------------------------------------------------------------
+struct LaunchTimer {
+    rtx_ctx* c;
+    int k;
+    EventPair ep{};
+    bool on;
+    LaunchTimer(rtx_ctx* ctx, int kernel) : c(ctx), k(kernel), on(ctx->profile) {
+        c->prof.kernel[k].launches += 1;
+        if (on) {
+            cudaEventCreate(&ep.a);
+            cudaEventCreate(&ep.b);
+            ep.kernel = k;
+            cudaEventRecord(ep.a, c->stream);
+        }
+    }
+    ~LaunchTimer() {
+        if (on) {
+            cudaEventRecord(ep.b, c->stream);
+            c->events.push_back(ep);
+        }
+    }
+};
+
+static void drain_events(rtx_ctx* c) {
+    for (auto& ep : c->events) {
+        cudaEventSynchronize(ep.b);
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, ep.a, ep.b) == cudaSuccess) c->prof.kernel[ep.kernel].total_ms += ms;
+        cudaEventDestroy(ep.a);
+        cudaEventDestroy(ep.b);
+    }
+    c->events.clear();
+}
+
+// ---------------------------------------------------------------------------------------------------------
+#define RTX_API extern "C" __attribute__((visibility("default")))
+
+RTX_API int rtx_abi_version(void) { return RTX_ABI_VERSION; }
+
+RTX_API const char* rtx_last_error(const rtx_ctx* ctx) {
+    if (ctx) return ctx->err.c_str();
+    std::lock_guard<std::mutex> g(g_create_mtx);
+    return g_create_err.c_str();
+}
+
+RTX_API int rtx_ctx_create(int device_ordinal, rtx_ctx** out) {
+    rtx_ctx* ctx = nullptr;  // for the macros: errors land in the global slot
+    if (!out) return set_err(nullptr, RTX_ERR_INVALID, "rtx_ctx_create: out is NULL");
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0)
+        return set_err(nullptr, RTX_ERR_NO_DEVICE,
+                       std::string("no CUDA device available (") + (e != cudaSuccess ? cudaGetErrorString(e) : "device count 0") +
+                           "); raxtax_b200 has no CPU fallback");
+    if (device_ordinal < 0 || device_ordinal >= n) return set_err(nullptr, RTX_ERR_INVALID, "device ordinal out of range");
+    CU(cudaSetDevice(device_ordinal));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device_ordinal));
+    if (prop.major < 10)
+        return set_err(nullptr, RTX_ERR_NO_DEVICE, std::string("device ") + prop.name + " is not sm_100-class; this library is built for sm_100a only");
+    rtx_ctx* c = new rtx_ctx();
+    c->device = device_ordinal;
+    c->n_sms = prop.multiProcessorCount;
+    e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) {
+        delete c;
+        return set_err(nullptr, RTX_ERR_CUDA, std::string("cudaStreamCreate: ") + cudaGetErrorString(e));
+    }
+    // ln n! table: exact factorials up to 170, lgamma beyond (the reference's statrs::ln_factorial does the same)
+    const u32 len = 98304 + 8;  // K + t <= 65535 + 32767
+    std::vector<double> lf(len);
+    double f = 1.0;
+    lf[0] = 0.0;
+    for (u32 i = 1; i < len; ++i) {
+        if (i <= 170) {
+            f *= (double)i;
+            lf[i] = std::log(f);
+        } else lf[i] = std::lgamma((double)i + 1.0);
+    }
+    ctx = c;
+    e = c->d_lnfact.ensure(len * sizeof(double));
+    if (e == cudaSuccess) e = cudaMemcpy(c->d_lnfact.p, lf.data(), len * sizeof(double), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+        std::string m = std::string("lnfact upload: ") + cudaGetErrorString(e);
+        rtx_ctx_destroy(c);
+        return set_err(nullptr, RTX_ERR_CUDA, m);
+    }
+    c->ix.lnfact = c->d_lnfact.as<double>();
+    c->ix.lnfact_len = len;
+    *out = c;
+    return RTX_OK;
+}
+
+RTX_API void rtx_ctx_destroy(rtx_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    drain_events(c);
+    DevBuf* bufs[] = {&c->d_bitrows, &c->d_rowmap, &c->d_present, &c->d_csr_off, &c->d_csr_ids, &c->d_node_lo, &c->d_node_hi,
+                      &c->d_node_type, &c->d_child_first, &c->d_child_count, &c->d_node_blo, &c->d_node_bhi, &c->d_bnd_after,
+                      &c->d_bnd_rank, &c->d_ref_levels, &c->d_lnfact, &c->d_seq_off, &c->d_codes, &c->d_exact_off, &c->d_exact_ids,
+                      &c->d_K, &c->d_kmers, &c->d_rows, &c->d_nrows, &c->d_hist, &c->d_counts, &c->d_pool_first, &c->d_pool_nlev,
+                      &c->d_pool_conf, &c->d_pool_local, &c->d_pool_used, &c->d_res_off, &c->d_res_cnt, &c->d_global, &c->d_status,
+                      &c->d_hits, &c->d_cbuf, &c->d_preb, &c->d_st_first, &c->d_st_nlev, &c->d_st_conf, &c->d_st_local};
+    for (DevBuf* b : bufs) b->release();
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+RTX_API int rtx_ctx_set_option(rtx_ctx* ctx, int option, int64_t value) {
+    if (!ctx) return RTX_ERR_INVALID;
+    switch (option) {
+        case RTX_OPT_HITCOUNT_VARIANT:
+            REQUIRE(value == RTX_HITCOUNT_BITROWS || value == RTX_HITCOUNT_CSR, "unknown hit-count variant");
+            ctx->variant = (int)value;
+            return RTX_OK;
+        case RTX_OPT_SUB_BATCH:
+            REQUIRE(value >= 0 && value <= 65535, "sub-batch must be in [0, 65535]");
+            ctx->sub_batch_opt = value;
+            return RTX_OK;
+        case RTX_OPT_KEEP_CSR:
+            ctx->keep_csr = value != 0;
+            return RTX_OK;
+        case RTX_OPT_PROFILE:
+            ctx->profile = value != 0;
+            return RTX_OK;
+        default:
+            return set_err(ctx, RTX_ERR_INVALID, "unknown option");
+    }
+}
+
+RTX_API void* rtx_ctx_stream(rtx_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+
+RTX_API int rtx_ctx_synchronize(rtx_ctx* ctx) {
+    if (!ctx) return RTX_ERR_INVALID;
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return RTX_OK;
+}
+
+RTX_API uint64_t rtx_index_n_refs(const rtx_ctx* c) { return c && c->has_index ? c->ix.n_refs : 0; }
+RTX_API uint64_t rtx_index_shard_refs(const rtx_ctx* c) { return c && c->has_index ? c->ix.shard_refs : 0; }
+RTX_API uint32_t rtx_index_max_levels(const rtx_ctx* c) { return c && c->has_index ? c->ix.max_levels : 0; }
+RTX_API uint64_t rtx_index_device_bytes(const rtx_ctx* c) { return c && c->has_index ? c->index_bytes : 0; }
+
+// ---------------------------------------------------------------------------------------------------------
+// index upload
+// ---------------------------------------------------------------------------------------------------------
+template <typename T>
+static cudaError_t upload_vec(DevBuf& buf, const T* src, size_t n, u64* acc) {
+    cudaError_t e = buf.ensure(std::max<size_t>(n, 1) * sizeof(T));
+    if (e != cudaSuccess) return e;
+    if (n) e = cudaMemcpy(buf.p, src, n * sizeof(T), cudaMemcpyHostToDevice);
+    if (acc) *acc += n * sizeof(T);
+    return e;
+}
+
+RTX_API int rtx_index_upload(rtx_ctx* ctx, const rtx_index_desc* d) {
+    if (!ctx) return RTX_ERR_INVALID;
+    REQUIRE(d != nullptr, "rtx_index_upload: desc is NULL");
+    REQUIRE(d->n_refs >= 1 && d->n_refs <= 0xFFFFFFFFull, "n_refs must be in [1, 2^32) (tree.rs:24-31)");
+    REQUIRE(d->csr_offsets && d->n_nodes >= 1 && d->node_lo && d->node_hi && d->node_type && d->child_first && d->child_count &&
+                d->ref_levels,
+            "rtx_index_upload: NULL array");
+    const u64 N = d->n_refs;
+    const u64 s0 = d->ref_shard_begin, s1 = d->ref_shard_end ? d->ref_shard_end : N;
+    REQUIRE(s0 < s1 && s1 <= N, "bad reference shard range");
+    const u64 nnz = d->csr_offsets[65536];
+    REQUIRE(d->csr_offsets[0] == 0, "csr_offsets[0] must be 0");
+    for (u32 k = 0; k < 65536; ++k) REQUIRE(d->csr_offsets[k] <= d->csr_offsets[k + 1], "csr_offsets must be non-decreasing");
+    REQUIRE(nnz == 0 || d->csr_ids, "csr_ids is NULL");
+    REQUIRE(d->node_lo[0] == 0 && d->node_hi[0] == N, "node 0 must be the root with range [0, n_refs)");
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamSynchronize(ctx->stream));
+    ctx->has_index = false;
+    ctx->has_batch = false;
+
+    // ---- tree checks, depth --------------------------------------------------------------------------
+    const u32 nn = d->n_nodes;
+    std::vector<u32> depth(nn, 0);
+    u32 max_depth = 0;
+    u64 child_total = 0;
+    for (u32 i = 0; i < nn; ++i) {
+        REQUIRE(d->node_lo[i] < d->node_hi[i] && d->node_hi[i] <= N, "node range out of bounds");
+        REQUIRE(d->node_type[i] <= 2, "node_type must be 0 (Inner), 1 (Taxon) or 2 (Sequence with children)");
+        const u32 cf = d->child_first[i], cc = d->child_count[i];
+        child_total += cc;
+        if (cc) {
+            REQUIRE(cf > i && (u64)cf + cc <= nn, "children must follow their parent and stay in range");
+            for (u32 c = cf; c < cf + cc; ++c) {
+                depth[c] = depth[i] + 1;
+                max_depth = std::max(max_depth, depth[c]);
+                REQUIRE(d->node_lo[c] >= d->node_lo[i] && d->node_hi[c] <= d->node_hi[i], "child range outside its parent");
+            }
+        } else {
+            REQUIRE(d->node_type[i] != 0, "an Inner node must have children (lineage.rs:162 unwrap)");
+        }
+    }
+    REQUIRE(child_total == nn - 1, "every node except the root must be the child of exactly one node");
+    u32 max_levels = std::max(1u, max_depth);
+    for (u64 r = 0; r < N; ++r) max_levels = std::max<u32>(max_levels, d->ref_levels[r]);
+    if (max_levels > RTX_MAX_LEVELS) return set_err(ctx, RTX_ERR_UNSUPPORTED, "lineage deeper than RTX_MAX_LEVELS");
+
+    IndexView& ix = ctx->ix;
+    const u64 Ns = s1 - s0;
+    const u32 row_words = round_up((u32)((Ns + 31) / 32), kRowAlignWords);
+    u64 bytes = 0;
+
+    // ---- row map: k-mers with at least one posting inside the shard ------------------------------------
+    std::vector<u32> rowmap(65536, 0), present(2048, 0);
+    u32 n_rows = 1;
+    for (u32 k = 0; k < 65536; ++k) {
+        const u64 o0 = d->csr_offsets[k], o1 = d->csr_offsets[k + 1];
+        if (o0 == o1) continue;
+        bool in = true;
+        if (s0 != 0 || s1 != N) {
+            const u32* it = std::lower_bound(d->csr_ids + o0, d->csr_ids + o1, (u32)s0);
+            in = (it != d->csr_ids + o1) && (*it < s1);
+        }
+        if (in) {
+            rowmap[k] = n_rows++;
+            present[k >> 5] |= 1u << (k & 31);
+        }
+    }
+    CU(upload_vec(ctx->d_rowmap, rowmap.data(), 65536, &bytes));
+    CU(upload_vec(ctx->d_present, present.data(), 2048, &bytes));
+
+    // ---- node boundaries ---------------------------------------------------------------------------------
+    std::vector<u32> bnd_after(row_words, 0), bnd_rank(row_words, 0), blo(nn), bhi(nn);
+    auto clampu = [&](u64 x) { return std::min(std::max(x, s0), s1); };
+    auto mark = [&](u64 pos) {
+        if (pos > s0) {
+            u64 r = pos - s0 - 1;
+            bnd_after[r >> 5] |= 1u << (r & 31);
+        }
+    };
+    mark(s1);
+    for (u32 i = 0; i < nn; ++i) {
+        mark(clampu(d->node_lo[i]));
+        mark(clampu(d->node_hi[i]));
+    }
+    u32 run = 0;
+    for (u32 w = 0; w < row_words; ++w) {
+        bnd_rank[w] = run;
+        run += (u32)__builtin_popcount(bnd_after[w]);
+    }
+    const u32 n_bnd = run + 1;
+    auto bidx = [&](u64 pos) -> u32 {
+        if (pos == s0) return 0;
+        u64 r = pos - s0 - 1;
+        u32 w = bnd_after[r >> 5];
+        return 1u + bnd_rank[r >> 5] + (u32)__builtin_popcount(w & ((1u << (r & 31)) - 1u));
+    };
+    for (u32 i = 0; i < nn; ++i) {
+        blo[i] = bidx(clampu(d->node_lo[i]));
+        bhi[i] = bidx(clampu(d->node_hi[i]));
+    }
+    CU(upload_vec(ctx->d_node_lo, d->node_lo, nn, &bytes));
+    CU(upload_vec(ctx->d_node_hi, d->node_hi, nn, &bytes));
+    CU(upload_vec(ctx->d_node_type, d->node_type, nn, &bytes));
+    CU(upload_vec(ctx->d_child_first, d->child_first, nn, &bytes));
+    CU(upload_vec(ctx->d_child_count, d->child_count, nn, &bytes));
+    CU(upload_vec(ctx->d_node_blo, blo.data(), nn, &bytes));
+    CU(upload_vec(ctx->d_node_bhi, bhi.data(), nn, &bytes));
+    CU(upload_vec(ctx->d_bnd_after, bnd_after.data(), row_words, &bytes));
+    CU(upload_vec(ctx->d_bnd_rank, bnd_rank.data(), row_words, &bytes));
+    CU(upload_vec(ctx->d_ref_levels, d->ref_levels, N, &bytes));
+
+    // ---- bit rows -----------------------------------------------------------------------------------------
+    const size_t row_bytes = (size_t)row_words * 4;
+    CU(ctx->d_bitrows.ensure((size_t)n_rows * row_bytes));
+    CU(cudaMemsetAsync(ctx->d_bitrows.p, 0, (size_t)n_rows * row_bytes, ctx->stream));
+    bytes += (u64)n_rows * row_bytes;
+    CU(upload_vec(ctx->d_csr_off, d->csr_offsets, 65537, nullptr));
+    if (nnz) {
+        if (ctx->keep_csr) {
+            CU(upload_vec(ctx->d_csr_ids, d->csr_ids, nnz, &bytes));
+            bytes += 65537 * 8;
+            LaunchTimer lt(ctx, RTX_K_INDEX);
+            build_bitrows_kernel<<<ctx->n_sms * 8, 256, 0, ctx->stream>>>(ctx->d_csr_off.as<u64>(), ctx->d_csr_ids.as<u32>(), nnz,
+                                                                         ctx->d_rowmap.as<u32>(), ctx->d_bitrows.as<u32>(), row_words,
+                                                                         s0, s1);
+        } else {
+            // stream the postings through a bounded device buffer; offsets are rebased per chunk on the device side
+            const u64 chunk = 64ull << 20;  // postings per chunk (256 MB)
+            CU(ctx->d_csr_ids.ensure(std::min(nnz, chunk) * 4));
+            std::vector<u64> off_chunk(65537);
+            for (u64 p0 = 0; p0 < nnz; p0 += chunk) {
+                const u64 cn = std::min(chunk, nnz - p0);
+                CU(cudaMemcpyAsync(ctx->d_csr_ids.p, d->csr_ids + p0, cn * 4, cudaMemcpyHostToDevice, ctx->stream));
+                for (u32 k = 0; k <= 65536; ++k) {
+                    u64 o = d->csr_offsets[k];
+                    off_chunk[k] = o <= p0 ? 0 : std::min(o - p0, cn);
+                }
+                // csr_off[k] <= p  <=> posting p of this chunk belongs to a k-mer >= k
+                CU(cudaMemcpyAsync(ctx->d_csr_off.p, off_chunk.data(), 65537 * 8, cudaMemcpyHostToDevice, ctx->stream));
+                {
+                    LaunchTimer lt(ctx, RTX_K_INDEX);
+                    build_bitrows_kernel<<<ctx->n_sms * 8, 256, 0, ctx->stream>>>(ctx->d_csr_off.as<u64>(), ctx->d_csr_ids.as<u32>(),
+                                                                                 cn, ctx->d_rowmap.as<u32>(), ctx->d_bitrows.as<u32>(),
+                                                                                 row_words, s0, s1);
+                }
+                CU(cudaStreamSynchronize(ctx->stream));  // off_chunk / pageable source reused next iteration
+            }
+        }
+    }
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(ctx->stream));
+    if (!ctx->keep_csr) {
+        ctx->d_csr_ids.release();
+        ctx->d_csr_off.release();
+    }
+
+    ix.bitrows = ctx->d_bitrows.as<u32>();
+    ix.rowmap = ctx->d_rowmap.as<u32>();
+    ix.present = ctx->d_present.as<u32>();
+    ix.csr_off = ctx->keep_csr ? ctx->d_csr_off.as<u64>() : nullptr;
+    ix.csr_ids = ctx->keep_csr ? ctx->d_csr_ids.as<u32>() : nullptr;
+    ix.row_words = row_words;
+    ix.n_refs = N;
+    ix.shard_begin = s0;
+    ix.shard_refs = Ns;
+    ix.n_pad = (u64)row_words * 32;
+    ix.node_lo = ctx->d_node_lo.as<u32>();
+    ix.node_hi = ctx->d_node_hi.as<u32>();
+    ix.node_type = ctx->d_node_type.as<u8>();
+    ix.child_first = ctx->d_child_first.as<u32>();
+    ix.child_count = ctx->d_child_count.as<u32>();
+    ix.node_blo = ctx->d_node_blo.as<u32>();
+    ix.node_bhi = ctx->d_node_bhi.as<u32>();
+    ix.bnd_after = ctx->d_bnd_after.as<u32>();
+    ix.bnd_rank = ctx->d_bnd_rank.as<u32>();
+    ix.n_bnd = n_bnd;
+    ix.n_nodes = nn;
+    ix.max_levels = max_levels;
+    ix.ref_levels = ctx->d_ref_levels.as<u8>();
+    ctx->n_rows = n_rows;
+    ctx->index_bytes = bytes;
+    ctx->has_index = true;
+    return RTX_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// batch upload
+// ---------------------------------------------------------------------------------------------------------
+static int ensure_pool(rtx_ctx* ctx, u64 cap) {
+    const u32 ML = ctx->ix.max_levels;
+    CU(ctx->d_pool_first.ensure(cap * 4));
+    CU(ctx->d_pool_nlev.ensure(cap));
+    CU(ctx->d_pool_conf.ensure(cap * ML * 8));
+    CU(ctx->d_pool_local.ensure(cap * 8));
+    CU(ctx->d_pool_used.ensure(8));
+    ctx->pool.first_ref = ctx->d_pool_first.as<u32>();
+    ctx->pool.n_levels = ctx->d_pool_nlev.as<u8>();
+    ctx->pool.conf = ctx->d_pool_conf.as<double>();
+    ctx->pool.local = ctx->d_pool_local.as<double>();
+    ctx->pool.used = ctx->d_pool_used.as<unsigned long long>();
+    ctx->pool.cap = cap;
+    return RTX_OK;
+}
+
+RTX_API int rtx_batch_upload(rtx_ctx* ctx, const rtx_batch* batch) {
+    if (!ctx) return RTX_ERR_INVALID;
+    if (!ctx->has_index) return set_err(ctx, RTX_ERR_NO_INDEX, "rtx_batch_upload: no index uploaded");
+    REQUIRE(batch != nullptr, "batch is NULL");
+    const u32 nq = batch->n_queries;
+    REQUIRE(nq == 0 || batch->seq_offsets, "seq_offsets is NULL");
+    CU(cudaSetDevice(ctx->device));
+    ctx->has_batch = false;
+    ctx->ran = false;
+    BatchView& bv = ctx->bv;
+    bv = BatchView{};
+    bv.n_queries = nq;
+    bv.flags = batch->flags;
+    if (nq == 0) {
+        ctx->has_batch = true;
+        return RTX_OK;
+    }
+    u32 max_len = 0;
+    for (u32 q = 0; q < nq; ++q) {
+        REQUIRE(batch->seq_offsets[q] <= batch->seq_offsets[q + 1], "seq_offsets must be non-decreasing");
+        u64 l = batch->seq_offsets[q + 1] - batch->seq_offsets[q];
+        REQUIRE(l <= 0x7FFFFFFFull, "query too long");
+        max_len = std::max<u32>(max_len, (u32)l);
+    }
+    const u64 total = batch->seq_offsets[nq] - batch->seq_offsets[0];
+    REQUIRE(total == 0 || batch->seq_codes, "seq_codes is NULL");
+    const u32 kmax = max_len >= 8 ? max_len - 7 : 0;  // upper bound on unique 8-mers of one query
+    if (kmax > 65535) return set_err(ctx, RTX_ERR_UNSUPPORTED, "query with more than 65535 8-mer windows (raxtax.rs:56 asserts the same)");
+    const u32 kstride = round_up(std::max(kmax, 1u), 16);
+    const u32 hstride = round_up(kmax + 1, 4);
+    const size_t smem = ProbSmem::bytes(hstride, hstride / 2 + 1);
+    if (smem > 200 * 1024)
+        return set_err(ctx, RTX_ERR_UNSUPPORTED, "query too long for the shared-memory probability tables (more than ~5800 unique 8-mers)");
+    ctx->max_len = max_len;
+    ctx->total_codes = total;
+    u64 total_exact = 0;
+    if (batch->exact_offsets) {
+        for (u32 q = 0; q < nq; ++q) REQUIRE(batch->exact_offsets[q] <= batch->exact_offsets[q + 1], "exact_offsets must be non-decreasing");
+        REQUIRE(batch->exact_offsets[0] == 0, "exact_offsets[0] must be 0");
+        total_exact = batch->exact_offsets[nq];
+        REQUIRE(total_exact == 0 || batch->exact_ids, "exact_ids is NULL");
+        for (u64 e = 0; e < total_exact; ++e) REQUIRE(batch->exact_ids[e] < ctx->ix.n_refs, "exact id out of range");
+    }
+    ctx->total_exact = total_exact;
+
+    // H2D (offsets are rebased to 0 so that callers may pass a window of a larger array)
+    CU(ctx->d_seq_off.ensure((nq + 1) * 8));
+    CU(ctx->d_codes.ensure(std::max<u64>(total, 1)));
+    if (batch->seq_offsets[0] == 0) {
+        CU(cudaMemcpyAsync(ctx->d_seq_off.p, batch->seq_offsets, (nq + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+    } else {
+        std::vector<u64> reb(nq + 1);
+        for (u32 q = 0; q <= nq; ++q) reb[q] = batch->seq_offsets[q] - batch->seq_offsets[0];
+        CU(cudaMemcpyAsync(ctx->d_seq_off.p, reb.data(), (nq + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+    }
+    if (total) CU(cudaMemcpyAsync(ctx->d_codes.p, batch->seq_codes + batch->seq_offsets[0], total, cudaMemcpyHostToDevice, ctx->stream));
+    ctx->prof.h2d_bytes += (nq + 1) * 8 + total;
+    if (batch->exact_offsets) {
+        CU(ctx->d_exact_off.ensure((nq + 1) * 4));
+        CU(ctx->d_exact_ids.ensure(std::max<u64>(total_exact, 1) * 4));
+        CU(cudaMemcpyAsync(ctx->d_exact_off.p, batch->exact_offsets, (nq + 1) * 4, cudaMemcpyHostToDevice, ctx->stream));
+        if (total_exact) CU(cudaMemcpyAsync(ctx->d_exact_ids.p, batch->exact_ids, total_exact * 4, cudaMemcpyHostToDevice, ctx->stream));
+        ctx->prof.h2d_bytes += (nq + 1) * 4 + total_exact * 4;
+        bv.exact_off = ctx->d_exact_off.as<u32>();
+        bv.exact_ids = ctx->d_exact_ids.as<u32>();
+    }
+    bv.seq_off = ctx->d_seq_off.as<u64>();
+    bv.codes = ctx->d_codes.as<u8>();
+    bv.kstride = kstride;
+    bv.hstride = hstride;
+
+    // per-query device arrays
+    CU(ctx->d_K.ensure(nq * 2));
+    CU(ctx->d_kmers.ensure((size_t)nq * kstride * 2));
+    CU(ctx->d_rows.ensure((size_t)nq * kstride * 4));
+    CU(ctx->d_nrows.ensure(nq * 4));
+    CU(ctx->d_hist.ensure((size_t)nq * hstride * 4));
+    bv.K = ctx->d_K.as<u16>();
+    bv.kmers = ctx->d_kmers.as<u16>();
+    bv.rows = ctx->d_rows.as<u32>();
+    bv.nrows = ctx->d_nrows.as<u32>();
+    bv.hist = ctx->d_hist.as<u32>();
+    CU(ctx->d_res_off.ensure(nq * 4));
+    CU(ctx->d_res_cnt.ensure(nq * 4));
+    CU(ctx->d_global.ensure(nq * 8));
+    CU(ctx->d_status.ensure(nq * 4));
+    CU(ctx->d_hits.ensure(8));
+    ctx->pool.res_off = ctx->d_res_off.as<u32>();
+    ctx->pool.res_cnt = ctx->d_res_cnt.as<u32>();
+    ctx->pool.global_sig = ctx->d_global.as<double>();
+    ctx->pool.status = ctx->d_status.as<int>();
+    if (ctx->pool.cap < (u64)nq * 4 + 1024) {
+        int rc = ensure_pool(ctx, (u64)nq * 4 + 1024);
+        if (rc) return rc;
+    }
+
+    // sub-batch: bound the per-query count vectors to ~2 GiB
+    const u64 per_query = ctx->ix.n_pad * 2;
+    u64 sb = ctx->sub_batch_opt ? (u64)ctx->sub_batch_opt : std::max<u64>(1, (2ull << 30) / per_query);
+    sb = std::min<u64>(std::min<u64>(sb, nq), 65535);
+    ctx->sub_batch = (u32)sb;
+    CU(ctx->d_counts.ensure(sb * per_query));
+
+    // probability kernel scratch
+    ctx->prob_smem = smem;
+    CU(cudaFuncSetAttribute(prob_lineage_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int occ = 0;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, prob_lineage_kernel, kProbThreads, smem));
+    if (occ < 1) return set_err(ctx, RTX_ERR_CUDA, "prob_lineage_kernel does not fit on an SM");
+    const int slots = (int)std::min<u64>((u64)ctx->n_sms * occ, sb);
+    ctx->prob_slots = slots;
+    const u32 tstride = round_up(hstride / 2 + 1, 4);
+    ctx->sc.tstride = tstride;
+    ctx->sc.cbuf_stride = (size_t)hstride * tstride;
+    ctx->sc.preb_stride = round_up(ctx->ix.n_bnd, 4);
+    CU(ctx->d_cbuf.ensure((size_t)slots * ctx->sc.cbuf_stride * 8));
+    CU(ctx->d_preb.ensure((size_t)slots * ctx->sc.preb_stride * 8));
+    CU(ctx->d_st_first.ensure((size_t)slots * RTX_MAX_RESULTS_PER_QUERY * 4));
+    CU(ctx->d_st_nlev.ensure((size_t)slots * RTX_MAX_RESULTS_PER_QUERY));
+    CU(ctx->d_st_conf.ensure((size_t)slots * RTX_MAX_RESULTS_PER_QUERY * ctx->ix.max_levels * 8));
+    CU(ctx->d_st_local.ensure((size_t)slots * RTX_MAX_RESULTS_PER_QUERY * 8));
+    ctx->sc.cbuf = ctx->d_cbuf.as<double>();
+    ctx->sc.preb = ctx->d_preb.as<double>();
+    ctx->sc.st_first = ctx->d_st_first.as<u32>();
+    ctx->sc.st_nlev = ctx->d_st_nlev.as<u8>();
+    ctx->sc.st_conf = ctx->d_st_conf.as<double>();
+    ctx->sc.st_local = ctx->d_st_local.as<double>();
+    ctx->has_batch = true;
+    return RTX_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// kernels
+// ---------------------------------------------------------------------------------------------------------
+template <int V, int NP>
+static cudaError_t launch_hitcount(rtx_ctx* c, int q_base, int qb) {
+    const int n_tiles = (int)(c->ix.row_words / (32 * V));
+    const int max_tiles = 64;
+    const int groups = (n_tiles + max_tiles - 1) / max_tiles;
+    const int tiles_per_cta = (n_tiles + groups - 1) / groups;
+    const size_t smem = (size_t)(kRowListCap + c->bv.hstride) * 4;
+    cudaError_t e = cudaFuncSetAttribute(hitcount_bitrows_kernel<V, NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    dim3 grid(qb, groups);
+    hitcount_bitrows_kernel<V, NP><<<grid, kHitThreads, smem, c->stream>>>(c->ix, c->bv, c->d_counts.as<u16>(), q_base, tiles_per_cta, n_tiles);
+    return cudaGetLastError();
+}
+
+template <int V>
+static cudaError_t launch_hitcount_np(rtx_ctx* c, int q_base, int qb, u32 kmax) {
+    if (kmax < (1u << 8)) return launch_hitcount<V, 8>(c, q_base, qb);
+    if (kmax < (1u << 10)) return launch_hitcount<V, 10>(c, q_base, qb);
+    if (kmax < (1u << 11)) return launch_hitcount<V, 11>(c, q_base, qb);
+    if (kmax < (1u << 13)) return launch_hitcount<V, 13>(c, q_base, qb);
+    return launch_hitcount<V, 16>(c, q_base, qb);
+}
+
+static int run_phase1(rtx_ctx* ctx, int q_base, int qb) {
+    const u32 kmax = ctx->max_len >= 8 ? ctx->max_len - 7 : 0;
+    LaunchTimer lt(ctx, RTX_K_HITCOUNT);
+    if (ctx->variant == RTX_HITCOUNT_CSR) {
+        if (!ctx->ix.csr_ids && kmax > 0 && ctx->n_rows > 1)
+            return set_err(ctx, RTX_ERR_INVALID, "CSR hit-count variant needs RTX_OPT_KEEP_CSR set before rtx_index_upload");
+        const size_t smem = (size_t)(kCsrTileRefs / 2 + ctx->bv.hstride) * 4;
+        CU(cudaFuncSetAttribute(hitcount_csr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        dim3 grid(qb, (unsigned)((ctx->ix.shard_refs + kCsrTileRefs - 1) / kCsrTileRefs));
+        hitcount_csr_kernel<<<grid, kCsrThreads, smem, ctx->stream>>>(ctx->ix, ctx->bv, ctx->d_counts.as<u16>(), q_base);
+        CU(cudaGetLastError());
+    } else {
+        CU(launch_hitcount_np<4>(ctx, q_base, qb, kmax));
+    }
+    return RTX_OK;
+}
+
+static int run_all(rtx_ctx* ctx) {
+    BatchView& bv = ctx->bv;
+    const u32 nq = bv.n_queries;
+    if (nq == 0) return RTX_OK;
+    CU(cudaMemsetAsync(ctx->d_hist.p, 0, (size_t)nq * bv.hstride * 4, ctx->stream));
+    CU(cudaMemsetAsync(ctx->d_pool_used.p, 0, 8, ctx->stream));
+    CU(cudaMemsetAsync(ctx->d_hits.p, 0, 8, ctx->stream));
+    {
+        LaunchTimer lt(ctx, RTX_K_KMERS);
+        kmers_kernel<<<nq, kKmerThreads, 0, ctx->stream>>>(ctx->ix, bv);
+        CU(cudaGetLastError());
+    }
+    for (u32 q0 = 0; q0 < nq; q0 += ctx->sub_batch) {
+        const int qb = (int)std::min<u32>(ctx->sub_batch, nq - q0);
+        int rc = run_phase1(ctx, (int)q0, qb);
+        if (rc) return rc;
+        if ((bv.flags & RTX_SKIP_EXACT_MATCHES) && bv.exact_off) {
+            LaunchTimer lt(ctx, RTX_K_FIXUP);
+            fixup_exact_kernel<<<(qb + 127) / 128, 128, 0, ctx->stream>>>(ctx->ix, bv, ctx->d_counts.as<u16>(), (int)q0, qb);
+            CU(cudaGetLastError());
+        }
+        {
+            LaunchTimer lt(ctx, RTX_K_PROB);
+            const int grid = std::min(ctx->prob_slots, qb);
+            prob_lineage_kernel<<<grid, kProbThreads, ctx->prob_smem, ctx->stream>>>(ctx->ix, bv, ctx->pool, ctx->sc, ctx->d_counts.as<u16>(),
+                                                                                   (int)q0, qb, ctx->d_hits.as<unsigned long long>());
+            CU(cudaGetLastError());
+        }
+        if (ctx->tap_counts_host) {
+            const u64 Ns = ctx->ix.shard_refs;
+            CU(cudaMemcpy2DAsync(ctx->tap_counts_host + (size_t)q0 * Ns, Ns * 2, ctx->d_counts.p, ctx->ix.n_pad * 2, Ns * 2, qb,
+                                 cudaMemcpyDeviceToHost, ctx->stream));
+            ctx->prof.d2h_bytes += (u64)qb * Ns * 2;
+        }
+    }
+    ctx->prof.queries += nq;
+    ctx->ran = true;
+    return RTX_OK;
+}
+
+RTX_API int rtx_batch_run(rtx_ctx* ctx) {
+    if (!ctx) return RTX_ERR_INVALID;
+    if (!ctx->has_batch) return set_err(ctx, RTX_ERR_INVALID, "rtx_batch_run: no batch uploaded");
+    CU(cudaSetDevice(ctx->device));
+    return run_all(ctx);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// download
+// ---------------------------------------------------------------------------------------------------------
+RTX_API int rtx_batch_download(rtx_ctx* ctx, rtx_results* res) {
+    if (!ctx) return RTX_ERR_INVALID;
+    REQUIRE(res != nullptr, "results is NULL");
+    if (!ctx->has_batch || (!ctx->ran && ctx->bv.n_queries)) return set_err(ctx, RTX_ERR_INVALID, "rtx_batch_download: nothing was run");
+    CU(cudaSetDevice(ctx->device));
+    const BatchView& bv = ctx->bv;
+    const u32 nq = bv.n_queries;
+    res->n_results = 0;
+    if (nq == 0) {
+        if (res->result_begin) res->result_begin[0] = 0;
+        return RTX_OK;
+    }
+    REQUIRE(res->result_begin && res->n_kmers && res->global_signal, "result_begin / n_kmers / global_signal must be provided");
+    const u32 ML = ctx->ix.max_levels;
+    unsigned long long used = 0, hits = 0;
+    ctx->h_res_off.resize(nq);
+    ctx->h_res_cnt.resize(nq);
+    ctx->h_status.resize(nq);
+    ctx->h_nrows.resize(nq);
+    CU(cudaMemcpyAsync(&used, ctx->d_pool_used.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaMemcpyAsync(&hits, ctx->d_hits.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaMemcpyAsync(ctx->h_res_off.data(), ctx->d_res_off.p, nq * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaMemcpyAsync(ctx->h_res_cnt.data(), ctx->d_res_cnt.p, nq * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaMemcpyAsync(ctx->h_status.data(), ctx->d_status.p, nq * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaMemcpyAsync(ctx->h_nrows.data(), ctx->d_nrows.p, nq * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaMemcpyAsync(res->n_kmers, ctx->d_K.p, nq * 2, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaMemcpyAsync(res->global_signal, ctx->d_global.p, nq * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    ctx->prof.d2h_bytes += 16 + (u64)nq * (4 * 4 + 2 + 8);
+    ctx->prof.hits += hits;
+    {
+        u64 rows = 0;
+        for (u32 q = 0; q < nq; ++q) rows += ctx->h_nrows[q];
+        ctx->prof.bitrow_bytes += rows * (u64)ctx->ix.row_words * 4 + (u64)nq * ctx->ix.n_pad * 2;
+        ctx->prof.csr_equiv_bytes += 4 * (u64)hits + (u64)nq * ctx->ix.shard_refs * 2;
+    }
+    bool pool_overflow = false;
+    for (u32 q = 0; q < nq; ++q) {
+        switch (ctx->h_status[q]) {
+            case kQOk: break;
+            case kQPoolOverflow: pool_overflow = true; break;
+            case kQProbSumZero:
+                return set_err(ctx, RTX_ERR_ASSERT, "query " + std::to_string(q) + ": probs_sum > 0.0 violated (prob.rs:98)");
+            case kQEmptyResult:
+                return set_err(ctx, RTX_ERR_ASSERT, "query " + std::to_string(q) + ": empty evaluation result (raxtax.rs:72)");
+            case kQTooManyResults:
+                return set_err(ctx, RTX_ERR_UNSUPPORTED, "query " + std::to_string(q) + ": more than RTX_MAX_RESULTS_PER_QUERY result lines");
+            default: return set_err(ctx, RTX_ERR_CUDA, "query " + std::to_string(q) + ": unknown device status");
+        }
+    }
+    if (pool_overflow) {
+        // grow the pool and redo the whole batch once (counts of earlier sub-batches are gone)
+        int rc = ensure_pool(ctx, used + 1024);
+        if (rc) return rc;
+        rc = run_all(ctx);
+        if (rc) return rc;
+        return rtx_batch_download(ctx, res);
+    }
+    res->n_results = used;
+    u64 acc = 0;
+    for (u32 q = 0; q < nq; ++q) {
+        res->result_begin[q] = (u32)acc;
+        acc += ctx->h_res_cnt[q];
+    }
+    res->result_begin[nq] = (u32)acc;
+    if (acc != used) return set_err(ctx, RTX_ERR_CUDA, "result accounting mismatch");
+    if (used > res->result_capacity) return set_err(ctx, RTX_ERR_INVALID, "result_capacity too small; n_results holds the needed size");
+    if (used) {
+        REQUIRE(res->first_ref && res->n_levels && res->confidence && res->local_signal, "per-result output arrays must be provided");
+        ctx->h_pool_first.resize(used);
+        ctx->h_pool_nlev.resize(used);
+        ctx->h_pool_conf.resize(used * ML);
+        ctx->h_pool_local.resize(used);
+        CU(cudaMemcpyAsync(ctx->h_pool_first.data(), ctx->d_pool_first.p, used * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaMemcpyAsync(ctx->h_pool_nlev.data(), ctx->d_pool_nlev.p, used, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaMemcpyAsync(ctx->h_pool_conf.data(), ctx->d_pool_conf.p, used * ML * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaMemcpyAsync(ctx->h_pool_local.data(), ctx->d_pool_local.p, used * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+        ctx->prof.d2h_bytes += used * (4 + 1 + 8 + (u64)ML * 8);
+        for (u32 q = 0; q < nq; ++q) {
+            const u32 src = ctx->h_res_off[q], dst = res->result_begin[q], n = ctx->h_res_cnt[q];
+            if (!n) continue;
+            memcpy(res->first_ref + dst, ctx->h_pool_first.data() + src, n * 4);
+            memcpy(res->n_levels + dst, ctx->h_pool_nlev.data() + src, n);
+            memcpy(res->confidence + (size_t)dst * ML, ctx->h_pool_conf.data() + (size_t)src * ML, (size_t)n * ML * 8);
+            memcpy(res->local_signal + dst, ctx->h_pool_local.data() + src, n * 8);
+        }
+    }
+    // taps
+    if (res->tap_hist) {
+        REQUIRE(res->tap_hist_stride >= bv.hstride || res->tap_hist_stride >= (u64)(ctx->max_len >= 8 ? ctx->max_len - 7 : 0) + 1,
+                "tap_hist_stride too small");
+        const u64 w = std::min<u64>(res->tap_hist_stride, bv.hstride);
+        CU(cudaMemcpy2DAsync(res->tap_hist, res->tap_hist_stride * 4, ctx->d_hist.p, (size_t)bv.hstride * 4, w * 4, nq, cudaMemcpyDeviceToHost,
+                             ctx->stream));
+        ctx->prof.d2h_bytes += (u64)nq * w * 4;
+    }
+    if (res->tap_kmers) {
+        const u64 w = std::min<u64>(res->tap_kmer_stride, bv.kstride);
+        CU(cudaMemcpy2DAsync(res->tap_kmers, res->tap_kmer_stride * 2, ctx->d_kmers.p, (size_t)bv.kstride * 2, w * 2, nq,
+                             cudaMemcpyDeviceToHost, ctx->stream));
+        ctx->prof.d2h_bytes += (u64)nq * w * 2;
+    }
+    if (res->tap_counts && !ctx->tap_counts_host) {
+        REQUIRE(ctx->sub_batch >= nq, "tap_counts through rtx_batch_download needs the whole batch in one sub-batch; use rtx_classify_batch");
+        const u64 Ns = ctx->ix.shard_refs;
+        CU(cudaMemcpy2DAsync(res->tap_counts, Ns * 2, ctx->d_counts.p, ctx->ix.n_pad * 2, Ns * 2, nq, cudaMemcpyDeviceToHost, ctx->stream));
+        ctx->prof.d2h_bytes += (u64)nq * Ns * 2;
+    }
+    CU(cudaStreamSynchronize(ctx->stream));
+    return RTX_OK;
+}
+
+RTX_API int rtx_classify_batch(rtx_ctx* ctx, const rtx_batch* batch, rtx_results* results) {
+    if (!ctx) return RTX_ERR_INVALID;
+    REQUIRE(results != nullptr, "results is NULL");
+    int rc = rtx_batch_upload(ctx, batch);
+    if (rc) return rc;
+    ctx->tap_counts_host = results->tap_counts;
+    rc = rtx_batch_run(ctx);
+    if (rc == RTX_OK) rc = rtx_batch_download(ctx, results);
+    ctx->tap_counts_host = nullptr;
+    return rc;
+}
+
+// ---- sharded mode ------------------------------------------------------------------------------------------
+RTX_API int rtx_shard_phase1(rtx_ctx* ctx) { return set_err(ctx, RTX_ERR_UNSUPPORTED, "reference-sharded mode is not implemented yet"); }
+RTX_API int rtx_shard_hist_buffer(rtx_ctx* ctx, void** p, uint64_t* n) {
+    (void)p;
+    (void)n;
+    return set_err(ctx, RTX_ERR_UNSUPPORTED, "reference-sharded mode is not implemented yet");
+}
+RTX_API int rtx_shard_phase2(rtx_ctx* ctx) { return set_err(ctx, RTX_ERR_UNSUPPORTED, "reference-sharded mode is not implemented yet"); }
+RTX_API int rtx_shard_partial_buffer(rtx_ctx* ctx, void** p, uint64_t* n) {
+    (void)p;
+    (void)n;
+    return set_err(ctx, RTX_ERR_UNSUPPORTED, "reference-sharded mode is not implemented yet");
+}
+RTX_API int rtx_shard_phase3(rtx_ctx* ctx) { return set_err(ctx, RTX_ERR_UNSUPPORTED, "reference-sharded mode is not implemented yet"); }
+
+// ---- measurement -------------------------------------------------------------------------------------------
+RTX_API int rtx_profile_reset(rtx_ctx* ctx) {
+    if (!ctx) return RTX_ERR_INVALID;
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamSynchronize(ctx->stream));
+    drain_events(ctx);
+    ctx->prof = rtx_profile{};
+    return RTX_OK;
+}
+
+RTX_API int rtx_profile_get(rtx_ctx* ctx, rtx_profile* out) {
+    if (!ctx || !out) return RTX_ERR_INVALID;
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamSynchronize(ctx->stream));
+    drain_events(ctx);
+    *out = ctx->prof;
+    return RTX_OK;
+}
+

@@ -1,0 +1,717 @@
+// raxtax_host.cpp -- C++ host side of the B200 raxtax hot path (libraxtax_host.so, C ABI in include/raxtax_host.h).
+//
+// Mirrors the reference's host-side interface around the device boundary:
+//   parser::parse_reference_fasta_str / parse_query_fasta_str   src/parser.rs:46-154
+//   Tree::new                                                   src/tree.rs:47-140
+//   raxtax::raxtax                                              src/raxtax.rs:14-97
+//   EvaluationResult::get_output_string / get_tsv_string        src/lineage.rs:17-48, src/utils.rs:62-89
+// Data layout is flat (CSR postings, BFS-numbered node arrays, one sequence blob) because it feeds
+// rtx_index_upload directly; the per-query numerics all run on the GPU through include/raxtax_b200.h.
+
+#include <algorithm>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <numeric>
+#include <stdexcept>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "raxtax_host.h"
+
+namespace raxtax {
+
+typedef uint8_t u8;
+typedef uint16_t u16;
+typedef uint32_t u32;
+typedef uint64_t u64;
+
+struct Error : std::runtime_error {
+    using std::runtime_error::runtime_error;
+};
+
+// ---- parser.rs:11-34 ------------------------------------------------------------------------------------------
+struct DnaTable {
+    u8 t[256];
+    DnaTable() {
+        memset(t, 0, sizeof t);
+        const u8 a = 1, c = 2, g = 4, tt = 8;
+        auto set = [&](char ch, u8 v) {
+            t[(unsigned char)ch] = v;
+            t[(unsigned char)(ch + 32)] = v;  // to_ascii_uppercase
+        };
+        set('A', a); set('C', c); set('G', g); set('T', tt);
+        set('W', a | tt); set('S', c | g); set('M', a | c); set('K', g | tt); set('R', a | g); set('Y', c | tt);
+        set('B', c | g | tt); set('D', a | g | tt); set('H', a | c | tt); set('V', a | c | g); set('N', a | c | g | tt);
+    }
+};
+static const DnaTable kDna;
+
+static inline u8 map_dna_char(char ch) {
+    u8 v = kDna.t[(unsigned char)ch];
+    if (!v) throw Error(std::string("Unexpected character: ") + ch);  // panic! in the reference (parser.rs:32)
+    return v;
+}
+
+// One logical FASTA line: str::lines() then trim() (parser.rs:53-57).  Returns false at end of input.
+struct LineReader {
+    const char* p;
+    const char* end;
+    LineReader(const char* text, size_t len) : p(text), end(text + len) {}
+    static bool ws(unsigned char c) { return c == ' ' || (c >= 9 && c <= 13); }
+    bool next(const char** b, const char** e) {
+        while (p < end) {
+            const char* nl = (const char*)memchr(p, '\n', (size_t)(end - p));
+            const char* le = nl ? nl : end;
+            const char* lb = p;
+            p = nl ? nl + 1 : end;
+            while (lb < le && ws((unsigned char)*lb)) ++lb;
+            while (le > lb && ws((unsigned char)le[-1])) --le;
+            if (le > lb && *lb != ';') {  // filter(|l| !l.is_empty() && !l.starts_with(';'))
+                *b = lb;
+                *e = le;
+                return true;
+            }
+        }
+        return false;
+    }
+};
+
+// regex `tax=([^;]+);` -- leftmost match (parser.rs:50)
+static bool capture_tax(const char* b, const char* e, std::string* out) {
+    static const char pat[] = "tax=";
+    const char* from = b;
+    while (true) {
+        const char* p = std::search(from, e, pat, pat + 4);
+        if (p == e) return false;
+        const char* s = p + 4;
+        const char* q = s;
+        while (q < e && *q != ';') ++q;
+        if (q > s && q < e) {
+            out->assign(s, q);
+            return true;
+        }
+        from = p + 1;
+    }
+}
+
+// ---- Tree (tree.rs:36-43) in flat form --------------------------------------------------------------------------
+struct Tree {
+    size_t num_tips = 0;
+    std::vector<std::string> lineages;  // sorted (tree.rs:128-131)
+    std::vector<u64> seq_off;           // sorted sequences, 4-bit codes
+    std::vector<u8> seq_codes;
+    std::vector<u64> csr_off;  // k_mer_map (tree.rs:41): 65537 offsets
+    std::vector<u32> csr_ids;
+    std::unordered_map<u64, std::vector<u32>> seq_hash;  // sequences (tree.rs:40): hash of codes -> ids, verified on lookup
+    // Inner / Taxon (and non-leaf Sequence) nodes, BFS order, children contiguous
+    std::vector<u32> node_lo, node_hi, child_first, child_count;
+    std::vector<u8> node_type;
+    std::vector<u8> ref_levels;
+
+    static u64 hash_bytes(const u8* p, size_t n) {
+        u64 h = 0x9E3779B97F4A7C15ull ^ (n * 0xff51afd7ed558ccdull);
+        size_t i = 0;
+        for (; i + 8 <= n; i += 8) {
+            u64 w;
+            memcpy(&w, p + i, 8);
+            h = (h ^ w) * 0x9FB21C651E98DF25ull;
+            h ^= h >> 29;
+        }
+        u64 tail = 0;
+        for (size_t j = 0; i + j < n; ++j) tail |= (u64)p[i + j] << (8 * j);
+        h = (h ^ tail) * 0xD6E8FEB86659FD93ull;
+        return h ^ (h >> 32);
+    }
+
+    // tree.sequences.get(seq) (raxtax.rs:42)
+    void exact(const u8* seq, size_t len, std::vector<u32>* out) const {
+        out->clear();
+        auto it = seq_hash.find(hash_bytes(seq, len));
+        if (it == seq_hash.end()) return;
+        for (u32 id : it->second) {
+            size_t l = (size_t)(seq_off[id + 1] - seq_off[id]);
+            if (l == len && (len == 0 || memcmp(seq_codes.data() + seq_off[id], seq, len) == 0)) out->push_back(id);
+        }
+    }
+};
+
+struct BNode {  // build-time node (tree.rs:189-194)
+    std::string label;
+    u32 lo, hi;
+    u8 type;  // 0 Inner, 1 Taxon, 2 Sequence
+    std::vector<u32> children;  // materialised children only
+    bool trailing_seq = false;  // the last child is an implicit (childless) Sequence leaf labelled like this node
+};
+
+static inline int two_bit(u8 c) {  // utils.rs:17-25
+    switch (c) {
+        case 1: return 0;
+        case 2: return 1;
+        case 4: return 2;
+        case 8: return 3;
+        default: return -1;
+    }
+}
+
+template <typename F>
+static inline void for_each_kmer(const u8* s, size_t n, F&& f) {  // windows(8) with the None-on-ambiguity fold (utils.rs:29-38)
+    u32 val = 0, run = 0;
+    for (size_t i = 0; i < n; ++i) {
+        int t = two_bit(s[i]);
+        if (t < 0) {
+            run = 0;
+            continue;
+        }
+        val = ((val << 2) | (u32)t) & 0xFFFFu;
+        if (++run >= 8) f((u16)val);
+    }
+}
+
+// Tree::new (tree.rs:47-140)
+static std::unique_ptr<Tree> tree_new(std::vector<std::string> lineages, const u64* seq_off, const u8* codes) {
+    const size_t n = lineages.size();
+    if (n > 0xFFFFFFFFull)
+        throw Error("Too many database sequences to run with 32-bit indices!");  // tree.rs:24-31
+    auto tree = std::make_unique<Tree>();
+    std::vector<u32> order(n);
+    std::iota(order.begin(), order.end(), 0u);
+    std::stable_sort(order.begin(), order.end(), [&](u32 a, u32 b) { return lineages[a].compare(lineages[b]) < 0; });  // tree.rs:54
+
+    std::vector<BNode> nodes;
+    nodes.reserve(n / 2 + 16);
+    nodes.push_back(BNode{"root", 0, 1, 0, {}, false});
+    size_t confidence_idx = 0;
+    tree->seq_off.assign(n + 1, 0);
+    tree->ref_levels.resize(n);
+    {
+        u64 total = 0;
+        for (size_t i = 0; i < n; ++i) total += seq_off[order[i] + 1] - seq_off[order[i]];
+        tree->seq_codes.resize(total);
+    }
+    std::vector<u32> kcount(65537, 0), last(65536, 0xFFFFFFFFu);
+    std::vector<std::string> levels;
+    u64 wpos = 0;
+    for (size_t idx = 0; idx < n; ++idx) {  // tree.rs:56-126
+        const std::string& lineage = lineages[order[idx]];
+        levels.clear();
+        {
+            size_t start = 0;
+            while (true) {
+                size_t p = lineage.find(',', start);
+                if (p == std::string::npos) {
+                    levels.emplace_back(lineage, start);
+                    break;
+                }
+                levels.emplace_back(lineage, start, p - start);
+                start = p + 1;
+            }
+        }
+        if (levels.size() > 255) throw Error("lineage with more than 255 ranks");
+        tree->ref_levels[idx] = (u8)levels.size();
+        const size_t last_level = levels.size() - 1;
+        u32 cur = 0;
+        for (size_t level = 0; level < levels.size(); ++level) {
+            const std::string& label = levels[level];
+            const u8 nt = level == last_level ? 1 : 0;
+            BNode& c = nodes[cur];
+            bool need_new = true;
+            u32 next = 0;
+            if (c.trailing_seq) {  // last child is the Sequence leaf carrying this node's own label (tree.rs:102-106)
+                if (c.label == label) {
+                    // degenerate lineage (a rank repeats its parent's label): the reference walks INTO the Sequence node
+                    BNode s{c.label, c.hi - 1, c.hi, 2, {}, false};
+                    next = (u32)nodes.size();
+                    nodes.push_back(std::move(s));
+                    nodes[cur].children.push_back(next);
+                    nodes[cur].trailing_seq = false;
+                    need_new = false;
+                }
+            } else if (!c.children.empty()) {
+                next = c.children.back();
+                if (nodes[next].label == label) need_new = false;
+            }
+            if (need_new) {
+                next = (u32)nodes.size();
+                nodes.push_back(BNode{label, (u32)confidence_idx, (u32)confidence_idx + 1, nt, {}, false});
+                nodes[cur].children.push_back(next);
+                nodes[cur].trailing_seq = false;
+            }
+            nodes[cur].hi = (u32)confidence_idx + 1;
+            if (level == last_level) confidence_idx += 1;
+            cur = next;
+        }
+        nodes[cur].trailing_seq = true;  // add_child(Sequence(label, ci-1)) (tree.rs:102-106)
+        nodes[cur].hi = (u32)confidence_idx;  // tree.rs:107
+
+        const u64 o = seq_off[order[idx]], l = seq_off[order[idx] + 1] - o;
+        memcpy(tree->seq_codes.data() + wpos, codes + o, l);
+        tree->seq_off[idx] = wpos;
+        tree->seq_hash[Tree::hash_bytes(codes + o, l)].push_back((u32)idx);  // tree.rs:109-112
+        for_each_kmer(codes + o, l, [&](u16 k) {                             // tree.rs:114-123 (+ unique, 134-137)
+            if (last[k] != (u32)idx) {
+                last[k] = (u32)idx;
+                kcount[k + 1]++;
+            }
+        });
+        wpos += l;
+    }
+    tree->seq_off[n] = wpos;
+    nodes[0].hi = (u32)confidence_idx;  // tree.rs:127
+    tree->num_tips = confidence_idx;    // tree.rs:138
+    tree->lineages.resize(n);
+    for (size_t i = 0; i < n; ++i) tree->lineages[i] = std::move(lineages[order[i]]);
+
+    // k_mer_map as CSR: second pass fills the lists (ids ascend, duplicates were skipped)
+    tree->csr_off.assign(65537, 0);
+    for (u32 k = 0; k < 65536; ++k) tree->csr_off[k + 1] = tree->csr_off[k] + kcount[k + 1];
+    tree->csr_ids.resize(tree->csr_off[65536]);
+    {
+        std::vector<u64> pos(tree->csr_off.begin(), tree->csr_off.end() - 1);
+        std::fill(last.begin(), last.end(), 0xFFFFFFFFu);
+        for (size_t idx = 0; idx < n; ++idx) {
+            const u8* s = tree->seq_codes.data() + tree->seq_off[idx];
+            for_each_kmer(s, (size_t)(tree->seq_off[idx + 1] - tree->seq_off[idx]), [&](u16 k) {
+                if (last[k] != (u32)idx) {
+                    last[k] = (u32)idx;
+                    tree->csr_ids[pos[k]++] = (u32)idx;
+                }
+            });
+        }
+    }
+
+    // flatten: BFS numbering, children contiguous.  Implicit Sequence leaves are dropped: they can neither be emitted
+    // nor change a decision of Lineage::eval_recurse (lineage.rs:119-179) because their parent is never Inner.
+    const size_t nn = nodes.size();
+    std::vector<u32> bfs;
+    bfs.reserve(nn);
+    bfs.push_back(0);
+    tree->node_lo.reserve(nn);
+    for (size_t head = 0; head < bfs.size(); ++head) {
+        const BNode& b = nodes[bfs[head]];
+        if (b.type == 0 && b.trailing_seq) throw Error("internal: Inner node with a Sequence child");
+        tree->node_lo.push_back(b.lo);
+        tree->node_hi.push_back(b.hi);
+        tree->node_type.push_back(b.type);
+        tree->child_first.push_back(b.children.empty() ? 0u : (u32)bfs.size());
+        tree->child_count.push_back((u32)b.children.size());
+        for (u32 c : b.children) bfs.push_back(c);
+    }
+    return tree;
+}
+
+// parser.rs:46-105
+static std::unique_ptr<Tree> parse_reference_fasta_str(const char* text, size_t len) {
+    if (len == 0) throw Error("File is empty");
+    LineReader lr(text, len);
+    const char *b, *e;
+    std::vector<std::string> labels;
+    std::vector<u64> off{0};
+    std::vector<u8> codes;
+    bool first = true, have_current = false;
+    u64 cur_start = 0;
+    while (lr.next(&b, &e)) {
+        if (first) {
+            if (*b != '>') throw Error("Not a valid FASTA file");
+            first = false;
+        }
+        if (*b == '>') {
+            std::string lineage;
+            if (!capture_tax(b + 1, e, &lineage))
+                throw Error("Unexpected taxonomical annotation detected in label " + std::string(b + 1, e));
+            labels.push_back(std::move(lineage));
+            if (codes.size() > cur_start) {  // !current_sequence.is_empty()
+                off.push_back(codes.size());
+                cur_start = codes.size();
+            }
+            have_current = true;
+        } else {
+            for (const char* p = b; p < e; ++p) codes.push_back(map_dna_char(*p));
+        }
+    }
+    if (first) throw Error("Not a valid FASTA file");  // the reference indexes lines[0] and panics on an all-blank file
+    (void)have_current;
+    off.push_back(codes.size());  // sequences.push(current_sequence)
+    if (labels.size() != off.size() - 1) throw Error("Number of sequences does not match number of labels");
+    return tree_new(std::move(labels), off.data(), codes.data());
+}
+
+struct Queries {
+    std::vector<std::string> labels;
+    std::vector<u64> off;
+    std::vector<u8> codes;
+    size_t size() const { return labels.size(); }
+};
+
+// parser.rs:117-154 (queries_to_skip is applied by the caller that owns the checkpoint)
+static std::unique_ptr<Queries> parse_query_fasta_str(const char* text, size_t len) {
+    if (len == 0) throw Error("File is empty");
+    LineReader lr(text, len);
+    const char *b, *e;
+    auto q = std::make_unique<Queries>();
+    q->off.push_back(0);
+    bool first = true;
+    std::string cur_label;
+    u64 cur_start = 0;
+    while (lr.next(&b, &e)) {
+        if (first) {
+            if (*b != '>') throw Error("Not a valid FASTA file");
+            first = false;
+        }
+        if (*b == '>') {
+            if (q->codes.size() > cur_start) {  // push the finished record; empty records are silently merged (parser.rs:138-141)
+                q->labels.push_back(cur_label);
+                q->off.push_back(q->codes.size());
+                cur_start = q->codes.size();
+            }
+            cur_label.assign(b + 1, e);
+        } else {
+            for (const char* p = b; p < e; ++p) q->codes.push_back(map_dna_char(*p));
+        }
+    }
+    if (first) throw Error("Not a valid FASTA file");
+    q->labels.push_back(cur_label);  // queries.push(current_query)
+    q->off.push_back(q->codes.size());
+    return q;
+}
+
+// ---- formatting (lineage.rs:17-48, utils.rs:62-89) ------------------------------------------------------------------
+static void append_fixed(std::string& s, double v, int prec) {
+    char buf[64];
+    int n = snprintf(buf, sizeof buf, "%.*f", prec, v);
+    s.append(buf, (size_t)n);
+}
+
+struct ResultView {
+    const std::string* lineage;
+    const double* conf;
+    u32 n_levels;
+    double local, global;
+};
+
+static void output_string(std::string& s, const std::string& label, const ResultView& r) {  // lineage.rs:17-30
+    s += label;
+    s += '\t';
+    s += *r.lineage;
+    s += '\t';
+    for (u32 i = 0; i < r.n_levels; ++i) {
+        if (i) s += ',';
+        append_fixed(s, r.conf[i], 2);
+    }
+    s += '\t';
+    append_fixed(s, r.local, 5);
+    s += '\t';
+    append_fixed(s, r.global, 5);
+}
+
+static void tsv_string(std::string& s, const std::string& label, const ResultView& r, const std::string& sequence) {  // lineage.rs:32-48
+    s += label;
+    s += '\t';
+    // itertools::interleave(lineage.split(','), confidences): alternate while both last, then drain the rest
+    const std::string& lin = *r.lineage;
+    size_t start = 0;
+    bool lin_done = false;
+    u32 ci = 0;
+    bool first = true, take_lin = true;
+    while (!lin_done || ci < r.n_levels) {
+        bool use_lin = take_lin ? !lin_done : !(ci < r.n_levels);
+        if (!first) s += '\t';
+        first = false;
+        if (use_lin) {
+            size_t p = lin.find(',', start);
+            if (p == std::string::npos) {
+                s.append(lin, start, std::string::npos);
+                lin_done = true;
+            } else {
+                s.append(lin, start, p - start);
+                start = p + 1;
+            }
+        } else {
+            append_fixed(s, r.conf[ci++], 2);
+        }
+        take_lin = !take_lin;
+    }
+    s += '\t';
+    append_fixed(s, r.local, 5);
+    s += '\t';
+    append_fixed(s, r.global, 5);
+    s += '\t';
+    s += sequence;
+}
+
+static std::string decompress_sequence(const u8* seq, size_t len) {  // utils.rs:70-81
+    std::string s(len, '-');
+    for (size_t i = 0; i < len; ++i) {
+        switch (seq[i]) {
+            case 1: s[i] = 'A'; break;
+            case 2: s[i] = 'C'; break;
+            case 4: s[i] = 'G'; break;
+            case 8: s[i] = 'T'; break;
+            default: break;
+        }
+    }
+    return s;
+}
+
+}  // namespace raxtax
+
+// =================================================================================================================
+// C ABI
+// =================================================================================================================
+using namespace raxtax;
+
+struct rxh_tree {
+    std::unique_ptr<Tree> t;
+};
+struct rxh_queries {
+    std::unique_ptr<Queries> q;
+};
+
+static thread_local std::string g_err;
+
+#define RXH_API extern "C" __attribute__((visibility("default")))
+
+RXH_API const char* rxh_last_error(void) { return g_err.c_str(); }
+
+RXH_API rxh_tree* rxh_tree_from_fasta(const char* text, size_t len) {
+    try {
+        auto h = new rxh_tree();
+        h->t = parse_reference_fasta_str(text, len);
+        return h;
+    } catch (const std::exception& e) {
+        g_err = e.what();
+        return nullptr;
+    }
+}
+
+static std::vector<std::string> split_blob(const char* blob, size_t blob_len, size_t n) {
+    std::vector<std::string> out;
+    out.reserve(n);
+    const char* p = blob;
+    const char* end = blob + blob_len;
+    for (size_t i = 0; i < n; ++i) {
+        const char* nl = p < end ? (const char*)memchr(p, '\n', (size_t)(end - p)) : nullptr;
+        const char* e = nl ? nl : end;
+        out.emplace_back(p, e);
+        p = nl ? nl + 1 : end;
+    }
+    return out;
+}
+
+RXH_API rxh_tree* rxh_tree_new(size_t n, const char* lineage_blob, size_t blob_len, const uint64_t* seq_offsets, const uint8_t* seq_codes) {
+    try {
+        auto h = new rxh_tree();
+        h->t = tree_new(split_blob(lineage_blob, blob_len, n), seq_offsets, seq_codes);
+        return h;
+    } catch (const std::exception& e) {
+        g_err = e.what();
+        return nullptr;
+    }
+}
+
+RXH_API void rxh_tree_free(rxh_tree* t) { delete t; }
+RXH_API size_t rxh_tree_num_tips(const rxh_tree* t) { return t->t->num_tips; }
+RXH_API const char* rxh_tree_lineage(const rxh_tree* t, size_t i) { return t->t->lineages[i].c_str(); }
+RXH_API void rxh_tree_csr(const rxh_tree* t, const uint64_t** offsets, const uint32_t** ids) {
+    *offsets = t->t->csr_off.data();
+    *ids = t->t->csr_ids.data();
+}
+RXH_API size_t rxh_tree_exact(const rxh_tree* t, const uint8_t* seq, size_t len, uint32_t* out, size_t cap) {
+    std::vector<u32> v;
+    t->t->exact(seq, len, &v);
+    for (size_t i = 0; i < v.size() && i < cap; ++i) out[i] = v[i];
+    return v.size();
+}
+
+RXH_API int rxh_tree_index_desc(const rxh_tree* h, rtx_index_desc* d) {
+    const Tree& t = *h->t;
+    memset(d, 0, sizeof *d);
+    d->n_refs = t.num_tips;
+    d->csr_offsets = t.csr_off.data();
+    d->csr_ids = t.csr_ids.data();
+    d->n_nodes = (uint32_t)t.node_lo.size();
+    d->node_lo = t.node_lo.data();
+    d->node_hi = t.node_hi.data();
+    d->node_type = t.node_type.data();
+    d->child_first = t.child_first.data();
+    d->child_count = t.child_count.data();
+    d->ref_levels = t.ref_levels.data();
+    d->ref_shard_begin = 0;
+    d->ref_shard_end = 0;
+    return 0;
+}
+
+RXH_API int rxh_tree_upload(const rxh_tree* t, rtx_ctx* ctx, uint64_t shard_begin, uint64_t shard_end) {
+    rtx_index_desc d;
+    rxh_tree_index_desc(t, &d);
+    d.ref_shard_begin = shard_begin;
+    d.ref_shard_end = shard_end;
+    int rc = rtx_index_upload(ctx, &d);
+    if (rc) g_err = rtx_last_error(ctx);
+    return rc;
+}
+
+RXH_API rxh_queries* rxh_queries_from_fasta(const char* text, size_t len) {
+    try {
+        auto h = new rxh_queries();
+        h->q = parse_query_fasta_str(text, len);
+        return h;
+    } catch (const std::exception& e) {
+        g_err = e.what();
+        return nullptr;
+    }
+}
+
+RXH_API rxh_queries* rxh_queries_new(size_t n, const char* label_blob, size_t blob_len, const uint64_t* seq_offsets, const uint8_t* seq_codes) {
+    try {
+        auto h = new rxh_queries();
+        h->q = std::make_unique<Queries>();
+        h->q->labels = split_blob(label_blob, blob_len, n);
+        h->q->off.assign(seq_offsets, seq_offsets + n + 1);
+        const u64 base = n ? seq_offsets[0] : 0;
+        for (auto& o : h->q->off) o -= base;
+        h->q->codes.assign(seq_codes + base, seq_codes + base + h->q->off[n]);
+        return h;
+    } catch (const std::exception& e) {
+        g_err = e.what();
+        return nullptr;
+    }
+}
+RXH_API void rxh_queries_free(rxh_queries* q) { delete q; }
+RXH_API size_t rxh_queries_len(const rxh_queries* q) { return q->q->size(); }
+RXH_API const char* rxh_queries_label(const rxh_queries* q, size_t i) { return q->q->labels[i].c_str(); }
+RXH_API void rxh_queries_arrays(const rxh_queries* q, const uint64_t** seq_offsets, const uint8_t** seq_codes) {
+    *seq_offsets = q->q->off.data();
+    *seq_codes = q->q->codes.data();
+}
+
+RXH_API uint64_t rxh_exact_batch(const rxh_tree* t, size_t n, const uint64_t* seq_offsets, const uint8_t* seq_codes, uint32_t* exact_offsets,
+                                 uint32_t* exact_ids, uint64_t cap) {
+    std::vector<u32> v;
+    u64 total = 0;
+    for (size_t q = 0; q < n; ++q) {
+        exact_offsets[q] = (u32)total;
+        t->t->exact(seq_codes + seq_offsets[q], (size_t)(seq_offsets[q + 1] - seq_offsets[q]), &v);
+        for (u32 id : v) {
+            if (total < cap) exact_ids[total] = id;
+            ++total;
+        }
+    }
+    exact_offsets[n] = (u32)total;
+    return total;
+}
+
+// raxtax::raxtax (raxtax.rs:14-97)
+RXH_API int rxh_raxtax(rtx_ctx* ctx, const rxh_queries* queries, const rxh_tree* tree_h, int skip_exact_matches, int raw_confidence,
+                       size_t chunk_size, rxh_sender sender, void* sender_user, int tsv, rxh_logger logger, void* logger_user, int* warnings) {
+    try {
+        const Tree& tree = *tree_h->t;
+        const Queries& qs = *queries->q;
+        const size_t nq = qs.size();
+        if (warnings) *warnings = 0;
+        if (chunk_size == 0) chunk_size = nq ? nq : 1;
+        const u32 ML = rtx_index_max_levels(ctx);
+        if (rtx_index_n_refs(ctx) != tree.num_tips) throw Error("the context's index does not belong to this tree");
+        std::vector<u32> exact_off, exact_ids, first_ref, result_begin;
+        std::vector<u16> n_kmers;
+        std::vector<u8> n_levels;
+        std::vector<double> conf, local, global;
+        std::vector<u32> ex;
+        std::string primary, tsv_out, msg;
+        bool warned = false;
+        for (size_t c0 = 0; c0 < nq; c0 += chunk_size) {
+            const size_t cn = std::min(chunk_size, nq - c0);
+            exact_off.assign(cn + 1, 0);
+            exact_ids.clear();
+            for (size_t i = 0; i < cn; ++i) {  // tree.sequences.get(query_sequence) (raxtax.rs:42)
+                const size_t q = c0 + i;
+                tree.exact(qs.codes.data() + qs.off[q], (size_t)(qs.off[q + 1] - qs.off[q]), &ex);
+                exact_ids.insert(exact_ids.end(), ex.begin(), ex.end());
+                exact_off[i + 1] = (u32)exact_ids.size();
+                if (!skip_exact_matches) {  // raxtax.rs:43-53
+                    bool all_equal = true;
+                    std::string first_parent;
+                    for (size_t j = 0; j < ex.size(); ++j) {
+                        const std::string& l = tree.lineages[ex[j]];
+                        if (logger) {
+                            msg = "Exact sequence match for query " + qs.labels[q] + ": " + l;
+                            logger(logger_user, 3, msg.c_str());
+                        }
+                        size_t p = l.rfind(',');
+                        if (p == std::string::npos)
+                            throw Error("called `Option::unwrap()` on a `None` value: lineage without ',' (raxtax.rs:49)");
+                        if (j == 0) first_parent.assign(l, 0, p);
+                        else if (l.compare(0, p, first_parent) != 0 || p != first_parent.size()) all_equal = false;
+                    }
+                    if (!all_equal) {
+                        if (logger) {
+                            msg = "Exact matches for " + qs.labels[q] + " differ above the leafs of the lineage tree!";
+                            logger(logger_user, 2, msg.c_str());
+                        }
+                        warned = true;
+                    }
+                }
+            }
+            rtx_batch batch{};
+            batch.n_queries = (u32)cn;
+            batch.seq_offsets = qs.off.data() + c0;
+            batch.seq_codes = qs.codes.data();
+            batch.exact_offsets = exact_off.data();
+            batch.exact_ids = exact_ids.empty() ? nullptr : exact_ids.data();
+            batch.flags = (skip_exact_matches ? RTX_SKIP_EXACT_MATCHES : 0u) | (raw_confidence ? RTX_RAW_CONFIDENCE : 0u);
+            // the device batch API wants seq_codes to be the base the offsets index into
+            rtx_results res{};
+            n_kmers.resize(cn);
+            result_begin.resize(cn + 1);
+            global.resize(cn);
+            size_t cap = std::max<size_t>(first_ref.size(), cn * 4 + 64);
+            while (true) {
+                first_ref.resize(cap);
+                n_levels.resize(cap);
+                conf.resize(cap * ML);
+                local.resize(cap);
+                res = rtx_results{};
+                res.n_kmers = n_kmers.data();
+                res.result_begin = result_begin.data();
+                res.global_signal = global.data();
+                res.result_capacity = cap;
+                res.first_ref = first_ref.data();
+                res.n_levels = n_levels.data();
+                res.confidence = conf.data();
+                res.local_signal = local.data();
+                int rc = rtx_classify_batch(ctx, &batch, &res);
+                if (rc == RTX_ERR_INVALID && res.n_results > cap) {
+                    cap = res.n_results + 64;
+                    continue;
+                }
+                if (rc) throw Error(std::string("rtx_classify_batch: ") + rtx_last_error(ctx));
+                break;
+            }
+            for (size_t i = 0; i < cn; ++i) {  // utils::get_results / get_results_tsv (raxtax.rs:85-87)
+                const size_t q = c0 + i;
+                primary.clear();
+                tsv_out.clear();
+                std::string seq;
+                if (tsv) seq = decompress_sequence(qs.codes.data() + qs.off[q], (size_t)(qs.off[q + 1] - qs.off[q]));
+                for (u32 r = result_begin[i]; r < result_begin[i + 1]; ++r) {
+                    ResultView rv{&tree.lineages[first_ref[r]], conf.data() + (size_t)r * ML, n_levels[r], local[r], global[i]};
+                    if (r != result_begin[i]) primary += '\n';
+                    output_string(primary, qs.labels[q], rv);
+                    if (tsv) {
+                        if (r != result_begin[i]) tsv_out += '\n';
+                        tsv_string(tsv_out, qs.labels[q], rv, seq);
+                    }
+                }
+                if (sender && sender(sender_user, qs.labels[q].c_str(), primary.c_str(), tsv ? tsv_out.c_str() : nullptr) != 0)
+                    throw Error("sending on a disconnected channel (raxtax.rs:87)");
+            }
+        }
+        if (warnings) *warnings = warned ? 1 : 0;
+        return 0;
+    } catch (const std::exception& e) {
+        g_err = e.what();
+        return -1;
+    }
+}

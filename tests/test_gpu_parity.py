@@ -1,0 +1,237 @@
+"""GPU parity tests (run on the B200 box with `-m gpu`): the CUDA path, called through the C ABI, against the
+CPU oracle on the same seeded inputs, against the committed golden fixtures and through size-independent properties."""
+import os
+
+import numpy as np
+import pytest
+
+from raxtax_b200 import capi, synth
+from tests import parity
+from tests.test_oracle_kats import KMER_KAT_CODES, KMER_KAT_EXPECTED, REF_FASTA_KMERS, REF_FASTA_STR_PARSER
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = capi.Context(0)
+    yield c
+    c.close()
+
+
+def _pack(orc, seqs):
+    return orc.pack_sequences([np.asarray(s, np.uint8) for s in seqs])
+
+
+def _run_both(orc, ctx, ds_or_tuple, skip=False, raw=False, sub_batch=0, variant=capi.RTX_HITCOUNT_BITROWS, threads=4):
+    """-> (oracle dict, device ClassifyOutput, oracle tree, host tree)"""
+    if isinstance(ds_or_tuple, tuple):
+        lineages, ref_off, ref_codes, q_off, q_codes = ds_or_tuple
+    else:
+        ds = ds_or_tuple
+        lineages, ref_off, ref_codes, q_off, q_codes = ds.ref_lineages, ds.ref_off, ds.ref_codes, ds.query_off, ds.query_codes
+    seqs = [ref_codes[int(ref_off[i]): int(ref_off[i + 1])] for i in range(len(lineages))]
+    ot = orc.Tree.new(lineages, seqs)
+    ht = capi.Tree.new(lineages, ref_off, ref_codes)
+    ctx.set_option(capi.RTX_OPT_KEEP_CSR, 1 if variant == capi.RTX_HITCOUNT_CSR else 0)
+    ctx.set_option(capi.RTX_OPT_HITCOUNT_VARIANT, variant)
+    ctx.set_option(capi.RTX_OPT_SUB_BATCH, sub_batch)
+    ctx.upload_tree(ht)
+    eo, eids = ht.exact_batch(q_off, q_codes)
+    dev = ctx.classify(q_off, q_codes, eo, eids, skip_exact=skip, raw_conf=raw, taps=("counts", "hist", "kmers"))
+    o = ot.classify(q_off, q_codes, skip_exact=skip, raw_conf=raw, threads=threads, chunk_size=16, want_counts=True, want_probs=True,
+                    want_kmers=True)
+    ctx.set_option(capi.RTX_OPT_HITCOUNT_VARIANT, capi.RTX_HITCOUNT_BITROWS)
+    ctx.set_option(capi.RTX_OPT_SUB_BATCH, 0)
+    return o, dev, ot, ht
+
+
+def _assert_integer_parity(o, dev, nq):
+    assert np.array_equal(o["K"], dev.n_kmers)
+    for q in range(nq):
+        K = int(o["K"][q])
+        assert np.array_equal(o["kmers"][q, :K], dev.kmers[q, :K]), f"k-mer list of query {q}"
+    assert np.array_equal(o["counts"], dev.counts), "hit counts"
+    for q in range(nq):
+        K = int(o["K"][q])
+        assert np.array_equal(parity.hist_from_counts(o["counts"][q], K), dev.hist[q, : K + 1]), f"histogram of query {q}"
+
+
+def _assert_result_parity(o, dev, ot, nq, max_tolerated_frac=0.05):
+    checker = parity.TolerantChecker(ot.flatten(), ot.num_tips)
+    ok, tol, bad = parity.compare_batch(o, dev, nq, checker, o["probs"])
+    assert not bad, f"{len(bad)} queries differ beyond tie/boundary tolerance, first: {bad[:5]}: oracle={o['results'].for_query(bad[0])} device={dev.for_query(bad[0])}"
+    assert tol <= max(1, int(max_tolerated_frac * nq)), f"{tol} of {nq} queries needed tie/boundary tolerance"
+    return ok, tol
+
+
+# ---- reference KATs through the CUDA path ---------------------------------------------------------------------------
+def test_kmer_kat_on_device(oracle, ctx):  # utils.rs:245-263
+    ht = capi.Tree.from_fasta(REF_FASTA_STR_PARSER)
+    ctx.upload_tree(ht)
+    off, codes = _pack(oracle, [KMER_KAT_CODES, [1] * 7, [], [8] * 30, [1] * 7 + [15] + [1] * 7])
+    dev = ctx.classify(off, codes, taps=("kmers",))
+    assert list(dev.n_kmers) == [8, 0, 0, 1, 0]
+    assert list(dev.kmers[0, :8]) == KMER_KAT_EXPECTED
+    assert dev.kmers[3, 0] == 0xFFFF
+
+
+@pytest.mark.parametrize("fasta", [REF_FASTA_STR_PARSER, REF_FASTA_KMERS])
+def test_parser_kat_databases_classified_like_oracle(oracle, ctx, fasta):  # parser.rs:166-299 databases, self-queries
+    ot = oracle.Tree.from_fasta(fasta)
+    seqs = [ot.sequence(i) for i in range(ot.num_tips)] + [oracle.map_dna("ATACGCTTTGGGTA"), oracle.map_dna("NNNNNNNNNN")]
+    q_off, q_codes = _pack(oracle, seqs)
+    r_off, r_codes = _pack(oracle, [ot.sequence(i) for i in range(ot.num_tips)])
+    for skip, raw in [(False, False), (True, False), (False, True)]:
+        o, dev, ot2, _ = _run_both(oracle, ctx, (ot.lineages, r_off, r_codes, q_off, q_codes), skip=skip, raw=raw)
+        _assert_integer_parity(o, dev, len(seqs))
+        _assert_result_parity(o, dev, ot2, len(seqs), max_tolerated_frac=1.0)
+
+
+# ---- seeded synthetic data ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("skip,raw", [(False, False), (True, False), (False, True)])
+def test_tiny_dataset_parity(oracle, ctx, skip, raw):
+    ds = synth.generate("tiny", measure=False)
+    o, dev, ot, _ = _run_both(oracle, ctx, ds, skip=skip, raw=raw)
+    _assert_integer_parity(o, dev, ds.n_queries)
+    _assert_result_parity(o, dev, ot, ds.n_queries)
+
+
+def test_small_dataset_parity_and_text_output(oracle, ctx):
+    ds = synth.generate("small", measure=False)
+    o, dev, ot, ht = _run_both(oracle, ctx, ds)
+    _assert_integer_parity(o, dev, ds.n_queries)
+    ok, tol = _assert_result_parity(o, dev, ot, ds.n_queries)
+    # formatted raxtax.out / raxtax.tsv lines through the host driver vs the oracle's formatting of its own results
+    qs = capi.Queries.new(ds.query_labels, ds.query_off, ds.query_codes)
+    sent, logs, _ = capi.raxtax(ctx, qs, ht, chunk_size=100, tsv=True)
+    assert [s[0] for s in sent] == ds.query_labels
+    exp_primary = oracle.format_results(ot, o["results"], ds.query_labels).split("\n")
+    exp_tsv = oracle.format_results(ot, o["results"], ds.query_labels, ds.query_off, ds.query_codes, tsv=True).split("\n")
+    got_primary = [l for s in sent for l in s[1].split("\n")]
+    got_tsv = [l for s in sent for l in s[2].split("\n")]
+    if tol == 0:
+        assert got_primary == exp_primary
+        assert got_tsv == exp_tsv
+    else:
+        same = sum(a == b for a, b in zip(got_primary, exp_primary))
+        assert same >= 0.95 * len(exp_primary)
+    # log lines: one Info line per exact match (raxtax.rs:46-48)
+    n_exact = int(o["nexact"].sum())
+    assert sum(1 for lvl, _ in logs if lvl == 3) == n_exact
+
+
+def test_small_dataset_skip_exact_sub_batched(oracle, ctx):
+    ds = synth.generate("small", measure=False)
+    o, dev, ot, _ = _run_both(oracle, ctx, ds, skip=True, sub_batch=37)
+    _assert_integer_parity(o, dev, ds.n_queries)
+    _assert_result_parity(o, dev, ot, ds.n_queries)
+
+
+def test_csr_variant_matches_bitrows(oracle, ctx):
+    ds = synth.generate("tiny", measure=False)
+    o, dev, ot, _ = _run_both(oracle, ctx, ds, variant=capi.RTX_HITCOUNT_CSR)
+    _assert_integer_parity(o, dev, ds.n_queries)
+    _assert_result_parity(o, dev, ot, ds.n_queries)
+
+
+def test_16s_like_long_queries(oracle, ctx):
+    ds = synth.generate("x16s", n_refs=1500, n_queries=48, length=1500, kind="16s", seed=77, measure=False)
+    o, dev, ot, _ = _run_both(oracle, ctx, ds, skip=True)
+    assert int(o["K"].max()) > 1023  # needs the 11-plane kernel
+    _assert_integer_parity(o, dev, ds.n_queries)
+    _assert_result_parity(o, dev, ot, ds.n_queries)
+
+
+# ---- real data: golden sample of the reference's example file, used as its own database -------------------
+def test_diptera_sample_self_classification(oracle, ctx):
+    text = open(os.path.join(GOLDEN, "diptera_sample.fasta")).read()
+    ot = oracle.Tree.from_fasta(text)
+    ht = capi.Tree.from_fasta(text)
+    labels, q_off, q_codes = oracle.parse_queries(text)
+    ctx.upload_tree(ht)
+    for skip in (False, True):
+        eo, eids = ht.exact_batch(q_off, q_codes)
+        dev = ctx.classify(q_off, q_codes, eo, eids, skip_exact=skip, taps=("counts", "hist", "kmers"))
+        o = ot.classify(q_off, q_codes, skip_exact=skip, threads=4, chunk_size=16, want_counts=True, want_probs=True, want_kmers=True)
+        _assert_integer_parity(o, dev, len(labels))
+        _assert_result_parity(o, dev, ot, len(labels))
+        golden = os.path.join(GOLDEN, "diptera_sample.skip.out" if skip else "diptera_sample.default.out")
+        qs = capi.Queries.from_fasta(text)
+        sent, _, _ = capi.raxtax(ctx, qs, ht, skip_exact_matches=skip)
+        got = "\n".join(s[1] for s in sent) + "\n"
+        exp = open(golden).read()
+        same = sum(a == b for a, b in zip(got.split("\n"), exp.split("\n")))
+        assert same >= 0.98 * len(exp.split("\n")), "raxtax.out lines vs golden"
+
+
+# ---- edge cases ---------------------------------------------------------------------------------------------------------
+def test_edge_cases(oracle, ctx):
+    rng = np.random.default_rng(5)
+    base = synth.BASE_CODES[rng.integers(0, 4, 120)]
+    refs = [base.copy() for _ in range(6)]
+    refs[1][50] = synth.BASE_CODES[(int(np.log2(refs[1][50])) + 1) % 4]
+    refs[2] = synth.BASE_CODES[rng.integers(0, 4, 120)]
+    refs[3] = base[:7]  # shorter than one 8-mer: no postings at all
+    refs[4] = np.full(40, 15, np.uint8)  # all N
+    refs[5] = base.copy()  # exact duplicate of ref 0 under another species
+    lineages = ["k,p,a,s1", "k,p,a,s2", "k,q,b,s3", "k,q,b,s4", "k,q,c,s5", "k,r,d,s6"]
+    queries = [base, base[:30], base[:8], base[:7], np.zeros(0, np.uint8), np.full(33, 15, np.uint8),
+               synth.BASE_CODES[rng.integers(0, 4, 64)], refs[1], refs[2][10:90], np.full(20, 1, np.uint8)]
+    r_off, r_codes = _pack(oracle, refs)
+    q_off, q_codes = _pack(oracle, queries)
+    for skip, raw in [(False, False), (True, False), (False, True)]:
+        o, dev, ot, _ = _run_both(oracle, ctx, (lineages, r_off, r_codes, q_off, q_codes), skip=skip, raw=raw)
+        _assert_integer_parity(o, dev, len(queries))
+        _assert_result_parity(o, dev, ot, len(queries), max_tolerated_frac=1.0)
+    # single-reference database
+    o, dev, ot, _ = _run_both(oracle, ctx, (["only,one"], *_pack(oracle, [base]), q_off, q_codes))
+    _assert_integer_parity(o, dev, len(queries))
+    _assert_result_parity(o, dev, ot, len(queries), max_tolerated_frac=1.0)
+    # empty batch
+    dev = ctx.classify(np.zeros(1, np.uint64), np.zeros(0, np.uint8))
+    assert len(dev.first_ref) == 0
+
+
+def test_errors_are_loud(ctx):
+    c2 = capi.Context(0)
+    with pytest.raises(capi.RtxError) as ei:
+        c2.classify(np.array([0, 8], np.uint64), np.ones(8, np.uint8))
+    assert ei.value.code == capi.RTX_ERR_NO_INDEX
+    c2.close()
+    with pytest.raises(capi.RtxError):
+        ctx.upload_index_arrays(0, np.zeros(65537, np.uint64), np.zeros(1, np.uint32), [0], [0], [0], [0], [0], [1])
+
+
+# ---- full-size properties (BASELINE config 2 shape, reduced query count) ---------------------------------------------------
+def test_c2_scale_properties(ctx):
+    ds = synth.generate("c2", n_queries=300, measure=False)
+    ht = capi.Tree.new(ds.ref_lineages, ds.ref_off, ds.ref_codes)
+    ctx.upload_tree(ht)
+    eo, eids = ht.exact_batch(ds.query_off, ds.query_codes)
+    dev = ctx.classify(ds.query_off, ds.query_codes, eo, eids, taps=("counts", "hist", "kmers"))
+    N = ht.num_tips
+    off, ids = ht.csr()
+    lens = (off[1:] - off[:-1]).astype(np.int64)
+    lin = ht.lineages
+    for q in range(ds.n_queries):
+        K = int(dev.n_kmers[q])
+        km = dev.kmers[q, :K]
+        assert np.array_equal(km, synth.kmers_of(ds.query_seq(q)))
+        h = dev.hist[q, : K + 1].astype(np.int64)
+        assert h.sum() == N  # every reference lands in exactly one bin
+        assert (h * np.arange(K + 1)).sum() == lens[km].sum() == dev.counts[q].astype(np.int64).sum()  # checksum of postings
+        res = dev.for_query(q)
+        assert res, "no empty result (raxtax.rs:72)"
+        for fr, conf, local, glob in res:
+            assert len(conf) == lin[fr].count(",") + 1
+            assert np.all(np.diff(conf) <= 1e-12) and 0.0 < conf[-1] <= conf[0] <= 1.0 + 1e-12  # confidences shrink down the lineage
+            assert 0.0 <= glob <= 1.0 and local >= 0.0
+        confs = [tuple(c) for _, c, _, _ in res]
+        assert confs == sorted(confs, reverse=True)  # lineage.rs:93
+        ne = int(eo[q + 1] - eo[q])
+        if ne == 1:  # override (raxtax.rs:73-84)
+            assert len(res) == 1 and res[0][0] == int(eids[eo[q]]) and np.all(res[0][1] == 1.0)
+        if ne >= 1:
+            assert dev.counts[q, eids[eo[q]]] == K  # an exact copy shares every k-mer

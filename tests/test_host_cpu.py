@@ -1,0 +1,181 @@
+"""CPU-side tests (no GPU): the C++ host library against the reference's KATs and against the oracle, and the
+C-ABI surface of both shared libraries (load + every symbol the headers declare; no compute calls)."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from raxtax_b200 import _build, capi, synth
+from tests.test_oracle_kats import KMER_KAT_CODES, REF_FASTA_KMERS, REF_FASTA_STR_PARSER
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _built():
+    _build.build_all()
+
+
+def _header_functions(path):
+    text = open(path).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b((?:rtx|rxh)_[a-z0-9_]+)\s*\(", text)) - {"rxh_sender", "rxh_logger"})
+
+
+def test_device_abi_exports_every_declared_symbol():
+    names = _header_functions(os.path.join(ROOT, "include", "raxtax_b200.h"))
+    assert sorted(names) == sorted(capi.DEVICE_SYMBOLS)
+    lib = C.CDLL(_build.DEVICE_LIB)
+    for n in names:
+        assert hasattr(lib, n), n
+    lib.rtx_abi_version.restype = C.c_int
+    assert lib.rtx_abi_version() == 1
+
+
+def test_host_abi_exports_every_declared_symbol():
+    names = _header_functions(os.path.join(ROOT, "include", "raxtax_host.h"))
+    assert sorted(names) == sorted(capi.HOST_SYMBOLS)
+    lib = capi.host_lib()
+    for n in names:
+        assert hasattr(lib, n), n
+
+
+def test_no_cpu_fallback_without_gpu():
+    """Without a CUDA device the product must fail loudly instead of computing on the CPU."""
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(capi.RtxError) as ei:
+        capi.Context(0)
+    assert ei.value.code == capi.RTX_ERR_NO_DEVICE
+    assert "no CPU fallback" in ei.value.msg
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "raxtax_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h", ".hpp")):
+                src = open(os.path.join(dirpath, f), errors="replace").read()
+                assert "oracle" not in src.lower(), f"{f} mentions the oracle"
+
+
+# ---- reference KATs through the host library --------------------------------------------------------------------
+def test_host_str_parser_kat():  # parser.rs:166-217
+    tree = capi.Tree.from_fasta(REF_FASTA_STR_PARSER)
+    assert list(tree.k_mer_map(0b1_0101_1111_1110)) == [0]
+    assert list(tree.k_mer_map(0b11_0001_1001_1111)) == [1, 4, 5]
+    assert list(tree.k_mer_map(0b110_0111_0011_1010)) == [3]
+    assert tree.num_tips == 6
+    assert tree.lineages[0].endswith("s:Species1") and tree.lineages[5].startswith("p:Phylum2")
+
+
+def test_host_kmers_kat():  # parser.rs:235-299
+    tree = capi.Tree.from_fasta(REF_FASTA_KMERS)
+    assert list(tree.k_mer_map(0b1_0101_0110)) == [0, 4]
+    assert list(tree.k_mer_map(0b101_0101_1010)) == [1, 4]
+    assert list(tree.k_mer_map(0b1111_1100_0000_0001)) == [2, 3]
+
+
+def test_host_query_parser_kat():  # parser.rs:219-233
+    q = capi.Queries.from_fasta(">label1\nACGTWSMKRYBDHVN")
+    off, codes = q.arrays()
+    assert q.labels == ["label1"]
+    assert list(codes) == [1, 2, 4, 8, 9, 6, 3, 12, 5, 10, 14, 13, 11, 7, 15]
+
+
+def test_host_parser_errors():
+    for text, msg in [("", "File is empty"), ("ACGT\n>x;tax=a,b;\nACGT", "Not a valid FASTA"), (">x;tax=a,b;\nACGU", "Unexpected character"),
+                      (">x;taxon=a,b\nACGT", "taxonomical annotation"), (">x;tax=a,b;\n>y;tax=a,c;\nACGT", "does not match")]:
+        with pytest.raises(capi.HostError, match=msg):
+            capi.Tree.from_fasta(text)
+    with pytest.raises(capi.HostError, match="File is empty"):
+        capi.Queries.from_fasta("")
+
+
+def _node_set_oracle(flat):
+    """(lo, hi, type, depth) of the oracle's nodes minus childless Sequence leaves, children order preserved per parent."""
+    keep = [i for i in range(len(flat["lo"])) if not (flat["type"][i] == 2 and flat["nchildren"][i] == 0)]
+    return keep
+
+
+def _compare_tree(orc_tree, host_tree):
+    assert orc_tree.num_tips == host_tree.num_tips
+    assert orc_tree.lineages == host_tree.lineages
+    off_o, ids_o = orc_tree.csr()
+    off_h, ids_h = host_tree.csr()
+    assert np.array_equal(off_o, off_h)
+    assert np.array_equal(ids_o, ids_h)
+    # node structure: rebuild parent/child lists from the BFS arrays and compare with the oracle's pre-order tree
+    ia = host_tree.index_arrays()
+    flat = orc_tree.flatten()
+    keep = _node_set_oracle(flat)
+    assert len(keep) == len(ia["node_lo"])
+    # walk both trees simultaneously
+    o_children = {i: [] for i in range(len(flat["lo"]))}
+    for i in range(1, len(flat["lo"])):
+        o_children[int(flat["parent"][i])].append(i)
+    keepset = set(keep)
+    stack = [(0, 0)]
+    while stack:
+        o, h = stack.pop()
+        assert (int(flat["lo"][o]), int(flat["hi"][o]), int(flat["type"][o])) == (int(ia["node_lo"][h]), int(ia["node_hi"][h]), int(ia["node_type"][h]))
+        oc = [c for c in o_children[o] if c in keepset]
+        cf, cc = int(ia["child_first"][h]), int(ia["child_count"][h])
+        assert len(oc) == cc
+        for j, c in enumerate(oc):
+            stack.append((c, cf + j))
+    # ref_levels
+    assert list(ia["ref_levels"]) == [l.count(",") + 1 for l in host_tree.lineages]
+
+
+def test_host_tree_matches_oracle_on_kat_fastas(oracle):
+    for text in (REF_FASTA_STR_PARSER, REF_FASTA_KMERS):
+        _compare_tree(oracle.Tree.from_fasta(text), capi.Tree.from_fasta(text))
+
+
+def test_host_tree_matches_oracle_variable_depth_and_degenerate(oracle):
+    lineages = [
+        "Animalia,Chordata,Mammalia,Primates,Hominidae,Homo,Homo_sapiens", "Animalia,Chordata,Mammalia,Primates,Hominidae,Pan",
+        "Animalia,Chordata,Mammalia,Carnivora,Canidae,Canis", "Animalia,Chordata,Mammalia,Carnivora,Doggo",
+        "Animalia,Chordata,Mammalia,Mouse", "Animalia,Chordata,Mammalia,Carnivora,Felidae,Felis",
+        "Animalia,Chordata,Mammalia,Carnivora,Felidae,Felis",
+        "A,X", "A,X,X", "A,X,X,Y", "A,B", "A,B,C", "A,B!,C", "A,B-x,C", "Z", "Z", "",
+    ]
+    rng = np.random.default_rng(0)
+    seqs = [synth.BASE_CODES[rng.integers(0, 4, 40)] for _ in lineages]
+    off, codes = oracle.pack_sequences(seqs)
+    _compare_tree(oracle.Tree.new(lineages, seqs), capi.Tree.new(lineages, off, codes))
+
+
+def test_host_tree_matches_oracle_on_synthetic(oracle):
+    ds = synth.generate("tiny")
+    seqs = [ds.ref_seq(i) for i in range(ds.n_refs)]
+    ot = oracle.Tree.new(ds.ref_lineages, seqs)
+    ht = capi.Tree.new(ds.ref_lineages, ds.ref_off, ds.ref_codes)
+    _compare_tree(ot, ht)
+    # exact-match map
+    for q in range(ds.n_queries):
+        s = ds.query_seq(q)
+        assert list(ot.exact(s)) == list(ht.exact(s))
+    eo, eids = ht.exact_batch(ds.query_off, ds.query_codes)
+    assert eo[-1] == len(eids) and eo[-1] > 0
+    # FASTA round trip through both parsers
+    ot2 = oracle.Tree.from_fasta(ds.ref_fasta())
+    ht2 = capi.Tree.from_fasta(ds.ref_fasta())
+    _compare_tree(ot2, ht2)
+    assert ot2.lineages == ot.lineages
+    lab_o, off_o, codes_o = oracle.parse_queries(ds.query_fasta())
+    hq = capi.Queries.from_fasta(ds.query_fasta())
+    off_h, codes_h = hq.arrays()
+    assert lab_o == hq.labels and np.array_equal(off_o, off_h) and np.array_equal(codes_o, codes_h)
+
+
+def test_synth_kmers_match_oracle(oracle):
+    ds = synth.generate("tiny", measure=False)
+    for q in list(range(10)) + [ds.n_queries - 1]:
+        assert np.array_equal(synth.kmers_of(ds.query_seq(q)), oracle.sequence_to_kmers(ds.query_seq(q)))
+    assert list(synth.kmers_of(np.array(KMER_KAT_CODES, np.uint8))) == list(oracle.sequence_to_kmers(KMER_KAT_CODES))

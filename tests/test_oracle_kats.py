@@ -244,3 +244,18 @@ def test_hit_prob_edge_cases(oracle):
     # all references hit zero k-mers while K > 0: slow branch, uniform
     p = oracle.highest_hit_prob_per_reference(20, 10, np.zeros(3, np.uint16))
     assert p == pytest.approx([1 / 3] * 3)
+
+
+# ---- golden end-to-end text of the oracle on real data (tests/golden/make_golden_outputs.py) ----------------------
+def test_oracle_reproduces_golden_outputs(oracle):
+    import os
+
+    g = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    text = open(os.path.join(g, "diptera_sample.fasta")).read()
+    tree = oracle.Tree.from_fasta(text)
+    labels, off, codes = oracle.parse_queries(text)
+    assert tree.num_tips == 400 and len(labels) == 400
+    for skip, name in ((False, "default"), (True, "skip")):
+        out = tree.classify(off, codes, skip_exact=skip, threads=2, chunk_size=32)
+        txt = oracle.format_results(tree, out["results"], labels) + "\n"
+        assert txt == open(os.path.join(g, f"diptera_sample.{name}.out")).read()
