@@ -483,8 +483,6 @@ __global__ void __launch_bounds__(kProbThreads)
     __shared__ double part[kProbWarps][32];
     __shared__ u32 wsum[kProbWarps];
     __shared__ double wtot[kProbWarps];
-    __shared__ u32 sh_D;
-    __shared__ double sh_S;
     // tree-walk state (warp 0)
     __shared__ u32 st_node[RTX_MAX_LEVELS + 1];
     __shared__ u32 st_next[RTX_MAX_LEVELS + 1];
@@ -744,27 +742,24 @@ __global__ void __launch_bounds__(kProbThreads)
                     if (ix.node_type[node] == 0) {  // Inner with no significant child: follow the best children
                         while (ix.node_type[cur] == 0) {
                             const u32 f = ix.child_first[cur], n_c = ix.child_count[cur];
-                            // max_by(partial_cmp): the LAST maximal child wins (lineage.rs:156-164)
+                            // max_by(partial_cmp): the LAST maximal child wins (lineage.rs:156-164).  Children that are
+                            // tied in exact arithmetic (same hit counts) differ here only by the rounding noise of the
+                            // prefix sums, so values within 1e-12 relative of the maximum count as maximal.
                             double best = -CUDART_INF;
+                            for (u32 cb = 0; cb < n_c; cb += 32) {
+                                const u32 ci = cb + lane;
+                                if (ci < n_c) best = fmax(best, preb[ix.node_bhi[f + ci]] - preb[ix.node_blo[f + ci]]);
+                            }
+#pragma unroll
+                            for (int o = 16; o > 0; o >>= 1) best = fmax(best, __shfl_xor_sync(kFullMask, best, o));
+                            const double thr = best - fabs(best) * 1e-12;
                             u32 besti = 0;
                             for (u32 cb = 0; cb < n_c; cb += 32) {
                                 const u32 ci = cb + lane;
-                                double cv = -CUDART_INF;
-                                if (ci < n_c) cv = preb[ix.node_bhi[f + ci]] - preb[ix.node_blo[f + ci]];
-                                if (ci < n_c && cv >= best) {
-                                    best = cv;
-                                    besti = ci;
-                                }
+                                if (ci < n_c && preb[ix.node_bhi[f + ci]] - preb[ix.node_blo[f + ci]] >= thr) besti = ci;
                             }
 #pragma unroll
-                            for (int o = 16; o > 0; o >>= 1) {
-                                double ob = __shfl_xor_sync(kFullMask, best, o);
-                                u32 oi = __shfl_xor_sync(kFullMask, besti, o);
-                                if (ob > best || (ob == best && oi > besti)) {
-                                    best = ob;
-                                    besti = oi;
-                                }
-                            }
+                            for (int o = 16; o > 0; o >>= 1) besti = max(besti, __shfl_xor_sync(kFullMask, besti, o));
                             cur = f + besti;
                             if (lane == 0) {
                                 path_conf[d] = 1.0 / 100.0;

@@ -57,6 +57,7 @@ struct rtx_ctx {
     std::vector<double> h_pool_conf, h_pool_local;
     // taps wired by rtx_classify_batch for sub-batched runs
     u16* tap_counts_host = nullptr;
+    u64 runs_since_download = 0;
     // profile
     rtx_profile prof{};
     std::vector<EventPair> events;
@@ -542,8 +543,8 @@ RTX_API int rtx_batch_upload(rtx_ctx* ctx, const rtx_batch* batch) {
     ctx->pool.res_cnt = ctx->d_res_cnt.as<u32>();
     ctx->pool.global_sig = ctx->d_global.as<double>();
     ctx->pool.status = ctx->d_status.as<int>();
-    if (ctx->pool.cap < (u64)nq * 4 + 1024) {
-        int rc = ensure_pool(ctx, (u64)nq * 4 + 1024);
+    if (ctx->pool.cap < (u64)nq * 8 + 1024) {
+        int rc = ensure_pool(ctx, (u64)nq * 8 + 1024);
         if (rc) return rc;
     }
 
@@ -661,6 +662,7 @@ static int run_all(rtx_ctx* ctx) {
         }
     }
     ctx->prof.queries += nq;
+    ctx->runs_since_download += 1;
     ctx->ran = true;
     return RTX_OK;
 }
@@ -704,12 +706,15 @@ RTX_API int rtx_batch_download(rtx_ctx* ctx, rtx_results* res) {
     CU(cudaMemcpyAsync(res->global_signal, ctx->d_global.p, nq * 8, cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
     ctx->prof.d2h_bytes += 16 + (u64)nq * (4 * 4 + 2 + 8);
-    ctx->prof.hits += hits;
     {
+        // every run since the last download processed this same batch: account them all
+        const u64 runs = ctx->runs_since_download;
+        ctx->runs_since_download = 0;
         u64 rows = 0;
         for (u32 q = 0; q < nq; ++q) rows += ctx->h_nrows[q];
-        ctx->prof.bitrow_bytes += rows * (u64)ctx->ix.row_words * 4 + (u64)nq * ctx->ix.n_pad * 2;
-        ctx->prof.csr_equiv_bytes += 4 * (u64)hits + (u64)nq * ctx->ix.shard_refs * 2;
+        ctx->prof.hits += hits * runs;
+        ctx->prof.bitrow_bytes += runs * (rows * (u64)ctx->ix.row_words * 4 + (u64)nq * ctx->ix.n_pad * 2);
+        ctx->prof.csr_equiv_bytes += runs * (4 * (u64)hits + (u64)nq * ctx->ix.shard_refs * 2);
     }
     bool pool_overflow = false;
     for (u32 q = 0; q < nq; ++q) {
@@ -727,7 +732,7 @@ RTX_API int rtx_batch_download(rtx_ctx* ctx, rtx_results* res) {
     }
     if (pool_overflow) {
         // grow the pool and redo the whole batch once (counts of earlier sub-batches are gone)
-        int rc = ensure_pool(ctx, used + 1024);
+        int rc = ensure_pool(ctx, used + used / 4 + 1024);
         if (rc) return rc;
         rc = run_all(ctx);
         if (rc) return rc;
@@ -822,6 +827,7 @@ RTX_API int rtx_profile_reset(rtx_ctx* ctx) {
     CU(cudaStreamSynchronize(ctx->stream));
     drain_events(ctx);
     ctx->prof = rtx_profile{};
+    ctx->runs_since_download = 0;
     return RTX_OK;
 }
 

@@ -84,7 +84,8 @@ class TolerantChecker:
                     sub = walk(c, prefix + [o])
                     if not sub and self.type[c] == 1:
                         outs.append((int(self.lo[c]), tuple(prefix + [o])))
-                    pushed = True
+                        pushed = True
+                    pushed = pushed or sub
             if not definite_sig and self.type[node] == 0:
                 cur, pf = node, list(prefix)
                 frontier = [(cur, pf)]
