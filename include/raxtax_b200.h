@@ -51,7 +51,9 @@ typedef enum {
     RTX_OPT_HITCOUNT_VARIANT = 1,
     RTX_OPT_SUB_BATCH = 2,      /* queries per device sub-batch (0 = auto) */
     RTX_OPT_KEEP_CSR = 3,       /* keep the CSR postings resident after building bit rows (needed for variant CSR) */
-    RTX_OPT_PROFILE = 4         /* record a CUDA event pair around every kernel launch (rtx_profile_get) */
+    RTX_OPT_PROFILE = 4,        /* record a CUDA event pair around every kernel launch (rtx_profile_get) */
+    RTX_OPT_HITCOUNT_TUNE = 5,  /* bit-row kernel geometry: V + 10*prefetch + 100*warps_per_cta, 0 = library default */
+    RTX_OPT_HITCOUNT_MAX_TILES = 6 /* warp tiles (32*V words each) per CTA; fewer = more reference tile groups (L2 blocking); 0 = default */
 } rtx_option;
 
 /* ---- context ------------------------------------------------------------------------------------------- */

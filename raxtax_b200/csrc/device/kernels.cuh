@@ -250,9 +250,30 @@ struct RowVec<4> {
 __device__ __forceinline__ u32 vec_get(const uint2& v, int i) { return i == 0 ? v.x : v.y; }
 __device__ __forceinline__ u32 vec_get(const uint4& v, int i) { return i == 0 ? v.x : i == 1 ? v.y : i == 2 ? v.z : v.w; }
 
-// grid: x = query within the sub-batch, y = tile group.  block: kHitThreads.
+// grid: x = query within the sub-batch, y = tile group.  block: 32 * nwarps threads (nwarps chosen by the host so that
+// the tiles of a CTA divide evenly over its warps).
 // dynamic shared memory: u32 srow[kRowListCap] + u32 shist[hstride]
-template <int V, int NP>
+// PF = software prefetch: the next 16 rows are requested before the current 16 are folded (register double buffer).
+template <int V, typename vec_t>
+__device__ __forceinline__ void load16(vec_t (&x)[16], const u32* __restrict__ colbase, const u32* __restrict__ srow, u32 j, u32 row_words) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        const u32 rid = srow[j + i];
+        x[i] = ldg_stream(reinterpret_cast<const vec_t*>(colbase + (size_t)rid * row_words));
+    }
+}
+template <int V, int NP, typename vec_t>
+__device__ __forceinline__ void fold16(u32 (&pl)[V][NP], const vec_t (&x)[16]) {
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+        u32 xv[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) xv[i] = vec_get(x[i], v);
+        add16<NP>(pl[v], xv);
+    }
+}
+
+template <int V, int NP, bool PF>
 __global__ void __launch_bounds__(kHitThreads)
     hitcount_bitrows_kernel(IndexView ix, BatchView b, u16* __restrict__ counts, int q_base, int tiles_per_cta, int n_tiles) {
     extern __shared__ __align__(16) u32 hsm[];
@@ -260,25 +281,26 @@ __global__ void __launch_bounds__(kHitThreads)
     u32* shist = hsm + kRowListCap;
     typedef typename RowVec<V>::T vec_t;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int nthreads = blockDim.x, nwarps = nthreads >> 5;
     const int ql = blockIdx.x;
     const int q = q_base + ql;
     const u32 n = b.nrows[q];
     const u32* __restrict__ qrows = b.rows + (size_t)q * b.kstride;
     const int tile_begin = blockIdx.y * tiles_per_cta;
     const int tile_end = min(n_tiles, tile_begin + tiles_per_cta);
-    const int rounds = (tile_end - tile_begin + kHitWarps - 1) / kHitWarps;
+    const int rounds = (tile_end - tile_begin + nwarps - 1) / nwarps;
     const u32 nbins = (u32)b.K[q] + 1u;
 
-    for (u32 i = tid; i < nbins; i += kHitThreads) shist[i] = 0;
+    for (u32 i = tid; i < nbins; i += nthreads) shist[i] = 0;
     const bool single = n <= (u32)kRowListCap;
     if (single) {
-        for (u32 i = tid; i < n; i += kHitThreads) srow[i] = qrows[i];
+        for (u32 i = tid; i < n; i += nthreads) srow[i] = qrows[i];
     }
     __syncthreads();
 
     u16* __restrict__ qcounts = counts + (size_t)ql * ix.n_pad;
     for (int r = 0; r < rounds; ++r) {
-        const int tile = tile_begin + r * kHitWarps + warp;
+        const int tile = tile_begin + r * nwarps + warp;
         const bool active = tile < tile_end;
         const u32 word0 = (u32)tile * (32 * V) + lane * V;  // first word of this lane
         u32 pl[V][NP];
@@ -291,24 +313,26 @@ __global__ void __launch_bounds__(kHitThreads)
             const u32 cn = min((u32)kRowListCap, n - c0);
             if (!single) {
                 __syncthreads();
-                for (u32 i = tid; i < cn; i += kHitThreads) srow[i] = qrows[c0 + i];
+                for (u32 i = tid; i < cn; i += nthreads) srow[i] = qrows[c0 + i];
                 __syncthreads();
             }
             if (active) {
                 const u32* __restrict__ colbase = ix.bitrows + word0;
-                for (u32 j = 0; j < cn; j += 16) {
-                    vec_t x[16];
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        const u32 rid = srow[j + i];
-                        x[i] = ldg_stream(reinterpret_cast<const vec_t*>(colbase + (size_t)rid * ix.row_words));
+                if (PF) {
+                    vec_t xa[16], xb[16];
+                    load16<V>(xa, colbase, srow, 0, ix.row_words);
+                    for (u32 j = 0; j < cn; j += 32) {
+                        const bool has_b = j + 16 < cn;
+                        if (has_b) load16<V>(xb, colbase, srow, j + 16, ix.row_words);
+                        fold16<V, NP>(pl, xa);
+                        if (j + 32 < cn) load16<V>(xa, colbase, srow, j + 32, ix.row_words);
+                        if (has_b) fold16<V, NP>(pl, xb);
                     }
-#pragma unroll
-                    for (int v = 0; v < V; ++v) {
-                        u32 xv[16];
-#pragma unroll
-                        for (int i = 0; i < 16; ++i) xv[i] = vec_get(x[i], v);
-                        add16<NP>(pl[v], xv);
+                } else {
+                    for (u32 j = 0; j < cn; j += 16) {
+                        vec_t x[16];
+                        load16<V>(x, colbase, srow, j, ix.row_words);
+                        fold16<V, NP>(pl, x);
                     }
                 }
             }
@@ -340,7 +364,7 @@ __global__ void __launch_bounds__(kHitThreads)
     }
     __syncthreads();
     u32* __restrict__ ghist = b.hist + (size_t)q * b.hstride;
-    for (u32 i = tid; i < nbins; i += kHitThreads) {
+    for (u32 i = tid; i < nbins; i += nthreads) {
         u32 h = shist[i];
         if (h) atomicAdd(&ghist[i], h);
     }
@@ -437,75 +461,89 @@ __global__ void fixup_exact_kernel(IndexView ix, BatchView b, u16* __restrict__ 
 // =========================================================================================================
 constexpr int kProbThreads = 256;
 constexpr int kProbWarps = kProbThreads / 32;
+constexpr int kEntCap = 2048;  // frontier entries of the tree walk held in shared memory (<= 200 per level)
 
 struct ProbScratch {
-    double* cbuf;        // [slots][cbuf_stride] log-CMFs of the slow branch, row d = distinct count d
+    double* cbuf;        // [slots][cbuf_stride] r_m[i] = pmf_m(i) / cmf_m(i) of the slow branch, row d = distinct count d
     size_t cbuf_stride;  // = hstride * tstride doubles
     u32 tstride;         // doubles per cbuf row ( >= max t + 1 )
     double* preb;        // [slots][preb_stride] prefix sums of normalised probabilities at node boundaries
     size_t preb_stride;
-    u32* st_first;       // [slots][RTX_MAX_RESULTS_PER_QUERY] staged results (DFS order)
-    u8* st_nlev;
-    double* st_conf;     // [slots][RTX_MAX_RESULTS_PER_QUERY][max_levels]
-    double* st_local;
 };
 
-__device__ __forceinline__ double round_conf(double x) {
-    return round(x * 100.0) / 100.0;  // f64::round = half away from zero (lineage.rs:129)
-}
-
-// dynamic smem carve-up (all sizes depend on H = hstride, T1 = H/2 + 1)
+// dynamic smem carve-up (sizes depend on H = hstride, T1 = H/2 + 1, ML = max_levels)
 struct ProbSmem {
-    double* Ptab;   // [H]   P(m) then P(m)/S, direct-indexed by count
-    double* dval;   // [H]   per distinct count: scan carry (pass 1) / P (pass 2)
+    double* Ptab;   // [H]   P(m)/S, direct-indexed by count
+    double* dval;   // [H]   per distinct count: running cmf (pass 1) / P (pass 2)
+    double* dcar;   // [H]   per distinct count: ln of the running cmf
     double* g;      // [T1]  ln i! + ln (t-i)!
-    double* prod;   // [T1]  sum_m h[m] * c_m[i]
+    double* prod;   // [T1]  sum_m h[m] * ln cmf_m(i), then E[i] = exp(prod[i])
+    double* res_local;  // [RTX_MAX_RESULTS_PER_QUERY]
     u32* hist;      // [H]
     u32* dh;        // [H]   multiplicity of distinct count d
+    u32* res_first; // [RTX_MAX_RESULTS_PER_QUERY]
+    u32* ent_node;  // [kEntCap]
     u16* dm;        // [H]   distinct counts ascending
-    __device__ ProbSmem(unsigned char* base, u32 H, u32 T1) {
+    u16* ent_parent;  // [kEntCap]
+    u16* order;       // [RTX_MAX_RESULTS_PER_QUERY]
+    u8* ent_k;        // [kEntCap] rounded confidence in hundredths
+    u8* res_nlev;     // [RTX_MAX_RESULTS_PER_QUERY]
+    u8* res_k;        // [RTX_MAX_RESULTS_PER_QUERY][ML] rounded confidences in hundredths
+    __host__ __device__ ProbSmem(unsigned char* base, u32 H, u32 T1, u32 ML) {
         Ptab = reinterpret_cast<double*>(base);
         dval = Ptab + H;
-        g = dval + H;
+        dcar = dval + H;
+        g = dcar + H;
         prod = g + T1;
-        hist = reinterpret_cast<u32*>(prod + T1);
+        res_local = prod + T1;
+        hist = reinterpret_cast<u32*>(res_local + RTX_MAX_RESULTS_PER_QUERY);
         dh = hist + H;
-        dm = reinterpret_cast<u16*>(dh + H);
+        res_first = dh + H;
+        ent_node = res_first + RTX_MAX_RESULTS_PER_QUERY;
+        dm = reinterpret_cast<u16*>(ent_node + kEntCap);
+        ent_parent = dm + H;
+        order = ent_parent + kEntCap;
+        ent_k = reinterpret_cast<u8*>(order + RTX_MAX_RESULTS_PER_QUERY);
+        res_nlev = ent_k + kEntCap;
+        res_k = res_nlev + RTX_MAX_RESULTS_PER_QUERY;
     }
-    static size_t bytes(u32 H, u32 T1) { return (size_t)H * (8 + 8 + 4 + 4 + 2) + (size_t)T1 * 16 + 16; }
+    static size_t bytes(u32 H, u32 T1, u32 ML) {
+        return (size_t)H * (8 * 3 + 4 * 2 + 2) + (size_t)T1 * 16 + (size_t)RTX_MAX_RESULTS_PER_QUERY * (ML + 8 + 4 + 2 + 1) +
+               (size_t)kEntCap * (4 + 2 + 1) + 64;
+    }
+};
+
+// node record: one 16-byte load gives everything the walk needs about a child
+struct __align__(16) NodeRec {
+    u32 blo, bhi;      // boundary indices of [lo, hi) clamped to the shard
+    u32 child_first;
+    u32 cc_type;       // child_count | node_type << 30
 };
 
 __global__ void __launch_bounds__(kProbThreads)
-    prob_lineage_kernel(IndexView ix, BatchView b, ResultPool pool, ProbScratch sc, const u16* __restrict__ counts, int q_base,
-                        int q_count, unsigned long long* __restrict__ hits_total) {
+    prob_lineage_kernel(IndexView ix, const NodeRec* __restrict__ recs, BatchView b, ResultPool pool, ProbScratch sc,
+                        const u16* __restrict__ counts, int q_base, int q_count, unsigned long long* __restrict__ hits_total) {
     extern __shared__ __align__(16) unsigned char psm_raw[];
     __shared__ double red[40];
     __shared__ double part[kProbWarps][32];
     __shared__ u32 wsum[kProbWarps];
     __shared__ double wtot[kProbWarps];
-    // tree-walk state (warp 0)
-    __shared__ u32 st_node[RTX_MAX_LEVELS + 1];
-    __shared__ u32 st_next[RTX_MAX_LEVELS + 1];
-    __shared__ u8 st_any[RTX_MAX_LEVELS + 1];
-    __shared__ double path_conf[RTX_MAX_LEVELS + 1];
-    __shared__ double path_exp[RTX_MAX_LEVELS + 1];
-    __shared__ u16 order[RTX_MAX_RESULTS_PER_QUERY];
+    __shared__ u32 sh_ent_end, sh_nres, sh_flags;
+    __shared__ u32 chain_nodes[kProbWarps][RTX_MAX_LEVELS + 1];
+    __shared__ u8 chain_k[kProbWarps][RTX_MAX_LEVELS + 1];
+    __shared__ unsigned long long sh_base;
 
     const u32 H = b.hstride;
     const u32 T1 = H / 2 + 1;
-    ProbSmem sm(psm_raw, H, T1);
+    const u32 ML = ix.max_levels;
+    ProbSmem sm(psm_raw, H, T1, ML);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const double* __restrict__ lf = ix.lnfact;
     const double NEG_INF = -CUDART_INF;
-    const u32 ML = ix.max_levels;
     const double Nd = (double)ix.n_refs;
 
     double* cbuf = sc.cbuf + (size_t)blockIdx.x * sc.cbuf_stride;
     double* preb = sc.preb + (size_t)blockIdx.x * sc.preb_stride;
-    u32* stg_first = sc.st_first + (size_t)blockIdx.x * RTX_MAX_RESULTS_PER_QUERY;
-    u8* stg_nlev = sc.st_nlev + (size_t)blockIdx.x * RTX_MAX_RESULTS_PER_QUERY;
-    double* stg_conf = sc.st_conf + (size_t)blockIdx.x * RTX_MAX_RESULTS_PER_QUERY * ML;
-    double* stg_local = sc.st_local + (size_t)blockIdx.x * RTX_MAX_RESULTS_PER_QUERY;
 
     for (int ql = blockIdx.x; ql < q_count; ql += gridDim.x) {
         const int q = q_base + ql;
@@ -532,9 +570,15 @@ __global__ void __launch_bounds__(kProbThreads)
                 sm.dm[dpos] = (u16)m;
                 sm.dh[dpos] = h;
                 sm.dval[dpos] = 0.0;
+                sm.dcar[dpos] = NEG_INF;
                 ++dpos;
             }
             sm.Ptab[m] = 0.0;
+        }
+        if (tid == 0) {
+            sh_ent_end = 1;
+            sh_nres = 0;
+            sh_flags = 0;
         }
         __syncthreads();
         // postings a CSR walk would have touched for this query = sum_r count[r]
@@ -562,8 +606,7 @@ __global__ void __launch_bounds__(kProbThreads)
             for (u32 i = tid; i <= t; i += kProbThreads) sm.g[i] = lf[i] + lf[t - i];
             __syncthreads();
             const u32 nchunks = (t + 1 + 31) / 32;
-            double* __restrict__ crow_base = cbuf;
-            // pass 1: log-CMFs c_m[i] and prod[i] = sum_m h[m] c_m[i]
+            // pass 1: e = pmf_m(i), running cmf S, c = ln S, prod[i] = sum_m h[m] c_m[i]; r = e / S is kept for pass 2
             for (u32 ch = 0; ch < nchunks; ++ch) {
                 const u32 i = ch * 32 + lane;
                 const bool valid = i <= t;
@@ -572,18 +615,27 @@ __global__ void __launch_bounds__(kProbThreads)
                     const u32 m = sm.dm[d];
                     if (m == 0) continue;  // pmf = [1,0,0,..] => cmf == 1 => ln cmf == 0 for every i
                     const double cm = lf[m - 1] + lf[K - m - 1] + T;
-                    double e = 0.0;
-                    if (valid) {
-                        // ln pmf_m(i) = ln C(m+i-1,i) + ln C(K-m+t-i-1,t-i) - T   (closed form of prob.rs:136-166)
-                        double p = lf[m + i - 1] + lf[K - m + t - i - 1] - sm.g[i] - cm;
-                        e = exp(p);
-                    }
-                    double s = warp_scan_incl(e, lane) + sm.dval[d];
+                    // ln pmf_m(i) = ln C(m+i-1,i) + ln C(K-m+t-i-1,t-i) - T   (closed form of prob.rs:136-166)
+                    const double p = valid ? lf[m + i - 1] + lf[K - m + t - i - 1] - sm.g[i] - cm : NEG_INF;
+                    const double e = valid ? exp(p) : 0.0;
+                    const double S0 = sm.dval[d], c0 = sm.dcar[d];
                     __syncwarp();
-                    if (lane == 31) sm.dval[d] = s;
-                    double c = log(s);  // s == 0 -> -inf, as the reference's sum.ln()
+                    double S, c;
+                    // upper tail: every term of this chunk is below half an ulp of the running sum, so the reference's
+                    // sequential `sum += pmf.exp()` leaves the sum (and its ln) bit-for-bit unchanged
+                    if (__all_sync(kFullMask, p < c0 - 38.0)) {
+                        S = S0;
+                        c = c0;
+                    } else {
+                        S = warp_scan_incl(e, lane) + S0;
+                        c = log(S);  // S == 0 -> -inf, as the reference's sum.ln()
+                        if (lane == 31) {
+                            sm.dval[d] = S;
+                            sm.dcar[d] = c;
+                        }
+                    }
                     if (valid) {
-                        crow_base[(size_t)d * sc.tstride + i] = c;
+                        cbuf[(size_t)d * sc.tstride + i] = (S > 0.0) ? e / S : 0.0;
                         acc += (double)sm.dh[d] * c;
                     }
                 }
@@ -593,26 +645,21 @@ __global__ void __launch_bounds__(kProbThreads)
                     double s = 0.0;
 #pragma unroll
                     for (int w = 0; w < kProbWarps; ++w) s += part[w][lane];
-                    if (valid) sm.prod[i] = s;
+                    // E[i] = exp(prod[i]); exp(-inf) = 0 reproduces the reference's `prod == -inf => 0` branch
+                    if (valid) sm.prod[i] = exp(s);
                 }
                 __syncthreads();
             }
-            // pass 2: P(m) = sum_i exp(p_m[i] + prod[i] - c_m[i])   (prob.rs:74-90)
+            // pass 2: P(m) = sum_i exp(p_m[i] + prod[i] - c_m[i]) = sum_i (pmf_m(i)/cmf_m(i)) * E[i]   (prob.rs:74-90)
             for (u32 d = warp; d < D; d += kProbWarps) {
                 const u32 m = sm.dm[d];
                 double val;
                 if (m == 0) {
-                    double pr = sm.prod[0];
-                    val = (pr == NEG_INF) ? 0.0 : exp(pr);
+                    val = sm.prod[0];  // p = [0,-inf,..], c = 0
                 } else {
-                    const double cm = lf[m - 1] + lf[K - m - 1] + T;
                     double s = 0.0;
-                    for (u32 i = lane; i <= t; i += 32) {
-                        double p = lf[m + i - 1] + lf[K - m + t - i - 1] - sm.g[i] - cm;
-                        double c = crow_base[(size_t)d * sc.tstride + i];
-                        double pr = sm.prod[i];
-                        s += (c == NEG_INF || pr == NEG_INF) ? 0.0 : exp(p + pr - c);
-                    }
+                    const double* __restrict__ row = cbuf + (size_t)d * sc.tstride;
+                    for (u32 i = lane; i <= t; i += 32) s = fma(row[i], sm.prod[i], s);
                     val = warp_sum(s);
                 }
                 if (lane == 0) sm.dval[d] = val;
@@ -681,207 +728,226 @@ __global__ void __launch_bounds__(kProbThreads)
                 carry += tot;
                 __syncthreads();
             }
-            if (tid == 0) preb[0] = 0.0;
+            if (tid == 0) {
+                preb[0] = 0.0;
+                sm.ent_node[0] = 0;  // root
+                sm.ent_parent[0] = 0xFFFF;
+                sm.ent_k[0] = 0;
+            }
             __syncthreads();
         }
 
-        // ---- tree walk (lineage.rs:119-179), warp 0 ----------------------------------------------------
-        if (warp == 0) {
-            u32 n_res = 0;
-            bool overflow = false;
-            int depth = 0;
-            if (lane == 0) {
-                st_node[0] = 0;
-                st_next[0] = 0;
-                st_any[0] = 0;
-            }
-            __syncwarp();
-            while (depth >= 0 && !bad_sum) {
-                const u32 node = st_node[depth];
-                const u32 cf = ix.child_first[node], cc = ix.child_count[node];
-                u32 nxt = st_next[depth];
-                bool found = false;
-                u32 child = 0;
-                double cconf = 0.0;
-                for (u32 cb = nxt; cb < cc; cb += 32) {
-                    const u32 ci = cb + lane;
-                    double rc = 0.0;
-                    if (ci < cc) {
-                        const u32 c = cf + ci;
-                        rc = round_conf(preb[ix.node_bhi[c]] - preb[ix.node_blo[c]]);
+        // ---- tree walk (lineage.rs:119-179), level-synchronous: one warp per visited node ----------------
+        // The reference recurses depth-first and then sorts stably by the confidence vectors; emitting nodes have
+        // disjoint reference ranges, so "depth-first order" == "ascending first reference id", which the sort below
+        // uses as its tie-break.  Entry = (node, parent entry, rounded confidence in hundredths).
+        if (!bad_sum) {
+            u32 lvl_begin = 0, lvl_end = 1;
+            int depth = 0;  // path length of the entries of this level
+            while (lvl_begin < lvl_end) {
+                for (u32 e = lvl_begin + warp; e < lvl_end; e += kProbWarps) {
+                    const u32 node = sm.ent_node[e];
+                    const NodeRec nr = recs[node];
+                    const u32 cf = nr.child_first, cc = nr.cc_type & 0x3FFFFFFFu, ntype = nr.cc_type >> 30;
+                    bool any = false;
+                    for (u32 cb = 0; cb < cc; cb += 32) {
+                        const u32 ci = cb + lane;
+                        u32 k = 0;
+                        if (ci < cc) {
+                            const NodeRec cr = recs[cf + ci];
+                            const double conf = preb[cr.bhi] - preb[cr.blo];
+                            k = (u32)round(conf * 100.0);  // round(conf*100)/100 != 0  <=>  k != 0 (lineage.rs:129-131)
+                        }
+                        const u32 mask = __ballot_sync(kFullMask, k != 0);
+                        if (mask) {
+                            any = true;
+                            u32 base_slot = 0;
+                            if (lane == 0) base_slot = atomicAdd(&sh_ent_end, (u32)__popc(mask));
+                            base_slot = __shfl_sync(kFullMask, base_slot, 0);
+                            if (k != 0) {
+                                const u32 slot = base_slot + __popc(mask & ((1u << lane) - 1u));
+                                if (slot < kEntCap) {
+                                    sm.ent_node[slot] = cf + ci;
+                                    sm.ent_parent[slot] = (u16)e;
+                                    sm.ent_k[slot] = (u8)min(k, 255u);
+                                } else if (lane == (__ffs(mask) - 1)) atomicOr(&sh_flags, 1u);
+                            }
+                        }
                     }
-                    const u32 mask = __ballot_sync(kFullMask, rc != 0.0);
-                    if (mask) {
-                        const int j = __ffs(mask) - 1;
-                        child = cf + cb + j;
-                        cconf = __shfl_sync(kFullMask, rc, j);
-                        nxt = cb + j + 1;
-                        found = true;
-                        break;
-                    }
-                }
-                if (found) {
-                    if (lane == 0) {
-                        st_next[depth] = nxt;
-                        st_any[depth] = 1;
-                        path_conf[depth] = cconf;
-                        path_exp[depth] = (double)(ix.node_hi[child] - ix.node_lo[child]) / Nd;
-                        st_node[depth + 1] = child;
-                        st_next[depth + 1] = 0;
-                        st_any[depth + 1] = 0;
-                    }
-                    __syncwarp();
-                    ++depth;  // depth <= max_levels by construction of the tree
-                    continue;
-                }
-                // children exhausted
-                if (!st_any[depth]) {
+                    if (any) continue;
+                    // no significant child: a Taxon is emitted as it is (lineage.rs:142-148), an Inner node follows its
+                    // best children down to a non-Inner node with 0.01 per level (lineage.rs:151-177)
+                    if (ntype == 2 || (ntype == 1 && depth == 0)) continue;
                     int d = depth;
                     u32 cur = node;
-                    bool emit = true;
-                    if (ix.node_type[node] == 0) {  // Inner with no significant child: follow the best children
-                        while (ix.node_type[cur] == 0) {
-                            const u32 f = ix.child_first[cur], n_c = ix.child_count[cur];
-                            // max_by(partial_cmp): the LAST maximal child wins (lineage.rs:156-164).  Children that are
-                            // tied in exact arithmetic (same hit counts) differ here only by the rounding noise of the
-                            // prefix sums, so values within 1e-12 relative of the maximum count as maximal.
+                    if (ntype == 0) {
+                        u32 cur_cf = cf, cur_cc = cc, cur_type = 0;
+                        while (cur_type == 0) {
+                            // max_by(partial_cmp): the LAST maximal child wins (lineage.rs:156-164).  Children tied in exact
+                            // arithmetic (same hit counts) differ here only by rounding noise of the prefix sums, so values
+                            // within 1e-12 relative of the maximum count as maximal.
                             double best = -CUDART_INF;
-                            for (u32 cb = 0; cb < n_c; cb += 32) {
+                            for (u32 cb = 0; cb < cur_cc; cb += 32) {
                                 const u32 ci = cb + lane;
-                                if (ci < n_c) best = fmax(best, preb[ix.node_bhi[f + ci]] - preb[ix.node_blo[f + ci]]);
+                                if (ci < cur_cc) {
+                                    const NodeRec cr = recs[cur_cf + ci];
+                                    best = fmax(best, preb[cr.bhi] - preb[cr.blo]);
+                                }
                             }
 #pragma unroll
                             for (int o = 16; o > 0; o >>= 1) best = fmax(best, __shfl_xor_sync(kFullMask, best, o));
                             const double thr = best - fabs(best) * 1e-12;
                             u32 besti = 0;
-                            for (u32 cb = 0; cb < n_c; cb += 32) {
+                            for (u32 cb = 0; cb < cur_cc; cb += 32) {
                                 const u32 ci = cb + lane;
-                                if (ci < n_c && preb[ix.node_bhi[f + ci]] - preb[ix.node_blo[f + ci]] >= thr) besti = ci;
+                                if (ci < cur_cc) {
+                                    const NodeRec cr = recs[cur_cf + ci];
+                                    if (preb[cr.bhi] - preb[cr.blo] >= thr) besti = ci;
+                                }
                             }
 #pragma unroll
                             for (int o = 16; o > 0; o >>= 1) besti = max(besti, __shfl_xor_sync(kFullMask, besti, o));
-                            cur = f + besti;
-                            if (lane == 0) {
-                                path_conf[d] = 1.0 / 100.0;
-                                path_exp[d] = (double)(ix.node_hi[cur] - ix.node_lo[cur]) / Nd;
+                            cur = cur_cf + besti;
+                            const NodeRec br = recs[cur];
+                            if (lane == 0 && d < RTX_MAX_LEVELS) {
+                                chain_nodes[warp][d] = cur;
+                                chain_k[warp][d] = 1;  // 1.0 / rounding_factor
                             }
                             ++d;
+                            cur_cf = br.child_first;
+                            cur_cc = br.cc_type & 0x3FFFFFFFu;
+                            cur_type = br.cc_type >> 30;
+                            if (d > RTX_MAX_LEVELS) break;
                         }
-                    } else if (ix.node_type[node] != 1 || depth == 0) {
-                        emit = false;  // only Taxon nodes are emitted (lineage.rs:143); Sequence-typed pass-through nodes are not
+                    }
+                    // path of the visited node itself: follow the parent links (depth entries)
+                    if (lane == 0) {
+                        u32 pe = e;
+                        for (int l = depth - 1; l >= 0; --l) {
+                            chain_nodes[warp][l] = sm.ent_node[pe];
+                            chain_k[warp][l] = sm.ent_k[pe];
+                            pe = sm.ent_parent[pe];
+                        }
                     }
                     __syncwarp();
-                    if (emit) {
-                        if (n_res >= RTX_MAX_RESULTS_PER_QUERY) overflow = true;
-                        else {
-                            // local signal (lineage.rs:95-102, utils.rs:91-105), sequential like the reference
-                            if (lane == 0) {
-                                int start = d - 1;
-                                for (int i = 0; i < d; ++i)
-                                    if (1.0 > path_exp[i]) {
-                                        start = i;
-                                        break;
-                                    }
-                                double a_sum = 0.0, b_sum = 0.0;
-                                for (int i = start; i < d; ++i) a_sum += path_conf[i];
-                                for (int i = start; i < d; ++i) b_sum += path_exp[i];
-                                double s2 = 0.0;
-                                for (int i = start; i < d; ++i) {
-                                    double df = path_conf[i] / a_sum - path_exp[i] / b_sum;
-                                    s2 += df * df;
-                                }
-                                stg_local[n_res] = (d > 0) ? sqrt(s2) : 0.0;
-                                stg_first[n_res] = ix.node_lo[cur];
-                                stg_nlev[n_res] = (u8)d;
-                            }
-                            for (int i = lane; i < d; i += 32) stg_conf[(size_t)n_res * ML + i] = path_conf[i];
-                            ++n_res;
-                        }
+                    u32 slot = 0;
+                    if (lane == 0) slot = atomicAdd(&sh_nres, 1u);
+                    slot = __shfl_sync(kFullMask, slot, 0);
+                    if (slot >= RTX_MAX_RESULTS_PER_QUERY || d > RTX_MAX_LEVELS) {
+                        if (lane == 0) atomicOr(&sh_flags, 1u);
+                        continue;
                     }
-                }
-                --depth;
-                __syncwarp();
-            }
-            __syncwarp();
-            // ---- order: stable sort, descending lexicographic on the confidence vectors (lineage.rs:93)
-            int status = kQOk;
-            if (bad_sum) status = kQProbSumZero;
-            else if (overflow) status = kQTooManyResults;
-            else if (n_res == 0) status = kQEmptyResult;  // assert!(!eval_res.is_empty()) raxtax.rs:72
-            if (lane == 0) {
-                for (u32 i = 0; i < n_res; ++i) {
-                    int j = (int)i - 1;
-                    const double* ci = stg_conf + (size_t)i * ML;
-                    const u32 li = stg_nlev[i];
-                    while (j >= 0) {
-                        const u32 oj = order[j];
-                        const double* cj = stg_conf + (size_t)oj * ML;
-                        const u32 lj = stg_nlev[oj];
-                        // does i sort strictly before order[j]?  <=> conf_i > conf_j lexicographically
-                        bool before = false, decided = false;
-                        for (u32 l = 0; l < min(li, lj); ++l) {
-                            if (ci[l] > cj[l]) {
-                                before = true;
-                                decided = true;
-                                break;
-                            }
-                            if (ci[l] < cj[l]) {
-                                decided = true;
-                                break;
-                            }
-                        }
-                        if (!decided) before = li > lj;
-                        if (!before) break;
-                        order[j + 1] = order[j];
-                        --j;
+                    // confidence and expected vectors of this line; local signal (lineage.rs:95-102, utils.rs:91-105)
+                    double cv = 0.0, ev = 0.0;
+                    if (lane < d) {
+                        const u32 nd = chain_nodes[warp][lane];
+                        cv = (double)chain_k[warp][lane] / 100.0;  // == round(conf*100)/100 of the reference
+                        ev = (double)(ix.node_hi[nd] - ix.node_lo[nd]) / Nd;
+                        sm.res_k[(size_t)slot * ML + lane] = chain_k[warp][lane];
                     }
-                    order[j + 1] = (u16)i;
-                }
-            }
-            __syncwarp();
-            // ---- override (raxtax.rs:73-84) and emission into the result pool ---------------------------
-            u32 n_out = n_res;
-            bool ovr = false;
-            u32 ovr_idx = 0;
-            if (status == kQOk && !(b.flags & RTX_RAW_CONFIDENCE) && !(b.flags & RTX_SKIP_EXACT_MATCHES) && b.exact_off) {
-                if (b.exact_off[q + 1] - b.exact_off[q] == 1) {
-                    ovr = true;
-                    ovr_idx = b.exact_ids[b.exact_off[q]];
-                    n_out = 1;
-                }
-            }
-            if (status != kQOk) n_out = 0;
-            unsigned long long base = 0;
-            if (lane == 0) base = atomicAdd(pool.used, (unsigned long long)n_out);
-            base = __shfl_sync(kFullMask, base, 0);
-            if (base + n_out > pool.cap) {
-                if (status == kQOk) status = kQPoolOverflow;
-            } else if (ovr) {
-                const u32 nl = ix.ref_levels[ovr_idx];
-                if (lane == 0) {
-                    pool.first_ref[base] = ovr_idx;
-                    pool.n_levels[base] = (u8)nl;
-                    pool.local[base] = stg_local[order[0]];
-                }
-                for (u32 l = lane; l < ML; l += 32) pool.conf[base * ML + l] = (l < nl) ? 1.0 : 0.0;
-            } else {
-                for (u32 i = 0; i < n_out; ++i) {
-                    const u32 src = order[i];
+                    const u32 lt1 = __ballot_sync(kFullMask, lane < d && 1.0 > ev);
+                    const int start = lt1 ? (__ffs(lt1) - 1) : (d - 1);
+                    // sequential sums like the reference (lane order = level order)
+                    double a_sum = 0.0, b_sum = 0.0;
+                    for (int i2 = start; i2 < d; ++i2) {
+                        a_sum += __shfl_sync(kFullMask, cv, i2);
+                        b_sum += __shfl_sync(kFullMask, ev, i2);
+                    }
+                    double s2 = 0.0;
+                    for (int i2 = start; i2 < d; ++i2) {
+                        const double df = __shfl_sync(kFullMask, cv, i2) / a_sum - __shfl_sync(kFullMask, ev, i2) / b_sum;
+                        s2 += df * df;
+                    }
                     if (lane == 0) {
-                        pool.first_ref[base + i] = stg_first[src];
-                        pool.n_levels[base + i] = stg_nlev[src];
-                        pool.local[base + i] = stg_local[src];
+                        sm.res_local[slot] = sqrt(s2);
+                        sm.res_first[slot] = ix.node_lo[cur];
+                        sm.res_nlev[slot] = (u8)d;
                     }
-                    const u32 nl = stg_nlev[src];
-                    for (u32 l = lane; l < ML; l += 32) pool.conf[(base + i) * ML + l] = (l < nl) ? stg_conf[(size_t)src * ML + l] : 0.0;
                 }
+                __syncthreads();
+                lvl_begin = lvl_end;
+                lvl_end = min(sh_ent_end, (u32)kEntCap);
+                ++depth;
+                __syncthreads();
             }
-            if (lane == 0) {
-                pool.res_off[q] = (u32)base;
-                pool.res_cnt[q] = n_out;
-                pool.global_sig[q] = global_signal;
-                pool.status[q] = status;
+        }
+        __syncthreads();
+        // ---- order (lineage.rs:93): descending lexicographic on the confidence vectors, ties in depth-first order ----
+        const u32 n_res = min(sh_nres, (u32)RTX_MAX_RESULTS_PER_QUERY);
+        int status = kQOk;
+        if (bad_sum) status = kQProbSumZero;
+        else if (sh_flags & 1u) status = kQTooManyResults;
+        else if (n_res == 0) status = kQEmptyResult;  // assert!(!eval_res.is_empty()) raxtax.rs:72
+        for (u32 i = tid; i < n_res; i += kProbThreads) {
+            const u8* ci = sm.res_k + (size_t)i * ML;
+            const u32 li = sm.res_nlev[i], fi = sm.res_first[i];
+            u32 rank = 0;
+            for (u32 j = 0; j < n_res; ++j) {
+                if (j == i) continue;
+                const u8* cj = sm.res_k + (size_t)j * ML;
+                const u32 lj = sm.res_nlev[j];
+                // does j sort before i?  conf_j > conf_i lexicographically (a longer vector wins on an equal prefix),
+                // or the vectors are equal and j comes first in depth-first order
+                int cmp = 0;  // +1: j > i, -1: j < i
+                for (u32 l = 0; l < min(li, lj); ++l) {
+                    if (cj[l] > ci[l]) {
+                        cmp = 1;
+                        break;
+                    }
+                    if (cj[l] < ci[l]) {
+                        cmp = -1;
+                        break;
+                    }
+                }
+                if (cmp == 0) cmp = (lj > li) ? 1 : (lj < li) ? -1 : 0;
+                if (cmp > 0 || (cmp == 0 && sm.res_first[j] < fi)) ++rank;
             }
+            sm.order[rank] = (u16)i;
+        }
+        __syncthreads();
+        // ---- override (raxtax.rs:73-84) and emission into the result pool ---------------------------------------
+        u32 n_out = n_res;
+        bool ovr = false;
+        u32 ovr_idx = 0;
+        if (status == kQOk && !(b.flags & RTX_RAW_CONFIDENCE) && !(b.flags & RTX_SKIP_EXACT_MATCHES) && b.exact_off) {
+            if (b.exact_off[q + 1] - b.exact_off[q] == 1) {
+                ovr = true;
+                ovr_idx = b.exact_ids[b.exact_off[q]];
+                n_out = 1;
+            }
+        }
+        if (status != kQOk) n_out = 0;
+        if (tid == 0) sh_base = atomicAdd(pool.used, (unsigned long long)n_out);
+        __syncthreads();
+        const unsigned long long base = sh_base;
+        if (base + n_out > pool.cap) {
+            if (status == kQOk) status = kQPoolOverflow;
+        } else if (ovr) {
+            const u32 nl = ix.ref_levels[ovr_idx];
+            if (tid == 0) {
+                pool.first_ref[base] = ovr_idx;
+                pool.n_levels[base] = (u8)nl;
+                pool.local[base] = sm.res_local[sm.order[0]];
+            }
+            for (u32 l = tid; l < ML; l += kProbThreads) pool.conf[base * ML + l] = (l < nl) ? 1.0 : 0.0;
+        } else {
+            for (u32 x = tid; x < n_out * ML; x += kProbThreads) {
+                const u32 i = x / ML, l = x - i * ML;
+                const u32 src = sm.order[i];
+                pool.conf[(base + i) * ML + l] = (l < sm.res_nlev[src]) ? (double)sm.res_k[(size_t)src * ML + l] / 100.0 : 0.0;
+            }
+            for (u32 i = tid; i < n_out; i += kProbThreads) {
+                const u32 src = sm.order[i];
+                pool.first_ref[base + i] = sm.res_first[src];
+                pool.n_levels[base + i] = sm.res_nlev[src];
+                pool.local[base + i] = sm.res_local[src];
+            }
+        }
+        if (tid == 0) {
+            pool.res_off[q] = (u32)base;
+            pool.res_cnt[q] = n_out;
+            pool.global_sig[q] = global_signal;
+            pool.status[q] = status;
         }
     }
 }

@@ -26,13 +26,15 @@ struct rtx_ctx {
     int64_t sub_batch_opt = 0;
     bool keep_csr = false;
     bool profile = false;
+    int hit_tune = 0;
+    int hit_max_tiles = 0;
     // index
     bool has_index = false;
     IndexView ix{};
     u32 n_rows = 0;
     u64 index_bytes = 0;
     DevBuf d_bitrows, d_rowmap, d_present, d_csr_off, d_csr_ids, d_node_lo, d_node_hi, d_node_type, d_child_first, d_child_count,
-        d_node_blo, d_node_bhi, d_bnd_after, d_bnd_rank, d_ref_levels, d_lnfact;
+        d_node_blo, d_node_bhi, d_bnd_after, d_bnd_rank, d_ref_levels, d_lnfact, d_recs;
     // batch
     bool has_batch = false;
     bool ran = false;
@@ -49,7 +51,7 @@ struct rtx_ctx {
     ProbScratch sc{};
     int prob_slots = 0;
     size_t prob_smem = 0;
-    DevBuf d_cbuf, d_preb, d_st_first, d_st_nlev, d_st_conf, d_st_local;
+    DevBuf d_cbuf, d_preb;
     // host staging
     std::vector<u32> h_res_off, h_res_cnt, h_nrows, h_pool_first;
     std::vector<int> h_status;
@@ -193,7 +195,7 @@ RTX_API void rtx_ctx_destroy(rtx_ctx* c) {
                       &c->d_bnd_rank, &c->d_ref_levels, &c->d_lnfact, &c->d_seq_off, &c->d_codes, &c->d_exact_off, &c->d_exact_ids,
                       &c->d_K, &c->d_kmers, &c->d_rows, &c->d_nrows, &c->d_hist, &c->d_counts, &c->d_pool_first, &c->d_pool_nlev,
                       &c->d_pool_conf, &c->d_pool_local, &c->d_pool_used, &c->d_res_off, &c->d_res_cnt, &c->d_global, &c->d_status,
-                      &c->d_hits, &c->d_cbuf, &c->d_preb, &c->d_st_first, &c->d_st_nlev, &c->d_st_conf, &c->d_st_local};
+                      &c->d_hits, &c->d_cbuf, &c->d_preb, &c->d_recs};
     for (DevBuf* b : bufs) b->release();
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
@@ -215,6 +217,14 @@ RTX_API int rtx_ctx_set_option(rtx_ctx* ctx, int option, int64_t value) {
             return RTX_OK;
         case RTX_OPT_PROFILE:
             ctx->profile = value != 0;
+            return RTX_OK;
+        case RTX_OPT_HITCOUNT_MAX_TILES:
+            REQUIRE(value >= 0 && value <= 4096, "bad max tiles per CTA");
+            ctx->hit_max_tiles = (int)value;
+            return RTX_OK;
+        case RTX_OPT_HITCOUNT_TUNE:
+            REQUIRE(value >= 0 && value < 1000 && (value % 10 == 0 || value % 10 == 2 || value % 10 == 4), "bad hit-count tuning word");
+            ctx->hit_tune = (int)value;
             return RTX_OK;
         default:
             return set_err(ctx, RTX_ERR_INVALID, "unknown option");
@@ -274,6 +284,7 @@ RTX_API int rtx_index_upload(rtx_ctx* ctx, const rtx_index_desc* d) {
     u64 child_total = 0;
     for (u32 i = 0; i < nn; ++i) {
         REQUIRE(d->node_lo[i] < d->node_hi[i] && d->node_hi[i] <= N, "node range out of bounds");
+        REQUIRE(d->child_count[i] < (1u << 30), "too many children");
         REQUIRE(d->node_type[i] <= 2, "node_type must be 0 (Inner), 1 (Taxon) or 2 (Sequence with children)");
         const u32 cf = d->child_first[i], cc = d->child_count[i];
         child_total += cc;
@@ -352,6 +363,11 @@ RTX_API int rtx_index_upload(rtx_ctx* ctx, const rtx_index_desc* d) {
     CU(upload_vec(ctx->d_node_type, d->node_type, nn, &bytes));
     CU(upload_vec(ctx->d_child_first, d->child_first, nn, &bytes));
     CU(upload_vec(ctx->d_child_count, d->child_count, nn, &bytes));
+    {
+        std::vector<NodeRec> recs(nn);
+        for (u32 i = 0; i < nn; ++i) recs[i] = NodeRec{blo[i], bhi[i], d->child_first[i], d->child_count[i] | ((u32)d->node_type[i] << 30)};
+        CU(upload_vec(ctx->d_recs, recs.data(), nn, &bytes));
+    }
     CU(upload_vec(ctx->d_node_blo, blo.data(), nn, &bytes));
     CU(upload_vec(ctx->d_node_bhi, bhi.data(), nn, &bytes));
     CU(upload_vec(ctx->d_bnd_after, bnd_after.data(), row_words, &bytes));
@@ -481,7 +497,7 @@ RTX_API int rtx_batch_upload(rtx_ctx* ctx, const rtx_batch* batch) {
     if (kmax > 65535) return set_err(ctx, RTX_ERR_UNSUPPORTED, "query with more than 65535 8-mer windows (raxtax.rs:56 asserts the same)");
     const u32 kstride = round_up(std::max(kmax, 1u), 16);
     const u32 hstride = round_up(kmax + 1, 4);
-    const size_t smem = ProbSmem::bytes(hstride, hstride / 2 + 1);
+    const size_t smem = ProbSmem::bytes(hstride, hstride / 2 + 1, ctx->ix.max_levels);
     if (smem > 200 * 1024)
         return set_err(ctx, RTX_ERR_UNSUPPORTED, "query too long for the shared-memory probability tables (more than ~5800 unique 8-mers)");
     ctx->max_len = max_len;
@@ -569,16 +585,8 @@ RTX_API int rtx_batch_upload(rtx_ctx* ctx, const rtx_batch* batch) {
     ctx->sc.preb_stride = round_up(ctx->ix.n_bnd, 4);
     CU(ctx->d_cbuf.ensure((size_t)slots * ctx->sc.cbuf_stride * 8));
     CU(ctx->d_preb.ensure((size_t)slots * ctx->sc.preb_stride * 8));
-    CU(ctx->d_st_first.ensure((size_t)slots * RTX_MAX_RESULTS_PER_QUERY * 4));
-    CU(ctx->d_st_nlev.ensure((size_t)slots * RTX_MAX_RESULTS_PER_QUERY));
-    CU(ctx->d_st_conf.ensure((size_t)slots * RTX_MAX_RESULTS_PER_QUERY * ctx->ix.max_levels * 8));
-    CU(ctx->d_st_local.ensure((size_t)slots * RTX_MAX_RESULTS_PER_QUERY * 8));
     ctx->sc.cbuf = ctx->d_cbuf.as<double>();
     ctx->sc.preb = ctx->d_preb.as<double>();
-    ctx->sc.st_first = ctx->d_st_first.as<u32>();
-    ctx->sc.st_nlev = ctx->d_st_nlev.as<u8>();
-    ctx->sc.st_conf = ctx->d_st_conf.as<double>();
-    ctx->sc.st_local = ctx->d_st_local.as<double>();
     ctx->has_batch = true;
     return RTX_OK;
 }
@@ -586,27 +594,57 @@ RTX_API int rtx_batch_upload(rtx_ctx* ctx, const rtx_batch* batch) {
 // ---------------------------------------------------------------------------------------------------------
 // kernels
 // ---------------------------------------------------------------------------------------------------------
-template <int V, int NP>
-static cudaError_t launch_hitcount(rtx_ctx* c, int q_base, int qb) {
+// Launch geometry of the bit-row kernel.  `tune` (RTX_OPT_HITCOUNT_TUNE) = V + 10*PF + 100*nwarps, 0 = default.
+template <int V, int NP, bool PF>
+static cudaError_t launch_hitcount(rtx_ctx* c, int q_base, int qb, int nwarps_opt) {
     const int n_tiles = (int)(c->ix.row_words / (32 * V));
-    const int max_tiles = 64;
+    // L2 blocking: CTAs are scheduled query-fastest, so all queries of one reference tile group run together; the
+    // group's slice of the bit matrix (n_rows x tiles x 128*V bytes) should stay resident in the 126 MB L2.
+    int max_tiles = c->hit_max_tiles;
+    if (max_tiles <= 0) {
+        const double slice_bytes_per_tile = (double)c->n_rows * 32.0 * V * 4.0;
+        max_tiles = (int)std::min(64.0, std::max(4.0, std::floor(64e6 / slice_bytes_per_tile)));
+    }
     const int groups = (n_tiles + max_tiles - 1) / max_tiles;
     const int tiles_per_cta = (n_tiles + groups - 1) / groups;
+    // warps per CTA: the count in [4, 8] that wastes the fewest warp slots in the last round
+    int nwarps = nwarps_opt;
+    if (nwarps <= 0) {
+        double best = -1.0;
+        for (int w = 8; w >= 4; --w) {
+            const int rounds = (tiles_per_cta + w - 1) / w;
+            const double eff = (double)tiles_per_cta / (rounds * w);
+            if (eff > best + 1e-9) {
+                best = eff;
+                nwarps = w;
+            }
+        }
+    }
+    nwarps = std::max(1, std::min(nwarps, kHitThreads / 32));
     const size_t smem = (size_t)(kRowListCap + c->bv.hstride) * 4;
-    cudaError_t e = cudaFuncSetAttribute(hitcount_bitrows_kernel<V, NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(hitcount_bitrows_kernel<V, NP, PF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     dim3 grid(qb, groups);
-    hitcount_bitrows_kernel<V, NP><<<grid, kHitThreads, smem, c->stream>>>(c->ix, c->bv, c->d_counts.as<u16>(), q_base, tiles_per_cta, n_tiles);
+    hitcount_bitrows_kernel<V, NP, PF><<<grid, nwarps * 32, smem, c->stream>>>(c->ix, c->bv, c->d_counts.as<u16>(), q_base, tiles_per_cta, n_tiles);
     return cudaGetLastError();
 }
 
-template <int V>
-static cudaError_t launch_hitcount_np(rtx_ctx* c, int q_base, int qb, u32 kmax) {
-    if (kmax < (1u << 8)) return launch_hitcount<V, 8>(c, q_base, qb);
-    if (kmax < (1u << 10)) return launch_hitcount<V, 10>(c, q_base, qb);
-    if (kmax < (1u << 11)) return launch_hitcount<V, 11>(c, q_base, qb);
-    if (kmax < (1u << 13)) return launch_hitcount<V, 13>(c, q_base, qb);
-    return launch_hitcount<V, 16>(c, q_base, qb);
+template <int V, bool PF>
+static cudaError_t launch_hitcount_np(rtx_ctx* c, int q_base, int qb, u32 kmax, int nwarps) {
+    if (kmax < (1u << 8)) return launch_hitcount<V, 8, PF>(c, q_base, qb, nwarps);
+    if (kmax < (1u << 10)) return launch_hitcount<V, 10, PF>(c, q_base, qb, nwarps);
+    if (kmax < (1u << 11)) return launch_hitcount<V, 11, PF>(c, q_base, qb, nwarps);
+    if (kmax < (1u << 13)) return launch_hitcount<V, 13, PF>(c, q_base, qb, nwarps);
+    return launch_hitcount<V, 16, PF>(c, q_base, qb, nwarps);
+}
+
+static cudaError_t launch_hitcount_tuned(rtx_ctx* c, int q_base, int qb, u32 kmax) {
+    const int tune = c->hit_tune ? c->hit_tune : 12;  // default: 2 words per lane, register double buffering
+    const int V = tune % 10 ? tune % 10 : 4;
+    const bool PF = (tune / 10) % 10 != 0;
+    const int nwarps = tune / 100;
+    if (V == 2) return PF ? launch_hitcount_np<2, true>(c, q_base, qb, kmax, nwarps) : launch_hitcount_np<2, false>(c, q_base, qb, kmax, nwarps);
+    return launch_hitcount_np<4, false>(c, q_base, qb, kmax, nwarps);
 }
 
 static int run_phase1(rtx_ctx* ctx, int q_base, int qb) {
@@ -621,7 +659,7 @@ static int run_phase1(rtx_ctx* ctx, int q_base, int qb) {
         hitcount_csr_kernel<<<grid, kCsrThreads, smem, ctx->stream>>>(ctx->ix, ctx->bv, ctx->d_counts.as<u16>(), q_base);
         CU(cudaGetLastError());
     } else {
-        CU(launch_hitcount_np<4>(ctx, q_base, qb, kmax));
+        CU(launch_hitcount_tuned(ctx, q_base, qb, kmax));
     }
     return RTX_OK;
 }
@@ -650,7 +688,7 @@ static int run_all(rtx_ctx* ctx) {
         {
             LaunchTimer lt(ctx, RTX_K_PROB);
             const int grid = std::min(ctx->prob_slots, qb);
-            prob_lineage_kernel<<<grid, kProbThreads, ctx->prob_smem, ctx->stream>>>(ctx->ix, bv, ctx->pool, ctx->sc, ctx->d_counts.as<u16>(),
+            prob_lineage_kernel<<<grid, kProbThreads, ctx->prob_smem, ctx->stream>>>(ctx->ix, ctx->d_recs.as<NodeRec>(), bv, ctx->pool, ctx->sc, ctx->d_counts.as<u16>(),
                                                                                    (int)q0, qb, ctx->d_hits.as<unsigned long long>());
             CU(cudaGetLastError());
         }
