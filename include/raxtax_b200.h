@@ -167,7 +167,7 @@ typedef struct {
     double total_ms;     /* sum of CUDA-event durations (only with RTX_OPT_PROFILE) */
 } rtx_kernel_stat;
 
-enum { RTX_K_KMERS = 0, RTX_K_HITCOUNT = 1, RTX_K_FIXUP = 2, RTX_K_PROB = 3, RTX_K_INDEX = 4, RTX_K_COUNT = 5 };
+enum { RTX_K_KMERS = 0, RTX_K_HITCOUNT = 1, RTX_K_FIXUP = 2, RTX_K_PROB = 3, RTX_K_INDEX = 4, RTX_K_WALK = 5, RTX_K_COUNT = 6 };
 
 typedef struct {
     rtx_kernel_stat kernel[RTX_K_COUNT];

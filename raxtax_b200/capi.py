@@ -22,7 +22,7 @@ RTX_OK, RTX_ERR_INVALID, RTX_ERR_CUDA, RTX_ERR_NO_DEVICE, RTX_ERR_NO_INDEX, RTX_
 RTX_SKIP_EXACT_MATCHES, RTX_RAW_CONFIDENCE = 1, 2
 RTX_HITCOUNT_BITROWS, RTX_HITCOUNT_CSR = 0, 1
 RTX_OPT_HITCOUNT_VARIANT, RTX_OPT_SUB_BATCH, RTX_OPT_KEEP_CSR, RTX_OPT_PROFILE, RTX_OPT_HITCOUNT_TUNE, RTX_OPT_HITCOUNT_MAX_TILES = 1, 2, 3, 4, 5, 6
-KERNEL_NAMES = ["kmers", "hitcount", "fixup", "prob", "index"]
+KERNEL_NAMES = ["kmers", "hitcount", "fixup", "prob", "index", "walk"]
 
 # every symbol include/raxtax_b200.h declares
 DEVICE_SYMBOLS = [
@@ -63,7 +63,7 @@ class KernelStat(C.Structure):
 
 
 class Profile(C.Structure):
-    _fields_ = [("kernel", KernelStat * 5), ("queries", C.c_uint64), ("hits", C.c_uint64), ("bitrow_bytes", C.c_uint64),
+    _fields_ = [("kernel", KernelStat * 6), ("queries", C.c_uint64), ("hits", C.c_uint64), ("bitrow_bytes", C.c_uint64),
                 ("csr_equiv_bytes", C.c_uint64), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64)]
 
 
@@ -294,8 +294,8 @@ class Context:
     def _alloc_results(self, nq, cap, max_len, taps):
         ML = max(self.max_levels, 1)
         kmax = max(max_len - 7, 0)
-        out = ClassifyOutput(np.zeros(nq, np.uint16), np.zeros(nq + 1, np.uint32), np.zeros(nq, np.float64), np.zeros(cap, np.uint32),
-                             np.zeros(cap, np.uint8), np.zeros((cap, ML), np.float64), np.zeros(cap, np.float64))
+        out = ClassifyOutput(np.zeros(nq, np.uint16), np.zeros(nq + 1, np.uint32), np.zeros(nq, np.float64), np.empty(cap, np.uint32),
+                             np.empty(cap, np.uint8), np.empty((cap, ML), np.float64), np.empty(cap, np.float64))
         r = ResultsStruct()
         r.n_kmers = _ptr(out.n_kmers, C.c_uint16)
         r.result_begin = _ptr(out.result_begin, C.c_uint32)
@@ -332,12 +332,13 @@ class Context:
         nq = b.n_queries
         so = keep[0]
         max_len = int((so[1:] - so[:-1]).max()) if nq else 0
-        cap = nq * 4 + 64
+        cap = max(nq * 8 + 64, getattr(self, "_cap_hint", 0))
         while True:
             out, r = self._alloc_results(nq, cap, max_len, taps)
             rc = L.rtx_classify_batch(self._h, C.byref(b), C.byref(r))
             if rc == RTX_ERR_INVALID and r.n_results > cap:
-                cap = int(r.n_results) + 64
+                cap = int(r.n_results) + int(r.n_results) // 4 + 64
+                self._cap_hint = cap
                 continue
             self._check(rc)
             return self._trim(out, int(r.n_results))
@@ -355,12 +356,13 @@ class Context:
     def batch_download(self, taps=()) -> ClassifyOutput:
         L = device_lib()
         nq, max_len = self._batch_info
-        cap = nq * 4 + 64
+        cap = max(nq * 8 + 64, getattr(self, "_cap_hint", 0))
         while True:
             out, r = self._alloc_results(nq, cap, max_len, taps)
             rc = L.rtx_batch_download(self._h, C.byref(r))
             if rc == RTX_ERR_INVALID and r.n_results > cap:
-                cap = int(r.n_results) + 64
+                cap = int(r.n_results) + int(r.n_results) // 4 + 64
+                self._cap_hint = cap
                 continue
             self._check(rc)
             return self._trim(out, int(r.n_results))

@@ -461,56 +461,35 @@ __global__ void fixup_exact_kernel(IndexView ix, BatchView b, u16* __restrict__ 
 // =========================================================================================================
 constexpr int kProbThreads = 256;
 constexpr int kProbWarps = kProbThreads / 32;
-constexpr int kEntCap = 2048;  // frontier entries of the tree walk held in shared memory (<= 200 per level)
-
 struct ProbScratch {
     double* cbuf;        // [slots][cbuf_stride] r_m[i] = pmf_m(i) / cmf_m(i) of the slow branch, row d = distinct count d
     size_t cbuf_stride;  // = hstride * tstride doubles
     u32 tstride;         // doubles per cbuf row ( >= max t + 1 )
-    double* preb;        // [slots][preb_stride] prefix sums of normalised probabilities at node boundaries
+    double* preb;        // [sub-batch queries][preb_stride] prefix sums of normalised probabilities at node boundaries
     size_t preb_stride;
 };
 
-// dynamic smem carve-up (sizes depend on H = hstride, T1 = H/2 + 1, ML = max_levels)
+// dynamic smem carve-up (sizes depend on H = hstride, T1 = H/2 + 1)
 struct ProbSmem {
     double* Ptab;   // [H]   P(m)/S, direct-indexed by count
     double* dval;   // [H]   per distinct count: running cmf (pass 1) / P (pass 2)
     double* dcar;   // [H]   per distinct count: ln of the running cmf
     double* g;      // [T1]  ln i! + ln (t-i)!
     double* prod;   // [T1]  sum_m h[m] * ln cmf_m(i), then E[i] = exp(prod[i])
-    double* res_local;  // [RTX_MAX_RESULTS_PER_QUERY]
     u32* hist;      // [H]
     u32* dh;        // [H]   multiplicity of distinct count d
-    u32* res_first; // [RTX_MAX_RESULTS_PER_QUERY]
-    u32* ent_node;  // [kEntCap]
     u16* dm;        // [H]   distinct counts ascending
-    u16* ent_parent;  // [kEntCap]
-    u16* order;       // [RTX_MAX_RESULTS_PER_QUERY]
-    u8* ent_k;        // [kEntCap] rounded confidence in hundredths
-    u8* res_nlev;     // [RTX_MAX_RESULTS_PER_QUERY]
-    u8* res_k;        // [RTX_MAX_RESULTS_PER_QUERY][ML] rounded confidences in hundredths
-    __host__ __device__ ProbSmem(unsigned char* base, u32 H, u32 T1, u32 ML) {
+    __host__ __device__ ProbSmem(unsigned char* base, u32 H, u32 T1) {
         Ptab = reinterpret_cast<double*>(base);
         dval = Ptab + H;
         dcar = dval + H;
         g = dcar + H;
         prod = g + T1;
-        res_local = prod + T1;
-        hist = reinterpret_cast<u32*>(res_local + RTX_MAX_RESULTS_PER_QUERY);
+        hist = reinterpret_cast<u32*>(prod + T1);
         dh = hist + H;
-        res_first = dh + H;
-        ent_node = res_first + RTX_MAX_RESULTS_PER_QUERY;
-        dm = reinterpret_cast<u16*>(ent_node + kEntCap);
-        ent_parent = dm + H;
-        order = ent_parent + kEntCap;
-        ent_k = reinterpret_cast<u8*>(order + RTX_MAX_RESULTS_PER_QUERY);
-        res_nlev = ent_k + kEntCap;
-        res_k = res_nlev + RTX_MAX_RESULTS_PER_QUERY;
+        dm = reinterpret_cast<u16*>(dh + H);
     }
-    static size_t bytes(u32 H, u32 T1, u32 ML) {
-        return (size_t)H * (8 * 3 + 4 * 2 + 2) + (size_t)T1 * 16 + (size_t)RTX_MAX_RESULTS_PER_QUERY * (ML + 8 + 4 + 2 + 1) +
-               (size_t)kEntCap * (4 + 2 + 1) + 64;
-    }
+    static size_t bytes(u32 H, u32 T1) { return (size_t)H * (8 * 3 + 4 * 2 + 2) + (size_t)T1 * 16 + 64; }
 };
 
 // node record: one 16-byte load gives everything the walk needs about a child
@@ -520,30 +499,26 @@ struct __align__(16) NodeRec {
     u32 cc_type;       // child_count | node_type << 30
 };
 
+// K3 + K4: per query, P(count) table -> normalise -> global signal -> prefix sums at the node boundaries.
+// Outputs: preb[ql][*] (HBM), pool.global_sig[q], pool.status[q] (kQOk / kQProbSumZero).
 __global__ void __launch_bounds__(kProbThreads)
-    prob_lineage_kernel(IndexView ix, const NodeRec* __restrict__ recs, BatchView b, ResultPool pool, ProbScratch sc,
-                        const u16* __restrict__ counts, int q_base, int q_count, unsigned long long* __restrict__ hits_total) {
+    prob_prefix_kernel(IndexView ix, BatchView b, ResultPool pool, ProbScratch sc, const u16* __restrict__ counts, int q_base, int q_count,
+                       unsigned long long* __restrict__ hits_total) {
     extern __shared__ __align__(16) unsigned char psm_raw[];
     __shared__ double red[40];
     __shared__ double part[kProbWarps][32];
     __shared__ u32 wsum[kProbWarps];
     __shared__ double wtot[kProbWarps];
-    __shared__ u32 sh_ent_end, sh_nres, sh_flags;
-    __shared__ u32 chain_nodes[kProbWarps][RTX_MAX_LEVELS + 1];
-    __shared__ u8 chain_k[kProbWarps][RTX_MAX_LEVELS + 1];
-    __shared__ unsigned long long sh_base;
 
     const u32 H = b.hstride;
     const u32 T1 = H / 2 + 1;
-    const u32 ML = ix.max_levels;
-    ProbSmem sm(psm_raw, H, T1, ML);
+    ProbSmem sm(psm_raw, H, T1);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const double* __restrict__ lf = ix.lnfact;
     const double NEG_INF = -CUDART_INF;
     const double Nd = (double)ix.n_refs;
 
     double* cbuf = sc.cbuf + (size_t)blockIdx.x * sc.cbuf_stride;
-    double* preb = sc.preb + (size_t)blockIdx.x * sc.preb_stride;
 
     for (int ql = blockIdx.x; ql < q_count; ql += gridDim.x) {
         const int q = q_base + ql;
@@ -551,6 +526,7 @@ __global__ void __launch_bounds__(kProbThreads)
         const u32 t = K / 2;  // raxtax.rs:57
         const u32* __restrict__ ghist = b.hist + (size_t)q * H;
         const u16* __restrict__ qcounts = counts + (size_t)ql * ix.n_pad;
+        double* __restrict__ preb = sc.preb + (size_t)ql * sc.preb_stride;
         __syncthreads();  // smem reuse across queries
 
         // ---- histogram -> distinct counts (ascending), prob.rs:13-19 ------------------------------------
@@ -574,11 +550,6 @@ __global__ void __launch_bounds__(kProbThreads)
                 ++dpos;
             }
             sm.Ptab[m] = 0.0;
-        }
-        if (tid == 0) {
-            sh_ent_end = 1;
-            sh_nres = 0;
-            sh_flags = 0;
         }
         __syncthreads();
         // postings a CSR walk would have touched for this query = sum_r count[r]
@@ -728,127 +699,206 @@ __global__ void __launch_bounds__(kProbThreads)
                 carry += tot;
                 __syncthreads();
             }
-            if (tid == 0) {
-                preb[0] = 0.0;
-                sm.ent_node[0] = 0;  // root
-                sm.ent_parent[0] = 0xFFFF;
-                sm.ent_k[0] = 0;
-            }
-            __syncthreads();
+            if (tid == 0) preb[0] = 0.0;
         }
+        if (tid == 0) {
+            pool.global_sig[q] = global_signal;
+            pool.status[q] = bad_sum ? kQProbSumZero : kQOk;
+        }
+    }
+}
 
-        // ---- tree walk (lineage.rs:119-179), level-synchronous: one warp per visited node ----------------
-        // The reference recurses depth-first and then sorts stably by the confidence vectors; emitting nodes have
-        // disjoint reference ranges, so "depth-first order" == "ascending first reference id", which the sort below
-        // uses as its tie-break.  Entry = (node, parent entry, rounded confidence in hundredths).
-        if (!bad_sum) {
-            u32 lvl_begin = 0, lvl_end = 1;
-            int depth = 0;  // path length of the entries of this level
-            while (lvl_begin < lvl_end) {
-                for (u32 e = lvl_begin + warp; e < lvl_end; e += kProbWarps) {
-                    const u32 node = sm.ent_node[e];
-                    const NodeRec nr = recs[node];
-                    const u32 cf = nr.child_first, cc = nr.cc_type & 0x3FFFFFFFu, ntype = nr.cc_type >> 30;
-                    bool any = false;
-                    for (u32 cb = 0; cb < cc; cb += 32) {
-                        const u32 ci = cb + lane;
-                        u32 k = 0;
-                        if (ci < cc) {
-                            const NodeRec cr = recs[cf + ci];
-                            const double conf = preb[cr.bhi] - preb[cr.blo];
-                            k = (u32)round(conf * 100.0);  // round(conf*100)/100 != 0  <=>  k != 0 (lineage.rs:129-131)
-                        }
-                        const u32 mask = __ballot_sync(kFullMask, k != 0);
-                        if (mask) {
-                            any = true;
-                            u32 base_slot = 0;
-                            if (lane == 0) base_slot = atomicAdd(&sh_ent_end, (u32)__popc(mask));
-                            base_slot = __shfl_sync(kFullMask, base_slot, 0);
-                            if (k != 0) {
-                                const u32 slot = base_slot + __popc(mask & ((1u << lane) - 1u));
-                                if (slot < kEntCap) {
-                                    sm.ent_node[slot] = cf + ci;
-                                    sm.ent_parent[slot] = (u16)e;
-                                    sm.ent_k[slot] = (u8)min(k, 255u);
-                                } else if (lane == (__ffs(mask) - 1)) atomicOr(&sh_flags, 1u);
-                            }
-                        }
-                    }
-                    if (any) continue;
-                    // no significant child: a Taxon is emitted as it is (lineage.rs:142-148), an Inner node follows its
-                    // best children down to a non-Inner node with 0.01 per level (lineage.rs:151-177)
-                    if (ntype == 2 || (ntype == 1 && depth == 0)) continue;
-                    int d = depth;
-                    u32 cur = node;
-                    if (ntype == 0) {
-                        u32 cur_cf = cf, cur_cc = cc, cur_type = 0;
-                        while (cur_type == 0) {
-                            // max_by(partial_cmp): the LAST maximal child wins (lineage.rs:156-164).  Children tied in exact
-                            // arithmetic (same hit counts) differ here only by rounding noise of the prefix sums, so values
-                            // within 1e-12 relative of the maximum count as maximal.
-                            double best = -CUDART_INF;
-                            for (u32 cb = 0; cb < cur_cc; cb += 32) {
-                                const u32 ci = cb + lane;
-                                if (ci < cur_cc) {
-                                    const NodeRec cr = recs[cur_cf + ci];
-                                    best = fmax(best, preb[cr.bhi] - preb[cr.blo]);
+// =========================================================================================================
+// K5: tree walk, ordering, override, emission.  One warp per query (thousands of independent walkers hide the
+// latency of the dependent loads); 4 warps per CTA.
+//
+// Lineage::eval_recurse (lineage.rs:119-179) as an explicit depth-first stack: a frame is (node, next child to
+// look at, "had a significant child").  Confidences are carried as integers k = round(conf*100), so that the
+// reported value k/100 is bit-identical to the reference's round(conf*100)/100.
+// =========================================================================================================
+constexpr int kWalkWarps = 1;  // one warp per CTA: a slot frees as soon as its walker finishes (walk lengths vary a lot)
+
+// per-warp shared state; res_k rows have stride ML
+struct WalkSmem {
+    double* res_local;  // [R]
+    u32* res_first;     // [R]
+    u32* st_node;       // [RTX_MAX_LEVELS + 1]
+    u32* st_next;
+    u32* st_cf;         // child_first of the frame's node
+    u32* st_cc;         // child_count | type << 30 of the frame's node
+    u32* path_node;     // [RTX_MAX_LEVELS + 1]
+    u16* order;         // [R]
+    u8* res_nlev;       // [R]
+    u8* res_k;          // [R][ML]
+    u8* st_any;         // [RTX_MAX_LEVELS + 1]
+    u8* path_k;         // [RTX_MAX_LEVELS + 1]
+    static constexpr u32 R = RTX_MAX_RESULTS_PER_QUERY;
+    static constexpr u32 L1 = RTX_MAX_LEVELS + 1;
+    __host__ __device__ static size_t bytes(u32 ML) {
+        size_t b = (size_t)R * (8 + 4 + 2 + 1 + ML) + (size_t)L1 * (4 * 5 + 2);
+        return (b + 15) & ~(size_t)15;
+    }
+    __device__ WalkSmem(unsigned char* base, u32 ML) {
+        res_local = reinterpret_cast<double*>(base);
+        res_first = reinterpret_cast<u32*>(res_local + R);
+        st_node = res_first + R;
+        st_next = st_node + L1;
+        st_cf = st_next + L1;
+        st_cc = st_cf + L1;
+        path_node = st_cc + L1;
+        order = reinterpret_cast<u16*>(path_node + L1);
+        res_nlev = reinterpret_cast<u8*>(order + R);
+        res_k = res_nlev + R;
+        st_any = res_k + (size_t)R * ML;
+        path_k = st_any + L1;
+    }
+};
+
+__global__ void __launch_bounds__(kWalkWarps * 32)
+    lineage_walk_kernel(IndexView ix, const NodeRec* __restrict__ recs, BatchView b, ResultPool pool, ProbScratch sc, int q_base, int q_count) {
+    extern __shared__ __align__(16) unsigned char wsm_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int ql = blockIdx.x * kWalkWarps + warp;
+    if (ql >= q_count) return;
+    const int q = q_base + ql;
+    const u32 ML = ix.max_levels;
+    WalkSmem ws(wsm_raw + (size_t)warp * WalkSmem::bytes(ML), ML);
+    const double Nd = (double)ix.n_refs;
+    const double* __restrict__ preb = sc.preb + (size_t)ql * sc.preb_stride;
+    int status = pool.status[q];
+
+    u32 n_res = 0;
+    bool overflow = false;
+    if (status == kQOk) {
+        int depth = 0;
+        if (lane == 0) {
+            const NodeRec root = recs[0];
+            ws.st_node[0] = 0;
+            ws.st_next[0] = 0;
+            ws.st_any[0] = 0;
+            ws.st_cf[0] = root.child_first;
+            ws.st_cc[0] = root.cc_type;
+        }
+        __syncwarp();
+        while (depth >= 0) {
+            const u32 node = ws.st_node[depth];
+            const u32 cf = ws.st_cf[depth], cct = ws.st_cc[depth];
+            const u32 cc = cct & 0x3FFFFFFFu, ntype = cct >> 30;
+            u32 nxt = ws.st_next[depth];
+            bool found = false;
+            u32 child = 0, ck = 0, ccf = 0, ccc = 0;
+            for (u32 cb = nxt; cb < cc; cb += 32) {
+                const u32 ci = cb + lane;
+                u32 k = 0;
+                NodeRec cr = NodeRec{0, 0, 0, 0};
+                if (ci < cc) {
+                    cr = recs[cf + ci];
+                    k = (u32)round((preb[cr.bhi] - preb[cr.blo]) * 100.0);  // f64::round, half away from zero (lineage.rs:129)
+                }
+                const u32 mask = __ballot_sync(kFullMask, k != 0);
+                if (mask) {
+                    const int j = __ffs(mask) - 1;
+                    child = cf + cb + j;
+                    ck = __shfl_sync(kFullMask, k, j);
+                    ccf = __shfl_sync(kFullMask, cr.child_first, j);
+                    ccc = __shfl_sync(kFullMask, cr.cc_type, j);
+                    nxt = cb + j + 1;
+                    found = true;
+                    break;
+                }
+            }
+            if (found) {
+                if (depth >= RTX_MAX_LEVELS) {
+                    overflow = true;
+                    break;
+                }
+                if (lane == 0) {
+                    ws.st_next[depth] = nxt;
+                    ws.st_any[depth] = 1;
+                    ws.path_node[depth] = child;
+                    ws.path_k[depth] = (u8)min(ck, 255u);
+                    ws.st_node[depth + 1] = child;
+                    ws.st_next[depth + 1] = 0;
+                    ws.st_any[depth + 1] = 0;
+                    ws.st_cf[depth + 1] = ccf;
+                    ws.st_cc[depth + 1] = ccc;
+                }
+                __syncwarp();
+                ++depth;
+                continue;
+            }
+            // children exhausted
+            if (!ws.st_any[depth] && ntype != 2 && !(ntype == 1 && depth == 0)) {
+                int d = depth;
+                u32 cur = node;
+                if (ntype == 0) {  // Inner without a significant child: follow the best children (lineage.rs:151-177)
+                    u32 cur_cf = cf, cur_cc = cc, cur_type = 0;
+                    while (cur_type == 0 && d < RTX_MAX_LEVELS) {
+                        // max_by(partial_cmp): the LAST maximal child wins (lineage.rs:156-164).  Children tied in exact
+                        // arithmetic (same hit counts) differ here only by rounding noise of the prefix sums, so values
+                        // within 1e-12 relative of the maximum count as maximal.
+                        double best = -CUDART_INF;
+                        double cv0 = -CUDART_INF;      // this lane's child of the first 32 (kept for the second pass)
+                        NodeRec cr0 = NodeRec{0, 0, 0, 0};
+                        for (u32 cb = 0; cb < cur_cc; cb += 32) {
+                            const u32 ci = cb + lane;
+                            if (ci < cur_cc) {
+                                const NodeRec cr = recs[cur_cf + ci];
+                                const double v = preb[cr.bhi] - preb[cr.blo];
+                                if (cb == 0) {
+                                    cv0 = v;
+                                    cr0 = cr;
                                 }
+                                best = fmax(best, v);
                             }
-#pragma unroll
-                            for (int o = 16; o > 0; o >>= 1) best = fmax(best, __shfl_xor_sync(kFullMask, best, o));
-                            const double thr = best - fabs(best) * 1e-12;
-                            u32 besti = 0;
-                            for (u32 cb = 0; cb < cur_cc; cb += 32) {
-                                const u32 ci = cb + lane;
-                                if (ci < cur_cc) {
-                                    const NodeRec cr = recs[cur_cf + ci];
-                                    if (preb[cr.bhi] - preb[cr.blo] >= thr) besti = ci;
-                                }
-                            }
-#pragma unroll
-                            for (int o = 16; o > 0; o >>= 1) besti = max(besti, __shfl_xor_sync(kFullMask, besti, o));
-                            cur = cur_cf + besti;
-                            const NodeRec br = recs[cur];
-                            if (lane == 0 && d < RTX_MAX_LEVELS) {
-                                chain_nodes[warp][d] = cur;
-                                chain_k[warp][d] = 1;  // 1.0 / rounding_factor
-                            }
-                            ++d;
-                            cur_cf = br.child_first;
-                            cur_cc = br.cc_type & 0x3FFFFFFFu;
-                            cur_type = br.cc_type >> 30;
-                            if (d > RTX_MAX_LEVELS) break;
                         }
-                    }
-                    // path of the visited node itself: follow the parent links (depth entries)
-                    if (lane == 0) {
-                        u32 pe = e;
-                        for (int l = depth - 1; l >= 0; --l) {
-                            chain_nodes[warp][l] = sm.ent_node[pe];
-                            chain_k[warp][l] = sm.ent_k[pe];
-                            pe = sm.ent_parent[pe];
+#pragma unroll
+                        for (int o = 16; o > 0; o >>= 1) best = fmax(best, __shfl_xor_sync(kFullMask, best, o));
+                        const double thr = best - fabs(best) * 1e-12;
+                        u32 besti = 0;
+                        if (lane < cur_cc && cv0 >= thr) besti = lane;
+                        for (u32 cb = 32; cb < cur_cc; cb += 32) {
+                            const u32 ci = cb + lane;
+                            if (ci < cur_cc) {
+                                const NodeRec cr = recs[cur_cf + ci];
+                                if (preb[cr.bhi] - preb[cr.blo] >= thr) besti = ci;
+                            }
                         }
+#pragma unroll
+                        for (int o = 16; o > 0; o >>= 1) besti = max(besti, __shfl_xor_sync(kFullMask, besti, o));
+                        cur = cur_cf + besti;
+                        NodeRec br;
+                        if (besti < 32) {  // the winner's record is already in a register of lane besti
+                            br.child_first = __shfl_sync(kFullMask, cr0.child_first, besti);
+                            br.cc_type = __shfl_sync(kFullMask, cr0.cc_type, besti);
+                        } else {
+                            br = recs[cur];
+                        }
+                        if (lane == 0) {
+                            ws.path_node[d] = cur;
+                            ws.path_k[d] = 1;  // 1.0 / rounding_factor
+                        }
+                        ++d;
+                        cur_cf = br.child_first;
+                        cur_cc = br.cc_type & 0x3FFFFFFFu;
+                        cur_type = br.cc_type >> 30;
                     }
-                    __syncwarp();
-                    u32 slot = 0;
-                    if (lane == 0) slot = atomicAdd(&sh_nres, 1u);
-                    slot = __shfl_sync(kFullMask, slot, 0);
-                    if (slot >= RTX_MAX_RESULTS_PER_QUERY || d > RTX_MAX_LEVELS) {
-                        if (lane == 0) atomicOr(&sh_flags, 1u);
-                        continue;
-                    }
-                    // confidence and expected vectors of this line; local signal (lineage.rs:95-102, utils.rs:91-105)
+                    if (cur_type == 0) overflow = true;
+                }
+                __syncwarp();
+                if (n_res >= RTX_MAX_RESULTS_PER_QUERY) overflow = true;
+                if (!overflow) {
+                    // confidence / expected vectors of this line; local signal (lineage.rs:95-102, utils.rs:91-105)
                     double cv = 0.0, ev = 0.0;
                     if (lane < d) {
-                        const u32 nd = chain_nodes[warp][lane];
-                        cv = (double)chain_k[warp][lane] / 100.0;  // == round(conf*100)/100 of the reference
+                        const u32 nd = ws.path_node[lane];
+                        cv = (double)ws.path_k[lane] / 100.0;
                         ev = (double)(ix.node_hi[nd] - ix.node_lo[nd]) / Nd;
-                        sm.res_k[(size_t)slot * ML + lane] = chain_k[warp][lane];
+                        ws.res_k[(size_t)n_res * ML + lane] = ws.path_k[lane];
                     }
                     const u32 lt1 = __ballot_sync(kFullMask, lane < d && 1.0 > ev);
                     const int start = lt1 ? (__ffs(lt1) - 1) : (d - 1);
-                    // sequential sums like the reference (lane order = level order)
-                    double a_sum = 0.0, b_sum = 0.0;
+                    double a_sum = 0.0, b_sum = 0.0;  // sequential sums, level order, like the reference
                     for (int i2 = start; i2 < d; ++i2) {
                         a_sum += __shfl_sync(kFullMask, cv, i2);
                         b_sum += __shfl_sync(kFullMask, ev, i2);
@@ -859,96 +909,87 @@ __global__ void __launch_bounds__(kProbThreads)
                         s2 += df * df;
                     }
                     if (lane == 0) {
-                        sm.res_local[slot] = sqrt(s2);
-                        sm.res_first[slot] = ix.node_lo[cur];
-                        sm.res_nlev[slot] = (u8)d;
+                        ws.res_local[n_res] = sqrt(s2);
+                        ws.res_first[n_res] = ix.node_lo[cur];
+                        ws.res_nlev[n_res] = (u8)d;
                     }
+                    ++n_res;
                 }
-                __syncthreads();
-                lvl_begin = lvl_end;
-                lvl_end = min(sh_ent_end, (u32)kEntCap);
-                ++depth;
-                __syncthreads();
+                if (overflow) break;
             }
+            --depth;
+            __syncwarp();
         }
-        __syncthreads();
-        // ---- order (lineage.rs:93): descending lexicographic on the confidence vectors, ties in depth-first order ----
-        const u32 n_res = min(sh_nres, (u32)RTX_MAX_RESULTS_PER_QUERY);
-        int status = kQOk;
-        if (bad_sum) status = kQProbSumZero;
-        else if (sh_flags & 1u) status = kQTooManyResults;
+        __syncwarp();
+        if (overflow) status = kQTooManyResults;
         else if (n_res == 0) status = kQEmptyResult;  // assert!(!eval_res.is_empty()) raxtax.rs:72
-        for (u32 i = tid; i < n_res; i += kProbThreads) {
-            const u8* ci = sm.res_k + (size_t)i * ML;
-            const u32 li = sm.res_nlev[i], fi = sm.res_first[i];
+    }
+    // ---- order (lineage.rs:93): stable sort, descending lexicographic on the confidence vectors.  Results were pushed
+    // in depth-first order, so the tie-break is the push index.
+    if (status == kQOk) {
+        for (u32 i = lane; i < n_res; i += 32) {
+            const u8* ci = ws.res_k + (size_t)i * ML;
+            const u32 li = ws.res_nlev[i];
             u32 rank = 0;
             for (u32 j = 0; j < n_res; ++j) {
                 if (j == i) continue;
-                const u8* cj = sm.res_k + (size_t)j * ML;
-                const u32 lj = sm.res_nlev[j];
-                // does j sort before i?  conf_j > conf_i lexicographically (a longer vector wins on an equal prefix),
-                // or the vectors are equal and j comes first in depth-first order
-                int cmp = 0;  // +1: j > i, -1: j < i
+                const u8* cj = ws.res_k + (size_t)j * ML;
+                const u32 lj = ws.res_nlev[j];
+                int cmp = 0;  // +1: vector j > vector i
                 for (u32 l = 0; l < min(li, lj); ++l) {
-                    if (cj[l] > ci[l]) {
-                        cmp = 1;
-                        break;
-                    }
-                    if (cj[l] < ci[l]) {
-                        cmp = -1;
+                    if (cj[l] != ci[l]) {
+                        cmp = cj[l] > ci[l] ? 1 : -1;
                         break;
                     }
                 }
                 if (cmp == 0) cmp = (lj > li) ? 1 : (lj < li) ? -1 : 0;
-                if (cmp > 0 || (cmp == 0 && sm.res_first[j] < fi)) ++rank;
+                if (cmp > 0 || (cmp == 0 && j < i)) ++rank;
             }
-            sm.order[rank] = (u16)i;
+            ws.order[rank] = (u16)i;
         }
-        __syncthreads();
-        // ---- override (raxtax.rs:73-84) and emission into the result pool ---------------------------------------
-        u32 n_out = n_res;
-        bool ovr = false;
-        u32 ovr_idx = 0;
-        if (status == kQOk && !(b.flags & RTX_RAW_CONFIDENCE) && !(b.flags & RTX_SKIP_EXACT_MATCHES) && b.exact_off) {
-            if (b.exact_off[q + 1] - b.exact_off[q] == 1) {
-                ovr = true;
-                ovr_idx = b.exact_ids[b.exact_off[q]];
-                n_out = 1;
-            }
+    }
+    __syncwarp();
+    // ---- override (raxtax.rs:73-84) and emission into the result pool ---------------------------------------
+    u32 n_out = (status == kQOk) ? n_res : 0;
+    bool ovr = false;
+    u32 ovr_idx = 0;
+    if (status == kQOk && !(b.flags & RTX_RAW_CONFIDENCE) && !(b.flags & RTX_SKIP_EXACT_MATCHES) && b.exact_off) {
+        if (b.exact_off[q + 1] - b.exact_off[q] == 1) {
+            ovr = true;
+            ovr_idx = b.exact_ids[b.exact_off[q]];
+            n_out = 1;
         }
-        if (status != kQOk) n_out = 0;
-        if (tid == 0) sh_base = atomicAdd(pool.used, (unsigned long long)n_out);
-        __syncthreads();
-        const unsigned long long base = sh_base;
-        if (base + n_out > pool.cap) {
-            if (status == kQOk) status = kQPoolOverflow;
-        } else if (ovr) {
-            const u32 nl = ix.ref_levels[ovr_idx];
-            if (tid == 0) {
-                pool.first_ref[base] = ovr_idx;
-                pool.n_levels[base] = (u8)nl;
-                pool.local[base] = sm.res_local[sm.order[0]];
-            }
-            for (u32 l = tid; l < ML; l += kProbThreads) pool.conf[base * ML + l] = (l < nl) ? 1.0 : 0.0;
-        } else {
-            for (u32 x = tid; x < n_out * ML; x += kProbThreads) {
-                const u32 i = x / ML, l = x - i * ML;
-                const u32 src = sm.order[i];
-                pool.conf[(base + i) * ML + l] = (l < sm.res_nlev[src]) ? (double)sm.res_k[(size_t)src * ML + l] / 100.0 : 0.0;
-            }
-            for (u32 i = tid; i < n_out; i += kProbThreads) {
-                const u32 src = sm.order[i];
-                pool.first_ref[base + i] = sm.res_first[src];
-                pool.n_levels[base + i] = sm.res_nlev[src];
-                pool.local[base + i] = sm.res_local[src];
-            }
+    }
+    unsigned long long base = 0;
+    if (lane == 0) base = atomicAdd(pool.used, (unsigned long long)n_out);
+    base = __shfl_sync(kFullMask, base, 0);
+    if (base + n_out > pool.cap) {
+        if (status == kQOk) status = kQPoolOverflow;
+    } else if (ovr) {
+        const u32 nl = ix.ref_levels[ovr_idx];
+        if (lane == 0) {
+            pool.first_ref[base] = ovr_idx;
+            pool.n_levels[base] = (u8)nl;
+            pool.local[base] = ws.res_local[ws.order[0]];
         }
-        if (tid == 0) {
-            pool.res_off[q] = (u32)base;
-            pool.res_cnt[q] = n_out;
-            pool.global_sig[q] = global_signal;
-            pool.status[q] = status;
+        for (u32 l = lane; l < ML; l += 32) pool.conf[base * ML + l] = (l < nl) ? 1.0 : 0.0;
+    } else {
+        for (u32 x = lane; x < n_out * ML; x += 32) {
+            const u32 i = x / ML, l = x - i * ML;
+            const u32 src = ws.order[i];
+            pool.conf[(base + i) * ML + l] = (l < ws.res_nlev[src]) ? (double)ws.res_k[(size_t)src * ML + l] / 100.0 : 0.0;
         }
+        for (u32 i = lane; i < n_out; i += 32) {
+            const u32 src = ws.order[i];
+            pool.first_ref[base + i] = ws.res_first[src];
+            pool.n_levels[base + i] = ws.res_nlev[src];
+            pool.local[base + i] = ws.res_local[src];
+        }
+    }
+    if (lane == 0) {
+        pool.res_off[q] = (u32)base;
+        pool.res_cnt[q] = n_out;
+        pool.status[q] = status;
     }
 }
 

@@ -50,7 +50,7 @@ struct rtx_ctx {
     // prob scratch
     ProbScratch sc{};
     int prob_slots = 0;
-    size_t prob_smem = 0;
+    size_t prob_smem = 0, walk_smem = 0;
     DevBuf d_cbuf, d_preb;
     // host staging
     std::vector<u32> h_res_off, h_res_cnt, h_nrows, h_pool_first;
@@ -497,7 +497,7 @@ RTX_API int rtx_batch_upload(rtx_ctx* ctx, const rtx_batch* batch) {
     if (kmax > 65535) return set_err(ctx, RTX_ERR_UNSUPPORTED, "query with more than 65535 8-mer windows (raxtax.rs:56 asserts the same)");
     const u32 kstride = round_up(std::max(kmax, 1u), 16);
     const u32 hstride = round_up(kmax + 1, 4);
-    const size_t smem = ProbSmem::bytes(hstride, hstride / 2 + 1, ctx->ix.max_levels);
+    const size_t smem = ProbSmem::bytes(hstride, hstride / 2 + 1);
     if (smem > 200 * 1024)
         return set_err(ctx, RTX_ERR_UNSUPPORTED, "query too long for the shared-memory probability tables (more than ~5800 unique 8-mers)");
     ctx->max_len = max_len;
@@ -573,10 +573,12 @@ RTX_API int rtx_batch_upload(rtx_ctx* ctx, const rtx_batch* batch) {
 
     // probability kernel scratch
     ctx->prob_smem = smem;
-    CU(cudaFuncSetAttribute(prob_lineage_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CU(cudaFuncSetAttribute(prob_prefix_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 0;
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, prob_lineage_kernel, kProbThreads, smem));
-    if (occ < 1) return set_err(ctx, RTX_ERR_CUDA, "prob_lineage_kernel does not fit on an SM");
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, prob_prefix_kernel, kProbThreads, smem));
+    if (occ < 1) return set_err(ctx, RTX_ERR_CUDA, "prob_prefix_kernel does not fit on an SM");
+    ctx->walk_smem = (size_t)kWalkWarps * WalkSmem::bytes(ctx->ix.max_levels);
+    CU(cudaFuncSetAttribute(lineage_walk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->walk_smem));
     const int slots = (int)std::min<u64>((u64)ctx->n_sms * occ, sb);
     ctx->prob_slots = slots;
     const u32 tstride = round_up(hstride / 2 + 1, 4);
@@ -584,7 +586,7 @@ RTX_API int rtx_batch_upload(rtx_ctx* ctx, const rtx_batch* batch) {
     ctx->sc.cbuf_stride = (size_t)hstride * tstride;
     ctx->sc.preb_stride = round_up(ctx->ix.n_bnd, 4);
     CU(ctx->d_cbuf.ensure((size_t)slots * ctx->sc.cbuf_stride * 8));
-    CU(ctx->d_preb.ensure((size_t)slots * ctx->sc.preb_stride * 8));
+    CU(ctx->d_preb.ensure((size_t)sb * ctx->sc.preb_stride * 8));
     ctx->sc.cbuf = ctx->d_cbuf.as<double>();
     ctx->sc.preb = ctx->d_preb.as<double>();
     ctx->has_batch = true;
@@ -688,8 +690,14 @@ static int run_all(rtx_ctx* ctx) {
         {
             LaunchTimer lt(ctx, RTX_K_PROB);
             const int grid = std::min(ctx->prob_slots, qb);
-            prob_lineage_kernel<<<grid, kProbThreads, ctx->prob_smem, ctx->stream>>>(ctx->ix, ctx->d_recs.as<NodeRec>(), bv, ctx->pool, ctx->sc, ctx->d_counts.as<u16>(),
-                                                                                   (int)q0, qb, ctx->d_hits.as<unsigned long long>());
+            prob_prefix_kernel<<<grid, kProbThreads, ctx->prob_smem, ctx->stream>>>(ctx->ix, bv, ctx->pool, ctx->sc, ctx->d_counts.as<u16>(), (int)q0, qb,
+                                                                                  ctx->d_hits.as<unsigned long long>());
+            CU(cudaGetLastError());
+        }
+        {
+            LaunchTimer lt(ctx, RTX_K_WALK);
+            lineage_walk_kernel<<<(qb + kWalkWarps - 1) / kWalkWarps, kWalkWarps * 32, ctx->walk_smem, ctx->stream>>>(
+                ctx->ix, ctx->d_recs.as<NodeRec>(), bv, ctx->pool, ctx->sc, (int)q0, qb);
             CU(cudaGetLastError());
         }
         if (ctx->tap_counts_host) {

@@ -666,7 +666,7 @@ RXH_API int rxh_raxtax(rtx_ctx* ctx, const rxh_queries* queries, const rxh_tree*
             n_kmers.resize(cn);
             result_begin.resize(cn + 1);
             global.resize(cn);
-            size_t cap = std::max<size_t>(first_ref.size(), cn * 4 + 64);
+            size_t cap = std::max<size_t>(first_ref.size(), cn * 8 + 64);
             while (true) {
                 first_ref.resize(cap);
                 n_levels.resize(cap);

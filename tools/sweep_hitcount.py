@@ -34,5 +34,5 @@ for t in tunes:
         ref = chk
     ms = p["hitcount"]["total_ms"] / p["hitcount"]["launches"]
     gbs = p["bitrow_bytes"] / p["hitcount"]["launches"] / ms / 1e6
-    print(json.dumps(dict(tune=t, hitcount_ms=round(ms, 3), bitrow_GBps=round(gbs, 1), prob_ms=round(p["prob"]["total_ms"] / p["prob"]["launches"], 3),
+    print(json.dumps(dict(tune=t, hitcount_ms=round(ms, 3), bitrow_GBps=round(gbs, 1), prob_ms=round(p["prob"]["total_ms"] / p["prob"]["launches"], 3), walk_ms=round(p["walk"]["total_ms"] / max(p["walk"]["launches"], 1), 3),
                           checksum_ok=chk == ref)), flush=True)
