@@ -91,6 +91,11 @@ typedef struct {
     const uint8_t* ref_levels;
     uint64_t ref_shard_begin;
     uint64_t ref_shard_end; /* 0 = n_refs */
+    /* reference-sharded operation over several contexts / ranks (0 or 1 = off): shard r holds references
+     * [shard_cuts[r], shard_cuts[r+1]); when n_shards > 1 ref_shard_begin/end are taken from shard_cuts[shard_rank]. */
+    uint32_t n_shards;
+    uint32_t shard_rank;
+    const uint64_t* shard_cuts; /* [n_shards + 1], shard_cuts[0] = 0, shard_cuts[n_shards] = n_refs */
 } rtx_index_desc;
 
 int rtx_index_upload(rtx_ctx* ctx, const rtx_index_desc* desc);
@@ -150,15 +155,22 @@ int rtx_batch_run(rtx_ctx* ctx);
 int rtx_batch_download(rtx_ctx* ctx, rtx_results* results);
 
 /* ---- reference-sharded mode (north_star: NCCL all-reduce of the per-query count histograms) -------------
- * rtx_batch_run == rtx_shard_phase1 ; [all-reduce hist] ; rtx_shard_phase2 ; [all-reduce partial] ; rtx_shard_phase3.
- * The buffers are device pointers owned by the library, valid until the next rtx_batch_upload:
- *   hist:    uint32 [n_queries * hist_stride]          summed over ranks -> global histograms
- *   partial: double [n_queries * partial_stride]       summed over ranks -> per-shard probability mass
+ * Every rank uploads the same batch.  Per batch (which must fit one sub-batch):
+ *   rtx_shard_phase1      k-mers, local hit counts, local histograms
+ *   [all-reduce SUM, in place, of the hist buffer: uint32 [n_queries * hist_stride]]     <- the only O(Q*K) exchange
+ *   rtx_shard_phase2      P(count) from the global histogram, local boundary prefixes, one record per
+ *                         (query, straddling node): local mass, local best child, local significant children
+ *   [all-gather of the records buffer: send_bytes from every rank -> recv = n_shards * send_bytes, rank order]
+ *   rtx_shard_phase3      combines the records, walks the part of the tree this rank owns
+ *   rtx_batch_download    this rank's result lines WITHOUT the one-exact-match override; the caller merges the
+ *                         ranks' lines per query (sort by confidence vector descending, first_ref ascending) and
+ *                         applies the override (raxtax.rs:73-84) -- see raxtax_b200/dist.py.
+ * The buffers are device pointers owned by the library, valid until the next rtx_batch_upload.
  */
 int rtx_shard_phase1(rtx_ctx* ctx);
 int rtx_shard_hist_buffer(rtx_ctx* ctx, void** dev_ptr, uint64_t* n_elems);
 int rtx_shard_phase2(rtx_ctx* ctx);
-int rtx_shard_partial_buffer(rtx_ctx* ctx, void** dev_ptr, uint64_t* n_elems);
+int rtx_shard_records_buffers(rtx_ctx* ctx, void** send_ptr, uint64_t* send_bytes, void** recv_ptr, uint64_t* recv_bytes);
 int rtx_shard_phase3(rtx_ctx* ctx);
 
 /* ---- measurement ---------------------------------------------------------------------------------------- */

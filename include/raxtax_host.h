@@ -43,6 +43,8 @@ size_t rxh_tree_exact(const rxh_tree* t, const uint8_t* seq, size_t len, uint32_
 int rxh_tree_index_desc(const rxh_tree* t, rtx_index_desc* out);
 /* convenience: rtx_index_upload(ctx, desc of t) restricted to references [shard_begin, shard_end) (0,0 = all) */
 int rxh_tree_upload(const rxh_tree* t, rtx_ctx* ctx, uint64_t shard_begin, uint64_t shard_end);
+/* reference-sharded upload: this context becomes shard `shard_rank` of `n_shards` (rtx_index_desc.shard_cuts) */
+int rxh_tree_upload_sharded(const rxh_tree* t, rtx_ctx* ctx, uint32_t n_shards, uint32_t shard_rank, const uint64_t* shard_cuts);
 
 /* ---- queries ----------------------------------------------------------------------------------------------- */
 rxh_queries* rxh_queries_from_fasta(const char* text, size_t len);

@@ -29,13 +29,13 @@ DEVICE_SYMBOLS = [
     "rtx_abi_version", "rtx_ctx_create", "rtx_ctx_destroy", "rtx_last_error", "rtx_ctx_set_option", "rtx_ctx_stream",
     "rtx_ctx_synchronize", "rtx_index_upload", "rtx_index_n_refs", "rtx_index_shard_refs", "rtx_index_max_levels",
     "rtx_index_device_bytes", "rtx_classify_batch", "rtx_batch_upload", "rtx_batch_run", "rtx_batch_download",
-    "rtx_shard_phase1", "rtx_shard_hist_buffer", "rtx_shard_phase2", "rtx_shard_partial_buffer", "rtx_shard_phase3",
+    "rtx_shard_phase1", "rtx_shard_hist_buffer", "rtx_shard_phase2", "rtx_shard_records_buffers", "rtx_shard_phase3",
     "rtx_profile_reset", "rtx_profile_get",
 ]
 # every symbol include/raxtax_host.h declares
 HOST_SYMBOLS = [
     "rxh_last_error", "rxh_tree_from_fasta", "rxh_tree_new", "rxh_tree_free", "rxh_tree_num_tips", "rxh_tree_lineage",
-    "rxh_tree_csr", "rxh_tree_exact", "rxh_tree_index_desc", "rxh_tree_upload", "rxh_queries_from_fasta", "rxh_queries_new",
+    "rxh_tree_csr", "rxh_tree_exact", "rxh_tree_index_desc", "rxh_tree_upload", "rxh_tree_upload_sharded", "rxh_queries_from_fasta", "rxh_queries_new",
     "rxh_queries_free", "rxh_queries_len", "rxh_queries_label", "rxh_queries_arrays", "rxh_raxtax", "rxh_exact_batch",
 ]
 
@@ -43,7 +43,8 @@ HOST_SYMBOLS = [
 class IndexDesc(C.Structure):
     _fields_ = [("n_refs", C.c_uint64), ("csr_offsets", u64p), ("csr_ids", u32p), ("n_nodes", C.c_uint32), ("node_lo", u32p),
                 ("node_hi", u32p), ("node_type", u8p), ("child_first", u32p), ("child_count", u32p), ("ref_levels", u8p),
-                ("ref_shard_begin", C.c_uint64), ("ref_shard_end", C.c_uint64)]
+                ("ref_shard_begin", C.c_uint64), ("ref_shard_end", C.c_uint64), ("n_shards", C.c_uint32), ("shard_rank", C.c_uint32),
+                ("shard_cuts", u64p)]
 
 
 class Batch(C.Structure):
@@ -112,7 +113,7 @@ def device_lib():
     for f in ("rtx_shard_phase1", "rtx_shard_phase2", "rtx_shard_phase3", "rtx_profile_reset"):
         getattr(L, f).argtypes = [C.c_void_p]
     L.rtx_shard_hist_buffer.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]
-    L.rtx_shard_partial_buffer.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]
+    L.rtx_shard_records_buffers.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64), C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]
     L.rtx_profile_get.argtypes = [C.c_void_p, C.POINTER(Profile)]
     _dev = L
     return L
@@ -144,6 +145,7 @@ def host_lib():
     L.rxh_tree_exact.argtypes = [C.c_void_p, u8p, C.c_size_t, u32p, C.c_size_t]
     L.rxh_tree_index_desc.argtypes = [C.c_void_p, C.POINTER(IndexDesc)]
     L.rxh_tree_upload.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint64]
+    L.rxh_tree_upload_sharded.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, u64p]
     L.rxh_queries_from_fasta.restype = C.c_void_p
     L.rxh_queries_from_fasta.argtypes = [C.c_char_p, C.c_size_t]
     L.rxh_queries_new.restype = C.c_void_p
@@ -272,6 +274,27 @@ class Context:
     def upload_tree(self, tree: "Tree", shard=(0, 0)):
         rc = host_lib().rxh_tree_upload(tree._h, self._h, shard[0], shard[1])
         self._check(rc)
+
+    def upload_tree_sharded(self, tree: "Tree", n_shards: int, rank: int, cuts):
+        cuts = np.ascontiguousarray(cuts, np.uint64)
+        assert len(cuts) == n_shards + 1
+        rc = host_lib().rxh_tree_upload_sharded(tree._h, self._h, n_shards, rank, _ptr(cuts, C.c_uint64))
+        self._check(rc)
+
+    # ---- reference-sharded phases (see raxtax_b200/dist.py for the exchange between them) --------------------
+    def shard_phase(self, n):
+        f = getattr(device_lib(), f"rtx_shard_phase{n}")
+        self._check(f(self._h))
+
+    def shard_hist_buffer(self):
+        p, n = C.c_void_p(), C.c_uint64()
+        self._check(device_lib().rtx_shard_hist_buffer(self._h, C.byref(p), C.byref(n)))
+        return p.value or 0, int(n.value)
+
+    def shard_records_buffers(self):
+        sp, sb, rp, rb = C.c_void_p(), C.c_uint64(), C.c_void_p(), C.c_uint64()
+        self._check(device_lib().rtx_shard_records_buffers(self._h, C.byref(sp), C.byref(sb), C.byref(rp), C.byref(rb)))
+        return (sp.value or 0, int(sb.value)), (rp.value or 0, int(rb.value))
 
     # ---- batches -------------------------------------------------------------------------------------------
     def _make_batch(self, seq_off, codes, exact_off, exact_ids, flags):

@@ -709,6 +709,122 @@ __global__ void __launch_bounds__(kProbThreads)
 }
 
 // =========================================================================================================
+// Reference-sharded mode.  A node whose reference range crosses a shard cut ("straddler") cannot be evaluated by one
+// rank: every rank contributes a record per (query, straddler) -- its local probability mass, and what it knows about
+// the straddler's children that lie wholly inside its shard -- the records are all-gathered, and each rank then walks
+// the part of the tree it owns with the combined values.
+// =========================================================================================================
+struct ShardRec {
+    double mass;     // sum of normalised probabilities of the straddler's references inside this shard
+    double best;     // largest confidence among the straddler's non-straddling children inside this shard (-inf if none)
+    u32 best_child;  // node id of the last such child within 1e-12 relative of `best`
+    u32 n_sig;       // how many of those children have round(conf*100) != 0
+};
+
+struct ShardView {
+    u32 n_strad, n_shards, rank, pad;
+    const int* strad_of_node;  // [n_nodes] straddler index or -1
+    const u32* strad_nodes;    // [n_strad]
+    const int* strad_parent;   // [n_strad] straddler index of the parent node or -1
+    ShardRec* send;            // [Q][n_strad]
+    const ShardRec* recv;      // [n_shards][Q][n_strad]
+    u8* sk;                    // [Q][n_strad] combined round(conf*100)
+    u8* sany;                  // [Q][n_strad] combined "has a significant child"
+    u32* sbest;                // [Q][n_strad] combined best child (node id)
+};
+
+__device__ __forceinline__ bool node_inside(const IndexView& ix, u32 node) {
+    return ix.node_lo[node] >= ix.shard_begin && ix.node_hi[node] <= ix.shard_begin + ix.shard_refs;
+}
+
+// one warp per (query, straddler)
+__global__ void __launch_bounds__(128) shard_records_kernel(IndexView ix, const NodeRec* __restrict__ recs, ProbScratch sc, ShardView sv, int q_count) {
+    const int lane = threadIdx.x & 31;
+    const long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (w >= (long long)q_count * sv.n_strad) return;
+    const int ql = (int)(w / sv.n_strad), j = (int)(w % sv.n_strad);
+    const double* __restrict__ preb = sc.preb + (size_t)ql * sc.preb_stride;
+    const u32 node = sv.strad_nodes[j];
+    const NodeRec nr = recs[node];
+    const u32 cf = nr.child_first, cc = nr.cc_type & 0x3FFFFFFFu;
+    double best = -CUDART_INF;
+    u32 n_sig = 0;
+    for (u32 cb = 0; cb < cc; cb += 32) {
+        const u32 ci = cb + lane;
+        if (ci < cc && sv.strad_of_node[cf + ci] < 0 && node_inside(ix, cf + ci)) {
+            const NodeRec cr = recs[cf + ci];
+            const double v = preb[cr.bhi] - preb[cr.blo];
+            best = fmax(best, v);
+            n_sig += ((u32)round(v * 100.0) != 0);
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        best = fmax(best, __shfl_xor_sync(kFullMask, best, o));
+        n_sig += __shfl_xor_sync(kFullMask, n_sig, o);
+    }
+    u32 besti = 0;
+    if (best > -CUDART_INF) {
+        const double thr = best - fabs(best) * 1e-12;
+        for (u32 cb = 0; cb < cc; cb += 32) {
+            const u32 ci = cb + lane;
+            if (ci < cc && sv.strad_of_node[cf + ci] < 0 && node_inside(ix, cf + ci)) {
+                const NodeRec cr = recs[cf + ci];
+                if (preb[cr.bhi] - preb[cr.blo] >= thr) besti = cf + ci;
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) besti = max(besti, __shfl_xor_sync(kFullMask, besti, o));
+    }
+    if (lane == 0) {
+        ShardRec r;
+        r.mass = preb[nr.bhi] - preb[nr.blo];
+        r.best = best;
+        r.best_child = besti;
+        r.n_sig = n_sig;
+        sv.send[(size_t)ql * sv.n_strad + j] = r;
+    }
+}
+
+// one thread per query: masses summed in rank order (deterministic), then any-significant-child and best child
+__global__ void shard_combine_kernel(ShardView sv, int q_count) {
+    const int ql = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ql >= q_count) return;
+    const u32 S = sv.n_strad;
+    const size_t rank_stride = (size_t)q_count * S;
+    auto mass_of = [&](u32 j) {
+        double m = 0.0;
+        for (u32 r = 0; r < sv.n_shards; ++r) m += sv.recv[r * rank_stride + (size_t)ql * S + j].mass;
+        return m;
+    };
+    for (u32 j = 0; j < S; ++j) sv.sk[(size_t)ql * S + j] = (u8)min((u32)round(mass_of(j) * 100.0), 255u);
+    for (u32 j = 0; j < S; ++j) {
+        u32 nsig = 0;
+        double gmax = -CUDART_INF;
+        for (u32 r = 0; r < sv.n_shards; ++r) {
+            const ShardRec rec = sv.recv[r * rank_stride + (size_t)ql * S + j];
+            nsig += rec.n_sig;
+            gmax = fmax(gmax, rec.best);
+        }
+        for (u32 c = 0; c < S; ++c)
+            if (sv.strad_parent[c] == (int)j) {
+                nsig += sv.sk[(size_t)ql * S + c] != 0;
+                gmax = fmax(gmax, mass_of(c));
+            }
+        const double thr = gmax - fabs(gmax) * 1e-12;
+        u32 best_child = 0;
+        for (u32 r = 0; r < sv.n_shards; ++r) {
+            const ShardRec rec = sv.recv[r * rank_stride + (size_t)ql * S + j];
+            if (rec.best > -CUDART_INF && rec.best >= thr) best_child = max(best_child, rec.best_child);
+        }
+        for (u32 c = 0; c < S; ++c)
+            if (sv.strad_parent[c] == (int)j && mass_of(c) >= thr) best_child = max(best_child, sv.strad_nodes[c]);
+        sv.sany[(size_t)ql * S + j] = nsig != 0;
+        sv.sbest[(size_t)ql * S + j] = best_child;
+    }
+}
+
+// =========================================================================================================
 // K5: tree walk, ordering, override, emission.  One warp per query (thousands of independent walkers hide the
 // latency of the dependent loads); 4 warps per CTA.
 //
@@ -754,8 +870,10 @@ struct WalkSmem {
     }
 };
 
+template <bool SH>
 __global__ void __launch_bounds__(kWalkWarps * 32)
-    lineage_walk_kernel(IndexView ix, const NodeRec* __restrict__ recs, BatchView b, ResultPool pool, ProbScratch sc, int q_base, int q_count) {
+    lineage_walk_kernel(IndexView ix, const NodeRec* __restrict__ recs, BatchView b, ResultPool pool, ProbScratch sc, ShardView sv, int q_base,
+                        int q_count) {
     extern __shared__ __align__(16) unsigned char wsm_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int ql = blockIdx.x * kWalkWarps + warp;
@@ -793,7 +911,14 @@ __global__ void __launch_bounds__(kWalkWarps * 32)
                 NodeRec cr = NodeRec{0, 0, 0, 0};
                 if (ci < cc) {
                     cr = recs[cf + ci];
-                    k = (u32)round((preb[cr.bhi] - preb[cr.blo]) * 100.0);  // f64::round, half away from zero (lineage.rs:129)
+                    if (SH) {
+                        const int sj = sv.strad_of_node[cf + ci];
+                        if (sj >= 0) k = sv.sk[(size_t)ql * sv.n_strad + sj];  // combined over the ranks
+                        else if (node_inside(ix, cf + ci)) k = (u32)round((preb[cr.bhi] - preb[cr.blo]) * 100.0);
+                        // children inside another shard are walked by their owner
+                    } else {
+                        k = (u32)round((preb[cr.bhi] - preb[cr.blo]) * 100.0);  // f64::round, half away from zero (lineage.rs:129)
+                    }
                 }
                 const u32 mask = __ballot_sync(kFullMask, k != 0);
                 if (mask) {
@@ -828,12 +953,38 @@ __global__ void __launch_bounds__(kWalkWarps * 32)
                 continue;
             }
             // children exhausted
-            if (!ws.st_any[depth] && ntype != 2 && !(ntype == 1 && depth == 0)) {
+            bool any_sig = ws.st_any[depth] != 0;
+            bool mine = true;  // does this rank emit for `node`?
+            if (SH) {
+                const int sj = sv.strad_of_node[node];
+                if (sj >= 0) {
+                    any_sig = any_sig || sv.sany[(size_t)ql * sv.n_strad + sj];
+                    mine = ix.node_lo[node] >= ix.shard_begin && ix.node_lo[node] < ix.shard_begin + ix.shard_refs;
+                }
+            }
+            if (!any_sig && ntype != 2 && !(ntype == 1 && depth == 0) && (ntype == 0 || mine)) {
                 int d = depth;
                 u32 cur = node;
                 if (ntype == 0) {  // Inner without a significant child: follow the best children (lineage.rs:151-177)
                     u32 cur_cf = cf, cur_cc = cc, cur_type = 0;
                     while (cur_type == 0 && d < RTX_MAX_LEVELS) {
+                        if (SH) {
+                            const int sj = sv.strad_of_node[cur];
+                            if (sj >= 0) {  // the best child of a straddler was decided from all ranks' records
+                                cur = sv.sbest[(size_t)ql * sv.n_strad + sj];
+                                const NodeRec br = recs[cur];
+                                if (lane == 0) {
+                                    ws.path_node[d] = cur;
+                                    ws.path_k[d] = 1;
+                                }
+                                ++d;
+                                cur_cf = br.child_first;
+                                cur_cc = br.cc_type & 0x3FFFFFFFu;
+                                cur_type = br.cc_type >> 30;
+                                continue;
+                            }
+                            if (!node_inside(ix, cur)) break;  // the chain continues in another rank's shard
+                        }
                         // max_by(partial_cmp): the LAST maximal child wins (lineage.rs:156-164).  Children tied in exact
                         // arithmetic (same hit counts) differ here only by rounding noise of the prefix sums, so values
                         // within 1e-12 relative of the maximum count as maximal.
@@ -883,11 +1034,15 @@ __global__ void __launch_bounds__(kWalkWarps * 32)
                         cur_cc = br.cc_type & 0x3FFFFFFFu;
                         cur_type = br.cc_type >> 30;
                     }
-                    if (cur_type == 0) overflow = true;
+                    if (SH) {
+                        const int sj = sv.strad_of_node[cur];
+                        mine = cur_type != 0 && (sj >= 0 ? (ix.node_lo[cur] >= ix.shard_begin && ix.node_lo[cur] < ix.shard_begin + ix.shard_refs)
+                                                         : node_inside(ix, cur));
+                    } else if (cur_type == 0) overflow = true;
                 }
                 __syncwarp();
-                if (n_res >= RTX_MAX_RESULTS_PER_QUERY) overflow = true;
-                if (!overflow) {
+                if (mine && n_res >= RTX_MAX_RESULTS_PER_QUERY) overflow = true;
+                if (mine && !overflow) {
                     // confidence / expected vectors of this line; local signal (lineage.rs:95-102, utils.rs:91-105)
                     double cv = 0.0, ev = 0.0;
                     if (lane < d) {
@@ -922,7 +1077,7 @@ __global__ void __launch_bounds__(kWalkWarps * 32)
         }
         __syncwarp();
         if (overflow) status = kQTooManyResults;
-        else if (n_res == 0) status = kQEmptyResult;  // assert!(!eval_res.is_empty()) raxtax.rs:72
+        else if (n_res == 0 && !SH) status = kQEmptyResult;  // assert!(!eval_res.is_empty()) raxtax.rs:72 (sharded: checked after the merge)
     }
     // ---- order (lineage.rs:93): stable sort, descending lexicographic on the confidence vectors.  Results were pushed
     // in depth-first order, so the tie-break is the push index.
@@ -953,8 +1108,8 @@ __global__ void __launch_bounds__(kWalkWarps * 32)
     u32 n_out = (status == kQOk) ? n_res : 0;
     bool ovr = false;
     u32 ovr_idx = 0;
-    if (status == kQOk && !(b.flags & RTX_RAW_CONFIDENCE) && !(b.flags & RTX_SKIP_EXACT_MATCHES) && b.exact_off) {
-        if (b.exact_off[q + 1] - b.exact_off[q] == 1) {
+    if (!SH && status == kQOk && !(b.flags & RTX_RAW_CONFIDENCE) && !(b.flags & RTX_SKIP_EXACT_MATCHES) && b.exact_off) {
+        if (b.exact_off[q + 1] - b.exact_off[q] == 1) {  // sharded: the caller applies the override after merging the ranks
             ovr = true;
             ovr_idx = b.exact_ids[b.exact_off[q]];
             n_out = 1;

@@ -52,6 +52,10 @@ struct rtx_ctx {
     int prob_slots = 0;
     size_t prob_smem = 0, walk_smem = 0;
     DevBuf d_cbuf, d_preb;
+    // reference-sharded mode
+    ShardView sv{};
+    int shard_phase = 0;
+    DevBuf d_strad_of_node, d_strad_nodes, d_strad_parent, d_send, d_recv, d_sk, d_sany, d_sbest;
     // host staging
     std::vector<u32> h_res_off, h_res_cnt, h_nrows, h_pool_first;
     std::vector<int> h_status;
@@ -195,7 +199,8 @@ RTX_API void rtx_ctx_destroy(rtx_ctx* c) {
                       &c->d_bnd_rank, &c->d_ref_levels, &c->d_lnfact, &c->d_seq_off, &c->d_codes, &c->d_exact_off, &c->d_exact_ids,
                       &c->d_K, &c->d_kmers, &c->d_rows, &c->d_nrows, &c->d_hist, &c->d_counts, &c->d_pool_first, &c->d_pool_nlev,
                       &c->d_pool_conf, &c->d_pool_local, &c->d_pool_used, &c->d_res_off, &c->d_res_cnt, &c->d_global, &c->d_status,
-                      &c->d_hits, &c->d_cbuf, &c->d_preb, &c->d_recs};
+                      &c->d_hits, &c->d_cbuf, &c->d_preb, &c->d_recs, &c->d_strad_of_node, &c->d_strad_nodes, &c->d_strad_parent,
+                      &c->d_send, &c->d_recv, &c->d_sk, &c->d_sany, &c->d_sbest};
     for (DevBuf* b : bufs) b->release();
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
@@ -265,7 +270,15 @@ RTX_API int rtx_index_upload(rtx_ctx* ctx, const rtx_index_desc* d) {
                 d->ref_levels,
             "rtx_index_upload: NULL array");
     const u64 N = d->n_refs;
-    const u64 s0 = d->ref_shard_begin, s1 = d->ref_shard_end ? d->ref_shard_end : N;
+    u64 s0 = d->ref_shard_begin, s1 = d->ref_shard_end ? d->ref_shard_end : N;
+    const u32 n_shards = d->n_shards > 1 ? d->n_shards : 1;
+    if (n_shards > 1) {
+        REQUIRE(d->shard_cuts != nullptr && d->shard_rank < n_shards, "shard_cuts / shard_rank invalid");
+        REQUIRE(d->shard_cuts[0] == 0 && d->shard_cuts[n_shards] == N, "shard_cuts must span [0, n_refs]");
+        for (u32 r = 0; r < n_shards; ++r) REQUIRE(d->shard_cuts[r] < d->shard_cuts[r + 1], "shard_cuts must be strictly increasing");
+        s0 = d->shard_cuts[d->shard_rank];
+        s1 = d->shard_cuts[d->shard_rank + 1];
+    }
     REQUIRE(s0 < s1 && s1 <= N, "bad reference shard range");
     const u64 nnz = d->csr_offsets[65536];
     REQUIRE(d->csr_offsets[0] == 0, "csr_offsets[0] must be 0");
@@ -417,6 +430,37 @@ RTX_API int rtx_index_upload(rtx_ctx* ctx, const rtx_index_desc* d) {
     if (!ctx->keep_csr) {
         ctx->d_csr_ids.release();
         ctx->d_csr_off.release();
+    }
+
+    // ---- straddling nodes (reference-sharded mode) -----------------------------------------------------------
+    {
+        std::vector<int> strad_of(nn, -1), strad_parent;
+        std::vector<u32> strad_nodes;
+        if (n_shards > 1) {
+            std::vector<int> parent(nn, -1);
+            for (u32 i = 0; i < nn; ++i)
+                for (u32 c = d->child_first[i]; c < d->child_first[i] + d->child_count[i]; ++c) parent[c] = (int)i;
+            for (u32 i = 0; i < nn; ++i) {  // BFS order: parents precede children
+                const u64 lo = d->node_lo[i], hi = d->node_hi[i];
+                bool crosses = false;
+                for (u32 r = 1; r < n_shards && !crosses; ++r) crosses = lo < d->shard_cuts[r] && d->shard_cuts[r] < hi;
+                if (crosses) {
+                    strad_of[i] = (int)strad_nodes.size();
+                    strad_nodes.push_back(i);
+                    strad_parent.push_back(parent[i] >= 0 ? strad_of[parent[i]] : -1);
+                }
+            }
+        }
+        CU(upload_vec(ctx->d_strad_of_node, strad_of.data(), nn, &bytes));
+        CU(upload_vec(ctx->d_strad_nodes, strad_nodes.data(), strad_nodes.size(), &bytes));
+        CU(upload_vec(ctx->d_strad_parent, strad_parent.data(), strad_parent.size(), &bytes));
+        ctx->sv = ShardView{};
+        ctx->sv.n_strad = (u32)strad_nodes.size();
+        ctx->sv.n_shards = n_shards;
+        ctx->sv.rank = n_shards > 1 ? d->shard_rank : 0;
+        ctx->sv.strad_of_node = ctx->d_strad_of_node.as<int>();
+        ctx->sv.strad_nodes = ctx->d_strad_nodes.as<u32>();
+        ctx->sv.strad_parent = ctx->d_strad_parent.as<int>();
     }
 
     ix.bitrows = ctx->d_bitrows.as<u32>();
@@ -578,7 +622,9 @@ RTX_API int rtx_batch_upload(rtx_ctx* ctx, const rtx_batch* batch) {
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, prob_prefix_kernel, kProbThreads, smem));
     if (occ < 1) return set_err(ctx, RTX_ERR_CUDA, "prob_prefix_kernel does not fit on an SM");
     ctx->walk_smem = (size_t)kWalkWarps * WalkSmem::bytes(ctx->ix.max_levels);
-    CU(cudaFuncSetAttribute(lineage_walk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->walk_smem));
+    CU(cudaFuncSetAttribute(lineage_walk_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->walk_smem));
+    CU(cudaFuncSetAttribute(lineage_walk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->walk_smem));
+    ctx->shard_phase = 0;
     const int slots = (int)std::min<u64>((u64)ctx->n_sms * occ, sb);
     ctx->prob_slots = slots;
     const u32 tstride = round_up(hstride / 2 + 1, 4);
@@ -670,6 +716,8 @@ static int run_all(rtx_ctx* ctx) {
     BatchView& bv = ctx->bv;
     const u32 nq = bv.n_queries;
     if (nq == 0) return RTX_OK;
+    if (ctx->sv.n_shards > 1)
+        return set_err(ctx, RTX_ERR_INVALID, "this context holds one shard of a reference-sharded index: use the rtx_shard_phase* calls");
     CU(cudaMemsetAsync(ctx->d_hist.p, 0, (size_t)nq * bv.hstride * 4, ctx->stream));
     CU(cudaMemsetAsync(ctx->d_pool_used.p, 0, 8, ctx->stream));
     CU(cudaMemsetAsync(ctx->d_hits.p, 0, 8, ctx->stream));
@@ -696,8 +744,8 @@ static int run_all(rtx_ctx* ctx) {
         }
         {
             LaunchTimer lt(ctx, RTX_K_WALK);
-            lineage_walk_kernel<<<(qb + kWalkWarps - 1) / kWalkWarps, kWalkWarps * 32, ctx->walk_smem, ctx->stream>>>(
-                ctx->ix, ctx->d_recs.as<NodeRec>(), bv, ctx->pool, ctx->sc, (int)q0, qb);
+            lineage_walk_kernel<false><<<(qb + kWalkWarps - 1) / kWalkWarps, kWalkWarps * 32, ctx->walk_smem, ctx->stream>>>(
+                ctx->ix, ctx->d_recs.as<NodeRec>(), bv, ctx->pool, ctx->sc, ShardView{}, (int)q0, qb);
             CU(cudaGetLastError());
         }
         if (ctx->tap_counts_host) {
@@ -780,6 +828,13 @@ RTX_API int rtx_batch_download(rtx_ctx* ctx, rtx_results* res) {
         // grow the pool and redo the whole batch once (counts of earlier sub-batches are gone)
         int rc = ensure_pool(ctx, used + used / 4 + 1024);
         if (rc) return rc;
+        if (ctx->sv.n_shards > 1) {  // counts and prefixes are still resident: only the walk has to be repeated
+            CU(cudaMemsetAsync(ctx->d_pool_used.p, 0, 8, ctx->stream));
+            ctx->shard_phase = 2;
+            rc = rtx_shard_phase3(ctx);
+            if (rc) return rc;
+            return rtx_batch_download(ctx, res);
+        }
         rc = run_all(ctx);
         if (rc) return rc;
         return rtx_batch_download(ctx, res);
@@ -852,19 +907,118 @@ RTX_API int rtx_classify_batch(rtx_ctx* ctx, const rtx_batch* batch, rtx_results
 }
 
 // ---- sharded mode ------------------------------------------------------------------------------------------
-RTX_API int rtx_shard_phase1(rtx_ctx* ctx) { return set_err(ctx, RTX_ERR_UNSUPPORTED, "reference-sharded mode is not implemented yet"); }
-RTX_API int rtx_shard_hist_buffer(rtx_ctx* ctx, void** p, uint64_t* n) {
-    (void)p;
-    (void)n;
-    return set_err(ctx, RTX_ERR_UNSUPPORTED, "reference-sharded mode is not implemented yet");
+static int shard_precheck(rtx_ctx* ctx, int want_phase, const char* who) {
+    if (!ctx) return RTX_ERR_INVALID;
+    if (!ctx->has_batch) return set_err(ctx, RTX_ERR_INVALID, std::string(who) + ": no batch uploaded");
+    if (ctx->bv.n_queries > ctx->sub_batch) return set_err(ctx, RTX_ERR_INVALID, std::string(who) + ": the batch must fit one sub-batch in sharded mode");
+    if (ctx->shard_phase != want_phase) return set_err(ctx, RTX_ERR_INVALID, std::string(who) + ": phases must run in order 1, 2, 3 after rtx_batch_upload");
+    cudaError_t e = cudaSetDevice(ctx->device);
+    if (e != cudaSuccess) return set_err(ctx, RTX_ERR_CUDA, cudaGetErrorString(e));
+    return RTX_OK;
 }
-RTX_API int rtx_shard_phase2(rtx_ctx* ctx) { return set_err(ctx, RTX_ERR_UNSUPPORTED, "reference-sharded mode is not implemented yet"); }
-RTX_API int rtx_shard_partial_buffer(rtx_ctx* ctx, void** p, uint64_t* n) {
-    (void)p;
-    (void)n;
-    return set_err(ctx, RTX_ERR_UNSUPPORTED, "reference-sharded mode is not implemented yet");
+
+RTX_API int rtx_shard_phase1(rtx_ctx* ctx) {
+    int rc = shard_precheck(ctx, 0, "rtx_shard_phase1");
+    if (rc) return rc;
+    BatchView& bv = ctx->bv;
+    const u32 nq = bv.n_queries;
+    ctx->shard_phase = 1;
+    if (nq == 0) return RTX_OK;
+    CU(cudaMemsetAsync(ctx->d_hist.p, 0, (size_t)nq * bv.hstride * 4, ctx->stream));
+    CU(cudaMemsetAsync(ctx->d_pool_used.p, 0, 8, ctx->stream));
+    CU(cudaMemsetAsync(ctx->d_hits.p, 0, 8, ctx->stream));
+    {
+        LaunchTimer lt(ctx, RTX_K_KMERS);
+        kmers_kernel<<<nq, kKmerThreads, 0, ctx->stream>>>(ctx->ix, bv);
+        CU(cudaGetLastError());
+    }
+    rc = run_phase1(ctx, 0, (int)nq);
+    if (rc) return rc;
+    if ((bv.flags & RTX_SKIP_EXACT_MATCHES) && bv.exact_off) {
+        LaunchTimer lt(ctx, RTX_K_FIXUP);
+        fixup_exact_kernel<<<(nq + 127) / 128, 128, 0, ctx->stream>>>(ctx->ix, bv, ctx->d_counts.as<u16>(), 0, (int)nq);
+        CU(cudaGetLastError());
+    }
+    // exchange buffers
+    const size_t S = ctx->sv.n_strad;
+    CU(ctx->d_send.ensure(std::max<size_t>(1, (size_t)nq * S) * sizeof(ShardRec)));
+    CU(ctx->d_recv.ensure(std::max<size_t>(1, (size_t)nq * S) * sizeof(ShardRec) * ctx->sv.n_shards));
+    CU(ctx->d_sk.ensure(std::max<size_t>(1, (size_t)nq * S)));
+    CU(ctx->d_sany.ensure(std::max<size_t>(1, (size_t)nq * S)));
+    CU(ctx->d_sbest.ensure(std::max<size_t>(1, (size_t)nq * S) * 4));
+    ctx->sv.send = ctx->d_send.as<ShardRec>();
+    ctx->sv.recv = ctx->d_recv.as<ShardRec>();
+    ctx->sv.sk = ctx->d_sk.as<u8>();
+    ctx->sv.sany = ctx->d_sany.as<u8>();
+    ctx->sv.sbest = ctx->d_sbest.as<u32>();
+    CU(cudaStreamSynchronize(ctx->stream));
+    return RTX_OK;
 }
-RTX_API int rtx_shard_phase3(rtx_ctx* ctx) { return set_err(ctx, RTX_ERR_UNSUPPORTED, "reference-sharded mode is not implemented yet"); }
+
+RTX_API int rtx_shard_hist_buffer(rtx_ctx* ctx, void** dev_ptr, uint64_t* n_elems) {
+    if (!ctx || !dev_ptr || !n_elems) return RTX_ERR_INVALID;
+    if (!ctx->has_batch) return set_err(ctx, RTX_ERR_INVALID, "rtx_shard_hist_buffer: no batch uploaded");
+    *dev_ptr = ctx->d_hist.p;
+    *n_elems = (uint64_t)ctx->bv.n_queries * ctx->bv.hstride;
+    return RTX_OK;
+}
+
+RTX_API int rtx_shard_phase2(rtx_ctx* ctx) {
+    int rc = shard_precheck(ctx, 1, "rtx_shard_phase2");
+    if (rc) return rc;
+    BatchView& bv = ctx->bv;
+    const u32 nq = bv.n_queries;
+    ctx->shard_phase = 2;
+    if (nq == 0) return RTX_OK;
+    {
+        LaunchTimer lt(ctx, RTX_K_PROB);
+        const int grid = std::min<int>(ctx->prob_slots, (int)nq);
+        prob_prefix_kernel<<<grid, kProbThreads, ctx->prob_smem, ctx->stream>>>(ctx->ix, bv, ctx->pool, ctx->sc, ctx->d_counts.as<u16>(), 0, (int)nq,
+                                                                              ctx->d_hits.as<unsigned long long>());
+        CU(cudaGetLastError());
+    }
+    if (ctx->sv.n_strad) {
+        const long long warps = (long long)nq * ctx->sv.n_strad;
+        shard_records_kernel<<<(unsigned)((warps * 32 + 127) / 128), 128, 0, ctx->stream>>>(ctx->ix, ctx->d_recs.as<NodeRec>(), ctx->sc, ctx->sv, (int)nq);
+        CU(cudaGetLastError());
+    }
+    CU(cudaStreamSynchronize(ctx->stream));
+    return RTX_OK;
+}
+
+RTX_API int rtx_shard_records_buffers(rtx_ctx* ctx, void** send_ptr, uint64_t* send_bytes, void** recv_ptr, uint64_t* recv_bytes) {
+    if (!ctx || !send_ptr || !send_bytes || !recv_ptr || !recv_bytes) return RTX_ERR_INVALID;
+    if (!ctx->has_batch || ctx->shard_phase < 1) return set_err(ctx, RTX_ERR_INVALID, "rtx_shard_records_buffers: run rtx_shard_phase1 first");
+    const uint64_t b = (uint64_t)ctx->bv.n_queries * ctx->sv.n_strad * sizeof(ShardRec);
+    *send_ptr = ctx->d_send.p;
+    *send_bytes = b;
+    *recv_ptr = ctx->d_recv.p;
+    *recv_bytes = b * ctx->sv.n_shards;
+    return RTX_OK;
+}
+
+RTX_API int rtx_shard_phase3(rtx_ctx* ctx) {
+    int rc = shard_precheck(ctx, 2, "rtx_shard_phase3");
+    if (rc) return rc;
+    BatchView& bv = ctx->bv;
+    const u32 nq = bv.n_queries;
+    ctx->shard_phase = 3;
+    if (nq == 0) return RTX_OK;
+    if (ctx->sv.n_strad) {
+        shard_combine_kernel<<<(nq + 127) / 128, 128, 0, ctx->stream>>>(ctx->sv, (int)nq);
+        CU(cudaGetLastError());
+    }
+    {
+        LaunchTimer lt(ctx, RTX_K_WALK);
+        lineage_walk_kernel<true><<<(nq + kWalkWarps - 1) / kWalkWarps, kWalkWarps * 32, ctx->walk_smem, ctx->stream>>>(
+            ctx->ix, ctx->d_recs.as<NodeRec>(), bv, ctx->pool, ctx->sc, ctx->sv, 0, (int)nq);
+        CU(cudaGetLastError());
+    }
+    ctx->prof.queries += nq;
+    ctx->runs_since_download += 1;
+    ctx->ran = true;
+    return RTX_OK;
+}
 
 // ---- measurement -------------------------------------------------------------------------------------------
 RTX_API int rtx_profile_reset(rtx_ctx* ctx) {

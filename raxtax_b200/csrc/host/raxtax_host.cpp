@@ -553,6 +553,17 @@ RXH_API int rxh_tree_upload(const rxh_tree* t, rtx_ctx* ctx, uint64_t shard_begi
     return rc;
 }
 
+RXH_API int rxh_tree_upload_sharded(const rxh_tree* t, rtx_ctx* ctx, uint32_t n_shards, uint32_t shard_rank, const uint64_t* shard_cuts) {
+    rtx_index_desc d;
+    rxh_tree_index_desc(t, &d);
+    d.n_shards = n_shards;
+    d.shard_rank = shard_rank;
+    d.shard_cuts = shard_cuts;
+    int rc = rtx_index_upload(ctx, &d);
+    if (rc) g_err = rtx_last_error(ctx);
+    return rc;
+}
+
 RXH_API rxh_queries* rxh_queries_from_fasta(const char* text, size_t len) {
     try {
         auto h = new rxh_queries();

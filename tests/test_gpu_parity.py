@@ -235,3 +235,41 @@ def test_c2_scale_properties(ctx):
             assert len(res) == 1 and res[0][0] == int(eids[eo[q]]) and np.all(res[0][1] == 1.0)
         if ne >= 1:
             assert dev.counts[q, eids[eo[q]]] == K  # an exact copy shares every k-mer
+
+
+# ---- reference-sharded mode: several shards on ONE GPU (one context per shard), exchanges by device copies -----------------
+@pytest.mark.parametrize("n_shards,skip,raw", [(2, False, False), (3, True, False), (5, False, True)])
+def test_reference_sharded_matches_oracle(oracle, n_shards, skip, raw):
+    from raxtax_b200 import dist as rdist
+
+    ds = synth.generate("small", n_queries=96, measure=False)
+    seqs = [ds.ref_seq(i) for i in range(ds.n_refs)]
+    ot = oracle.Tree.new(ds.ref_lineages, seqs)
+    ht = capi.Tree.new(ds.ref_lineages, ds.ref_off, ds.ref_codes)
+    cuts = rdist.shard_cuts(ht.num_tips, n_shards)
+    ctxs = [capi.Context(0) for _ in range(n_shards)]
+    try:
+        for r, c in enumerate(ctxs):
+            c.upload_tree_sharded(ht, n_shards, r, cuts)
+        eo, eids = ht.exact_batch(ds.query_off, ds.query_codes)
+        ref_levels = ht.index_arrays()["ref_levels"]
+        merged, outs = rdist.classify_sharded_local(ctxs, ds.query_off, ds.query_codes, eo, eids, ref_levels, skip_exact=skip, raw_conf=raw,
+                                                    taps=("counts", "hist", "kmers"))
+        o = ot.classify(ds.query_off, ds.query_codes, skip_exact=skip, raw_conf=raw, threads=4, chunk_size=16, want_counts=True, want_probs=True,
+                        want_kmers=True)
+        # integer parity: the shards' count vectors concatenate to the oracle's, the all-reduced histograms are the global ones
+        assert np.array_equal(np.concatenate([x.counts for x in outs], axis=1), o["counts"])
+        for q in range(ds.n_queries):
+            K = int(o["K"][q])
+            for x in outs:
+                assert np.array_equal(parity.hist_from_counts(o["counts"][q], K), x.hist[q, : K + 1])
+        assert np.array_equal(o["K"], merged.n_kmers)
+        _assert_result_parity(o, merged, ot, ds.n_queries)
+        # phases out of order are refused
+        with pytest.raises(capi.RtxError):
+            ctxs[0].shard_phase(3)
+        with pytest.raises(capi.RtxError):
+            ctxs[0].batch_run()
+    finally:
+        for c in ctxs:
+            c.close()
