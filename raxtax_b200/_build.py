@@ -53,9 +53,20 @@ def build_host(force=False):
     return HOST_LIB
 
 
+def build_cli(force=False):
+    src = [os.path.join(PKG, "csrc", "host", "main.cpp")]
+    if force or _stale(CLI_BIN, src + [HOST_LIB, os.path.join(INC, "raxtax_host.h")]):
+        cxx = os.environ.get("CXX", "g++")
+        cmd = [cxx, "-O2", "-std=c++17", "-Wall", "-Wextra", "-I", INC, "-o", CLI_BIN] + src + [
+            "-L", PKG, "-lraxtax_host", "-lraxtax_b200", "-lz", "-Wl,-rpath,$ORIGIN"]
+        subprocess.check_call(cmd)
+    return CLI_BIN
+
+
 def build_all(force=False, verbose=False):
     build_device(force, verbose)
     build_host(force)
+    build_cli(force)
     return DEVICE_LIB, HOST_LIB
 
 

@@ -273,3 +273,29 @@ def test_reference_sharded_matches_oracle(oracle, n_shards, skip, raw):
     finally:
         for c in ctxs:
             c.close()
+
+
+# ---- the raxtax command-line binary: unchanged CLI flags and output files ---------------------------------
+def test_cli_binary_writes_reference_format_files(tmp_path):
+    import subprocess
+
+    from raxtax_b200 import _build
+
+    fasta = os.path.join(GOLDEN, "diptera_sample.fasta")
+    for skip, golden in ((False, "diptera_sample.default.out"), (True, "diptera_sample.skip.out")):
+        prefix = tmp_path / ("skip" if skip else "default")
+        cmd = [_build.CLI_BIN, "-d", fasta, "-i", fasta, "-o", str(prefix), "--tsv", "--batch", "150"] + (["--skip-exact-matches"] if skip else [])
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+        out = (prefix / "raxtax.out").read_text().split("\n")
+        exp = open(os.path.join(GOLDEN, golden)).read().split("\n")
+        assert len(out) == len(exp)
+        assert sum(a == b for a, b in zip(out, exp)) >= 0.98 * len(exp)
+        tsv = (prefix / "raxtax.tsv").read_text().split("\n")
+        assert len(tsv) == len(exp) and tsv[0].count("\t") == 15  # label + 6 x (rank, conf) + 2 signals + sequence
+        assert len((prefix / "raxtax.ckp").read_text().splitlines()) == 400
+        log = (prefix / "raxtax.log").read_text()
+        assert log.startswith("raxtax-b200") and ("Exact sequence match for query" in log) == (not skip)
+        # a second run into the same folder is refused without --redo (io.rs:231-233)
+        r2 = subprocess.run(cmd, capture_output=True, text=True)
+        assert r2.returncode == 73 and "already exists" in r2.stderr

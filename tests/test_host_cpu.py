@@ -179,3 +179,19 @@ def test_synth_kmers_match_oracle(oracle):
     for q in list(range(10)) + [ds.n_queries - 1]:
         assert np.array_equal(synth.kmers_of(ds.query_seq(q)), oracle.sequence_to_kmers(ds.query_seq(q)))
     assert list(synth.kmers_of(np.array(KMER_KAT_CODES, np.uint8))) == list(oracle.sequence_to_kmers(KMER_KAT_CODES))
+
+
+def test_cli_exit_codes_without_gpu(tmp_path):
+    """main.rs exit codes: NOINPUT for unreadable input; without a GPU the binary stops with TEMPFAIL instead of computing on the CPU."""
+    import subprocess
+
+    import torch
+
+    r = subprocess.run([_build.CLI_BIN, "-d", "/nonexistent.fasta", "-i", "/nonexistent.fasta", "-o", str(tmp_path / "o1")], capture_output=True, text=True)
+    assert r.returncode == 66 and "Failed to parse" in r.stderr
+    r = subprocess.run([_build.CLI_BIN, "--only-db", "-d", "x"], capture_output=True, text=True)
+    assert r.returncode == 73
+    if not torch.cuda.is_available():
+        fasta = os.path.join(ROOT, "tests", "golden", "diptera_sample.fasta")
+        r = subprocess.run([_build.CLI_BIN, "-d", fasta, "-i", fasta, "-o", str(tmp_path / "o2")], capture_output=True, text=True)
+        assert r.returncode == 75 and "no CPU fallback" in r.stderr
