@@ -259,7 +259,7 @@ def main():
             traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
         except Exception:
             traffic = None
-    kernel_ms = {k: prof[k]["total_ms"] / args.steps for k in ("kmers", "hitcount", "fixup", "prob", "walk")}
+    kernel_ms = {k: prof[k]["total_ms"] / args.steps for k in ("kmers", "hitcount", "fixup", "prob", "prefix", "walk")}
     roofline = {"bound": "hbm", "kernel": "hitcount_bitrows_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": bytes_per_launch,
                 "launch_ms": hc_ms, "csr_equivalent": {"bytes_per_launch": csr_bytes_per_launch,

@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define RTX_ABI_VERSION 1
+#define RTX_ABI_VERSION 2
 #define RTX_MAX_LEVELS 32 /* deepest lineage (comma-separated ranks) the device tree walk supports */
 #define RTX_MAX_RESULTS_PER_QUERY 256 /* >= the 200 lines a query can produce with the 0.01 cutoff */
 
@@ -126,6 +126,8 @@ typedef struct {
  *   tap_counts[q * shard_refs + r]  = intersect_buffer after the skip-zeroing (raxtax.rs:58-68), u16
  *   tap_hist[q * tap_hist_stride + m] = number of references with count m (prob.rs:13-19), this shard only
  *   tap_kmers[q * tap_kmer_stride + i] = sorted unique 8-mers (utils.rs:27-40)
+ *   tap_probs[q * tap_prob_stride + m] = normalised probability of a reference with count m (prob.rs:92-102),
+ *                                        valid where tap_hist (the global histogram) is non-zero
  */
 typedef struct {
     uint16_t* n_kmers;       /* [n_queries] */
@@ -143,6 +145,8 @@ typedef struct {
     uint64_t tap_hist_stride;
     uint16_t* tap_kmers;
     uint64_t tap_kmer_stride;
+    double* tap_probs;
+    uint64_t tap_prob_stride;
 } rtx_results;
 
 /* One call = H2D of the batch, all kernels, D2H of the results (the end-to-end path). */
@@ -179,7 +183,7 @@ typedef struct {
     double total_ms;     /* sum of CUDA-event durations (only with RTX_OPT_PROFILE) */
 } rtx_kernel_stat;
 
-enum { RTX_K_KMERS = 0, RTX_K_HITCOUNT = 1, RTX_K_FIXUP = 2, RTX_K_PROB = 3, RTX_K_INDEX = 4, RTX_K_WALK = 5, RTX_K_COUNT = 6 };
+enum { RTX_K_KMERS = 0, RTX_K_HITCOUNT = 1, RTX_K_FIXUP = 2, RTX_K_PROB = 3, RTX_K_INDEX = 4, RTX_K_WALK = 5, RTX_K_PREFIX = 6, RTX_K_COUNT = 7 };
 
 typedef struct {
     rtx_kernel_stat kernel[RTX_K_COUNT];

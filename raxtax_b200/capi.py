@@ -22,7 +22,7 @@ RTX_OK, RTX_ERR_INVALID, RTX_ERR_CUDA, RTX_ERR_NO_DEVICE, RTX_ERR_NO_INDEX, RTX_
 RTX_SKIP_EXACT_MATCHES, RTX_RAW_CONFIDENCE = 1, 2
 RTX_HITCOUNT_BITROWS, RTX_HITCOUNT_CSR = 0, 1
 RTX_OPT_HITCOUNT_VARIANT, RTX_OPT_SUB_BATCH, RTX_OPT_KEEP_CSR, RTX_OPT_PROFILE, RTX_OPT_HITCOUNT_TUNE, RTX_OPT_HITCOUNT_MAX_TILES = 1, 2, 3, 4, 5, 6
-KERNEL_NAMES = ["kmers", "hitcount", "fixup", "prob", "index", "walk"]
+KERNEL_NAMES = ["kmers", "hitcount", "fixup", "prob", "index", "walk", "prefix"]
 
 # every symbol include/raxtax_b200.h declares
 DEVICE_SYMBOLS = [
@@ -56,7 +56,7 @@ class ResultsStruct(C.Structure):
     _fields_ = [("n_kmers", u16p), ("result_begin", u32p), ("global_signal", f64p), ("result_capacity", C.c_uint64),
                 ("first_ref", u32p), ("n_levels", u8p), ("confidence", f64p), ("local_signal", f64p), ("n_results", C.c_uint64),
                 ("tap_counts", u16p), ("tap_hist", u32p), ("tap_hist_stride", C.c_uint64), ("tap_kmers", u16p),
-                ("tap_kmer_stride", C.c_uint64)]
+                ("tap_kmer_stride", C.c_uint64), ("tap_probs", f64p), ("tap_prob_stride", C.c_uint64)]
 
 
 class KernelStat(C.Structure):
@@ -64,7 +64,7 @@ class KernelStat(C.Structure):
 
 
 class Profile(C.Structure):
-    _fields_ = [("kernel", KernelStat * 6), ("queries", C.c_uint64), ("hits", C.c_uint64), ("bitrow_bytes", C.c_uint64),
+    _fields_ = [("kernel", KernelStat * 7), ("queries", C.c_uint64), ("hits", C.c_uint64), ("bitrow_bytes", C.c_uint64),
                 ("csr_equiv_bytes", C.c_uint64), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64)]
 
 
@@ -192,6 +192,7 @@ class ClassifyOutput:
     counts: np.ndarray | None = None
     hist: np.ndarray | None = None
     kmers: np.ndarray | None = None
+    probs: np.ndarray | None = None  # [nq, kmax + 1] normalised P(m) by count (valid where the histogram is non-zero)
 
     def for_query(self, q):
         a, b = int(self.result_begin[q]), int(self.result_begin[q + 1])
@@ -339,6 +340,10 @@ class Context:
             out.kmers = np.zeros((nq, max(kmax, 1)), np.uint16)
             r.tap_kmers = _ptr(out.kmers, C.c_uint16)
             r.tap_kmer_stride = max(kmax, 1)
+        if "probs" in taps:
+            out.probs = np.zeros((nq, kmax + 1), np.float64)
+            r.tap_probs = _ptr(out.probs, C.c_double)
+            r.tap_prob_stride = kmax + 1
         return out, r
 
     @staticmethod

@@ -5,10 +5,10 @@
 //   K2 hitcount_bitrows_kernel per-query hit counts (raxtax.rs:58-64) by positional popcount over bit rows,
 //                              fused count histogram (prob.rs:13-19)
 //   K2' fixup_exact_kernel     --skip-exact-matches zeroing (raxtax.rs:65-68) applied to counts + histogram
-//   K3-5 prob_lineage_kernel   highest-hit probabilities (prob.rs:20-102), prefix sums at node boundaries
-//                              (lineage.rs:61-77,114-117), tree walk with the 0.01 cutoff / fallback
-//                              (lineage.rs:119-179), signals and ordering (lineage.rs:86-111), override
-//                              (raxtax.rs:73-84)
+//   K3 prob_table_kernel       highest-hit probabilities (prob.rs:20-102) on the windows that can matter
+//   K4 prefix_kernel           prefix sums of the probabilities at node boundaries (lineage.rs:61-77,114-117)
+//   K5 lineage_walk_kernel     tree walk with the 0.01 cutoff / fallback (lineage.rs:119-179), signals and ordering
+//                              (lineage.rs:86-111), override (raxtax.rs:73-84)
 #pragma once
 
 #include <math_constants.h>
@@ -457,39 +457,64 @@ __global__ void fixup_exact_kernel(IndexView ix, BatchView b, u16* __restrict__ 
 }
 
 // =========================================================================================================
-// K3-K5: probabilities, lineage aggregation, selection.  Persistent CTAs (256 threads), one query at a time.
+// K3: highest-hit probabilities (prob.rs:8-103).  Persistent CTAs (256 threads), one query at a time.
+//
+// The reference evaluates, for every distinct count m, the log-pmf p_m(i), its log-cmf c_m(i) and
+//   P(m) = sum_i exp(p_m(i) + prod(i) - c_m(i)),   prod(i) = sum_m' h[m'] c_m'(i)            (prob.rs:43-91)
+// over the full D x (t+1) grid.  Almost all of that grid cannot influence a result digit:
+//   * E(i) = exp(prod(i)) is a product of cmfs, non-decreasing in i, and sum_r P_r >= 1 (some reference always attains
+//     the maximum), so every term with E(i) < e^-70 changes a normalised probability by < 1e-30.  An upper bound
+//     B(i) >= prod(i) with a closed form per row (geometric bound of the cmf below the mode, -pmf(i+1) above it) is
+//     searched for the largest i with B(i) <= -70; everything below i0 = i + 1 is skipped (E := 0).
+//   * above its mode the pmf is log-concave and decays geometrically; once p_m(i) < -(40 + ln h[m]) the remaining tail
+//     changes neither c_m (h[m]*tail < 1e-17) nor P(m) (tail < 1e-17/h[m]).  That index hi_m is found by a warp-wide
+//     search on the closed form.
+// What is left per row is the window [i0, hi_m): empty for the bulk of the references (their tail is gone long
+// before E wakes up), a few dozen entries for the rows in between (evaluated from the top: cmf = 1 - sf, c = log1p(-sf)),
+// and a forward cmf from the first representable pmf for the few rows whose mode lies above i0.
+// Result: the same normalised probabilities to ~1e-13 absolute (tests pin 1e-6) at a fraction of the ln/exp count.
 // =========================================================================================================
 constexpr int kProbThreads = 256;
 constexpr int kProbWarps = kProbThreads / 32;
+constexpr double kEcut = 70.0;       // E(i) < e^-70 is dropped
+constexpr float kTailNats = 40.0f;   // pmf tail cut-off: p < -(kTailNats + ln h)
+
 struct ProbScratch {
     double* cbuf;        // [slots][cbuf_stride] r_m[i] = pmf_m(i) / cmf_m(i) of the slow branch, row d = distinct count d
     size_t cbuf_stride;  // = hstride * tstride doubles
     u32 tstride;         // doubles per cbuf row ( >= max t + 1 )
     double* preb;        // [sub-batch queries][preb_stride] prefix sums of normalised probabilities at node boundaries
     size_t preb_stride;
+    double* ptab;        // [sub-batch queries][hstride] normalised P(m), direct-indexed by count (K3 -> K4)
+    int nprod;           // kProbWarps: one partial prod array per warp; 1: a single array updated with shared-memory atomics
+    int lf_smem;         // 1: ln n! staged in shared memory, 0: read from HBM/L2 (very long queries)
 };
 
 // dynamic smem carve-up (sizes depend on H = hstride, T1 = H/2 + 1)
 struct ProbSmem {
-    double* Ptab;   // [H]   P(m)/S, direct-indexed by count
-    double* dval;   // [H]   per distinct count: running cmf (pass 1) / P (pass 2)
-    double* dcar;   // [H]   per distinct count: ln of the running cmf
-    double* g;      // [T1]  ln i! + ln (t-i)!
-    double* prod;   // [T1]  sum_m h[m] * ln cmf_m(i), then E[i] = exp(prod[i])
+    double* lf;     // [H + T1]  ln n! for n < K + t (query independent, loaded once per CTA)
+    double* Pd;     // [H]       P(m) per distinct count
+    double* prodw;  // [kProbWarps][T1]  per-warp partial sums of h[m] * ln cmf_m(i)
+    double* E;      // [T1]      exp(prod(i))
     u32* hist;      // [H]
     u32* dh;        // [H]   multiplicity of distinct count d
     u16* dm;        // [H]   distinct counts ascending
-    __host__ __device__ ProbSmem(unsigned char* base, u32 H, u32 T1) {
-        Ptab = reinterpret_cast<double*>(base);
-        dval = Ptab + H;
-        dcar = dval + H;
-        g = dcar + H;
-        prod = g + T1;
-        hist = reinterpret_cast<u32*>(prod + T1);
+    u16* wlo;       // [H]   per distinct count: window [wlo, whi) of entries stored in cbuf
+    u16* whi;       // [H]
+    __host__ __device__ ProbSmem(unsigned char* base, u32 H, u32 T1, int nprod, int lf_smem) {
+        lf = reinterpret_cast<double*>(base);
+        Pd = lf + (lf_smem ? H + T1 : 0);
+        prodw = Pd + H;
+        E = prodw + (size_t)nprod * T1;
+        hist = reinterpret_cast<u32*>(E + T1);
         dh = hist + H;
         dm = reinterpret_cast<u16*>(dh + H);
+        wlo = dm + H;
+        whi = wlo + H;
     }
-    static size_t bytes(u32 H, u32 T1) { return (size_t)H * (8 * 3 + 4 * 2 + 2) + (size_t)T1 * 16 + 64; }
+    static size_t bytes(u32 H, u32 T1, int nprod, int lf_smem) {
+        return (size_t)H * (8 + 4 * 2 + 2 * 3) + (size_t)T1 * 8 * (1 + nprod) + (lf_smem ? (size_t)(H + T1) * 8 : 0) + 64;
+    }
 };
 
 // node record: one 16-byte load gives everything the walk needs about a child
@@ -499,34 +524,75 @@ struct __align__(16) NodeRec {
     u32 cc_type;       // child_count | node_type << 30
 };
 
-// K3 + K4: per query, P(count) table -> normalise -> global signal -> prefix sums at the node boundaries.
-// Outputs: preb[ql][*] (HBM), pool.global_sig[q], pool.status[q] (kQOk / kQProbSumZero).
+// ln pmf_m(i) = ln C(m+i-1,i) + ln C(K-m+t-i-1,t-i) - ln C(K+t-1,t): closed form of the iterative sums of prob.rs:136-166.
+// cm = ln (m-1)! + ln (K-m-1)! + T collects the terms that do not depend on i.   Requires 1 <= m <= K-1, i <= t.
+__device__ __forceinline__ double ln_pmf(const double* __restrict__ lf, u32 K, u32 t, u32 m, u32 i, double cm) {
+    return (lf[m + i - 1] - lf[i]) + (lf[K - m + t - i - 1] - lf[t - i]) - cm;
+}
+
+// mode of pmf_m: the first i with pmf(i+1)/pmf(i) = (m+i)(t-i) / ((i+1)(K-m+t-i-1)) < 1, i.e. i > (m t - K + m - t + 1)/(K - 2)
+__device__ __forceinline__ u32 pmf_mode(u32 K, u32 t, u32 m) {
+    if (K <= 2) return t;
+    const long long num = (long long)m * t - (long long)K + m - (long long)t + 1;
+    if (num < 0) return 0;
+    const long long q = num / (long long)(K - 2) + 1;
+    return (u32)min((long long)t, q);
+}
+
+// smallest i in [a, bnd) with pred(i), else bnd; pred is monotone (false.. true..).  Warp-wide 32-ary search.
+template <typename Pred>
+__device__ __forceinline__ u32 warp_first_true(u32 a, u32 bnd, int lane, Pred pred) {
+    while (a < bnd) {
+        const u32 s = (bnd - a + 31u) / 32u;
+        const u32 x = a + (u32)lane * s;
+        const bool tested = x < bnd;
+        const bool pr = tested && pred(x);
+        const u32 hit = __ballot_sync(kFullMask, pr);
+        if (!hit) {
+            const u32 tmask = __ballot_sync(kFullMask, tested);
+            a = a + (u32)(31 - __clz(tmask)) * s + 1u;  // everything up to the last tested point is false
+            continue;
+        }
+        const u32 j = (u32)__ffs(hit) - 1u;
+        if (j == 0) return a;
+        bnd = a + j * s;          // pred(bnd) holds
+        a = bnd - s + 1u;         // pred(a - 1) does not
+    }
+    return bnd;
+}
+
 __global__ void __launch_bounds__(kProbThreads)
-    prob_prefix_kernel(IndexView ix, BatchView b, ResultPool pool, ProbScratch sc, const u16* __restrict__ counts, int q_base, int q_count,
-                       unsigned long long* __restrict__ hits_total) {
+    prob_table_kernel(IndexView ix, BatchView b, ResultPool pool, ProbScratch sc, int q_base, int q_count,
+                      unsigned long long* __restrict__ hits_total) {
     extern __shared__ __align__(16) unsigned char psm_raw[];
     __shared__ double red[40];
-    __shared__ double part[kProbWarps][32];
     __shared__ u32 wsum[kProbWarps];
-    __shared__ double wtot[kProbWarps];
+    __shared__ int sflag[kProbWarps];
 
     const u32 H = b.hstride;
     const u32 T1 = H / 2 + 1;
-    ProbSmem sm(psm_raw, H, T1);
+    ProbSmem sm(psm_raw, H, T1, sc.nprod, sc.lf_smem);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const double* __restrict__ lf = ix.lnfact;
     const double NEG_INF = -CUDART_INF;
     const double Nd = (double)ix.n_refs;
+    const double* __restrict__ lf = sc.lf_smem ? sm.lf : ix.lnfact;
 
     double* cbuf = sc.cbuf + (size_t)blockIdx.x * sc.cbuf_stride;
+    if (sc.lf_smem)
+        for (u32 i = tid; i < H + T1; i += kProbThreads) sm.lf[i] = ix.lnfact[i];
+    const bool own_prod = sc.nprod == kProbWarps;
+    double* __restrict__ myprod = sm.prodw + (own_prod ? (size_t)warp * T1 : 0);
+    auto prod_add = [&](u32 i, double v) {
+        if (own_prod) myprod[i] += v;
+        else atomicAdd(&myprod[i], v);
+    };
 
     for (int ql = blockIdx.x; ql < q_count; ql += gridDim.x) {
         const int q = q_base + ql;
         const u32 K = b.K[q];
         const u32 t = K / 2;  // raxtax.rs:57
         const u32* __restrict__ ghist = b.hist + (size_t)q * H;
-        const u16* __restrict__ qcounts = counts + (size_t)ql * ix.n_pad;
-        double* __restrict__ preb = sc.preb + (size_t)ql * sc.preb_stride;
+        double* __restrict__ ptab = sc.ptab + (size_t)ql * H;
         __syncthreads();  // smem reuse across queries
 
         // ---- histogram -> distinct counts (ascending), prob.rs:13-19 ------------------------------------
@@ -537,6 +603,7 @@ __global__ void __launch_bounds__(kProbThreads)
             u32 h = ghist[m];
             sm.hist[m] = h;
             nz += (h != 0);
+            ptab[m] = 0.0;
         }
         u32 D;
         u32 dpos = block_scan_excl(nz, wsum, tid, kProbWarps, &D);
@@ -545,11 +612,11 @@ __global__ void __launch_bounds__(kProbThreads)
             if (h) {
                 sm.dm[dpos] = (u16)m;
                 sm.dh[dpos] = h;
-                sm.dval[dpos] = 0.0;
-                sm.dcar[dpos] = NEG_INF;
+                sm.Pd[dpos] = 0.0;
+                sm.wlo[dpos] = 0;
+                sm.whi[dpos] = 0;
                 ++dpos;
             }
-            sm.Ptab[m] = 0.0;
         }
         __syncthreads();
         // postings a CSR walk would have touched for this query = sum_r count[r]
@@ -571,141 +638,249 @@ __global__ void __launch_bounds__(kProbThreads)
                 if (m == K) P = 1.0;
                 else if (m == 0) P = 0.0;
                 else P = exp(lf[m + t - 1] - lf[t] - lf[m - 1] - T);
-                sm.dval[d] = P;
+                sm.Pd[d] = P;
             }
         } else {  // slow branch (prob.rs:43-91); here 0 <= m < K for every distinct count
-            for (u32 i = tid; i <= t; i += kProbThreads) sm.g[i] = lf[i] + lf[t - i];
-            __syncthreads();
-            const u32 nchunks = (t + 1 + 31) / 32;
-            // pass 1: e = pmf_m(i), running cmf S, c = ln S, prod[i] = sum_m h[m] c_m[i]; r = e / S is kept for pass 2
-            for (u32 ch = 0; ch < nchunks; ++ch) {
-                const u32 i = ch * 32 + lane;
-                const bool valid = i <= t;
-                double acc = 0.0;
-                for (u32 d = warp; d < D; d += kProbWarps) {
-                    const u32 m = sm.dm[d];
-                    if (m == 0) continue;  // pmf = [1,0,0,..] => cmf == 1 => ln cmf == 0 for every i
-                    const double cm = lf[m - 1] + lf[K - m - 1] + T;
-                    // ln pmf_m(i) = ln C(m+i-1,i) + ln C(K-m+t-i-1,t-i) - T   (closed form of prob.rs:136-166)
-                    const double p = valid ? lf[m + i - 1] + lf[K - m + t - i - 1] - sm.g[i] - cm : NEG_INF;
-                    const double e = valid ? exp(p) : 0.0;
-                    const double S0 = sm.dval[d], c0 = sm.dcar[d];
-                    __syncwarp();
-                    double S, c;
-                    // upper tail: every term of this chunk is below half an ulp of the running sum, so the reference's
-                    // sequential `sum += pmf.exp()` leaves the sum (and its ln) bit-for-bit unchanged
-                    if (__all_sync(kFullMask, p < c0 - 38.0)) {
-                        S = S0;
-                        c = c0;
-                    } else {
-                        S = warp_scan_incl(e, lane) + S0;
-                        c = log(S);  // S == 0 -> -inf, as the reference's sum.ln()
-                        if (lane == 31) {
-                            sm.dval[d] = S;
-                            sm.dcar[d] = c;
+            // ---- i0: everything below has E(i) < e^-kEcut -------------------------------------------------
+            int slo = -1, shi = (int)t + 1;  // B(slo) <= -kEcut (or slo == -1); nothing known at or above shi
+            while (shi - slo > 1) {
+                const int s = max(1, (shi - slo - 1 + kProbWarps - 1) / kProbWarps);
+                const int cand = slo + (warp + 1) * s;
+                bool ok = false;
+                if (cand < shi) {
+                    const u32 i = (u32)cand;
+                    double bsum = 0.0;
+                    for (u32 d = lane; d < D; d += 32) {
+                        const u32 m = sm.dm[d];
+                        if (m == 0) continue;  // cmf == 1
+                        const double cm = lf[m - 1] + lf[K - m - 1] + T;
+                        double u;
+                        if (i < pmf_mode(K, t, m)) {  // cmf(i) <= pmf(i) / (1 - pmf(i-1)/pmf(i)): ratios shrink downwards
+                            u = ln_pmf(lf, K, t, m, i, cm);
+                            if (i > 0) {
+                                const double rd = ((double)i * (double)(K - m + t - i)) / ((double)(m + i - 1) * (double)(t - i + 1));
+                                u = (rd < 1.0) ? u - log1p(-rd) : 0.0;
+                            }
+                            u = fmin(u, 0.0);
+                        } else {  // ln cmf = ln(1 - sf) <= -sf <= -pmf(i+1)
+                            u = (i + 1 <= t) ? -exp(ln_pmf(lf, K, t, m, i + 1, cm)) : 0.0;
                         }
+                        bsum = fma((double)sm.dh[d], u, bsum);
                     }
-                    if (valid) {
-                        cbuf[(size_t)d * sc.tstride + i] = (S > 0.0) ? e / S : 0.0;
-                        acc += (double)sm.dh[d] * c;
-                    }
+                    bsum = warp_sum(bsum);
+                    ok = bsum <= -kEcut;
                 }
-                part[warp][lane] = acc;
+                if (lane == 0) sflag[warp] = ok;
                 __syncthreads();
-                if (warp == 0) {
-                    double s = 0.0;
+                int best = -1;
 #pragma unroll
-                    for (int w = 0; w < kProbWarps; ++w) s += part[w][lane];
-                    // E[i] = exp(prod[i]); exp(-inf) = 0 reproduces the reference's `prod == -inf => 0` branch
-                    if (valid) sm.prod[i] = exp(s);
+                for (int k = 0; k < kProbWarps; ++k)
+                    if (sflag[k]) best = k;
+                if (best < 0) shi = min(shi, slo + s);
+                else {
+                    if (best + 1 < kProbWarps) shi = min(shi, slo + (best + 2) * s);
+                    slo = slo + (best + 1) * s;
                 }
                 __syncthreads();
             }
-            // pass 2: P(m) = sum_i exp(p_m[i] + prod[i] - c_m[i]) = sum_i (pmf_m(i)/cmf_m(i)) * E[i]   (prob.rs:74-90)
-            for (u32 d = warp; d < D; d += kProbWarps) {
+            const u32 i0 = (u32)(slo + 1);
+            for (u32 i = tid; i < (u32)sc.nprod * T1; i += kProbThreads) sm.prodw[i] = 0.0;
+            __syncthreads();
+
+            // ---- pass 1: one warp per row, rows dealt in descending m ---------------------------------------
+            for (int d = (int)D - 1 - warp; d >= 0; d -= kProbWarps) {
+                const u32 m = sm.dm[d];
+                if (m == 0) continue;  // pmf = [1,0,..]: cmf == 1, ln cmf == 0, P(0) = E(0)
+                const double hd = (double)sm.dh[d];
+                const double cm = lf[m - 1] + lf[K - m - 1] + T;
+                const u32 mode = pmf_mode(K, t, m);
+                const double thr = -(double)(kTailNats + __logf((float)sm.dh[d]));
+                // hi: first i above the mode whose pmf (and, by log-concavity, whole remaining tail) is negligible
+                const u32 hi = warp_first_true(mode + 1, t + 1, lane, [&](u32 i) { return ln_pmf(lf, K, t, m, i, cm) < thr; });
+                double* __restrict__ row = cbuf + (size_t)d * sc.tstride;
+                if (i0 > mode) {  // cmf(i0) >~ 1/2: evaluate from the top, cmf = 1 - sf
+                    if (hi <= i0) continue;  // the row is finished before E wakes up: c == 0, P == 0
+                    double carry = 0.0;
+                    for (int c = (int)((hi - 1) >> 5); c >= (int)(i0 >> 5); --c) {
+                        const u32 i = (u32)c * 32 + lane;
+                        const bool valid = i >= i0 && i < hi;
+                        const double e = valid ? exp(ln_pmf(lf, K, t, m, i, cm)) : 0.0;
+                        double sfx = e;  // inclusive suffix sum over the lanes
+#pragma unroll
+                        for (int o = 1; o < 32; o <<= 1) {
+                            const double y = __shfl_down_sync(kFullMask, sfx, o);
+                            if (lane + o < 32) sfx += y;
+                        }
+                        const double sf = (sfx - e) + carry;  // sum_{j > i} pmf(j)
+                        carry += __shfl_sync(kFullMask, sfx, 0);
+                        if (valid) {
+                            prod_add(i, hd * log1p(-sf));
+                            row[i] = e / (1.0 - sf);
+                        }
+                    }
+                    if (lane == 0) {
+                        sm.wlo[d] = (u16)i0;
+                        sm.whi[d] = (u16)hi;
+                    }
+                } else {  // forward from the first representable pmf, as the reference's running sum
+                    const u32 lo = warp_first_true(0u, mode + 1, lane, [&](u32 i) { return ln_pmf(lf, K, t, m, i, cm) > -745.0; });
+                    double S = 0.0;
+                    for (u32 c = lo >> 5; c <= ((hi - 1) >> 5); ++c) {
+                        const u32 i = c * 32 + lane;
+                        const bool valid = i >= lo && i < hi;
+                        const double e = valid ? exp(ln_pmf(lf, K, t, m, i, cm)) : 0.0;
+                        const double inc = warp_scan_incl(e, lane);
+                        const double Sv = inc + S;
+                        S += __shfl_sync(kFullMask, inc, 31);
+                        if (valid && i >= i0) {
+                            if (Sv > 0.0) {
+                                prod_add(i, hd * log(Sv));
+                                row[i] = e / Sv;
+                            } else {  // cmf == 0: prod = -inf, E = 0 (prob.rs:81-85)
+                                prod_add(i, NEG_INF);
+                                row[i] = 0.0;
+                            }
+                        }
+                    }
+                    for (u32 i = i0 + lane; i < lo; i += 32) prod_add(i, NEG_INF);  // pmf underflows: cmf == 0 there
+                    const double cf = hd * log(S);  // beyond hi the running sum no longer moves
+                    for (u32 i = max(hi, i0) + lane; i <= t; i += 32) prod_add(i, cf);
+                    if (lane == 0) {
+                        sm.wlo[d] = (u16)max(lo, i0);
+                        sm.whi[d] = (u16)hi;
+                    }
+                }
+                __syncwarp();
+            }
+            __syncthreads();
+            // E(i) = exp(prod(i)); exp(-inf) = 0 reproduces the reference's `prod == -inf => 0` branch
+            for (u32 i = tid; i <= t; i += kProbThreads) {
+                double s = NEG_INF;
+                if (i >= i0) {
+                    s = 0.0;
+#pragma unroll
+                    for (int w = 0; w < kProbWarps; ++w)
+                        if (w < sc.nprod) s += sm.prodw[(size_t)w * T1 + i];
+                }
+                sm.E[i] = exp(s);
+            }
+            __syncthreads();
+            // ---- pass 2: P(m) = sum_i (pmf_m(i)/cmf_m(i)) * E(i)   (prob.rs:74-90), same warp as pass 1 ----------
+            for (int d = (int)D - 1 - warp; d >= 0; d -= kProbWarps) {
                 const u32 m = sm.dm[d];
                 double val;
                 if (m == 0) {
-                    val = sm.prod[0];  // p = [0,-inf,..], c = 0
+                    val = sm.E[0];  // p = [0,-inf,..], c = 0
                 } else {
                     double s = 0.0;
                     const double* __restrict__ row = cbuf + (size_t)d * sc.tstride;
-                    for (u32 i = lane; i <= t; i += 32) s = fma(row[i], sm.prod[i], s);
+                    const u32 a = sm.wlo[d], e = sm.whi[d];
+                    for (u32 i = a + lane; i < e; i += 32) s = fma(row[i], sm.E[i], s);
                     val = warp_sum(s);
                 }
-                if (lane == 0) sm.dval[d] = val;
+                if (lane == 0) sm.Pd[d] = val;
             }
         }
         __syncthreads();
         // ---- normalise (prob.rs:97-102) and global signal (lineage.rs:86-90) ---------------------------
         double sl = 0.0;
-        for (u32 d = tid; d < D; d += kProbThreads) sl += (double)sm.dh[d] * sm.dval[d];
+        for (u32 d = tid; d < D; d += kProbThreads) sl += (double)sm.dh[d] * sm.Pd[d];
         const double S = block_sum(sl, red, tid, kProbWarps);
         const bool bad_sum = !(S > 0.0);  // assert!(probs_sum > 0.0)
         double gl = 0.0;
         for (u32 d = tid; d < D; d += kProbThreads) {
-            double pn = sm.dval[d] / S;
-            sm.Ptab[sm.dm[d]] = pn;
+            double pn = sm.Pd[d] / S;
+            ptab[sm.dm[d]] = pn;
             double df = pn - 1.0 / Nd;
             gl += (double)sm.dh[d] * (df * df);
         }
         const double gsum = block_sum(gl, red, tid, kProbWarps);
-        const double global_signal = sqrt(gsum);
-
-        // ---- prefix sums of the normalised probabilities at node boundaries (lineage.rs:61-77) ---------
-        {
-            double carry = 0.0;
-            const u64 Ns = ix.shard_refs;
-            for (u64 base = 0; base < Ns; base += (u64)kProbThreads * 8) {
-                const u64 r0 = base + (u64)tid * 8;
-                double v[8];
-                if (r0 < Ns) {
-                    uint4 cw = *reinterpret_cast<const uint4*>(qcounts + r0);
-                    u32 w[4] = {cw.x, cw.y, cw.z, cw.w};
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        v[2 * k] = (r0 + 2 * k < Ns) ? sm.Ptab[w[k] & 0xFFFFu] : 0.0;
-                        v[2 * k + 1] = (r0 + 2 * k + 1 < Ns) ? sm.Ptab[w[k] >> 16] : 0.0;
-                    }
-                } else {
-#pragma unroll
-                    for (int k = 0; k < 8; ++k) v[k] = 0.0;
-                }
-#pragma unroll
-                for (int k = 1; k < 8; ++k) v[k] += v[k - 1];
-                double inc = warp_scan_incl(v[7], lane);
-                if (lane == 31) wtot[warp] = inc;
-                __syncthreads();
-                double offs = carry + inc - v[7];
-                double tot = 0.0;
-#pragma unroll
-                for (int w = 0; w < kProbWarps; ++w) {
-                    double x = wtot[w];
-                    if (w < warp) offs += x;
-                    tot += x;
-                }
-                if (r0 < Ns) {
-                    const u32 word = ix.bnd_after[r0 >> 5];
-                    const u32 sh = (u32)(r0 & 31);
-                    u32 byte = (word >> sh) & 0xFFu;
-                    if (byte) {
-                        u32 idx = 1u + ix.bnd_rank[r0 >> 5] + __popc(word & ((1u << sh) - 1u));
-#pragma unroll
-                        for (int k = 0; k < 8; ++k) {
-                            if (byte & (1u << k)) preb[idx++] = offs + v[k];
-                        }
-                    }
-                }
-                carry += tot;
-                __syncthreads();
-            }
-            if (tid == 0) preb[0] = 0.0;
-        }
         if (tid == 0) {
-            pool.global_sig[q] = global_signal;
+            pool.global_sig[q] = sqrt(gsum);
             pool.status[q] = bad_sum ? kQProbSumZero : kQOk;
         }
     }
+}
+
+// =========================================================================================================
+// K4: prefix sums of the normalised probabilities at node boundaries (lineage.rs:61-77,114-117).
+// One CTA per query; the P(m) table sits in shared memory, every thread owns 16 consecutive references per
+// step (two 16-byte loads of counts), one barrier per 4096 references.
+// =========================================================================================================
+constexpr int kPrefixThreads = 256;
+constexpr int kPrefixWarps = kPrefixThreads / 32;
+constexpr int kPrefixPer = 16;
+
+__global__ void __launch_bounds__(kPrefixThreads)
+    prefix_kernel(IndexView ix, BatchView b, ProbScratch sc, const u16* __restrict__ counts, int q_base, int q_count) {
+    extern __shared__ __align__(16) unsigned char xsm_raw[];
+    __shared__ double wtot[2][kPrefixWarps];
+    double* Ptab = reinterpret_cast<double*>(xsm_raw);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int ql = blockIdx.x;
+    if (ql >= q_count) return;
+    const int q = q_base + ql;
+    const u32 K = b.K[q];
+    const double* __restrict__ gp = sc.ptab + (size_t)ql * b.hstride;
+    for (u32 m = tid; m <= K; m += kPrefixThreads) Ptab[m] = gp[m];
+    __syncthreads();
+    const u16* __restrict__ qcounts = counts + (size_t)ql * ix.n_pad;
+    double* __restrict__ preb = sc.preb + (size_t)ql * sc.preb_stride;
+    const u64 Ns = ix.shard_refs;
+    double carry = 0.0;
+    int buf = 0;
+    for (u64 base = 0; base < Ns; base += (u64)kPrefixThreads * kPrefixPer, buf ^= 1) {
+        const u64 r0 = base + (u64)tid * kPrefixPer;
+        double v[kPrefixPer];
+        if (r0 < Ns) {
+            const uint4 c0 = *reinterpret_cast<const uint4*>(qcounts + r0);
+            const uint4 c1 = *reinterpret_cast<const uint4*>(qcounts + r0 + 8);
+            const u32 w[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+            if (r0 + kPrefixPer <= Ns) {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    v[2 * k] = Ptab[w[k] & 0xFFFFu];
+                    v[2 * k + 1] = Ptab[w[k] >> 16];
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    v[2 * k] = (r0 + 2 * k < Ns) ? Ptab[w[k] & 0xFFFFu] : 0.0;
+                    v[2 * k + 1] = (r0 + 2 * k + 1 < Ns) ? Ptab[w[k] >> 16] : 0.0;
+                }
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < kPrefixPer; ++k) v[k] = 0.0;
+        }
+#pragma unroll
+        for (int k = 1; k < kPrefixPer; ++k) v[k] += v[k - 1];
+        const double inc = warp_scan_incl(v[kPrefixPer - 1], lane);
+        if (lane == 31) wtot[buf][warp] = inc;
+        __syncthreads();
+        double offs = carry + (inc - v[kPrefixPer - 1]);
+        double tot = 0.0;
+#pragma unroll
+        for (int w2 = 0; w2 < kPrefixWarps; ++w2) {
+            const double x = wtot[buf][w2];
+            if (w2 < warp) offs += x;
+            tot += x;
+        }
+        if (r0 < Ns) {
+            const u32 word = ix.bnd_after[r0 >> 5];
+            const u32 sh = (u32)(r0 & 31);
+            const u32 bits = (word >> sh) & 0xFFFFu;
+            if (bits) {
+                u32 idx = 1u + ix.bnd_rank[r0 >> 5] + __popc(word & ((1u << sh) - 1u));
+#pragma unroll
+                for (int k = 0; k < kPrefixPer; ++k) {
+                    if (bits & (1u << k)) preb[idx++] = offs + v[k];
+                }
+            }
+        }
+        carry += tot;
+    }
+    if (tid == 0) preb[0] = 0.0;
 }
 
 // =========================================================================================================

@@ -50,8 +50,8 @@ struct rtx_ctx {
     // prob scratch
     ProbScratch sc{};
     int prob_slots = 0;
-    size_t prob_smem = 0, walk_smem = 0;
-    DevBuf d_cbuf, d_preb;
+    size_t prob_smem = 0, walk_smem = 0, prefix_smem = 0;
+    DevBuf d_cbuf, d_preb, d_ptab;
     // reference-sharded mode
     ShardView sv{};
     int shard_phase = 0;
@@ -63,6 +63,8 @@ struct rtx_ctx {
     std::vector<double> h_pool_conf, h_pool_local;
     // taps wired by rtx_classify_batch for sub-batched runs
     u16* tap_counts_host = nullptr;
+    double* tap_probs_host = nullptr;
+    u64 tap_prob_stride = 0;
     u64 runs_since_download = 0;
     // profile
     rtx_profile prof{};
@@ -199,7 +201,7 @@ RTX_API void rtx_ctx_destroy(rtx_ctx* c) {
                       &c->d_bnd_rank, &c->d_ref_levels, &c->d_lnfact, &c->d_seq_off, &c->d_codes, &c->d_exact_off, &c->d_exact_ids,
                       &c->d_K, &c->d_kmers, &c->d_rows, &c->d_nrows, &c->d_hist, &c->d_counts, &c->d_pool_first, &c->d_pool_nlev,
                       &c->d_pool_conf, &c->d_pool_local, &c->d_pool_used, &c->d_res_off, &c->d_res_cnt, &c->d_global, &c->d_status,
-                      &c->d_hits, &c->d_cbuf, &c->d_preb, &c->d_recs, &c->d_strad_of_node, &c->d_strad_nodes, &c->d_strad_parent,
+                      &c->d_hits, &c->d_cbuf, &c->d_preb, &c->d_ptab, &c->d_recs, &c->d_strad_of_node, &c->d_strad_nodes, &c->d_strad_parent,
                       &c->d_send, &c->d_recv, &c->d_sk, &c->d_sany, &c->d_sbest};
     for (DevBuf* b : bufs) b->release();
     if (c->stream) cudaStreamDestroy(c->stream);
@@ -541,9 +543,18 @@ RTX_API int rtx_batch_upload(rtx_ctx* ctx, const rtx_batch* batch) {
     if (kmax > 65535) return set_err(ctx, RTX_ERR_UNSUPPORTED, "query with more than 65535 8-mer windows (raxtax.rs:56 asserts the same)");
     const u32 kstride = round_up(std::max(kmax, 1u), 16);
     const u32 hstride = round_up(kmax + 1, 4);
-    const size_t smem = ProbSmem::bytes(hstride, hstride / 2 + 1);
+    // probability tables in shared memory: per-warp partial sums and the ln n! table while they fit, else the compact layout
+    int nprod = kProbWarps, lf_smem = 1;
+    size_t smem = ProbSmem::bytes(hstride, hstride / 2 + 1, nprod, lf_smem);
+    if (smem > 100 * 1024) {
+        nprod = 1;
+        lf_smem = 0;
+        smem = ProbSmem::bytes(hstride, hstride / 2 + 1, nprod, lf_smem);
+    }
     if (smem > 200 * 1024)
-        return set_err(ctx, RTX_ERR_UNSUPPORTED, "query too long for the shared-memory probability tables (more than ~5800 unique 8-mers)");
+        return set_err(ctx, RTX_ERR_UNSUPPORTED, "query too long for the shared-memory probability tables (more than ~6800 unique 8-mers)");
+    ctx->sc.nprod = nprod;
+    ctx->sc.lf_smem = lf_smem;
     ctx->max_len = max_len;
     ctx->total_codes = total;
     u64 total_exact = 0;
@@ -617,10 +628,12 @@ RTX_API int rtx_batch_upload(rtx_ctx* ctx, const rtx_batch* batch) {
 
     // probability kernel scratch
     ctx->prob_smem = smem;
-    CU(cudaFuncSetAttribute(prob_prefix_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CU(cudaFuncSetAttribute(prob_table_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 0;
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, prob_prefix_kernel, kProbThreads, smem));
-    if (occ < 1) return set_err(ctx, RTX_ERR_CUDA, "prob_prefix_kernel does not fit on an SM");
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, prob_table_kernel, kProbThreads, smem));
+    if (occ < 1) return set_err(ctx, RTX_ERR_CUDA, "prob_table_kernel does not fit on an SM");
+    ctx->prefix_smem = (size_t)hstride * 8;
+    CU(cudaFuncSetAttribute(prefix_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->prefix_smem));
     ctx->walk_smem = (size_t)kWalkWarps * WalkSmem::bytes(ctx->ix.max_levels);
     CU(cudaFuncSetAttribute(lineage_walk_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->walk_smem));
     CU(cudaFuncSetAttribute(lineage_walk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->walk_smem));
@@ -633,6 +646,8 @@ RTX_API int rtx_batch_upload(rtx_ctx* ctx, const rtx_batch* batch) {
     ctx->sc.preb_stride = round_up(ctx->ix.n_bnd, 4);
     CU(ctx->d_cbuf.ensure((size_t)slots * ctx->sc.cbuf_stride * 8));
     CU(ctx->d_preb.ensure((size_t)sb * ctx->sc.preb_stride * 8));
+    CU(ctx->d_ptab.ensure((size_t)sb * hstride * 8));
+    ctx->sc.ptab = ctx->d_ptab.as<double>();
     ctx->sc.cbuf = ctx->d_cbuf.as<double>();
     ctx->sc.preb = ctx->d_preb.as<double>();
     ctx->has_batch = true;
@@ -712,6 +727,23 @@ static int run_phase1(rtx_ctx* ctx, int q_base, int qb) {
     return RTX_OK;
 }
 
+// K3 (P(m) tables) + K4 (prefix sums at node boundaries) of one sub-batch
+static int launch_prob(rtx_ctx* ctx, int q0, int qb) {
+    {
+        LaunchTimer lt(ctx, RTX_K_PROB);
+        const int grid = std::min(ctx->prob_slots, qb);
+        prob_table_kernel<<<grid, kProbThreads, ctx->prob_smem, ctx->stream>>>(ctx->ix, ctx->bv, ctx->pool, ctx->sc, q0, qb,
+                                                                             ctx->d_hits.as<unsigned long long>());
+        CU(cudaGetLastError());
+    }
+    {
+        LaunchTimer lt(ctx, RTX_K_PREFIX);
+        prefix_kernel<<<qb, kPrefixThreads, ctx->prefix_smem, ctx->stream>>>(ctx->ix, ctx->bv, ctx->sc, ctx->d_counts.as<u16>(), q0, qb);
+        CU(cudaGetLastError());
+    }
+    return RTX_OK;
+}
+
 static int run_all(rtx_ctx* ctx) {
     BatchView& bv = ctx->bv;
     const u32 nq = bv.n_queries;
@@ -736,11 +768,8 @@ static int run_all(rtx_ctx* ctx) {
             CU(cudaGetLastError());
         }
         {
-            LaunchTimer lt(ctx, RTX_K_PROB);
-            const int grid = std::min(ctx->prob_slots, qb);
-            prob_prefix_kernel<<<grid, kProbThreads, ctx->prob_smem, ctx->stream>>>(ctx->ix, bv, ctx->pool, ctx->sc, ctx->d_counts.as<u16>(), (int)q0, qb,
-                                                                                  ctx->d_hits.as<unsigned long long>());
-            CU(cudaGetLastError());
+            int rc2 = launch_prob(ctx, (int)q0, qb);
+            if (rc2) return rc2;
         }
         {
             LaunchTimer lt(ctx, RTX_K_WALK);
@@ -753,6 +782,12 @@ static int run_all(rtx_ctx* ctx) {
             CU(cudaMemcpy2DAsync(ctx->tap_counts_host + (size_t)q0 * Ns, Ns * 2, ctx->d_counts.p, ctx->ix.n_pad * 2, Ns * 2, qb,
                                  cudaMemcpyDeviceToHost, ctx->stream));
             ctx->prof.d2h_bytes += (u64)qb * Ns * 2;
+        }
+        if (ctx->tap_probs_host) {
+            const u64 w = std::min<u64>(ctx->tap_prob_stride, bv.hstride);
+            CU(cudaMemcpy2DAsync(ctx->tap_probs_host + (size_t)q0 * ctx->tap_prob_stride, ctx->tap_prob_stride * 8, ctx->d_ptab.p,
+                                 (size_t)bv.hstride * 8, w * 8, qb, cudaMemcpyDeviceToHost, ctx->stream));
+            ctx->prof.d2h_bytes += (u64)qb * w * 8;
         }
     }
     ctx->prof.queries += nq;
@@ -884,6 +919,13 @@ RTX_API int rtx_batch_download(rtx_ctx* ctx, rtx_results* res) {
                              cudaMemcpyDeviceToHost, ctx->stream));
         ctx->prof.d2h_bytes += (u64)nq * w * 2;
     }
+    if (res->tap_probs && !ctx->tap_probs_host) {
+        REQUIRE(ctx->sub_batch >= nq, "tap_probs through rtx_batch_download needs the whole batch in one sub-batch; use rtx_classify_batch");
+        const u64 w = std::min<u64>(res->tap_prob_stride, bv.hstride);
+        CU(cudaMemcpy2DAsync(res->tap_probs, res->tap_prob_stride * 8, ctx->d_ptab.p, (size_t)bv.hstride * 8, w * 8, nq, cudaMemcpyDeviceToHost,
+                             ctx->stream));
+        ctx->prof.d2h_bytes += (u64)nq * w * 8;
+    }
     if (res->tap_counts && !ctx->tap_counts_host) {
         REQUIRE(ctx->sub_batch >= nq, "tap_counts through rtx_batch_download needs the whole batch in one sub-batch; use rtx_classify_batch");
         const u64 Ns = ctx->ix.shard_refs;
@@ -900,9 +942,12 @@ RTX_API int rtx_classify_batch(rtx_ctx* ctx, const rtx_batch* batch, rtx_results
     int rc = rtx_batch_upload(ctx, batch);
     if (rc) return rc;
     ctx->tap_counts_host = results->tap_counts;
+    ctx->tap_probs_host = results->tap_probs;
+    ctx->tap_prob_stride = results->tap_prob_stride;
     rc = rtx_batch_run(ctx);
     if (rc == RTX_OK) rc = rtx_batch_download(ctx, results);
     ctx->tap_counts_host = nullptr;
+    ctx->tap_probs_host = nullptr;
     return rc;
 }
 
@@ -970,13 +1015,8 @@ RTX_API int rtx_shard_phase2(rtx_ctx* ctx) {
     const u32 nq = bv.n_queries;
     ctx->shard_phase = 2;
     if (nq == 0) return RTX_OK;
-    {
-        LaunchTimer lt(ctx, RTX_K_PROB);
-        const int grid = std::min<int>(ctx->prob_slots, (int)nq);
-        prob_prefix_kernel<<<grid, kProbThreads, ctx->prob_smem, ctx->stream>>>(ctx->ix, bv, ctx->pool, ctx->sc, ctx->d_counts.as<u16>(), 0, (int)nq,
-                                                                              ctx->d_hits.as<unsigned long long>());
-        CU(cudaGetLastError());
-    }
+    rc = launch_prob(ctx, 0, (int)nq);
+    if (rc) return rc;
     if (ctx->sv.n_strad) {
         const long long warps = (long long)nq * ctx->sv.n_strad;
         shard_records_kernel<<<(unsigned)((warps * 32 + 127) / 128), 128, 0, ctx->stream>>>(ctx->ix, ctx->d_recs.as<NodeRec>(), ctx->sc, ctx->sv, (int)nq);

@@ -39,7 +39,7 @@ def _run_both(orc, ctx, ds_or_tuple, skip=False, raw=False, sub_batch=0, variant
     ctx.set_option(capi.RTX_OPT_SUB_BATCH, sub_batch)
     ctx.upload_tree(ht)
     eo, eids = ht.exact_batch(q_off, q_codes)
-    dev = ctx.classify(q_off, q_codes, eo, eids, skip_exact=skip, raw_conf=raw, taps=("counts", "hist", "kmers"))
+    dev = ctx.classify(q_off, q_codes, eo, eids, skip_exact=skip, raw_conf=raw, taps=("counts", "hist", "kmers", "probs"))
     o = ot.classify(q_off, q_codes, skip_exact=skip, raw_conf=raw, threads=threads, chunk_size=16, want_counts=True, want_probs=True,
                     want_kmers=True)
     ctx.set_option(capi.RTX_OPT_HITCOUNT_VARIANT, capi.RTX_HITCOUNT_BITROWS)
@@ -58,7 +58,21 @@ def _assert_integer_parity(o, dev, nq):
         assert np.array_equal(parity.hist_from_counts(o["counts"][q], K), dev.hist[q, : K + 1]), f"histogram of query {q}"
 
 
+PROB_ATOL = 1e-9  # normalised highest-hit probabilities (prob.rs:8-103); north_star tolerance is 1e-6, observed ~1e-13
+
+
+def _assert_prob_parity(o, dev, nq):
+    worst = 0.0
+    for q in range(nq):
+        dp = dev.probs[q][dev.counts[q].astype(np.int64)]  # gather per reference, as prob.rs:92-95
+        worst = max(worst, float(np.max(np.abs(dp - o["probs"][q]))))
+    assert worst <= PROB_ATOL, f"probabilities differ from the oracle by {worst:.3e}"
+    return worst
+
+
 def _assert_result_parity(o, dev, ot, nq, max_tolerated_frac=0.05):
+    if dev.probs is not None and dev.counts is not None and "probs" in o:
+        _assert_prob_parity(o, dev, nq)
     checker = parity.TolerantChecker(ot.flatten(), ot.num_tips)
     ok, tol, bad = parity.compare_batch(o, dev, nq, checker, o["probs"])
     assert not bad, f"{len(bad)} queries differ beyond tie/boundary tolerance, first: {bad[:5]}: oracle={o['results'].for_query(bad[0])} device={dev.for_query(bad[0])}"
