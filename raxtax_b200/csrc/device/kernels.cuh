@@ -804,22 +804,51 @@ __global__ void __launch_bounds__(kProbThreads)
 
 // =========================================================================================================
 // K4: prefix sums of the normalised probabilities at node boundaries (lineage.rs:61-77,114-117).
-// One CTA per query; the P(m) table sits in shared memory, every thread owns 16 consecutive references per
-// step (two 16-byte loads of counts), one barrier per 4096 references.
+//
+// One CTA per query, two barrier-free passes over the count vector in 512-reference segments (one segment = one warp
+// iteration, 16 references per lane):
+//   pass 1  segment totals  sum_r P(count[r])  -> shared memory, then one block-wide exclusive scan of the totals;
+//   pass 2  per segment: thread-serial + warp scan on top of the segment offset, the values at the node boundaries of
+//           the segment are compacted in a per-warp staging buffer and stored with coalesced 8-byte lanes.
+// No warp ever waits for another one inside a pass (the old kernel took a block barrier every 4096 references; a
+// chained-scan variant with one CTA per chunk spent 40 % of its time waiting for the preceding chunks' totals).
+// dynamic smem: double Ptab[hstride] | double segoff[n_seg] | double stage[kPrefixWarps][kPrefixSeg]
 // =========================================================================================================
 constexpr int kPrefixThreads = 256;
 constexpr int kPrefixWarps = kPrefixThreads / 32;
 constexpr int kPrefixPer = 16;
+constexpr u32 kPrefixSeg = 32 * kPrefixPer;  // 512 references; n_pad (a multiple of 4096) is a whole number of segments
+
+__device__ __forceinline__ void prefix_gather(double (&v)[kPrefixPer], const double* __restrict__ Ptab, const uint4& c0, const uint4& c1,
+                                              u64 r0, u64 Ns) {
+    const u32 w[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+    if (r0 + kPrefixPer <= Ns) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            v[2 * k] = Ptab[w[k] & 0xFFFFu];
+            v[2 * k + 1] = Ptab[w[k] >> 16];
+        }
+    } else {  // padding references beyond the shard carry no probability
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            v[2 * k] = (r0 + 2 * k < Ns) ? Ptab[w[k] & 0xFFFFu] : 0.0;
+            v[2 * k + 1] = (r0 + 2 * k + 1 < Ns) ? Ptab[w[k] >> 16] : 0.0;
+        }
+    }
+}
 
 __global__ void __launch_bounds__(kPrefixThreads)
     prefix_kernel(IndexView ix, BatchView b, ProbScratch sc, const u16* __restrict__ counts, int q_base, int q_count) {
     extern __shared__ __align__(16) unsigned char xsm_raw[];
-    __shared__ double wtot[2][kPrefixWarps];
-    double* Ptab = reinterpret_cast<double*>(xsm_raw);
+    __shared__ double wtot[kPrefixWarps];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int ql = blockIdx.x;
     if (ql >= q_count) return;
     const int q = q_base + ql;
+    const u32 n_seg = (u32)(ix.n_pad / kPrefixSeg);
+    double* Ptab = reinterpret_cast<double*>(xsm_raw);
+    double* segoff = Ptab + b.hstride;
+    double* stage = segoff + ((n_seg + 1u) & ~1u) + (size_t)warp * kPrefixSeg;
     const u32 K = b.K[q];
     const double* __restrict__ gp = sc.ptab + (size_t)ql * b.hstride;
     for (u32 m = tid; m <= K; m += kPrefixThreads) Ptab[m] = gp[m];
@@ -827,58 +856,84 @@ __global__ void __launch_bounds__(kPrefixThreads)
     const u16* __restrict__ qcounts = counts + (size_t)ql * ix.n_pad;
     double* __restrict__ preb = sc.preb + (size_t)ql * sc.preb_stride;
     const u64 Ns = ix.shard_refs;
-    double carry = 0.0;
-    int buf = 0;
-    for (u64 base = 0; base < Ns; base += (u64)kPrefixThreads * kPrefixPer, buf ^= 1) {
-        const u64 r0 = base + (u64)tid * kPrefixPer;
-        double v[kPrefixPer];
-        if (r0 < Ns) {
-            const uint4 c0 = *reinterpret_cast<const uint4*>(qcounts + r0);
-            const uint4 c1 = *reinterpret_cast<const uint4*>(qcounts + r0 + 8);
-            const u32 w[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
-            if (r0 + kPrefixPer <= Ns) {
-#pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                    v[2 * k] = Ptab[w[k] & 0xFFFFu];
-                    v[2 * k + 1] = Ptab[w[k] >> 16];
-                }
-            } else {
-#pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                    v[2 * k] = (r0 + 2 * k < Ns) ? Ptab[w[k] & 0xFFFFu] : 0.0;
-                    v[2 * k + 1] = (r0 + 2 * k + 1 < Ns) ? Ptab[w[k] >> 16] : 0.0;
-                }
-            }
-        } else {
-#pragma unroll
-            for (int k = 0; k < kPrefixPer; ++k) v[k] = 0.0;
+
+    // ---- pass 1: segment totals (two segments in flight per warp) ---------------------------------------------
+    for (u32 s = warp; s < n_seg; s += 2 * kPrefixWarps) {
+        const u32 s2 = s + kPrefixWarps;
+        const u64 ra = (u64)s * kPrefixSeg + (u64)lane * kPrefixPer;
+        const u64 rb = (u64)s2 * kPrefixSeg + (u64)lane * kPrefixPer;
+        const bool has_b = s2 < n_seg;
+        const uint4 a0 = *reinterpret_cast<const uint4*>(qcounts + ra);
+        const uint4 a1 = *reinterpret_cast<const uint4*>(qcounts + ra + 8);
+        uint4 b0 = make_uint4(0, 0, 0, 0), b1 = b0;
+        if (has_b) {
+            b0 = *reinterpret_cast<const uint4*>(qcounts + rb);
+            b1 = *reinterpret_cast<const uint4*>(qcounts + rb + 8);
         }
+        double v[kPrefixPer];
+        prefix_gather(v, Ptab, a0, a1, ra, Ns);
+        double sa = 0.0;
+#pragma unroll
+        for (int k = 0; k < kPrefixPer; ++k) sa += v[k];
+        sa = warp_sum(sa);
+        if (lane == 0) segoff[s] = sa;
+        if (has_b) {
+            prefix_gather(v, Ptab, b0, b1, rb, Ns);
+            double sb = 0.0;
+#pragma unroll
+            for (int k = 0; k < kPrefixPer; ++k) sb += v[k];
+            sb = warp_sum(sb);
+            if (lane == 0) segoff[s2] = sb;
+        }
+    }
+    __syncthreads();
+    // ---- exclusive scan of the segment totals, in place --------------------------------------------------------
+    {
+        const u32 per = (n_seg + kPrefixThreads - 1) / kPrefixThreads;
+        const u32 lo = min(n_seg, (u32)tid * per), hi = min(n_seg, lo + per);
+        double loc = 0.0;
+        for (u32 i = lo; i < hi; ++i) loc += segoff[i];
+        const double inc = warp_scan_incl(loc, lane);
+        if (lane == 31) wtot[warp] = inc;
+        __syncthreads();
+        double run = inc - loc;
+#pragma unroll
+        for (int w2 = 0; w2 < kPrefixWarps; ++w2)
+            if (w2 < warp) run += wtot[w2];
+        for (u32 i = lo; i < hi; ++i) {
+            const double x = segoff[i];
+            segoff[i] = run;
+            run += x;
+        }
+    }
+    __syncthreads();
+    // ---- pass 2: prefix sums at the node boundaries ---------------------------------------------------------------
+    for (u32 s = warp; s < n_seg; s += kPrefixWarps) {
+        const u64 r0 = (u64)s * kPrefixSeg + (u64)lane * kPrefixPer;
+        if ((u64)s * kPrefixSeg >= Ns) break;
+        const uint4 c0 = *reinterpret_cast<const uint4*>(qcounts + r0);
+        const uint4 c1 = *reinterpret_cast<const uint4*>(qcounts + r0 + 8);
+        const u32 word = ix.bnd_after[r0 >> 5];
+        const u32 rank0 = ix.bnd_rank[s * (kPrefixSeg / 32)];  // boundaries before this segment
+        double v[kPrefixPer];
+        prefix_gather(v, Ptab, c0, c1, r0, Ns);
 #pragma unroll
         for (int k = 1; k < kPrefixPer; ++k) v[k] += v[k - 1];
         const double inc = warp_scan_incl(v[kPrefixPer - 1], lane);
-        if (lane == 31) wtot[buf][warp] = inc;
-        __syncthreads();
-        double offs = carry + (inc - v[kPrefixPer - 1]);
-        double tot = 0.0;
+        const double offs = segoff[s] + (inc - v[kPrefixPer - 1]);
+        const u32 bits = (r0 < Ns) ? ((word >> (u32)(r0 & 31)) & 0xFFFFu) : 0u;
+        const u32 nb = __popc(bits);
+        const u32 pinc = warp_scan_incl(nb, lane);
+        const u32 total_b = __shfl_sync(kFullMask, pinc, 31);
+        u32 pos = pinc - nb;
 #pragma unroll
-        for (int w2 = 0; w2 < kPrefixWarps; ++w2) {
-            const double x = wtot[buf][w2];
-            if (w2 < warp) offs += x;
-            tot += x;
+        for (int k = 0; k < kPrefixPer; ++k) {
+            if (bits & (1u << k)) stage[pos++] = offs + v[k];
         }
-        if (r0 < Ns) {
-            const u32 word = ix.bnd_after[r0 >> 5];
-            const u32 sh = (u32)(r0 & 31);
-            const u32 bits = (word >> sh) & 0xFFFFu;
-            if (bits) {
-                u32 idx = 1u + ix.bnd_rank[r0 >> 5] + __popc(word & ((1u << sh) - 1u));
-#pragma unroll
-                for (int k = 0; k < kPrefixPer; ++k) {
-                    if (bits & (1u << k)) preb[idx++] = offs + v[k];
-                }
-            }
-        }
-        carry += tot;
+        __syncwarp();
+        double* __restrict__ dst = preb + 1u + rank0;
+        for (u32 i = lane; i < total_b; i += 32) dst[i] = stage[i];
+        __syncwarp();
     }
     if (tid == 0) preb[0] = 0.0;
 }

@@ -632,7 +632,12 @@ RTX_API int rtx_batch_upload(rtx_ctx* ctx, const rtx_batch* batch) {
     int occ = 0;
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, prob_table_kernel, kProbThreads, smem));
     if (occ < 1) return set_err(ctx, RTX_ERR_CUDA, "prob_table_kernel does not fit on an SM");
-    ctx->prefix_smem = (size_t)hstride * 8;
+    {
+        const size_t n_seg = ctx->ix.n_pad / kPrefixSeg;
+        ctx->prefix_smem = ((size_t)hstride + ((n_seg + 1) & ~(size_t)1) + (size_t)kPrefixWarps * kPrefixSeg) * 8;
+        if (ctx->prefix_smem > 220 * 1024)
+            return set_err(ctx, RTX_ERR_UNSUPPORTED, "reference shard too large for the prefix kernel's segment table (more than ~11 M references per GPU): shard the references");
+    }
     CU(cudaFuncSetAttribute(prefix_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->prefix_smem));
     ctx->walk_smem = (size_t)kWalkWarps * WalkSmem::bytes(ctx->ix.max_levels);
     CU(cudaFuncSetAttribute(lineage_walk_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->walk_smem));
