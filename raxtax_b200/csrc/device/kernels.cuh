@@ -483,8 +483,10 @@ struct ProbScratch {
     double* cbuf;        // [slots][cbuf_stride] r_m[i] = pmf_m(i) / cmf_m(i) of the slow branch, row d = distinct count d
     size_t cbuf_stride;  // = hstride * tstride doubles
     u32 tstride;         // doubles per cbuf row ( >= max t + 1 )
-    double* preb;        // [sub-batch queries][preb_stride] prefix sums of normalised probabilities at node boundaries
-    size_t preb_stride;
+    double* preb;        // [sub-batch queries][preb_stride] prefix sums of normalised probabilities at node boundaries, relative
+    size_t preb_stride;  //   to the start of the 512-reference segment the boundary belongs to
+    double* segoff;      // [sub-batch queries][segoff_stride] prefix sum at the start of every 512-reference segment
+    size_t segoff_stride;
     double* ptab;        // [sub-batch queries][hstride] normalised P(m), direct-indexed by count (K3 -> K4)
     int nprod;           // kProbWarps: one partial prod array per warp; 1: a single array updated with shared-memory atomics
     int lf_smem;         // 1: ln n! staged in shared memory, 0: read from HBM/L2 (very long queries)
@@ -522,7 +524,14 @@ struct __align__(16) NodeRec {
     u32 blo, bhi;      // boundary indices of [lo, hi) clamped to the shard
     u32 child_first;
     u32 cc_type;       // child_count | node_type << 30
+    u32 slo, shi;      // prefix segment the boundary blo / bhi belongs to (segment of the reference in front of it)
+    u32 pad0, pad1;
 };
+
+// confidence of a node = sum of the normalised probabilities of its references (lineage.rs:114-117)
+__device__ __forceinline__ double node_conf(const double* __restrict__ preb, const double* __restrict__ segoff, const NodeRec& r) {
+    return (segoff[r.shi] - segoff[r.slo]) + (preb[r.bhi] - preb[r.blo]);
+}
 
 // ln pmf_m(i) = ln C(m+i-1,i) + ln C(K-m+t-i-1,t-i) - ln C(K+t-1,t): closed form of the iterative sums of prob.rs:136-166.
 // cm = ln (m-1)! + ln (K-m-1)! + T collects the terms that do not depend on i.   Requires 1 <= m <= K-1, i <= t.
@@ -805,14 +814,15 @@ __global__ void __launch_bounds__(kProbThreads)
 // =========================================================================================================
 // K4: prefix sums of the normalised probabilities at node boundaries (lineage.rs:61-77,114-117).
 //
-// One CTA per query, two barrier-free passes over the count vector in 512-reference segments (one segment = one warp
-// iteration, 16 references per lane):
-//   pass 1  segment totals  sum_r P(count[r])  -> shared memory, then one block-wide exclusive scan of the totals;
-//   pass 2  per segment: thread-serial + warp scan on top of the segment offset, the values at the node boundaries of
-//           the segment are compacted in a per-warp staging buffer and stored with coalesced 8-byte lanes.
-// No warp ever waits for another one inside a pass (the old kernel took a block barrier every 4096 references; a
-// chained-scan variant with one CTA per chunk spent 40 % of its time waiting for the preceding chunks' totals).
-// dynamic smem: double Ptab[hstride] | double segoff[n_seg] | double stage[kPrefixWarps][kPrefixSeg]
+// One CTA per query, ONE barrier-free pass over the count vector in 512-reference segments (one segment = one warp
+// iteration, 16 references per lane): thread-serial + warp scan of P(count[r]); the values at the node boundaries of the
+// segment -- relative to the segment start -- are compacted in a per-warp staging buffer and stored with coalesced
+// 8-byte lanes; the segment total goes to shared memory.  After the pass one block-wide exclusive scan turns the totals
+// into segment offsets (a few KB per query).  A node confidence is then
+//     (segoff[seg(hi)] - segoff[seg(lo)]) + (preb[bhi] - preb[blo])                                   (node_conf)
+// so no warp ever waits for another one and the P(m) table is gathered exactly once per reference (the gathers from
+// shared memory are what bounds this kernel: l1tex 97 % in the two-pass version).
+// dynamic smem: double Ptab[hstride] | double segtot[n_seg (even)] | double stage[kPrefixWarps][kPrefixSeg]
 // =========================================================================================================
 constexpr int kPrefixThreads = 256;
 constexpr int kPrefixWarps = kPrefixThreads / 32;
@@ -847,8 +857,8 @@ __global__ void __launch_bounds__(kPrefixThreads)
     const int q = q_base + ql;
     const u32 n_seg = (u32)(ix.n_pad / kPrefixSeg);
     double* Ptab = reinterpret_cast<double*>(xsm_raw);
-    double* segoff = Ptab + b.hstride;
-    double* stage = segoff + ((n_seg + 1u) & ~1u) + (size_t)warp * kPrefixSeg;
+    double* segtot = Ptab + b.hstride;
+    double* stage = segtot + ((n_seg + 1u) & ~1u) + (size_t)warp * kPrefixSeg;
     const u32 K = b.K[q];
     const double* __restrict__ gp = sc.ptab + (size_t)ql * b.hstride;
     for (u32 m = tid; m <= K; m += kPrefixThreads) Ptab[m] = gp[m];
@@ -857,70 +867,29 @@ __global__ void __launch_bounds__(kPrefixThreads)
     double* __restrict__ preb = sc.preb + (size_t)ql * sc.preb_stride;
     const u64 Ns = ix.shard_refs;
 
-    // ---- pass 1: segment totals (two segments in flight per warp) ---------------------------------------------
-    for (u32 s = warp; s < n_seg; s += 2 * kPrefixWarps) {
-        const u32 s2 = s + kPrefixWarps;
-        const u64 ra = (u64)s * kPrefixSeg + (u64)lane * kPrefixPer;
-        const u64 rb = (u64)s2 * kPrefixSeg + (u64)lane * kPrefixPer;
-        const bool has_b = s2 < n_seg;
-        const uint4 a0 = *reinterpret_cast<const uint4*>(qcounts + ra);
-        const uint4 a1 = *reinterpret_cast<const uint4*>(qcounts + ra + 8);
-        uint4 b0 = make_uint4(0, 0, 0, 0), b1 = b0;
-        if (has_b) {
-            b0 = *reinterpret_cast<const uint4*>(qcounts + rb);
-            b1 = *reinterpret_cast<const uint4*>(qcounts + rb + 8);
-        }
-        double v[kPrefixPer];
-        prefix_gather(v, Ptab, a0, a1, ra, Ns);
-        double sa = 0.0;
-#pragma unroll
-        for (int k = 0; k < kPrefixPer; ++k) sa += v[k];
-        sa = warp_sum(sa);
-        if (lane == 0) segoff[s] = sa;
-        if (has_b) {
-            prefix_gather(v, Ptab, b0, b1, rb, Ns);
-            double sb = 0.0;
-#pragma unroll
-            for (int k = 0; k < kPrefixPer; ++k) sb += v[k];
-            sb = warp_sum(sb);
-            if (lane == 0) segoff[s2] = sb;
-        }
+    uint4 c0 = make_uint4(0, 0, 0, 0), c1 = c0;
+    if ((u32)warp < n_seg) {
+        const u64 r0 = (u64)warp * kPrefixSeg + (u64)lane * kPrefixPer;
+        c0 = *reinterpret_cast<const uint4*>(qcounts + r0);
+        c1 = *reinterpret_cast<const uint4*>(qcounts + r0 + 8);
     }
-    __syncthreads();
-    // ---- exclusive scan of the segment totals, in place --------------------------------------------------------
-    {
-        const u32 per = (n_seg + kPrefixThreads - 1) / kPrefixThreads;
-        const u32 lo = min(n_seg, (u32)tid * per), hi = min(n_seg, lo + per);
-        double loc = 0.0;
-        for (u32 i = lo; i < hi; ++i) loc += segoff[i];
-        const double inc = warp_scan_incl(loc, lane);
-        if (lane == 31) wtot[warp] = inc;
-        __syncthreads();
-        double run = inc - loc;
-#pragma unroll
-        for (int w2 = 0; w2 < kPrefixWarps; ++w2)
-            if (w2 < warp) run += wtot[w2];
-        for (u32 i = lo; i < hi; ++i) {
-            const double x = segoff[i];
-            segoff[i] = run;
-            run += x;
-        }
-    }
-    __syncthreads();
-    // ---- pass 2: prefix sums at the node boundaries ---------------------------------------------------------------
     for (u32 s = warp; s < n_seg; s += kPrefixWarps) {
         const u64 r0 = (u64)s * kPrefixSeg + (u64)lane * kPrefixPer;
-        if ((u64)s * kPrefixSeg >= Ns) break;
-        const uint4 c0 = *reinterpret_cast<const uint4*>(qcounts + r0);
-        const uint4 c1 = *reinterpret_cast<const uint4*>(qcounts + r0 + 8);
         const u32 word = ix.bnd_after[r0 >> 5];
         const u32 rank0 = ix.bnd_rank[s * (kPrefixSeg / 32)];  // boundaries before this segment
+        const uint4 x0 = c0, x1 = c1;
+        if (s + kPrefixWarps < n_seg) {  // the next segment's counts are requested before this one is used
+            const u64 rn = r0 + (u64)kPrefixWarps * kPrefixSeg;
+            c0 = *reinterpret_cast<const uint4*>(qcounts + rn);
+            c1 = *reinterpret_cast<const uint4*>(qcounts + rn + 8);
+        }
         double v[kPrefixPer];
-        prefix_gather(v, Ptab, c0, c1, r0, Ns);
+        prefix_gather(v, Ptab, x0, x1, r0, Ns);
 #pragma unroll
         for (int k = 1; k < kPrefixPer; ++k) v[k] += v[k - 1];
         const double inc = warp_scan_incl(v[kPrefixPer - 1], lane);
-        const double offs = segoff[s] + (inc - v[kPrefixPer - 1]);
+        const double offs = inc - v[kPrefixPer - 1];
+        if (lane == 31) segtot[s] = inc;
         const u32 bits = (r0 < Ns) ? ((word >> (u32)(r0 & 31)) & 0xFFFFu) : 0u;
         const u32 nb = __popc(bits);
         const u32 pinc = warp_scan_incl(nb, lane);
@@ -934,6 +903,26 @@ __global__ void __launch_bounds__(kPrefixThreads)
         double* __restrict__ dst = preb + 1u + rank0;
         for (u32 i = lane; i < total_b; i += 32) dst[i] = stage[i];
         __syncwarp();
+    }
+    __syncthreads();
+    // ---- exclusive scan of the segment totals -> segment offsets -------------------------------------------------
+    {
+        double* __restrict__ gseg = sc.segoff + (size_t)ql * sc.segoff_stride;
+        const u32 per = (n_seg + kPrefixThreads - 1) / kPrefixThreads;
+        const u32 lo = min(n_seg, (u32)tid * per), hi = min(n_seg, lo + per);
+        double loc = 0.0;
+        for (u32 i = lo; i < hi; ++i) loc += segtot[i];
+        const double inc = warp_scan_incl(loc, lane);
+        if (lane == 31) wtot[warp] = inc;
+        __syncthreads();
+        double run = inc - loc;
+#pragma unroll
+        for (int w2 = 0; w2 < kPrefixWarps; ++w2)
+            if (w2 < warp) run += wtot[w2];
+        for (u32 i = lo; i < hi; ++i) {
+            gseg[i] = run;
+            run += segtot[i];
+        }
     }
     if (tid == 0) preb[0] = 0.0;
 }
@@ -974,6 +963,7 @@ __global__ void __launch_bounds__(128) shard_records_kernel(IndexView ix, const 
     if (w >= (long long)q_count * sv.n_strad) return;
     const int ql = (int)(w / sv.n_strad), j = (int)(w % sv.n_strad);
     const double* __restrict__ preb = sc.preb + (size_t)ql * sc.preb_stride;
+    const double* __restrict__ segoff = sc.segoff + (size_t)ql * sc.segoff_stride;
     const u32 node = sv.strad_nodes[j];
     const NodeRec nr = recs[node];
     const u32 cf = nr.child_first, cc = nr.cc_type & 0x3FFFFFFFu;
@@ -983,7 +973,7 @@ __global__ void __launch_bounds__(128) shard_records_kernel(IndexView ix, const 
         const u32 ci = cb + lane;
         if (ci < cc && sv.strad_of_node[cf + ci] < 0 && node_inside(ix, cf + ci)) {
             const NodeRec cr = recs[cf + ci];
-            const double v = preb[cr.bhi] - preb[cr.blo];
+            const double v = node_conf(preb, segoff, cr);
             best = fmax(best, v);
             n_sig += ((u32)round(v * 100.0) != 0);
         }
@@ -1000,7 +990,7 @@ __global__ void __launch_bounds__(128) shard_records_kernel(IndexView ix, const 
             const u32 ci = cb + lane;
             if (ci < cc && sv.strad_of_node[cf + ci] < 0 && node_inside(ix, cf + ci)) {
                 const NodeRec cr = recs[cf + ci];
-                if (preb[cr.bhi] - preb[cr.blo] >= thr) besti = cf + ci;
+                if (node_conf(preb, segoff, cr) >= thr) besti = cf + ci;
             }
         }
 #pragma unroll
@@ -1008,7 +998,7 @@ __global__ void __launch_bounds__(128) shard_records_kernel(IndexView ix, const 
     }
     if (lane == 0) {
         ShardRec r;
-        r.mass = preb[nr.bhi] - preb[nr.blo];
+        r.mass = node_conf(preb, segoff, nr);
         r.best = best;
         r.best_child = besti;
         r.n_sig = n_sig;
@@ -1113,6 +1103,7 @@ __global__ void __launch_bounds__(kWalkWarps * 32)
     WalkSmem ws(wsm_raw + (size_t)warp * WalkSmem::bytes(ML), ML);
     const double Nd = (double)ix.n_refs;
     const double* __restrict__ preb = sc.preb + (size_t)ql * sc.preb_stride;
+    const double* __restrict__ segoff = sc.segoff + (size_t)ql * sc.segoff_stride;
     int status = pool.status[q];
 
     u32 n_res = 0;
@@ -1138,16 +1129,16 @@ __global__ void __launch_bounds__(kWalkWarps * 32)
             for (u32 cb = nxt; cb < cc; cb += 32) {
                 const u32 ci = cb + lane;
                 u32 k = 0;
-                NodeRec cr = NodeRec{0, 0, 0, 0};
+                NodeRec cr = NodeRec{0, 0, 0, 0, 0, 0, 0, 0};
                 if (ci < cc) {
                     cr = recs[cf + ci];
                     if (SH) {
                         const int sj = sv.strad_of_node[cf + ci];
                         if (sj >= 0) k = sv.sk[(size_t)ql * sv.n_strad + sj];  // combined over the ranks
-                        else if (node_inside(ix, cf + ci)) k = (u32)round((preb[cr.bhi] - preb[cr.blo]) * 100.0);
+                        else if (node_inside(ix, cf + ci)) k = (u32)round((node_conf(preb, segoff, cr)) * 100.0);
                         // children inside another shard are walked by their owner
                     } else {
-                        k = (u32)round((preb[cr.bhi] - preb[cr.blo]) * 100.0);  // f64::round, half away from zero (lineage.rs:129)
+                        k = (u32)round((node_conf(preb, segoff, cr)) * 100.0);  // f64::round, half away from zero (lineage.rs:129)
                     }
                 }
                 const u32 mask = __ballot_sync(kFullMask, k != 0);
@@ -1220,12 +1211,12 @@ __global__ void __launch_bounds__(kWalkWarps * 32)
                         // within 1e-12 relative of the maximum count as maximal.
                         double best = -CUDART_INF;
                         double cv0 = -CUDART_INF;      // this lane's child of the first 32 (kept for the second pass)
-                        NodeRec cr0 = NodeRec{0, 0, 0, 0};
+                        NodeRec cr0 = NodeRec{0, 0, 0, 0, 0, 0, 0, 0};
                         for (u32 cb = 0; cb < cur_cc; cb += 32) {
                             const u32 ci = cb + lane;
                             if (ci < cur_cc) {
                                 const NodeRec cr = recs[cur_cf + ci];
-                                const double v = preb[cr.bhi] - preb[cr.blo];
+                                const double v = node_conf(preb, segoff, cr);
                                 if (cb == 0) {
                                     cv0 = v;
                                     cr0 = cr;
@@ -1242,7 +1233,7 @@ __global__ void __launch_bounds__(kWalkWarps * 32)
                             const u32 ci = cb + lane;
                             if (ci < cur_cc) {
                                 const NodeRec cr = recs[cur_cf + ci];
-                                if (preb[cr.bhi] - preb[cr.blo] >= thr) besti = ci;
+                                if (node_conf(preb, segoff, cr) >= thr) besti = ci;
                             }
                         }
 #pragma unroll

@@ -51,7 +51,7 @@ struct rtx_ctx {
     ProbScratch sc{};
     int prob_slots = 0;
     size_t prob_smem = 0, walk_smem = 0, prefix_smem = 0;
-    DevBuf d_cbuf, d_preb, d_ptab;
+    DevBuf d_cbuf, d_preb, d_ptab, d_segoff;
     // reference-sharded mode
     ShardView sv{};
     int shard_phase = 0;
@@ -201,7 +201,7 @@ RTX_API void rtx_ctx_destroy(rtx_ctx* c) {
                       &c->d_bnd_rank, &c->d_ref_levels, &c->d_lnfact, &c->d_seq_off, &c->d_codes, &c->d_exact_off, &c->d_exact_ids,
                       &c->d_K, &c->d_kmers, &c->d_rows, &c->d_nrows, &c->d_hist, &c->d_counts, &c->d_pool_first, &c->d_pool_nlev,
                       &c->d_pool_conf, &c->d_pool_local, &c->d_pool_used, &c->d_res_off, &c->d_res_cnt, &c->d_global, &c->d_status,
-                      &c->d_hits, &c->d_cbuf, &c->d_preb, &c->d_ptab, &c->d_recs, &c->d_strad_of_node, &c->d_strad_nodes, &c->d_strad_parent,
+                      &c->d_hits, &c->d_cbuf, &c->d_preb, &c->d_ptab, &c->d_segoff, &c->d_recs, &c->d_strad_of_node, &c->d_strad_nodes, &c->d_strad_parent,
                       &c->d_send, &c->d_recv, &c->d_sk, &c->d_sany, &c->d_sbest};
     for (DevBuf* b : bufs) b->release();
     if (c->stream) cudaStreamDestroy(c->stream);
@@ -380,7 +380,10 @@ RTX_API int rtx_index_upload(rtx_ctx* ctx, const rtx_index_desc* d) {
     CU(upload_vec(ctx->d_child_count, d->child_count, nn, &bytes));
     {
         std::vector<NodeRec> recs(nn);
-        for (u32 i = 0; i < nn; ++i) recs[i] = NodeRec{blo[i], bhi[i], d->child_first[i], d->child_count[i] | ((u32)d->node_type[i] << 30)};
+        auto seg_of = [&](u64 pos) -> u32 { return pos > s0 ? (u32)((pos - s0 - 1) / kPrefixSeg) : 0u; };  // segment of the reference in front of pos
+        for (u32 i = 0; i < nn; ++i)
+            recs[i] = NodeRec{blo[i], bhi[i], d->child_first[i], d->child_count[i] | ((u32)d->node_type[i] << 30),
+                              seg_of(clampu(d->node_lo[i])), seg_of(clampu(d->node_hi[i])), 0u, 0u};
         CU(upload_vec(ctx->d_recs, recs.data(), nn, &bytes));
     }
     CU(upload_vec(ctx->d_node_blo, blo.data(), nn, &bytes));
@@ -655,6 +658,9 @@ RTX_API int rtx_batch_upload(rtx_ctx* ctx, const rtx_batch* batch) {
     ctx->sc.ptab = ctx->d_ptab.as<double>();
     ctx->sc.cbuf = ctx->d_cbuf.as<double>();
     ctx->sc.preb = ctx->d_preb.as<double>();
+    ctx->sc.segoff_stride = round_up((u32)(ctx->ix.n_pad / kPrefixSeg), 4);
+    CU(ctx->d_segoff.ensure((size_t)sb * ctx->sc.segoff_stride * 8));
+    ctx->sc.segoff = ctx->d_segoff.as<double>();
     ctx->has_batch = true;
     return RTX_OK;
 }
