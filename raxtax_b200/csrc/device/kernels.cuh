@@ -194,8 +194,9 @@ __device__ __forceinline__ void csa(u32& s, u32& c, u32 a, u32 b, u32 d) {
     s = x ^ d;
 }
 
+// 16 rows into the planes 0..3; the weight-16 carry is returned, not rippled (two of them are merged first, see fold32)
 template <int NP>
-__device__ __forceinline__ void add16(u32 (&pl)[NP], const u32 (&x)[16]) {
+__device__ __forceinline__ u32 add16_carry(u32 (&pl)[NP], const u32 (&x)[16]) {
     u32 a[8], b4[4], d2[2], e;
 #pragma unroll
     for (int i = 0; i < 8; ++i) csa(pl[0], a[i], pl[0], x[2 * i], x[2 * i + 1]);
@@ -204,11 +205,29 @@ __device__ __forceinline__ void add16(u32 (&pl)[NP], const u32 (&x)[16]) {
 #pragma unroll
     for (int i = 0; i < 2; ++i) csa(pl[2], d2[i], pl[2], b4[2 * i], b4[2 * i + 1]);
     csa(pl[3], e, pl[3], d2[0], d2[1]);
+    return e;
+}
+// ripple a carry of weight 2^P0 into the planes P0..NP-1
+template <int NP, int P0>
+__device__ __forceinline__ void ripple(u32 (&pl)[NP], u32 e) {
 #pragma unroll
-    for (int p = 4; p < NP; ++p) {
+    for (int p = P0; p < NP; ++p) {
         u32 t = pl[p] & e;
         pl[p] ^= e;
         e = t;
+    }
+}
+template <int NP>
+__device__ __forceinline__ void add16(u32 (&pl)[NP], const u32 (&x)[16]) {
+    ripple<NP, 4>(pl, add16_carry<NP>(pl, x));
+}
+// two weight-16 carries: one full adder into plane 4, then a single ripple from plane 5
+template <int NP>
+__device__ __forceinline__ void merge_carries(u32 (&pl)[NP], u32 ea, u32 eb) {
+    if (NP > 4) {
+        u32 c;
+        csa(pl[4 < NP ? 4 : 0], c, pl[4 < NP ? 4 : 0], ea, eb);
+        ripple<NP, 5>(pl, c);
     }
 }
 
@@ -254,13 +273,17 @@ __device__ __forceinline__ u32 vec_get(const uint4& v, int i) { return i == 0 ? 
 // the tiles of a CTA divide evenly over its warps).
 // dynamic shared memory: u32 srow[kRowListCap] + u32 shist[hstride]
 // PF = software prefetch: the next 16 rows are requested before the current 16 are folded (register double buffer).
+// address of a row's slice: one IMAD.WIDE on the fma pipe (the compiler's own choice, IMAD.WIDE + two LEAs, put a third of
+// the inner loop's alu-pipe work into address arithmetic; LOP3 shares that pipe at half rate)
+__device__ __forceinline__ const void* row_ptr(const u32* __restrict__ colbase, u32 rid, u32 row_bytes) {
+    u64 a;
+    asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(a) : "r"(rid), "r"(row_bytes), "l"(colbase));
+    return reinterpret_cast<const void*>(a);
+}
 template <int V, typename vec_t>
-__device__ __forceinline__ void load16(vec_t (&x)[16], const u32* __restrict__ colbase, const u32* __restrict__ srow, u32 j, u32 row_words) {
+__device__ __forceinline__ void load16(vec_t (&x)[16], const u32* __restrict__ colbase, const u32* __restrict__ srow, u32 j, u32 row_bytes) {
 #pragma unroll
-    for (int i = 0; i < 16; ++i) {
-        const u32 rid = srow[j + i];
-        x[i] = ldg_stream(reinterpret_cast<const vec_t*>(colbase + (size_t)rid * row_words));
-    }
+    for (int i = 0; i < 16; ++i) x[i] = ldg_stream(reinterpret_cast<const vec_t*>(row_ptr(colbase, srow[j + i], row_bytes)));
 }
 template <int V, int NP, typename vec_t>
 __device__ __forceinline__ void fold16(u32 (&pl)[V][NP], const vec_t (&x)[16]) {
@@ -271,6 +294,22 @@ __device__ __forceinline__ void fold16(u32 (&pl)[V][NP], const vec_t (&x)[16]) {
         for (int i = 0; i < 16; ++i) xv[i] = vec_get(x[i], v);
         add16<NP>(pl[v], xv);
     }
+}
+
+template <int V, int NP, typename vec_t>
+__device__ __forceinline__ void fold16_carry(u32 (&pl)[V][NP], const vec_t (&x)[16], u32 (&e)[V]) {
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+        u32 xv[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) xv[i] = vec_get(x[i], v);
+        e[v] = add16_carry<NP>(pl[v], xv);
+    }
+}
+template <int V, int NP>
+__device__ __forceinline__ void merge_carries_v(u32 (&pl)[V][NP], const u32 (&ea)[V], const u32 (&eb)[V]) {
+#pragma unroll
+    for (int v = 0; v < V; ++v) merge_carries<NP>(pl[v], ea[v], eb[v]);
 }
 
 template <int V, int NP, bool PF>
@@ -290,6 +329,7 @@ __global__ void __launch_bounds__(kHitThreads)
     const int tile_end = min(n_tiles, tile_begin + tiles_per_cta);
     const int rounds = (tile_end - tile_begin + nwarps - 1) / nwarps;
     const u32 nbins = (u32)b.K[q] + 1u;
+    const u32 row_bytes = ix.row_words * 4u;
 
     for (u32 i = tid; i < nbins; i += nthreads) shist[i] = 0;
     const bool single = n <= (u32)kRowListCap;
@@ -320,18 +360,24 @@ __global__ void __launch_bounds__(kHitThreads)
                 const u32* __restrict__ colbase = ix.bitrows + word0;
                 if (PF) {
                     vec_t xa[16], xb[16];
-                    load16<V>(xa, colbase, srow, 0, ix.row_words);
+                    load16<V>(xa, colbase, srow, 0, row_bytes);
                     for (u32 j = 0; j < cn; j += 32) {
                         const bool has_b = j + 16 < cn;
-                        if (has_b) load16<V>(xb, colbase, srow, j + 16, ix.row_words);
-                        fold16<V, NP>(pl, xa);
-                        if (j + 32 < cn) load16<V>(xa, colbase, srow, j + 32, ix.row_words);
-                        if (has_b) fold16<V, NP>(pl, xb);
+                        u32 ea[V], eb[V];
+                        if (has_b) load16<V>(xb, colbase, srow, j + 16, row_bytes);
+                        fold16_carry<V, NP>(pl, xa, ea);
+                        if (j + 32 < cn) load16<V>(xa, colbase, srow, j + 32, row_bytes);
+                        if (has_b) fold16_carry<V, NP>(pl, xb, eb);
+                        else {
+#pragma unroll
+                            for (int v = 0; v < V; ++v) eb[v] = 0;
+                        }
+                        merge_carries_v<V, NP>(pl, ea, eb);
                     }
                 } else {
                     for (u32 j = 0; j < cn; j += 16) {
                         vec_t x[16];
-                        load16<V>(x, colbase, srow, j, ix.row_words);
+                        load16<V>(x, colbase, srow, j, row_bytes);
                         fold16<V, NP>(pl, x);
                     }
                 }
@@ -367,6 +413,142 @@ __global__ void __launch_bounds__(kHitThreads)
     for (u32 i = tid; i < nbins; i += nthreads) {
         u32 h = shist[i];
         if (h) atomicAdd(&ghist[i], h);
+    }
+}
+
+// =========================================================================================================
+// K2 (query-group form): the single-query kernel above sits exactly on the L2 -> SM bandwidth cap (every bit row of every
+// query is fetched from L2 once per reference tile: 82 GB per 10 k queries on C2 = 12.4 TB/s).  Queries of one batch share
+// rows (two COI queries have ~22 % of their 8-mers in common; the union of 16 queries' rows is ~half the sum), so here a
+// CTA carries G queries -- one per warp -- over the SAME reference tile and keeps them in lockstep over the row-id space:
+// the sorted row lists are cut at common row-id boundaries ("chunks") and a block barrier separates the chunks, so that a
+// row wanted by several warps is requested within one chunk's time window and all but the first request hit the L1
+// (plain ld.global.nc, L1-allocating; one chunk's union of rows is sized to fit the L1 carve-out).
+// grid: x = query group (fastest: L2 blocking over reference tile groups as before), y = tile group.
+// dynamic smem: u32 srow[G][kstride] | u32 shist[G][hstride] | u16 cpos[G][n_chunks]
+// =========================================================================================================
+__device__ __forceinline__ uint2 ldg_l1(const uint2* p) {
+    uint2 r;
+    asm volatile("ld.global.nc.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ uint4 ldg_l1(const uint4* p) {
+    uint4 r;
+    asm volatile("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+}
+template <int V, typename vec_t>
+__device__ __forceinline__ void load16_l1(vec_t (&x)[16], const u32* __restrict__ colbase, const u32* __restrict__ srow, u32 j, u32 row_bytes) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) x[i] = ldg_l1(reinterpret_cast<const vec_t*>(row_ptr(colbase, srow[j + i], row_bytes)));
+}
+
+constexpr int kHitGroupMaxThreads = 512;
+
+template <int V, int NP>
+__global__ void __launch_bounds__(kHitGroupMaxThreads, 1)
+    hitcount_group_kernel(IndexView ix, BatchView b, u16* __restrict__ counts, int q_base, int q_count, int tiles_per_cta, int n_tiles,
+                          u32 chunk_rows, int n_chunks) {
+    extern __shared__ __align__(16) u32 hsm[];
+    typedef typename RowVec<V>::T vec_t;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int G = blockDim.x >> 5;
+    u32* srow = hsm + (size_t)warp * b.kstride;
+    u32* shist = hsm + (size_t)G * b.kstride + (size_t)warp * b.hstride;
+    u16* cpos = reinterpret_cast<u16*>(hsm + (size_t)G * (b.kstride + b.hstride)) + (size_t)warp * n_chunks;
+    const int ql = blockIdx.x * G + warp;
+    const bool valid = ql < q_count;
+    const int q = q_base + (valid ? ql : 0);
+    const u32 n = valid ? b.nrows[q] : 0u;  // padded to a multiple of 16 with the all-zero row 0
+    const u32 nbins = valid ? (u32)b.K[q] + 1u : 0u;
+    const u32* __restrict__ qrows = b.rows + (size_t)q * b.kstride;
+    for (u32 i = lane; i < n; i += 32) srow[i] = qrows[i];
+    for (u32 i = lane; i < nbins; i += 32) shist[i] = 0;
+    __syncwarp();
+    // chunk c holds the rows with id in [c * chunk_rows, (c + 1) * chunk_rows); cpos[c] = list position where it ends
+    for (int c = lane; c < n_chunks; c += 32) {
+        u32 lo = 0, hi = n;
+        if (c < n_chunks - 1) {
+            const u32 bound = (u32)(c + 1) * chunk_rows;
+            while (lo < hi) {
+                const u32 mid = (lo + hi) >> 1;
+                const u32 x = srow[mid];
+                if (x != 0u && x < bound) lo = mid + 1;  // the padding rows (id 0) sit at the end of the ascending list
+                else hi = mid;
+            }
+        } else lo = n;
+        cpos[c] = (u16)lo;
+    }
+    __syncwarp();
+
+    const int tile_begin = blockIdx.y * tiles_per_cta;
+    const int tile_end = min(n_tiles, tile_begin + tiles_per_cta);
+    const u32 row_bytes = ix.row_words * 4u;
+    u16* __restrict__ qcounts = counts + (size_t)ql * ix.n_pad;
+    for (int tile = tile_begin; tile < tile_end; ++tile) {
+        const u32 word0 = (u32)tile * (32 * V) + lane * V;
+        const u32* __restrict__ colbase = ix.bitrows + word0;
+        u32 pl[V][NP];
+#pragma unroll
+        for (int v = 0; v < V; ++v)
+#pragma unroll
+            for (int p = 0; p < NP; ++p) pl[v][p] = 0;
+        int c = 0;
+        vec_t xa[16], xb[16];
+        if (n) load16_l1<V>(xa, colbase, srow, 0, row_bytes);
+        for (u32 j = 0; j < n; j += 32) {
+            while (c < n_chunks && j >= (u32)cpos[c]) {  // this warp is done with chunk c: wait for the others
+                __syncthreads();
+                ++c;
+            }
+            const bool has_b = j + 16 < n;
+            u32 ea[V], eb[V];
+            if (has_b) load16_l1<V>(xb, colbase, srow, j + 16, row_bytes);
+            fold16_carry<V, NP>(pl, xa, ea);
+            if (j + 32 < n) load16_l1<V>(xa, colbase, srow, j + 32, row_bytes);
+            if (has_b) fold16_carry<V, NP>(pl, xb, eb);
+            else {
+#pragma unroll
+                for (int v = 0; v < V; ++v) eb[v] = 0;
+            }
+            merge_carries_v<V, NP>(pl, ea, eb);
+        }
+        while (c < n_chunks) {
+            __syncthreads();
+            ++c;
+        }
+        if (valid) {
+#pragma unroll
+            for (int v = 0; v < V; ++v) {
+                u32 out[16];
+                planes_to_counts<NP>(pl[v], out);
+                const u64 ref0 = (u64)(word0 + v) * 32;
+                uint4* dst = reinterpret_cast<uint4*>(qcounts + ref0);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) dst[i] = make_uint4(out[4 * i], out[4 * i + 1], out[4 * i + 2], out[4 * i + 3]);
+                if (ref0 + 32 <= ix.shard_refs) {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        atomicAdd(&shist[out[i] & 0xFFFFu], 1u);
+                        atomicAdd(&shist[out[i] >> 16], 1u);
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        if (ref0 + 2 * i < ix.shard_refs) atomicAdd(&shist[out[i] & 0xFFFFu], 1u);
+                        if (ref0 + 2 * i + 1 < ix.shard_refs) atomicAdd(&shist[out[i] >> 16], 1u);
+                    }
+                }
+            }
+        }
+    }
+    __syncwarp();
+    if (valid) {
+        u32* __restrict__ ghist = b.hist + (size_t)q * b.hstride;
+        for (u32 i = lane; i < nbins; i += 32) {
+            const u32 h = shist[i];
+            if (h) atomicAdd(&ghist[i], h);
+        }
     }
 }
 
@@ -1052,7 +1234,7 @@ __global__ void shard_combine_kernel(ShardView sv, int q_count) {
 // look at, "had a significant child").  Confidences are carried as integers k = round(conf*100), so that the
 // reported value k/100 is bit-identical to the reference's round(conf*100)/100.
 // =========================================================================================================
-constexpr int kWalkWarps = 1;  // one warp per CTA: a slot frees as soon as its walker finishes (walk lengths vary a lot)
+constexpr int kWalkWarps = 1;  // one warp per CTA: a slot frees as soon as its walker finishes (2 per CTA measured equal: the tail is the longest walk)
 
 // per-warp shared state; res_k rows have stride ML
 struct WalkSmem {

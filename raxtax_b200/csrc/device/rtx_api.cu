@@ -28,6 +28,8 @@ struct rtx_ctx {
     bool profile = false;
     int hit_tune = 0;
     int hit_max_tiles = 0;
+    int hit_group = 0;   // RTX_OPT_HITCOUNT_GROUP
+    int hit_chunks = 0;  // RTX_OPT_HITCOUNT_CHUNKS
     // index
     bool has_index = false;
     IndexView ix{};
@@ -228,6 +230,14 @@ RTX_API int rtx_ctx_set_option(rtx_ctx* ctx, int option, int64_t value) {
         case RTX_OPT_HITCOUNT_MAX_TILES:
             REQUIRE(value >= 0 && value <= 4096, "bad max tiles per CTA");
             ctx->hit_max_tiles = (int)value;
+            return RTX_OK;
+        case RTX_OPT_HITCOUNT_GROUP:
+            REQUIRE((value >= 0 && value <= kHitGroupMaxThreads / 32) || value == 101, "bad query group size");  // 101: group kernel with one query per CTA (experiments)
+            ctx->hit_group = (int)value;
+            return RTX_OK;
+        case RTX_OPT_HITCOUNT_CHUNKS:
+            REQUIRE(value >= 0 && value <= 4096, "bad chunk count");
+            ctx->hit_chunks = (int)value;
             return RTX_OK;
         case RTX_OPT_HITCOUNT_TUNE:
             REQUIRE(value >= 0 && value < 1000 && (value % 10 == 0 || value % 10 == 2 || value % 10 == 4), "bad hit-count tuning word");
@@ -712,7 +722,53 @@ static cudaError_t launch_hitcount_np(rtx_ctx* c, int q_base, int qb, u32 kmax, 
     return launch_hitcount<V, 16, PF>(c, q_base, qb, nwarps);
 }
 
+// L2 blocking shared by both bit-row kernels: CTAs are scheduled query-fastest, so all queries of one reference tile group
+// run together; the group's slice of the bit matrix (n_rows x tiles x 128*V bytes) should stay resident in the 126 MB L2.
+static void hit_tile_groups(const rtx_ctx* c, int V, int* n_tiles, int* groups, int* tiles_per_cta) {
+    *n_tiles = (int)(c->ix.row_words / (32 * V));
+    int max_tiles = c->hit_max_tiles;
+    if (max_tiles <= 0) {
+        const double slice_bytes_per_tile = (double)c->n_rows * 32.0 * V * 4.0;
+        max_tiles = (int)std::min(64.0, std::max(4.0, std::floor(64e6 / slice_bytes_per_tile)));
+    }
+    *groups = (*n_tiles + max_tiles - 1) / max_tiles;
+    *tiles_per_cta = (*n_tiles + *groups - 1) / *groups;
+}
+
+// query-group kernel: G queries per CTA (one per warp) in lockstep over row-id chunks sized to the L1
+template <int NP>
+static cudaError_t launch_hitcount_group(rtx_ctx* c, int q_base, int qb, int G) {
+    constexpr int V = 2;
+    int n_tiles, groups, tiles_per_cta;
+    hit_tile_groups(c, V, &n_tiles, &groups, &tiles_per_cta);
+    const u32 ks = c->bv.kstride, hs = c->bv.hstride;
+    // lockstep chunks: measured on C2 (profiles/r01_hitcount_group_sweep.txt) the barriers cost more than the L1 hits save
+    // (G16: L1 hit rate 48 %, L2 throughput 22 %, but 7.6 ms against 5.6 ms without barriers), so the default is none.
+    int n_chunks = c->hit_chunks > 0 ? c->hit_chunks : 1;
+    n_chunks = std::max(1, std::min(n_chunks, 4096));
+    const u32 chunk_rows = (c->n_rows + n_chunks - 1) / n_chunks + 1;
+    const size_t smem = (size_t)G * (ks + hs) * 4 + (size_t)G * n_chunks * 2 + 16;
+    cudaError_t e = cudaFuncSetAttribute(hitcount_group_kernel<V, NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    dim3 grid((qb + G - 1) / G, groups);
+    hitcount_group_kernel<V, NP><<<grid, G * 32, smem, c->stream>>>(c->ix, c->bv, c->d_counts.as<u16>(), q_base, qb, tiles_per_cta, n_tiles,
+                                                                   chunk_rows, n_chunks);
+    return cudaGetLastError();
+}
+
 static cudaError_t launch_hitcount_tuned(rtx_ctx* c, int q_base, int qb, u32 kmax) {
+    int G = c->hit_group;  // 0 = default
+    const bool force_group = G == 101;
+    if (force_group) G = 1;
+    if (G == 0) G = 4;
+    while (G > 1 && (size_t)G * (c->bv.kstride + c->bv.hstride) * 4 > 150 * 1024) G /= 2;  // long queries: smaller groups
+    if ((G > 1 || force_group) && qb >= G) {
+        if (kmax < (1u << 8)) return launch_hitcount_group<8>(c, q_base, qb, G);
+        if (kmax < (1u << 10)) return launch_hitcount_group<10>(c, q_base, qb, G);
+        if (kmax < (1u << 11)) return launch_hitcount_group<11>(c, q_base, qb, G);
+        if (kmax < (1u << 13)) return launch_hitcount_group<13>(c, q_base, qb, G);
+        return launch_hitcount_group<16>(c, q_base, qb, G);
+    }
     const int tune = c->hit_tune ? c->hit_tune : 12;  // default: 2 words per lane, register double buffering
     const int V = tune % 10 ? tune % 10 : 4;
     const bool PF = (tune / 10) % 10 != 0;

@@ -1,7 +1,13 @@
-"""GPU micro-benchmark: hit-count kernel time on the C2 workload for each geometry (RTX_OPT_HITCOUNT_TUNE)."""
+"""GPU micro-benchmark: hit-count kernel time on a workload for each geometry.
+
+usage: sweep_hitcount.py [workload] [configs]     configs = comma-separated words of letter+number fields, e.g.  G16C0,G8C12,G1T12M4
+   G = RTX_OPT_HITCOUNT_GROUP (queries per CTA; 1 = single-query kernel), C = RTX_OPT_HITCOUNT_CHUNKS, T = RTX_OPT_HITCOUNT_TUNE,
+   M = RTX_OPT_HITCOUNT_MAX_TILES.  Every configuration's histograms are compared with the first one's (bit-exact).
+"""
 import json
-import sys
 import os
+import re
+import sys
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
@@ -9,17 +15,20 @@ import numpy as np
 from raxtax_b200 import capi, synth
 
 name = sys.argv[1] if len(sys.argv) > 1 else "c2"
-tunes = [int(x) for x in sys.argv[2].split(",")] if len(sys.argv) > 2 else [0, 804, 504, 404, 802, 502, 602, 702, 402, 812, 512, 412]
-ds = synth.generate(name, measure=False)
+configs = sys.argv[2].split(",") if len(sys.argv) > 2 else ["G1", "G16", "G8", "G4"]
+nq = int(sys.argv[3]) if len(sys.argv) > 3 else None
+ds = synth.generate(name, n_queries=nq, measure=False)
 tree = capi.Tree.new(ds.ref_lineages, ds.ref_off, ds.ref_codes)
 ctx = capi.Context(0)
 ctx.upload_tree(tree)
 eo, eids = tree.exact_batch(ds.query_off, ds.query_codes)
 ctx.batch_upload(ds.query_off, ds.query_codes, eo, eids)
+OPT = {"G": capi.RTX_OPT_HITCOUNT_GROUP, "C": capi.RTX_OPT_HITCOUNT_CHUNKS, "T": capi.RTX_OPT_HITCOUNT_TUNE, "M": capi.RTX_OPT_HITCOUNT_MAX_TILES}
 ref = None
-for t in tunes:
-    ctx.set_option(capi.RTX_OPT_HITCOUNT_TUNE, t % 1000)
-    ctx.set_option(capi.RTX_OPT_HITCOUNT_MAX_TILES, t // 1000)
+for cfg in configs:
+    f = {k: int(v) for k, v in re.findall(r"([GCTM])(\d+)", cfg)}
+    for k, o in OPT.items():
+        ctx.set_option(o, f.get(k, 0))
     ctx.set_option(capi.RTX_OPT_PROFILE, 0)
     ctx.batch_run()
     ctx.synchronize()
@@ -29,10 +38,10 @@ for t in tunes:
         ctx.batch_run()
     out = ctx.batch_download(taps=("hist",))
     p = ctx.profile()
-    chk = int(out.hist.astype(np.int64).sum()), int((out.hist.astype(np.int64) * np.arange(out.hist.shape[1])).sum())
     if ref is None:
-        ref = chk
+        ref = out.hist.copy()
     ms = p["hitcount"]["total_ms"] / p["hitcount"]["launches"]
     gbs = p["bitrow_bytes"] / p["hitcount"]["launches"] / ms / 1e6
-    print(json.dumps(dict(tune=t, hitcount_ms=round(ms, 3), bitrow_GBps=round(gbs, 1), prob_ms=round(p["prob"]["total_ms"] / p["prob"]["launches"], 3), walk_ms=round(p["walk"]["total_ms"] / max(p["walk"]["launches"], 1), 3),
-                          checksum_ok=chk == ref)), flush=True)
+    print(json.dumps(dict(cfg=cfg, hitcount_ms=round(ms, 3), bitrow_GBps=round(gbs, 1), prob_ms=round(p["prob"]["total_ms"] / p["prob"]["launches"], 3),
+                          prefix_ms=round(p["prefix"]["total_ms"] / max(p["prefix"]["launches"], 1), 3),
+                          walk_ms=round(p["walk"]["total_ms"] / max(p["walk"]["launches"], 1), 3), hist_identical=bool(np.array_equal(out.hist, ref)))), flush=True)
