@@ -218,24 +218,30 @@ def test_errors_are_loud(ctx):
         ctx.upload_index_arrays(0, np.zeros(65537, np.uint64), np.zeros(1, np.uint32), [0], [0], [0], [0], [0], [1])
 
 
-# ---- full-size properties (BASELINE config 2 shape, reduced query count) ---------------------------------------------------
-def test_c2_scale_properties(ctx):
-    ds = synth.generate("c2", n_queries=300, measure=False)
+# ---- full-size properties (BASELINE configs 2, 3, 4 at their full reference counts, reduced query counts) -----------------------
+def _check_scale_properties(ctx, ds, skip):
+    """Size-independent properties of one classified batch: k-mer lists, histogram mass, the postings checksum
+    sum_r count[r] == sum_k |postings(k)| (bit-exact, integer), result ordering, override / skip-exact handling."""
     ht = capi.Tree.new(ds.ref_lineages, ds.ref_off, ds.ref_codes)
     ctx.upload_tree(ht)
     eo, eids = ht.exact_batch(ds.query_off, ds.query_codes)
-    dev = ctx.classify(ds.query_off, ds.query_codes, eo, eids, taps=("counts", "hist", "kmers"))
+    dev = ctx.classify(ds.query_off, ds.query_codes, eo, eids, skip_exact=skip, taps=("counts", "hist", "kmers"))
     N = ht.num_tips
     off, ids = ht.csr()
     lens = (off[1:] - off[:-1]).astype(np.int64)
     lin = ht.lineages
+    n_override = 0
     for q in range(ds.n_queries):
         K = int(dev.n_kmers[q])
         km = dev.kmers[q, :K]
         assert np.array_equal(km, synth.kmers_of(ds.query_seq(q)))
         h = dev.hist[q, : K + 1].astype(np.int64)
         assert h.sum() == N  # every reference lands in exactly one bin
-        assert (h * np.arange(K + 1)).sum() == lens[km].sum() == dev.counts[q].astype(np.int64).sum()  # checksum of postings
+        ex = eids[eo[q]: eo[q + 1]].astype(np.int64)
+        cnt = dev.counts[q].astype(np.int64)
+        zeroed = int(K * len(ex)) if skip else 0  # an exact copy shares every k-mer; --skip-exact-matches zeroes it (raxtax.rs:65-68)
+        assert (h * np.arange(K + 1)).sum() == cnt.sum() == lens[km.astype(np.int64)].sum() - zeroed  # checksum of postings
+        assert np.array_equal(np.bincount(cnt, minlength=K + 1)[: K + 1], h)
         res = dev.for_query(q)
         assert res, "no empty result (raxtax.rs:72)"
         for fr, conf, local, glob in res:
@@ -244,11 +250,41 @@ def test_c2_scale_properties(ctx):
             assert 0.0 <= glob <= 1.0 and local >= 0.0
         confs = [tuple(c) for _, c, _, _ in res]
         assert confs == sorted(confs, reverse=True)  # lineage.rs:93
-        ne = int(eo[q + 1] - eo[q])
-        if ne == 1:  # override (raxtax.rs:73-84)
-            assert len(res) == 1 and res[0][0] == int(eids[eo[q]]) and np.all(res[0][1] == 1.0)
-        if ne >= 1:
-            assert dev.counts[q, eids[eo[q]]] == K  # an exact copy shares every k-mer
+        if len(ex) == 1 and not skip:  # override (raxtax.rs:73-84)
+            assert len(res) == 1 and res[0][0] == int(ex[0]) and np.all(res[0][1] == 1.0)
+            n_override += 1
+        if len(ex) >= 1:
+            assert np.all(cnt[ex] == (0 if skip else K))
+    return ht, eo, eids, dev, n_override
+
+
+def test_c2_scale_properties(ctx):
+    ds = synth.generate("c2", n_queries=300, measure=False)
+    _, _, _, _, n_override = _check_scale_properties(ctx, ds, skip=False)
+    assert n_override > 0
+
+
+@pytest.mark.parametrize("cfg,nq,skip", [("c3", 192, False), ("c4", 96, True)])
+def test_full_scale_configs(oracle, ctx, cfg, nq, skip):
+    """BASELINE configs 3 (1 M COI refs) and 4 (500 k 16S-like 1500 bp refs, --skip-exact-matches) at their full reference
+    counts: size-independent properties of every query, then full parity of the first 48 queries against the CPU oracle
+    built over the same references (RTX_FULL_ORACLE=0 skips the oracle part; it costs 20-60 s of host time per config)."""
+    ds = synth.generate(cfg, n_queries=nq, measure=False)
+    ht, eo, eids, dev, _ = _check_scale_properties(ctx, ds, skip=skip)
+    assert ht.num_tips == synth.CONFIGS[cfg][0]
+    if os.environ.get("RTX_FULL_ORACLE", "1") != "0":
+        n = 48
+        ot = parity.oracle_tree_from_ds(oracle, ds)
+        q_off = ds.query_off[: n + 1]
+        q_codes = ds.query_codes[: int(q_off[-1])]
+        o = ot.classify(q_off, q_codes, skip_exact=skip, threads=os.cpu_count() or 4, chunk_size=4, want_counts=True, want_probs=True, want_kmers=True)
+        assert np.array_equal(o["K"], dev.n_kmers[:n])
+        assert np.array_equal(o["counts"], dev.counts[:n]), "hit counts at full scale"
+        checker = parity.TolerantChecker(ot.flatten(), ot.num_tips)
+        ok, tol, bad = parity.compare_batch(o, dev, n, checker, o["probs"])
+        assert not bad, f"{len(bad)} queries differ from the oracle at full scale, first {bad[:3]}"
+        assert tol <= max(1, n // 10)
+        print(f"{cfg}: {ok} of {n} queries identical to the oracle at N = {ht.num_tips}, {tol} within tie/rounding tolerance")
 
 
 # ---- reference-sharded mode: several shards on ONE GPU (one context per shard), exchanges by device copies -----------------
