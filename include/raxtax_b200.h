@@ -56,8 +56,12 @@ typedef enum {
     RTX_OPT_HITCOUNT_MAX_TILES = 6, /* warp tiles (32*V words each) per CTA; fewer = more reference tile groups (L2 blocking); 0 = default */
     RTX_OPT_HITCOUNT_GROUP = 7,     /* queries per CTA (one per warp) of the query-group bit-row kernel: 0 = library default (4),
                                        1 = single-query kernel (one warp per reference tile), 2..16 = group size, 101 = group kernel with 1 */
-    RTX_OPT_HITCOUNT_CHUNKS = 8     /* row-id chunks the warps of a group cross in lockstep (block barrier per chunk) so that shared rows
+    RTX_OPT_HITCOUNT_CHUNKS = 8,    /* row-id chunks the warps of a group cross in lockstep (block barrier per chunk) so that shared rows
                                        hit the L1; 0 or 1 = no lockstep (default, fastest measured) */
+    RTX_OPT_WALK_VARIANT = 9,       /* tree walk: 0 = level-synchronous kernel + depth-first retry of overflowing queries (default),
+                                       1 = depth-first walker only */
+    RTX_OPT_WALK_LOG_CAP = 10       /* test hook: significant-node log capacity of the level-synchronous walk (0 = full); queries that
+                                       exceed it take the depth-first retry path */
 } rtx_option;
 
 /* ---- context ------------------------------------------------------------------------------------------- */

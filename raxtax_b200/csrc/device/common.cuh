@@ -133,6 +133,6 @@ struct ResultPool {
     int* status;
 };
 
-enum QueryStatus : int { kQOk = 0, kQProbSumZero = 1, kQTooManyResults = 2, kQEmptyResult = 3, kQPoolOverflow = 4 };
+enum QueryStatus : int { kQOk = 0, kQProbSumZero = 1, kQTooManyResults = 2, kQEmptyResult = 3, kQPoolOverflow = 4, kQWalkRetry = 5 };
 
 }  // namespace rtx

@@ -707,7 +707,7 @@ struct __align__(16) NodeRec {
     u32 child_first;
     u32 cc_type;       // child_count | node_type << 30
     u32 slo, shi;      // prefix segment the boundary blo / bhi belongs to (segment of the reference in front of it)
-    u32 pad0, pad1;
+    u32 lo, size;      // node_lo and node_hi - node_lo (global reference ids, not clamped to the shard)
 };
 
 // confidence of a node = sum of the normalised probabilities of its references (lineage.rs:114-117)
@@ -1275,18 +1275,23 @@ struct WalkSmem {
 template <bool SH>
 __global__ void __launch_bounds__(kWalkWarps * 32)
     lineage_walk_kernel(IndexView ix, const NodeRec* __restrict__ recs, BatchView b, ResultPool pool, ProbScratch sc, ShardView sv, int q_base,
-                        int q_count) {
+                        int q_count, int retry_only) {
     extern __shared__ __align__(16) unsigned char wsm_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int ql = blockIdx.x * kWalkWarps + warp;
     if (ql >= q_count) return;
     const int q = q_base + ql;
+    if (retry_only) {  // clean-up pass behind lineage_bfs_kernel: only the queries whose significant-node log overflowed there
+        if (pool.status[q] != kQWalkRetry) return;
+        if (lane == 0) pool.status[q] = kQOk;
+        __syncwarp();
+    }
     const u32 ML = ix.max_levels;
     WalkSmem ws(wsm_raw + (size_t)warp * WalkSmem::bytes(ML), ML);
     const double Nd = (double)ix.n_refs;
     const double* __restrict__ preb = sc.preb + (size_t)ql * sc.preb_stride;
     const double* __restrict__ segoff = sc.segoff + (size_t)ql * sc.segoff_stride;
-    int status = pool.status[q];
+    int status = retry_only ? (int)kQOk : pool.status[q];
 
     u32 n_res = 0;
     bool overflow = false;
@@ -1545,6 +1550,405 @@ __global__ void __launch_bounds__(kWalkWarps * 32)
         }
     }
     if (lane == 0) {
+        pool.res_off[q] = (u32)base;
+        pool.res_cnt[q] = n_out;
+        pool.status[q] = status;
+    }
+}
+
+// =========================================================================================================
+// K5 (level-synchronous form, the default for unsharded indexes).  The depth-first walker above follows one chain of
+// dependent loads per 32 children it looks at; taxonomies have nodes with thousands of children, so even a query with a
+// single result line evaluates ~2 500 children (80 dependent round trips), and a query with a flat probability profile
+// (40 orders above the cutoff, a 0.01 fallback chain under each) 78 000 of them -- that one walk set the kernel time
+// (3.3 M cycles against a median of 0.11 M on C2).  Here a CTA of four warps owns a query and works level by level:
+//   * the significant nodes of all levels are appended to a log in shared memory; the log range of one level is the
+//     frontier, the children of the whole frontier are flattened (prefix sum of child counts + binary search) and every
+//     warp evaluates 2 x 32 of them per step with independent loads;
+//   * frontier entries without a significant child become a result (Taxon) or the head of a fallback chain (Inner,
+//     lineage.rs:151-177); all chains advance together, one level per round, with a segmented arg-max over the
+//     flattened children (last maximal child wins, ties as in the walker above);
+//   * results are ordered by (confidence vector descending, first reference ascending): depth-first push order IS
+//     ascending first reference, because emitted nodes own disjoint reference ranges and siblings ascend.  The order of
+//     the log itself (shared-memory atomics) therefore does not matter.
+// A query whose log or frontier would overflow is marked kQWalkRetry and redone by lineage_walk_kernel<false>.
+// =========================================================================================================
+constexpr u32 kBfsEntries = 512;   // significant nodes + fallback chain nodes of one query
+constexpr u32 kBfsFrontier = 256;  // nodes of one level / simultaneously active fallback chains
+constexpr int kBfsThreads = 128;
+constexpr int kBfsWarps = kBfsThreads / 32;
+
+struct BfsSmem {
+    unsigned long long* best;  // [F] arg-max value (bits of a non-negative double)
+    double* res_local;         // [R]
+    u32* ent_cf;               // [E]
+    u32* ent_cc;               // [E] child_count | type << 30
+    u32* ent_lo;               // [E]
+    u32* ent_size;             // [E]
+    u32* fr_off;               // [F + 1]
+    u32* besti;                // [F]
+    u16* ent_parent;           // [E]
+    u16* list_a;               // [F] fallback heads / active chains (current)
+    u16* list_b;               // [F] active chains (next)
+    u16* res_ent;              // [R]
+    u16* order;                // [R]
+    u8* ent_k;                 // [E]
+    u8* ent_depth;             // [E]
+    u8* ent_any;               // [E]
+    u8* res_k;                 // [R][ML]
+    static constexpr u32 E = kBfsEntries, F = kBfsFrontier, R = RTX_MAX_RESULTS_PER_QUERY;
+    __host__ __device__ static size_t bytes(u32 ML) {
+        size_t b = (size_t)F * 8 + (size_t)R * 8 + (size_t)E * 16 + (size_t)(F + 1) * 4 + (size_t)F * 4 + (size_t)E * 2 + (size_t)F * 4 + (size_t)R * 4 +
+                   (size_t)E * 3 + (size_t)R * ML;
+        return (b + 64 + 15) & ~(size_t)15;
+    }
+    __device__ BfsSmem(unsigned char* base, u32 ML) {
+        best = reinterpret_cast<unsigned long long*>(base);
+        res_local = reinterpret_cast<double*>(best + F);
+        ent_cf = reinterpret_cast<u32*>(res_local + R);
+        ent_cc = ent_cf + E;
+        ent_lo = ent_cc + E;
+        ent_size = ent_lo + E;
+        fr_off = ent_size + E;
+        besti = fr_off + F + 1;
+        ent_parent = reinterpret_cast<u16*>(besti + F);
+        list_a = ent_parent + E;
+        list_b = list_a + F;
+        res_ent = list_b + F;
+        order = res_ent + R;
+        ent_k = reinterpret_cast<u8*>(order + R);
+        ent_depth = ent_k + E;
+        ent_any = ent_depth + E;
+        res_k = ent_any + E;
+    }
+};
+
+// warp 0: exclusive prefix of the child counts of `n` log entries (given by index list or by a contiguous range) -> fr_off[0..n]
+__device__ __forceinline__ void bfs_child_offsets(const BfsSmem& w, u32 n, u32 range_begin, const u16* __restrict__ list, int lane) {
+    u32 running = 0;
+    for (u32 bb = 0; bb < n; bb += 32) {
+        const u32 i = bb + lane;
+        const u32 e = (i < n) ? (list ? (u32)list[i] : range_begin + i) : 0u;
+        const u32 c = (i < n) ? (w.ent_cc[e] & 0x3FFFFFFFu) : 0u;
+        const u32 inc = warp_scan_incl(c, lane);
+        if (i < n) w.fr_off[i] = running + inc - c;
+        running += __shfl_sync(kFullMask, inc, 31);
+    }
+    if (lane == 0) w.fr_off[n] = running;
+}
+// largest i in [0, n) with fr_off[i] <= idx (entries without children share their successor's offset and are skipped)
+__device__ __forceinline__ u32 bfs_owner(const u32* __restrict__ fr_off, u32 n, u32 idx) {
+    u32 lo = 0, hi = n;
+    while (hi - lo > 1) {
+        const u32 mid = (lo + hi) >> 1;
+        if (fr_off[mid] <= idx) lo = mid;
+        else hi = mid;
+    }
+    return lo;
+}
+
+__global__ void __launch_bounds__(kBfsThreads)
+    lineage_bfs_kernel(IndexView ix, const NodeRec* __restrict__ recs, BatchView b, ResultPool pool, ProbScratch sc, int q_base, int q_count,
+                       u32 entry_cap) {
+    extern __shared__ __align__(16) unsigned char bsm_raw[];
+    __shared__ u32 s_log_n, s_lvl_begin, s_lvl_end, s_n_res, s_n_fb, s_n_next, s_retry;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int ql = blockIdx.x;
+    if (ql >= q_count) return;
+    const int q = q_base + ql;
+    const u32 ML = ix.max_levels;
+    BfsSmem w(bsm_raw, ML);
+    constexpr u32 F = BfsSmem::F, R = BfsSmem::R;
+    const u32 E = min(BfsSmem::E, entry_cap);  // a smaller cap only serves the tests of the retry path
+    const double Nd = (double)ix.n_refs;
+    const double* __restrict__ preb = sc.preb + (size_t)ql * sc.preb_stride;
+    const double* __restrict__ segoff = sc.segoff + (size_t)ql * sc.segoff_stride;
+    const u32 lt_mask = (1u << lane) - 1u;
+    int status = pool.status[q];
+
+    u32 n_res = 0;
+    if (status == kQOk) {  // block-uniform
+        if (tid == 0) {
+            const NodeRec root = recs[0];
+            w.ent_cf[0] = root.child_first;
+            w.ent_cc[0] = root.cc_type;
+            w.ent_lo[0] = root.lo;
+            w.ent_size[0] = root.size;
+            w.ent_parent[0] = 0xFFFFu;
+            w.ent_k[0] = 0;
+            w.ent_depth[0] = 0;
+            w.ent_any[0] = 0;
+            s_log_n = 1;
+            s_lvl_begin = 0;
+            s_lvl_end = 1;
+            s_n_res = 0;
+            s_n_fb = 0;
+            s_retry = 0;
+        }
+        __syncthreads();
+        // ---- significant nodes, level by level (lineage.rs:126-149) ---------------------------------------------
+        while (true) {
+            const u32 lvl_begin = s_lvl_begin, lvl_end = s_lvl_end;
+            if (lvl_begin >= lvl_end || s_retry) break;
+            const u32 nf = lvl_end - lvl_begin;
+            if (warp == 0) bfs_child_offsets(w, nf, lvl_begin, nullptr, lane);
+            __syncthreads();
+            const u32 total = w.fr_off[nf];
+            for (u32 base = (u32)warp * 64; base < total; base += kBfsWarps * 64) {  // two chunks of 32 children in flight per warp
+                u32 kk[2], ee[2];
+                NodeRec cr[2];
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    const u32 idx = base + u * 32 + lane;
+                    ee[u] = 0;
+                    cr[u] = NodeRec{0, 0, 0, 0, 0, 0, 0, 0};
+                    if (idx < total) {
+                        ee[u] = lvl_begin + bfs_owner(w.fr_off, nf, idx);
+                        cr[u] = recs[w.ent_cf[ee[u]] + (idx - w.fr_off[ee[u] - lvl_begin])];
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    const u32 idx = base + u * 32 + lane;
+                    kk[u] = (idx < total) ? (u32)round(node_conf(preb, segoff, cr[u]) * 100.0) : 0u;  // f64::round (lineage.rs:129)
+                }
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    const u32 mask = __ballot_sync(kFullMask, kk[u] != 0);
+                    if (mask) {
+                        u32 pos0 = 0;
+                        if (lane == 0) pos0 = atomicAdd(&s_log_n, (u32)__popc(mask));
+                        pos0 = __shfl_sync(kFullMask, pos0, 0);
+                        if (pos0 + __popc(mask) > E) {
+                            if (lane == 0) s_retry = 1;
+                        } else if (kk[u] != 0) {
+                            const u32 pos = pos0 + __popc(mask & lt_mask);
+                            w.ent_cf[pos] = cr[u].child_first;
+                            w.ent_cc[pos] = cr[u].cc_type;
+                            w.ent_lo[pos] = cr[u].lo;
+                            w.ent_size[pos] = cr[u].size;
+                            w.ent_parent[pos] = (u16)ee[u];
+                            w.ent_k[pos] = (u8)min(kk[u], 255u);
+                            w.ent_depth[pos] = (u8)(w.ent_depth[ee[u]] + 1);
+                            w.ent_any[pos] = 0;
+                            w.ent_any[ee[u]] = 1;
+                        }
+                    }
+                }
+            }
+            __syncthreads();
+            if (s_retry) break;
+            // frontier entries without a significant child: Taxon -> result line, Inner -> head of a fallback chain
+            for (u32 bb = 0; bb < nf; bb += kBfsThreads) {
+                const u32 i = bb + tid;
+                bool is_res = false, is_fb = false;
+                const u32 e = lvl_begin + i;
+                if (i < nf && !w.ent_any[e]) {
+                    const u32 type = w.ent_cc[e] >> 30;
+                    is_fb = type == 0;
+                    is_res = type == 1 && e != 0;  // the root never reports itself
+                }
+                const u32 mr = __ballot_sync(kFullMask, is_res), mf = __ballot_sync(kFullMask, is_fb);
+                u32 pr = 0, pf = 0;
+                if (lane == 0) {
+                    if (mr) pr = atomicAdd(&s_n_res, (u32)__popc(mr));
+                    if (mf) pf = atomicAdd(&s_n_fb, (u32)__popc(mf));
+                }
+                pr = __shfl_sync(kFullMask, pr, 0);
+                pf = __shfl_sync(kFullMask, pf, 0);
+                if (pr + __popc(mr) > R || pf + __popc(mf) > F) {
+                    if (lane == 0) s_retry = 1;
+                } else {
+                    if (is_res) w.res_ent[pr + __popc(mr & lt_mask)] = (u16)e;
+                    if (is_fb) w.list_a[pf + __popc(mf & lt_mask)] = (u16)e;
+                }
+            }
+            __syncthreads();
+            if (tid == 0) {
+                s_lvl_begin = lvl_end;
+                s_lvl_end = s_log_n;
+                if (s_log_n - lvl_end > F) s_retry = 1;
+            }
+            __syncthreads();
+        }
+        __syncthreads();
+        // ---- fallback chains (lineage.rs:151-177): all heads advance together, one level per round -------------------
+        u16* cur = w.list_a;
+        u16* nxt = w.list_b;
+        u32 n_ch = s_retry ? 0u : s_n_fb;
+        while (n_ch > 0) {  // block-uniform
+            if (warp == 0) bfs_child_offsets(w, n_ch, 0, cur, lane);
+            for (u32 i = tid; i < n_ch; i += kBfsThreads) {
+                w.best[i] = 0ull;
+                w.besti[i] = 0u;
+            }
+            if (tid == 0) s_n_next = 0;
+            __syncthreads();
+            const u32 total = w.fr_off[n_ch];
+            for (u32 idx = tid; idx < total; idx += kBfsThreads) {  // pass A: the largest child confidence of every chain head
+                const u32 c = bfs_owner(w.fr_off, n_ch, idx);
+                const NodeRec cr = recs[w.ent_cf[cur[c]] + (idx - w.fr_off[c])];
+                const double v = fmax(node_conf(preb, segoff, cr), 0.0);
+                atomicMax(&w.best[c], (unsigned long long)__double_as_longlong(v));  // non-negative doubles order like their bits
+            }
+            __syncthreads();
+            for (u32 idx = tid; idx < total; idx += kBfsThreads) {  // pass B: the LAST child within 1e-12 relative of the maximum
+                const u32 c = bfs_owner(w.fr_off, n_ch, idx);
+                const u32 ci = idx - w.fr_off[c];
+                const NodeRec cr = recs[w.ent_cf[cur[c]] + ci];
+                const double v = fmax(node_conf(preb, segoff, cr), 0.0);
+                const double bestv = __longlong_as_double((long long)w.best[c]);
+                if (v >= bestv - fabs(bestv) * 1e-12) atomicMax(&w.besti[c], ci);
+            }
+            __syncthreads();
+            for (u32 bb = 0; bb < n_ch; bb += kBfsThreads) {  // one new log entry (0.01) per chain; Inner nodes stay active
+                const u32 i = bb + tid;
+                const bool valid = i < n_ch;
+                NodeRec br = NodeRec{0, 0, 0, 0, 0, 0, 0, 0};
+                u32 head = 0;
+                if (valid) {
+                    head = cur[i];
+                    br = recs[w.ent_cf[head] + w.besti[i]];
+                }
+                const bool go_on = valid && (br.cc_type >> 30) == 0;
+                const bool done = valid && !go_on;
+                const u32 mv = __ballot_sync(kFullMask, valid), mg = __ballot_sync(kFullMask, go_on), md = __ballot_sync(kFullMask, done);
+                u32 pv = 0, pg = 0, pd = 0;
+                if (lane == 0) {
+                    if (mv) pv = atomicAdd(&s_log_n, (u32)__popc(mv));
+                    if (mg) pg = atomicAdd(&s_n_next, (u32)__popc(mg));
+                    if (md) pd = atomicAdd(&s_n_res, (u32)__popc(md));
+                }
+                pv = __shfl_sync(kFullMask, pv, 0);
+                pg = __shfl_sync(kFullMask, pg, 0);
+                pd = __shfl_sync(kFullMask, pd, 0);
+                if (pv + __popc(mv) > E || pd + __popc(md) > R) {
+                    if (lane == 0) s_retry = 1;
+                } else if (valid) {
+                    const u32 pos = pv + __popc(mv & lt_mask);
+                    w.ent_cf[pos] = br.child_first;
+                    w.ent_cc[pos] = br.cc_type;
+                    w.ent_lo[pos] = br.lo;
+                    w.ent_size[pos] = br.size;
+                    w.ent_parent[pos] = (u16)head;
+                    w.ent_k[pos] = 1;  // 1.0 / rounding_factor
+                    w.ent_depth[pos] = (u8)(w.ent_depth[head] + 1);
+                    w.ent_any[pos] = 0;
+                    if (go_on) nxt[pg + __popc(mg & lt_mask)] = (u16)pos;
+                    else w.res_ent[pd + __popc(md & lt_mask)] = (u16)pos;
+                }
+            }
+            __syncthreads();
+            u16* t = cur;
+            cur = nxt;
+            nxt = t;
+            n_ch = s_retry ? 0u : s_n_next;
+            __syncthreads();
+        }
+        const bool retry = s_retry != 0;
+        n_res = retry ? 0u : s_n_res;
+        // ---- confidence vectors and local signals of the result lines (lineage.rs:95-102, utils.rs:91-105) -------------
+        bool too_deep = false;
+        for (u32 r = warp; r < n_res; r += kBfsWarps) {
+            const u32 e = w.res_ent[r];
+            const int d = w.ent_depth[e];
+            if (d > (int)ML || d > 32) {
+                too_deep = true;
+                continue;
+            }
+            double cv = 0.0, ev = 0.0;
+            if (lane < d) {
+                u32 c = e;
+                for (int s2 = d - 1; s2 > lane; --s2) c = w.ent_parent[c];  // the path node of level `lane`
+                cv = (double)w.ent_k[c] / 100.0;
+                ev = (double)w.ent_size[c] / Nd;
+                w.res_k[(size_t)r * ML + lane] = w.ent_k[c];
+            }
+            const u32 lt1 = __ballot_sync(kFullMask, lane < d && 1.0 > ev);
+            const int start = lt1 ? (__ffs(lt1) - 1) : (d - 1);
+            double a_sum = 0.0, b_sum = 0.0;  // sequential sums, level order, like the reference
+            for (int i2 = start; i2 < d; ++i2) {
+                a_sum += __shfl_sync(kFullMask, cv, i2);
+                b_sum += __shfl_sync(kFullMask, ev, i2);
+            }
+            double s2 = 0.0;
+            for (int i2 = start; i2 < d; ++i2) {
+                const double df = __shfl_sync(kFullMask, cv, i2) / a_sum - __shfl_sync(kFullMask, ev, i2) / b_sum;
+                s2 += df * df;
+            }
+            if (lane == 0) w.res_local[r] = sqrt(s2);
+        }
+        if (__syncthreads_or(too_deep ? 1 : 0) || retry) status = kQWalkRetry;
+        else if (n_res == 0) status = kQEmptyResult;  // assert!(!eval_res.is_empty()) raxtax.rs:72
+    }
+    if (status == kQWalkRetry) {  // lineage_walk_kernel<false> redoes this query
+        if (tid == 0) pool.status[q] = status;
+        return;
+    }
+    // ---- order (lineage.rs:93): stable sort, descending lexicographic on the confidence vectors; the tie-break of the
+    // reference's stable sort is the depth-first push order == ascending first reference
+    if (status == kQOk) {
+        for (u32 i = tid; i < n_res; i += kBfsThreads) {
+            const u8* ci = w.res_k + (size_t)i * ML;
+            const u32 li = w.ent_depth[w.res_ent[i]], fi = w.ent_lo[w.res_ent[i]];
+            u32 rank = 0;
+            for (u32 j = 0; j < n_res; ++j) {
+                if (j == i) continue;
+                const u8* cj = w.res_k + (size_t)j * ML;
+                const u32 lj = w.ent_depth[w.res_ent[j]];
+                int cmp = 0;  // +1: vector j > vector i
+                for (u32 l = 0; l < min(li, lj); ++l) {
+                    if (cj[l] != ci[l]) {
+                        cmp = cj[l] > ci[l] ? 1 : -1;
+                        break;
+                    }
+                }
+                if (cmp == 0) cmp = (lj > li) ? 1 : (lj < li) ? -1 : 0;
+                if (cmp > 0 || (cmp == 0 && w.ent_lo[w.res_ent[j]] < fi)) ++rank;
+            }
+            w.order[rank] = (u16)i;
+        }
+    }
+    __syncthreads();
+    // ---- override (raxtax.rs:73-84) and emission into the result pool ---------------------------------------
+    u32 n_out = (status == kQOk) ? n_res : 0;
+    bool ovr = false;
+    u32 ovr_idx = 0;
+    if (status == kQOk && !(b.flags & RTX_RAW_CONFIDENCE) && !(b.flags & RTX_SKIP_EXACT_MATCHES) && b.exact_off) {
+        if (b.exact_off[q + 1] - b.exact_off[q] == 1) {
+            ovr = true;
+            ovr_idx = b.exact_ids[b.exact_off[q]];
+            n_out = 1;
+        }
+    }
+    __shared__ unsigned long long s_base;
+    if (tid == 0) s_base = atomicAdd(pool.used, (unsigned long long)n_out);
+    __syncthreads();
+    const unsigned long long base = s_base;
+    if (base + n_out > pool.cap) {
+        if (status == kQOk) status = kQPoolOverflow;
+    } else if (ovr) {
+        const u32 nl = ix.ref_levels[ovr_idx];
+        if (tid == 0) {
+            pool.first_ref[base] = ovr_idx;
+            pool.n_levels[base] = (u8)nl;
+            pool.local[base] = w.res_local[w.order[0]];
+        }
+        for (u32 l = tid; l < ML; l += kBfsThreads) pool.conf[base * ML + l] = (l < nl) ? 1.0 : 0.0;
+    } else {
+        for (u32 x = tid; x < n_out * ML; x += kBfsThreads) {
+            const u32 i = x / ML, l = x - i * ML;
+            const u32 src = w.order[i];
+            pool.conf[(base + i) * ML + l] = (l < w.ent_depth[w.res_ent[src]]) ? (double)w.res_k[(size_t)src * ML + l] / 100.0 : 0.0;
+        }
+        for (u32 i = tid; i < n_out; i += kBfsThreads) {
+            const u32 src = w.order[i];
+            pool.first_ref[base + i] = w.ent_lo[w.res_ent[src]];
+            pool.n_levels[base + i] = w.ent_depth[w.res_ent[src]];
+            pool.local[base + i] = w.res_local[src];
+        }
+    }
+    if (tid == 0) {
         pool.res_off[q] = (u32)base;
         pool.res_cnt[q] = n_out;
         pool.status[q] = status;

@@ -28,6 +28,8 @@ struct rtx_ctx {
     bool profile = false;
     int hit_tune = 0;
     int hit_max_tiles = 0;
+    int walk_variant = 0;  // RTX_OPT_WALK_VARIANT: 0 level-synchronous (+ depth-first retry), 1 depth-first only
+    int walk_log_cap = 0;  // RTX_OPT_WALK_LOG_CAP
     int hit_group = 0;   // RTX_OPT_HITCOUNT_GROUP
     int hit_chunks = 0;  // RTX_OPT_HITCOUNT_CHUNKS
     // index
@@ -52,7 +54,7 @@ struct rtx_ctx {
     // prob scratch
     ProbScratch sc{};
     int prob_slots = 0;
-    size_t prob_smem = 0, walk_smem = 0, prefix_smem = 0;
+    size_t prob_smem = 0, walk_smem = 0, prefix_smem = 0, bfs_smem = 0;
     DevBuf d_cbuf, d_preb, d_ptab, d_segoff;
     // reference-sharded mode
     ShardView sv{};
@@ -231,6 +233,14 @@ RTX_API int rtx_ctx_set_option(rtx_ctx* ctx, int option, int64_t value) {
             REQUIRE(value >= 0 && value <= 4096, "bad max tiles per CTA");
             ctx->hit_max_tiles = (int)value;
             return RTX_OK;
+        case RTX_OPT_WALK_VARIANT:
+            REQUIRE(value == 0 || value == 1, "unknown walk variant");
+            ctx->walk_variant = (int)value;
+            return RTX_OK;
+        case RTX_OPT_WALK_LOG_CAP:
+            REQUIRE(value >= 0 && value <= (int64_t)kBfsEntries, "bad walk log cap");
+            ctx->walk_log_cap = (int)value;
+            return RTX_OK;
         case RTX_OPT_HITCOUNT_GROUP:
             REQUIRE((value >= 0 && value <= kHitGroupMaxThreads / 32) || value == 101, "bad query group size");  // 101: group kernel with one query per CTA (experiments)
             ctx->hit_group = (int)value;
@@ -393,7 +403,7 @@ RTX_API int rtx_index_upload(rtx_ctx* ctx, const rtx_index_desc* d) {
         auto seg_of = [&](u64 pos) -> u32 { return pos > s0 ? (u32)((pos - s0 - 1) / kPrefixSeg) : 0u; };  // segment of the reference in front of pos
         for (u32 i = 0; i < nn; ++i)
             recs[i] = NodeRec{blo[i], bhi[i], d->child_first[i], d->child_count[i] | ((u32)d->node_type[i] << 30),
-                              seg_of(clampu(d->node_lo[i])), seg_of(clampu(d->node_hi[i])), 0u, 0u};
+                              seg_of(clampu(d->node_lo[i])), seg_of(clampu(d->node_hi[i])), d->node_lo[i], d->node_hi[i] - d->node_lo[i]};
         CU(upload_vec(ctx->d_recs, recs.data(), nn, &bytes));
     }
     CU(upload_vec(ctx->d_node_blo, blo.data(), nn, &bytes));
@@ -655,6 +665,8 @@ RTX_API int rtx_batch_upload(rtx_ctx* ctx, const rtx_batch* batch) {
     ctx->walk_smem = (size_t)kWalkWarps * WalkSmem::bytes(ctx->ix.max_levels);
     CU(cudaFuncSetAttribute(lineage_walk_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->walk_smem));
     CU(cudaFuncSetAttribute(lineage_walk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->walk_smem));
+    ctx->bfs_smem = BfsSmem::bytes(ctx->ix.max_levels);
+    CU(cudaFuncSetAttribute(lineage_bfs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->bfs_smem));
     ctx->shard_phase = 0;
     const int slots = (int)std::min<u64>((u64)ctx->n_sms * occ, sb);
     ctx->prob_slots = slots;
@@ -840,8 +852,13 @@ static int run_all(rtx_ctx* ctx) {
         }
         {
             LaunchTimer lt(ctx, RTX_K_WALK);
+            if (ctx->walk_variant == 0) {  // level-synchronous walk, then the depth-first walker for the queries it handed back
+                lineage_bfs_kernel<<<qb, kBfsThreads, ctx->bfs_smem, ctx->stream>>>(
+                    ctx->ix, ctx->d_recs.as<NodeRec>(), bv, ctx->pool, ctx->sc, (int)q0, qb, ctx->walk_log_cap ? (u32)ctx->walk_log_cap : kBfsEntries);
+                CU(cudaGetLastError());
+            }
             lineage_walk_kernel<false><<<(qb + kWalkWarps - 1) / kWalkWarps, kWalkWarps * 32, ctx->walk_smem, ctx->stream>>>(
-                ctx->ix, ctx->d_recs.as<NodeRec>(), bv, ctx->pool, ctx->sc, ShardView{}, (int)q0, qb);
+                ctx->ix, ctx->d_recs.as<NodeRec>(), bv, ctx->pool, ctx->sc, ShardView{}, (int)q0, qb, ctx->walk_variant == 0 ? 1 : 0);
             CU(cudaGetLastError());
         }
         if (ctx->tap_counts_host) {
@@ -1118,7 +1135,7 @@ RTX_API int rtx_shard_phase3(rtx_ctx* ctx) {
     {
         LaunchTimer lt(ctx, RTX_K_WALK);
         lineage_walk_kernel<true><<<(nq + kWalkWarps - 1) / kWalkWarps, kWalkWarps * 32, ctx->walk_smem, ctx->stream>>>(
-            ctx->ix, ctx->d_recs.as<NodeRec>(), bv, ctx->pool, ctx->sc, ctx->sv, 0, (int)nq);
+            ctx->ix, ctx->d_recs.as<NodeRec>(), bv, ctx->pool, ctx->sc, ctx->sv, 0, (int)nq, 0);
         CU(cudaGetLastError());
     }
     ctx->prof.queries += nq;

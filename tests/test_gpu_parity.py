@@ -150,6 +150,34 @@ def test_csr_variant_matches_bitrows(oracle, ctx):
     _assert_result_parity(o, dev, ot, ds.n_queries)
 
 
+def _same_outputs(a, b):
+    return (np.array_equal(a.result_begin, b.result_begin) and np.array_equal(a.first_ref, b.first_ref) and np.array_equal(a.n_levels, b.n_levels)
+            and np.array_equal(a.confidence, b.confidence) and np.array_equal(a.local_signal, b.local_signal)
+            and np.array_equal(a.global_signal, b.global_signal))
+
+
+@pytest.mark.parametrize("skip", [False, True])
+def test_walk_variants_agree(ctx, skip):
+    """Level-synchronous walk (default), depth-first walker, and the retry path (log cap forced down so that most queries are
+    handed back to the depth-first walker) must produce bit-identical result lists."""
+    ds = synth.generate("small", n_queries=512, measure=False)
+    ht = capi.Tree.new(ds.ref_lineages, ds.ref_off, ds.ref_codes)
+    ctx.upload_tree(ht)
+    eo, eids = ht.exact_batch(ds.query_off, ds.query_codes)
+    outs = []
+    try:
+        for variant, cap in ((0, 0), (1, 0), (0, 8), (0, 40)):
+            ctx.set_option(capi.RTX_OPT_WALK_VARIANT, variant)
+            ctx.set_option(capi.RTX_OPT_WALK_LOG_CAP, cap)
+            outs.append(ctx.classify(ds.query_off, ds.query_codes, eo, eids, skip_exact=skip))
+    finally:
+        ctx.set_option(capi.RTX_OPT_WALK_VARIANT, 0)
+        ctx.set_option(capi.RTX_OPT_WALK_LOG_CAP, 0)
+    assert len(outs[0].first_ref) >= ds.n_queries
+    for o in outs[1:]:
+        assert _same_outputs(outs[0], o)
+
+
 def test_16s_like_long_queries(oracle, ctx):
     ds = synth.generate("x16s", n_refs=1500, n_queries=48, length=1500, kind="16s", seed=77, measure=False)
     o, dev, ot, _ = _run_both(oracle, ctx, ds, skip=True)
