@@ -685,6 +685,7 @@ struct ProbSmem {
     u16* dm;        // [H]   distinct counts ascending
     u16* wlo;       // [H]   per distinct count: window [wlo, whi) of entries stored in cbuf
     u16* whi;       // [H]
+    u16* mode;      // [H]   mode of pmf_m per distinct count (the 64-bit division is done once per row)
     __host__ __device__ ProbSmem(unsigned char* base, u32 H, u32 T1, int nprod, int lf_smem) {
         lf = reinterpret_cast<double*>(base);
         Pd = lf + (lf_smem ? H + T1 : 0);
@@ -695,9 +696,10 @@ struct ProbSmem {
         dm = reinterpret_cast<u16*>(dh + H);
         wlo = dm + H;
         whi = wlo + H;
+        mode = whi + H;
     }
     static size_t bytes(u32 H, u32 T1, int nprod, int lf_smem) {
-        return (size_t)H * (8 + 4 * 2 + 2 * 3) + (size_t)T1 * 8 * (1 + nprod) + (lf_smem ? (size_t)(H + T1) * 8 : 0) + 64;
+        return (size_t)H * (8 + 4 * 2 + 2 * 4) + (size_t)T1 * 8 * (1 + nprod) + (lf_smem ? (size_t)(H + T1) * 8 : 0) + 64;
     }
 };
 
@@ -752,7 +754,7 @@ __device__ __forceinline__ u32 warp_first_true(u32 a, u32 bnd, int lane, Pred pr
     return bnd;
 }
 
-__global__ void __launch_bounds__(kProbThreads)
+__global__ void __launch_bounds__(kProbThreads, 4)
     prob_table_kernel(IndexView ix, BatchView b, ResultPool pool, ProbScratch sc, int q_base, int q_count,
                       unsigned long long* __restrict__ hits_total) {
     extern __shared__ __align__(16) unsigned char psm_raw[];
@@ -806,6 +808,7 @@ __global__ void __launch_bounds__(kProbThreads)
                 sm.Pd[dpos] = 0.0;
                 sm.wlo[dpos] = 0;
                 sm.whi[dpos] = 0;
+                sm.mode[dpos] = (u16)pmf_mode(K, K / 2, m);
                 ++dpos;
             }
         }
@@ -846,7 +849,7 @@ __global__ void __launch_bounds__(kProbThreads)
                         if (m == 0) continue;  // cmf == 1
                         const double cm = lf[m - 1] + lf[K - m - 1] + T;
                         double u;
-                        if (i < pmf_mode(K, t, m)) {  // cmf(i) <= pmf(i) / (1 - pmf(i-1)/pmf(i)): ratios shrink downwards
+                        if (i < (u32)sm.mode[d]) {  // cmf(i) <= pmf(i) / (1 - pmf(i-1)/pmf(i)): ratios shrink downwards
                             u = ln_pmf(lf, K, t, m, i, cm);
                             if (i > 0) {
                                 const double rd = ((double)i * (double)(K - m + t - i)) / ((double)(m + i - 1) * (double)(t - i + 1));
@@ -884,7 +887,7 @@ __global__ void __launch_bounds__(kProbThreads)
                 if (m == 0) continue;  // pmf = [1,0,..]: cmf == 1, ln cmf == 0, P(0) = E(0)
                 const double hd = (double)sm.dh[d];
                 const double cm = lf[m - 1] + lf[K - m - 1] + T;
-                const u32 mode = pmf_mode(K, t, m);
+                const u32 mode = sm.mode[d];
                 const double thr = -(double)(kTailNats + __logf((float)sm.dh[d]));
                 // hi: first i above the mode whose pmf (and, by log-concavity, whole remaining tail) is negligible
                 const u32 hi = warp_first_true(mode + 1, t + 1, lane, [&](u32 i) { return ln_pmf(lf, K, t, m, i, cm) < thr; });
@@ -1575,7 +1578,7 @@ __global__ void __launch_bounds__(kWalkWarps * 32)
 // =========================================================================================================
 constexpr u32 kBfsEntries = 512;   // significant nodes + fallback chain nodes of one query
 constexpr u32 kBfsFrontier = 256;  // nodes of one level / simultaneously active fallback chains
-constexpr int kBfsThreads = 128;
+constexpr int kBfsThreads = 256;
 constexpr int kBfsWarps = kBfsThreads / 32;
 
 struct BfsSmem {
