@@ -128,6 +128,8 @@ def main():
     ap.add_argument("--workload", default="c2")
     ap.add_argument("--cpu-sample", type=int, default=0, help="queries in the bounded CPU sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--sub-batch", type=int, default=0, help="RTX_OPT_SUB_BATCH for the timed legs (0 = library default)")
+    ap.add_argument("--pipeline", type=int, default=-1, help="RTX_OPT_PIPELINE for the timed legs (-1 = library default)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
 
@@ -203,6 +205,10 @@ def main():
 
     stream = torch.cuda.ExternalStream(ctx.stream, device=torch.device("cuda", local_rank))
 
+    if args.sub_batch:
+        ctx.set_option(capi.RTX_OPT_SUB_BATCH, args.sub_batch)
+    if args.pipeline >= 0:
+        ctx.set_option(capi.RTX_OPT_PIPELINE, args.pipeline)
     # ---- device-resident leg ------------------------------------------------------------------------------
     ctx.batch_upload(off_p, codes_p, eo_p, eids_p)
     for _ in range(args.warmup):
@@ -225,10 +231,30 @@ def main():
     dev_ms = max_over_ranks(ev0.elapsed_time(ev1))
     clocks = sampler.stop()
     res = ctx.batch_download()
-    prof = ctx.profile()
-    ctx.set_option(capi.RTX_OPT_PROFILE, 0)
+    prof_main = ctx.profile()
     n_results = len(res.first_ref)
     value = q_per_gpu * world * args.steps / (dev_ms / 1e3)
+
+    # ---- per-kernel leg: the same batch with the sub-batch pipeline off, so that every kernel runs alone on the GPU and its
+    # CUDA-event duration is its own (in the pipelined run above hit counting shares the SMs with the other stream's kernels)
+    ctx.set_option(capi.RTX_OPT_PIPELINE, 0)
+    ctx.set_option(capi.RTX_OPT_SUB_BATCH, 0)
+    ctx.batch_upload(off_p, codes_p, eo_p, eids_p)
+    for _ in range(2):
+        ctx.batch_run()
+    ctx.profile_reset()
+    ser0, ser1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ser0.record(stream)
+    for _ in range(args.steps):
+        ctx.batch_run()
+    ser1.record(stream)
+    ctx.synchronize()
+    serial_ms = ser0.elapsed_time(ser1) / args.steps
+    ctx.batch_download()
+    prof = ctx.profile()
+    ctx.set_option(capi.RTX_OPT_PROFILE, 0)
+    ctx.set_option(capi.RTX_OPT_PIPELINE, args.pipeline if args.pipeline >= 0 else 0)
+    ctx.set_option(capi.RTX_OPT_SUB_BATCH, args.sub_batch)
 
     # ---- end-to-end leg (host buffers, H2D + kernels + D2H per step) ---------------------------------------------
     for _ in range(2):
@@ -262,18 +288,20 @@ def main():
     kernel_ms = {k: prof[k]["total_ms"] / args.steps for k in ("kmers", "hitcount", "fixup", "prob", "prefix", "walk")}
     roofline = {"bound": "hbm", "kernel": "hitcount_bitrows_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": bytes_per_launch,
-                "launch_ms": hc_ms, "csr_equivalent": {"bytes_per_launch": csr_bytes_per_launch,
+                "launch_ms": hc_ms, "timed": "kernels serialized (RTX_OPT_PIPELINE=0), CUDA events around each launch on the launching stream",
+                "serial_ms_per_step": serial_ms, "csr_equivalent": {"bytes_per_launch": csr_bytes_per_launch,
                                                        "achieved": csr_bytes_per_launch / (hc_ms * 1e-3) / 1e9 if hc_ms > 0 else 0.0,
                                                        "note": "4*hits+2*N per query: what the reference's CSR walk would move (SURVEY 8d primary figure)"},
                 "kernel_ms_per_step": kernel_ms}
 
-    launches = sum(prof[k]["launches"] for k in capi.KERNEL_NAMES)
+    launches = sum(prof_main[k]["launches"] for k in capi.KERNEL_NAMES)
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32 bit-planes/u16 counts/f64",
             "data": "synthetic",
             "config": {"workload": f"{args.workload}: {ds.n_refs} COI-like refs x 650 bp (6-rank lineages) x {q_per_gpu} queries per GPU, index replicated, queries partitioned",
                        "l2": "no flush needed: bit rows %.0f MB + count vectors %.0f MB per step >> 126 MB L2" % (
                            ctx.index_bytes / 1e6, q_per_gpu * ctx.shard_refs * 2 / 1e6),
+                       "sub_batch": ctx.sub_batch, "pipeline": bool(args.pipeline > 0),
                        "tree_build_s": round(t_tree, 2), "index_upload_s": round(t_upload, 2), "results_per_step": n_results},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": prof_e2e["h2d_bytes"] // args.steps,

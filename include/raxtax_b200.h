@@ -60,6 +60,9 @@ typedef enum {
                                        hit the L1; 0 or 1 = no lockstep (default, fastest measured) */
     RTX_OPT_WALK_VARIANT = 9,       /* tree walk: 0 = level-synchronous kernel + depth-first retry of overflowing queries (default),
                                        1 = depth-first walker only */
+    RTX_OPT_PIPELINE = 11,          /* 1: batches of >= 4096 queries are cut into >= 4 sub-batches and hit counting of sub-batch i+1 overlaps
+                                       probabilities / prefix sums / tree walk of sub-batch i on a second, higher-priority stream;
+                                       0 (default) = serial: on B200 the overlap only recovers what the shorter launches lose */
     RTX_OPT_WALK_LOG_CAP = 10       /* test hook: significant-node log capacity of the level-synchronous walk (0 = full); queries that
                                        exceed it take the depth-first retry path */
 } rtx_option;
@@ -110,6 +113,7 @@ int rtx_index_upload(rtx_ctx* ctx, const rtx_index_desc* desc);
 /* sizes a caller needs to allocate tap buffers */
 uint64_t rtx_index_n_refs(const rtx_ctx* ctx);       /* global N */
 uint64_t rtx_index_shard_refs(const rtx_ctx* ctx);   /* references held by this context */
+uint32_t rtx_batch_sub_batch(const rtx_ctx* ctx);     /* queries per device sub-batch of the uploaded batch (0 = no batch) */
 uint32_t rtx_index_max_levels(const rtx_ctx* ctx);   /* stride of rtx_results.confidence */
 uint64_t rtx_index_device_bytes(const rtx_ctx* ctx); /* HBM held by the index */
 

@@ -22,13 +22,13 @@ RTX_OK, RTX_ERR_INVALID, RTX_ERR_CUDA, RTX_ERR_NO_DEVICE, RTX_ERR_NO_INDEX, RTX_
 RTX_SKIP_EXACT_MATCHES, RTX_RAW_CONFIDENCE = 1, 2
 RTX_HITCOUNT_BITROWS, RTX_HITCOUNT_CSR = 0, 1
 RTX_OPT_HITCOUNT_VARIANT, RTX_OPT_SUB_BATCH, RTX_OPT_KEEP_CSR, RTX_OPT_PROFILE, RTX_OPT_HITCOUNT_TUNE, RTX_OPT_HITCOUNT_MAX_TILES = 1, 2, 3, 4, 5, 6
-RTX_OPT_HITCOUNT_GROUP, RTX_OPT_HITCOUNT_CHUNKS, RTX_OPT_WALK_VARIANT, RTX_OPT_WALK_LOG_CAP = 7, 8, 9, 10
+RTX_OPT_HITCOUNT_GROUP, RTX_OPT_HITCOUNT_CHUNKS, RTX_OPT_WALK_VARIANT, RTX_OPT_WALK_LOG_CAP, RTX_OPT_PIPELINE = 7, 8, 9, 10, 11
 KERNEL_NAMES = ["kmers", "hitcount", "fixup", "prob", "index", "walk", "prefix"]
 
 # every symbol include/raxtax_b200.h declares
 DEVICE_SYMBOLS = [
     "rtx_abi_version", "rtx_ctx_create", "rtx_ctx_destroy", "rtx_last_error", "rtx_ctx_set_option", "rtx_ctx_stream",
-    "rtx_ctx_synchronize", "rtx_index_upload", "rtx_index_n_refs", "rtx_index_shard_refs", "rtx_index_max_levels",
+    "rtx_ctx_synchronize", "rtx_index_upload", "rtx_index_n_refs", "rtx_index_shard_refs", "rtx_index_max_levels", "rtx_batch_sub_batch",
     "rtx_index_device_bytes", "rtx_classify_batch", "rtx_batch_upload", "rtx_batch_run", "rtx_batch_download",
     "rtx_shard_phase1", "rtx_shard_hist_buffer", "rtx_shard_phase2", "rtx_shard_records_buffers", "rtx_shard_phase3",
     "rtx_profile_reset", "rtx_profile_get",
@@ -107,6 +107,8 @@ def device_lib():
         getattr(L, f).argtypes = [C.c_void_p]
     L.rtx_index_max_levels.restype = C.c_uint32
     L.rtx_index_max_levels.argtypes = [C.c_void_p]
+    L.rtx_batch_sub_batch.restype = C.c_uint32
+    L.rtx_batch_sub_batch.argtypes = [C.c_void_p]
     L.rtx_classify_batch.argtypes = [C.c_void_p, C.POINTER(Batch), C.POINTER(ResultsStruct)]
     L.rtx_batch_upload.argtypes = [C.c_void_p, C.POINTER(Batch)]
     L.rtx_batch_run.argtypes = [C.c_void_p]
@@ -246,6 +248,10 @@ class Context:
     @property
     def shard_refs(self):
         return device_lib().rtx_index_shard_refs(self._h)
+
+    @property
+    def sub_batch(self):
+        return int(device_lib().rtx_batch_sub_batch(self._h))
 
     @property
     def max_levels(self):

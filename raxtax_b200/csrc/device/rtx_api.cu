@@ -20,6 +20,15 @@ struct rtx_ctx {
     int device = 0;
     int n_sms = 148;
     cudaStream_t stream = nullptr;
+    // sub-batch pipeline: hit counting of sub-batch i+1 (stream) overlaps probabilities / prefix sums / tree walk of sub-batch i
+    // (stream2); the per-sub-batch buffers exist twice ("slots"), events order the two streams
+    cudaStream_t stream2 = nullptr;
+    cudaEvent_t ev_hit[2] = {nullptr, nullptr}, ev_post[2] = {nullptr, nullptr};
+    bool pipeline_opt = false;  // RTX_OPT_PIPELINE (off: measured 9.95-10.2 ms pipelined against 9.89 ms serial on C2, profiles/r01x_pipeline.txt)
+    bool two_slots = false;    // this batch runs pipelined
+    cudaStream_t cur_stream = nullptr;  // what the launch helpers use: stream / slot of the sub-batch being issued
+    u16* cur_counts = nullptr;
+    ProbScratch* cur_sc = nullptr;
     std::string err;
     // options
     int variant = RTX_HITCOUNT_BITROWS;
@@ -46,16 +55,16 @@ struct rtx_ctx {
     u32 max_len = 0;
     u64 total_codes = 0, total_exact = 0;
     DevBuf d_seq_off, d_codes, d_exact_off, d_exact_ids, d_K, d_kmers, d_rows, d_nrows, d_hist;
-    DevBuf d_counts;
+    DevBuf d_counts, d_counts1;
     u32 sub_batch = 0;
     // results
     ResultPool pool{};
     DevBuf d_pool_first, d_pool_nlev, d_pool_conf, d_pool_local, d_pool_used, d_res_off, d_res_cnt, d_global, d_status, d_hits;
     // prob scratch
-    ProbScratch sc{};
+    ProbScratch sc{}, sc1{};
     int prob_slots = 0;
     size_t prob_smem = 0, walk_smem = 0, prefix_smem = 0, bfs_smem = 0;
-    DevBuf d_cbuf, d_preb, d_ptab, d_segoff;
+    DevBuf d_cbuf, d_preb, d_ptab, d_segoff, d_preb1, d_ptab1, d_segoff1;
     // reference-sharded mode
     ShardView sv{};
     int shard_phase = 0;
@@ -113,12 +122,12 @@ struct LaunchTimer {
             cudaEventCreate(&ep.a);
             cudaEventCreate(&ep.b);
             ep.kernel = k;
-            cudaEventRecord(ep.a, c->stream);
+            cudaEventRecord(ep.a, c->cur_stream ? c->cur_stream : c->stream);
         }
     }
     ~LaunchTimer() {
         if (on) {
-            cudaEventRecord(ep.b, c->stream);
+            cudaEventRecord(ep.b, c->cur_stream ? c->cur_stream : c->stream);
             c->events.push_back(ep);
         }
     }
@@ -166,10 +175,21 @@ RTX_API int rtx_ctx_create(int device_ordinal, rtx_ctx** out) {
     c->device = device_ordinal;
     c->n_sms = prop.multiProcessorCount;
     e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
-    if (e != cudaSuccess) {
-        delete c;
-        return set_err(nullptr, RTX_ERR_CUDA, std::string("cudaStreamCreate: ") + cudaGetErrorString(e));
+    if (e == cudaSuccess) {  // the second stream carries the short kernels behind hit counting: its CTAs go first whenever an SM frees up
+        int prio_lo = 0, prio_hi = 0;
+        cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+        e = cudaStreamCreateWithPriority(&c->stream2, cudaStreamNonBlocking, prio_hi);
     }
+    for (int i = 0; i < 2 && e == cudaSuccess; ++i) {
+        e = cudaEventCreateWithFlags(&c->ev_hit[i], cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_post[i], cudaEventDisableTiming);
+    }
+    if (e != cudaSuccess) {
+        std::string m = std::string("stream / event creation: ") + cudaGetErrorString(e);
+        rtx_ctx_destroy(c);
+        return set_err(nullptr, RTX_ERR_CUDA, m);
+    }
+    c->cur_stream = c->stream;
     // ln n! table: exact factorials up to 170, lgamma beyond (the reference's statrs::ln_factorial does the same)
     const u32 len = 98304 + 8;  // K + t <= 65535 + 32767
     std::vector<double> lf(len);
@@ -199,15 +219,21 @@ RTX_API void rtx_ctx_destroy(rtx_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
+    if (c->stream2) cudaStreamSynchronize(c->stream2);
     drain_events(c);
     DevBuf* bufs[] = {&c->d_bitrows, &c->d_rowmap, &c->d_present, &c->d_csr_off, &c->d_csr_ids, &c->d_node_lo, &c->d_node_hi,
                       &c->d_node_type, &c->d_child_first, &c->d_child_count, &c->d_node_blo, &c->d_node_bhi, &c->d_bnd_after,
                       &c->d_bnd_rank, &c->d_ref_levels, &c->d_lnfact, &c->d_seq_off, &c->d_codes, &c->d_exact_off, &c->d_exact_ids,
-                      &c->d_K, &c->d_kmers, &c->d_rows, &c->d_nrows, &c->d_hist, &c->d_counts, &c->d_pool_first, &c->d_pool_nlev,
+                      &c->d_K, &c->d_kmers, &c->d_rows, &c->d_nrows, &c->d_hist, &c->d_counts, &c->d_counts1, &c->d_preb1, &c->d_ptab1, &c->d_segoff1, &c->d_pool_first, &c->d_pool_nlev,
                       &c->d_pool_conf, &c->d_pool_local, &c->d_pool_used, &c->d_res_off, &c->d_res_cnt, &c->d_global, &c->d_status,
                       &c->d_hits, &c->d_cbuf, &c->d_preb, &c->d_ptab, &c->d_segoff, &c->d_recs, &c->d_strad_of_node, &c->d_strad_nodes, &c->d_strad_parent,
                       &c->d_send, &c->d_recv, &c->d_sk, &c->d_sany, &c->d_sbest};
     for (DevBuf* b : bufs) b->release();
+    for (int i = 0; i < 2; ++i) {
+        if (c->ev_hit[i]) cudaEventDestroy(c->ev_hit[i]);
+        if (c->ev_post[i]) cudaEventDestroy(c->ev_post[i]);
+    }
+    if (c->stream2) cudaStreamDestroy(c->stream2);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -232,6 +258,9 @@ RTX_API int rtx_ctx_set_option(rtx_ctx* ctx, int option, int64_t value) {
         case RTX_OPT_HITCOUNT_MAX_TILES:
             REQUIRE(value >= 0 && value <= 4096, "bad max tiles per CTA");
             ctx->hit_max_tiles = (int)value;
+            return RTX_OK;
+        case RTX_OPT_PIPELINE:
+            ctx->pipeline_opt = value != 0;
             return RTX_OK;
         case RTX_OPT_WALK_VARIANT:
             REQUIRE(value == 0 || value == 1, "unknown walk variant");
@@ -264,6 +293,7 @@ RTX_API int rtx_ctx_synchronize(rtx_ctx* ctx) {
     if (!ctx) return RTX_ERR_INVALID;
     CU(cudaSetDevice(ctx->device));
     CU(cudaStreamSynchronize(ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream2));
     return RTX_OK;
 }
 
@@ -271,6 +301,7 @@ RTX_API uint64_t rtx_index_n_refs(const rtx_ctx* c) { return c && c->has_index ?
 RTX_API uint64_t rtx_index_shard_refs(const rtx_ctx* c) { return c && c->has_index ? c->ix.shard_refs : 0; }
 RTX_API uint32_t rtx_index_max_levels(const rtx_ctx* c) { return c && c->has_index ? c->ix.max_levels : 0; }
 RTX_API uint64_t rtx_index_device_bytes(const rtx_ctx* c) { return c && c->has_index ? c->index_bytes : 0; }
+RTX_API uint32_t rtx_batch_sub_batch(const rtx_ctx* c) { return c && c->has_batch ? c->sub_batch : 0; }
 
 // ---------------------------------------------------------------------------------------------------------
 // index upload
@@ -645,9 +676,13 @@ RTX_API int rtx_batch_upload(rtx_ctx* ctx, const rtx_batch* batch) {
     // sub-batch: bound the per-query count vectors to ~2 GiB
     const u64 per_query = ctx->ix.n_pad * 2;
     u64 sb = ctx->sub_batch_opt ? (u64)ctx->sub_batch_opt : std::max<u64>(1, (2ull << 30) / per_query);
+    const bool may_pipe = ctx->pipeline_opt && ctx->sv.n_shards <= 1;
+    if (!ctx->sub_batch_opt && may_pipe && nq >= 4096) sb = std::min<u64>(sb, std::max<u64>(1024, (nq + 3) / 4));  // >= 4 pipeline stages
     sb = std::min<u64>(std::min<u64>(sb, nq), 65535);
     ctx->sub_batch = (u32)sb;
+    ctx->two_slots = may_pipe && nq > sb;
     CU(ctx->d_counts.ensure(sb * per_query));
+    if (ctx->two_slots) CU(ctx->d_counts1.ensure(sb * per_query));
 
     // probability kernel scratch
     ctx->prob_smem = smem;
@@ -683,6 +718,19 @@ RTX_API int rtx_batch_upload(rtx_ctx* ctx, const rtx_batch* batch) {
     ctx->sc.segoff_stride = round_up((u32)(ctx->ix.n_pad / kPrefixSeg), 4);
     CU(ctx->d_segoff.ensure((size_t)sb * ctx->sc.segoff_stride * 8));
     ctx->sc.segoff = ctx->d_segoff.as<double>();
+    ctx->sc1 = ctx->sc;
+    if (ctx->two_slots) {
+        CU(ctx->d_preb1.ensure((size_t)sb * ctx->sc.preb_stride * 8));
+        CU(ctx->d_ptab1.ensure((size_t)sb * hstride * 8));
+        CU(ctx->d_segoff1.ensure((size_t)sb * ctx->sc.segoff_stride * 8));
+        ctx->sc1.preb = ctx->d_preb1.as<double>();
+        ctx->sc1.ptab = ctx->d_ptab1.as<double>();
+        ctx->sc1.segoff = ctx->d_segoff1.as<double>();
+        // the log-CMF scratch is indexed by CTA slot of prob_table_kernel, which only ever runs on stream2: shared
+    }
+    ctx->cur_stream = ctx->stream;
+    ctx->cur_counts = ctx->d_counts.as<u16>();
+    ctx->cur_sc = &ctx->sc;
     ctx->has_batch = true;
     return RTX_OK;
 }
@@ -721,7 +769,7 @@ static cudaError_t launch_hitcount(rtx_ctx* c, int q_base, int qb, int nwarps_op
     cudaError_t e = cudaFuncSetAttribute(hitcount_bitrows_kernel<V, NP, PF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     dim3 grid(qb, groups);
-    hitcount_bitrows_kernel<V, NP, PF><<<grid, nwarps * 32, smem, c->stream>>>(c->ix, c->bv, c->d_counts.as<u16>(), q_base, tiles_per_cta, n_tiles);
+    hitcount_bitrows_kernel<V, NP, PF><<<grid, nwarps * 32, smem, c->cur_stream>>>(c->ix, c->bv, c->cur_counts, q_base, tiles_per_cta, n_tiles);
     return cudaGetLastError();
 }
 
@@ -763,7 +811,7 @@ static cudaError_t launch_hitcount_group(rtx_ctx* c, int q_base, int qb, int G) 
     cudaError_t e = cudaFuncSetAttribute(hitcount_group_kernel<V, NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     dim3 grid((qb + G - 1) / G, groups);
-    hitcount_group_kernel<V, NP><<<grid, G * 32, smem, c->stream>>>(c->ix, c->bv, c->d_counts.as<u16>(), q_base, qb, tiles_per_cta, n_tiles,
+    hitcount_group_kernel<V, NP><<<grid, G * 32, smem, c->cur_stream>>>(c->ix, c->bv, c->cur_counts, q_base, qb, tiles_per_cta, n_tiles,
                                                                    chunk_rows, n_chunks);
     return cudaGetLastError();
 }
@@ -798,7 +846,7 @@ static int run_phase1(rtx_ctx* ctx, int q_base, int qb) {
         const size_t smem = (size_t)(kCsrTileRefs / 2 + ctx->bv.hstride) * 4;
         CU(cudaFuncSetAttribute(hitcount_csr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         dim3 grid(qb, (unsigned)((ctx->ix.shard_refs + kCsrTileRefs - 1) / kCsrTileRefs));
-        hitcount_csr_kernel<<<grid, kCsrThreads, smem, ctx->stream>>>(ctx->ix, ctx->bv, ctx->d_counts.as<u16>(), q_base);
+        hitcount_csr_kernel<<<grid, kCsrThreads, smem, ctx->cur_stream>>>(ctx->ix, ctx->bv, ctx->cur_counts, q_base);
         CU(cudaGetLastError());
     } else {
         CU(launch_hitcount_tuned(ctx, q_base, qb, kmax));
@@ -811,13 +859,13 @@ static int launch_prob(rtx_ctx* ctx, int q0, int qb) {
     {
         LaunchTimer lt(ctx, RTX_K_PROB);
         const int grid = std::min(ctx->prob_slots, qb);
-        prob_table_kernel<<<grid, kProbThreads, ctx->prob_smem, ctx->stream>>>(ctx->ix, ctx->bv, ctx->pool, ctx->sc, q0, qb,
+        prob_table_kernel<<<grid, kProbThreads, ctx->prob_smem, ctx->cur_stream>>>(ctx->ix, ctx->bv, ctx->pool, *ctx->cur_sc, q0, qb,
                                                                              ctx->d_hits.as<unsigned long long>());
         CU(cudaGetLastError());
     }
     {
         LaunchTimer lt(ctx, RTX_K_PREFIX);
-        prefix_kernel<<<qb, kPrefixThreads, ctx->prefix_smem, ctx->stream>>>(ctx->ix, ctx->bv, ctx->sc, ctx->d_counts.as<u16>(), q0, qb);
+        prefix_kernel<<<qb, kPrefixThreads, ctx->prefix_smem, ctx->cur_stream>>>(ctx->ix, ctx->bv, *ctx->cur_sc, ctx->cur_counts, q0, qb);
         CU(cudaGetLastError());
     }
     return RTX_OK;
@@ -837,14 +885,29 @@ static int run_all(rtx_ctx* ctx) {
         kmers_kernel<<<nq, kKmerThreads, 0, ctx->stream>>>(ctx->ix, bv);
         CU(cudaGetLastError());
     }
-    for (u32 q0 = 0; q0 < nq; q0 += ctx->sub_batch) {
+    // Sub-batch pipeline: hit counting of sub-batch i runs on `stream`, everything behind it (probabilities, prefix sums,
+    // tree walk, taps) on `stream2` with the buffers of slot i & 1, so that the L2/ALU-bound hit counting of the next
+    // sub-batch overlaps the FP64/latency-bound tail of this one.
+    const bool pipe = ctx->two_slots;
+    u32 i_sub = 0;
+    for (u32 q0 = 0; q0 < nq; q0 += ctx->sub_batch, ++i_sub) {
         const int qb = (int)std::min<u32>(ctx->sub_batch, nq - q0);
+        const int slot = pipe ? (int)(i_sub & 1u) : 0;
+        ctx->cur_counts = slot ? ctx->d_counts1.as<u16>() : ctx->d_counts.as<u16>();
+        ctx->cur_sc = slot ? &ctx->sc1 : &ctx->sc;
+        ctx->cur_stream = ctx->stream;
+        if (pipe && i_sub >= 2) CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_post[slot], 0));  // the slot's previous tenant is done
         int rc = run_phase1(ctx, (int)q0, qb);
         if (rc) return rc;
         if ((bv.flags & RTX_SKIP_EXACT_MATCHES) && bv.exact_off) {
             LaunchTimer lt(ctx, RTX_K_FIXUP);
-            fixup_exact_kernel<<<(qb + 127) / 128, 128, 0, ctx->stream>>>(ctx->ix, bv, ctx->d_counts.as<u16>(), (int)q0, qb);
+            fixup_exact_kernel<<<(qb + 127) / 128, 128, 0, ctx->cur_stream>>>(ctx->ix, bv, ctx->cur_counts, (int)q0, qb);
             CU(cudaGetLastError());
+        }
+        if (pipe) {
+            CU(cudaEventRecord(ctx->ev_hit[slot], ctx->stream));
+            ctx->cur_stream = ctx->stream2;
+            CU(cudaStreamWaitEvent(ctx->stream2, ctx->ev_hit[slot], 0));
         }
         {
             int rc2 = launch_prob(ctx, (int)q0, qb);
@@ -853,27 +916,35 @@ static int run_all(rtx_ctx* ctx) {
         {
             LaunchTimer lt(ctx, RTX_K_WALK);
             if (ctx->walk_variant == 0) {  // level-synchronous walk, then the depth-first walker for the queries it handed back
-                lineage_bfs_kernel<<<qb, kBfsThreads, ctx->bfs_smem, ctx->stream>>>(
-                    ctx->ix, ctx->d_recs.as<NodeRec>(), bv, ctx->pool, ctx->sc, (int)q0, qb, ctx->walk_log_cap ? (u32)ctx->walk_log_cap : kBfsEntries);
+                lineage_bfs_kernel<<<qb, kBfsThreads, ctx->bfs_smem, ctx->cur_stream>>>(
+                    ctx->ix, ctx->d_recs.as<NodeRec>(), bv, ctx->pool, *ctx->cur_sc, (int)q0, qb, ctx->walk_log_cap ? (u32)ctx->walk_log_cap : kBfsEntries);
                 CU(cudaGetLastError());
             }
-            lineage_walk_kernel<false><<<(qb + kWalkWarps - 1) / kWalkWarps, kWalkWarps * 32, ctx->walk_smem, ctx->stream>>>(
-                ctx->ix, ctx->d_recs.as<NodeRec>(), bv, ctx->pool, ctx->sc, ShardView{}, (int)q0, qb, ctx->walk_variant == 0 ? 1 : 0);
+            lineage_walk_kernel<false><<<(qb + kWalkWarps - 1) / kWalkWarps, kWalkWarps * 32, ctx->walk_smem, ctx->cur_stream>>>(
+                ctx->ix, ctx->d_recs.as<NodeRec>(), bv, ctx->pool, *ctx->cur_sc, ShardView{}, (int)q0, qb, ctx->walk_variant == 0 ? 1 : 0);
             CU(cudaGetLastError());
         }
         if (ctx->tap_counts_host) {
             const u64 Ns = ctx->ix.shard_refs;
-            CU(cudaMemcpy2DAsync(ctx->tap_counts_host + (size_t)q0 * Ns, Ns * 2, ctx->d_counts.p, ctx->ix.n_pad * 2, Ns * 2, qb,
-                                 cudaMemcpyDeviceToHost, ctx->stream));
+            CU(cudaMemcpy2DAsync(ctx->tap_counts_host + (size_t)q0 * Ns, Ns * 2, ctx->cur_counts, ctx->ix.n_pad * 2, Ns * 2, qb,
+                                 cudaMemcpyDeviceToHost, ctx->cur_stream));
             ctx->prof.d2h_bytes += (u64)qb * Ns * 2;
         }
         if (ctx->tap_probs_host) {
             const u64 w = std::min<u64>(ctx->tap_prob_stride, bv.hstride);
-            CU(cudaMemcpy2DAsync(ctx->tap_probs_host + (size_t)q0 * ctx->tap_prob_stride, ctx->tap_prob_stride * 8, ctx->d_ptab.p,
-                                 (size_t)bv.hstride * 8, w * 8, qb, cudaMemcpyDeviceToHost, ctx->stream));
+            CU(cudaMemcpy2DAsync(ctx->tap_probs_host + (size_t)q0 * ctx->tap_prob_stride, ctx->tap_prob_stride * 8, ctx->cur_sc->ptab,
+                                 (size_t)bv.hstride * 8, w * 8, qb, cudaMemcpyDeviceToHost, ctx->cur_stream));
             ctx->prof.d2h_bytes += (u64)qb * w * 8;
         }
+        if (pipe) CU(cudaEventRecord(ctx->ev_post[slot], ctx->stream2));
     }
+    if (pipe) {  // everything issued later on `stream` (downloads, the next run) is ordered behind both slots
+        CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_post[0], 0));
+        if (i_sub >= 2) CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_post[1], 0));
+    }
+    ctx->cur_stream = ctx->stream;
+    ctx->cur_counts = ctx->d_counts.as<u16>();
+    ctx->cur_sc = &ctx->sc;
     ctx->prof.queries += nq;
     ctx->runs_since_download += 1;
     ctx->ran = true;

@@ -178,6 +178,31 @@ def test_walk_variants_agree(ctx, skip):
         assert _same_outputs(outs[0], o)
 
 
+def test_pipelined_batch_matches_serial(ctx):
+    """A batch large enough for the two-stream sub-batch pipeline (>= 4096 queries) must give bit-identical outputs with the
+    pipeline on (default), off, and with an odd sub-batch size; taps included."""
+    ds = synth.generate("small", n_queries=4500, measure=False)
+    ht = capi.Tree.new(ds.ref_lineages, ds.ref_off, ds.ref_codes)
+    ctx.upload_tree(ht)
+    eo, eids = ht.exact_batch(ds.query_off, ds.query_codes)
+    outs = []
+    try:
+        for pipe, sb in ((1, 0), (0, 0), (1, 777)):
+            ctx.set_option(capi.RTX_OPT_PIPELINE, pipe)
+            ctx.set_option(capi.RTX_OPT_SUB_BATCH, sb)
+            outs.append(ctx.classify(ds.query_off, ds.query_codes, eo, eids, taps=("counts", "hist", "probs")))
+            if pipe and sb == 0:
+                assert ctx.sub_batch < ds.n_queries  # really pipelined
+    finally:
+        ctx.set_option(capi.RTX_OPT_PIPELINE, 1)
+        ctx.set_option(capi.RTX_OPT_SUB_BATCH, 0)
+    for o in outs[1:]:
+        assert _same_outputs(outs[0], o)
+        assert np.array_equal(outs[0].counts, o.counts) and np.array_equal(outs[0].hist, o.hist)
+        cnt = o.counts.astype(np.int64)
+        assert np.array_equal(np.take_along_axis(outs[0].probs, cnt, 1), np.take_along_axis(o.probs, cnt, 1))  # P(m) where the histogram is non-zero
+
+
 def test_16s_like_long_queries(oracle, ctx):
     ds = synth.generate("x16s", n_refs=1500, n_queries=48, length=1500, kind="16s", seed=77, measure=False)
     o, dev, ot, _ = _run_both(oracle, ctx, ds, skip=True)

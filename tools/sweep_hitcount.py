@@ -2,7 +2,7 @@
 
 usage: sweep_hitcount.py [workload] [configs]     configs = comma-separated words of letter+number fields, e.g.  G16C0,G8C12,G1T12M4
    G = RTX_OPT_HITCOUNT_GROUP (queries per CTA; 1 = single-query kernel), C = RTX_OPT_HITCOUNT_CHUNKS, T = RTX_OPT_HITCOUNT_TUNE,
-   M = RTX_OPT_HITCOUNT_MAX_TILES.  Every configuration's histograms are compared with the first one's (bit-exact).
+   M = RTX_OPT_HITCOUNT_MAX_TILES, S = RTX_OPT_SUB_BATCH (queries per device sub-batch).  Every configuration's histograms are compared with the first one's (bit-exact).
 """
 import json
 import os
@@ -23,12 +23,14 @@ ctx = capi.Context(0)
 ctx.upload_tree(tree)
 eo, eids = tree.exact_batch(ds.query_off, ds.query_codes)
 ctx.batch_upload(ds.query_off, ds.query_codes, eo, eids)
-OPT = {"G": capi.RTX_OPT_HITCOUNT_GROUP, "C": capi.RTX_OPT_HITCOUNT_CHUNKS, "T": capi.RTX_OPT_HITCOUNT_TUNE, "M": capi.RTX_OPT_HITCOUNT_MAX_TILES}
+OPT = {"G": capi.RTX_OPT_HITCOUNT_GROUP, "C": capi.RTX_OPT_HITCOUNT_CHUNKS, "T": capi.RTX_OPT_HITCOUNT_TUNE, "M": capi.RTX_OPT_HITCOUNT_MAX_TILES,
+       "S": capi.RTX_OPT_SUB_BATCH}
 ref = None
 for cfg in configs:
-    f = {k: int(v) for k, v in re.findall(r"([GCTM])(\d+)", cfg)}
+    f = {k: int(v) for k, v in re.findall(r"([GCTMS])(\d+)", cfg)}
     for k, o in OPT.items():
         ctx.set_option(o, f.get(k, 0))
+    ctx.batch_upload(ds.query_off, ds.query_codes, eo, eids)  # the sub-batch size is fixed at upload time
     ctx.set_option(capi.RTX_OPT_PROFILE, 0)
     ctx.batch_run()
     ctx.synchronize()
@@ -40,8 +42,8 @@ for cfg in configs:
     p = ctx.profile()
     if ref is None:
         ref = out.hist.copy()
-    ms = p["hitcount"]["total_ms"] / p["hitcount"]["launches"]
-    gbs = p["bitrow_bytes"] / p["hitcount"]["launches"] / ms / 1e6
-    print(json.dumps(dict(cfg=cfg, hitcount_ms=round(ms, 3), bitrow_GBps=round(gbs, 1), prob_ms=round(p["prob"]["total_ms"] / p["prob"]["launches"], 3),
-                          prefix_ms=round(p["prefix"]["total_ms"] / max(p["prefix"]["launches"], 1), 3),
-                          walk_ms=round(p["walk"]["total_ms"] / max(p["walk"]["launches"], 1), 3), hist_identical=bool(np.array_equal(out.hist, ref)))), flush=True)
+    ms = p["hitcount"]["total_ms"] / 3  # per pass over the whole batch (a pass is several launches when sub-batched)
+    gbs = p["bitrow_bytes"] / 3 / ms / 1e6
+    print(json.dumps(dict(cfg=cfg, hitcount_ms=round(ms, 3), bitrow_GBps=round(gbs, 1), prob_ms=round(p["prob"]["total_ms"] / 3, 3),
+                          prefix_ms=round(p["prefix"]["total_ms"] / 3, 3), walk_ms=round(p["walk"]["total_ms"] / 3, 3),
+                          hist_identical=bool(np.array_equal(out.hist, ref)))), flush=True)
