@@ -80,7 +80,8 @@ int rtx_ctx_synchronize(rtx_ctx* ctx);
 /* ---- reference index ("Tree", src/tree.rs:36-43) --------------------------------------------------------
  * Flattened form of what Tree::new (tree.rs:47-140) builds:
  *  - reference ids are positions in the lineage-sorted order (tree.rs:53-54), n_refs = Tree.num_tips;
- *  - k_mer_map (tree.rs:41,134-137) as CSR: csr_offsets[65537], csr_ids ascending and unique per list;
+ *  - k_mer_map (tree.rs:41,134-137) as CSR: csr_offsets[65537], csr_ids ascending and unique per list -- or, instead,
+ *    the sorted reference sequences (ref_seq_*), from which the device builds its index directly;
  *  - the Node tree (tree.rs:189-194) without its childless Sequence leaves (they never influence
  *    Lineage::evaluate, lineage.rs:119-179, because their parent is never Inner), numbered so that the children of node i are the consecutive
  *    nodes child_first[i] .. child_first[i]+child_count[i]-1 in the reference's child order; node 0 = root;
@@ -107,6 +108,12 @@ typedef struct {
     uint32_t n_shards;
     uint32_t shard_rank;
     const uint64_t* shard_cuts; /* [n_shards + 1], shard_cuts[0] = 0, shard_cuts[n_shards] = n_refs */
+    /* Alternative to the CSR (used when csr_offsets == NULL): the lineage-sorted reference sequences themselves, 4-bit codes as
+     * parser.rs:11-34, reference r = ref_seq_codes[ref_seq_offsets[r] .. ref_seq_offsets[r+1]).  The library then does the windowing
+     * and de-duplication of tree.rs:114-123,134-137 on the device and never materialises k_mer_map (the CSR hit-count variant
+     * is unavailable for such an index). */
+    const uint64_t* ref_seq_offsets; /* [n_refs + 1] */
+    const uint8_t* ref_seq_codes;
 } rtx_index_desc;
 
 int rtx_index_upload(rtx_ctx* ctx, const rtx_index_desc* desc);

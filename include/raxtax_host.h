@@ -36,6 +36,11 @@ void rxh_tree_free(rxh_tree* t);
 size_t rxh_tree_num_tips(const rxh_tree* t);
 const char* rxh_tree_lineage(const rxh_tree* t, size_t i); /* Tree.lineages[i] (sorted order) */
 /* Tree.k_mer_map as CSR (pointers stay valid for the life of the tree) */
+/* Tree.k_mer_map (tree.rs:41) is materialised on first use only: the device builds its index from the sorted sequences
+ * (rtx_index_desc.ref_seq_*), so classification never needs the lists on the host.  rxh_tree_build_kmer_map forces it (after which
+ * rxh_tree_index_desc / rxh_tree_upload hand the CSR to the device instead); rxh_tree_csr builds it if needed and returns it. */
+void rxh_tree_build_kmer_map(const rxh_tree* t);
+int rxh_tree_has_kmer_map(const rxh_tree* t);
 void rxh_tree_csr(const rxh_tree* t, const uint64_t** offsets, const uint32_t** ids);
 /* Tree.sequences.get(seq): number of matches; up to cap ascending ids are written */
 size_t rxh_tree_exact(const rxh_tree* t, const uint8_t* seq, size_t len, uint32_t* out, size_t cap);

@@ -36,7 +36,7 @@ DEVICE_SYMBOLS = [
 # every symbol include/raxtax_host.h declares
 HOST_SYMBOLS = [
     "rxh_last_error", "rxh_tree_from_fasta", "rxh_tree_new", "rxh_tree_free", "rxh_tree_num_tips", "rxh_tree_lineage",
-    "rxh_tree_csr", "rxh_tree_exact", "rxh_tree_index_desc", "rxh_tree_upload", "rxh_tree_upload_sharded", "rxh_queries_from_fasta", "rxh_queries_new",
+    "rxh_tree_csr", "rxh_tree_build_kmer_map", "rxh_tree_has_kmer_map", "rxh_tree_exact", "rxh_tree_index_desc", "rxh_tree_upload", "rxh_tree_upload_sharded", "rxh_queries_from_fasta", "rxh_queries_new",
     "rxh_queries_free", "rxh_queries_len", "rxh_queries_label", "rxh_queries_arrays", "rxh_raxtax", "rxh_exact_batch",
 ]
 
@@ -45,7 +45,7 @@ class IndexDesc(C.Structure):
     _fields_ = [("n_refs", C.c_uint64), ("csr_offsets", u64p), ("csr_ids", u32p), ("n_nodes", C.c_uint32), ("node_lo", u32p),
                 ("node_hi", u32p), ("node_type", u8p), ("child_first", u32p), ("child_count", u32p), ("ref_levels", u8p),
                 ("ref_shard_begin", C.c_uint64), ("ref_shard_end", C.c_uint64), ("n_shards", C.c_uint32), ("shard_rank", C.c_uint32),
-                ("shard_cuts", u64p)]
+                ("shard_cuts", u64p), ("ref_seq_offsets", u64p), ("ref_seq_codes", u8p)]
 
 
 class Batch(C.Structure):
@@ -144,6 +144,10 @@ def host_lib():
     L.rxh_tree_lineage.argtypes = [C.c_void_p, C.c_size_t]
     L.rxh_tree_csr.argtypes = [C.c_void_p, C.POINTER(u64p), C.POINTER(u32p)]
     L.rxh_tree_csr.restype = None
+    L.rxh_tree_build_kmer_map.argtypes = [C.c_void_p]
+    L.rxh_tree_build_kmer_map.restype = None
+    L.rxh_tree_has_kmer_map.argtypes = [C.c_void_p]
+    L.rxh_tree_has_kmer_map.restype = C.c_int
     L.rxh_tree_exact.restype = C.c_size_t
     L.rxh_tree_exact.argtypes = [C.c_void_p, u8p, C.c_size_t, u32p, C.c_size_t]
     L.rxh_tree_index_desc.argtypes = [C.c_void_p, C.POINTER(IndexDesc)]
@@ -429,13 +433,25 @@ class Tree:
         return cls(host_lib().rxh_tree_from_fasta(b, len(b)))
 
     @classmethod
-    def new(cls, lineages, seq_off, codes) -> "Tree":  # Tree::new
+    def new(cls, lineages, seq_off, codes, eager_kmer_map=False) -> "Tree":  # Tree::new
+        """k_mer_map (the CSR postings) is built on first use only unless eager_kmer_map: the device derives its index from the
+        sorted sequences, and uploads of a tree WITH a materialised k_mer_map go through the CSR instead."""
         blob = "\n".join(lineages).encode()
         seq_off = np.ascontiguousarray(seq_off, np.uint64)
         codes = np.ascontiguousarray(codes, np.uint8)
         if codes.size == 0:
             codes = np.zeros(1, np.uint8)
-        return cls(host_lib().rxh_tree_new(len(lineages), blob, len(blob), _ptr(seq_off, C.c_uint64), _ptr(codes, C.c_uint8)))
+        t = cls(host_lib().rxh_tree_new(len(lineages), blob, len(blob), _ptr(seq_off, C.c_uint64), _ptr(codes, C.c_uint8)))
+        if eager_kmer_map:
+            t.build_kmer_map()
+        return t
+
+    def build_kmer_map(self):
+        host_lib().rxh_tree_build_kmer_map(self._h)
+
+    @property
+    def has_kmer_map(self) -> bool:
+        return bool(host_lib().rxh_tree_has_kmer_map(self._h))
 
     def __del__(self):
         try:
@@ -493,6 +509,7 @@ class Tree:
             cap = int(tot)
 
     def index_arrays(self) -> dict:
+        self.build_kmer_map()
         d = IndexDesc()
         host_lib().rxh_tree_index_desc(self._h, C.byref(d))
         nn, N = d.n_nodes, d.n_refs

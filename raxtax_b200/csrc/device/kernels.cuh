@@ -115,6 +115,62 @@ __global__ void __launch_bounds__(256) build_bitrows_kernel(const u64* __restric
 }
 
 // =========================================================================================================
+// K0 (from sequences): the k-mer -> reference index straight from the lineage-sorted reference sequences, without the
+// CSR detour (tree.rs:114-123 windowing, 134-137 unique: setting a bit is idempotent).  Two passes over the 4-bit codes:
+//   kmer_presence_kernel     which of the 65 536 8-mers occur in the shard at all (shared-memory bitmap per CTA, OR-ed out)
+//   bitrows_from_seq_kernel  bit (row of the k-mer, reference) := 1
+// One warp per reference, every lane folds its own windows; a window with an ambiguous base yields nothing (utils.rs:29-38).
+// ref_off are offsets into `codes` of the references [ref_first, ref_first + n) of the current upload chunk, rebased to 0.
+// =========================================================================================================
+__device__ __forceinline__ bool window_kmer(const u8* __restrict__ p, u32* kmer) {
+    u32 k = 0;
+    bool ok = true;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const u32 c = p[j];
+        ok &= (c == 1u) | (c == 2u) | (c == 4u) | (c == 8u);
+        k |= ((u32)(__ffs(c) - 1) & 3u) << (14 - 2 * j);
+    }
+    *kmer = k;
+    return ok;
+}
+
+__global__ void __launch_bounds__(256) kmer_presence_kernel(const u64* __restrict__ ref_off, const u8* __restrict__ codes, u32 n, u32* __restrict__ present) {
+    __shared__ u32 bitmap[2048];
+    const int tid = threadIdx.x, lane = tid & 31;
+    for (int i = tid; i < 2048; i += 256) bitmap[i] = 0;
+    __syncthreads();
+    const u32 warps = gridDim.x * 8u;
+    for (u32 r = blockIdx.x * 8u + (tid >> 5); r < n; r += warps) {
+        const u64 o = ref_off[r];
+        const u32 L = (u32)(ref_off[r + 1] - o);
+        for (u32 i = lane; i + 8 <= L; i += 32) {
+            u32 k;
+            if (window_kmer(codes + o + i, &k)) atomicOr(&bitmap[k >> 5], 1u << (k & 31));
+        }
+    }
+    __syncthreads();
+    for (int i = tid; i < 2048; i += 256)
+        if (bitmap[i]) atomicOr(&present[i], bitmap[i]);
+}
+
+__global__ void __launch_bounds__(256) bitrows_from_seq_kernel(const u64* __restrict__ ref_off, const u8* __restrict__ codes, u32 n, u64 local_first,
+                                                               const u32* __restrict__ rowmap, u32* __restrict__ bitrows, u32 row_words) {
+    const int tid = threadIdx.x, lane = tid & 31;
+    const u32 warps = gridDim.x * 8u;
+    for (u32 r = blockIdx.x * 8u + (tid >> 5); r < n; r += warps) {
+        const u64 o = ref_off[r];
+        const u32 L = (u32)(ref_off[r + 1] - o);
+        const u64 local = local_first + r;  // reference id relative to the shard
+        const u32 word = (u32)(local >> 5), bit = 1u << (u32)(local & 31);
+        for (u32 i = lane; i + 8 <= L; i += 32) {
+            u32 k;
+            if (window_kmer(codes + o + i, &k)) atomicOr(&bitrows[(size_t)rowmap[k] * row_words + word], bit);
+        }
+    }
+}
+
+// =========================================================================================================
 // K1: one CTA (128 threads) per query.  A 65 536-bit bitmap in shared memory is both the dedup set and the
 // sort: scanning it in word order emits the unique k-mers ascending (utils.rs:39).
 // =========================================================================================================

@@ -54,6 +54,7 @@ struct rtx_ctx {
     BatchView bv{};
     u32 max_len = 0;
     u64 total_codes = 0, total_exact = 0;
+    DevBuf d_seq_codes;  // reference sequences while the index is built from them
     DevBuf d_seq_off, d_codes, d_exact_off, d_exact_ids, d_K, d_kmers, d_rows, d_nrows, d_hist;
     DevBuf d_counts, d_counts1;
     u32 sub_batch = 0;
@@ -226,7 +227,7 @@ RTX_API void rtx_ctx_destroy(rtx_ctx* c) {
                       &c->d_bnd_rank, &c->d_ref_levels, &c->d_lnfact, &c->d_seq_off, &c->d_codes, &c->d_exact_off, &c->d_exact_ids,
                       &c->d_K, &c->d_kmers, &c->d_rows, &c->d_nrows, &c->d_hist, &c->d_counts, &c->d_counts1, &c->d_preb1, &c->d_ptab1, &c->d_segoff1, &c->d_pool_first, &c->d_pool_nlev,
                       &c->d_pool_conf, &c->d_pool_local, &c->d_pool_used, &c->d_res_off, &c->d_res_cnt, &c->d_global, &c->d_status,
-                      &c->d_hits, &c->d_cbuf, &c->d_preb, &c->d_ptab, &c->d_segoff, &c->d_recs, &c->d_strad_of_node, &c->d_strad_nodes, &c->d_strad_parent,
+                      &c->d_hits, &c->d_seq_codes, &c->d_cbuf, &c->d_preb, &c->d_ptab, &c->d_segoff, &c->d_recs, &c->d_strad_of_node, &c->d_strad_nodes, &c->d_strad_parent,
                       &c->d_send, &c->d_recv, &c->d_sk, &c->d_sany, &c->d_sbest};
     for (DevBuf* b : bufs) b->release();
     for (int i = 0; i < 2; ++i) {
@@ -319,9 +320,12 @@ RTX_API int rtx_index_upload(rtx_ctx* ctx, const rtx_index_desc* d) {
     if (!ctx) return RTX_ERR_INVALID;
     REQUIRE(d != nullptr, "rtx_index_upload: desc is NULL");
     REQUIRE(d->n_refs >= 1 && d->n_refs <= 0xFFFFFFFFull, "n_refs must be in [1, 2^32) (tree.rs:24-31)");
-    REQUIRE(d->csr_offsets && d->n_nodes >= 1 && d->node_lo && d->node_hi && d->node_type && d->child_first && d->child_count &&
-                d->ref_levels,
+    REQUIRE(d->n_nodes >= 1 && d->node_lo && d->node_hi && d->node_type && d->child_first && d->child_count && d->ref_levels,
             "rtx_index_upload: NULL array");
+    const bool from_seq = d->csr_offsets == nullptr;  // build the index on the device from the sorted reference sequences
+    REQUIRE(!from_seq || (d->ref_seq_offsets && (d->ref_seq_codes || d->ref_seq_offsets[d->n_refs] == d->ref_seq_offsets[0])),
+            "rtx_index_upload: neither a CSR (csr_offsets) nor reference sequences (ref_seq_offsets / ref_seq_codes) given");
+    REQUIRE(!(from_seq && ctx->keep_csr), "RTX_OPT_KEEP_CSR (CSR hit-count variant) needs an index described by its CSR");
     const u64 N = d->n_refs;
     u64 s0 = d->ref_shard_begin, s1 = d->ref_shard_end ? d->ref_shard_end : N;
     const u32 n_shards = d->n_shards > 1 ? d->n_shards : 1;
@@ -333,10 +337,14 @@ RTX_API int rtx_index_upload(rtx_ctx* ctx, const rtx_index_desc* d) {
         s1 = d->shard_cuts[d->shard_rank + 1];
     }
     REQUIRE(s0 < s1 && s1 <= N, "bad reference shard range");
-    const u64 nnz = d->csr_offsets[65536];
-    REQUIRE(d->csr_offsets[0] == 0, "csr_offsets[0] must be 0");
-    for (u32 k = 0; k < 65536; ++k) REQUIRE(d->csr_offsets[k] <= d->csr_offsets[k + 1], "csr_offsets must be non-decreasing");
-    REQUIRE(nnz == 0 || d->csr_ids, "csr_ids is NULL");
+    const u64 nnz = from_seq ? 0 : d->csr_offsets[65536];
+    if (!from_seq) {
+        REQUIRE(d->csr_offsets[0] == 0, "csr_offsets[0] must be 0");
+        for (u32 k = 0; k < 65536; ++k) REQUIRE(d->csr_offsets[k] <= d->csr_offsets[k + 1], "csr_offsets must be non-decreasing");
+        REQUIRE(nnz == 0 || d->csr_ids, "csr_ids is NULL");
+    } else {
+        for (u64 r = s0; r < s1; ++r) REQUIRE(d->ref_seq_offsets[r] <= d->ref_seq_offsets[r + 1], "ref_seq_offsets must be non-decreasing");
+    }
     REQUIRE(d->node_lo[0] == 0 && d->node_hi[0] == N, "node 0 must be the root with range [0, n_refs)");
     CU(cudaSetDevice(ctx->device));
     CU(cudaStreamSynchronize(ctx->stream));
@@ -378,21 +386,72 @@ RTX_API int rtx_index_upload(rtx_ctx* ctx, const rtx_index_desc* d) {
     // ---- row map: k-mers with at least one posting inside the shard ------------------------------------
     std::vector<u32> rowmap(65536, 0), present(2048, 0);
     u32 n_rows = 1;
-    for (u32 k = 0; k < 65536; ++k) {
-        const u64 o0 = d->csr_offsets[k], o1 = d->csr_offsets[k + 1];
-        if (o0 == o1) continue;
-        bool in = true;
-        if (s0 != 0 || s1 != N) {
-            const u32* it = std::lower_bound(d->csr_ids + o0, d->csr_ids + o1, (u32)s0);
-            in = (it != d->csr_ids + o1) && (*it < s1);
+    // upload chunks of the sequence path: whole references, at most ~256 MB of codes each
+    std::vector<u64> seq_chunks;  // reference ids where a chunk starts, + s1
+    if (from_seq) {
+        const u64 cap = 256ull << 20;
+        seq_chunks.push_back(s0);
+        u64 begin = s0;
+        for (u64 r = s0; r < s1; ++r) {
+            if (d->ref_seq_offsets[r + 1] - d->ref_seq_offsets[begin] > cap && r > begin) {
+                seq_chunks.push_back(r);
+                begin = r;
+            }
         }
-        if (in) {
-            rowmap[k] = n_rows++;
-            present[k >> 5] |= 1u << (k & 31);
+        seq_chunks.push_back(s1);
+        u64 max_codes = 1, max_refs = 1;
+        for (size_t c = 0; c + 1 < seq_chunks.size(); ++c) {
+            max_codes = std::max(max_codes, d->ref_seq_offsets[seq_chunks[c + 1]] - d->ref_seq_offsets[seq_chunks[c]]);
+            max_refs = std::max(max_refs, seq_chunks[c + 1] - seq_chunks[c]);
         }
+        CU(ctx->d_seq_codes.ensure(max_codes + 16));
+        CU(ctx->d_seq_off.ensure((max_refs + 1) * 8));
+        CU(ctx->d_present.ensure(2048 * 4));
+        CU(cudaMemsetAsync(ctx->d_present.p, 0, 2048 * 4, ctx->stream));
+    }
+    // one chunk of reference sequences -> device (offsets rebased to the chunk)
+    std::vector<u64> reb;
+    auto seq_chunk_to_device = [&](size_t c) -> cudaError_t {
+        const u64 r0 = seq_chunks[c], r1 = seq_chunks[c + 1];
+        const u64 o0 = d->ref_seq_offsets[r0], bytes_c = d->ref_seq_offsets[r1] - o0;
+        reb.resize(r1 - r0 + 1);
+        for (u64 r = r0; r <= r1; ++r) reb[r - r0] = d->ref_seq_offsets[r] - o0;
+        cudaError_t e = cudaMemcpyAsync(ctx->d_seq_off.p, reb.data(), reb.size() * 8, cudaMemcpyHostToDevice, ctx->stream);
+        if (e == cudaSuccess && bytes_c) e = cudaMemcpyAsync(ctx->d_seq_codes.p, d->ref_seq_codes + o0, bytes_c, cudaMemcpyHostToDevice, ctx->stream);
+        return e;
+    };
+    if (from_seq) {
+        for (size_t c = 0; c + 1 < seq_chunks.size(); ++c) {
+            CU(seq_chunk_to_device(c));
+            {
+                LaunchTimer lt(ctx, RTX_K_INDEX);
+                kmer_presence_kernel<<<ctx->n_sms * 4, 256, 0, ctx->stream>>>(ctx->d_seq_off.as<u64>(), ctx->d_seq_codes.as<u8>(),
+                                                                            (u32)(seq_chunks[c + 1] - seq_chunks[c]), ctx->d_present.as<u32>());
+            }
+            CU(cudaGetLastError());
+            CU(cudaStreamSynchronize(ctx->stream));  // reb / the pageable source are reused by the next chunk
+        }
+        CU(cudaMemcpy(present.data(), ctx->d_present.p, 2048 * 4, cudaMemcpyDeviceToHost));
+        for (u32 k = 0; k < 65536; ++k)
+            if (present[k >> 5] >> (k & 31) & 1u) rowmap[k] = n_rows++;
+        bytes += 2048 * 4;
+    } else {
+        for (u32 k = 0; k < 65536; ++k) {
+            const u64 o0 = d->csr_offsets[k], o1 = d->csr_offsets[k + 1];
+            if (o0 == o1) continue;
+            bool in = true;
+            if (s0 != 0 || s1 != N) {
+                const u32* it = std::lower_bound(d->csr_ids + o0, d->csr_ids + o1, (u32)s0);
+                in = (it != d->csr_ids + o1) && (*it < s1);
+            }
+            if (in) {
+                rowmap[k] = n_rows++;
+                present[k >> 5] |= 1u << (k & 31);
+            }
+        }
+        CU(upload_vec(ctx->d_present, present.data(), 2048, &bytes));
     }
     CU(upload_vec(ctx->d_rowmap, rowmap.data(), 65536, &bytes));
-    CU(upload_vec(ctx->d_present, present.data(), 2048, &bytes));
 
     // ---- node boundaries ---------------------------------------------------------------------------------
     std::vector<u32> bnd_after(row_words, 0), bnd_rank(row_words, 0), blo(nn), bhi(nn);
@@ -448,7 +507,21 @@ RTX_API int rtx_index_upload(rtx_ctx* ctx, const rtx_index_desc* d) {
     CU(ctx->d_bitrows.ensure((size_t)n_rows * row_bytes));
     CU(cudaMemsetAsync(ctx->d_bitrows.p, 0, (size_t)n_rows * row_bytes, ctx->stream));
     bytes += (u64)n_rows * row_bytes;
-    CU(upload_vec(ctx->d_csr_off, d->csr_offsets, 65537, nullptr));
+    if (from_seq) {
+        for (size_t c = 0; c + 1 < seq_chunks.size(); ++c) {
+            CU(seq_chunk_to_device(c));
+            {
+                LaunchTimer lt(ctx, RTX_K_INDEX);
+                bitrows_from_seq_kernel<<<ctx->n_sms * 8, 256, 0, ctx->stream>>>(ctx->d_seq_off.as<u64>(), ctx->d_seq_codes.as<u8>(),
+                                                                                (u32)(seq_chunks[c + 1] - seq_chunks[c]), seq_chunks[c] - s0,
+                                                                                ctx->d_rowmap.as<u32>(), ctx->d_bitrows.as<u32>(), row_words);
+            }
+            CU(cudaGetLastError());
+            CU(cudaStreamSynchronize(ctx->stream));
+        }
+        ctx->d_seq_codes.release();
+    } else
+        CU(upload_vec(ctx->d_csr_off, d->csr_offsets, 65537, nullptr));
     if (nnz) {
         if (ctx->keep_csr) {
             CU(upload_vec(ctx->d_csr_ids, d->csr_ids, nnz, &bytes));

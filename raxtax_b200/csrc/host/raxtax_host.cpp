@@ -9,10 +9,12 @@
 // rtx_index_upload directly; the per-query numerics all run on the GPU through include/raxtax_b200.h.
 
 #include <algorithm>
+#include <chrono>
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
 #include <memory>
+#include <mutex>
 #include <numeric>
 #include <stdexcept>
 #include <string>
@@ -103,8 +105,10 @@ struct Tree {
     std::vector<std::string> lineages;  // sorted (tree.rs:128-131)
     std::vector<u64> seq_off;           // sorted sequences, 4-bit codes
     std::vector<u8> seq_codes;
-    std::vector<u64> csr_off;  // k_mer_map (tree.rs:41): 65537 offsets
-    std::vector<u32> csr_ids;
+    std::vector<u64> csr_off;  // k_mer_map (tree.rs:41): 65537 offsets.  Built on first use (ensure_csr): the device builds its own
+    std::vector<u32> csr_ids;  // index from the sorted sequences, so the classification path never needs the lists on the host
+    bool has_csr = false;
+    std::mutex csr_mtx;
     std::unordered_map<u64, std::vector<u32>> seq_hash;  // sequences (tree.rs:40): hash of codes -> ids, verified on lookup
     // Inner / Taxon (and non-leaf Sequence) nodes, BFS order, children contiguous
     std::vector<u32> node_lo, node_hi, child_first, child_count;
@@ -137,6 +141,42 @@ struct Tree {
         }
     }
 };
+
+template <typename F>
+static inline void for_each_kmer(const u8* s, size_t n, F&& f);
+
+// k_mer_map as CSR (tree.rs:114-123 windowing, 134-137 unique + sorted): a counting pass and a fill pass over the sorted sequences
+static void build_csr(Tree& t) {
+    const size_t n = t.num_tips;
+    std::vector<u32> kcount(65537, 0), last(65536, 0xFFFFFFFFu);
+    for (size_t idx = 0; idx < n; ++idx) {
+        for_each_kmer(t.seq_codes.data() + t.seq_off[idx], (size_t)(t.seq_off[idx + 1] - t.seq_off[idx]), [&](u16 k) {
+            if (last[k] != (u32)idx) {
+                last[k] = (u32)idx;
+                kcount[k + 1]++;
+            }
+        });
+    }
+    t.csr_off.assign(65537, 0);
+    for (u32 k = 0; k < 65536; ++k) t.csr_off[k + 1] = t.csr_off[k] + kcount[k + 1];
+    t.csr_ids.resize(t.csr_off[65536]);
+    std::vector<u64> pos(t.csr_off.begin(), t.csr_off.end() - 1);
+    std::fill(last.begin(), last.end(), 0xFFFFFFFFu);
+    for (size_t idx = 0; idx < n; ++idx) {
+        for_each_kmer(t.seq_codes.data() + t.seq_off[idx], (size_t)(t.seq_off[idx + 1] - t.seq_off[idx]), [&](u16 k) {
+            if (last[k] != (u32)idx) {
+                last[k] = (u32)idx;
+                t.csr_ids[pos[k]++] = (u32)idx;
+            }
+        });
+    }
+    t.has_csr = true;
+}
+static void ensure_csr(const Tree& ct) {
+    Tree& t = const_cast<Tree&>(ct);
+    std::lock_guard<std::mutex> g(t.csr_mtx);
+    if (!t.has_csr) build_csr(t);
+}
 
 struct BNode {  // build-time node (tree.rs:189-194)
     std::string label;
@@ -171,15 +211,24 @@ static inline void for_each_kmer(const u8* s, size_t n, F&& f) {  // windows(8) 
 }
 
 // Tree::new (tree.rs:47-140)
-static std::unique_ptr<Tree> tree_new(std::vector<std::string> lineages, const u64* seq_off, const u8* codes) {
+static std::unique_ptr<Tree> tree_new(std::vector<std::string> lineages, const u64* seq_off, const u8* codes, bool eager_csr = false) {
     const size_t n = lineages.size();
     if (n > 0xFFFFFFFFull)
         throw Error("Too many database sequences to run with 32-bit indices!");  // tree.rs:24-31
     auto tree = std::make_unique<Tree>();
+    const bool timing = getenv("RXH_TIMING") != nullptr;  // phase times of the build on stderr
+    auto t_prev = std::chrono::steady_clock::now();
+    auto lap = [&](const char* what) {
+        if (!timing) return;
+        auto now = std::chrono::steady_clock::now();
+        fprintf(stderr, "[rxh tree_new] %-28s %8.3f s\n", what, std::chrono::duration<double>(now - t_prev).count());
+        t_prev = now;
+    };
     std::vector<u32> order(n);
     std::iota(order.begin(), order.end(), 0u);
     std::stable_sort(order.begin(), order.end(), [&](u32 a, u32 b) { return lineages[a].compare(lineages[b]) < 0; });  // tree.rs:54
 
+    lap("stable sort by lineage");
     std::vector<BNode> nodes;
     nodes.reserve(n / 2 + 16);
     nodes.push_back(BNode{"root", 0, 1, 0, {}, false});
@@ -191,7 +240,6 @@ static std::unique_ptr<Tree> tree_new(std::vector<std::string> lineages, const u
         for (size_t i = 0; i < n; ++i) total += seq_off[order[i] + 1] - seq_off[order[i]];
         tree->seq_codes.resize(total);
     }
-    std::vector<u32> kcount(65537, 0), last(65536, 0xFFFFFFFFu);
     std::vector<std::string> levels;
     u64 wpos = 0;
     for (size_t idx = 0; idx < n; ++idx) {  // tree.rs:56-126
@@ -250,38 +298,17 @@ static std::unique_ptr<Tree> tree_new(std::vector<std::string> lineages, const u
         memcpy(tree->seq_codes.data() + wpos, codes + o, l);
         tree->seq_off[idx] = wpos;
         tree->seq_hash[Tree::hash_bytes(codes + o, l)].push_back((u32)idx);  // tree.rs:109-112
-        for_each_kmer(codes + o, l, [&](u16 k) {                             // tree.rs:114-123 (+ unique, 134-137)
-            if (last[k] != (u32)idx) {
-                last[k] = (u32)idx;
-                kcount[k + 1]++;
-            }
-        });
         wpos += l;
     }
     tree->seq_off[n] = wpos;
+    lap("nodes + sequence hash map");
     nodes[0].hi = (u32)confidence_idx;  // tree.rs:127
     tree->num_tips = confidence_idx;    // tree.rs:138
     tree->lineages.resize(n);
     for (size_t i = 0; i < n; ++i) tree->lineages[i] = std::move(lineages[order[i]]);
 
-    // k_mer_map as CSR: second pass fills the lists (ids ascend, duplicates were skipped)
-    tree->csr_off.assign(65537, 0);
-    for (u32 k = 0; k < 65536; ++k) tree->csr_off[k + 1] = tree->csr_off[k] + kcount[k + 1];
-    tree->csr_ids.resize(tree->csr_off[65536]);
-    {
-        std::vector<u64> pos(tree->csr_off.begin(), tree->csr_off.end() - 1);
-        std::fill(last.begin(), last.end(), 0xFFFFFFFFu);
-        for (size_t idx = 0; idx < n; ++idx) {
-            const u8* s = tree->seq_codes.data() + tree->seq_off[idx];
-            for_each_kmer(s, (size_t)(tree->seq_off[idx + 1] - tree->seq_off[idx]), [&](u16 k) {
-                if (last[k] != (u32)idx) {
-                    last[k] = (u32)idx;
-                    tree->csr_ids[pos[k]++] = (u32)idx;
-                }
-            });
-        }
-    }
-
+    if (eager_csr) build_csr(*tree);  // tree.rs:114-123,134-137; otherwise on first use
+    lap(eager_csr ? "k_mer_map (CSR), 2 passes" : "k_mer_map deferred");
     // flatten: BFS numbering, children contiguous.  Implicit Sequence leaves are dropped: they can neither be emitted
     // nor change a decision of Lineage::eval_recurse (lineage.rs:119-179) because their parent is never Inner.
     const size_t nn = nodes.size();
@@ -299,6 +326,7 @@ static std::unique_ptr<Tree> tree_new(std::vector<std::string> lineages, const u
         tree->child_count.push_back((u32)b.children.size());
         for (u32 c : b.children) bfs.push_back(c);
     }
+    lap("flatten");
     return tree;
 }
 
@@ -514,7 +542,10 @@ RXH_API rxh_tree* rxh_tree_new(size_t n, const char* lineage_blob, size_t blob_l
 RXH_API void rxh_tree_free(rxh_tree* t) { delete t; }
 RXH_API size_t rxh_tree_num_tips(const rxh_tree* t) { return t->t->num_tips; }
 RXH_API const char* rxh_tree_lineage(const rxh_tree* t, size_t i) { return t->t->lineages[i].c_str(); }
+RXH_API void rxh_tree_build_kmer_map(const rxh_tree* t) { ensure_csr(*t->t); }
+RXH_API int rxh_tree_has_kmer_map(const rxh_tree* t) { return t->t->has_csr ? 1 : 0; }
 RXH_API void rxh_tree_csr(const rxh_tree* t, const uint64_t** offsets, const uint32_t** ids) {
+    ensure_csr(*t->t);
     *offsets = t->t->csr_off.data();
     *ids = t->t->csr_ids.data();
 }
@@ -529,8 +560,10 @@ RXH_API int rxh_tree_index_desc(const rxh_tree* h, rtx_index_desc* d) {
     const Tree& t = *h->t;
     memset(d, 0, sizeof *d);
     d->n_refs = t.num_tips;
-    d->csr_offsets = t.csr_off.data();
-    d->csr_ids = t.csr_ids.data();
+    d->csr_offsets = t.has_csr ? t.csr_off.data() : nullptr;  // without a materialised k_mer_map the device windows the sequences itself
+    d->csr_ids = t.has_csr ? t.csr_ids.data() : nullptr;
+    d->ref_seq_offsets = t.seq_off.data();
+    d->ref_seq_codes = t.seq_codes.data();
     d->n_nodes = (uint32_t)t.node_lo.size();
     d->node_lo = t.node_lo.data();
     d->node_hi = t.node_hi.data();

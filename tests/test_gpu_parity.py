@@ -33,7 +33,7 @@ def _run_both(orc, ctx, ds_or_tuple, skip=False, raw=False, sub_batch=0, variant
         lineages, ref_off, ref_codes, q_off, q_codes = ds.ref_lineages, ds.ref_off, ds.ref_codes, ds.query_off, ds.query_codes
     seqs = [ref_codes[int(ref_off[i]): int(ref_off[i + 1])] for i in range(len(lineages))]
     ot = orc.Tree.new(lineages, seqs)
-    ht = capi.Tree.new(lineages, ref_off, ref_codes)
+    ht = capi.Tree.new(lineages, ref_off, ref_codes, eager_kmer_map=variant == capi.RTX_HITCOUNT_CSR)  # the CSR variant walks Tree.k_mer_map itself
     ctx.set_option(capi.RTX_OPT_KEEP_CSR, 1 if variant == capi.RTX_HITCOUNT_CSR else 0)
     ctx.set_option(capi.RTX_OPT_HITCOUNT_VARIANT, variant)
     ctx.set_option(capi.RTX_OPT_SUB_BATCH, sub_batch)
@@ -43,6 +43,7 @@ def _run_both(orc, ctx, ds_or_tuple, skip=False, raw=False, sub_batch=0, variant
     o = ot.classify(q_off, q_codes, skip_exact=skip, raw_conf=raw, threads=threads, chunk_size=16, want_counts=True, want_probs=True,
                     want_kmers=True)
     ctx.set_option(capi.RTX_OPT_HITCOUNT_VARIANT, capi.RTX_HITCOUNT_BITROWS)
+    ctx.set_option(capi.RTX_OPT_KEEP_CSR, 0)
     ctx.set_option(capi.RTX_OPT_SUB_BATCH, 0)
     return o, dev, ot, ht
 
@@ -176,6 +177,33 @@ def test_walk_variants_agree(ctx, skip):
     assert len(outs[0].first_ref) >= ds.n_queries
     for o in outs[1:]:
         assert _same_outputs(outs[0], o)
+
+
+def test_index_built_from_sequences_matches_csr_index(ctx):
+    """The device builds its bit rows either from the host's k_mer_map (CSR, tree.rs:41) or -- default, no k_mer_map on the host --
+    from the sorted reference sequences themselves (tree.rs:114-123 windowing on the device): same counts, same results."""
+    ds = synth.generate("small", n_queries=300, measure=False)
+    ht = capi.Tree.new(ds.ref_lineages, ds.ref_off, ds.ref_codes)
+    assert not ht.has_kmer_map
+    eo, eids = ht.exact_batch(ds.query_off, ds.query_codes)
+    ctx.upload_tree(ht)  # sequence path
+    a = ctx.classify(ds.query_off, ds.query_codes, eo, eids, taps=("counts", "hist", "kmers"))
+    bytes_seq = ctx.index_bytes
+    ht.build_kmer_map()
+    assert ht.has_kmer_map
+    ctx.upload_tree(ht)  # CSR path
+    b = ctx.classify(ds.query_off, ds.query_codes, eo, eids, taps=("counts", "hist", "kmers"))
+    assert _same_outputs(a, b)
+    assert np.array_equal(a.counts, b.counts) and np.array_equal(a.hist, b.hist) and np.array_equal(a.n_kmers, b.n_kmers)
+    assert bytes_seq == ctx.index_bytes
+    # reference shard of the same tree: rows restricted to the k-mers present in the shard, either way
+    N = ht.num_tips
+    outs = []
+    for t in (capi.Tree.new(ds.ref_lineages, ds.ref_off, ds.ref_codes), ht):
+        ctx.upload_tree(t, (N // 3, 2 * N // 3))
+        outs.append(ctx.classify(ds.query_off, ds.query_codes, eo, eids, taps=("counts", "hist")))
+    assert np.array_equal(outs[0].counts, outs[1].counts) and np.array_equal(outs[0].hist, outs[1].hist)
+    assert np.array_equal(outs[0].counts, a.counts[:, N // 3: 2 * N // 3])
 
 
 def test_pipelined_batch_matches_serial(ctx):

@@ -195,3 +195,22 @@ def test_cli_exit_codes_without_gpu(tmp_path):
         fasta = os.path.join(ROOT, "tests", "golden", "diptera_sample.fasta")
         r = subprocess.run([_build.CLI_BIN, "-d", fasta, "-i", fasta, "-o", str(tmp_path / "o2")], capture_output=True, text=True)
         assert r.returncode == 75 and "no CPU fallback" in r.stderr
+
+
+def test_kmer_map_is_lazy_and_identical_to_the_oracles():
+    """Tree.k_mer_map (tree.rs:41) is materialised on first use; content = the oracle's (parser.rs:166-217 style check on synthetic data)."""
+    from oracle import oracle as orc
+    from raxtax_b200 import synth
+
+    ds = synth.generate("tiny", measure=False)
+    ht = capi.Tree.new(ds.ref_lineages, ds.ref_off, ds.ref_codes)
+    assert not ht.has_kmer_map
+    off, ids = ht.csr()
+    assert ht.has_kmer_map
+    ot = orc.Tree.new(ds.ref_lineages, [ds.ref_seq(i) for i in range(ds.n_refs)])
+    ooff, oids = ot.csr()
+    assert np.array_equal(off, ooff) and np.array_equal(ids, oids)
+    eager = capi.Tree.new(ds.ref_lineages, ds.ref_off, ds.ref_codes, eager_kmer_map=True)
+    assert eager.has_kmer_map
+    eoff, eids = eager.csr()
+    assert np.array_equal(off, eoff) and np.array_equal(ids, eids)
