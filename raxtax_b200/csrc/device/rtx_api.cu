@@ -46,6 +46,7 @@ struct rtx_ctx {
     IndexView ix{};
     u32 n_rows = 0;
     u64 index_bytes = 0;
+    u64 mem_free_after_index = 8ull << 30;
     DevBuf d_bitrows, d_rowmap, d_present, d_csr_off, d_csr_ids, d_node_lo, d_node_hi, d_node_type, d_child_first, d_child_count,
         d_node_blo, d_node_bhi, d_bnd_after, d_bnd_rank, d_ref_levels, d_lnfact, d_recs;
     // batch
@@ -617,6 +618,13 @@ RTX_API int rtx_index_upload(rtx_ctx* ctx, const rtx_index_desc* d) {
     ix.ref_levels = ctx->d_ref_levels.as<u8>();
     ctx->n_rows = n_rows;
     ctx->index_bytes = bytes;
+    {
+        DevBuf* scratch[] = {&ctx->d_counts, &ctx->d_counts1, &ctx->d_preb, &ctx->d_preb1, &ctx->d_segoff, &ctx->d_segoff1, &ctx->d_ptab, &ctx->d_ptab1, &ctx->d_cbuf};
+        for (DevBuf* b : scratch) b->release();  // sized for the previous index
+        size_t mem_free = 0, mem_total = 0;
+        if (cudaMemGetInfo(&mem_free, &mem_total) != cudaSuccess) mem_free = 8ull << 30;
+        ctx->mem_free_after_index = mem_free;
+    }
     ctx->has_index = true;
     return RTX_OK;
 }
@@ -746,9 +754,17 @@ RTX_API int rtx_batch_upload(rtx_ctx* ctx, const rtx_batch* batch) {
         if (rc) return rc;
     }
 
-    // sub-batch: bound the per-query count vectors to ~2 GiB
+    // sub-batch: the per-query scratch (count vector, boundary prefixes, segment offsets, P(m) table) of one sub-batch may take a
+    // quarter of the memory that is free now, at most 48 GB and at least 2 GiB -- large sub-batches amortise the launch tails of
+    // the walk and probability kernels (C3: 1 069 queries per sub-batch at the old fixed 2 GiB, ~6 000 now)
     const u64 per_query = ctx->ix.n_pad * 2;
-    u64 sb = ctx->sub_batch_opt ? (u64)ctx->sub_batch_opt : std::max<u64>(1, (2ull << 30) / per_query);
+    u64 sb = (u64)ctx->sub_batch_opt;
+    if (!sb) {
+        const u64 mem_free = ctx->mem_free_after_index;  // sampled once per index upload (cudaMemGetInfo costs ~1 ms per call)
+        const u64 budget = std::min<u64>(std::max<u64>(mem_free / 4, 2ull << 30), 48ull << 30);
+        const u64 scratch_per_query = per_query + ((u64)round_up(ctx->ix.n_bnd, 4) + ctx->ix.n_pad / kPrefixSeg + 4 + hstride) * 8;
+        sb = std::max<u64>(1, budget / scratch_per_query);
+    }
     const bool may_pipe = ctx->pipeline_opt && ctx->sv.n_shards <= 1;
     if (!ctx->sub_batch_opt && may_pipe && nq >= 4096) sb = std::min<u64>(sb, std::max<u64>(1024, (nq + 3) / 4));  // >= 4 pipeline stages
     sb = std::min<u64>(std::min<u64>(sb, nq), 65535);
