@@ -897,12 +897,15 @@ static cudaError_t launch_hitcount_group(rtx_ctx* c, int q_base, int qb, int G) 
     n_chunks = std::max(1, std::min(n_chunks, 4096));
     const u32 chunk_rows = (c->n_rows + n_chunks - 1) / n_chunks + 1;
     const size_t smem = (size_t)G * (ks + hs) * 4 + (size_t)G * n_chunks * 2 + 16;
-    cudaError_t e = cudaFuncSetAttribute(hitcount_group_kernel<V, NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
     dim3 grid((qb + G - 1) / G, groups);
-    hitcount_group_kernel<V, NP><<<grid, G * 32, smem, c->cur_stream>>>(c->ix, c->bv, c->cur_counts, q_base, qb, tiles_per_cta, n_tiles,
-                                                                   chunk_rows, n_chunks);
-    return cudaGetLastError();
+    auto go = [&](auto kernel) -> cudaError_t {
+        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        kernel<<<grid, G * 32, smem, c->cur_stream>>>(c->ix, c->bv, c->cur_counts, q_base, qb, tiles_per_cta, n_tiles, chunk_rows, n_chunks);
+        return cudaGetLastError();
+    };
+    if (n_chunks > 1) return go(hitcount_group_kernel<V, NP, true, kHitGroupMaxThreads, 1>);
+    return go(hitcount_group_kernel<V, NP, false, kHitGroupMaxThreads, 1>);
 }
 
 static cudaError_t launch_hitcount_tuned(rtx_ctx* c, int q_base, int qb, u32 kmax) {
