@@ -336,10 +336,23 @@ __device__ __forceinline__ const void* row_ptr(const u32* __restrict__ colbase, 
     asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(a) : "r"(rid), "r"(row_bytes), "l"(colbase));
     return reinterpret_cast<const void*>(a);
 }
+// 16 row ids of the list as four broadcast LDS.128 (one data-pipe wavefront per four rows instead of one per row: with 256 B per row
+// and warp the per-row LDS.32 was a third of the L1 data-pipe wavefronts, the unit this kernel saturates first).  j % 16 == 0 and the
+// lists start 16-byte aligned (kstride % 16 == 0).
+__device__ __forceinline__ void row_ids16(u32 (&r)[16], const u32* __restrict__ srow, u32 j) {
+    const uint4* p = reinterpret_cast<const uint4*>(srow + j);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const uint4 t = p[i];
+        r[4 * i] = t.x, r[4 * i + 1] = t.y, r[4 * i + 2] = t.z, r[4 * i + 3] = t.w;
+    }
+}
 template <int V, typename vec_t>
 __device__ __forceinline__ void load16(vec_t (&x)[16], const u32* __restrict__ colbase, const u32* __restrict__ srow, u32 j, u32 row_bytes) {
+    u32 r[16];
+    row_ids16(r, srow, j);
 #pragma unroll
-    for (int i = 0; i < 16; ++i) x[i] = ldg_stream(reinterpret_cast<const vec_t*>(row_ptr(colbase, srow[j + i], row_bytes)));
+    for (int i = 0; i < 16; ++i) x[i] = ldg_stream(reinterpret_cast<const vec_t*>(row_ptr(colbase, r[i], row_bytes)));
 }
 template <int V, int NP, typename vec_t>
 __device__ __forceinline__ void fold16(u32 (&pl)[V][NP], const vec_t (&x)[16]) {
@@ -495,8 +508,10 @@ __device__ __forceinline__ uint4 ldg_l1(const uint4* p) {
 }
 template <int V, typename vec_t>
 __device__ __forceinline__ void load16_l1(vec_t (&x)[16], const u32* __restrict__ colbase, const u32* __restrict__ srow, u32 j, u32 row_bytes) {
+    u32 r[16];
+    row_ids16(r, srow, j);
 #pragma unroll
-    for (int i = 0; i < 16; ++i) x[i] = ldg_l1(reinterpret_cast<const vec_t*>(row_ptr(colbase, srow[j + i], row_bytes)));
+    for (int i = 0; i < 16; ++i) x[i] = ldg_l1(reinterpret_cast<const vec_t*>(reinterpret_cast<const char*>(colbase) + (u64)r[i] * 512u));
 }
 
 constexpr int kHitGroupMaxThreads = 512;
@@ -520,14 +535,17 @@ __global__ void __launch_bounds__(MAX_THREADS, CTAS_PER_SM)
     const u32 n = valid ? b.nrows[q] : 0u;  // padded to a multiple of 16 with the all-zero row 0
     const u32 nbins = valid ? (u32)b.K[q] + 1u : 0u;
     const u32* __restrict__ qrows = b.rows + (size_t)q * b.kstride;
-    for (u32 i = lane; i < n; i += 32) srow[i] = qrows[i];
+    // staged as row offsets in 512-byte units (rows are padded to 128 words), so that the address of a row's slice is ONE
+    // IMAD.WIDE.U32 with an immediate multiplier (with the row size in a uniform register ptxas emits IMAD.WIDE + IADD3 + IMAD.X)
+    const u32 row_units = ix.row_words >> 7;
+    for (u32 i = lane; i < n; i += 32) srow[i] = qrows[i] * row_units;
     for (u32 i = lane; i < nbins; i += 32) shist[i] = 0;
     __syncwarp();
     // chunk c holds the rows with id in [c * chunk_rows, (c + 1) * chunk_rows); cpos[c] = list position where it ends
     for (int c = lane; LOCKSTEP && c < n_chunks; c += 32) {
         u32 lo = 0, hi = n;
         if (c < n_chunks - 1) {
-            const u32 bound = (u32)(c + 1) * chunk_rows;
+            const u32 bound = (u32)(c + 1) * chunk_rows * row_units;  // the staged list holds scaled ids
             while (lo < hi) {
                 const u32 mid = (lo + hi) >> 1;
                 const u32 x = srow[mid];
@@ -727,6 +745,9 @@ struct ProbScratch {
     size_t preb_stride;  //   to the start of the 512-reference segment the boundary belongs to
     double* segoff;      // [sub-batch queries][segoff_stride] prefix sum at the start of every 512-reference segment
     size_t segoff_stride;
+    u32 seg_aux_off;     // per query, behind the segment offsets (in doubles): u32 aux[] = { m_min, 0, skip bitmap words ... }
+                         //   m_min (K3 -> K4): counts below it carry < kMassCut of the probability mass altogether and are taken as 0
+                         //   skip bit s (K4 -> walk): no reference of segment s reaches m_min; its boundary prefixes were not written
     double* ptab;        // [sub-batch queries][hstride] normalised P(m), direct-indexed by count (K3 -> K4)
     int nprod;           // kProbWarps: one partial prod array per warp; 1: a single array updated with shared-memory atomics
     int lf_smem;         // 1: ln n! staged in shared memory, 0: read from HBM/L2 (very long queries)
@@ -771,9 +792,17 @@ struct __align__(16) NodeRec {
 };
 
 // confidence of a node = sum of the normalised probabilities of its references (lineage.rs:114-117)
-__device__ __forceinline__ double node_conf(const double* __restrict__ preb, const double* __restrict__ segoff, const NodeRec& r) {
-    return (segoff[r.shi] - segoff[r.slo]) + (preb[r.bhi] - preb[r.blo]);
+// Boundaries inside a skipped segment (see ProbScratch::seg_aux_off) sit at relative prefix 0; their preb slots hold stale data.
+__device__ __forceinline__ double node_conf(const double* __restrict__ preb, const double* __restrict__ segoff, const u32* __restrict__ skipw,
+                                            const NodeRec& r) {
+    const double ph = preb[r.bhi], pl = preb[r.blo];  // both loads are issued before the bitmap words are known
+    const bool sh = (skipw[r.shi >> 5] >> (r.shi & 31)) & 1u, sl = (skipw[r.slo >> 5] >> (r.slo & 31)) & 1u;
+    return (segoff[r.shi] - segoff[r.slo]) + ((sh ? 0.0 : ph) - (sl ? 0.0 : pl));
 }
+__device__ __forceinline__ const u32* seg_aux(const ProbScratch& sc, int ql) {
+    return reinterpret_cast<const u32*>(sc.segoff + (size_t)ql * sc.segoff_stride + sc.seg_aux_off);
+}
+constexpr double kMassCut = 1e-25;
 
 // ln pmf_m(i) = ln C(m+i-1,i) + ln C(K-m+t-i-1,t-i) - ln C(K+t-1,t): closed form of the iterative sums of prob.rs:136-166.
 // cm = ln (m-1)! + ln (K-m-1)! + T collects the terms that do not depend on i.   Requires 1 <= m <= K-1, i <= t.
@@ -1051,6 +1080,27 @@ __global__ void __launch_bounds__(kProbThreads, 4)
             pool.global_sig[q] = sqrt(gsum);
             pool.status[q] = bad_sum ? kQProbSumZero : kQOk;
         }
+        // m_min: the references whose count lies below it hold, all together, no more than kMassCut of the probability mass
+        // (the histogram tells without touching the count vector); K4 takes them as exactly 0 -- 1e-9 of the 1.1e-16 rounding
+        // noise the reference's own sequential prefix sums carry (lineage.rs:66-71)
+        if (warp == 0) {
+            double run = 0.0;
+            u32 mmin = 0;  // 0 keeps every reference (also the answer when the sum is not a number)
+            if (!bad_sum) {
+                for (u32 base = 0; base < D; base += 32) {
+                    const u32 d = base + lane;
+                    const double v = d < D ? (double)sm.dh[d] * (sm.Pd[d] / S) : 0.0;
+                    const double inc = warp_scan_incl(v, lane) + run;
+                    const u32 hit = __ballot_sync(kFullMask, d < D && inc > kMassCut);
+                    if (hit) {
+                        mmin = sm.dm[base + (u32)__ffs(hit) - 1u];
+                        break;
+                    }
+                    run = __shfl_sync(kFullMask, inc, 31);
+                }
+            }
+            if (lane == 0) const_cast<u32*>(seg_aux(sc, ql))[0] = mmin;
+        }
     }
 }
 
@@ -1102,6 +1152,7 @@ __global__ void __launch_bounds__(kPrefixThreads)
     double* Ptab = reinterpret_cast<double*>(xsm_raw);
     double* segtot = Ptab + b.hstride;
     double* stage = segtot + ((n_seg + 1u) & ~1u) + (size_t)warp * kPrefixSeg;
+    double* stage_end = segtot + ((n_seg + 1u) & ~1u) + (size_t)kPrefixWarps * kPrefixSeg;  // u32 skip bitmap words behind the staging area
     const u32 K = b.K[q];
     const double* __restrict__ gp = sc.ptab + (size_t)ql * b.hstride;
     for (u32 m = tid; m <= K; m += kPrefixThreads) Ptab[m] = gp[m];
@@ -1109,6 +1160,11 @@ __global__ void __launch_bounds__(kPrefixThreads)
     const u16* __restrict__ qcounts = counts + (size_t)ql * ix.n_pad;
     double* __restrict__ preb = sc.preb + (size_t)ql * sc.preb_stride;
     const u64 Ns = ix.shard_refs;
+    u32* __restrict__ aux = const_cast<u32*>(seg_aux(sc, ql));
+    const u32 mmin2 = aux[0] * 0x10001u;  // m_min in both half-words
+    u32* skipw_s = reinterpret_cast<u32*>(stage_end);
+    for (u32 i = tid; i < (n_seg + 31u) / 32u; i += kPrefixThreads) skipw_s[i] = 0u;
+    __syncthreads();
 
     uint4 c0 = make_uint4(0, 0, 0, 0), c1 = c0;
     if ((u32)warp < n_seg) {
@@ -1125,6 +1181,16 @@ __global__ void __launch_bounds__(kPrefixThreads)
             const u64 rn = r0 + (u64)kPrefixWarps * kPrefixSeg;
             c0 = *reinterpret_cast<const uint4*>(qcounts + rn);
             c1 = *reinterpret_cast<const uint4*>(qcounts + rn + 8);
+        }
+        {   // does any reference of the segment reach m_min?  (padding references have count 0; m_min == 0 keeps everything)
+            const u32 mx = __vmaxu2(__vmaxu2(__vmaxu2(x0.x, x0.y), __vmaxu2(x0.z, x0.w)), __vmaxu2(__vmaxu2(x1.x, x1.y), __vmaxu2(x1.z, x1.w)));
+            if (!__any_sync(kFullMask, __vcmpgeu2(mx, mmin2) != 0u)) {
+                if (lane == 0) {
+                    segtot[s] = 0.0;
+                    atomicOr(&skipw_s[s >> 5], 1u << (s & 31));
+                }
+                continue;
+            }
         }
         double v[kPrefixPer];
         prefix_gather(v, Ptab, x0, x1, r0, Ns);
@@ -1168,6 +1234,7 @@ __global__ void __launch_bounds__(kPrefixThreads)
         }
     }
     if (tid == 0) preb[0] = 0.0;
+    for (u32 i = tid; i < (n_seg + 31u) / 32u; i += kPrefixThreads) aux[2 + i] = skipw_s[i];
 }
 
 // =========================================================================================================
@@ -1207,6 +1274,7 @@ __global__ void __launch_bounds__(128) shard_records_kernel(IndexView ix, const 
     const int ql = (int)(w / sv.n_strad), j = (int)(w % sv.n_strad);
     const double* __restrict__ preb = sc.preb + (size_t)ql * sc.preb_stride;
     const double* __restrict__ segoff = sc.segoff + (size_t)ql * sc.segoff_stride;
+    const u32* __restrict__ skipw = seg_aux(sc, ql) + 2;
     const u32 node = sv.strad_nodes[j];
     const NodeRec nr = recs[node];
     const u32 cf = nr.child_first, cc = nr.cc_type & 0x3FFFFFFFu;
@@ -1216,7 +1284,7 @@ __global__ void __launch_bounds__(128) shard_records_kernel(IndexView ix, const 
         const u32 ci = cb + lane;
         if (ci < cc && sv.strad_of_node[cf + ci] < 0 && node_inside(ix, cf + ci)) {
             const NodeRec cr = recs[cf + ci];
-            const double v = node_conf(preb, segoff, cr);
+            const double v = node_conf(preb, segoff, skipw, cr);
             best = fmax(best, v);
             n_sig += ((u32)round(v * 100.0) != 0);
         }
@@ -1233,7 +1301,7 @@ __global__ void __launch_bounds__(128) shard_records_kernel(IndexView ix, const 
             const u32 ci = cb + lane;
             if (ci < cc && sv.strad_of_node[cf + ci] < 0 && node_inside(ix, cf + ci)) {
                 const NodeRec cr = recs[cf + ci];
-                if (node_conf(preb, segoff, cr) >= thr) besti = cf + ci;
+                if (node_conf(preb, segoff, skipw, cr) >= thr) besti = cf + ci;
             }
         }
 #pragma unroll
@@ -1241,7 +1309,7 @@ __global__ void __launch_bounds__(128) shard_records_kernel(IndexView ix, const 
     }
     if (lane == 0) {
         ShardRec r;
-        r.mass = node_conf(preb, segoff, nr);
+        r.mass = node_conf(preb, segoff, skipw, nr);
         r.best = best;
         r.best_child = besti;
         r.n_sig = n_sig;
@@ -1352,6 +1420,7 @@ __global__ void __launch_bounds__(kWalkWarps * 32)
     const double Nd = (double)ix.n_refs;
     const double* __restrict__ preb = sc.preb + (size_t)ql * sc.preb_stride;
     const double* __restrict__ segoff = sc.segoff + (size_t)ql * sc.segoff_stride;
+    const u32* __restrict__ skipw = seg_aux(sc, ql) + 2;
     int status = retry_only ? (int)kQOk : pool.status[q];
 
     u32 n_res = 0;
@@ -1383,10 +1452,10 @@ __global__ void __launch_bounds__(kWalkWarps * 32)
                     if (SH) {
                         const int sj = sv.strad_of_node[cf + ci];
                         if (sj >= 0) k = sv.sk[(size_t)ql * sv.n_strad + sj];  // combined over the ranks
-                        else if (node_inside(ix, cf + ci)) k = (u32)round((node_conf(preb, segoff, cr)) * 100.0);
+                        else if (node_inside(ix, cf + ci)) k = (u32)round((node_conf(preb, segoff, skipw, cr)) * 100.0);
                         // children inside another shard are walked by their owner
                     } else {
-                        k = (u32)round((node_conf(preb, segoff, cr)) * 100.0);  // f64::round, half away from zero (lineage.rs:129)
+                        k = (u32)round((node_conf(preb, segoff, skipw, cr)) * 100.0);  // f64::round, half away from zero (lineage.rs:129)
                     }
                 }
                 const u32 mask = __ballot_sync(kFullMask, k != 0);
@@ -1464,7 +1533,7 @@ __global__ void __launch_bounds__(kWalkWarps * 32)
                             const u32 ci = cb + lane;
                             if (ci < cur_cc) {
                                 const NodeRec cr = recs[cur_cf + ci];
-                                const double v = node_conf(preb, segoff, cr);
+                                const double v = node_conf(preb, segoff, skipw, cr);
                                 if (cb == 0) {
                                     cv0 = v;
                                     cr0 = cr;
@@ -1481,7 +1550,7 @@ __global__ void __launch_bounds__(kWalkWarps * 32)
                             const u32 ci = cb + lane;
                             if (ci < cur_cc) {
                                 const NodeRec cr = recs[cur_cf + ci];
-                                if (node_conf(preb, segoff, cr) >= thr) besti = ci;
+                                if (node_conf(preb, segoff, skipw, cr) >= thr) besti = ci;
                             }
                         }
 #pragma unroll
@@ -1724,6 +1793,7 @@ __global__ void __launch_bounds__(kBfsThreads)
     const double Nd = (double)ix.n_refs;
     const double* __restrict__ preb = sc.preb + (size_t)ql * sc.preb_stride;
     const double* __restrict__ segoff = sc.segoff + (size_t)ql * sc.segoff_stride;
+    const u32* __restrict__ skipw = seg_aux(sc, ql) + 2;
     const u32 lt_mask = (1u << lane) - 1u;
     int status = pool.status[q];
 
@@ -1771,7 +1841,7 @@ __global__ void __launch_bounds__(kBfsThreads)
 #pragma unroll
                 for (int u = 0; u < 2; ++u) {
                     const u32 idx = base + u * 32 + lane;
-                    kk[u] = (idx < total) ? (u32)round(node_conf(preb, segoff, cr[u]) * 100.0) : 0u;  // f64::round (lineage.rs:129)
+                    kk[u] = (idx < total) ? (u32)round(node_conf(preb, segoff, skipw, cr[u]) * 100.0) : 0u;  // f64::round (lineage.rs:129)
                 }
 #pragma unroll
                 for (int u = 0; u < 2; ++u) {
@@ -1849,7 +1919,7 @@ __global__ void __launch_bounds__(kBfsThreads)
             for (u32 idx = tid; idx < total; idx += kBfsThreads) {  // pass A: the largest child confidence of every chain head
                 const u32 c = bfs_owner(w.fr_off, n_ch, idx);
                 const NodeRec cr = recs[w.ent_cf[cur[c]] + (idx - w.fr_off[c])];
-                const double v = fmax(node_conf(preb, segoff, cr), 0.0);
+                const double v = fmax(node_conf(preb, segoff, skipw, cr), 0.0);
                 atomicMax(&w.best[c], (unsigned long long)__double_as_longlong(v));  // non-negative doubles order like their bits
             }
             __syncthreads();
@@ -1857,7 +1927,7 @@ __global__ void __launch_bounds__(kBfsThreads)
                 const u32 c = bfs_owner(w.fr_off, n_ch, idx);
                 const u32 ci = idx - w.fr_off[c];
                 const NodeRec cr = recs[w.ent_cf[cur[c]] + ci];
-                const double v = fmax(node_conf(preb, segoff, cr), 0.0);
+                const double v = fmax(node_conf(preb, segoff, skipw, cr), 0.0);
                 const double bestv = __longlong_as_double((long long)w.best[c]);
                 if (v >= bestv - fabs(bestv) * 1e-12) atomicMax(&w.besti[c], ci);
             }

@@ -762,7 +762,7 @@ RTX_API int rtx_batch_upload(rtx_ctx* ctx, const rtx_batch* batch) {
     if (!sb) {
         const u64 mem_free = ctx->mem_free_after_index;  // sampled once per index upload (cudaMemGetInfo costs ~1 ms per call)
         const u64 budget = std::min<u64>(std::max<u64>(mem_free / 4, 2ull << 30), 48ull << 30);
-        const u64 scratch_per_query = per_query + ((u64)round_up(ctx->ix.n_bnd, 4) + ctx->ix.n_pad / kPrefixSeg + 4 + hstride) * 8;
+        const u64 scratch_per_query = per_query + ((u64)round_up(ctx->ix.n_bnd, 4) + ctx->ix.n_pad / kPrefixSeg + ctx->ix.n_pad / kPrefixSeg / 64 + 8 + hstride) * 8;
         sb = std::max<u64>(1, budget / scratch_per_query);
     }
     const bool may_pipe = ctx->pipeline_opt && ctx->sv.n_shards <= 1;
@@ -781,7 +781,7 @@ RTX_API int rtx_batch_upload(rtx_ctx* ctx, const rtx_batch* batch) {
     if (occ < 1) return set_err(ctx, RTX_ERR_CUDA, "prob_table_kernel does not fit on an SM");
     {
         const size_t n_seg = ctx->ix.n_pad / kPrefixSeg;
-        ctx->prefix_smem = ((size_t)hstride + ((n_seg + 1) & ~(size_t)1) + (size_t)kPrefixWarps * kPrefixSeg) * 8;
+        ctx->prefix_smem = ((size_t)hstride + ((n_seg + 1) & ~(size_t)1) + (size_t)kPrefixWarps * kPrefixSeg) * 8 + ((n_seg + 31) / 32) * 4 + 16;
         if (ctx->prefix_smem > 220 * 1024)
             return set_err(ctx, RTX_ERR_UNSUPPORTED, "reference shard too large for the prefix kernel's segment table (more than ~11 M references per GPU): shard the references");
     }
@@ -804,7 +804,11 @@ RTX_API int rtx_batch_upload(rtx_ctx* ctx, const rtx_batch* batch) {
     ctx->sc.ptab = ctx->d_ptab.as<double>();
     ctx->sc.cbuf = ctx->d_cbuf.as<double>();
     ctx->sc.preb = ctx->d_preb.as<double>();
-    ctx->sc.segoff_stride = round_up((u32)(ctx->ix.n_pad / kPrefixSeg), 4);
+    {   // per query: n_seg segment offsets | u32 aux[2 + n_seg/32] (m_min, skip bitmap; ProbScratch::seg_aux_off)
+        const u32 n_seg = (u32)(ctx->ix.n_pad / kPrefixSeg);
+        ctx->sc.seg_aux_off = round_up(n_seg, 2);
+        ctx->sc.segoff_stride = round_up(ctx->sc.seg_aux_off + 1 + ((n_seg + 31) / 32 + 1) / 2, 4);
+    }
     CU(ctx->d_segoff.ensure((size_t)sb * ctx->sc.segoff_stride * 8));
     ctx->sc.segoff = ctx->d_segoff.as<double>();
     ctx->sc1 = ctx->sc;
