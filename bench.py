@@ -257,14 +257,16 @@ def main():
     ctx.set_option(capi.RTX_OPT_SUB_BATCH, args.sub_batch)
 
     # ---- end-to-end leg (host buffers, H2D + kernels + D2H per step) ---------------------------------------------
+    # inputs and result arrays page-locked (rtx_host_alloc), reused from step to step as a long-running caller would
+    res_buf = ctx.pinned_results(q_per_gpu, max(q_per_gpu * 8 + 64, n_results + n_results // 4 + 64))
     for _ in range(2):
-        ctx.classify(off_p, codes_p, eo_p, eids_p)
+        ctx.classify(off_p, codes_p, eo_p, eids_p, out=res_buf)
     ctx.profile_reset()
     barrier()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        out = ctx.classify(off_p, codes_p, eo_p, eids_p)
+        out = ctx.classify(off_p, codes_p, eo_p, eids_p, out=res_buf)
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     barrier()
     prof_e2e = ctx.profile()

@@ -76,6 +76,11 @@ int rtx_ctx_set_option(rtx_ctx* ctx, int option, int64_t value);
 /* the CUDA stream (cudaStream_t) all of this context's work is issued on; lets a caller record its own events */
 void* rtx_ctx_stream(rtx_ctx* ctx);
 int rtx_ctx_synchronize(rtx_ctx* ctx);
+/* Page-locked host memory for batch inputs and result arrays.  Optional: every call accepts ordinary memory (results then pass
+ * through the context's own pinned staging arena and one memcpy); buffers from rtx_host_alloc -- or registered by the caller with
+ * cudaHostRegister -- are written by DMA directly.  No counterpart in the reference (its results are owned Strings, raxtax.rs:85-88). */
+int rtx_host_alloc(size_t bytes, void** out);
+int rtx_host_free(void* p);
 
 /* ---- reference index ("Tree", src/tree.rs:36-43) --------------------------------------------------------
  * Flattened form of what Tree::new (tree.rs:47-140) builds:

@@ -28,7 +28,7 @@ KERNEL_NAMES = ["kmers", "hitcount", "fixup", "prob", "index", "walk", "prefix"]
 # every symbol include/raxtax_b200.h declares
 DEVICE_SYMBOLS = [
     "rtx_abi_version", "rtx_ctx_create", "rtx_ctx_destroy", "rtx_last_error", "rtx_ctx_set_option", "rtx_ctx_stream",
-    "rtx_ctx_synchronize", "rtx_index_upload", "rtx_index_n_refs", "rtx_index_shard_refs", "rtx_index_max_levels", "rtx_batch_sub_batch",
+    "rtx_ctx_synchronize", "rtx_host_alloc", "rtx_host_free", "rtx_index_upload", "rtx_index_n_refs", "rtx_index_shard_refs", "rtx_index_max_levels", "rtx_batch_sub_batch",
     "rtx_index_device_bytes", "rtx_classify_batch", "rtx_batch_upload", "rtx_batch_run", "rtx_batch_download",
     "rtx_shard_phase1", "rtx_shard_hist_buffer", "rtx_shard_phase2", "rtx_shard_records_buffers", "rtx_shard_phase3",
     "rtx_profile_reset", "rtx_profile_get",
@@ -101,6 +101,8 @@ def device_lib():
     L.rtx_ctx_stream.restype = C.c_void_p
     L.rtx_ctx_stream.argtypes = [C.c_void_p]
     L.rtx_ctx_synchronize.argtypes = [C.c_void_p]
+    L.rtx_host_alloc.argtypes = [C.c_size_t, C.POINTER(C.c_void_p)]
+    L.rtx_host_free.argtypes = [C.c_void_p]
     L.rtx_index_upload.argtypes = [C.c_void_p, C.POINTER(IndexDesc)]
     for f in ("rtx_index_n_refs", "rtx_index_shard_refs", "rtx_index_device_bytes"):
         getattr(L, f).restype = C.c_uint64
@@ -217,11 +219,15 @@ class Context:
         if rc != 0:
             raise RtxError(rc, L.rtx_last_error(None).decode())
         self._h = h
+        self._pinned = []
         self._keep = []
         self.device = device
 
     def close(self):
         if getattr(self, "_h", None):
+            for p in getattr(self, "_pinned", []):
+                device_lib().rtx_host_free(p)
+            self._pinned = []
             device_lib().rtx_ctx_destroy(self._h)
             self._h = None
 
@@ -326,11 +332,36 @@ class Context:
         b.flags = flags
         return b, keep
 
-    def _alloc_results(self, nq, cap, max_len, taps):
+    def pinned_array(self, shape, dtype) -> np.ndarray:
+        """numpy array over rtx_host_alloc memory (freed with the context): results land in it by DMA, no staging copy."""
+        n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        p = C.c_void_p()
+        self._check(device_lib().rtx_host_alloc(max(n, 1), C.byref(p)))
+        self._pinned.append(p)
+        buf = (C.c_char * max(n, 1)).from_address(p.value)
+        return np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+
+    def pinned_results(self, nq, cap=0):
+        """Reusable page-locked result buffers for classify(..., out=...) / batch_download(out=...): (ClassifyOutput, capacity)."""
+        ML = max(self.max_levels, 1)
+        cap = cap or nq * 8 + 64
+        pa = self.pinned_array
+        return ClassifyOutput(pa(nq, np.uint16), pa(nq + 1, np.uint32), pa(nq, np.float64), pa(cap, np.uint32), pa(cap, np.uint8),
+                              pa((cap, ML), np.float64), pa(cap, np.float64)), cap
+
+    def _alloc_results(self, nq, cap, max_len, taps, reuse=None):
         ML = max(self.max_levels, 1)
         kmax = max(max_len - 7, 0)
-        out = ClassifyOutput(np.zeros(nq, np.uint16), np.zeros(nq + 1, np.uint32), np.zeros(nq, np.float64), np.empty(cap, np.uint32),
-                             np.empty(cap, np.uint8), np.empty((cap, ML), np.float64), np.empty(cap, np.float64))
+        if reuse is not None:  # caller-owned (pinned) buffers; the views handed back alias them until the next call
+            buf, bcap = reuse
+            if len(buf.n_kmers) < nq:
+                raise ValueError("pinned result buffers hold fewer queries than this batch")
+            out = ClassifyOutput(buf.n_kmers[:nq], buf.result_begin[:nq + 1], buf.global_signal[:nq], buf.first_ref, buf.n_levels,
+                                 buf.confidence, buf.local_signal)
+            cap = bcap
+        else:
+            out = ClassifyOutput(np.zeros(nq, np.uint16), np.zeros(nq + 1, np.uint32), np.zeros(nq, np.float64), np.empty(cap, np.uint32),
+                                 np.empty(cap, np.uint8), np.empty((cap, ML), np.float64), np.empty(cap, np.float64))
         r = ResultsStruct()
         r.n_kmers = _ptr(out.n_kmers, C.c_uint16)
         r.result_begin = _ptr(out.result_begin, C.c_uint32)
@@ -363,8 +394,8 @@ class Context:
         out.confidence, out.local_signal = out.confidence[:n], out.local_signal[:n]
         return out
 
-    def classify(self, seq_off, codes, exact_off=None, exact_ids=None, skip_exact=False, raw_conf=False, taps=()) -> ClassifyOutput:
-        """rtx_classify_batch: H2D + kernels + D2H in one call."""
+    def classify(self, seq_off, codes, exact_off=None, exact_ids=None, skip_exact=False, raw_conf=False, taps=(), out=None) -> ClassifyOutput:
+        """rtx_classify_batch: H2D + kernels + D2H in one call.  out = pinned_results(...) reuses page-locked result buffers."""
         L = device_lib()
         flags = (RTX_SKIP_EXACT_MATCHES if skip_exact else 0) | (RTX_RAW_CONFIDENCE if raw_conf else 0)
         b, keep = self._make_batch(seq_off, codes, exact_off, exact_ids, flags)
@@ -372,9 +403,12 @@ class Context:
         so = keep[0]
         max_len = int((so[1:] - so[:-1]).max()) if nq else 0
         cap = max(nq * 8 + 64, getattr(self, "_cap_hint", 0))
+        reuse = out
         while True:
-            out, r = self._alloc_results(nq, cap, max_len, taps)
+            out, r = self._alloc_results(nq, cap, max_len, taps, reuse)
             rc = L.rtx_classify_batch(self._h, C.byref(b), C.byref(r))
+            if rc == RTX_ERR_INVALID and r.n_results > r.result_capacity and reuse is not None:
+                raise ValueError(f"pinned result buffers too small: {int(r.n_results)} result lines, capacity {int(r.result_capacity)}")
             if rc == RTX_ERR_INVALID and r.n_results > cap:
                 cap = int(r.n_results) + int(r.n_results) // 4 + 64
                 self._cap_hint = cap

@@ -1687,6 +1687,52 @@ __global__ void __launch_bounds__(kWalkWarps * 32)
 }
 
 // =========================================================================================================
+// Result ordering.  The walk kernels append to the pool in completion order (one atomic bump per query); the two kernels
+// below put the lines of a batch into query order on the device, so that the download is one contiguous copy per array
+// and the host never touches individual results.
+// =========================================================================================================
+constexpr int kScanThreads = 1024;
+// ord_begin[q] = sum of res_cnt[0..q), ord_begin[nq] = total.  Single CTA (nq <= a few 100 k: ~10 us).
+__global__ void __launch_bounds__(kScanThreads) result_scan_kernel(ResultPool pool, u32* __restrict__ ord_begin, u32 nq) {
+    __shared__ u32 wtot[kScanThreads / 32];
+    const u32 tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const u32 per = (nq + kScanThreads - 1) / kScanThreads;
+    const u32 lo = min(nq, tid * per), hi = min(nq, lo + per);
+    u32 loc = 0;
+    for (u32 q = lo; q < hi; ++q) loc += pool.res_cnt[q];
+    const u32 inc = warp_scan_incl(loc, (int)lane);
+    if (lane == 31) wtot[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        const u32 v = wtot[lane];
+        const u32 vi = warp_scan_incl(v, (int)lane);
+        wtot[lane] = vi - v;
+    }
+    __syncthreads();
+    u32 run = wtot[warp] + inc - loc;
+    for (u32 q = lo; q < hi; ++q) {
+        ord_begin[q] = run;
+        run += pool.res_cnt[q];
+    }
+    if (tid == kScanThreads - 1) ord_begin[nq] = run;
+}
+// one warp per query; queries whose lines fell off the end of the pool (kQPoolOverflow: the batch is re-run) are left out
+__global__ void __launch_bounds__(256) result_gather_kernel(ResultPool pool, const u32* __restrict__ ord_begin, u32* __restrict__ o_first,
+                                                            u8* __restrict__ o_nlev, double* __restrict__ o_conf, double* __restrict__ o_local,
+                                                            u32 nq, u32 ML) {
+    const u32 q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (q >= nq) return;
+    const u64 src = pool.res_off[q], n = pool.res_cnt[q], dst = ord_begin[q];
+    if (src + n > pool.cap || dst + n > pool.cap) return;
+    for (u32 i = lane; i < n; i += 32) {
+        o_first[dst + i] = pool.first_ref[src + i];
+        o_nlev[dst + i] = pool.n_levels[src + i];
+        o_local[dst + i] = pool.local[src + i];
+    }
+    for (u32 x = lane; x < n * ML; x += 32) o_conf[dst * ML + x] = pool.conf[src * ML + x];
+}
+
+// =========================================================================================================
 // K5 (level-synchronous form, the default for unsharded indexes).  The depth-first walker above follows one chain of
 // dependent loads per 32 children it looks at; taxonomies have nodes with thousands of children, so even a query with a
 // single result line evaluates ~2 500 children (80 dependent round trips), and a query with a flat probability profile

@@ -71,11 +71,16 @@ struct rtx_ctx {
     ShardView sv{};
     int shard_phase = 0;
     DevBuf d_strad_of_node, d_strad_nodes, d_strad_parent, d_send, d_recv, d_sk, d_sany, d_sbest;
-    // host staging
-    std::vector<u32> h_res_off, h_res_cnt, h_nrows, h_pool_first;
-    std::vector<int> h_status;
-    std::vector<u8> h_pool_nlev;
-    std::vector<double> h_pool_conf, h_pool_local;
+    // results in query order (result_scan_kernel / result_gather_kernel)
+    DevBuf d_ord_begin, d_ord_first, d_ord_nlev, d_ord_conf, d_ord_local;
+    // host staging: one pinned arena (device -> arena by DMA, arena -> caller memory by memcpy unless the caller's memory is pinned itself)
+    unsigned char* h_arena = nullptr;
+    size_t h_arena_cap = 0, h_arena_used = 0;
+    struct PendingCopy {
+        void* dst;
+        size_t arena_off, bytes;
+    };
+    std::vector<PendingCopy> h_pending;
     // taps wired by rtx_classify_batch for sub-batched runs
     u16* tap_counts_host = nullptr;
     double* tap_probs_host = nullptr;
@@ -144,6 +149,51 @@ static void drain_events(rtx_ctx* c) {
         cudaEventDestroy(ep.b);
     }
     c->events.clear();
+}
+
+// ---- pinned staging ------------------------------------------------------------------------------------
+static cudaError_t arena_reserve(rtx_ctx* c, size_t bytes) {  // only between downloads: nothing may be in flight into the arena
+    c->h_arena_used = 0;
+    c->h_pending.clear();
+    if (bytes <= c->h_arena_cap) return cudaSuccess;
+    if (c->h_arena) cudaFreeHost(c->h_arena);
+    c->h_arena = nullptr;
+    c->h_arena_cap = 0;
+    const size_t cap = bytes + bytes / 4 + 4096;
+    cudaError_t e = cudaHostAlloc((void**)&c->h_arena, cap, cudaHostAllocDefault);
+    if (e == cudaSuccess) c->h_arena_cap = cap;
+    return e;
+}
+static bool host_ptr_pinned(const void* p) {
+    cudaPointerAttributes a{};
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return a.type == cudaMemoryTypeHost;
+}
+// device -> caller memory: straight DMA when the caller's buffer is pinned, else DMA into the arena and a memcpy after the sync
+static cudaError_t d2h(rtx_ctx* c, void* dst, const void* src, size_t bytes, bool dst_pinned) {
+    if (!bytes) return cudaSuccess;
+    if (dst_pinned) return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, c->stream);
+    const size_t off = (c->h_arena_used + 63) & ~(size_t)63;
+    if (off + bytes > c->h_arena_cap) return cudaErrorMemoryAllocation;
+    c->h_arena_used = off + bytes;
+    c->h_pending.push_back({dst, off, bytes});
+    return cudaMemcpyAsync(c->h_arena + off, src, bytes, cudaMemcpyDeviceToHost, c->stream);
+}
+static void* arena_take(rtx_ctx* c, size_t bytes) {  // arena space the library reads itself
+    const size_t off = (c->h_arena_used + 63) & ~(size_t)63;
+    if (off + bytes > c->h_arena_cap) return nullptr;
+    c->h_arena_used = off + bytes;
+    return c->h_arena + off;
+}
+static cudaError_t d2h_finish(rtx_ctx* c) {
+    cudaError_t e = cudaStreamSynchronize(c->stream);
+    if (e != cudaSuccess) return e;
+    for (auto& pc : c->h_pending) memcpy(pc.dst, c->h_arena + pc.arena_off, pc.bytes);
+    c->h_pending.clear();
+    return cudaSuccess;
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -229,8 +279,10 @@ RTX_API void rtx_ctx_destroy(rtx_ctx* c) {
                       &c->d_K, &c->d_kmers, &c->d_rows, &c->d_nrows, &c->d_hist, &c->d_counts, &c->d_counts1, &c->d_preb1, &c->d_ptab1, &c->d_segoff1, &c->d_pool_first, &c->d_pool_nlev,
                       &c->d_pool_conf, &c->d_pool_local, &c->d_pool_used, &c->d_res_off, &c->d_res_cnt, &c->d_global, &c->d_status,
                       &c->d_hits, &c->d_seq_codes, &c->d_cbuf, &c->d_preb, &c->d_ptab, &c->d_segoff, &c->d_recs, &c->d_strad_of_node, &c->d_strad_nodes, &c->d_strad_parent,
-                      &c->d_send, &c->d_recv, &c->d_sk, &c->d_sany, &c->d_sbest};
+                      &c->d_send, &c->d_recv, &c->d_sk, &c->d_sany, &c->d_sbest, &c->d_ord_begin, &c->d_ord_first, &c->d_ord_nlev,
+                      &c->d_ord_conf, &c->d_ord_local};
     for (DevBuf* b : bufs) b->release();
+    if (c->h_arena) cudaFreeHost(c->h_arena);
     for (int i = 0; i < 2; ++i) {
         if (c->ev_hit[i]) cudaEventDestroy(c->ev_hit[i]);
         if (c->ev_post[i]) cudaEventDestroy(c->ev_post[i]);
@@ -297,6 +349,18 @@ RTX_API int rtx_ctx_synchronize(rtx_ctx* ctx) {
     CU(cudaStreamSynchronize(ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream2));
     return RTX_OK;
+}
+
+RTX_API int rtx_host_alloc(size_t bytes, void** out) {
+    if (!out) return RTX_ERR_INVALID;
+    *out = nullptr;
+    cudaError_t e = cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocDefault);
+    if (e != cudaSuccess) return set_err(nullptr, RTX_ERR_CUDA, std::string("cudaHostAlloc: ") + cudaGetErrorString(e));
+    return RTX_OK;
+}
+RTX_API int rtx_host_free(void* p) {
+    if (!p) return RTX_OK;
+    return cudaFreeHost(p) == cudaSuccess ? RTX_OK : RTX_ERR_CUDA;
 }
 
 RTX_API uint64_t rtx_index_n_refs(const rtx_ctx* c) { return c && c->has_index ? c->ix.n_refs : 0; }
@@ -639,6 +703,10 @@ static int ensure_pool(rtx_ctx* ctx, u64 cap) {
     CU(ctx->d_pool_conf.ensure(cap * ML * 8));
     CU(ctx->d_pool_local.ensure(cap * 8));
     CU(ctx->d_pool_used.ensure(8));
+    CU(ctx->d_ord_first.ensure(cap * 4));
+    CU(ctx->d_ord_nlev.ensure(cap));
+    CU(ctx->d_ord_conf.ensure(cap * ML * 8));
+    CU(ctx->d_ord_local.ensure(cap * 8));
     ctx->pool.first_ref = ctx->d_pool_first.as<u32>();
     ctx->pool.n_levels = ctx->d_pool_nlev.as<u8>();
     ctx->pool.conf = ctx->d_pool_conf.as<double>();
@@ -742,6 +810,7 @@ RTX_API int rtx_batch_upload(rtx_ctx* ctx, const rtx_batch* batch) {
     bv.hist = ctx->d_hist.as<u32>();
     CU(ctx->d_res_off.ensure(nq * 4));
     CU(ctx->d_res_cnt.ensure(nq * 4));
+    CU(ctx->d_ord_begin.ensure(((size_t)nq + 1) * 4));
     CU(ctx->d_global.ensure(nq * 8));
     CU(ctx->d_status.ensure(nq * 4));
     CU(ctx->d_hits.ensure(8));
@@ -967,6 +1036,24 @@ static int launch_prob(rtx_ctx* ctx, int q0, int qb) {
     return RTX_OK;
 }
 
+// the batch's result lines into query order (d_ord_*); part of every run, so that a download is plain copies
+static int order_results(rtx_ctx* ctx) {
+    const u32 nq = ctx->bv.n_queries;
+    {
+        LaunchTimer lt(ctx, RTX_K_WALK);
+        result_scan_kernel<<<1, kScanThreads, 0, ctx->stream>>>(ctx->pool, ctx->d_ord_begin.as<u32>(), nq);
+        CU(cudaGetLastError());
+    }
+    {
+        LaunchTimer lt(ctx, RTX_K_WALK);
+        result_gather_kernel<<<(nq + 7) / 8, 256, 0, ctx->stream>>>(ctx->pool, ctx->d_ord_begin.as<u32>(), ctx->d_ord_first.as<u32>(),
+                                                                    ctx->d_ord_nlev.as<u8>(), ctx->d_ord_conf.as<double>(),
+                                                                    ctx->d_ord_local.as<double>(), nq, ctx->ix.max_levels);
+        CU(cudaGetLastError());
+    }
+    return RTX_OK;
+}
+
 static int run_all(rtx_ctx* ctx) {
     BatchView& bv = ctx->bv;
     const u32 nq = bv.n_queries;
@@ -1041,6 +1128,10 @@ static int run_all(rtx_ctx* ctx) {
     ctx->cur_stream = ctx->stream;
     ctx->cur_counts = ctx->d_counts.as<u16>();
     ctx->cur_sc = &ctx->sc;
+    {
+        int rc = order_results(ctx);
+        if (rc) return rc;
+    }
     ctx->prof.queries += nq;
     ctx->runs_since_download += 1;
     ctx->ran = true;
@@ -1071,34 +1162,36 @@ RTX_API int rtx_batch_download(rtx_ctx* ctx, rtx_results* res) {
     }
     REQUIRE(res->result_begin && res->n_kmers && res->global_signal, "result_begin / n_kmers / global_signal must be provided");
     const u32 ML = ctx->ix.max_levels;
-    unsigned long long used = 0, hits = 0;
-    ctx->h_res_off.resize(nq);
-    ctx->h_res_cnt.resize(nq);
-    ctx->h_status.resize(nq);
-    ctx->h_nrows.resize(nq);
-    CU(cudaMemcpyAsync(&used, ctx->d_pool_used.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
-    CU(cudaMemcpyAsync(&hits, ctx->d_hits.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
-    CU(cudaMemcpyAsync(ctx->h_res_off.data(), ctx->d_res_off.p, nq * 4, cudaMemcpyDeviceToHost, ctx->stream));
-    CU(cudaMemcpyAsync(ctx->h_res_cnt.data(), ctx->d_res_cnt.p, nq * 4, cudaMemcpyDeviceToHost, ctx->stream));
-    CU(cudaMemcpyAsync(ctx->h_status.data(), ctx->d_status.p, nq * 4, cudaMemcpyDeviceToHost, ctx->stream));
-    CU(cudaMemcpyAsync(ctx->h_nrows.data(), ctx->d_nrows.p, nq * 4, cudaMemcpyDeviceToHost, ctx->stream));
-    CU(cudaMemcpyAsync(res->n_kmers, ctx->d_K.p, nq * 2, cudaMemcpyDeviceToHost, ctx->stream));
-    CU(cudaMemcpyAsync(res->global_signal, ctx->d_global.p, nq * 8, cudaMemcpyDeviceToHost, ctx->stream));
-    CU(cudaStreamSynchronize(ctx->stream));
-    ctx->prof.d2h_bytes += 16 + (u64)nq * (4 * 4 + 2 + 8);
+    // round 1: per-query metadata through the pinned arena, one synchronisation
+    const size_t meta_bytes = 2 * 64 + ((size_t)nq + 1) * 4 + (size_t)nq * (4 + 4 + 2 + 8) + 6 * 64;
+    CU(arena_reserve(ctx, meta_bytes));
+    unsigned long long* h_used = (unsigned long long*)arena_take(ctx, 16);
+    u32* h_begin = (u32*)arena_take(ctx, ((size_t)nq + 1) * 4);
+    int* h_status = (int*)arena_take(ctx, (size_t)nq * 4);
+    u32* h_nrows = (u32*)arena_take(ctx, (size_t)nq * 4);
+    CU(cudaMemcpyAsync(&h_used[0], ctx->d_pool_used.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaMemcpyAsync(&h_used[1], ctx->d_hits.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaMemcpyAsync(h_begin, ctx->d_ord_begin.p, ((size_t)nq + 1) * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaMemcpyAsync(h_status, ctx->d_status.p, (size_t)nq * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaMemcpyAsync(h_nrows, ctx->d_nrows.p, (size_t)nq * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(d2h(ctx, res->n_kmers, ctx->d_K.p, (size_t)nq * 2, host_ptr_pinned(res->n_kmers)));
+    CU(d2h(ctx, res->global_signal, ctx->d_global.p, (size_t)nq * 8, host_ptr_pinned(res->global_signal)));
+    CU(d2h_finish(ctx));
+    const unsigned long long used = h_used[0], hits = h_used[1];
+    ctx->prof.d2h_bytes += 16 + 4 + (u64)nq * (3 * 4 + 2 + 8);
     {
         // every run since the last download processed this same batch: account them all
         const u64 runs = ctx->runs_since_download;
         ctx->runs_since_download = 0;
         u64 rows = 0;
-        for (u32 q = 0; q < nq; ++q) rows += ctx->h_nrows[q];
+        for (u32 q = 0; q < nq; ++q) rows += h_nrows[q];
         ctx->prof.hits += hits * runs;
         ctx->prof.bitrow_bytes += runs * (rows * (u64)ctx->ix.row_words * 4 + (u64)nq * ctx->ix.n_pad * 2);
         ctx->prof.csr_equiv_bytes += runs * (4 * (u64)hits + (u64)nq * ctx->ix.shard_refs * 2);
     }
     bool pool_overflow = false;
     for (u32 q = 0; q < nq; ++q) {
-        switch (ctx->h_status[q]) {
+        switch (h_status[q]) {
             case kQOk: break;
             case kQPoolOverflow: pool_overflow = true; break;
             case kQProbSumZero:
@@ -1126,34 +1219,19 @@ RTX_API int rtx_batch_download(rtx_ctx* ctx, rtx_results* res) {
         return rtx_batch_download(ctx, res);
     }
     res->n_results = used;
-    u64 acc = 0;
-    for (u32 q = 0; q < nq; ++q) {
-        res->result_begin[q] = (u32)acc;
-        acc += ctx->h_res_cnt[q];
-    }
-    res->result_begin[nq] = (u32)acc;
-    if (acc != used) return set_err(ctx, RTX_ERR_CUDA, "result accounting mismatch");
+    if ((u64)h_begin[nq] != used) return set_err(ctx, RTX_ERR_CUDA, "result accounting mismatch");
     if (used > res->result_capacity) return set_err(ctx, RTX_ERR_INVALID, "result_capacity too small; n_results holds the needed size");
+    memcpy(res->result_begin, h_begin, ((size_t)nq + 1) * 4);  // before the arena is recycled for round 2
     if (used) {
+        // round 2: the result lines, already in query order on the device
         REQUIRE(res->first_ref && res->n_levels && res->confidence && res->local_signal, "per-result output arrays must be provided");
-        ctx->h_pool_first.resize(used);
-        ctx->h_pool_nlev.resize(used);
-        ctx->h_pool_conf.resize(used * ML);
-        ctx->h_pool_local.resize(used);
-        CU(cudaMemcpyAsync(ctx->h_pool_first.data(), ctx->d_pool_first.p, used * 4, cudaMemcpyDeviceToHost, ctx->stream));
-        CU(cudaMemcpyAsync(ctx->h_pool_nlev.data(), ctx->d_pool_nlev.p, used, cudaMemcpyDeviceToHost, ctx->stream));
-        CU(cudaMemcpyAsync(ctx->h_pool_conf.data(), ctx->d_pool_conf.p, used * ML * 8, cudaMemcpyDeviceToHost, ctx->stream));
-        CU(cudaMemcpyAsync(ctx->h_pool_local.data(), ctx->d_pool_local.p, used * 8, cudaMemcpyDeviceToHost, ctx->stream));
-        CU(cudaStreamSynchronize(ctx->stream));
+        CU(arena_reserve(ctx, used * (4 + 1 + 8 + (size_t)ML * 8) + 4 * 64));
+        CU(d2h(ctx, res->first_ref, ctx->d_ord_first.p, used * 4, host_ptr_pinned(res->first_ref)));
+        CU(d2h(ctx, res->n_levels, ctx->d_ord_nlev.p, used, host_ptr_pinned(res->n_levels)));
+        CU(d2h(ctx, res->confidence, ctx->d_ord_conf.p, used * ML * 8, host_ptr_pinned(res->confidence)));
+        CU(d2h(ctx, res->local_signal, ctx->d_ord_local.p, used * 8, host_ptr_pinned(res->local_signal)));
+        CU(d2h_finish(ctx));
         ctx->prof.d2h_bytes += used * (4 + 1 + 8 + (u64)ML * 8);
-        for (u32 q = 0; q < nq; ++q) {
-            const u32 src = ctx->h_res_off[q], dst = res->result_begin[q], n = ctx->h_res_cnt[q];
-            if (!n) continue;
-            memcpy(res->first_ref + dst, ctx->h_pool_first.data() + src, n * 4);
-            memcpy(res->n_levels + dst, ctx->h_pool_nlev.data() + src, n);
-            memcpy(res->confidence + (size_t)dst * ML, ctx->h_pool_conf.data() + (size_t)src * ML, (size_t)n * ML * 8);
-            memcpy(res->local_signal + dst, ctx->h_pool_local.data() + src, n * 8);
-        }
     }
     // taps
     if (res->tap_hist) {
@@ -1305,6 +1383,9 @@ RTX_API int rtx_shard_phase3(rtx_ctx* ctx) {
             ctx->ix, ctx->d_recs.as<NodeRec>(), bv, ctx->pool, ctx->sc, ctx->sv, 0, (int)nq, 0);
         CU(cudaGetLastError());
     }
+    ctx->cur_stream = ctx->stream;
+    rc = order_results(ctx);
+    if (rc) return rc;
     ctx->prof.queries += nq;
     ctx->runs_since_download += 1;
     ctx->ran = true;

@@ -430,3 +430,22 @@ def test_cli_binary_writes_reference_format_files(tmp_path):
         # a second run into the same folder is refused without --redo (io.rs:231-233)
         r2 = subprocess.run(cmd, capture_output=True, text=True)
         assert r2.returncode == 73 and "already exists" in r2.stderr
+
+
+def test_pinned_result_buffers_match_pageable(ctx):
+    """rtx_host_alloc buffers (results written by DMA, ordered on the device) give exactly what ordinary memory gives."""
+    ds = synth.generate("small", measure=False)
+    ht = capi.Tree.new(ds.ref_lineages, ds.ref_off, ds.ref_codes)
+    ctx.upload_tree(ht)
+    eo, eids = ht.exact_batch(ds.query_off, ds.query_codes)
+    a = ctx.classify(ds.query_off, ds.query_codes, eo, eids)
+    buf = ctx.pinned_results(ds.n_queries)
+    for sub in (0, 37):  # one sub-batch, and several (results of different sub-batches interleave in the pool)
+        ctx.set_option(capi.RTX_OPT_SUB_BATCH, sub)
+        b = ctx.classify(ds.query_off, ds.query_codes, eo, eids, out=buf)
+        ctx.set_option(capi.RTX_OPT_SUB_BATCH, 0)
+        n = int(a.result_begin[-1])
+        assert n > 0 and np.array_equal(a.result_begin, b.result_begin)
+        assert np.array_equal(a.n_kmers, b.n_kmers) and np.array_equal(a.global_signal, b.global_signal)
+        assert np.array_equal(a.first_ref, b.first_ref[:n]) and np.array_equal(a.n_levels, b.n_levels[:n])
+        assert np.array_equal(a.confidence, b.confidence[:n]) and np.array_equal(a.local_signal, b.local_signal[:n])
