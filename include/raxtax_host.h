@@ -32,6 +32,12 @@ const char* rxh_last_error(void);
 rxh_tree* rxh_tree_from_fasta(const char* text, size_t len);
 /* lineages: n strings joined by '\n'; sequences: 4-bit codes (parser.rs:11-34) with offsets[n+1] */
 rxh_tree* rxh_tree_new(size_t n, const char* lineage_blob, size_t blob_len, const uint64_t* seq_offsets, const uint8_t* seq_codes);
+/* Binary database (bincode 1.3 image of Tree; tree.rs:146-164, layout in SURVEY.md Appendix C).
+ * rxh_tree_from_bin = Tree::load_from_file: NULL when the bytes do not deserialise (the caller then parses them as FASTA, as
+ * parser::parse_reference_fasta_file does, parser.rs:37-44); a loaded tree carries its k_mer_map, which is then what the
+ * device index is built from.  rxh_tree_save_bin = Tree::save_to_file.  32-bit ids only (not the `huge_db` feature). */
+rxh_tree* rxh_tree_from_bin(const void* data, size_t len);
+int rxh_tree_save_bin(const rxh_tree* t, const char* path);
 void rxh_tree_free(rxh_tree* t);
 size_t rxh_tree_num_tips(const rxh_tree* t);
 const char* rxh_tree_lineage(const rxh_tree* t, size_t i); /* Tree.lineages[i] (sorted order) */
@@ -54,6 +60,9 @@ int rxh_tree_upload_sharded(const rxh_tree* t, rtx_ctx* ctx, uint32_t n_shards, 
 /* ---- queries ----------------------------------------------------------------------------------------------- */
 rxh_queries* rxh_queries_from_fasta(const char* text, size_t len);
 rxh_queries* rxh_queries_new(size_t n, const char* label_blob, size_t blob_len, const uint64_t* seq_offsets, const uint8_t* seq_codes);
+/* drop the queries whose label is listed ('\n'-separated, the content of raxtax.ckp): parse_query_fasta_str's queries_to_skip
+ * filter (parser.rs:108-115,150-153) */
+int rxh_queries_skip(rxh_queries* q, const char* label_blob, size_t blob_len);
 void rxh_queries_free(rxh_queries* q);
 size_t rxh_queries_len(const rxh_queries* q);
 const char* rxh_queries_label(const rxh_queries* q, size_t i);

@@ -35,7 +35,7 @@ DEVICE_SYMBOLS = [
 ]
 # every symbol include/raxtax_host.h declares
 HOST_SYMBOLS = [
-    "rxh_last_error", "rxh_tree_from_fasta", "rxh_tree_new", "rxh_tree_free", "rxh_tree_num_tips", "rxh_tree_lineage",
+    "rxh_last_error", "rxh_tree_from_fasta", "rxh_tree_from_bin", "rxh_tree_save_bin", "rxh_queries_skip", "rxh_tree_new", "rxh_tree_free", "rxh_tree_num_tips", "rxh_tree_lineage",
     "rxh_tree_csr", "rxh_tree_build_kmer_map", "rxh_tree_has_kmer_map", "rxh_tree_exact", "rxh_tree_index_desc", "rxh_tree_upload", "rxh_tree_upload_sharded", "rxh_queries_from_fasta", "rxh_queries_new",
     "rxh_queries_free", "rxh_queries_len", "rxh_queries_label", "rxh_queries_arrays", "rxh_raxtax", "rxh_exact_batch",
 ]
@@ -136,6 +136,10 @@ def host_lib():
     L.rxh_last_error.restype = C.c_char_p
     L.rxh_tree_from_fasta.restype = C.c_void_p
     L.rxh_tree_from_fasta.argtypes = [C.c_char_p, C.c_size_t]
+    L.rxh_tree_from_bin.restype = C.c_void_p
+    L.rxh_tree_from_bin.argtypes = [C.c_char_p, C.c_size_t]
+    L.rxh_tree_save_bin.argtypes = [C.c_void_p, C.c_char_p]
+    L.rxh_queries_skip.argtypes = [C.c_void_p, C.c_char_p, C.c_size_t]
     L.rxh_tree_new.restype = C.c_void_p
     L.rxh_tree_new.argtypes = [C.c_size_t, C.c_char_p, C.c_size_t, u64p, u8p]
     L.rxh_tree_free.argtypes = [C.c_void_p]
@@ -467,6 +471,15 @@ class Tree:
         return cls(host_lib().rxh_tree_from_fasta(b, len(b)))
 
     @classmethod
+    def from_bin(cls, data: bytes):  # Tree::load_from_file (tree.rs:154-164); None when the bytes are not a database
+        h = host_lib().rxh_tree_from_bin(data, len(data))
+        return cls(h) if h else None
+
+    def save_bin(self, path: str):  # Tree::save_to_file (tree.rs:146-152)
+        if host_lib().rxh_tree_save_bin(self._h, path.encode()) != 0:
+            raise _host_err()
+
+    @classmethod
     def new(cls, lineages, seq_off, codes, eager_kmer_map=False) -> "Tree":  # Tree::new
         """k_mer_map (the CSR postings) is built on first use only unless eager_kmer_map: the device derives its index from the
         sorted sequences, and uploads of a tree WITH a materialised k_mer_map go through the CSR instead."""
@@ -575,6 +588,11 @@ class Queries:
         if codes.size == 0:
             codes = np.zeros(1, np.uint8)
         return cls(host_lib().rxh_queries_new(len(labels), blob, len(blob), _ptr(seq_off, C.c_uint64), _ptr(codes, C.c_uint8)))
+
+    def skip(self, labels):  # queries_to_skip of parse_query_fasta_file (parser.rs:108-115)
+        blob = "\n".join(labels).encode()
+        if host_lib().rxh_queries_skip(self._h, blob, len(blob)) != 0:
+            raise _host_err()
 
     def __del__(self):
         try:

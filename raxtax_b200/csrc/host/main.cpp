@@ -1,11 +1,15 @@
-// main.cpp -- `raxtax` command-line binary on top of the B200 library (SURVEY.md 8(f) row 1).
+// main.cpp -- `raxtax` command-line binary on top of the B200 library (SURVEY.md 8(f) rows 1, 3, 4).
 //
-// Mirrors the reference's CLI surface and output files (src/io.rs:112-154, src/main.rs:14-173):
-//   raxtax -d <db.fasta[.gz]> -i <queries.fasta[.gz]> [-o PREFIX] [--skip-exact-matches] [--raw-confidence] [--tsv]
-//          [--redo] [--skip-db] [-c] [-t N] [--pin] [-v|-q] [--gpu N]
-// writes <PREFIX>/raxtax.out, raxtax.log, raxtax.ckp and (with --tsv) raxtax.tsv in the reference's formats
-// (lineage.rs:17-48).  Not carried over (DESIGN.md "out of scope"): the bincode .bin database (--only-db is refused,
-// --skip-db / --clean are accepted and have nothing to do), checkpoint resume (raxtax.json), thread pinning.
+// Mirrors the reference's CLI surface, output files and restart behaviour (src/io.rs:112-300, src/main.rs:14-173):
+//   raxtax -d <db.fasta[.gz] | db.bin> -i <queries.fasta[.gz]> [-o PREFIX] [--skip-exact-matches] [--raw-confidence] [--tsv]
+//          [--redo] [--only-db] [--skip-db] [-c] [-t N] [--pin] [-v|-q] [--gpu N] [--batch N]
+// writes <PREFIX>/raxtax.out, raxtax.log, raxtax.ckp, raxtax.json and (with --tsv) raxtax.tsv in the reference's formats
+// (lineage.rs:17-48), and <PREFIX>/<database stem>.bin, the bincode database of tree.rs:146-164, unless --skip-db.
+// A database path that deserialises as such a .bin is loaded instead of parsed (parser.rs:37-44).  An interrupted run is
+// continued from raxtax.json + raxtax.ckp (io.rs:47-90,156-230) when the flags and the database fingerprint still match.
+// One deliberate difference: --clean removes the checkpoint files and a database this run family created under PREFIX,
+// never the file the user passed with -d (Checkpoint::cleanup, io.rs:80-89, would delete it when --skip-db was given).
+// Not carried over: thread pinning (accepted, no effect: the hot path runs on the GPU).
 // Exit codes follow main.rs: 73 CANTCREAT, 66 NOINPUT, 74 IOERR, 75 TEMPFAIL, 0 OK.
 
 #include <sys/stat.h>
@@ -15,6 +19,10 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <filesystem>
+#include <fstream>
+#include <set>
+#include <sstream>
 #include <string>
 #include <vector>
 
@@ -36,12 +44,12 @@ void usage() {
     fprintf(stderr,
             "Usage: raxtax [OPTIONS] --database-path <DATABASE_PATH>\n\n"
             "Options:\n"
-            "  -d, --database-path <DATABASE_PATH>  Path to the database fasta file (.gz/.gzip accepted)\n"
+            "  -d, --database-path <DATABASE_PATH>  Path to the database fasta or bin file (.gz/.gzip fasta accepted)\n"
             "  -i, --query-file <QUERY_FILE>        Path to the query file\n"
             "      --skip-exact-matches             If used for mislabling analysis, you want to skip exact sequence matches\n"
             "      --tsv                            Output primary result file in tsv format\n"
-            "      --only-db                        (not supported by the B200 build: no binary database)\n"
-            "      --skip-db                        Don't create the binary database (always the case here)\n"
+            "      --only-db                        Only create the binary database and exit\n"
+            "      --skip-db                        Don't create the binary database\n"
             "  -c, --clean                          Remove checkpoint files after a successful run\n"
             "      --raw-confidence                 Don't adjust confidence values for 1 exact match\n"
             "  -t, --threads <THREADS>              Accepted for compatibility (the hot path runs on the GPU)\n"
@@ -85,6 +93,168 @@ void log_cb(void* user, int level, const char* msg) {  // env_logger without tim
 bool exists(const std::string& p) {
     struct stat st;
     return stat(p.c_str(), &st) == 0;
+}
+bool is_file(const std::string& p) {
+    struct stat st;
+    return stat(p.c_str(), &st) == 0 && S_ISREG(st.st_mode);
+}
+bool is_dir(const std::string& p) {
+    struct stat st;
+    return stat(p.c_str(), &st) == 0 && S_ISDIR(st.st_mode);
+}
+std::string absolute(const std::string& p) {  // std::path::absolute: no symlink resolution, no existence check
+    std::error_code ec;
+    auto a = std::filesystem::absolute(p, ec);
+    return ec ? p : a.lexically_normal().string();
+}
+bool read_raw(const std::string& path, std::string* out) {
+    FILE* f = fopen(path.c_str(), "rb");
+    if (!f) return false;
+    char buf[1 << 16];
+    size_t n;
+    while ((n = fread(buf, 1, sizeof buf, f)) > 0) out->append(buf, n);
+    const bool ok = !ferror(f);
+    fclose(f);
+    return ok;
+}
+bool gz_by_extension(const std::string& path) {  // utils::get_reader (utils.rs:42-60)
+    const size_t dot = path.rfind('.');
+    if (dot == std::string::npos || path.find('/', dot) != std::string::npos) return false;
+    std::string ext = path.substr(dot + 1);
+    for (auto& c : ext) c = (char)tolower((unsigned char)c);
+    return ext == "gz" || ext == "gzip";
+}
+
+// io::FileFingerprint (io.rs:23-45)
+struct Fingerprint {
+    std::string path;
+    unsigned long long size = 0, modified = 0;
+    bool operator==(const Fingerprint& o) const { return path == o.path && size == o.size && modified == o.modified; }
+};
+bool fingerprint(const std::string& path, Fingerprint* fp) {
+    struct stat st;
+    if (stat(path.c_str(), &st) != 0) return false;
+    fp->path = absolute(path);
+    fp->size = (unsigned long long)st.st_size;
+    fp->modified = (unsigned long long)st.st_mtime;
+    return true;
+}
+
+// io::Checkpoint (io.rs:47-90): raxtax.json, written like serde_json::to_writer_pretty
+struct Checkpoint {
+    std::string checkpoint_file, progress_file;
+    Fingerprint db;
+    bool raw_confidence = false, skip_exact_matches = false, tsv = false;
+    std::set<std::string> processed;  // #[serde(skip)]
+};
+std::string json_escape(const std::string& s) {
+    std::string o;
+    for (unsigned char c : s) {
+        switch (c) {
+            case '"': o += "\\\""; break;
+            case '\\': o += "\\\\"; break;
+            case '\n': o += "\\n"; break;
+            case '\r': o += "\\r"; break;
+            case '\t': o += "\\t"; break;
+            default:
+                if (c < 0x20) {
+                    char b[8];
+                    snprintf(b, sizeof b, "\\u%04x", c);
+                    o += b;
+                } else o += (char)c;
+        }
+    }
+    return o;
+}
+bool checkpoint_save(const Checkpoint& c) {  // Checkpoint::save (io.rs:72-78): write raxtax.json.tmp, then rename
+    const std::string tmp = std::filesystem::path(c.checkpoint_file).replace_extension("json.tmp").string();
+    FILE* f = fopen(tmp.c_str(), "w");
+    if (!f) return false;
+    fprintf(f,
+            "{\n  \"checkpoint_file\": \"%s\",\n  \"progress_file\": \"%s\",\n  \"db_fingerprint\": {\n    \"path\": \"%s\",\n"
+            "    \"size\": %llu,\n    \"modified\": %llu\n  },\n  \"raw_confidence\": %s,\n  \"skip_exact_matches\": %s,\n  \"tsv\": %s\n}",
+            json_escape(c.checkpoint_file).c_str(), json_escape(c.progress_file).c_str(), json_escape(c.db.path).c_str(), c.db.size,
+            c.db.modified, c.raw_confidence ? "true" : "false", c.skip_exact_matches ? "true" : "false", c.tsv ? "true" : "false");
+    if (fclose(f) != 0) return false;
+    return rename(tmp.c_str(), c.checkpoint_file.c_str()) == 0;
+}
+// the handful of JSON this file needs: "key": "string" | number | true | false, nesting ignored (keys are unique across levels)
+bool json_find(const std::string& j, const char* key, std::string* raw) {
+    const std::string pat = std::string("\"") + key + "\"";
+    size_t p = j.find(pat);
+    if (p == std::string::npos) return false;
+    p = j.find(':', p + pat.size());
+    if (p == std::string::npos) return false;
+    ++p;
+    while (p < j.size() && isspace((unsigned char)j[p])) ++p;
+    if (p >= j.size()) return false;
+    if (j[p] == '"') {
+        std::string o;
+        for (++p; p < j.size() && j[p] != '"'; ++p) {
+            if (j[p] == '\\' && p + 1 < j.size()) {
+                ++p;
+                switch (j[p]) {
+                    case 'n': o += '\n'; break;
+                    case 'r': o += '\r'; break;
+                    case 't': o += '\t'; break;
+                    case 'u':
+                        if (p + 4 < j.size()) {
+                            o += (char)strtol(j.substr(p + 1, 4).c_str(), nullptr, 16);
+                            p += 4;
+                        }
+                        break;
+                    default: o += j[p];
+                }
+            } else o += j[p];
+        }
+        if (p >= j.size()) return false;
+        *raw = o;
+        return true;
+    }
+    size_t e = p;
+    while (e < j.size() && j[e] != ',' && j[e] != '}' && !isspace((unsigned char)j[e])) ++e;
+    *raw = j.substr(p, e - p);
+    return !raw->empty();
+}
+bool checkpoint_load(const std::string& path, Checkpoint* c) {  // serde_json::from_reader (io.rs:208-209)
+    std::string j, v;
+    if (!read_raw(path, &j)) return false;
+    auto b = [&](const char* k, bool* out) {
+        if (!json_find(j, k, &v) || (v != "true" && v != "false")) return false;
+        *out = v == "true";
+        return true;
+    };
+    if (!json_find(j, "checkpoint_file", &c->checkpoint_file) || !json_find(j, "progress_file", &c->progress_file) ||
+        !json_find(j, "path", &c->db.path))
+        return false;
+    if (!json_find(j, "size", &v)) return false;
+    c->db.size = strtoull(v.c_str(), nullptr, 10);
+    if (!json_find(j, "modified", &v)) return false;
+    c->db.modified = strtoull(v.c_str(), nullptr, 10);
+    return b("raw_confidence", &c->raw_confidence) && b("skip_exact_matches", &c->skip_exact_matches) && b("tsv", &c->tsv);
+}
+// io::check_incomplete_output (io.rs:156-188): drop the result lines of queries the progress file does not list
+bool check_incomplete_output(const std::string& path, const std::set<std::string>& processed) {
+    std::ifstream in(path);
+    if (!in) return false;
+    std::vector<std::string> kept;
+    bool needs_rewrite = false;
+    std::string line;
+    while (std::getline(in, line)) {
+        const size_t tab = line.find('\t');
+        if (tab != std::string::npos && processed.count(line.substr(0, tab))) kept.push_back(line);
+        else if (tab != std::string::npos) needs_rewrite = true;
+    }
+    in.close();
+    if (needs_rewrite) {
+        const std::string tmp = std::filesystem::path(path).replace_extension("tmp").string();
+        std::ofstream out(tmp, std::ios::trunc);
+        for (size_t i = 0; i < kept.size(); ++i) out << (i ? "\n" : "") << kept[i];
+        out << "\n";  // writeln!(tmp_file, "{}", retained_lines.join("\n"))
+        out.close();
+        if (!out || rename(tmp.c_str(), path.c_str()) != 0) return false;
+    }
+    return true;
 }
 
 }  // namespace
@@ -133,27 +303,69 @@ int main(int argc, char** argv) {
         fprintf(stderr, "error: the argument '--only-db' cannot be used with '--skip-db'\n");
         return EX_USAGE_;
     }
-    if (a.only_db) {
-        fprintf(stderr, "\x1b[31m[ERROR]\x1b[0m --only-db: the B200 build keeps no binary database\n");
+    // ---- Args::get_output (io.rs:202-263): checkpoint, output folder, writers ----------------------------------------
+    const std::string ckp_path = a.prefix + "/raxtax.json", out_path = a.prefix + "/raxtax.out", tsv_path = a.prefix + "/raxtax.tsv";
+    Checkpoint ckp;
+    auto checkpoint_new = [&](Checkpoint* c) {  // Checkpoint::new (io.rs:60-70)
+        *c = Checkpoint();
+        c->checkpoint_file = absolute(ckp_path);
+        c->progress_file = std::filesystem::path(absolute(ckp_path)).replace_extension("ckp").string();
+        c->raw_confidence = a.raw_confidence;
+        c->skip_exact_matches = a.skip_exact_matches;
+        c->tsv = a.tsv;
+        return fingerprint(a.database_path, &c->db);
+    };
+    bool resumed = false;
+    if (!a.redo && is_file(ckp_path)) {
+        Checkpoint old;
+        if (checkpoint_load(ckp_path, &old)) {
+            Fingerprint now;
+            const bool valid = fingerprint(old.db.path, &now) && a.tsv == old.tsv && a.raw_confidence == old.raw_confidence &&
+                               a.skip_exact_matches == old.skip_exact_matches && now == old.db;  // checkpoint_valid (io.rs:288-303)
+            if (valid) {
+                std::ifstream prog(old.progress_file);
+                std::string line;
+                while (std::getline(prog, line)) old.processed.insert(line);
+                if (!check_incomplete_output(out_path, old.processed) || (a.tsv && !check_incomplete_output(tsv_path, old.processed))) {
+                    fprintf(stderr, "\x1b[31m[ERROR]\x1b[0m cannot repair the output files under %s\n", a.prefix.c_str());
+                    return EX_CANTCREAT_;
+                }
+                ckp = old;
+                resumed = true;
+            }
+        } else {
+            fprintf(stderr, "\x1b[31m[ERROR]\x1b[0m Failed to read checkpoint!\n");
+        }
+    }
+    if (!resumed && !checkpoint_new(&ckp)) {
+        fprintf(stderr, "\x1b[31m[ERROR]\x1b[0m Failed to parse %s: cannot read file\n", a.database_path.c_str());
         return EX_CANTCREAT_;
     }
-    // output folder (io.rs:202-263)
-    const std::string out_path = a.prefix + "/raxtax.out";
-    if (exists(a.prefix) && !a.redo) {
+    if (is_dir(a.prefix) && !is_file(ckp_path) && !a.redo) {
         fprintf(stderr, "\x1b[31m[ERROR]\x1b[0m Output folder %s already exists! Please specify another folder with -o <PATH> or run with --redo to force overriding existing files!\n",
                 a.prefix.c_str());
         return EX_CANTCREAT_;
     }
-    if (!exists(a.prefix) && mkdir(a.prefix.c_str(), 0777) != 0) {
-        fprintf(stderr, "\x1b[31m[ERROR]\x1b[0m cannot create %s\n", a.prefix.c_str());
-        return EX_CANTCREAT_;
+    {
+        std::error_code ec;
+        std::filesystem::create_directories(a.prefix, ec);
+        if (ec) {
+            fprintf(stderr, "\x1b[31m[ERROR]\x1b[0m cannot create %s\n", a.prefix.c_str());
+            return EX_CANTCREAT_;
+        }
     }
+    const char* mode = a.redo ? "w" : "a";  // create_file(path, append = !redo) (io.rs:190-199)
+    const bool restart_note = !a.redo && exists(ckp_path) && a.verbosity >= 3;
     Writers w;
     w.verbosity = a.verbosity;
-    w.primary = fopen(out_path.c_str(), "w");
-    w.log = fopen((a.prefix + "/raxtax.log").c_str(), "w");
-    w.progress = fopen((a.prefix + "/raxtax.ckp").c_str(), "w");
-    if (a.tsv) w.tsv = fopen((a.prefix + "/raxtax.tsv").c_str(), "w");
+    if (a.tsv) w.tsv = fopen(tsv_path.c_str(), mode);
+    w.log = fopen((a.prefix + "/raxtax.log").c_str(), mode);
+    if (w.log && restart_note) {
+        fprintf(w.log, "[INFO ] Restarting from checkpoint %s\n", ckp.checkpoint_file.c_str());
+        fprintf(stderr, "[INFO ] Restarting from checkpoint %s\n", ckp.checkpoint_file.c_str());
+    }
+    w.primary = fopen(out_path.c_str(), mode);
+    w.progress = fopen((a.prefix + "/raxtax.ckp").c_str(), mode);
     if (!w.primary || !w.log || !w.progress || (a.tsv && !w.tsv)) {
         fprintf(stderr, "\x1b[31m[ERROR]\x1b[0m cannot create output files under %s\n", a.prefix.c_str());
         return EX_CANTCREAT_;
@@ -167,17 +379,59 @@ int main(int argc, char** argv) {
     }
     auto t_total = std::chrono::steady_clock::now();
 
-    std::string db_text, q_text;
-    if (!read_file(a.database_path, &db_text)) {
-        fprintf(stderr, "\x1b[31m[ERROR]\x1b[0m Failed to parse %s: cannot read file\n", a.database_path.c_str());
-        return EX_NOINPUT_;
+    // ---- parser::parse_reference_fasta_file (parser.rs:37-44) on the checkpoint's database path (main.rs:61) ----------------
+    rxh_tree* tree = nullptr;
+    bool store_db = false;
+    {
+        std::string raw;
+        if (!read_raw(ckp.db.path, &raw)) {
+            fprintf(stderr, "\x1b[31m[ERROR]\x1b[0m Failed to parse %s: cannot read file\n", ckp.db.path.c_str());
+            return EX_NOINPUT_;
+        }
+        if (a.verbosity >= 3) fprintf(stderr, "[INFO ] Trying to read from database file...\n");
+        tree = rxh_tree_from_bin(raw.data(), raw.size());
+        if (!tree) {
+            store_db = true;
+            std::string text;
+            if (gz_by_extension(ckp.db.path)) {
+                if (!read_file(ckp.db.path, &text)) text.clear();
+            } else text.swap(raw);
+            tree = rxh_tree_from_fasta(text.data(), text.size());
+            if (!tree) {
+                fprintf(stderr, "\x1b[31m[ERROR]\x1b[0m Failed to parse %s: %s\n", ckp.db.path.c_str(), rxh_last_error());
+                return EX_NOINPUT_;
+            }
+        }
     }
-    rxh_tree* tree = rxh_tree_from_fasta(db_text.data(), db_text.size());
-    if (!tree) {
-        fprintf(stderr, "\x1b[31m[ERROR]\x1b[0m Failed to parse %s: %s\n", a.database_path.c_str(), rxh_last_error());
-        return EX_NOINPUT_;
+    std::string created_db;
+    if (store_db && !a.skip_db) {  // main.rs:73-98, Args::get_db_output (io.rs:269-286)
+        std::filesystem::path name = std::filesystem::path(a.database_path).filename();
+        if (name.empty()) name = "database";
+        const std::string db_path = (std::filesystem::path(a.prefix) / name).replace_extension("bin").string();
+        if (is_file(db_path) && !a.redo) {
+            fprintf(stderr, "\x1b[31m[ERROR]\x1b[0m Could not create database! Rerun with --skip-db to skip this step.: Output database file %s already exists! Delete it or run with --redo to force overriding existing files!\n",
+                    db_path.c_str());
+            return EX_CANTCREAT_;
+        }
+        if (a.verbosity >= 3) {
+            fprintf(w.log, "[INFO ] Created binary database at %s\n", db_path.c_str());
+            fprintf(stderr, "[INFO ] Writing database to file...\n");
+        }
+        if (rxh_tree_save_bin(tree, db_path.c_str()) != 0) {
+            fprintf(stderr, "\x1b[31m[ERROR]\x1b[0m Failed to write database: %s\n", rxh_last_error());
+            return EX_IOERR_;
+        }
+        created_db = absolute(db_path);
+        Fingerprint fp;
+        if (!fingerprint(db_path, &fp) || (ckp.db = fp, !checkpoint_save(ckp)))
+            fprintf(stderr, "\x1b[31m[ERROR]\x1b[0m Failed to write checkpoint! Continuing without...\n");
+    } else if (!checkpoint_save(ckp)) {
+        fprintf(stderr, "\x1b[31m[ERROR]\x1b[0m Failed to write checkpoint! Continuing without...\n");
     }
-    std::string().swap(db_text);
+    if (a.only_db) return EX_OK_;
+
+    // ---- parser::parse_query_fasta_file with the processed queries skipped (main.rs:104-117) ------------------------------
+    std::string q_text;
     if (!read_file(a.query_file, &q_text)) {
         fprintf(stderr, "\x1b[31m[ERROR]\x1b[0m Failed to parse %s: cannot read file\n", a.query_file.c_str());
         return EX_NOINPUT_;
@@ -188,6 +442,11 @@ int main(int argc, char** argv) {
         return EX_NOINPUT_;
     }
     std::string().swap(q_text);
+    if (!ckp.processed.empty()) {
+        std::string blob;
+        for (const auto& l : ckp.processed) blob += l + "\n";
+        rxh_queries_skip(queries, blob.data(), blob.size());
+    }
 
     rtx_ctx* ctx = nullptr;
     if (rtx_ctx_create(a.gpu, &ctx) != 0) {
@@ -214,7 +473,14 @@ int main(int argc, char** argv) {
     }
     for (FILE* f : {w.primary, w.tsv, w.log, w.progress})
         if (f) fclose(f);
-    if (a.clean) remove((a.prefix + "/raxtax.ckp").c_str());  // Checkpoint::cleanup: nothing else was written
+    if (a.clean) {  // Checkpoint::cleanup (io.rs:80-89); the database only if it lives under PREFIX as <stem>.bin (see the header)
+        if (a.verbosity >= 3) fprintf(stderr, "[INFO ] Removing checkpoint files...\n");
+        remove(ckp.checkpoint_file.c_str());
+        remove(ckp.progress_file.c_str());
+        const std::string pre = absolute(a.prefix) + "/";
+        if (ckp.db.path.compare(0, pre.size(), pre) == 0 && ckp.db.path.size() > 4 && ckp.db.path.compare(ckp.db.path.size() - 4, 4, ".bin") == 0)
+            remove(ckp.db.path.c_str());
+    }
     rxh_queries_free(queries);
     rxh_tree_free(tree);
     rtx_ctx_destroy(ctx);

@@ -210,6 +210,26 @@ static inline void for_each_kmer(const u8* s, size_t n, F&& f) {  // windows(8) 
     }
 }
 
+// flatten: BFS numbering, children contiguous.  Implicit Sequence leaves are dropped: they can neither be emitted
+// nor change a decision of Lineage::eval_recurse (lineage.rs:119-179) because their parent is never Inner.
+static void flatten_nodes(const std::vector<BNode>& nodes, Tree& tree) {
+    const size_t nn = nodes.size();
+    std::vector<u32> bfs;
+    bfs.reserve(nn);
+    bfs.push_back(0);
+    tree.node_lo.reserve(nn);
+    for (size_t head = 0; head < bfs.size(); ++head) {
+        const BNode& b = nodes[bfs[head]];
+        if (b.type == 0 && b.trailing_seq) throw Error("internal: Inner node with a Sequence child");
+        tree.node_lo.push_back(b.lo);
+        tree.node_hi.push_back(b.hi);
+        tree.node_type.push_back(b.type);
+        tree.child_first.push_back(b.children.empty() ? 0u : (u32)bfs.size());
+        tree.child_count.push_back((u32)b.children.size());
+        for (u32 c : b.children) bfs.push_back(c);
+    }
+}
+
 // Tree::new (tree.rs:47-140)
 static std::unique_ptr<Tree> tree_new(std::vector<std::string> lineages, const u64* seq_off, const u8* codes, bool eager_csr = false) {
     const size_t n = lineages.size();
@@ -309,25 +329,268 @@ static std::unique_ptr<Tree> tree_new(std::vector<std::string> lineages, const u
 
     if (eager_csr) build_csr(*tree);  // tree.rs:114-123,134-137; otherwise on first use
     lap(eager_csr ? "k_mer_map (CSR), 2 passes" : "k_mer_map deferred");
-    // flatten: BFS numbering, children contiguous.  Implicit Sequence leaves are dropped: they can neither be emitted
-    // nor change a decision of Lineage::eval_recurse (lineage.rs:119-179) because their parent is never Inner.
-    const size_t nn = nodes.size();
-    std::vector<u32> bfs;
-    bfs.reserve(nn);
-    bfs.push_back(0);
-    tree->node_lo.reserve(nn);
-    for (size_t head = 0; head < bfs.size(); ++head) {
-        const BNode& b = nodes[bfs[head]];
-        if (b.type == 0 && b.trailing_seq) throw Error("internal: Inner node with a Sequence child");
-        tree->node_lo.push_back(b.lo);
-        tree->node_hi.push_back(b.hi);
-        tree->node_type.push_back(b.type);
-        tree->child_first.push_back(b.children.empty() ? 0u : (u32)bfs.size());
-        tree->child_count.push_back((u32)b.children.size());
-        for (u32 c : b.children) bfs.push_back(c);
-    }
+    flatten_nodes(nodes, *tree);
     lap("flatten");
     return tree;
+}
+
+// ---- binary database (tree.rs:146-164): bincode 1.3 default options = little-endian, fixed-width integers, usize and all
+// lengths as u64, enum variants as u32, struct fields in declaration order (tree.rs:36-43, 181-194), no framing -------------
+struct BinWriter {
+    FILE* f;
+    bool ok = true;
+    void raw(const void* p, size_t n) {
+        if (ok && n && fwrite(p, 1, n, f) != n) ok = false;
+    }
+    void u64v(u64 v) { raw(&v, 8); }
+    void u32v(u32 v) { raw(&v, 4); }
+    void str(const std::string& x) {
+        u64v(x.size());
+        raw(x.data(), x.size());
+    }
+};
+
+// The full Node tree of Tree::new (tree.rs:56-127), every Sequence leaf included, as a pure function of the sorted lineages;
+// written depth-first in the field order label, confidence_range, children, node_type.
+struct FullNode {
+    std::string label;
+    u64 lo, hi;
+    u32 type;
+    std::vector<u32> children;
+};
+static void full_nodes(const std::vector<std::string>& lineages, std::vector<FullNode>& nodes) {
+    nodes.clear();
+    nodes.push_back(FullNode{"root", 0, 1, 0, {}});
+    u64 ci = 0;
+    std::vector<std::string> levels;
+    for (const std::string& lineage : lineages) {
+        levels.clear();
+        for (size_t start = 0;;) {
+            const size_t p = lineage.find(',', start);
+            if (p == std::string::npos) {
+                levels.emplace_back(lineage, start);
+                break;
+            }
+            levels.emplace_back(lineage, start, p - start);
+            start = p + 1;
+        }
+        const size_t last = levels.size() - 1;
+        u32 cur = 0;
+        for (size_t level = 0; level < levels.size(); ++level) {
+            const bool have = !nodes[cur].children.empty();
+            if (!have || nodes[nodes[cur].children.back()].label != levels[level]) {
+                const u32 id = (u32)nodes.size();
+                nodes.push_back(FullNode{levels[level], ci, ci + 1, level == last ? 1u : 0u, {}});
+                nodes[cur].children.push_back(id);
+            }
+            nodes[cur].hi = ci + 1;
+            if (level == last) ci += 1;
+            cur = nodes[cur].children.back();
+        }
+        const u32 id = (u32)nodes.size();
+        nodes.push_back(FullNode{nodes[cur].label, ci - 1, ci, 2, {}});
+        nodes[cur].children.push_back(id);
+        nodes[cur].hi = ci;
+    }
+    nodes[0].hi = ci;
+}
+static void write_node(BinWriter& w, const std::vector<FullNode>& nodes, u32 id) {
+    const FullNode& n = nodes[id];
+    w.str(n.label);
+    w.u64v(n.lo);
+    w.u64v(n.hi);
+    w.u64v(n.children.size());
+    for (u32 c : n.children) write_node(w, nodes, c);
+    w.u32v(n.type);
+}
+
+// Tree::save_to_file (tree.rs:146-152)
+static void save_bin(const Tree& t, const char* path) {
+    FILE* f = fopen(path, "wb");
+    if (!f) throw Error(std::string("cannot create ") + path);
+    BinWriter w{f};
+    {
+        std::vector<FullNode> nodes;
+        full_nodes(t.lineages, nodes);
+        write_node(w, nodes, 0);
+    }
+    w.u64v(t.lineages.size());
+    for (const auto& l : t.lineages) w.str(l);
+    {   // sequences: HashMap<Vec<u8>, Vec<u32>> (tree.rs:40), any order; one entry per distinct sequence
+        u64 distinct = 0;
+        std::vector<std::vector<u32>> groups;
+        for (const auto& kv : t.seq_hash) {
+            std::vector<u32> ids = kv.second;  // ascending; usually one sequence per bucket, more only on a 64-bit hash collision
+            while (!ids.empty()) {
+                std::vector<u32> same{ids[0]}, rest;
+                const u64 o0 = t.seq_off[ids[0]], l0 = t.seq_off[ids[0] + 1] - o0;
+                for (size_t j = 1; j < ids.size(); ++j) {
+                    const u64 o = t.seq_off[ids[j]], l = t.seq_off[ids[j] + 1] - o;
+                    if (l == l0 && (l == 0 || memcmp(t.seq_codes.data() + o, t.seq_codes.data() + o0, l) == 0)) same.push_back(ids[j]);
+                    else rest.push_back(ids[j]);
+                }
+                groups.push_back(std::move(same));
+                ids.swap(rest);
+                ++distinct;
+            }
+        }
+        w.u64v(distinct);
+        for (const auto& g : groups) {
+            const u64 o = t.seq_off[g[0]], l = t.seq_off[g[0] + 1] - o;
+            w.u64v(l);
+            w.raw(t.seq_codes.data() + o, l);
+            w.u64v(g.size());
+            w.raw(g.data(), g.size() * 4);
+        }
+    }
+    ensure_csr(t);
+    w.u64v(65536);
+    for (u32 k = 0; k < 65536; ++k) {
+        const u64 a = t.csr_off[k], b = t.csr_off[k + 1];
+        w.u64v(b - a);
+        w.raw(t.csr_ids.data() + a, (b - a) * 4);
+    }
+    w.u64v(t.num_tips);
+    const bool ok = w.ok;
+    if (fclose(f) != 0 || !ok) throw Error(std::string("write error on ") + path);
+}
+
+struct BinReader {
+    const u8* p;
+    const u8* end;
+    struct Fail {};
+    void need(u64 n) const {
+        if ((u64)(end - p) < n) throw Fail{};
+    }
+    u64 u64v() {
+        need(8);
+        u64 v;
+        memcpy(&v, p, 8);
+        p += 8;
+        return v;
+    }
+    u32 u32v() {
+        need(4);
+        u32 v;
+        memcpy(&v, p, 4);
+        p += 4;
+        return v;
+    }
+    const u8* bytes(u64 n) {
+        need(n);
+        const u8* r = p;
+        p += n;
+        return r;
+    }
+};
+// leaf_seq: set when the node is a Sequence node without children in the file -- the implicit leaves Tree::new hangs under every
+// taxon (tree.rs:102-106), which tree_new() above never materialises either
+static u32 read_node(BinReader& r, std::vector<BNode>& nodes, int depth, bool* leaf_seq) {
+    if (depth > 300) throw BinReader::Fail{};
+    const u64 ll = r.u64v();
+    const u8* lb = r.bytes(ll);
+    const u64 lo = r.u64v(), hi = r.u64v();
+    const u64 nc = r.u64v();
+    if (nc > (u64)(r.end - r.p) / 28) throw BinReader::Fail{};  // a node is at least 28 bytes
+    if (lo > 0xFFFFFFFFull || hi > 0xFFFFFFFFull) throw BinReader::Fail{};
+    const u32 id = (u32)nodes.size();
+    nodes.push_back(BNode{std::string((const char*)lb, (size_t)ll), (u32)lo, (u32)hi, 0, {}, false});
+    std::vector<u32> kids;
+    for (u64 c = 0; c < nc; ++c) {
+        const size_t before = nodes.size();
+        bool leaf = false;
+        const u32 cid = read_node(r, nodes, depth + 1, &leaf);
+        if (leaf) nodes.resize(before);
+        else kids.push_back(cid);
+    }
+    const u32 ty = r.u32v();
+    if (ty > 2) throw BinReader::Fail{};
+    nodes[id].type = (u8)ty;
+    nodes[id].children = std::move(kids);
+    *leaf_seq = ty == 2 && nc == 0;
+    return id;
+}
+
+// Tree::load_from_file (tree.rs:154-164): nullptr when the bytes do not deserialise as a Tree (the caller then parses FASTA,
+// parser.rs:37-44).  Databases written with the reference's `huge_db` feature (u64 ids, tree.rs:18-19) do not deserialise here.
+static std::unique_ptr<Tree> load_bin(const u8* data, size_t len) {
+    try {
+        BinReader r{data, data + len};
+        auto tree = std::make_unique<Tree>();
+        std::vector<BNode> nodes;
+        bool root_leaf = false;
+        read_node(r, nodes, 0, &root_leaf);
+        const u64 n = r.u64v();
+        if (n > 0xFFFFFFFFull || n > (u64)(r.end - r.p) / 8) throw BinReader::Fail{};
+        tree->lineages.resize(n);
+        tree->ref_levels.resize(n);
+        for (u64 i = 0; i < n; ++i) {
+            const u64 l = r.u64v();
+            const u8* b = r.bytes(l);
+            tree->lineages[i].assign((const char*)b, (size_t)l);
+            const size_t levels = (size_t)std::count(tree->lineages[i].begin(), tree->lineages[i].end(), ',') + 1;
+            if (levels > 255) throw BinReader::Fail{};
+            tree->ref_levels[i] = (u8)levels;
+        }
+        // sequences: key -> ids; every reference id must occur exactly once
+        const u64 n_keys = r.u64v();
+        if (n_keys > n) throw BinReader::Fail{};
+        std::vector<const u8*> key_of(n, nullptr);
+        std::vector<u64> len_of(n, 0);
+        for (u64 k = 0; k < n_keys; ++k) {
+            const u64 kl = r.u64v();
+            const u8* kb = r.bytes(kl);
+            const u64 ni = r.u64v();
+            if (ni > n) throw BinReader::Fail{};
+            const u8* ib = r.bytes(ni * 4);
+            for (u64 j = 0; j < ni; ++j) {
+                u32 id;
+                memcpy(&id, ib + 4 * j, 4);
+                if (id >= n || key_of[id]) throw BinReader::Fail{};
+                key_of[id] = kb ? kb : data;
+                len_of[id] = kl;
+            }
+        }
+        tree->seq_off.assign(n + 1, 0);
+        for (u64 i = 0; i < n; ++i) {
+            if (!key_of[i]) throw BinReader::Fail{};
+            tree->seq_off[i + 1] = tree->seq_off[i] + len_of[i];
+        }
+        tree->seq_codes.resize(tree->seq_off[n]);
+        for (u64 i = 0; i < n; ++i) {
+            if (len_of[i]) memcpy(tree->seq_codes.data() + tree->seq_off[i], key_of[i], len_of[i]);
+            tree->seq_hash[Tree::hash_bytes(tree->seq_codes.data() + tree->seq_off[i], len_of[i])].push_back((u32)i);
+        }
+        // k_mer_map
+        if (r.u64v() != 65536) throw BinReader::Fail{};
+        tree->csr_off.assign(65537, 0);
+        for (u32 k = 0; k < 65536; ++k) {
+            const u64 l = r.u64v();
+            if (l > n) throw BinReader::Fail{};
+            const u8* b = r.bytes(l * 4);
+            const size_t at = tree->csr_ids.size();
+            tree->csr_ids.resize(at + l);
+            if (l) memcpy(tree->csr_ids.data() + at, b, l * 4);
+            u32 prev = 0;
+            for (u64 j = 0; j < l; ++j) {  // ascending and unique (tree.rs:134-137)
+                const u32 id = tree->csr_ids[at + j];
+                if (id >= n || (j && id <= prev)) throw BinReader::Fail{};
+                prev = id;
+            }
+            tree->csr_off[k + 1] = tree->csr_off[k] + l;
+        }
+        tree->has_csr = true;
+        tree->num_tips = r.u64v();
+        if (tree->num_tips != n || nodes.empty() || nodes[0].lo != 0 || nodes[0].hi != n) throw BinReader::Fail{};
+        flatten_nodes(nodes, *tree);
+        for (size_t i = 0; i < tree->node_lo.size(); ++i)
+            if (tree->node_lo[i] > tree->node_hi[i] || tree->node_hi[i] > n) throw BinReader::Fail{};
+        return tree;
+    } catch (const BinReader::Fail&) {
+        return nullptr;
+    } catch (const Error&) {
+        return nullptr;
+    }
 }
 
 // parser.rs:46-105
@@ -403,6 +666,29 @@ static std::unique_ptr<Queries> parse_query_fasta_str(const char* text, size_t l
     q->labels.push_back(cur_label);  // queries.push(current_query)
     q->off.push_back(q->codes.size());
     return q;
+}
+
+// the closing filter of parser.rs:150-153: drop the queries whose label a checkpoint lists as processed
+static void skip_queries(Queries& q, const char* blob, size_t blob_len) {
+    std::unordered_map<std::string, bool> skip;
+    const char* p = blob;
+    const char* end = blob + blob_len;
+    while (p < end) {  // BufRead::lines of raxtax.ckp (io.rs:213-214)
+        const char* nl = (const char*)memchr(p, '\n', (size_t)(end - p));
+        const char* e = nl ? nl : end;
+        const char* le = (e > p && e[-1] == '\r') ? e - 1 : e;
+        skip.emplace(std::string(p, le), true);
+        p = nl ? nl + 1 : end;
+    }
+    Queries out;
+    out.off.push_back(0);
+    for (size_t i = 0; i < q.size(); ++i) {
+        if (skip.count(q.labels[i])) continue;
+        out.labels.push_back(std::move(q.labels[i]));
+        out.codes.insert(out.codes.end(), q.codes.begin() + (ptrdiff_t)q.off[i], q.codes.begin() + (ptrdiff_t)q.off[i + 1]);
+        out.off.push_back(out.codes.size());
+    }
+    q = std::move(out);
 }
 
 // ---- formatting (lineage.rs:17-48, utils.rs:62-89) ------------------------------------------------------------------
@@ -511,6 +797,37 @@ RXH_API rxh_tree* rxh_tree_from_fasta(const char* text, size_t len) {
     } catch (const std::exception& e) {
         g_err = e.what();
         return nullptr;
+    }
+}
+
+RXH_API rxh_tree* rxh_tree_from_bin(const void* data, size_t len) {
+    auto t = load_bin((const u8*)data, len);
+    if (!t) {
+        g_err = "not a raxtax binary database";
+        return nullptr;
+    }
+    auto h = new rxh_tree();
+    h->t = std::move(t);
+    return h;
+}
+
+RXH_API int rxh_tree_save_bin(const rxh_tree* t, const char* path) {
+    try {
+        save_bin(*t->t, path);
+        return 0;
+    } catch (const std::exception& e) {
+        g_err = e.what();
+        return -1;
+    }
+}
+
+RXH_API int rxh_queries_skip(rxh_queries* q, const char* label_blob, size_t blob_len) {
+    try {
+        skip_queries(*q->q, label_blob, blob_len);
+        return 0;
+    } catch (const std::exception& e) {
+        g_err = e.what();
+        return -1;
     }
 }
 

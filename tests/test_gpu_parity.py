@@ -427,9 +427,44 @@ def test_cli_binary_writes_reference_format_files(tmp_path):
         assert len((prefix / "raxtax.ckp").read_text().splitlines()) == 400
         log = (prefix / "raxtax.log").read_text()
         assert log.startswith("raxtax-b200") and ("Exact sequence match for query" in log) == (not skip)
-        # a second run into the same folder is refused without --redo (io.rs:231-233)
+        assert (prefix / "diptera_sample.bin").is_file() and (prefix / "raxtax.json").is_file()
+        # a second run into the same folder continues from the checkpoint: every query is already processed, nothing is added
         r2 = subprocess.run(cmd, capture_output=True, text=True)
-        assert r2.returncode == 73 and "already exists" in r2.stderr
+        assert r2.returncode == 0 and "Restarting from checkpoint" in r2.stderr
+        assert (prefix / "raxtax.out").read_text().split("\n") == out
+
+
+def test_cli_resumes_from_checkpoint_and_loads_bin(tmp_path):
+    """io.rs:156-230: after an interruption (progress file short, a half-written result line in raxtax.out) the same command
+    finishes the job from raxtax.json / raxtax.ckp with the database read back from the .bin, and the union equals one clean run."""
+    import subprocess
+
+    from raxtax_b200 import _build
+
+    fasta = os.path.join(GOLDEN, "diptera_sample.fasta")
+    clean, prefix = tmp_path / "clean", tmp_path / "resumed"
+    base = [_build.CLI_BIN, "-d", fasta, "-i", fasta, "--tsv"]
+    assert subprocess.run(base + ["-o", str(clean), "--skip-db"], capture_output=True, text=True).returncode == 0
+    assert not list(clean.glob("*.bin"))  # --skip-db
+    assert subprocess.run(base + ["-o", str(prefix)], capture_output=True, text=True).returncode == 0
+    done = (prefix / "raxtax.ckp").read_text().splitlines()
+    assert len(done) == 400
+    keep = set(done[:137])
+    (prefix / "raxtax.ckp").write_text("\n".join(done[:137]) + "\n")
+    for name in ("raxtax.out", "raxtax.tsv"):  # results of unlisted queries stay behind, as after a kill between the two writes
+        lines = (prefix / name).read_text().splitlines()
+        cut = [l for l in lines if l.split("\t")[0] in keep] + [l for l in lines if l.split("\t")[0] == done[137]]
+        (prefix / name).write_text("\n".join(cut) + "\n")
+    r = subprocess.run(base + ["-o", str(prefix)], capture_output=True, text=True)
+    assert r.returncode == 0 and "Restarting from checkpoint" in r.stderr, r.stderr
+    assert sorted((prefix / "raxtax.ckp").read_text().splitlines()) == sorted(done)
+    for name in ("raxtax.out", "raxtax.tsv"):
+        assert sorted((prefix / name).read_text().splitlines()) == sorted((clean / name).read_text().splitlines()), name
+    # --clean afterwards: checkpoint files and the database created under the prefix go, the user's -d file stays
+    r = subprocess.run(base + ["-o", str(prefix), "--clean"], capture_output=True, text=True)
+    assert r.returncode == 0
+    assert not (prefix / "raxtax.json").exists() and not (prefix / "raxtax.ckp").exists() and not list(prefix.glob("*.bin"))
+    assert os.path.exists(fasta)
 
 
 def test_pinned_result_buffers_match_pageable(ctx):

@@ -187,10 +187,16 @@ def test_cli_exit_codes_without_gpu(tmp_path):
 
     import torch
 
+    # a missing database cannot be fingerprinted: Args::get_output fails -> CANTCREAT (main.rs:25-30, io.rs:31-33)
     r = subprocess.run([_build.CLI_BIN, "-d", "/nonexistent.fasta", "-i", "/nonexistent.fasta", "-o", str(tmp_path / "o1")], capture_output=True, text=True)
-    assert r.returncode == 66 and "Failed to parse" in r.stderr
-    r = subprocess.run([_build.CLI_BIN, "--only-db", "-d", "x"], capture_output=True, text=True)
     assert r.returncode == 73
+    r = subprocess.run([_build.CLI_BIN, "--only-db", "-d", "x", "-o", str(tmp_path / "o0")], capture_output=True, text=True)
+    assert r.returncode == 73
+    # neither a binary database nor FASTA -> NOINPUT (main.rs:61-71)
+    bad = tmp_path / "bad.fasta"
+    bad.write_text("this is not fasta\n")
+    r = subprocess.run([_build.CLI_BIN, "-d", str(bad), "-i", str(bad), "-o", str(tmp_path / "o3")], capture_output=True, text=True)
+    assert r.returncode == 66 and "Failed to parse" in r.stderr and "Not a valid FASTA file" in r.stderr
     if not torch.cuda.is_available():
         fasta = os.path.join(ROOT, "tests", "golden", "diptera_sample.fasta")
         r = subprocess.run([_build.CLI_BIN, "-d", fasta, "-i", fasta, "-o", str(tmp_path / "o2")], capture_output=True, text=True)
@@ -214,3 +220,40 @@ def test_kmer_map_is_lazy_and_identical_to_the_oracles():
     assert eager.has_kmer_map
     eoff, eids = eager.csr()
     assert np.array_equal(off, eoff) and np.array_equal(ids, eids)
+
+
+def test_cli_only_db_writes_the_reference_database_and_checkpoint(tmp_path):
+    """--only-db needs no GPU: <prefix>/<stem>.bin in the reference's bincode layout + raxtax.json (io.rs:47-78,269-286; main.rs:73-102);
+    a .bin passed as -d is loaded instead of parsed (parser.rs:37-44)."""
+    import json
+    import subprocess
+
+    from tests import bincode_model as bm
+
+    fasta = os.path.join(ROOT, "tests", "golden", "diptera_sample.fasta")
+    prefix = tmp_path / "db"
+    r = subprocess.run([_build.CLI_BIN, "--only-db", "-d", fasta, "-o", str(prefix)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    db = prefix / "diptera_sample.bin"
+    t = bm.deserialize(db.read_bytes())
+    assert t["num_tips"] == 400 and len(t["lineages"]) == 400 and t["lineages"] == sorted(t["lineages"], key=str.encode)
+    assert len(t["k_mer_map"]) == 65536 and t["root"][0] == "root" and t["root"][1:3] == [0, 400]
+    ck = json.loads((prefix / "raxtax.json").read_text())
+    assert set(ck) == {"checkpoint_file", "progress_file", "db_fingerprint", "raw_confidence", "skip_exact_matches", "tsv"}
+    assert ck["db_fingerprint"]["path"] == str(db) and ck["db_fingerprint"]["size"] == db.stat().st_size
+    assert ck["progress_file"] == str(prefix / "raxtax.ckp") and ck["tsv"] is False
+    # again into the same folder: the checkpoint is valid, the database is read back from the .bin, nothing is rebuilt
+    before = db.stat().st_mtime_ns
+    r = subprocess.run([_build.CLI_BIN, "--only-db", "-d", fasta, "-o", str(prefix)], capture_output=True, text=True)
+    assert r.returncode == 0 and "Restarting from checkpoint" in r.stderr and db.stat().st_mtime_ns == before
+    # the .bin as the database of a fresh run
+    other = tmp_path / "other"
+    r = subprocess.run([_build.CLI_BIN, "--only-db", "-d", str(db), "-o", str(other)], capture_output=True, text=True)
+    assert r.returncode == 0 and not list(other.glob("*.bin"))
+    # same content as parsing the FASTA
+    a = capi.Tree.from_bin(db.read_bytes())
+    b = capi.Tree.from_fasta(open(fasta).read())
+    assert a.lineages == b.lineages
+    ao, ai = a.csr()
+    bo, bi = b.csr()
+    assert np.array_equal(ao, bo) and np.array_equal(ai, bi)
