@@ -70,7 +70,7 @@ void rxh_queries_arrays(const rxh_queries* q, const uint64_t** seq_offsets, cons
 
 /* ---- driver ------------------------------------------------------------------------------------------------
  * sender(user, query_label, primary_results, tsv_results_or_NULL) is called once per query, in query order,
- * from the calling thread; a non-zero return aborts the run like a failed channel send (raxtax.rs:87).
+ * from the calling thread (rxh_raxtax; see rxh_raxtax_multi for several GPUs); a non-zero return aborts the run like a failed channel send (raxtax.rs:87).
  * logger(user, level, message) receives the Info / Warn lines the reference writes to raxtax.log
  * (raxtax.rs:46-52): level 2 = Warn, 3 = Info.  chunk_size = queries per device batch (0 = all at once).
  * Returns 0, or -1 on error; *warnings (may be NULL) is set when exact matches disagreed above the leaf level
@@ -81,6 +81,14 @@ typedef void (*rxh_logger)(void* user, int level, const char* message);
 
 int rxh_raxtax(rtx_ctx* ctx, const rxh_queries* queries, const rxh_tree* tree, int skip_exact_matches, int raw_confidence,
                size_t chunk_size, rxh_sender sender, void* sender_user, int tsv, rxh_logger logger, void* logger_user, int* warnings);
+
+/* The same over several GPUs of one box (BASELINE config 3: queries partitioned, index replicated, no collective): ctxs[i] each hold
+ * the whole index of `tree` (rxh_tree_upload); one host thread per context pulls chunks of chunk_size queries (0 = ~8 chunks per
+ * context, >= 4096 queries) from a shared counter, as rayon's par_chunks does for the reference (raxtax.rs:35-39, main.rs:119-124).
+ * sender / logger are serialised; queries arrive in completion order (the reference's channel gives no order either). */
+int rxh_raxtax_multi(rtx_ctx* const* ctxs, size_t n_ctx, const rxh_queries* queries, const rxh_tree* tree, int skip_exact_matches,
+                     int raw_confidence, size_t chunk_size, rxh_sender sender, void* sender_user, int tsv, rxh_logger logger,
+                     void* logger_user, int* warnings);
 
 /* exact-match lookup for a whole batch (the host half of raxtax.rs:42): fills exact_offsets[n+1]; returns the
  * total number of ids; writes at most cap ids */

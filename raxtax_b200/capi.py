@@ -37,7 +37,7 @@ DEVICE_SYMBOLS = [
 HOST_SYMBOLS = [
     "rxh_last_error", "rxh_tree_from_fasta", "rxh_tree_from_bin", "rxh_tree_save_bin", "rxh_queries_skip", "rxh_tree_new", "rxh_tree_free", "rxh_tree_num_tips", "rxh_tree_lineage",
     "rxh_tree_csr", "rxh_tree_build_kmer_map", "rxh_tree_has_kmer_map", "rxh_tree_exact", "rxh_tree_index_desc", "rxh_tree_upload", "rxh_tree_upload_sharded", "rxh_queries_from_fasta", "rxh_queries_new",
-    "rxh_queries_free", "rxh_queries_len", "rxh_queries_label", "rxh_queries_arrays", "rxh_raxtax", "rxh_exact_batch",
+    "rxh_queries_free", "rxh_queries_len", "rxh_queries_label", "rxh_queries_arrays", "rxh_raxtax", "rxh_raxtax_multi", "rxh_exact_batch",
 ]
 
 
@@ -173,6 +173,8 @@ def host_lib():
     L.rxh_queries_arrays.restype = None
     L.rxh_raxtax.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_size_t, SENDER, C.c_void_p, C.c_int,
                              LOGGER, C.c_void_p, C.POINTER(C.c_int)]
+    L.rxh_raxtax_multi.argtypes = [C.POINTER(C.c_void_p), C.c_size_t, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_size_t, SENDER, C.c_void_p,
+                                   C.c_int, LOGGER, C.c_void_p, C.POINTER(C.c_int)]
     L.rxh_exact_batch.restype = C.c_uint64
     L.rxh_exact_batch.argtypes = [C.c_void_p, C.c_size_t, u64p, u8p, u32p, u32p, C.c_uint64]
     _host = L
@@ -631,8 +633,13 @@ def raxtax(ctx: Context, queries: Queries, tree: Tree, skip_exact_matches=False,
         logs.append((level, msg.decode()))
 
     warn = C.c_int(0)
-    rc = host_lib().rxh_raxtax(ctx._h, queries._h, tree._h, int(skip_exact_matches), int(raw_confidence), int(chunk_size), SENDER(_send),
-                               None, int(tsv), LOGGER(_log), None, C.byref(warn))
+    if isinstance(ctx, (list, tuple)):  # several GPUs (or several contexts on one): rxh_raxtax_multi, results in completion order
+        arr = (C.c_void_p * len(ctx))(*[c._h for c in ctx])
+        rc = host_lib().rxh_raxtax_multi(arr, len(ctx), queries._h, tree._h, int(skip_exact_matches), int(raw_confidence), int(chunk_size),
+                                         SENDER(_send), None, int(tsv), LOGGER(_log), None, C.byref(warn))
+    else:
+        rc = host_lib().rxh_raxtax(ctx._h, queries._h, tree._h, int(skip_exact_matches), int(raw_confidence), int(chunk_size), SENDER(_send),
+                                   None, int(tsv), LOGGER(_log), None, C.byref(warn))
     if rc != 0:
         raise _host_err()
     return sent, logs, bool(warn.value)

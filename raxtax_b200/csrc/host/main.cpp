@@ -2,7 +2,7 @@
 //
 // Mirrors the reference's CLI surface, output files and restart behaviour (src/io.rs:112-300, src/main.rs:14-173):
 //   raxtax -d <db.fasta[.gz] | db.bin> -i <queries.fasta[.gz]> [-o PREFIX] [--skip-exact-matches] [--raw-confidence] [--tsv]
-//          [--redo] [--only-db] [--skip-db] [-c] [-t N] [--pin] [-v|-q] [--gpu N] [--batch N]
+//          [--redo] [--only-db] [--skip-db] [-c] [-t N] [--pin] [-v|-q] [--gpu N] [--gpus N] [--batch N]
 // writes <PREFIX>/raxtax.out, raxtax.log, raxtax.ckp, raxtax.json and (with --tsv) raxtax.tsv in the reference's formats
 // (lineage.rs:17-48), and <PREFIX>/<database stem>.bin, the bincode database of tree.rs:146-164, unless --skip-db.
 // A database path that deserialises as such a .bin is loaded instead of parsed (parser.rs:37-44).  An interrupted run is
@@ -15,6 +15,7 @@
 #include <sys/stat.h>
 #include <zlib.h>
 
+#include <algorithm>
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -36,7 +37,7 @@ struct Args {
     std::string database_path, query_file, prefix = "raxtax";
     bool skip_exact_matches = false, tsv = false, only_db = false, skip_db = false, clean = false, raw_confidence = false, redo = false,
          pin = false;
-    int threads = 0, verbosity = 3 /* Info */, gpu = 0;
+    int threads = 0, verbosity = 3 /* Info */, gpu = 0, gpus = 1;
     size_t batch = 0;
 };
 
@@ -56,7 +57,9 @@ void usage() {
             "  -o, --prefix <PREFIX>                Output prefix [default: raxtax]\n"
             "      --redo                           Force override of existing output files\n"
             "      --pin                            Accepted for compatibility\n"
-            "      --gpu <ORDINAL>                  CUDA device to use [default: 0]\n"
+            "      --gpu <ORDINAL>                  First CUDA device to use [default: 0]\n"
+            "      --gpus <N>                       Number of GPUs (ORDINAL .. ORDINAL+N-1): queries are partitioned, the index is\n"
+            "                                       replicated [default: 1]\n"
             "      --batch <N>                      Queries per device batch [default: all]\n"
             "  -v / -q                              More / less output\n");
 }
@@ -283,6 +286,7 @@ int main(int argc, char** argv) {
         else if (s == "--redo") a.redo = true;
         else if (s == "--pin") a.pin = true;
         else if (s == "--gpu") a.gpu = atoi(val("--gpu"));
+        else if (s == "--gpus") a.gpus = std::max(1, atoi(val("--gpus")));
         else if (s == "--batch") a.batch = (size_t)atoll(val("--batch"));
         else if (s == "-v") a.verbosity = 4;
         else if (s == "-q") a.verbosity = 2;
@@ -448,18 +452,22 @@ int main(int argc, char** argv) {
         rxh_queries_skip(queries, blob.data(), blob.size());
     }
 
-    rtx_ctx* ctx = nullptr;
-    if (rtx_ctx_create(a.gpu, &ctx) != 0) {
-        fprintf(stderr, "\x1b[31m[ERROR]\x1b[0m %s\n", rtx_last_error(nullptr));
-        return EX_TEMPFAIL_;
-    }
-    if (rxh_tree_upload(tree, ctx, 0, 0) != 0) {
-        fprintf(stderr, "\x1b[31m[ERROR]\x1b[0m index upload: %s\n", rxh_last_error());
-        return EX_TEMPFAIL_;
+    // one context per GPU, the index replicated on each (BASELINE config 3: query-partitioned, no collective)
+    std::vector<rtx_ctx*> ctxs((size_t)a.gpus, nullptr);
+    for (int g = 0; g < a.gpus; ++g) {
+        if (rtx_ctx_create(a.gpu + g, &ctxs[(size_t)g]) != 0) {
+            fprintf(stderr, "\x1b[31m[ERROR]\x1b[0m %s\n", rtx_last_error(nullptr));
+            return EX_TEMPFAIL_;
+        }
+        if (rxh_tree_upload(tree, ctxs[(size_t)g], 0, 0) != 0) {
+            fprintf(stderr, "\x1b[31m[ERROR]\x1b[0m index upload: %s\n", rxh_last_error());
+            return EX_TEMPFAIL_;
+        }
     }
     int warnings = 0;
     auto t0 = std::chrono::steady_clock::now();
-    int rc = rxh_raxtax(ctx, queries, tree, a.skip_exact_matches, a.raw_confidence, a.batch, send_cb, &w, a.tsv, log_cb, &w, &warnings);
+    int rc = rxh_raxtax_multi(ctxs.data(), ctxs.size(), queries, tree, a.skip_exact_matches, a.raw_confidence, a.batch, send_cb, &w, a.tsv,
+                              log_cb, &w, &warnings);
     double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     if (rc != 0) {
         fprintf(stderr, "\x1b[31m[ERROR]\x1b[0m Error while sending results to IO-thread!: %s\n", rxh_last_error());
@@ -483,6 +491,6 @@ int main(int argc, char** argv) {
     }
     rxh_queries_free(queries);
     rxh_tree_free(tree);
-    rtx_ctx_destroy(ctx);
+    for (rtx_ctx* c : ctxs) rtx_ctx_destroy(c);
     return EX_OK_;
 }

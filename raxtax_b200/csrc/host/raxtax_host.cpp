@@ -9,6 +9,7 @@
 // rtx_index_upload directly; the per-query numerics all run on the GPU through include/raxtax_b200.h.
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cstdint>
 #include <cstdio>
@@ -18,6 +19,7 @@
 #include <numeric>
 #include <stdexcept>
 #include <string>
+#include <thread>
 #include <unordered_map>
 #include <vector>
 
@@ -964,15 +966,35 @@ RXH_API uint64_t rxh_exact_batch(const rxh_tree* t, size_t n, const uint64_t* se
     return total;
 }
 
-// raxtax::raxtax (raxtax.rs:14-97)
-RXH_API int rxh_raxtax(rtx_ctx* ctx, const rxh_queries* queries, const rxh_tree* tree_h, int skip_exact_matches, int raw_confidence,
-                       size_t chunk_size, rxh_sender sender, void* sender_user, int tsv, rxh_logger logger, void* logger_user, int* warnings) {
-    try {
-        const Tree& tree = *tree_h->t;
-        const Queries& qs = *queries->q;
-        const size_t nq = qs.size();
-        if (warnings) *warnings = 0;
-        if (chunk_size == 0) chunk_size = nq ? nq : 1;
+// raxtax::raxtax (raxtax.rs:14-97).  The reference fans chunks of queries out over the rayon pool (raxtax.rs:35-39); here every
+// context (= GPU, index replicated) has one host thread pulling chunks from a shared counter, with no collective between them;
+// sender and logger are called under one mutex, the lines of a query contiguous, queries in completion order as in the reference.
+namespace {
+struct Worker {
+    const Tree& tree;
+    const Queries& qs;
+    const size_t nq;
+    size_t chunk_size;
+    const int skip_exact_matches, raw_confidence, tsv;
+    rxh_sender sender;
+    void* sender_user;
+    rxh_logger logger;
+    void* logger_user;
+    std::atomic<size_t> next_chunk{0};
+    std::atomic<bool> failed{false}, warned{false};
+    std::mutex io_mtx{}, err_mtx{};
+    std::string err{};
+
+    void run(rtx_ctx* ctx) {
+        try {
+            run_inner(ctx);
+        } catch (const std::exception& e) {
+            failed.store(true);
+            std::lock_guard<std::mutex> g(err_mtx);
+            if (err.empty()) err = e.what();
+        }
+    }
+    void run_inner(rtx_ctx* ctx) {
         const u32 ML = rtx_index_max_levels(ctx);
         if (rtx_index_n_refs(ctx) != tree.num_tips) throw Error("the context's index does not belong to this tree");
         std::vector<u32> exact_off, exact_ids, first_ref, result_begin;
@@ -981,8 +1003,9 @@ RXH_API int rxh_raxtax(rtx_ctx* ctx, const rxh_queries* queries, const rxh_tree*
         std::vector<double> conf, local, global;
         std::vector<u32> ex;
         std::string primary, tsv_out, msg;
-        bool warned = false;
-        for (size_t c0 = 0; c0 < nq; c0 += chunk_size) {
+        while (true) {
+            const size_t c0 = next_chunk.fetch_add(1) * chunk_size;
+            if (c0 >= nq || failed.load()) break;
             const size_t cn = std::min(chunk_size, nq - c0);
             exact_off.assign(cn + 1, 0);
             exact_ids.clear();
@@ -998,6 +1021,7 @@ RXH_API int rxh_raxtax(rtx_ctx* ctx, const rxh_queries* queries, const rxh_tree*
                         const std::string& l = tree.lineages[ex[j]];
                         if (logger) {
                             msg = "Exact sequence match for query " + qs.labels[q] + ": " + l;
+                            std::lock_guard<std::mutex> g(io_mtx);
                             logger(logger_user, 3, msg.c_str());
                         }
                         size_t p = l.rfind(',');
@@ -1009,9 +1033,10 @@ RXH_API int rxh_raxtax(rtx_ctx* ctx, const rxh_queries* queries, const rxh_tree*
                     if (!all_equal) {
                         if (logger) {
                             msg = "Exact matches for " + qs.labels[q] + " differ above the leafs of the lineage tree!";
+                            std::lock_guard<std::mutex> g(io_mtx);
                             logger(logger_user, 2, msg.c_str());
                         }
-                        warned = true;
+                        warned.store(true);
                     }
                 }
             }
@@ -1065,14 +1090,48 @@ RXH_API int rxh_raxtax(rtx_ctx* ctx, const rxh_queries* queries, const rxh_tree*
                         tsv_string(tsv_out, qs.labels[q], rv, seq);
                     }
                 }
-                if (sender && sender(sender_user, qs.labels[q].c_str(), primary.c_str(), tsv ? tsv_out.c_str() : nullptr) != 0)
-                    throw Error("sending on a disconnected channel (raxtax.rs:87)");
+                if (sender) {
+                    std::lock_guard<std::mutex> g(io_mtx);
+                    if (sender(sender_user, qs.labels[q].c_str(), primary.c_str(), tsv ? tsv_out.c_str() : nullptr) != 0)
+                        throw Error("sending on a disconnected channel (raxtax.rs:87)");
+                }
             }
         }
-        if (warnings) *warnings = warned ? 1 : 0;
-        return 0;
-    } catch (const std::exception& e) {
-        g_err = e.what();
+    }
+};
+}  // namespace
+
+RXH_API int rxh_raxtax_multi(rtx_ctx* const* ctxs, size_t n_ctx, const rxh_queries* queries, const rxh_tree* tree_h, int skip_exact_matches,
+                             int raw_confidence, size_t chunk_size, rxh_sender sender, void* sender_user, int tsv, rxh_logger logger,
+                             void* logger_user, int* warnings) {
+    if (warnings) *warnings = 0;
+    if (!ctxs || n_ctx == 0 || !queries || !tree_h) {
+        g_err = "rxh_raxtax_multi: no context";
         return -1;
     }
+    const size_t nq = queries->q->size();
+    if (chunk_size == 0) {  // one chunk per context and pass when there is one context; else ~8 chunks per context, at least 4096 queries
+        chunk_size = n_ctx == 1 ? std::max<size_t>(nq, 1) : std::max<size_t>(4096, (nq + n_ctx * 8 - 1) / (n_ctx * 8));
+    }
+    Worker w{*tree_h->t, *queries->q, nq, chunk_size, skip_exact_matches, raw_confidence, tsv, sender, sender_user, logger, logger_user};
+    if (n_ctx == 1) w.run(ctxs[0]);
+    else {
+        std::vector<std::thread> th;
+        for (size_t i = 0; i < n_ctx; ++i) th.emplace_back([&w, ctx = ctxs[i]] { w.run(ctx); });
+        for (auto& t : th) t.join();
+    }
+    if (warnings) *warnings = w.warned.load() ? 1 : 0;
+    if (w.failed.load()) {
+        g_err = w.err;
+        return -1;
+    }
+    return 0;
 }
+
+RXH_API int rxh_raxtax(rtx_ctx* ctx, const rxh_queries* queries, const rxh_tree* tree_h, int skip_exact_matches, int raw_confidence,
+                       size_t chunk_size, rxh_sender sender, void* sender_user, int tsv, rxh_logger logger, void* logger_user, int* warnings) {
+    rtx_ctx* one[1] = {ctx};
+    return rxh_raxtax_multi(one, 1, queries, tree_h, skip_exact_matches, raw_confidence, chunk_size, sender, sender_user, tsv, logger,
+                            logger_user, warnings);
+}
+

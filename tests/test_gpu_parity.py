@@ -484,3 +484,22 @@ def test_pinned_result_buffers_match_pageable(ctx):
         assert np.array_equal(a.n_kmers, b.n_kmers) and np.array_equal(a.global_signal, b.global_signal)
         assert np.array_equal(a.first_ref, b.first_ref[:n]) and np.array_equal(a.n_levels, b.n_levels[:n])
         assert np.array_equal(a.confidence, b.confidence[:n]) and np.array_equal(a.local_signal, b.local_signal[:n])
+
+
+def test_raxtax_multi_context_equals_single(ctx):
+    """rxh_raxtax_multi (one host thread per context, chunks from a shared counter) sends exactly the lines rxh_raxtax sends;
+    two contexts on the one GPU of the test box stand in for two GPUs."""
+    ds = synth.generate("small", measure=False)
+    ht = capi.Tree.new(ds.ref_lineages, ds.ref_off, ds.ref_codes)
+    qs = capi.Queries.new(ds.query_labels, ds.query_off, ds.query_codes)
+    ctx.upload_tree(ht)
+    one, logs1, warn1 = capi.raxtax(ctx, qs, ht, tsv=True)
+    other = capi.Context(0)
+    try:
+        other.upload_tree(ht)
+        two, logs2, warn2 = capi.raxtax([ctx, other], qs, ht, chunk_size=17, tsv=True)
+    finally:
+        other.close()
+    assert [r[0] for r in one] == ds.query_labels  # single context: query order
+    assert sorted(two) == sorted(one) and len(two) == len(one)
+    assert sorted(logs1) == sorted(logs2) and warn1 == warn2
