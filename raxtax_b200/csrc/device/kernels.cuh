@@ -506,19 +506,23 @@ __device__ __forceinline__ uint4 ldg_l1(const uint4* p) {
     asm volatile("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
     return r;
 }
-template <int V, typename vec_t>
+template <int V, bool L1A, typename vec_t>
 __device__ __forceinline__ void load16_l1(vec_t (&x)[16], const u32* __restrict__ colbase, const u32* __restrict__ srow, u32 j, u32 row_bytes) {
     u32 r[16];
     row_ids16(r, srow, j);
 #pragma unroll
-    for (int i = 0; i < 16; ++i) x[i] = ldg_l1(reinterpret_cast<const vec_t*>(reinterpret_cast<const char*>(colbase) + (u64)r[i] * 512u));
+    for (int i = 0; i < 16; ++i) {
+        const vec_t* p = reinterpret_cast<const vec_t*>(reinterpret_cast<const char*>(colbase) + (u64)r[i] * 512u);
+        x[i] = L1A ? ldg_l1(p) : ldg_stream(p);
+    }
 }
 
 constexpr int kHitGroupMaxThreads = 512;
 
 // LOCKSTEP = false drops the chunk bookkeeping and every block barrier (the warps of a CTA then only share the launch).
 // (A 96-register build, 5 CTAs x 4 warps per SM instead of 4 x 4, spills and measured 6 % slower.)
-template <int V, int NP, bool LOCKSTEP, int MAX_THREADS, int CTAS_PER_SM>
+// L1A: row loads allocate in the L1 (rows shared by the warps of a CTA may hit) or bypass it (no fill wavefronts on the L1 data pipe)
+template <int V, int NP, bool LOCKSTEP, int MAX_THREADS, int CTAS_PER_SM, bool L1A = true>
 __global__ void __launch_bounds__(MAX_THREADS, CTAS_PER_SM)
     hitcount_group_kernel(IndexView ix, BatchView b, u16* __restrict__ counts, int q_base, int q_count, int tiles_per_cta, int n_tiles,
                           u32 chunk_rows, int n_chunks) {
@@ -571,7 +575,7 @@ __global__ void __launch_bounds__(MAX_THREADS, CTAS_PER_SM)
             for (int p = 0; p < NP; ++p) pl[v][p] = 0;
         int c = 0;
         vec_t xa[16], xb[16];
-        if (n) load16_l1<V>(xa, colbase, srow, 0, row_bytes);
+        if (n) load16_l1<V, L1A>(xa, colbase, srow, 0, row_bytes);
         for (u32 j = 0; j < n; j += 32) {
             while (LOCKSTEP && c < n_chunks && j >= (u32)cpos[c]) {  // this warp is done with chunk c: wait for the others
                 __syncthreads();
@@ -579,9 +583,9 @@ __global__ void __launch_bounds__(MAX_THREADS, CTAS_PER_SM)
             }
             const bool has_b = j + 16 < n;
             u32 ea[V], eb[V];
-            if (has_b) load16_l1<V>(xb, colbase, srow, j + 16, row_bytes);
+            if (has_b) load16_l1<V, L1A>(xb, colbase, srow, j + 16, row_bytes);
             fold16_carry<V, NP>(pl, xa, ea);
-            if (j + 32 < n) load16_l1<V>(xa, colbase, srow, j + 32, row_bytes);
+            if (j + 32 < n) load16_l1<V, L1A>(xa, colbase, srow, j + 32, row_bytes);
             if (has_b) fold16_carry<V, NP>(pl, xb, eb);
             else {
 #pragma unroll
@@ -1751,8 +1755,7 @@ __global__ void __launch_bounds__(256) result_gather_kernel(ResultPool pool, con
 // =========================================================================================================
 constexpr u32 kBfsEntries = 512;   // significant nodes + fallback chain nodes of one query
 constexpr u32 kBfsFrontier = 256;  // nodes of one level / simultaneously active fallback chains
-constexpr int kBfsThreads = 256;
-constexpr int kBfsWarps = kBfsThreads / 32;
+constexpr int kBfsThreadsDefault = 256;  // CTA size of lineage_bfs_kernel (template parameter: RTX_OPT_WALK_VARIANT 2 runs 128)
 
 struct BfsSmem {
     unsigned long long* best;  // [F] arg-max value (bits of a non-negative double)
@@ -1823,9 +1826,11 @@ __device__ __forceinline__ u32 bfs_owner(const u32* __restrict__ fr_off, u32 n, 
     return lo;
 }
 
+template <int kBfsThreads>
 __global__ void __launch_bounds__(kBfsThreads)
     lineage_bfs_kernel(IndexView ix, const NodeRec* __restrict__ recs, BatchView b, ResultPool pool, ProbScratch sc, int q_base, int q_count,
                        u32 entry_cap) {
+    constexpr int kBfsWarps = kBfsThreads / 32;
     extern __shared__ __align__(16) unsigned char bsm_raw[];
     __shared__ u32 s_log_n, s_lvl_begin, s_lvl_end, s_n_res, s_n_fb, s_n_next, s_retry;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;

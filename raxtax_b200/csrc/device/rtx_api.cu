@@ -859,7 +859,8 @@ RTX_API int rtx_batch_upload(rtx_ctx* ctx, const rtx_batch* batch) {
     CU(cudaFuncSetAttribute(lineage_walk_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->walk_smem));
     CU(cudaFuncSetAttribute(lineage_walk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->walk_smem));
     ctx->bfs_smem = BfsSmem::bytes(ctx->ix.max_levels);
-    CU(cudaFuncSetAttribute(lineage_bfs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->bfs_smem));
+    CU(cudaFuncSetAttribute(lineage_bfs_kernel<kBfsThreadsDefault>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->bfs_smem));
+    CU(cudaFuncSetAttribute(lineage_bfs_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->bfs_smem));
     ctx->shard_phase = 0;
     const int slots = (int)std::min<u64>((u64)ctx->n_sms * occ, sb);
     ctx->prob_slots = slots;
@@ -978,6 +979,7 @@ static cudaError_t launch_hitcount_group(rtx_ctx* c, int q_base, int qb, int G) 
         return cudaGetLastError();
     };
     if (n_chunks > 1) return go(hitcount_group_kernel<V, NP, true, kHitGroupMaxThreads, 1>);
+    if (c->hit_tune == 1) return go(hitcount_group_kernel<V, NP, false, kHitGroupMaxThreads, 1, false>);  // L1 bypass (measured option)
     return go(hitcount_group_kernel<V, NP, false, kHitGroupMaxThreads, 1>);
 }
 
@@ -1098,13 +1100,18 @@ static int run_all(rtx_ctx* ctx) {
         }
         {
             LaunchTimer lt(ctx, RTX_K_WALK);
-            if (ctx->walk_variant == 0) {  // level-synchronous walk, then the depth-first walker for the queries it handed back
-                lineage_bfs_kernel<<<qb, kBfsThreads, ctx->bfs_smem, ctx->cur_stream>>>(
-                    ctx->ix, ctx->d_recs.as<NodeRec>(), bv, ctx->pool, *ctx->cur_sc, (int)q0, qb, ctx->walk_log_cap ? (u32)ctx->walk_log_cap : kBfsEntries);
+            if (ctx->walk_variant == 0 || ctx->walk_variant == 2) {  // level-synchronous walk, then the depth-first walker for the queries it handed back
+                const u32 cap = ctx->walk_log_cap ? (u32)ctx->walk_log_cap : kBfsEntries;
+                if (ctx->walk_variant == 2)
+                    lineage_bfs_kernel<128><<<qb, 128, ctx->bfs_smem, ctx->cur_stream>>>(ctx->ix, ctx->d_recs.as<NodeRec>(), bv, ctx->pool,
+                                                                                         *ctx->cur_sc, (int)q0, qb, cap);
+                else
+                    lineage_bfs_kernel<kBfsThreadsDefault><<<qb, kBfsThreadsDefault, ctx->bfs_smem, ctx->cur_stream>>>(
+                        ctx->ix, ctx->d_recs.as<NodeRec>(), bv, ctx->pool, *ctx->cur_sc, (int)q0, qb, cap);
                 CU(cudaGetLastError());
             }
             lineage_walk_kernel<false><<<(qb + kWalkWarps - 1) / kWalkWarps, kWalkWarps * 32, ctx->walk_smem, ctx->cur_stream>>>(
-                ctx->ix, ctx->d_recs.as<NodeRec>(), bv, ctx->pool, *ctx->cur_sc, ShardView{}, (int)q0, qb, ctx->walk_variant == 0 ? 1 : 0);
+                ctx->ix, ctx->d_recs.as<NodeRec>(), bv, ctx->pool, *ctx->cur_sc, ShardView{}, (int)q0, qb, ctx->walk_variant != 1 ? 1 : 0);
             CU(cudaGetLastError());
         }
         if (ctx->tap_counts_host) {

@@ -2,7 +2,8 @@
 
 usage: sweep_hitcount.py [workload] [configs]     configs = comma-separated words of letter+number fields, e.g.  G16C0,G8C12,G1T12M4
    G = RTX_OPT_HITCOUNT_GROUP (queries per CTA; 1 = single-query kernel), C = RTX_OPT_HITCOUNT_CHUNKS, T = RTX_OPT_HITCOUNT_TUNE,
-   M = RTX_OPT_HITCOUNT_MAX_TILES, S = RTX_OPT_SUB_BATCH (queries per device sub-batch).  Every configuration's histograms are compared with the first one's (bit-exact).
+   M = RTX_OPT_HITCOUNT_MAX_TILES, S = RTX_OPT_SUB_BATCH (queries per device sub-batch), W = RTX_OPT_WALK_VARIANT
+   (group kernel: T1 = row loads bypass the L1).  Every configuration's histograms are compared with the first one's (bit-exact).
 """
 import json
 import os
@@ -24,10 +25,10 @@ ctx.upload_tree(tree)
 eo, eids = tree.exact_batch(ds.query_off, ds.query_codes)
 ctx.batch_upload(ds.query_off, ds.query_codes, eo, eids)
 OPT = {"G": capi.RTX_OPT_HITCOUNT_GROUP, "C": capi.RTX_OPT_HITCOUNT_CHUNKS, "T": capi.RTX_OPT_HITCOUNT_TUNE, "M": capi.RTX_OPT_HITCOUNT_MAX_TILES,
-       "S": capi.RTX_OPT_SUB_BATCH}
+       "S": capi.RTX_OPT_SUB_BATCH, "W": capi.RTX_OPT_WALK_VARIANT}
 ref = None
 for cfg in configs:
-    f = {k: int(v) for k, v in re.findall(r"([GCTMS])(\d+)", cfg)}
+    f = {k: int(v) for k, v in re.findall(r"([GCTMSW])(\d+)", cfg)}
     for k, o in OPT.items():
         ctx.set_option(o, f.get(k, 0))
     ctx.batch_upload(ds.query_off, ds.query_codes, eo, eids)  # the sub-batch size is fixed at upload time
