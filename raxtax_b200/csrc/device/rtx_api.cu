@@ -317,7 +317,7 @@ RTX_API int rtx_ctx_set_option(rtx_ctx* ctx, int option, int64_t value) {
             ctx->pipeline_opt = value != 0;
             return RTX_OK;
         case RTX_OPT_WALK_VARIANT:
-            REQUIRE(value == 0 || value == 1, "unknown walk variant");
+            REQUIRE(value >= 0 && value <= 2, "unknown walk variant");  // 2: level-synchronous walk with 128-thread CTAs
             ctx->walk_variant = (int)value;
             return RTX_OK;
         case RTX_OPT_WALK_LOG_CAP:
@@ -333,7 +333,8 @@ RTX_API int rtx_ctx_set_option(rtx_ctx* ctx, int option, int64_t value) {
             ctx->hit_chunks = (int)value;
             return RTX_OK;
         case RTX_OPT_HITCOUNT_TUNE:
-            REQUIRE(value >= 0 && value < 1000 && (value % 10 == 0 || value % 10 == 2 || value % 10 == 4), "bad hit-count tuning word");
+            REQUIRE(value == 1 || (value >= 0 && value < 1000 && (value % 10 == 0 || value % 10 == 2 || value % 10 == 4)),
+                    "bad hit-count tuning word");  // 1: query-group kernel with L1-bypassing row loads
             ctx->hit_tune = (int)value;
             return RTX_OK;
         default:

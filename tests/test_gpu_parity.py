@@ -503,3 +503,49 @@ def test_raxtax_multi_context_equals_single(ctx):
     assert [r[0] for r in one] == ds.query_labels  # single context: query order
     assert sorted(two) == sorted(one) and len(two) == len(one)
     assert sorted(logs1) == sorted(logs2) and warn1 == warn2
+
+
+# ---- randomised differential test: odd tree shapes, ragged lengths, ambiguity codes, duplicates ----------------------------------
+def _random_case(seed):
+    rng = np.random.default_rng(1000 + seed)
+    n_refs = int(rng.integers(1, 90))
+    depth_max = int(rng.integers(1, 7))
+    alphabet = ["a", "b", "c", "dd", "e"]
+    lineages, refs = [], []
+    root_seq = synth.BASE_CODES[rng.integers(0, 4, int(rng.integers(8, 260)))]
+    for _ in range(n_refs):
+        d = int(rng.integers(2, depth_max + 2))  # at least two ranks: raxtax.rs:49 unwraps the parent of the last rank
+        lineages.append(",".join(alphabet[int(rng.integers(0, len(alphabet)))] for _ in range(d)))
+        s = root_seq.copy()
+        mut = rng.random(len(s)) < rng.choice([0.0, 0.02, 0.1, 0.5])
+        s[mut] = synth.BASE_CODES[rng.integers(0, 4, int(mut.sum()))]
+        if rng.random() < 0.2:
+            s[rng.integers(0, len(s), 3)] = rng.choice([15, 5, 10, 3])  # N and two-fold IUPAC codes
+        if rng.random() < 0.15:
+            s = s[: int(rng.integers(0, len(s) + 1))]  # truncated, possibly shorter than one 8-mer or empty
+        refs.append(s)
+    queries = []
+    for _ in range(int(rng.integers(1, 40))):
+        r = rng.random()
+        if r < 0.35:
+            q = refs[int(rng.integers(0, n_refs))].copy()  # exact match (possibly of several references)
+        elif r < 0.8:
+            q = refs[int(rng.integers(0, n_refs))].copy()
+            if len(q):
+                mut = rng.random(len(q)) < 0.05
+                q[mut] = synth.BASE_CODES[rng.integers(0, 4, int(mut.sum()))]
+        else:
+            q = synth.BASE_CODES[rng.integers(0, 4, int(rng.integers(0, 300)))]
+        queries.append(q)
+    return lineages, refs, queries
+
+
+@pytest.mark.parametrize("seed", range(16))
+def test_random_shapes_against_oracle(oracle, ctx, seed):
+    lineages, refs, queries = _random_case(seed)
+    r_off, r_codes = _pack(oracle, refs)
+    q_off, q_codes = _pack(oracle, queries)
+    for skip, raw in [(False, False), (True, False), (False, True)]:
+        o, dev, ot, _ = _run_both(oracle, ctx, (lineages, r_off, r_codes, q_off, q_codes), skip=skip, raw=raw, sub_batch=int(seed % 3) * 5)
+        _assert_integer_parity(o, dev, len(queries))
+        _assert_result_parity(o, dev, ot, len(queries), max_tolerated_frac=1.0)

@@ -39,5 +39,36 @@ for skip in (False, True):
                                              for x, y in zip(a, b))
         print(f"sharded over {world} GPUs (NCCL), skip={skip}: {same}/{nq} queries identical to the unsharded run", flush=True)
         assert same >= nq - max(1, nq // 50)
+# ---- timing of the sharded data path (batch resident; phases + the two collectives; the per-query merge on rank 0 is host work) ----
+if len(sys.argv) > 3 and sys.argv[3] == "time":
+    import json
+    import time
+
+    ctx.batch_upload(ds.query_off, ds.query_codes, eo, eids)
+
+    def one_pass():
+        ctx.shard_phase(1)
+        group.allreduce_hist()
+        ctx.shard_phase(2)
+        group.allgather_records()
+        ctx.shard_phase(3)
+        ctx.synchronize()
+
+    for _ in range(2):
+        one_pass()
+    dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    steps = 5
+    for _ in range(steps):
+        one_pass()
+    torch.cuda.synchronize()
+    dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+    dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        ms = float(dt.item()) * 1e3 / steps
+        print(json.dumps({"mode": "reference-sharded", "workload": name, "n_gpus": world, "refs_per_shard": int(cuts[1] - cuts[0]), "queries": nq,
+                          "ms_per_batch": round(ms, 3), "queries_per_s": round(nq / ms * 1e3), "hist_allreduce_bytes": int(ctx.shard_hist_buffer()[1]) * 4,
+                          "timed": "phase1 + all_reduce + phase2 + all_gather + phase3, max over ranks, batch resident"}), flush=True)
 dist.barrier()
 dist.destroy_process_group()
