@@ -1293,6 +1293,7 @@ static int shard_precheck(rtx_ctx* ctx, int want_phase, const char* who) {
     if (!ctx) return RTX_ERR_INVALID;
     if (!ctx->has_batch) return set_err(ctx, RTX_ERR_INVALID, std::string(who) + ": no batch uploaded");
     if (ctx->bv.n_queries > ctx->sub_batch) return set_err(ctx, RTX_ERR_INVALID, std::string(who) + ": the batch must fit one sub-batch in sharded mode");
+    if (want_phase == 0 && ctx->shard_phase == 3) ctx->shard_phase = 0;  // a finished pass may be repeated on the resident batch
     if (ctx->shard_phase != want_phase) return set_err(ctx, RTX_ERR_INVALID, std::string(who) + ": phases must run in order 1, 2, 3 after rtx_batch_upload");
     cudaError_t e = cudaSetDevice(ctx->device);
     if (e != cudaSuccess) return set_err(ctx, RTX_ERR_CUDA, cudaGetErrorString(e));
