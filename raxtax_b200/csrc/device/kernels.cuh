@@ -847,7 +847,7 @@ __device__ __forceinline__ u32 warp_first_true(u32 a, u32 bnd, int lane, Pred pr
 
 __global__ void __launch_bounds__(kProbThreads, 4)
     prob_table_kernel(IndexView ix, BatchView b, ResultPool pool, ProbScratch sc, int q_base, int q_count,
-                      unsigned long long* __restrict__ hits_total) {
+                      unsigned long long* __restrict__ hits_total, unsigned long long* __restrict__ next_query) {
     extern __shared__ __align__(16) unsigned char psm_raw[];
     __shared__ double red[40];
     __shared__ u32 wsum[kProbWarps];
@@ -871,13 +871,20 @@ __global__ void __launch_bounds__(kProbThreads, 4)
         else atomicAdd(&myprod[i], v);
     };
 
-    for (int ql = blockIdx.x; ql < q_count; ql += gridDim.x) {
+    // queries are handed out through a counter: a fast-branch query costs a few microseconds, a slow-branch one up to ~100, and
+    // a static round-robin left the CTAs 12 % idle at the tail
+    __shared__ int s_next;
+    while (true) {
+        __syncthreads();  // smem reuse across queries (also orders the previous read of s_next)
+        if (tid == 0) s_next = (int)atomicAdd(next_query, 1ull);
+        __syncthreads();
+        const int ql = s_next;
+        if (ql >= q_count) break;
         const int q = q_base + ql;
         const u32 K = b.K[q];
         const u32 t = K / 2;  // raxtax.rs:57
         const u32* __restrict__ ghist = b.hist + (size_t)q * H;
         double* __restrict__ ptab = sc.ptab + (size_t)ql * H;
-        __syncthreads();  // smem reuse across queries
 
         // ---- histogram -> distinct counts (ascending), prob.rs:13-19 ------------------------------------
         const u32 per = (K + 1 + kProbThreads - 1) / kProbThreads;
@@ -1481,7 +1488,7 @@ __global__ void __launch_bounds__(kWalkWarps * 32)
                 }
                 if (lane == 0) {
                     ws.st_next[depth] = nxt;
-                    ws.st_any[depth] = 1;
+                    ws.st_any[depth] |= 1;  // bit 0: a significant child exists; bit 1: something was pushed below (set on the way up)
                     ws.path_node[depth] = child;
                     ws.path_k[depth] = (u8)min(ck, 255u);
                     ws.st_node[depth + 1] = child;
@@ -1494,17 +1501,25 @@ __global__ void __launch_bounds__(kWalkWarps * 32)
                 ++depth;
                 continue;
             }
-            // children exhausted
-            bool any_sig = ws.st_any[depth] != 0;
+            // children exhausted.  lineage.rs:126-177 keeps two facts apart: an Inner node falls back when NO CHILD IS SIGNIFICANT, a
+            // Taxon is reported by its parent when its recursion PUSHED NOTHING.  They differ only below a Taxon whose significant
+            // child is a Sequence node that itself has children (a rank repeating its parent's label, tree.rs:77-107): such a
+            // child is significant yet may push nothing.
+            const u32 fl = ws.st_any[depth];
+            bool any_sig = (fl & 1u) != 0, pushed = (fl & 2u) != 0;
             bool mine = true;  // does this rank emit for `node`?
             if (SH) {
                 const int sj = sv.strad_of_node[node];
                 if (sj >= 0) {
-                    any_sig = any_sig || sv.sany[(size_t)ql * sv.n_strad + sj];
+                    const bool sa = sv.sany[(size_t)ql * sv.n_strad + sj];
+                    any_sig = any_sig || sa;
+                    pushed = pushed || sa;
                     mine = ix.node_lo[node] >= ix.shard_begin && ix.node_lo[node] < ix.shard_begin + ix.shard_refs;
                 }
             }
-            if (!any_sig && ntype != 2 && !(ntype == 1 && depth == 0) && (ntype == 0 || mine)) {
+            const bool emits = ntype == 0 ? !any_sig : (ntype == 1 && !pushed && depth != 0);  // by this rank or the owner of the node
+            pushed = pushed || emits;
+            if (emits && (ntype == 0 || mine)) {
                 int d = depth;
                 u32 cur = node;
                 if (ntype == 0) {  // Inner without a significant child: follow the best children (lineage.rs:151-177)
@@ -1615,6 +1630,7 @@ __global__ void __launch_bounds__(kWalkWarps * 32)
                 if (overflow) break;
             }
             --depth;
+            if (depth >= 0 && pushed && lane == 0) ws.st_any[depth] |= 2;
             __syncwarp();
         }
         __syncwarp();
@@ -1832,7 +1848,7 @@ __global__ void __launch_bounds__(kBfsThreads)
                        u32 entry_cap) {
     constexpr int kBfsWarps = kBfsThreads / 32;
     extern __shared__ __align__(16) unsigned char bsm_raw[];
-    __shared__ u32 s_log_n, s_lvl_begin, s_lvl_end, s_n_res, s_n_fb, s_n_next, s_retry;
+    __shared__ u32 s_log_n, s_n_res, s_n_fb, s_n_next, s_retry;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int ql = blockIdx.x;
     if (ql >= q_count) return;
@@ -1861,20 +1877,47 @@ __global__ void __launch_bounds__(kBfsThreads)
             w.ent_depth[0] = 0;
             w.ent_any[0] = 0;
             s_log_n = 1;
-            s_lvl_begin = 0;
-            s_lvl_end = 1;
             s_n_res = 0;
             s_n_fb = 0;
             s_retry = 0;
         }
         __syncthreads();
-        // ---- significant nodes, level by level (lineage.rs:126-149) ---------------------------------------------
+        // ---- significant nodes, level by level (lineage.rs:126-149).  Two barriers per level: the child offsets of the current
+        // frontier (warp 0) are computed in the same phase in which the previous frontier is sorted into result lines and
+        // fallback heads (its ent_any flags are final since the barrier behind the evaluation that set them) -------------
+        u32 lvl_begin = 0, lvl_end = 1, prev_begin = 0, prev_end = 0;
         while (true) {
-            const u32 lvl_begin = s_lvl_begin, lvl_end = s_lvl_end;
-            if (lvl_begin >= lvl_end || s_retry) break;
+            const bool have = lvl_begin < lvl_end;
             const u32 nf = lvl_end - lvl_begin;
-            if (warp == 0) bfs_child_offsets(w, nf, lvl_begin, nullptr, lane);
+            if (have && warp == 0) bfs_child_offsets(w, nf, lvl_begin, nullptr, lane);
+            // entries of the previous frontier without a significant child: Taxon -> result line, Inner -> head of a fallback chain
+            const u32 pn = prev_end - prev_begin;
+            for (u32 bb = 0; bb < pn; bb += kBfsThreads) {
+                const u32 i = bb + tid;
+                bool is_res = false, is_fb = false;
+                const u32 e = prev_begin + i;
+                if (i < pn && !w.ent_any[e]) {
+                    const u32 type = w.ent_cc[e] >> 30;
+                    is_fb = type == 0;
+                    is_res = type == 1 && e != 0;  // the root never reports itself
+                }
+                const u32 mr = __ballot_sync(kFullMask, is_res), mf = __ballot_sync(kFullMask, is_fb);
+                u32 pr = 0, pf = 0;
+                if (lane == 0) {
+                    if (mr) pr = atomicAdd(&s_n_res, (u32)__popc(mr));
+                    if (mf) pf = atomicAdd(&s_n_fb, (u32)__popc(mf));
+                }
+                pr = __shfl_sync(kFullMask, pr, 0);
+                pf = __shfl_sync(kFullMask, pf, 0);
+                if (pr + __popc(mr) > R || pf + __popc(mf) > F) {
+                    if (lane == 0) s_retry = 1;
+                } else {
+                    if (is_res) w.res_ent[pr + __popc(mr & lt_mask)] = (u16)e;
+                    if (is_fb) w.list_a[pf + __popc(mf & lt_mask)] = (u16)e;
+                }
+            }
             __syncthreads();
+            if (!have || s_retry) break;
             const u32 total = w.fr_off[nf];
             for (u32 base = (u32)warp * 64; base < total; base += kBfsWarps * 64) {  // two chunks of 32 children in flight per warp
                 u32 kk[2], ee[2];
@@ -1914,44 +1957,23 @@ __global__ void __launch_bounds__(kBfsThreads)
                             w.ent_depth[pos] = (u8)(w.ent_depth[ee[u]] + 1);
                             w.ent_any[pos] = 0;
                             w.ent_any[ee[u]] = 1;
+                            // a significant Sequence node (it has children, or it would not be in the tree) may push nothing, and
+                            // its Taxon parent is then reported after all (lineage.rs:143-149): the depth-first walker tracks that
+                            if ((cr[u].cc_type >> 30) == 2u) s_retry = 1;
                         }
                     }
                 }
             }
             __syncthreads();
             if (s_retry) break;
-            // frontier entries without a significant child: Taxon -> result line, Inner -> head of a fallback chain
-            for (u32 bb = 0; bb < nf; bb += kBfsThreads) {
-                const u32 i = bb + tid;
-                bool is_res = false, is_fb = false;
-                const u32 e = lvl_begin + i;
-                if (i < nf && !w.ent_any[e]) {
-                    const u32 type = w.ent_cc[e] >> 30;
-                    is_fb = type == 0;
-                    is_res = type == 1 && e != 0;  // the root never reports itself
-                }
-                const u32 mr = __ballot_sync(kFullMask, is_res), mf = __ballot_sync(kFullMask, is_fb);
-                u32 pr = 0, pf = 0;
-                if (lane == 0) {
-                    if (mr) pr = atomicAdd(&s_n_res, (u32)__popc(mr));
-                    if (mf) pf = atomicAdd(&s_n_fb, (u32)__popc(mf));
-                }
-                pr = __shfl_sync(kFullMask, pr, 0);
-                pf = __shfl_sync(kFullMask, pf, 0);
-                if (pr + __popc(mr) > R || pf + __popc(mf) > F) {
-                    if (lane == 0) s_retry = 1;
-                } else {
-                    if (is_res) w.res_ent[pr + __popc(mr & lt_mask)] = (u16)e;
-                    if (is_fb) w.list_a[pf + __popc(mf & lt_mask)] = (u16)e;
-                }
+            prev_begin = lvl_begin;
+            prev_end = lvl_end;
+            lvl_begin = lvl_end;
+            lvl_end = s_log_n;  // stable: nothing appends to the log before the next evaluation phase
+            if (lvl_end - lvl_begin > F) {  // block-uniform
+                if (tid == 0) s_retry = 1;
+                break;
             }
-            __syncthreads();
-            if (tid == 0) {
-                s_lvl_begin = lvl_end;
-                s_lvl_end = s_log_n;
-                if (s_log_n - lvl_end > F) s_retry = 1;
-            }
-            __syncthreads();
         }
         __syncthreads();
         // ---- fallback chains (lineage.rs:151-177): all heads advance together, one level per round -------------------

@@ -814,7 +814,7 @@ RTX_API int rtx_batch_upload(rtx_ctx* ctx, const rtx_batch* batch) {
     CU(ctx->d_ord_begin.ensure(((size_t)nq + 1) * 4));
     CU(ctx->d_global.ensure(nq * 8));
     CU(ctx->d_status.ensure(nq * 4));
-    CU(ctx->d_hits.ensure(8));
+    CU(ctx->d_hits.ensure(16));  // [0] postings-touched counter, [1] work counter of prob_table_kernel
     ctx->pool.res_off = ctx->d_res_off.as<u32>();
     ctx->pool.res_cnt = ctx->d_res_cnt.as<u32>();
     ctx->pool.global_sig = ctx->d_global.as<double>();
@@ -1025,10 +1025,12 @@ static int run_phase1(rtx_ctx* ctx, int q_base, int qb) {
 // K3 (P(m) tables) + K4 (prefix sums at node boundaries) of one sub-batch
 static int launch_prob(rtx_ctx* ctx, int q0, int qb) {
     {
+        CU(cudaMemsetAsync(ctx->d_hits.as<unsigned long long>() + 1, 0, 8, ctx->cur_stream));  // the kernel's work counter
         LaunchTimer lt(ctx, RTX_K_PROB);
         const int grid = std::min(ctx->prob_slots, qb);
         prob_table_kernel<<<grid, kProbThreads, ctx->prob_smem, ctx->cur_stream>>>(ctx->ix, ctx->bv, ctx->pool, *ctx->cur_sc, q0, qb,
-                                                                             ctx->d_hits.as<unsigned long long>());
+                                                                             ctx->d_hits.as<unsigned long long>(),
+                                                                             ctx->d_hits.as<unsigned long long>() + 1);
         CU(cudaGetLastError());
     }
     {
