@@ -137,6 +137,14 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     cores = os.cpu_count() or 1
+    # stdout carries the ONE JSON line and nothing else: whatever libraries print (NCCL writes its version banner to stdout) goes to stderr
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(line):
+        sys.stdout.flush()
+        os.write(real_stdout, (json.dumps(line) + "\n").encode())
 
     # ------------------------------------------------------------------------------------------ reference arm
     if args.impl == "reference":
@@ -156,7 +164,7 @@ def main():
                 "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                                  "sample": f"{n_sample} queries of the {args.workload} workload per step, {args.steps} steps, all {cores} host threads"},
                 "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
-        print(json.dumps(line))
+        emit(line)
         return 0
 
     # ------------------------------------------------------------------------------------------ our arm
@@ -284,7 +292,8 @@ def main():
     tpath = os.path.join(ROOT, "profiles", "hitcount_traffic.json")
     if os.path.exists(tpath):
         try:
-            traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+            tj = json.load(open(tpath))
+            traffic = tj.get("dram_bytes_per_launch") if str(tj.get("workload", "")).startswith(args.workload + ",") else None  # measured on that workload only
         except Exception:
             traffic = None
     kernel_ms = {k: prof[k]["total_ms"] / args.steps for k in ("kmers", "hitcount", "fixup", "prob", "prefix", "walk")}
@@ -319,7 +328,7 @@ def main():
         line["cpu_baseline"] = {"value": n_sample / secs, "unit": UNIT, "cores": cores, "kind": "port",
                                 "sample": f"first {n_sample} queries of the same workload, all {cores} host threads, oracle port of raxtax.rs (Rust reference not buildable here)"}
     if rank == 0:
-        print(json.dumps(line))
+        emit(line)
     ctx.close()
     if world > 1:
         dist.destroy_process_group()

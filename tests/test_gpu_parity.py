@@ -369,7 +369,7 @@ def test_full_scale_configs(oracle, ctx, cfg, nq, skip):
 
 
 # ---- reference-sharded mode: several shards on ONE GPU (one context per shard), exchanges by device copies -----------------
-@pytest.mark.parametrize("n_shards,skip,raw", [(2, False, False), (3, True, False), (5, False, True)])
+@pytest.mark.parametrize("n_shards,skip,raw", [(2, False, False), (3, True, False), (5, False, True), (8, False, False)])  # 8 = BASELINE config 5's shard count
 def test_reference_sharded_matches_oracle(oracle, n_shards, skip, raw):
     from raxtax_b200 import dist as rdist
 
