@@ -1843,7 +1843,7 @@ __device__ __forceinline__ u32 bfs_owner(const u32* __restrict__ fr_off, u32 n, 
 }
 
 template <int kBfsThreads>
-__global__ void __launch_bounds__(kBfsThreads, 1536 / kBfsThreads)  // 6 CTAs of 256 threads per SM: the kernel is latency-bound, more queries in flight
+__global__ void __launch_bounds__(kBfsThreads)  // (a 6-CTA/SM bound, 40 registers with small spills, measured the same 0.89 ms)
     lineage_bfs_kernel(IndexView ix, const NodeRec* __restrict__ recs, BatchView b, ResultPool pool, ProbScratch sc, int q_base, int q_count,
                        u32 entry_cap) {
     constexpr int kBfsWarps = kBfsThreads / 32;
