@@ -61,6 +61,7 @@ struct rtx_ctx {
     u32 sub_batch = 0;
     // results
     ResultPool pool{};
+    u32 pool_levels = 0;  // max_levels the pool arrays were sized for
     DevBuf d_pool_first, d_pool_nlev, d_pool_conf, d_pool_local, d_pool_used, d_res_off, d_res_cnt, d_global, d_status, d_hits;
     // prob scratch
     ProbScratch sc{}, sc1{};
@@ -714,6 +715,7 @@ static int ensure_pool(rtx_ctx* ctx, u64 cap) {
     ctx->pool.local = ctx->d_pool_local.as<double>();
     ctx->pool.used = ctx->d_pool_used.as<unsigned long long>();
     ctx->pool.cap = cap;
+    ctx->pool_levels = ML;
     return RTX_OK;
 }
 
@@ -819,8 +821,9 @@ RTX_API int rtx_batch_upload(rtx_ctx* ctx, const rtx_batch* batch) {
     ctx->pool.res_cnt = ctx->d_res_cnt.as<u32>();
     ctx->pool.global_sig = ctx->d_global.as<double>();
     ctx->pool.status = ctx->d_status.as<int>();
-    if (ctx->pool.cap < (u64)nq * 8 + 1024) {
-        int rc = ensure_pool(ctx, (u64)nq * 8 + 1024);
+    // the pool's confidence arrays are sized cap x max_levels: a new index with deeper lineages needs them re-sized as well
+    if (ctx->pool.cap < (u64)nq * 8 + 1024 || ctx->pool_levels != ctx->ix.max_levels) {
+        int rc = ensure_pool(ctx, std::max<u64>(ctx->pool.cap, (u64)nq * 8 + 1024));
         if (rc) return rc;
     }
 

@@ -49,16 +49,18 @@ class TolerantChecker:
         self.N = n_tips
         self.eps = eps
 
-    def acceptable(self, probs, device_results):
+    def acceptable(self, probs, device_results, oracle_results=None):
         pre = np.concatenate([[0.0], np.cumsum(probs)])
         conf = lambda n: pre[self.hi[n]] - pre[self.lo[n]]
         outs = []
+        boundary = [False]  # some confidence of this query sits on a rounding boundary
 
         def rounded_options(x):
             r = np.round(x * 100.0 + 0.0) / 100.0
             y = x * 100.0
             opts = {float(np.floor(y + 0.5) / 100.0)}
             if abs((y - np.floor(y)) - 0.5) < self.eps * 100:
+                boundary[0] = True
                 opts.add(float(np.floor(y) / 100.0))
                 opts.add(float(np.ceil(y) / 100.0))
             del r
@@ -104,7 +106,15 @@ class TolerantChecker:
 
         walk(0, [])
         allowed = {(fr, tuple(np.round(np.array(c), 2))) for fr, c in outs}
-        return dev <= allowed and len(dev) > 0
+        if dev <= allowed and len(dev) > 0:
+            return True
+        # one-exact-match override (raxtax.rs:73-84): the line carries 1.0s and the signals of the BEST computed line; if a confidence
+        # of that evaluation sits on a rounding boundary, the best line's vector -- hence its local signal -- has two legitimate values
+        if oracle_results is not None and len(device_results) == 1 and len(oracle_results) == 1:
+            (fd, cd, _, gd), (fo, co, _, go) = device_results[0], oracle_results[0]
+            if fd == fo and len(cd) == len(co) and np.all(cd == 1.0) and np.all(co == 1.0) and abs(gd - go) <= CONF_TOL:
+                return boundary[0]
+        return False
 
 
 def compare_batch(orc_out, dev_out, n_queries, checker=None, probs=None):
@@ -117,7 +127,7 @@ def compare_batch(orc_out, dev_out, n_queries, checker=None, probs=None):
         b = dev_out.for_query(q)
         if results_equal(a, b):
             ok += 1
-        elif checker is not None and probs is not None and checker.acceptable(probs[q], b):
+        elif checker is not None and probs is not None and checker.acceptable(probs[q], b, a):
             tol += 1
         else:
             bad.append(q)

@@ -540,7 +540,7 @@ def _random_case(seed):
     return lineages, refs, queries
 
 
-@pytest.mark.parametrize("seed", range(16))
+@pytest.mark.parametrize("seed", range(int(os.environ.get("RTX_FUZZ_SEEDS", "16"))))  # RTX_FUZZ_SEEDS=200 for a longer hunt
 def test_random_shapes_against_oracle(oracle, ctx, seed):
     lineages, refs, queries = _random_case(seed)
     r_off, r_codes = _pack(oracle, refs)
@@ -549,3 +549,40 @@ def test_random_shapes_against_oracle(oracle, ctx, seed):
         o, dev, ot, _ = _run_both(oracle, ctx, (lineages, r_off, r_codes, q_off, q_codes), skip=skip, raw=raw, sub_batch=int(seed % 3) * 5)
         _assert_integer_parity(o, dev, len(queries))
         _assert_result_parity(o, dev, ot, len(queries), max_tolerated_frac=1.0)
+
+
+def test_context_reuse_across_indexes_of_different_depth(oracle, ctx):
+    """One context, a shallow database then a deep one (then back): the result pool and its query-ordered copy are re-sized with
+    max_levels; every run equals a fresh context's."""
+    rng = np.random.default_rng(77)
+    base = synth.BASE_CODES[rng.integers(0, 4, 150)]
+
+    def db(depth, n):
+        lin, refs = [], []
+        for i in range(n):
+            lin.append(",".join(f"r{l}_{(i >> (depth - 1 - l)) if l < depth - 1 else i}" for l in range(depth)))
+            s = base.copy()
+            mut = rng.random(len(s)) < 0.08
+            s[mut] = synth.BASE_CODES[rng.integers(0, 4, int(mut.sum()))]
+            refs.append(s)
+        return lin, refs
+
+    cases = [db(2, 40), db(9, 64), db(3, 24)]
+    queries = [cases[1][1][5], cases[0][1][7], base, synth.BASE_CODES[rng.integers(0, 4, 90)]]
+    q_off, q_codes = _pack(oracle, queries)
+    for lin, refs in cases:
+        r_off, r_codes = _pack(oracle, refs)
+        ht = capi.Tree.new(lin, r_off, r_codes)
+        eo, eids = ht.exact_batch(q_off, q_codes)
+        ctx.upload_tree(ht)
+        a = ctx.classify(q_off, q_codes, eo, eids)
+        fresh = capi.Context(0)
+        try:
+            fresh.upload_tree(ht)
+            b = fresh.classify(q_off, q_codes, eo, eids)
+        finally:
+            fresh.close()
+        assert np.array_equal(a.result_begin, b.result_begin) and np.array_equal(a.first_ref, b.first_ref)
+        assert np.array_equal(a.n_levels, b.n_levels) and np.array_equal(a.confidence, b.confidence)
+        assert np.array_equal(a.local_signal, b.local_signal) and np.array_equal(a.global_signal, b.global_signal)
+        assert a.confidence.shape[1] == max(l.count(",") + 1 for l in lin)
