@@ -1258,7 +1258,7 @@ struct ShardRec {
     double mass;     // sum of normalised probabilities of the straddler's references inside this shard
     double best;     // largest confidence among the straddler's non-straddling children inside this shard (-inf if none)
     u32 best_child;  // node id of the last such child within 1e-12 relative of `best`
-    u32 n_sig;       // how many of those children have round(conf*100) != 0
+    u32 n_sig;       // low half: how many of those children have round(conf*100) != 0; high half: below how many of them a line is pushed
 };
 
 struct ShardView {
@@ -1269,12 +1269,37 @@ struct ShardView {
     ShardRec* send;            // [Q][n_strad]
     const ShardRec* recv;      // [n_shards][Q][n_strad]
     u8* sk;                    // [Q][n_strad] combined round(conf*100)
-    u8* sany;                  // [Q][n_strad] combined "has a significant child"
+    u8* sany;                  // [Q][n_strad] combined: bit 0 "has a significant child" (Inner: fallback or not), bit 1 "a line is pushed below" (Taxon: report or not)
     u32* sbest;                // [Q][n_strad] combined best child (node id)
 };
 
 __device__ __forceinline__ bool node_inside(const IndexView& ix, u32 node) {
     return ix.node_lo[node] >= ix.shard_begin && ix.node_hi[node] <= ix.shard_begin + ix.shard_refs;
+}
+
+// Does the subtree of a significant Sequence node push a result line (lineage.rs:126-149)?  Its Taxon / Inner children do as soon as
+// they are significant; Sequence children (a rank repeating its parent's label again) are followed.  The node lies inside the shard,
+// hence so does its whole subtree.  Rare path (degenerate lineages), one lane.
+__device__ bool seq_subtree_pushes(const NodeRec* __restrict__ recs, const double* __restrict__ preb, const double* __restrict__ segoff,
+                                   const u32* __restrict__ skipw, const NodeRec& s) {
+    u32 st_cf[8], st_cc[8];
+    int sp = 1;
+    st_cf[0] = s.child_first;
+    st_cc[0] = s.cc_type & 0x3FFFFFFFu;
+    while (sp > 0) {
+        --sp;
+        const u32 cf = st_cf[sp], cc = st_cc[sp];
+        for (u32 i = 0; i < cc; ++i) {
+            const NodeRec c = recs[cf + i];
+            if ((u32)round(node_conf(preb, segoff, skipw, c) * 100.0) == 0u) continue;
+            if ((c.cc_type >> 30) != 2u) return true;
+            if (sp >= 8) return true;  // deeper than any sane lineage: be conservative
+            st_cf[sp] = c.child_first;
+            st_cc[sp] = c.cc_type & 0x3FFFFFFFu;
+            ++sp;
+        }
+    }
+    return false;
 }
 
 // one warp per (query, straddler)
@@ -1290,20 +1315,24 @@ __global__ void __launch_bounds__(128) shard_records_kernel(IndexView ix, const 
     const NodeRec nr = recs[node];
     const u32 cf = nr.child_first, cc = nr.cc_type & 0x3FFFFFFFu;
     double best = -CUDART_INF;
-    u32 n_sig = 0;
+    u32 n_sig = 0, n_push = 0;  // significant inside children; those of them below which a result line is pushed
     for (u32 cb = 0; cb < cc; cb += 32) {
         const u32 ci = cb + lane;
         if (ci < cc && sv.strad_of_node[cf + ci] < 0 && node_inside(ix, cf + ci)) {
             const NodeRec cr = recs[cf + ci];
             const double v = node_conf(preb, segoff, skipw, cr);
             best = fmax(best, v);
-            n_sig += ((u32)round(v * 100.0) != 0);
+            if ((u32)round(v * 100.0) != 0) {
+                ++n_sig;
+                n_push += ((cr.cc_type >> 30) != 2u) || seq_subtree_pushes(recs, preb, segoff, skipw, cr);
+            }
         }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         best = fmax(best, __shfl_xor_sync(kFullMask, best, o));
         n_sig += __shfl_xor_sync(kFullMask, n_sig, o);
+        n_push += __shfl_xor_sync(kFullMask, n_push, o);
     }
     u32 besti = 0;
     if (best > -CUDART_INF) {
@@ -1323,13 +1352,13 @@ __global__ void __launch_bounds__(128) shard_records_kernel(IndexView ix, const 
         r.mass = node_conf(preb, segoff, skipw, nr);
         r.best = best;
         r.best_child = besti;
-        r.n_sig = n_sig;
+        r.n_sig = min(n_sig, 0xFFFFu) | (min(n_push, 0xFFFFu) << 16);
         sv.send[(size_t)ql * sv.n_strad + j] = r;
     }
 }
 
 // one thread per query: masses summed in rank order (deterministic), then any-significant-child and best child
-__global__ void shard_combine_kernel(ShardView sv, int q_count) {
+__global__ void shard_combine_kernel(ShardView sv, const NodeRec* __restrict__ recs, int q_count) {
     const int ql = blockIdx.x * blockDim.x + threadIdx.x;
     if (ql >= q_count) return;
     const u32 S = sv.n_strad;
@@ -1340,17 +1369,21 @@ __global__ void shard_combine_kernel(ShardView sv, int q_count) {
         return m;
     };
     for (u32 j = 0; j < S; ++j) sv.sk[(size_t)ql * S + j] = (u8)min((u32)round(mass_of(j) * 100.0), 255u);
-    for (u32 j = 0; j < S; ++j) {
-        u32 nsig = 0;
+    for (int j = (int)S - 1; j >= 0; --j) {  // children before parents (straddlers are listed in BFS order): spush of a child is final
+        u32 nsig = 0, npush = 0;
         double gmax = -CUDART_INF;
         for (u32 r = 0; r < sv.n_shards; ++r) {
             const ShardRec rec = sv.recv[r * rank_stride + (size_t)ql * S + j];
-            nsig += rec.n_sig;
+            nsig += rec.n_sig & 0xFFFFu;
+            npush += rec.n_sig >> 16;
             gmax = fmax(gmax, rec.best);
         }
         for (u32 c = 0; c < S; ++c)
             if (sv.strad_parent[c] == (int)j) {
-                nsig += sv.sk[(size_t)ql * S + c] != 0;
+                const bool sig = sv.sk[(size_t)ql * S + c] != 0;
+                nsig += sig;
+                // a significant straddling child pushes when it is a Taxon / Inner node, or a Sequence node below which something is pushed
+                npush += sig && ((recs[sv.strad_nodes[c]].cc_type >> 30) != 2u || (sv.sany[(size_t)ql * S + c] & 2u));
                 gmax = fmax(gmax, mass_of(c));
             }
         const double thr = gmax - fabs(gmax) * 1e-12;
@@ -1361,7 +1394,7 @@ __global__ void shard_combine_kernel(ShardView sv, int q_count) {
         }
         for (u32 c = 0; c < S; ++c)
             if (sv.strad_parent[c] == (int)j && mass_of(c) >= thr) best_child = max(best_child, sv.strad_nodes[c]);
-        sv.sany[(size_t)ql * S + j] = nsig != 0;
+        sv.sany[(size_t)ql * S + j] = (u8)((nsig != 0) | ((npush != 0) << 1));  // bit 0: a significant child exists; bit 1: a line is pushed below
         sv.sbest[(size_t)ql * S + j] = best_child;
     }
 }
@@ -1511,9 +1544,9 @@ __global__ void __launch_bounds__(kWalkWarps * 32)
             if (SH) {
                 const int sj = sv.strad_of_node[node];
                 if (sj >= 0) {
-                    const bool sa = sv.sany[(size_t)ql * sv.n_strad + sj];
-                    any_sig = any_sig || sa;
-                    pushed = pushed || sa;
+                    const u32 sa = sv.sany[(size_t)ql * sv.n_strad + sj];
+                    any_sig = any_sig || (sa & 1u);
+                    pushed = pushed || (sa & 2u);
                     mine = ix.node_lo[node] >= ix.shard_begin && ix.node_lo[node] < ix.shard_begin + ix.shard_refs;
                 }
             }

@@ -1388,7 +1388,7 @@ RTX_API int rtx_shard_phase3(rtx_ctx* ctx) {
     ctx->shard_phase = 3;
     if (nq == 0) return RTX_OK;
     if (ctx->sv.n_strad) {
-        shard_combine_kernel<<<(nq + 127) / 128, 128, 0, ctx->stream>>>(ctx->sv, (int)nq);
+        shard_combine_kernel<<<(nq + 127) / 128, 128, 0, ctx->stream>>>(ctx->sv, ctx->d_recs.as<NodeRec>(), (int)nq);
         CU(cudaGetLastError());
     }
     {

@@ -586,3 +586,48 @@ def test_context_reuse_across_indexes_of_different_depth(oracle, ctx):
         assert np.array_equal(a.n_levels, b.n_levels) and np.array_equal(a.confidence, b.confidence)
         assert np.array_equal(a.local_signal, b.local_signal) and np.array_equal(a.global_signal, b.global_signal)
         assert a.confidence.shape[1] == max(l.count(",") + 1 for l in lin)
+
+
+@pytest.mark.parametrize("seed", range(int(os.environ.get("RTX_FUZZ_SEEDS", "16")) // 2))
+def test_random_shapes_walk_variants_and_shards(oracle, ctx, seed):
+    """The same random cases through (i) the depth-first walker alone and the forced retry path -- bit-identical to the default
+    level-synchronous walk -- and (ii) the reference-sharded phases with 2-4 shards cut at arbitrary references, against the oracle."""
+    from raxtax_b200 import dist as rdist
+
+    lineages, refs, queries = _random_case(5000 + seed)
+    r_off, r_codes = _pack(oracle, refs)
+    q_off, q_codes = _pack(oracle, queries)
+    ht = capi.Tree.new(lineages, r_off, r_codes)
+    eo, eids = ht.exact_batch(q_off, q_codes)
+    skip = seed % 2 == 1
+    ctx.upload_tree(ht)
+    outs = []
+    try:
+        for variant, cap in ((0, 0), (1, 0), (0, 4)):
+            ctx.set_option(capi.RTX_OPT_WALK_VARIANT, variant)
+            ctx.set_option(capi.RTX_OPT_WALK_LOG_CAP, cap)
+            outs.append(ctx.classify(q_off, q_codes, eo, eids, skip_exact=skip))
+    finally:
+        ctx.set_option(capi.RTX_OPT_WALK_VARIANT, 0)
+        ctx.set_option(capi.RTX_OPT_WALK_LOG_CAP, 0)
+    for o2 in outs[1:]:
+        assert _same_outputs(outs[0], o2)
+    n = ht.num_tips
+    if n < 2:
+        return
+    rng = np.random.default_rng(seed)
+    n_shards = int(min(n, rng.integers(2, 5)))
+    cuts = np.concatenate([[0], np.sort(rng.choice(np.arange(1, n), n_shards - 1, replace=False)), [n]]).astype(np.uint64)
+    ctxs = [capi.Context(0) for _ in range(n_shards)]
+    try:
+        for r, c in enumerate(ctxs):
+            c.upload_tree_sharded(ht, n_shards, r, cuts)
+        ref_levels = ht.index_arrays()["ref_levels"]
+        merged, per_rank = rdist.classify_sharded_local(ctxs, q_off, q_codes, eo, eids, ref_levels, skip_exact=skip, taps=("counts",))
+    finally:
+        for c in ctxs:
+            c.close()
+    ot = oracle.Tree.new(lineages, [np.asarray(r, np.uint8) for r in refs])
+    o = ot.classify(q_off, q_codes, skip_exact=skip, threads=2, chunk_size=8, want_counts=True, want_probs=True)
+    assert np.array_equal(np.concatenate([x.counts for x in per_rank], axis=1), o["counts"])
+    _assert_result_parity(o, merged, ot, len(queries), max_tolerated_frac=1.0)
