@@ -526,7 +526,7 @@ class Tree:
         host_lib().rxh_tree_csr(self._h, C.byref(off), C.byref(ids))
         o = np.ctypeslib.as_array(off, (65537,)).copy()
         nnz = int(o[-1])
-        i = np.ctypeslib.as_array(ids, (max(nnz, 1),))[:nnz].copy()
+        i = np.ctypeslib.as_array(ids, (nnz,)).copy() if nnz else np.zeros(0, np.uint32)  # no postings at all: the vector's data() is NULL
         return o, i
 
     def k_mer_map(self, kmer):
@@ -562,7 +562,7 @@ class Tree:
         d = IndexDesc()
         host_lib().rxh_tree_index_desc(self._h, C.byref(d))
         nn, N = d.n_nodes, d.n_refs
-        g = lambda p, n: np.ctypeslib.as_array(p, (max(n, 1),))[:n].copy()
+        g = lambda p, n: np.ctypeslib.as_array(p, (n,)).copy() if n and p else np.zeros(0, p._type_)
         off = g(d.csr_offsets, 65537)
         return dict(n_refs=N, csr_off=off, csr_ids=g(d.csr_ids, int(off[-1])), node_lo=g(d.node_lo, nn), node_hi=g(d.node_hi, nn),
                     node_type=g(d.node_type, nn), child_first=g(d.child_first, nn), child_count=g(d.child_count, nn),

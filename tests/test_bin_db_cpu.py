@@ -102,3 +102,27 @@ def test_queries_skip():
     assert q.labels == ["q1", "q3"]
     off, codes = q.arrays()
     assert list(off) == [0, 4, 8] and list(codes) == [1, 2, 4, 8, 2, 2, 2, 2]
+
+
+def _random_tree(seed):
+    """Random lineages of 1-7 ranks over a 5-letter alphabet (repeated labels, strict prefixes, duplicates) with short random sequences."""
+    rng = np.random.default_rng(seed)
+    n = int(rng.integers(1, 60))
+    alphabet = ["a", "b", "c", "dd", "e"]
+    lin = [",".join(alphabet[int(rng.integers(0, 5))] for _ in range(int(rng.integers(1, 8)))) for _ in range(n)]
+    pool = [list(map(int, rng.choice([1, 2, 4, 8, 15], int(rng.integers(0, 30)), p=[0.24, 0.24, 0.24, 0.24, 0.04]))) for _ in range(max(1, n // 2))]
+    seqs = [pool[int(rng.integers(0, len(pool)))] for _ in range(n)]
+    return lin, seqs
+
+
+@pytest.mark.parametrize("seed", range(40))
+def test_random_trees_round_trip(seed, tmp_path):
+    lin, seqs = _random_tree(seed)
+    model = bm.tree_new(lin, seqs)
+    host = _host_tree(lin, seqs)
+    _same_tree(capi.Tree.from_bin(bm.serialize(model)), host, seqs)
+    p = str(tmp_path / "db.bin")
+    host.save_bin(p)
+    got = bm.deserialize(open(p, "rb").read())
+    assert got["root"] == model["root"] and got["lineages"] == model["lineages"] and got["k_mer_map"] == model["k_mer_map"]
+    assert {k: sorted(v) for k, v in got["sequences"].items()} == {k: sorted(v) for k, v in model["sequences"].items()}

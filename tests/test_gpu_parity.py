@@ -631,3 +631,56 @@ def test_random_shapes_walk_variants_and_shards(oracle, ctx, seed):
     o = ot.classify(q_off, q_codes, skip_exact=skip, threads=2, chunk_size=8, want_counts=True, want_probs=True)
     assert np.array_equal(np.concatenate([x.counts for x in per_rank], axis=1), o["counts"])
     _assert_result_parity(o, merged, ot, len(queries), max_tolerated_frac=1.0)
+
+
+def _random_case_mid(seed):
+    """Mid-size random databases: several reference tiles and prefix segments with ragged tails, query lengths that land in every
+    counter-plane instantiation of the hit-count kernel (K < 256 / 1024 / 2048 / 8192), clade-structured similarity."""
+    rng = np.random.default_rng(9000 + seed)
+    n_refs = int(rng.choice([97, 511, 513, 2047, 2049, 4097, 6000]) + rng.integers(0, 40))
+    length = int(rng.choice([40, 200, 650, 1100, 2600]))
+    depth = int(rng.integers(2, 7))
+    fan = [int(rng.integers(1, 6)) for _ in range(depth)]
+    root = synth.BASE_CODES[rng.integers(0, 4, length)]
+    clade_seq = {(): root}
+    lineages, refs = [], []
+    for _ in range(n_refs):
+        path = tuple(int(rng.integers(0, f)) for f in fan)
+        for d in range(1, depth + 1):
+            key = path[:d]
+            if key not in clade_seq:
+                s = clade_seq[key[:-1]].copy()
+                mut = rng.random(length) < 0.04
+                s[mut] = synth.BASE_CODES[rng.integers(0, 4, int(mut.sum()))]
+                clade_seq[key] = s
+        s = clade_seq[path].copy()
+        mut = rng.random(length) < rng.choice([0.0, 0.01, 0.05])
+        s[mut] = synth.BASE_CODES[rng.integers(0, 4, int(mut.sum()))]
+        if rng.random() < 0.05:
+            s[rng.integers(0, length, 4)] = 15
+        if rng.random() < 0.05:
+            s = s[: int(rng.integers(0, length + 1))]
+        lineages.append(",".join(f"L{d}_{path[d]}" for d in range(depth)))
+        refs.append(s)
+    queries = []
+    for _ in range(int(rng.integers(3, 70))):
+        q = refs[int(rng.integers(0, n_refs))].copy()
+        r = rng.random()
+        if r > 0.3 and len(q):
+            mut = rng.random(len(q)) < rng.choice([0.01, 0.08, 0.3])
+            q[mut] = synth.BASE_CODES[rng.integers(0, 4, int(mut.sum()))]
+        if r > 0.9:
+            q = synth.BASE_CODES[rng.integers(0, 4, int(rng.integers(0, length + 50)))]
+        queries.append(q)
+    return lineages, refs, queries
+
+
+@pytest.mark.parametrize("seed", range(max(2, int(os.environ.get("RTX_FUZZ_SEEDS", "16")) // 4)))
+def test_random_mid_size_against_oracle(oracle, ctx, seed):
+    lineages, refs, queries = _random_case_mid(seed)
+    r_off, r_codes = _pack(oracle, refs)
+    q_off, q_codes = _pack(oracle, queries)
+    skip, variant = bool(seed & 1), (capi.RTX_HITCOUNT_CSR if seed % 5 == 4 else capi.RTX_HITCOUNT_BITROWS)
+    o, dev, ot, _ = _run_both(oracle, ctx, (lineages, r_off, r_codes, q_off, q_codes), skip=skip, sub_batch=int(seed % 4) * 7, variant=variant)
+    _assert_integer_parity(o, dev, len(queries))
+    _assert_result_parity(o, dev, ot, len(queries), max_tolerated_frac=1.0)
