@@ -140,7 +140,7 @@ def make_workload(name, world):
     return ds, cfg[1]
 
 
-def cpu_reference_rate(ds, q0, n_sample, threads, full_chunk):
+def cpu_reference_rate(ds, q0, n_sample, threads, full_chunk, skip=False):
     """The reference algorithm (oracle port of raxtax.rs:14-97, --threads 0 chunking of main.rs:119-124) on host cores."""
     from oracle import oracle as orc
 
@@ -150,7 +150,7 @@ def cpu_reference_rate(ds, q0, n_sample, threads, full_chunk):
     chunk = n_sample if threads == 1 else full_chunk
 
     def run():
-        o = ot.classify(off - off[0], codes[int(off[0]): int(off[-1])], threads=threads, chunk_size=chunk)
+        o = ot.classify(off - off[0], codes[int(off[0]): int(off[-1])], skip_exact=skip, threads=threads, chunk_size=chunk)
         return o["seconds"]
 
     return ot, run
@@ -196,7 +196,9 @@ def main():
             return 0
         ds, q_per_gpu = make_workload(args.workload, 1)
         n_sample, chunk = cpu_sample_plan(q_per_gpu, cores, args.cpu_sample)
-        _, run = cpu_reference_rate(ds, 0, n_sample, cores, chunk)
+        from raxtax_b200 import synth
+
+        _, run = cpu_reference_rate(ds, 0, n_sample, cores, chunk, skip=args.workload == "c4")
         for _ in range(args.warmup):
             run()
         secs = [run() for _ in range(args.steps)]
@@ -204,7 +206,7 @@ def main():
         v = n_sample * args.steps / total
         line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u16/f64",
-                "data": "synthetic", "config": {"workload": f"{args.workload}: {ds.n_refs} refs x 650 bp, bounded sample of {n_sample} queries per step"},
+                "data": "synthetic", "config": {"workload": f"{args.workload}: {ds.n_refs} refs x {synth.CONFIGS[args.workload][2]} bp, bounded sample of {n_sample} queries per step"},
                 "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                                  "sample": f"{n_sample} queries of the {args.workload} workload per step, {args.steps} steps, all {cores} host threads"},
                 "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
@@ -240,6 +242,11 @@ def main():
         return float(t.item())
 
     ds, q_per_gpu = make_workload(args.workload, world)
+    from raxtax_b200 import synth
+
+    ref_len, kind = synth.CONFIGS[args.workload][2], synth.CONFIGS[args.workload][3]
+    kind_name = "16S-like" if kind == "16s" else "COI-like"
+    skip = args.workload == "c4"  # BASELINE config 4 is the mislabel mode (--skip-exact-matches)
     t0 = time.time()
     tree = capi.Tree.new(ds.ref_lineages, ds.ref_off, ds.ref_codes)
     t_tree = time.time() - t0
@@ -262,7 +269,7 @@ def main():
     if args.pipeline >= 0:
         ctx.set_option(capi.RTX_OPT_PIPELINE, args.pipeline)
     # ---- device-resident leg ------------------------------------------------------------------------------
-    ctx.batch_upload(off_p, codes_p, eo_p, eids_p)
+    ctx.batch_upload(off_p, codes_p, eo_p, eids_p, skip_exact=skip)
     for _ in range(args.warmup):
         ctx.batch_run()
     ctx.synchronize()
@@ -291,7 +298,7 @@ def main():
     # CUDA-event duration is its own (in the pipelined run above hit counting shares the SMs with the other stream's kernels)
     ctx.set_option(capi.RTX_OPT_PIPELINE, 0)
     ctx.set_option(capi.RTX_OPT_SUB_BATCH, 0)
-    ctx.batch_upload(off_p, codes_p, eo_p, eids_p)
+    ctx.batch_upload(off_p, codes_p, eo_p, eids_p, skip_exact=skip)
     for _ in range(2):
         ctx.batch_run()
     ctx.profile_reset()
@@ -312,13 +319,13 @@ def main():
     # inputs and result arrays page-locked (rtx_host_alloc), reused from step to step as a long-running caller would
     res_buf = ctx.pinned_results(q_per_gpu, max(q_per_gpu * 8 + 64, n_results + n_results // 4 + 64))
     for _ in range(2):
-        ctx.classify(off_p, codes_p, eo_p, eids_p, out=res_buf)
+        ctx.classify(off_p, codes_p, eo_p, eids_p, skip_exact=skip, out=res_buf)
     ctx.profile_reset()
     barrier()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        out = ctx.classify(off_p, codes_p, eo_p, eids_p, out=res_buf)
+        out = ctx.classify(off_p, codes_p, eo_p, eids_p, skip_exact=skip, out=res_buf)
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     barrier()
     prof_e2e = ctx.profile()
@@ -356,7 +363,8 @@ def main():
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32 bit-planes/u16 counts/f64",
             "data": "synthetic",
-            "config": {"workload": f"{args.workload}: {ds.n_refs} COI-like refs x 650 bp (6-rank lineages) x {q_per_gpu} queries per GPU, index replicated, queries partitioned",
+            "config": {"workload": f"{args.workload}: {ds.n_refs} {kind_name} refs x {ref_len} bp (6-rank lineages) x {q_per_gpu} queries per GPU, index replicated, queries partitioned"
+                                   + (", --skip-exact-matches" if skip else ""),
                        "l2": "no flush needed: bit rows %.0f MB + count vectors %.0f MB per step >> 126 MB L2" % (
                            ctx.index_bytes / 1e6, q_per_gpu * ctx.shard_refs * 2 / 1e6),
                        "sub_batch": ctx.sub_batch, "pipeline": bool(args.pipeline > 0),
@@ -369,7 +377,7 @@ def main():
     # ---- CPU baseline beside it (rank 0, N = 1 only) -----------------------------------------------------------------
     if world == 1 and not args.no_cpu_baseline:
         n_sample, chunk = cpu_sample_plan(q_per_gpu, cores, args.cpu_sample)
-        _, run = cpu_reference_rate(ds, 0, n_sample, cores, chunk)
+        _, run = cpu_reference_rate(ds, 0, n_sample, cores, chunk, skip=skip)
         run()
         secs = run()
         line["cpu_baseline"] = {"value": n_sample / secs, "unit": UNIT, "cores": cores, "kind": "port",
