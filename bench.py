@@ -288,7 +288,6 @@ def main():
     torch.cuda.synchronize()
     barrier()
     dev_ms = max_over_ranks(ev0.elapsed_time(ev1))
-    clocks = sampler.stop()
     res = ctx.batch_download()
     prof_main = ctx.profile()
     n_results = len(res.first_ref)
@@ -328,6 +327,7 @@ def main():
         out = ctx.classify(off_p, codes_p, eo_p, eids_p, skip_exact=skip, out=res_buf)
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     barrier()
+    clocks = sampler.stop()  # polled from the start of the device-resident leg to the end of the end-to-end leg (all three timed legs)
     prof_e2e = ctx.profile()
     e2e_value = q_per_gpu * world * args.steps / e2e_s
     assert len(out.first_ref) == n_results
