@@ -525,7 +525,7 @@ constexpr int kHitGroupMaxThreads = 512;
 template <int V, int NP, bool LOCKSTEP, int MAX_THREADS, int CTAS_PER_SM, bool L1A = true>
 __global__ void __launch_bounds__(MAX_THREADS, CTAS_PER_SM)
     hitcount_group_kernel(IndexView ix, BatchView b, u16* __restrict__ counts, int q_base, int q_count, int tiles_per_cta, int n_tiles,
-                          u32 chunk_rows, int n_chunks) {
+                          u32 chunk_rows, int n_chunks, u16* __restrict__ segmax, size_t segmax_stride) {
     extern __shared__ __align__(16) u32 hsm[];
     typedef typename RowVec<V>::T vec_t;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -598,10 +598,13 @@ __global__ void __launch_bounds__(MAX_THREADS, CTAS_PER_SM)
             ++c;
         }
         if (valid) {
+            u32 lane_max = 0;  // largest count among this lane's 32 * V references, in both half-words
 #pragma unroll
             for (int v = 0; v < V; ++v) {
                 u32 out[16];
                 planes_to_counts<NP>(pl[v], out);
+#pragma unroll
+                for (int i = 0; i < 16; ++i) lane_max = __vmaxu2(lane_max, out[i]);
                 const u64 ref0 = (u64)(word0 + v) * 32;
                 uint4* dst = reinterpret_cast<uint4*>(qcounts + ref0);
 #pragma unroll
@@ -619,6 +622,16 @@ __global__ void __launch_bounds__(MAX_THREADS, CTAS_PER_SM)
                         if (ref0 + 2 * i + 1 < ix.shard_refs) atomicAdd(&shist[out[i] >> 16], 1u);
                     }
                 }
+            }
+            // largest count per 512-reference prefix segment (32 * V = 64 references per lane: 8 lanes per segment), so that K4 can
+            // drop a segment below m_min without reading its counts (padding references count 0 and never raise the maximum)
+            if (segmax != nullptr) {
+                u32 m = max(lane_max & 0xFFFFu, lane_max >> 16);
+                constexpr int kLanesPerSeg = 512 / (32 * V);
+#pragma unroll
+                for (int o = 1; o < kLanesPerSeg; o <<= 1) m = max(m, __shfl_xor_sync(kFullMask, m, o));
+                if ((lane & (kLanesPerSeg - 1)) == 0)
+                    segmax[(size_t)ql * segmax_stride + (size_t)tile * (32 / kLanesPerSeg) + lane / kLanesPerSeg] = (u16)m;
             }
         }
     }
@@ -749,7 +762,8 @@ struct ProbScratch {
     size_t preb_stride;  //   to the start of the 512-reference segment the boundary belongs to
     double* segoff;      // [sub-batch queries][segoff_stride] prefix sum at the start of every 512-reference segment
     size_t segoff_stride;
-    u32 seg_aux_off;     // per query, behind the segment offsets (in doubles): u32 aux[] = { m_min, 0, skip bitmap words ... }
+    u32 seg_aux_off;     // per query, behind the segment offsets (in doubles): u32 aux[] = { m_min, 0, skip bitmap words ..., u16 segmax[n_seg] }
+                         //   segmax (K2 -> K4): largest count of every 512-reference segment
                          //   m_min (K3 -> K4): counts below it carry < kMassCut of the probability mass altogether and are taken as 0
                          //   skip bit s (K4 -> walk): no reference of segment s reaches m_min; its boundary prefixes were not written
     double* ptab;        // [sub-batch queries][hstride] normalised P(m), direct-indexed by count (K3 -> K4)
@@ -805,6 +819,10 @@ __device__ __forceinline__ double node_conf(const double* __restrict__ preb, con
 }
 __device__ __forceinline__ const u32* seg_aux(const ProbScratch& sc, int ql) {
     return reinterpret_cast<const u32*>(sc.segoff + (size_t)ql * sc.segoff_stride + sc.seg_aux_off);
+}
+// u16 segmax[n_seg] behind the skip bitmap words (K2 -> K4)
+__host__ __device__ __forceinline__ const u16* seg_max(const ProbScratch& sc, int ql, u32 n_seg) {
+    return reinterpret_cast<const u16*>(reinterpret_cast<const u32*>(sc.segoff + (size_t)ql * sc.segoff_stride + sc.seg_aux_off) + 2 + (n_seg + 31) / 32);
 }
 constexpr double kMassCut = 1e-25;
 
@@ -1152,7 +1170,7 @@ __device__ __forceinline__ void prefix_gather(double (&v)[kPrefixPer], const dou
 }
 
 __global__ void __launch_bounds__(kPrefixThreads)
-    prefix_kernel(IndexView ix, BatchView b, ProbScratch sc, const u16* __restrict__ counts, int q_base, int q_count) {
+    prefix_kernel(IndexView ix, BatchView b, ProbScratch sc, const u16* __restrict__ counts, int q_base, int q_count, int use_segmax) {
     extern __shared__ __align__(16) unsigned char xsm_raw[];
     __shared__ double wtot[kPrefixWarps];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -1173,26 +1191,39 @@ __global__ void __launch_bounds__(kPrefixThreads)
     const u64 Ns = ix.shard_refs;
     u32* __restrict__ aux = const_cast<u32*>(seg_aux(sc, ql));
     const u32 mmin2 = aux[0] * 0x10001u;  // m_min in both half-words
+    // per-segment maxima left by the hit-count kernel (upper bounds in skip mode, where exact matches were zeroed afterwards)
+    const u16* __restrict__ smax = use_segmax ? seg_max(sc, ql, n_seg) : nullptr;
     u32* skipw_s = reinterpret_cast<u32*>(stage_end);
     for (u32 i = tid; i < (n_seg + 31u) / 32u; i += kPrefixThreads) skipw_s[i] = 0u;
     __syncthreads();
 
+    const u32 mmin = aux[0];
+    // a segment whose maximum stays below m_min is dropped without its counts ever being requested
+    auto dropped = [&](u32 s) { return smax != nullptr && (u32)smax[s] < mmin; };
     uint4 c0 = make_uint4(0, 0, 0, 0), c1 = c0;
-    if ((u32)warp < n_seg) {
+    if ((u32)warp < n_seg && !dropped(warp)) {
         const u64 r0 = (u64)warp * kPrefixSeg + (u64)lane * kPrefixPer;
         c0 = *reinterpret_cast<const uint4*>(qcounts + r0);
         c1 = *reinterpret_cast<const uint4*>(qcounts + r0 + 8);
     }
     for (u32 s = warp; s < n_seg; s += kPrefixWarps) {
         const u64 r0 = (u64)s * kPrefixSeg + (u64)lane * kPrefixPer;
-        const u32 word = ix.bnd_after[r0 >> 5];
-        const u32 rank0 = ix.bnd_rank[s * (kPrefixSeg / 32)];  // boundaries before this segment
         const uint4 x0 = c0, x1 = c1;
-        if (s + kPrefixWarps < n_seg) {  // the next segment's counts are requested before this one is used
+        const bool drop_this = dropped(s);
+        if (s + kPrefixWarps < n_seg && !dropped(s + kPrefixWarps)) {  // the next segment's counts are requested before this one is used
             const u64 rn = r0 + (u64)kPrefixWarps * kPrefixSeg;
             c0 = *reinterpret_cast<const uint4*>(qcounts + rn);
             c1 = *reinterpret_cast<const uint4*>(qcounts + rn + 8);
         }
+        if (drop_this) {
+            if (lane == 0) {
+                segtot[s] = 0.0;
+                atomicOr(&skipw_s[s >> 5], 1u << (s & 31));
+            }
+            continue;
+        }
+        const u32 word = ix.bnd_after[r0 >> 5];
+        const u32 rank0 = ix.bnd_rank[s * (kPrefixSeg / 32)];  // boundaries before this segment
         {   // does any reference of the segment reach m_min?  (padding references have count 0; m_min == 0 keeps everything)
             const u32 mx = __vmaxu2(__vmaxu2(__vmaxu2(x0.x, x0.y), __vmaxu2(x0.z, x0.w)), __vmaxu2(__vmaxu2(x1.x, x1.y), __vmaxu2(x1.z, x1.w)));
             if (!__any_sync(kFullMask, __vcmpgeu2(mx, mmin2) != 0u)) {

@@ -28,6 +28,7 @@ struct rtx_ctx {
     bool two_slots = false;    // this batch runs pipelined
     cudaStream_t cur_stream = nullptr;  // what the launch helpers use: stream / slot of the sub-batch being issued
     u16* cur_counts = nullptr;
+    bool segmax_valid = false;  // the last hit-count launch left per-segment maxima in cur_sc's aux area
     ProbScratch* cur_sc = nullptr;
     std::string err;
     // options
@@ -835,7 +836,7 @@ RTX_API int rtx_batch_upload(rtx_ctx* ctx, const rtx_batch* batch) {
     if (!sb) {
         const u64 mem_free = ctx->mem_free_after_index;  // sampled once per index upload (cudaMemGetInfo costs ~1 ms per call)
         const u64 budget = std::min<u64>(std::max<u64>(mem_free / 4, 2ull << 30), 48ull << 30);
-        const u64 scratch_per_query = per_query + ((u64)round_up(ctx->ix.n_bnd, 4) + ctx->ix.n_pad / kPrefixSeg + ctx->ix.n_pad / kPrefixSeg / 64 + 8 + hstride) * 8;
+        const u64 scratch_per_query = per_query + ((u64)round_up(ctx->ix.n_bnd, 4) + ctx->ix.n_pad / kPrefixSeg + ctx->ix.n_pad / kPrefixSeg / 64 + ctx->ix.n_pad / kPrefixSeg / 4 + 8 + hstride) * 8;
         sb = std::max<u64>(1, budget / scratch_per_query);
     }
     const bool may_pipe = ctx->pipeline_opt && ctx->sv.n_shards <= 1;
@@ -881,7 +882,7 @@ RTX_API int rtx_batch_upload(rtx_ctx* ctx, const rtx_batch* batch) {
     {   // per query: n_seg segment offsets | u32 aux[2 + n_seg/32] (m_min, skip bitmap; ProbScratch::seg_aux_off)
         const u32 n_seg = (u32)(ctx->ix.n_pad / kPrefixSeg);
         ctx->sc.seg_aux_off = round_up(n_seg, 2);
-        ctx->sc.segoff_stride = round_up(ctx->sc.seg_aux_off + 1 + ((n_seg + 31) / 32 + 1) / 2, 4);
+        ctx->sc.segoff_stride = round_up(ctx->sc.seg_aux_off + 1 + ((n_seg + 31) / 32 + 1) / 2 + (n_seg + 3) / 4, 4);  // + u16 segmax[n_seg]
     }
     CU(ctx->d_segoff.ensure((size_t)sb * ctx->sc.segoff_stride * 8));
     ctx->sc.segoff = ctx->d_segoff.as<double>();
@@ -979,7 +980,11 @@ static cudaError_t launch_hitcount_group(rtx_ctx* c, int q_base, int qb, int G) 
     auto go = [&](auto kernel) -> cudaError_t {
         cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        kernel<<<grid, G * 32, smem, c->cur_stream>>>(c->ix, c->bv, c->cur_counts, q_base, qb, tiles_per_cta, n_tiles, chunk_rows, n_chunks);
+        const u32 n_seg = (u32)(c->ix.n_pad / kPrefixSeg);
+        u16* segmax = const_cast<u16*>(seg_max(*c->cur_sc, 0, n_seg));
+        kernel<<<grid, G * 32, smem, c->cur_stream>>>(c->ix, c->bv, c->cur_counts, q_base, qb, tiles_per_cta, n_tiles, chunk_rows, n_chunks, segmax,
+                                                    c->cur_sc->segoff_stride * 4);
+        c->segmax_valid = true;
         return cudaGetLastError();
     };
     if (n_chunks > 1) return go(hitcount_group_kernel<V, NP, true, kHitGroupMaxThreads, 1>);
@@ -988,6 +993,7 @@ static cudaError_t launch_hitcount_group(rtx_ctx* c, int q_base, int qb, int G) 
 }
 
 static cudaError_t launch_hitcount_tuned(rtx_ctx* c, int q_base, int qb, u32 kmax) {
+    c->segmax_valid = false;  // only the query-group kernel leaves per-segment maxima
     int G = c->hit_group;  // 0 = default
     const bool force_group = G == 101;
     if (force_group) G = 1;
@@ -1011,6 +1017,7 @@ static cudaError_t launch_hitcount_tuned(rtx_ctx* c, int q_base, int qb, u32 kma
 static int run_phase1(rtx_ctx* ctx, int q_base, int qb) {
     const u32 kmax = ctx->max_len >= 8 ? ctx->max_len - 7 : 0;
     LaunchTimer lt(ctx, RTX_K_HITCOUNT);
+    ctx->segmax_valid = false;  // only the query-group bit-row kernel leaves per-segment maxima for K4
     if (ctx->variant == RTX_HITCOUNT_CSR) {
         if (!ctx->ix.csr_ids && kmax > 0 && ctx->n_rows > 1)
             return set_err(ctx, RTX_ERR_INVALID, "CSR hit-count variant needs RTX_OPT_KEEP_CSR set before rtx_index_upload");
@@ -1038,7 +1045,8 @@ static int launch_prob(rtx_ctx* ctx, int q0, int qb) {
     }
     {
         LaunchTimer lt(ctx, RTX_K_PREFIX);
-        prefix_kernel<<<qb, kPrefixThreads, ctx->prefix_smem, ctx->cur_stream>>>(ctx->ix, ctx->bv, *ctx->cur_sc, ctx->cur_counts, q0, qb);
+        prefix_kernel<<<qb, kPrefixThreads, ctx->prefix_smem, ctx->cur_stream>>>(ctx->ix, ctx->bv, *ctx->cur_sc, ctx->cur_counts, q0, qb,
+                                                                                 ctx->segmax_valid ? 1 : 0);
         CU(cudaGetLastError());
     }
     return RTX_OK;
