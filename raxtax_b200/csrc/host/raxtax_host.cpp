@@ -1001,19 +1001,69 @@ struct Worker {
         std::vector<u16> n_kmers;
         std::vector<u8> n_levels;
         std::vector<double> conf, local, global;
-        std::vector<u32> ex;
+        std::vector<u32> ex, rep, uniq_first;
+        std::vector<u64> u_off;
+        std::vector<u8> u_codes;
+        std::unordered_map<u64, std::vector<u32>> seen;
+        const bool dedup = getenv("RXH_NO_DEDUP") == nullptr;
         std::string primary, tsv_out, msg;
         while (true) {
             const size_t c0 = next_chunk.fetch_add(1) * chunk_size;
             if (c0 >= nq || failed.load()) break;
             const size_t cn = std::min(chunk_size, nq - c0);
-            exact_off.assign(cn + 1, 0);
+            // Queries with identical sequences (amplicon reads of an abundant taxon) get identical results: the device sees every
+            // distinct sequence of the chunk once, the lines are then written per query label as the reference would (RXH_NO_DEDUP=1
+            // switches this off).  rep[i] = position of query i's sequence among the distinct ones.
+            rep.assign(cn, 0);
+            size_t n_uniq = cn;
+            if (dedup && cn > 1) {
+                seen.clear();
+                uniq_first.clear();
+                for (size_t i = 0; i < cn; ++i) {
+                    const u8* sp = qs.codes.data() + qs.off[c0 + i];
+                    const size_t sl = (size_t)(qs.off[c0 + i + 1] - qs.off[c0 + i]);
+                    auto& bucket = seen[Tree::hash_bytes(sp, sl)];
+                    u32 found = 0xFFFFFFFFu;
+                    for (u32 u : bucket) {
+                        const size_t j = uniq_first[u];
+                        const size_t jl = (size_t)(qs.off[c0 + j + 1] - qs.off[c0 + j]);
+                        if (jl == sl && (sl == 0 || memcmp(qs.codes.data() + qs.off[c0 + j], sp, sl) == 0)) {
+                            found = u;
+                            break;
+                        }
+                    }
+                    if (found == 0xFFFFFFFFu) {
+                        found = (u32)uniq_first.size();
+                        uniq_first.push_back((u32)i);
+                        bucket.push_back(found);
+                    }
+                    rep[i] = found;
+                }
+                n_uniq = uniq_first.size();
+            }
+            const bool compact = n_uniq < cn;
+            if (compact) {  // the distinct sequences, contiguous
+                u_off.assign(1, 0);
+                u_codes.clear();
+                for (size_t u = 0; u < n_uniq; ++u) {
+                    const size_t q = c0 + uniq_first[u];
+                    u_codes.insert(u_codes.end(), qs.codes.begin() + (ptrdiff_t)qs.off[q], qs.codes.begin() + (ptrdiff_t)qs.off[q + 1]);
+                    u_off.push_back(u_codes.size());
+                }
+            } else {
+                for (size_t i = 0; i < cn; ++i) rep[i] = (u32)i;
+            }
+            exact_off.assign(n_uniq + 1, 0);
             exact_ids.clear();
-            for (size_t i = 0; i < cn; ++i) {  // tree.sequences.get(query_sequence) (raxtax.rs:42)
-                const size_t q = c0 + i;
+            for (size_t u = 0; u < n_uniq; ++u) {  // tree.sequences.get(query_sequence) (raxtax.rs:42), once per distinct sequence
+                const size_t q = c0 + (compact ? uniq_first[u] : u);
                 tree.exact(qs.codes.data() + qs.off[q], (size_t)(qs.off[q + 1] - qs.off[q]), &ex);
                 exact_ids.insert(exact_ids.end(), ex.begin(), ex.end());
-                exact_off[i + 1] = (u32)exact_ids.size();
+                exact_off[u + 1] = (u32)exact_ids.size();
+            }
+            for (size_t i = 0; i < cn; ++i) {  // the log lines of raxtax.rs:43-53, per query
+                const size_t q = c0 + i;
+                ex.assign(exact_ids.begin() + exact_off[rep[i]], exact_ids.begin() + exact_off[rep[i] + 1]);
                 if (!skip_exact_matches) {  // raxtax.rs:43-53
                     bool all_equal = true;
                     std::string first_parent;
@@ -1041,18 +1091,18 @@ struct Worker {
                 }
             }
             rtx_batch batch{};
-            batch.n_queries = (u32)cn;
-            batch.seq_offsets = qs.off.data() + c0;
-            batch.seq_codes = qs.codes.data();
+            batch.n_queries = (u32)n_uniq;
+            batch.seq_offsets = compact ? u_off.data() : qs.off.data() + c0;
+            batch.seq_codes = compact ? u_codes.data() : qs.codes.data();
             batch.exact_offsets = exact_off.data();
             batch.exact_ids = exact_ids.empty() ? nullptr : exact_ids.data();
             batch.flags = (skip_exact_matches ? RTX_SKIP_EXACT_MATCHES : 0u) | (raw_confidence ? RTX_RAW_CONFIDENCE : 0u);
             // the device batch API wants seq_codes to be the base the offsets index into
             rtx_results res{};
-            n_kmers.resize(cn);
-            result_begin.resize(cn + 1);
-            global.resize(cn);
-            size_t cap = std::max<size_t>(first_ref.size(), cn * 8 + 64);
+            n_kmers.resize(n_uniq);
+            result_begin.resize(n_uniq + 1);
+            global.resize(n_uniq);
+            size_t cap = std::max<size_t>(first_ref.size(), n_uniq * 8 + 64);
             while (true) {
                 first_ref.resize(cap);
                 n_levels.resize(cap);
@@ -1081,12 +1131,13 @@ struct Worker {
                 tsv_out.clear();
                 std::string seq;
                 if (tsv) seq = decompress_sequence(qs.codes.data() + qs.off[q], (size_t)(qs.off[q + 1] - qs.off[q]));
-                for (u32 r = result_begin[i]; r < result_begin[i + 1]; ++r) {
-                    ResultView rv{&tree.lineages[first_ref[r]], conf.data() + (size_t)r * ML, n_levels[r], local[r], global[i]};
-                    if (r != result_begin[i]) primary += '\n';
+                const u32 u = rep[i];
+                for (u32 r = result_begin[u]; r < result_begin[u + 1]; ++r) {
+                    ResultView rv{&tree.lineages[first_ref[r]], conf.data() + (size_t)r * ML, n_levels[r], local[r], global[u]};
+                    if (r != result_begin[u]) primary += '\n';
                     output_string(primary, qs.labels[q], rv);
                     if (tsv) {
-                        if (r != result_begin[i]) tsv_out += '\n';
+                        if (r != result_begin[u]) tsv_out += '\n';
                         tsv_string(tsv_out, qs.labels[q], rv, seq);
                     }
                 }

@@ -684,3 +684,29 @@ def test_random_mid_size_against_oracle(oracle, ctx, seed):
     o, dev, ot, _ = _run_both(oracle, ctx, (lineages, r_off, r_codes, q_off, q_codes), skip=skip, sub_batch=int(seed % 4) * 7, variant=variant)
     _assert_integer_parity(o, dev, len(queries))
     _assert_result_parity(o, dev, ot, len(queries), max_tolerated_frac=1.0)
+
+
+def test_host_driver_dedups_identical_queries(ctx):
+    """rxh_raxtax classifies every distinct sequence of a chunk once; the lines sent per query label (and the exact-match log lines)
+    are those of the plain one-by-one path (RXH_NO_DEDUP=1)."""
+    ds = synth.generate("small", n_queries=60, measure=False)
+    rng = np.random.default_rng(4)
+    pick = rng.integers(0, 60, 200)  # 200 queries drawn from 60 distinct sequences
+    seqs = [ds.query_seq(int(i)) for i in pick]
+    off = np.zeros(len(seqs) + 1, np.uint64)
+    off[1:] = np.cumsum([len(s) for s in seqs])
+    qs = capi.Queries.new([f"read{j}_{int(i)}" for j, i in enumerate(pick)], off, np.concatenate(seqs))
+    ht = capi.Tree.new(ds.ref_lineages, ds.ref_off, ds.ref_codes)
+    ctx.upload_tree(ht)
+    ctx.profile_reset()
+    a = capi.raxtax(ctx, qs, ht, chunk_size=64, tsv=True)
+    n_dedup = ctx.profile()["queries"]
+    os.environ["RXH_NO_DEDUP"] = "1"
+    try:
+        ctx.profile_reset()
+        b = capi.raxtax(ctx, qs, ht, chunk_size=64, tsv=True)
+        n_plain = ctx.profile()["queries"]
+    finally:
+        del os.environ["RXH_NO_DEDUP"]
+    assert a == b
+    assert n_plain == 200 and n_dedup < 200  # the device saw fewer queries
