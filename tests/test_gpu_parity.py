@@ -546,9 +546,16 @@ def test_random_shapes_against_oracle(oracle, ctx, seed):
     r_off, r_codes = _pack(oracle, refs)
     q_off, q_codes = _pack(oracle, queries)
     for skip, raw in [(False, False), (True, False), (False, True)]:
-        o, dev, ot, _ = _run_both(oracle, ctx, (lineages, r_off, r_codes, q_off, q_codes), skip=skip, raw=raw, sub_batch=int(seed % 3) * 5)
+        o, dev, ot, ht = _run_both(oracle, ctx, (lineages, r_off, r_codes, q_off, q_codes), skip=skip, raw=raw, sub_batch=int(seed % 3) * 5)
         _assert_integer_parity(o, dev, len(queries))
-        _assert_result_parity(o, dev, ot, len(queries), max_tolerated_frac=1.0)
+        ok, tol = _assert_result_parity(o, dev, ot, len(queries), max_tolerated_frac=1.0)
+        if tol == 0:  # the text the host driver sends (raxtax.out / raxtax.tsv lines, lineage.rs:17-48) against the oracle's formatting
+            labels = [f"q{i} some read" for i in range(len(queries))]
+            qs = capi.Queries.new(labels, q_off, q_codes)
+            sent, _, _ = capi.raxtax(ctx, qs, ht, skip_exact_matches=skip, raw_confidence=raw, chunk_size=7, tsv=True)
+            assert [x[0] for x in sent] == labels
+            assert [l for x in sent for l in x[1].split("\n")] == oracle.format_results(ot, o["results"], labels).split("\n")
+            assert [l for x in sent for l in x[2].split("\n")] == oracle.format_results(ot, o["results"], labels, q_off, q_codes, tsv=True).split("\n")
 
 
 def test_context_reuse_across_indexes_of_different_depth(oracle, ctx):
