@@ -717,3 +717,24 @@ def test_host_driver_dedups_identical_queries(ctx):
         del os.environ["RXH_NO_DEDUP"]
     assert a == b
     assert n_plain == 200 and n_dedup < 200  # the device saw fewer queries
+
+
+@pytest.mark.parametrize("n_taxa", [190, 200, 201, 210, 256])
+def test_many_equally_likely_taxa(oracle, ctx, n_taxa):
+    """n identical references under n different species: every species gets 1/n.  n < 200 -> n result lines (1/n > 0.005 rounds to
+    0.01; 200 is the most lines a query can produce), n > 200 -> nothing is significant below the genus and the fallback takes one of
+    n exactly tied children (lineage.rs:156-164: which one is ulp noise in the reference, the checker accepts any of the tied)."""
+    rng = np.random.default_rng(11)
+    seq = synth.BASE_CODES[rng.integers(0, 4, 120)]
+    other = synth.BASE_CODES[rng.integers(0, 4, 120)]
+    lineages = [f"k,g,s{i:03d}" for i in range(n_taxa)] + ["k,h,x"]
+    refs = [seq.copy() for _ in range(n_taxa)] + [other]
+    r_off, r_codes = _pack(oracle, refs)
+    q_off, q_codes = _pack(oracle, [seq, seq[:60], other])
+    for skip, raw in [(False, False), (False, True), (True, False)]:
+        o, dev, ot, _ = _run_both(oracle, ctx, (lineages, r_off, r_codes, q_off, q_codes), skip=skip, raw=raw)
+        _assert_integer_parity(o, dev, 3)
+        _assert_result_parity(o, dev, ot, 3, max_tolerated_frac=1.0)
+        if not skip and n_taxa != 200:  # 1/200 sits exactly on the rounding boundary: the reference itself reports 190 of the 200
+            n_lines = int(dev.result_begin[1] - dev.result_begin[0])
+            assert n_lines == (n_taxa if n_taxa < 200 else 1), n_lines
