@@ -759,7 +759,7 @@ RTX_API int rtx_batch_upload(rtx_ctx* ctx, const rtx_batch* batch) {
         smem = ProbSmem::bytes(hstride, hstride / 2 + 1, nprod, lf_smem);
     }
     if (smem > 200 * 1024)
-        return set_err(ctx, RTX_ERR_UNSUPPORTED, "query too long for the shared-memory probability tables (more than ~6800 unique 8-mers)");
+        return set_err(ctx, RTX_ERR_UNSUPPORTED, "query too long for the shared-memory probability tables (more than ~6 390 8-mer windows, i.e. queries longer than ~6.4 kb)");
     ctx->sc.nprod = nprod;
     ctx->sc.lf_smem = lf_smem;
     ctx->max_len = max_len;

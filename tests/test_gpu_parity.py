@@ -738,3 +738,49 @@ def test_many_equally_likely_taxa(oracle, ctx, n_taxa):
         if not skip and n_taxa != 200:  # 1/200 sits exactly on the rounding boundary: the reference itself reports 190 of the 200
             n_lines = int(dev.result_begin[1] - dev.result_begin[0])
             assert n_lines == (n_taxa if n_taxa < 200 else 1), n_lines
+
+
+def test_documented_limits(oracle, ctx):
+    """The envelope INTEGRATION.md states: lineages of up to RTX_MAX_LEVELS = 32 ranks and queries of up to ~6.4 kb (6 390 8-mer windows) are
+    classified like the oracle does; one rank / one kilobase more is refused loudly (RTX_ERR_UNSUPPORTED), never mis-computed."""
+    rng = np.random.default_rng(21)
+    base = synth.BASE_CODES[rng.integers(0, 4, 300)]
+
+    def db(depth):
+        lin, refs = [], []
+        for i in range(12):
+            lin.append(",".join(f"r{l}_{i if l >= depth - 2 else 0}" for l in range(depth)))
+            s = base.copy()
+            mut = rng.random(len(s)) < 0.05 * (i % 4)
+            s[mut] = synth.BASE_CODES[rng.integers(0, 4, int(mut.sum()))]
+            refs.append(s)
+        return lin, refs
+
+    lin, refs = db(32)
+    q_off, q_codes = _pack(oracle, [refs[3], base, base[:100]])
+    o, dev, ot, _ = _run_both(oracle, ctx, (lin, *_pack(oracle, refs), q_off, q_codes))
+    _assert_integer_parity(o, dev, 3)
+    _assert_result_parity(o, dev, ot, 3, max_tolerated_frac=1.0)
+    assert dev.confidence.shape[1] == 32
+    lin33, refs33 = db(33)
+    with pytest.raises(capi.RtxError) as ei:
+        ctx.upload_tree(capi.Tree.new(lin33, *_pack(oracle, refs33)))
+    assert ei.value.code == capi.RTX_ERR_UNSUPPORTED
+    # long queries: 6.3 kb (about 6 300 unique 8-mers) against 6.3 kb references
+    long_base = synth.BASE_CODES[rng.integers(0, 4, 6300)]
+    lrefs = []
+    for i in range(20):
+        s = long_base.copy()
+        mut = rng.random(len(s)) < 0.02 * (i % 5)
+        s[mut] = synth.BASE_CODES[rng.integers(0, 4, int(mut.sum()))]
+        lrefs.append(s)
+    llin = [f"k,p{i % 2},g{i % 5},s{i}" for i in range(20)]
+    lq = [lrefs[7], long_base[100:6250], long_base[:900]]
+    o, dev, ot, _ = _run_both(oracle, ctx, (llin, *_pack(oracle, lrefs), *_pack(oracle, lq)))
+    _assert_integer_parity(o, dev, 3)
+    _assert_result_parity(o, dev, ot, 3, max_tolerated_frac=1.0)
+    assert int(dev.n_kmers.max()) > 5500
+    too_long = synth.BASE_CODES[rng.integers(0, 4, 9000)]
+    with pytest.raises(capi.RtxError) as ei:
+        ctx.classify(*_pack(oracle, [too_long]))
+    assert ei.value.code == capi.RTX_ERR_UNSUPPORTED
