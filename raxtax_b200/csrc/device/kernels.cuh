@@ -383,10 +383,11 @@ __device__ __forceinline__ void merge_carries_v(u32 (&pl)[V][NP], const u32 (&ea
 
 template <int V, int NP, bool PF>
 __global__ void __launch_bounds__(kHitThreads)
-    hitcount_bitrows_kernel(IndexView ix, BatchView b, u16* __restrict__ counts, int q_base, int tiles_per_cta, int n_tiles) {
+    hitcount_bitrows_kernel(IndexView ix, BatchView b, u16* __restrict__ counts, int q_base, int tiles_per_cta, int n_tiles, int hist_global) {
     extern __shared__ __align__(16) u32 hsm[];
     u32* srow = hsm;
-    u32* shist = hsm + kRowListCap;
+    // hist_global: queries with tens of thousands of 8-mers, whose histogram does not fit shared memory: bins are bumped in global memory
+    u32* shist = hist_global ? b.hist + (size_t)(q_base + blockIdx.x) * b.hstride : hsm + kRowListCap;
     typedef typename RowVec<V>::T vec_t;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int nthreads = blockDim.x, nwarps = nthreads >> 5;
@@ -400,7 +401,8 @@ __global__ void __launch_bounds__(kHitThreads)
     const u32 nbins = (u32)b.K[q] + 1u;
     const u32 row_bytes = ix.row_words * 4u;
 
-    for (u32 i = tid; i < nbins; i += nthreads) shist[i] = 0;
+    if (!hist_global)
+        for (u32 i = tid; i < nbins; i += nthreads) shist[i] = 0;
     const bool single = n <= (u32)kRowListCap;
     if (single) {
         for (u32 i = tid; i < n; i += nthreads) srow[i] = qrows[i];
@@ -478,6 +480,7 @@ __global__ void __launch_bounds__(kHitThreads)
         }
     }
     __syncthreads();
+    if (hist_global) return;
     u32* __restrict__ ghist = b.hist + (size_t)q * b.hstride;
     for (u32 i = tid; i < nbins; i += nthreads) {
         u32 h = shist[i];
@@ -769,6 +772,10 @@ struct ProbScratch {
     double* ptab;        // [sub-batch queries][hstride] normalised P(m), direct-indexed by count (K3 -> K4)
     int nprod;           // kProbWarps: one partial prod array per warp; 1: a single array updated with shared-memory atomics
     int lf_smem;         // 1: ln n! staged in shared memory, 0: read from HBM/L2 (very long queries)
+    // queries beyond ~6.4 kb (up to the 65 535 8-mers raxtax.rs:56 allows): the per-query tables of K3 live in global scratch
+    // (one slot per CTA, same carve-up as the shared-memory layout) and K4 gathers P(m) from the global table
+    unsigned char* big;  // null: tables in shared memory
+    size_t big_stride;   // bytes per CTA slot
 };
 
 // dynamic smem carve-up (sizes depend on H = hstride, T1 = H/2 + 1)
@@ -873,7 +880,7 @@ __global__ void __launch_bounds__(kProbThreads, 4)
 
     const u32 H = b.hstride;
     const u32 T1 = H / 2 + 1;
-    ProbSmem sm(psm_raw, H, T1, sc.nprod, sc.lf_smem);
+    ProbSmem sm(sc.big ? sc.big + (size_t)blockIdx.x * sc.big_stride : psm_raw, H, T1, sc.nprod, sc.lf_smem);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const double NEG_INF = -CUDART_INF;
     const double Nd = (double)ix.n_refs;
@@ -1178,13 +1185,18 @@ __global__ void __launch_bounds__(kPrefixThreads)
     if (ql >= q_count) return;
     const int q = q_base + ql;
     const u32 n_seg = (u32)(ix.n_pad / kPrefixSeg);
-    double* Ptab = reinterpret_cast<double*>(xsm_raw);
-    double* segtot = Ptab + b.hstride;
+    const bool ptab_global = sc.big != nullptr;  // very long queries: P(m) is gathered from the global table (L2) instead of a shared-memory copy
+    double* segtot = reinterpret_cast<double*>(xsm_raw) + (ptab_global ? 0u : b.hstride);
     double* stage = segtot + ((n_seg + 1u) & ~1u) + (size_t)warp * kPrefixSeg;
     double* stage_end = segtot + ((n_seg + 1u) & ~1u) + (size_t)kPrefixWarps * kPrefixSeg;  // u32 skip bitmap words behind the staging area
     const u32 K = b.K[q];
     const double* __restrict__ gp = sc.ptab + (size_t)ql * b.hstride;
-    for (u32 m = tid; m <= K; m += kPrefixThreads) Ptab[m] = gp[m];
+    const double* __restrict__ Ptab = gp;
+    if (!ptab_global) {
+        double* Ps = reinterpret_cast<double*>(xsm_raw);
+        for (u32 m = tid; m <= K; m += kPrefixThreads) Ps[m] = gp[m];
+        Ptab = Ps;
+    }
     __syncthreads();
     const u16* __restrict__ qcounts = counts + (size_t)ql * ix.n_pad;
     double* __restrict__ preb = sc.preb + (size_t)ql * sc.preb_stride;

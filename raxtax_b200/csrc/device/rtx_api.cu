@@ -67,7 +67,8 @@ struct rtx_ctx {
     // prob scratch
     ProbScratch sc{}, sc1{};
     int prob_slots = 0;
-    size_t prob_smem = 0, walk_smem = 0, prefix_smem = 0, bfs_smem = 0;
+    size_t prob_smem = 0, walk_smem = 0, prefix_smem = 0, bfs_smem = 0, prob_big_bytes = 0;
+    DevBuf d_prob_big;
     DevBuf d_cbuf, d_preb, d_ptab, d_segoff, d_preb1, d_ptab1, d_segoff1;
     // reference-sharded mode
     ShardView sv{};
@@ -282,7 +283,7 @@ RTX_API void rtx_ctx_destroy(rtx_ctx* c) {
                       &c->d_pool_conf, &c->d_pool_local, &c->d_pool_used, &c->d_res_off, &c->d_res_cnt, &c->d_global, &c->d_status,
                       &c->d_hits, &c->d_seq_codes, &c->d_cbuf, &c->d_preb, &c->d_ptab, &c->d_segoff, &c->d_recs, &c->d_strad_of_node, &c->d_strad_nodes, &c->d_strad_parent,
                       &c->d_send, &c->d_recv, &c->d_sk, &c->d_sany, &c->d_sbest, &c->d_ord_begin, &c->d_ord_first, &c->d_ord_nlev,
-                      &c->d_ord_conf, &c->d_ord_local};
+                      &c->d_ord_conf, &c->d_ord_local, &c->d_prob_big};
     for (DevBuf* b : bufs) b->release();
     if (c->h_arena) cudaFreeHost(c->h_arena);
     for (int i = 0; i < 2; ++i) {
@@ -758,8 +759,9 @@ RTX_API int rtx_batch_upload(rtx_ctx* ctx, const rtx_batch* batch) {
         lf_smem = 0;
         smem = ProbSmem::bytes(hstride, hstride / 2 + 1, nprod, lf_smem);
     }
-    if (smem > 200 * 1024)
-        return set_err(ctx, RTX_ERR_UNSUPPORTED, "query too long for the shared-memory probability tables (more than ~6 390 8-mer windows, i.e. queries longer than ~6.4 kb)");
+    const bool big = smem > 200 * 1024;  // queries beyond ~6.4 kb: the tables of K3 move to global scratch (ProbScratch::big)
+    ctx->prob_big_bytes = big ? (smem + 255) & ~(size_t)255 : 0;
+    if (big) smem = 0;
     ctx->sc.nprod = nprod;
     ctx->sc.lf_smem = lf_smem;
     ctx->max_len = max_len;
@@ -855,7 +857,8 @@ RTX_API int rtx_batch_upload(rtx_ctx* ctx, const rtx_batch* batch) {
     if (occ < 1) return set_err(ctx, RTX_ERR_CUDA, "prob_table_kernel does not fit on an SM");
     {
         const size_t n_seg = ctx->ix.n_pad / kPrefixSeg;
-        ctx->prefix_smem = ((size_t)hstride + ((n_seg + 1) & ~(size_t)1) + (size_t)kPrefixWarps * kPrefixSeg) * 8 + ((n_seg + 31) / 32) * 4 + 16;
+        ctx->prefix_smem = ((ctx->prob_big_bytes ? (size_t)0 : (size_t)hstride) + ((n_seg + 1) & ~(size_t)1) + (size_t)kPrefixWarps * kPrefixSeg) * 8 +
+                           ((n_seg + 31) / 32) * 4 + 16;
         if (ctx->prefix_smem > 220 * 1024)
             return set_err(ctx, RTX_ERR_UNSUPPORTED, "reference shard too large for the prefix kernel's segment table (more than ~11 M references per GPU): shard the references");
     }
@@ -867,11 +870,26 @@ RTX_API int rtx_batch_upload(rtx_ctx* ctx, const rtx_batch* batch) {
     CU(cudaFuncSetAttribute(lineage_bfs_kernel<kBfsThreadsDefault>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->bfs_smem));
     CU(cudaFuncSetAttribute(lineage_bfs_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->bfs_smem));
     ctx->shard_phase = 0;
-    const int slots = (int)std::min<u64>((u64)ctx->n_sms * occ, sb);
-    ctx->prob_slots = slots;
+    int slots = (int)std::min<u64>((u64)ctx->n_sms * occ, sb);
     const u32 tstride = round_up(hstride / 2 + 1, 4);
     ctx->sc.tstride = tstride;
     ctx->sc.cbuf_stride = (size_t)hstride * tstride;
+    ctx->sc.big = nullptr;
+    ctx->sc.big_stride = 0;
+    if (ctx->prob_big_bytes) {
+        // long queries: the log-CMF scratch of one CTA slot is hstride x tstride doubles (1 GB at 16 k 8-mers); as many slots as fit a
+        // quarter of the free memory (at most 16 GB), at least one
+        const u64 per_slot = (u64)ctx->sc.cbuf_stride * 8 + ctx->prob_big_bytes;
+        const u64 budget = std::min<u64>(ctx->mem_free_after_index / 4, 16ull << 30);
+        if (per_slot > budget)
+            return set_err(ctx, RTX_ERR_UNSUPPORTED, "query too long: the probability scratch of one query (" + std::to_string(per_slot >> 20) +
+                                                         " MB) does not fit a quarter of the free device memory");
+        slots = (int)std::max<u64>(1, std::min<u64>((u64)slots, budget / per_slot));
+        CU(ctx->d_prob_big.ensure((size_t)slots * ctx->prob_big_bytes));
+        ctx->sc.big = ctx->d_prob_big.as<unsigned char>();
+        ctx->sc.big_stride = ctx->prob_big_bytes;
+    }
+    ctx->prob_slots = slots;
     ctx->sc.preb_stride = round_up(ctx->ix.n_bnd, 4);
     CU(ctx->d_cbuf.ensure((size_t)slots * ctx->sc.cbuf_stride * 8));
     CU(ctx->d_preb.ensure((size_t)sb * ctx->sc.preb_stride * 8));
@@ -933,11 +951,13 @@ static cudaError_t launch_hitcount(rtx_ctx* c, int q_base, int qb, int nwarps_op
         }
     }
     nwarps = std::max(1, std::min(nwarps, kHitThreads / 32));
-    const size_t smem = (size_t)(kRowListCap + c->bv.hstride) * 4;
+    const bool hist_global = (size_t)(kRowListCap + c->bv.hstride) * 4 > 200 * 1024;  // tens of thousands of 8-mers per query
+    const size_t smem = (size_t)(kRowListCap + (hist_global ? 0 : c->bv.hstride)) * 4;
     cudaError_t e = cudaFuncSetAttribute(hitcount_bitrows_kernel<V, NP, PF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     dim3 grid(qb, groups);
-    hitcount_bitrows_kernel<V, NP, PF><<<grid, nwarps * 32, smem, c->cur_stream>>>(c->ix, c->bv, c->cur_counts, q_base, tiles_per_cta, n_tiles);
+    hitcount_bitrows_kernel<V, NP, PF><<<grid, nwarps * 32, smem, c->cur_stream>>>(c->ix, c->bv, c->cur_counts, q_base, tiles_per_cta, n_tiles,
+                                                                                 hist_global ? 1 : 0);
     return cudaGetLastError();
 }
 

@@ -741,8 +741,9 @@ def test_many_equally_likely_taxa(oracle, ctx, n_taxa):
 
 
 def test_documented_limits(oracle, ctx):
-    """The envelope INTEGRATION.md states: lineages of up to RTX_MAX_LEVELS = 32 ranks and queries of up to ~6.4 kb (6 390 8-mer windows) are
-    classified like the oracle does; one rank / one kilobase more is refused loudly (RTX_ERR_UNSUPPORTED), never mis-computed."""
+    """The envelope INTEGRATION.md states: lineages of up to RTX_MAX_LEVELS = 32 ranks (one more is refused loudly, never mis-computed),
+    queries of any length raxtax.rs:56 admits as far as the probability scratch fits device memory (tables in shared memory up to
+    ~6.4 kb, in global scratch beyond)."""
     rng = np.random.default_rng(21)
     base = synth.BASE_CODES[rng.integers(0, 4, 300)]
 
@@ -780,7 +781,23 @@ def test_documented_limits(oracle, ctx):
     _assert_integer_parity(o, dev, 3)
     _assert_result_parity(o, dev, ot, 3, max_tolerated_frac=1.0)
     assert int(dev.n_kmers.max()) > 5500
-    too_long = synth.BASE_CODES[rng.integers(0, 4, 9000)]
+    # beyond ~6.4 kb the per-query tables of the probability kernel move to global scratch: 9 kb and 21 kb queries (a mitochondrial
+    # genome) against references of that length
+    for length in (9000, 21000):
+        gbase = synth.BASE_CODES[rng.integers(0, 4, length)]
+        grefs = []
+        for i in range(10):
+            s = gbase.copy()
+            mut = rng.random(len(s)) < 0.01 * (i % 4)
+            s[mut] = synth.BASE_CODES[rng.integers(0, 4, int(mut.sum()))]
+            grefs.append(s)
+        glin = [f"k,p{i % 2},g{i % 3},s{i}" for i in range(10)]
+        gq = [grefs[3], gbase[50:length - 70], gbase[:700]]
+        o, dev, ot, _ = _run_both(oracle, ctx, (glin, *_pack(oracle, grefs), *_pack(oracle, gq)), skip=length == 21000)
+        _assert_integer_parity(o, dev, 3)
+        _assert_result_parity(o, dev, ot, 3, max_tolerated_frac=1.0)
+        assert int(dev.n_kmers.max()) > length * 0.85
+    # raxtax.rs:56 asserts at most 65 535 unique 8-mers; longer queries are refused, loudly
     with pytest.raises(capi.RtxError) as ei:
-        ctx.classify(*_pack(oracle, [too_long]))
+        ctx.classify(*_pack(oracle, [synth.BASE_CODES[rng.integers(0, 4, 70000)]]))
     assert ei.value.code == capi.RTX_ERR_UNSUPPORTED
