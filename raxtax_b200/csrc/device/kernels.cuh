@@ -870,6 +870,7 @@ __device__ __forceinline__ u32 warp_first_true(u32 a, u32 bnd, int lane, Pred pr
     return bnd;
 }
 
+template <bool BIG>  // BIG: per-query tables in a global scratch slot (long queries); else shared memory, with shared-memory addressing
 __global__ void __launch_bounds__(kProbThreads, 4)
     prob_table_kernel(IndexView ix, BatchView b, ResultPool pool, ProbScratch sc, int q_base, int q_count,
                       unsigned long long* __restrict__ hits_total, unsigned long long* __restrict__ next_query) {
@@ -880,7 +881,7 @@ __global__ void __launch_bounds__(kProbThreads, 4)
 
     const u32 H = b.hstride;
     const u32 T1 = H / 2 + 1;
-    ProbSmem sm(sc.big ? sc.big + (size_t)blockIdx.x * sc.big_stride : psm_raw, H, T1, sc.nprod, sc.lf_smem);
+    ProbSmem sm(BIG ? sc.big + (size_t)blockIdx.x * sc.big_stride : psm_raw, H, T1, sc.nprod, sc.lf_smem);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const double NEG_INF = -CUDART_INF;
     const double Nd = (double)ix.n_refs;

@@ -851,9 +851,13 @@ RTX_API int rtx_batch_upload(rtx_ctx* ctx, const rtx_batch* batch) {
 
     // probability kernel scratch
     ctx->prob_smem = smem;
-    CU(cudaFuncSetAttribute(prob_table_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int occ = 0;
-    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, prob_table_kernel, kProbThreads, smem));
+    if (big) {
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, prob_table_kernel<true>, kProbThreads, 0));
+    } else {
+        CU(cudaFuncSetAttribute(prob_table_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, prob_table_kernel<false>, kProbThreads, smem));
+    }
     if (occ < 1) return set_err(ctx, RTX_ERR_CUDA, "prob_table_kernel does not fit on an SM");
     {
         const size_t n_seg = ctx->ix.n_pad / kPrefixSeg;
@@ -1058,9 +1062,14 @@ static int launch_prob(rtx_ctx* ctx, int q0, int qb) {
         CU(cudaMemsetAsync(ctx->d_hits.as<unsigned long long>() + 1, 0, 8, ctx->cur_stream));  // the kernel's work counter
         LaunchTimer lt(ctx, RTX_K_PROB);
         const int grid = std::min(ctx->prob_slots, qb);
-        prob_table_kernel<<<grid, kProbThreads, ctx->prob_smem, ctx->cur_stream>>>(ctx->ix, ctx->bv, ctx->pool, *ctx->cur_sc, q0, qb,
-                                                                             ctx->d_hits.as<unsigned long long>(),
-                                                                             ctx->d_hits.as<unsigned long long>() + 1);
+        if (ctx->cur_sc->big)
+            prob_table_kernel<true><<<grid, kProbThreads, 0, ctx->cur_stream>>>(ctx->ix, ctx->bv, ctx->pool, *ctx->cur_sc, q0, qb,
+                                                                                ctx->d_hits.as<unsigned long long>(),
+                                                                                ctx->d_hits.as<unsigned long long>() + 1);
+        else
+            prob_table_kernel<false><<<grid, kProbThreads, ctx->prob_smem, ctx->cur_stream>>>(ctx->ix, ctx->bv, ctx->pool, *ctx->cur_sc, q0, qb,
+                                                                                            ctx->d_hits.as<unsigned long long>(),
+                                                                                            ctx->d_hits.as<unsigned long long>() + 1);
         CU(cudaGetLastError());
     }
     {
