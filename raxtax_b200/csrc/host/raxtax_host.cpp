@@ -58,6 +58,20 @@ static inline u8 map_dna_char(char ch) {
     if (!v) throw Error(std::string("Unexpected character: ") + ch);  // panic! in the reference (parser.rs:32)
     return v;
 }
+// one sequence line appended to a code vector: table translation in bulk, the (rare) bad character found afterwards
+static inline void append_codes(std::vector<u8>& codes, const char* b, const char* e) {
+    const size_t at = codes.size(), n = (size_t)(e - b);
+    codes.resize(at + n);
+    u8* out = codes.data() + at;
+    u8 all = 0xFF;
+    for (size_t i = 0; i < n; ++i) {
+        const u8 v = kDna.t[(unsigned char)b[i]];
+        out[i] = v;
+        all &= (u8)(v ? 0xFF : 0x00);
+    }
+    if (!all)
+        for (size_t i = 0; i < n; ++i) map_dna_char(b[i]);  // throws at the first offender, as the reference panics
+}
 
 // One logical FASTA line: str::lines() then trim() (parser.rs:53-57).  Returns false at end of input.
 struct LineReader {
@@ -621,7 +635,7 @@ static std::unique_ptr<Tree> parse_reference_fasta_str(const char* text, size_t 
             }
             have_current = true;
         } else {
-            for (const char* p = b; p < e; ++p) codes.push_back(map_dna_char(*p));
+            append_codes(codes, b, e);
         }
     }
     if (first) throw Error("Not a valid FASTA file");  // the reference indexes lines[0] and panics on an all-blank file
@@ -661,7 +675,7 @@ static std::unique_ptr<Queries> parse_query_fasta_str(const char* text, size_t l
             }
             cur_label.assign(b + 1, e);
         } else {
-            for (const char* p = b; p < e; ++p) q->codes.push_back(map_dna_char(*p));
+            append_codes(q->codes, b, e);
         }
     }
     if (first) throw Error("Not a valid FASTA file");
