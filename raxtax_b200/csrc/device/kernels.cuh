@@ -1563,6 +1563,7 @@ __global__ void __launch_bounds__(kWalkWarps * 32)
                     overflow = true;
                     break;
                 }
+                __syncwarp();  // every lane has read this frame (top of the iteration) before lane 0 rewrites it
                 if (lane == 0) {
                     ws.st_next[depth] = nxt;
                     ws.st_any[depth] |= 1;  // bit 0: a significant child exists; bit 1: something was pushed below (set on the way up)
@@ -1925,7 +1926,7 @@ __global__ void __launch_bounds__(kBfsThreads)  // (a 6-CTA/SM bound, 40 registe
                        u32 entry_cap) {
     constexpr int kBfsWarps = kBfsThreads / 32;
     extern __shared__ __align__(16) unsigned char bsm_raw[];
-    __shared__ u32 s_log_n, s_n_res, s_n_fb, s_n_next, s_retry;
+    __shared__ u32 s_log_n, s_n_res, s_n_fb, s_n_next, s_retry, s_retry_cls;  // s_retry_cls: raised while sorting a frontier (see the level loop)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int ql = blockIdx.x;
     if (ql >= q_count) return;
@@ -1957,11 +1958,14 @@ __global__ void __launch_bounds__(kBfsThreads)  // (a 6-CTA/SM bound, 40 registe
             s_n_res = 0;
             s_n_fb = 0;
             s_retry = 0;
+            s_retry_cls = 0;
         }
         __syncthreads();
         // ---- significant nodes, level by level (lineage.rs:126-149).  Two barriers per level: the child offsets of the current
         // frontier (warp 0) are computed in the same phase in which the previous frontier is sorted into result lines and
-        // fallback heads (its ent_any flags are final since the barrier behind the evaluation that set them) -------------
+        // fallback heads (its ent_any flags are final since the barrier behind the evaluation that set them).  Each phase has its
+        // own overflow flag -- s_retry_cls is written before the first barrier and read behind it, s_retry between the barriers and
+        // read behind the second -- so that no warp can test a flag another warp is raising in the same phase -------------
         u32 lvl_begin = 0, lvl_end = 1, prev_begin = 0, prev_end = 0;
         while (true) {
             const bool have = lvl_begin < lvl_end;
@@ -1987,14 +1991,14 @@ __global__ void __launch_bounds__(kBfsThreads)  // (a 6-CTA/SM bound, 40 registe
                 pr = __shfl_sync(kFullMask, pr, 0);
                 pf = __shfl_sync(kFullMask, pf, 0);
                 if (pr + __popc(mr) > R || pf + __popc(mf) > F) {
-                    if (lane == 0) s_retry = 1;
+                    if (lane == 0) s_retry_cls = 1;
                 } else {
                     if (is_res) w.res_ent[pr + __popc(mr & lt_mask)] = (u16)e;
                     if (is_fb) w.list_a[pf + __popc(mf & lt_mask)] = (u16)e;
                 }
             }
             __syncthreads();
-            if (!have || s_retry) break;
+            if (!have || s_retry_cls) break;
             const u32 total = w.fr_off[nf];
             for (u32 base = (u32)warp * 64; base < total; base += kBfsWarps * 64) {  // two chunks of 32 children in flight per warp
                 u32 kk[2], ee[2];
@@ -2052,6 +2056,8 @@ __global__ void __launch_bounds__(kBfsThreads)  // (a 6-CTA/SM bound, 40 registe
                 break;
             }
         }
+        __syncthreads();
+        if (tid == 0 && s_retry_cls) s_retry = 1;
         __syncthreads();
         // ---- fallback chains (lineage.rs:151-177): all heads advance together, one level per round -------------------
         u16* cur = w.list_a;
