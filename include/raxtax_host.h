@@ -90,6 +90,16 @@ int rxh_raxtax_multi(rtx_ctx* const* ctxs, size_t n_ctx, const rxh_queries* quer
                      int raw_confidence, size_t chunk_size, rxh_sender sender, void* sender_user, int tsv, rxh_logger logger,
                      void* logger_user, int* warnings);
 
+/* Reference-sharded mode (BASELINE config 5): merge of the result lines the ranks emitted for one batch -- per query the ranks' lines
+ * in the order of lineage.rs:93, then the one-exact-match override of raxtax.rs:73-84 (which needs the best line of all ranks).
+ * Inputs are the rtx_results arrays of every rank (confidence rows have max_levels entries); the caller sizes the outputs for the
+ * sum of the ranks' line counts.  Returns 0, or -1 (rxh_last_error) e.g. for a query without any line (raxtax.rs:72). */
+int rxh_merge_shard_results(size_t n_ranks, size_t n_queries, uint32_t max_levels, const uint32_t* const* result_begin,
+                            const uint32_t* const* first_ref, const uint8_t* const* n_levels, const double* const* confidence,
+                            const double* const* local_signal, const uint32_t* exact_offsets, const uint32_t* exact_ids,
+                            const uint8_t* ref_levels, int skip_exact_matches, int raw_confidence, uint32_t* out_begin, uint32_t* out_first,
+                            uint8_t* out_nlev, double* out_conf, double* out_local, uint64_t out_capacity, uint64_t* n_out);
+
 /* exact-match lookup for a whole batch (the host half of raxtax.rs:42): fills exact_offsets[n+1]; returns the
  * total number of ids; writes at most cap ids */
 uint64_t rxh_exact_batch(const rxh_tree* t, size_t n, const uint64_t* seq_offsets, const uint8_t* seq_codes, uint32_t* exact_offsets,

@@ -37,7 +37,7 @@ DEVICE_SYMBOLS = [
 HOST_SYMBOLS = [
     "rxh_last_error", "rxh_tree_from_fasta", "rxh_tree_from_bin", "rxh_tree_save_bin", "rxh_queries_skip", "rxh_tree_new", "rxh_tree_free", "rxh_tree_num_tips", "rxh_tree_lineage",
     "rxh_tree_csr", "rxh_tree_build_kmer_map", "rxh_tree_has_kmer_map", "rxh_tree_exact", "rxh_tree_index_desc", "rxh_tree_upload", "rxh_tree_upload_sharded", "rxh_queries_from_fasta", "rxh_queries_new",
-    "rxh_queries_free", "rxh_queries_len", "rxh_queries_label", "rxh_queries_arrays", "rxh_raxtax", "rxh_raxtax_multi", "rxh_exact_batch",
+    "rxh_queries_free", "rxh_queries_len", "rxh_queries_label", "rxh_queries_arrays", "rxh_raxtax", "rxh_raxtax_multi", "rxh_merge_shard_results", "rxh_exact_batch",
 ]
 
 
@@ -175,6 +175,9 @@ def host_lib():
                              LOGGER, C.c_void_p, C.POINTER(C.c_int)]
     L.rxh_raxtax_multi.argtypes = [C.POINTER(C.c_void_p), C.c_size_t, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_size_t, SENDER, C.c_void_p,
                                    C.c_int, LOGGER, C.c_void_p, C.POINTER(C.c_int)]
+    L.rxh_merge_shard_results.argtypes = [C.c_size_t, C.c_size_t, C.c_uint32, C.POINTER(u32p), C.POINTER(u32p), C.POINTER(u8p), C.POINTER(f64p),
+                                          C.POINTER(f64p), u32p, u32p, u8p, C.c_int, C.c_int, u32p, u32p, u8p, f64p, f64p, C.c_uint64,
+                                          C.POINTER(C.c_uint64)]
     L.rxh_exact_batch.restype = C.c_uint64
     L.rxh_exact_batch.argtypes = [C.c_void_p, C.c_size_t, u64p, u8p, u32p, u32p, C.c_uint64]
     _host = L

@@ -11,6 +11,7 @@
 #include <algorithm>
 #include <atomic>
 #include <chrono>
+#include <cmath>
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
@@ -1191,6 +1192,71 @@ RXH_API int rxh_raxtax_multi(rtx_ctx* const* ctxs, size_t n_ctx, const rxh_queri
         return -1;
     }
     return 0;
+}
+
+// Reference-sharded mode: the result lines the ranks emitted for one batch, merged per query.  Lines are ordered like
+// lineage.rs:93 (confidence vectors descending lexicographically, on an equal prefix the longer vector first; ties in depth-first
+// push order == ascending first reference), then the one-exact-match override of raxtax.rs:73-84 is applied -- it needs the best
+// line of ALL ranks, which is why the ranks leave it to the merge.
+RXH_API int rxh_merge_shard_results(size_t n_ranks, size_t n_queries, uint32_t max_levels, const uint32_t* const* result_begin,
+                                    const uint32_t* const* first_ref, const uint8_t* const* n_levels, const double* const* confidence,
+                                    const double* const* local_signal, const uint32_t* exact_offsets, const uint32_t* exact_ids,
+                                    const uint8_t* ref_levels, int skip_exact_matches, int raw_confidence, uint32_t* out_begin,
+                                    uint32_t* out_first, uint8_t* out_nlev, double* out_conf, double* out_local, uint64_t out_capacity,
+                                    uint64_t* n_out) {
+    try {
+        struct Line {
+            u32 rank, idx, first;
+            u8 n;
+        };
+        const u32 ML = max_levels;
+        std::vector<Line> lines;
+        u64 w = 0;
+        out_begin[0] = 0;
+        for (size_t q = 0; q < n_queries; ++q) {
+            lines.clear();
+            for (size_t r = 0; r < n_ranks; ++r)
+                for (u32 i = result_begin[r][q]; i < result_begin[r][q + 1]; ++i) lines.push_back(Line{(u32)r, i, first_ref[r][i], n_levels[r][i]});
+            if (lines.empty()) throw Error("query " + std::to_string(q) + ": empty evaluation result (raxtax.rs:72)");
+            auto hundredths = [&](const Line& l, u32 lev) { return (long)std::lround(confidence[l.rank][(size_t)l.idx * ML + lev] * 100.0); };
+            std::sort(lines.begin(), lines.end(), [&](const Line& a, const Line& b) {
+                for (u32 lev = 0; lev < ML; ++lev) {
+                    const bool ha = lev < a.n, hb = lev < b.n;
+                    if (!ha && !hb) break;
+                    if (ha != hb) return ha;  // equal prefix: the longer vector first
+                    const long ka = hundredths(a, lev), kb = hundredths(b, lev);
+                    if (ka != kb) return ka > kb;
+                }
+                return a.first < b.first;
+            });
+            const u32 ne = exact_offsets ? exact_offsets[q + 1] - exact_offsets[q] : 0u;
+            if (!raw_confidence && !skip_exact_matches && ne == 1) {
+                if (w + 1 > out_capacity) throw Error("rxh_merge_shard_results: output capacity too small");
+                const u32 id = exact_ids[exact_offsets[q]];
+                const u32 n = ref_levels[id];
+                out_first[w] = id;
+                out_nlev[w] = (u8)n;
+                for (u32 lev = 0; lev < ML; ++lev) out_conf[w * ML + lev] = lev < n ? 1.0 : 0.0;
+                out_local[w] = local_signal[lines[0].rank][lines[0].idx];  // signals of the best computed line
+                ++w;
+            } else {
+                if (w + lines.size() > out_capacity) throw Error("rxh_merge_shard_results: output capacity too small");
+                for (const Line& l : lines) {
+                    out_first[w] = l.first;
+                    out_nlev[w] = l.n;
+                    memcpy(out_conf + w * ML, confidence[l.rank] + (size_t)l.idx * ML, (size_t)ML * 8);
+                    out_local[w] = local_signal[l.rank][l.idx];
+                    ++w;
+                }
+            }
+            out_begin[q + 1] = (u32)w;
+        }
+        if (n_out) *n_out = w;
+        return 0;
+    } catch (const std::exception& e) {
+        g_err = e.what();
+        return -1;
+    }
 }
 
 RXH_API int rxh_raxtax(rtx_ctx* ctx, const rxh_queries* queries, const rxh_tree* tree_h, int skip_exact_matches, int raw_confidence,

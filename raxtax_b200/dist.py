@@ -125,7 +125,42 @@ class TorchShardGroup:
 
 # ---------------------------------------------------------------------------------------------------------------
 def merge_shard_results(outs, exact_off, exact_ids, ref_levels, skip_exact=False, raw_conf=False) -> capi.ClassifyOutput:
-    """Merge the per-rank result lines of a reference-sharded batch.
+    """Merge the per-rank result lines of a reference-sharded batch (rxh_merge_shard_results in the C++ host library; the pure-Python
+    statement of the same rule below, `merge_shard_results_py`, is what the tests compare it with)."""
+    import ctypes as C
+
+    L = capi.host_lib()
+    nq = len(outs[0].n_kmers)
+    ML = outs[0].confidence.shape[1] if outs[0].confidence.ndim == 2 else 1
+    keep = []  # contiguous arrays must outlive the call
+
+    def col(get, dtype, ctype):
+        arrs = [np.ascontiguousarray(get(o), dtype) for o in outs]
+        arrs = [a if a.size else np.zeros(1, dtype) for a in arrs]
+        keep.append(arrs)
+        return (C.POINTER(ctype) * len(outs))(*[a.ctypes.data_as(C.POINTER(ctype)) for a in arrs])
+
+    total = int(sum(int(o.result_begin[-1]) for o in outs)) + nq
+    begin, first, nlev = np.zeros(nq + 1, np.uint32), np.zeros(max(total, 1), np.uint32), np.zeros(max(total, 1), np.uint8)
+    conf, local = np.zeros((max(total, 1), ML), np.float64), np.zeros(max(total, 1), np.float64)
+    eo = np.ascontiguousarray(exact_off, np.uint32) if exact_off is not None else None
+    ei = np.ascontiguousarray(exact_ids, np.uint32) if exact_ids is not None and len(exact_ids) else np.zeros(1, np.uint32)
+    rl = np.ascontiguousarray(ref_levels, np.uint8)
+    n_out = C.c_uint64(0)
+    p = lambda a, t: a.ctypes.data_as(C.POINTER(t)) if a is not None else None
+    rc = L.rxh_merge_shard_results(len(outs), nq, ML, col(lambda o: o.result_begin, np.uint32, C.c_uint32), col(lambda o: o.first_ref, np.uint32, C.c_uint32),
+                                   col(lambda o: o.n_levels, np.uint8, C.c_uint8), col(lambda o: o.confidence, np.float64, C.c_double),
+                                   col(lambda o: o.local_signal, np.float64, C.c_double), p(eo, C.c_uint32), p(ei, C.c_uint32), p(rl, C.c_uint8),
+                                   int(skip_exact), int(raw_conf), p(begin, C.c_uint32), p(first, C.c_uint32), p(nlev, C.c_uint8),
+                                   p(conf, C.c_double), p(local, C.c_double), total, C.byref(n_out))
+    if rc != 0:
+        raise capi.RtxError(capi.RTX_ERR_ASSERT, L.rxh_last_error().decode())
+    n = int(n_out.value)
+    return capi.ClassifyOutput(outs[0].n_kmers.copy(), begin, outs[0].global_signal.copy(), first[:n], nlev[:n], conf[:n], local[:n])
+
+
+def merge_shard_results_py(outs, exact_off, exact_ids, ref_levels, skip_exact=False, raw_conf=False) -> capi.ClassifyOutput:
+    """The same merge, stated in Python (test reference).
 
     Per query: concatenate the ranks' lines, order them like lineage.rs:93 (confidence vectors descending
     lexicographically, a longer vector first on an equal prefix; ties in depth-first order == ascending first

@@ -119,3 +119,32 @@ def test_sharded_merge_over_gloo_world_size_2():
     for p in procs:
         p.join(timeout=60)
     assert sorted(got) == [(0, "ok"), (1, "ok")], got
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_native_merge_equals_python_statement(seed):
+    """rxh_merge_shard_results against the pure-Python statement of the same rule on random per-rank outputs: ties between confidence
+    vectors, vectors of different length with an equal prefix, queries with and without a single exact match."""
+    rng = np.random.default_rng(seed)
+    n_ranks, nq, ML, n_refs = int(rng.integers(1, 6)), int(rng.integers(1, 40)), int(rng.integers(1, 7)), 500
+    ref_levels = rng.integers(1, ML + 1, n_refs).astype(np.uint8)
+    outs = []
+    for _ in range(n_ranks):
+        begin, first, nlev, conf, local = [0], [], [], [], []
+        for q in range(nq):
+            for _ in range(int(rng.integers(0, 5)) + (1 if len(outs) == 0 else 0)):  # rank 0 always contributes a line: no empty query
+                n = int(rng.integers(1, ML + 1))
+                c = np.zeros(ML)
+                c[:n] = np.sort(rng.integers(1, 5, n))[::-1] / 100.0 + (0.9 if rng.random() < 0.3 else 0.0)  # few distinct values: many ties
+                first.append(int(rng.integers(0, n_refs))); nlev.append(n); conf.append(c); local.append(float(rng.random()))
+            begin.append(len(first))
+        outs.append(capi.ClassifyOutput(np.zeros(nq, np.uint16), np.asarray(begin, np.uint32), rng.random(nq), np.asarray(first, np.uint32),
+                                        np.asarray(nlev, np.uint8), np.asarray(conf, np.float64).reshape(len(first), ML), np.asarray(local, np.float64)))
+    ne = rng.integers(0, 3, nq)
+    eo = np.concatenate([[0], np.cumsum(ne)]).astype(np.uint32)
+    eids = rng.integers(0, n_refs, int(eo[-1])).astype(np.uint32)
+    for skip, raw in [(False, False), (True, False), (False, True)]:
+        a = rdist.merge_shard_results(outs, eo, eids, ref_levels, skip_exact=skip, raw_conf=raw)
+        b = rdist.merge_shard_results_py(outs, eo, eids, ref_levels, skip_exact=skip, raw_conf=raw)
+        assert np.array_equal(a.result_begin, b.result_begin) and np.array_equal(a.first_ref, b.first_ref)
+        assert np.array_equal(a.n_levels, b.n_levels) and np.array_equal(a.confidence, b.confidence) and np.array_equal(a.local_signal, b.local_signal)
