@@ -200,6 +200,13 @@ int rtx_shard_hist_buffer(rtx_ctx* ctx, void** dev_ptr, uint64_t* n_elems);
 int rtx_shard_phase2(rtx_ctx* ctx);
 int rtx_shard_records_buffers(rtx_ctx* ctx, void** send_ptr, uint64_t* send_bytes, void** recv_ptr, uint64_t* recv_bytes);
 int rtx_shard_phase3(rtx_ctx* ctx);
+/* In-process stand-ins for the two collectives when ONE process drives all the shards (several GPUs of a box, or several contexts
+ * on one GPU): ctxs[r] is shard r of n.  ..._hist_local: element-wise sum of the histogram buffers, written back to every context
+ * (between phase 1 and 2).  ..._records_local: the straddler records of all shards, in shard order, into every context's receive
+ * buffer (between phase 2 and 3).  Staged through pinned host memory (~2.6 KB of histogram per query and shard).  With one process
+ * per GPU use ncclAllReduce / ncclAllGather on the buffers above instead (raxtax_b200/dist.py). */
+int rtx_shard_exchange_hist_local(rtx_ctx* const* ctxs, uint32_t n);
+int rtx_shard_exchange_records_local(rtx_ctx* const* ctxs, uint32_t n);
 
 /* ---- measurement ---------------------------------------------------------------------------------------- */
 typedef struct {

@@ -90,6 +90,14 @@ int rxh_raxtax_multi(rtx_ctx* const* ctxs, size_t n_ctx, const rxh_queries* quer
                      int raw_confidence, size_t chunk_size, rxh_sender sender, void* sender_user, int tsv, rxh_logger logger,
                      void* logger_user, int* warnings);
 
+/* raxtax::raxtax over a reference-sharded index (BASELINE config 5: databases too large to replicate) with all shards driven by this
+ * process: ctxs[r] holds shard r of n_ctx (rxh_tree_upload_sharded, any mix of devices).  Lines are sent in query order from the
+ * calling thread.  chunk_size = queries per sharded batch (0 = up to 8192; halved automatically until a batch fits one sub-batch
+ * of every shard). */
+int rxh_raxtax_sharded(rtx_ctx* const* ctxs, size_t n_ctx, const rxh_queries* queries, const rxh_tree* tree, int skip_exact_matches,
+                       int raw_confidence, size_t chunk_size, rxh_sender sender, void* sender_user, int tsv, rxh_logger logger,
+                       void* logger_user, int* warnings);
+
 /* Reference-sharded mode (BASELINE config 5): merge of the result lines the ranks emitted for one batch -- per query the ranks' lines
  * in the order of lineage.rs:93, then the one-exact-match override of raxtax.rs:73-84 (which needs the best line of all ranks).
  * Inputs are the rtx_results arrays of every rank (confidence rows have max_levels entries); the caller sizes the outputs for the

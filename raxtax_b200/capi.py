@@ -30,14 +30,14 @@ DEVICE_SYMBOLS = [
     "rtx_abi_version", "rtx_ctx_create", "rtx_ctx_destroy", "rtx_last_error", "rtx_ctx_set_option", "rtx_ctx_stream",
     "rtx_ctx_synchronize", "rtx_host_alloc", "rtx_host_free", "rtx_index_upload", "rtx_index_n_refs", "rtx_index_shard_refs", "rtx_index_max_levels", "rtx_batch_sub_batch",
     "rtx_index_device_bytes", "rtx_classify_batch", "rtx_batch_upload", "rtx_batch_run", "rtx_batch_download",
-    "rtx_shard_phase1", "rtx_shard_hist_buffer", "rtx_shard_phase2", "rtx_shard_records_buffers", "rtx_shard_phase3",
+    "rtx_shard_phase1", "rtx_shard_hist_buffer", "rtx_shard_phase2", "rtx_shard_records_buffers", "rtx_shard_phase3", "rtx_shard_exchange_hist_local", "rtx_shard_exchange_records_local",
     "rtx_profile_reset", "rtx_profile_get",
 ]
 # every symbol include/raxtax_host.h declares
 HOST_SYMBOLS = [
     "rxh_last_error", "rxh_tree_from_fasta", "rxh_tree_from_bin", "rxh_tree_save_bin", "rxh_queries_skip", "rxh_tree_new", "rxh_tree_free", "rxh_tree_num_tips", "rxh_tree_lineage",
     "rxh_tree_csr", "rxh_tree_build_kmer_map", "rxh_tree_has_kmer_map", "rxh_tree_exact", "rxh_tree_index_desc", "rxh_tree_upload", "rxh_tree_upload_sharded", "rxh_queries_from_fasta", "rxh_queries_new",
-    "rxh_queries_free", "rxh_queries_len", "rxh_queries_label", "rxh_queries_arrays", "rxh_raxtax", "rxh_raxtax_multi", "rxh_merge_shard_results", "rxh_exact_batch",
+    "rxh_queries_free", "rxh_queries_len", "rxh_queries_label", "rxh_queries_arrays", "rxh_raxtax", "rxh_raxtax_multi", "rxh_raxtax_sharded", "rxh_merge_shard_results", "rxh_exact_batch",
 ]
 
 
@@ -119,6 +119,8 @@ def device_lib():
         getattr(L, f).argtypes = [C.c_void_p]
     L.rtx_shard_hist_buffer.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]
     L.rtx_shard_records_buffers.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64), C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]
+    L.rtx_shard_exchange_hist_local.argtypes = [C.POINTER(C.c_void_p), C.c_uint32]
+    L.rtx_shard_exchange_records_local.argtypes = [C.POINTER(C.c_void_p), C.c_uint32]
     L.rtx_profile_get.argtypes = [C.c_void_p, C.POINTER(Profile)]
     _dev = L
     return L
@@ -175,6 +177,8 @@ def host_lib():
                              LOGGER, C.c_void_p, C.POINTER(C.c_int)]
     L.rxh_raxtax_multi.argtypes = [C.POINTER(C.c_void_p), C.c_size_t, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_size_t, SENDER, C.c_void_p,
                                    C.c_int, LOGGER, C.c_void_p, C.POINTER(C.c_int)]
+    L.rxh_raxtax_sharded.argtypes = [C.POINTER(C.c_void_p), C.c_size_t, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_size_t, SENDER, C.c_void_p,
+                                     C.c_int, LOGGER, C.c_void_p, C.POINTER(C.c_int)]
     L.rxh_merge_shard_results.argtypes = [C.c_size_t, C.c_size_t, C.c_uint32, C.POINTER(u32p), C.POINTER(u32p), C.POINTER(u8p), C.POINTER(f64p),
                                           C.POINTER(f64p), u32p, u32p, u8p, C.c_int, C.c_int, u32p, u32p, u8p, f64p, f64p, C.c_uint64,
                                           C.POINTER(C.c_uint64)]
@@ -623,7 +627,7 @@ class Queries:
         return o, c
 
 
-def raxtax(ctx: Context, queries: Queries, tree: Tree, skip_exact_matches=False, raw_confidence=False, chunk_size=0, tsv=False):
+def raxtax(ctx: Context, queries: Queries, tree: Tree, skip_exact_matches=False, raw_confidence=False, chunk_size=0, tsv=False, sharded=False):
     """raxtax::raxtax (raxtax.rs:14-97).  Returns (results, log_lines, warnings) where results is the list of
     (query_label, primary_results, tsv_results_or_None) tuples the reference sends to its writer thread."""
     sent, logs = [], []
@@ -636,7 +640,11 @@ def raxtax(ctx: Context, queries: Queries, tree: Tree, skip_exact_matches=False,
         logs.append((level, msg.decode()))
 
     warn = C.c_int(0)
-    if isinstance(ctx, (list, tuple)):  # several GPUs (or several contexts on one): rxh_raxtax_multi, results in completion order
+    if sharded:  # ctx = the shards' contexts in shard order (upload_tree_sharded): rxh_raxtax_sharded, results in query order
+        arr = (C.c_void_p * len(ctx))(*[c._h for c in ctx])
+        rc = host_lib().rxh_raxtax_sharded(arr, len(ctx), queries._h, tree._h, int(skip_exact_matches), int(raw_confidence), int(chunk_size),
+                                           SENDER(_send), None, int(tsv), LOGGER(_log), None, C.byref(warn))
+    elif isinstance(ctx, (list, tuple)):  # several GPUs (or several contexts on one): rxh_raxtax_multi, results in completion order
         arr = (C.c_void_p * len(ctx))(*[c._h for c in ctx])
         rc = host_lib().rxh_raxtax_multi(arr, len(ctx), queries._h, tree._h, int(skip_exact_matches), int(raw_confidence), int(chunk_size),
                                          SENDER(_send), None, int(tsv), LOGGER(_log), None, C.byref(warn))

@@ -1443,6 +1443,79 @@ RTX_API int rtx_shard_phase3(rtx_ctx* ctx) {
     return RTX_OK;
 }
 
+// ---- in-process exchange between the shards of one process (stand-ins for ncclAllReduce / ncclAllGather) ---------------------
+static int exchange_precheck(rtx_ctx* const* ctxs, uint32_t n, int want_phase, const char* who) {
+    if (!ctxs || n == 0 || !ctxs[0]) return RTX_ERR_INVALID;
+    rtx_ctx* ctx = ctxs[0];
+    for (uint32_t r = 0; r < n; ++r) {
+        rtx_ctx* c = ctxs[r];
+        if (!c || !c->has_batch || c->shard_phase != want_phase) return set_err(ctx, RTX_ERR_INVALID, std::string(who) + ": every context must have finished phase " + std::to_string(want_phase));
+        if (c->sv.n_shards != n || c->sv.rank != r) return set_err(ctx, RTX_ERR_INVALID, std::string(who) + ": contexts must be passed in shard order, one per shard");
+        if (c->bv.n_queries != ctx->bv.n_queries || c->bv.hstride != ctx->bv.hstride || c->sv.n_strad != ctx->sv.n_strad)
+            return set_err(ctx, RTX_ERR_INVALID, std::string(who) + ": the contexts hold different batches");
+    }
+    return RTX_OK;
+}
+
+RTX_API int rtx_shard_exchange_hist_local(rtx_ctx* const* ctxs, uint32_t n) {
+    int rc = exchange_precheck(ctxs, n, 1, "rtx_shard_exchange_hist_local");
+    if (rc) return rc;
+    rtx_ctx* ctx = ctxs[0];
+    const size_t n_el = (size_t)ctx->bv.n_queries * ctx->bv.hstride;
+    if (n_el == 0 || n == 1) return RTX_OK;
+    CU(cudaSetDevice(ctx->device));
+    CU(arena_reserve(ctx, (size_t)n * n_el * 4 + 64 * (size_t)n));
+    std::vector<u32*> part(n);
+    for (uint32_t r = 0; r < n; ++r) {
+        part[r] = (u32*)arena_take(ctx, n_el * 4);
+        CU(cudaSetDevice(ctxs[r]->device));
+        CU(cudaMemcpyAsync(part[r], ctxs[r]->d_hist.p, n_el * 4, cudaMemcpyDeviceToHost, ctxs[r]->stream));
+    }
+    for (uint32_t r = 0; r < n; ++r) {
+        CU(cudaSetDevice(ctxs[r]->device));
+        CU(cudaStreamSynchronize(ctxs[r]->stream));
+    }
+    for (uint32_t r = 1; r < n; ++r)
+        for (size_t i = 0; i < n_el; ++i) part[0][i] += part[r][i];
+    for (uint32_t r = 0; r < n; ++r) {
+        CU(cudaSetDevice(ctxs[r]->device));
+        CU(cudaMemcpyAsync(ctxs[r]->d_hist.p, part[0], n_el * 4, cudaMemcpyHostToDevice, ctxs[r]->stream));
+    }
+    for (uint32_t r = 0; r < n; ++r) {  // the arena is reused by the next exchange / download
+        CU(cudaSetDevice(ctxs[r]->device));
+        CU(cudaStreamSynchronize(ctxs[r]->stream));
+    }
+    return RTX_OK;
+}
+
+RTX_API int rtx_shard_exchange_records_local(rtx_ctx* const* ctxs, uint32_t n) {
+    int rc = exchange_precheck(ctxs, n, 2, "rtx_shard_exchange_records_local");
+    if (rc) return rc;
+    rtx_ctx* ctx = ctxs[0];
+    const size_t b = (size_t)ctx->bv.n_queries * ctx->sv.n_strad * sizeof(ShardRec);
+    if (b == 0) return RTX_OK;
+    CU(cudaSetDevice(ctx->device));
+    CU(arena_reserve(ctx, (size_t)n * b + 64));
+    unsigned char* all = (unsigned char*)arena_take(ctx, (size_t)n * b);
+    for (uint32_t r = 0; r < n; ++r) {
+        CU(cudaSetDevice(ctxs[r]->device));
+        CU(cudaMemcpyAsync(all + (size_t)r * b, ctxs[r]->d_send.p, b, cudaMemcpyDeviceToHost, ctxs[r]->stream));
+    }
+    for (uint32_t r = 0; r < n; ++r) {
+        CU(cudaSetDevice(ctxs[r]->device));
+        CU(cudaStreamSynchronize(ctxs[r]->stream));
+    }
+    for (uint32_t r = 0; r < n; ++r) {
+        CU(cudaSetDevice(ctxs[r]->device));
+        CU(cudaMemcpyAsync(ctxs[r]->d_recv.p, all, (size_t)n * b, cudaMemcpyHostToDevice, ctxs[r]->stream));
+    }
+    for (uint32_t r = 0; r < n; ++r) {
+        CU(cudaSetDevice(ctxs[r]->device));
+        CU(cudaStreamSynchronize(ctxs[r]->stream));
+    }
+    return RTX_OK;
+}
+
 // ---- measurement -------------------------------------------------------------------------------------------
 RTX_API int rtx_profile_reset(rtx_ctx* ctx) {
     if (!ctx) return RTX_ERR_INVALID;

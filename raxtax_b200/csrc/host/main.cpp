@@ -2,7 +2,7 @@
 //
 // Mirrors the reference's CLI surface, output files and restart behaviour (src/io.rs:112-300, src/main.rs:14-173):
 //   raxtax -d <db.fasta[.gz] | db.bin> -i <queries.fasta[.gz]> [-o PREFIX] [--skip-exact-matches] [--raw-confidence] [--tsv]
-//          [--redo] [--only-db] [--skip-db] [-c] [-t N] [--pin] [-v|-q] [--gpu N] [--gpus N] [--batch N]
+//          [--redo] [--only-db] [--skip-db] [-c] [-t N] [--pin] [-v|-q] [--gpu N] [--gpus N [--shard-references]] [--batch N]
 // writes <PREFIX>/raxtax.out, raxtax.log, raxtax.ckp, raxtax.json and (with --tsv) raxtax.tsv in the reference's formats
 // (lineage.rs:17-48), and <PREFIX>/<database stem>.bin, the bincode database of tree.rs:146-164, unless --skip-db.
 // A database path that deserialises as such a .bin is loaded instead of parsed (parser.rs:37-44).  An interrupted run is
@@ -36,7 +36,7 @@ enum { EX_OK_ = 0, EX_USAGE_ = 64, EX_NOINPUT_ = 66, EX_CANTCREAT_ = 73, EX_IOER
 struct Args {
     std::string database_path, query_file, prefix = "raxtax";
     bool skip_exact_matches = false, tsv = false, only_db = false, skip_db = false, clean = false, raw_confidence = false, redo = false,
-         pin = false;
+         pin = false, shard_refs = false;
     int threads = 0, verbosity = 3 /* Info */, gpu = 0, gpus = 1;
     size_t batch = 0;
 };
@@ -60,6 +60,8 @@ void usage() {
             "      --gpu <ORDINAL>                  First CUDA device to use [default: 0]\n"
             "      --gpus <N>                       Number of GPUs (ORDINAL .. ORDINAL+N-1): queries are partitioned, the index is\n"
             "                                       replicated [default: 1]\n"
+            "      --shard-references               With --gpus N: every GPU holds 1/N of the references (databases too large to\n"
+            "                                       replicate) instead of the whole index\n"
             "      --batch <N>                      Queries per device batch [default: all]\n"
             "  -v / -q                              More / less output\n");
 }
@@ -287,6 +289,7 @@ int main(int argc, char** argv) {
         else if (s == "--pin") a.pin = true;
         else if (s == "--gpu") a.gpu = atoi(val("--gpu"));
         else if (s == "--gpus") a.gpus = std::max(1, atoi(val("--gpus")));
+        else if (s == "--shard-references") a.shard_refs = true;
         else if (s == "--batch") a.batch = (size_t)atoll(val("--batch"));
         else if (s == "-v") a.verbosity = 4;
         else if (s == "-q") a.verbosity = 2;
@@ -452,22 +455,38 @@ int main(int argc, char** argv) {
         rxh_queries_skip(queries, blob.data(), blob.size());
     }
 
-    // one context per GPU, the index replicated on each (BASELINE config 3: query-partitioned, no collective)
+    // one context per GPU: the index replicated on each (BASELINE config 3: query-partitioned, no collective), or with
+    // --shard-references a contiguous 1/N of the lineage-sorted references on each (config 5)
+    const bool sharded = a.shard_refs && a.gpus > 1;
+    std::vector<uint64_t> cuts;
+    if (sharded) {
+        const uint64_t n = rxh_tree_num_tips(tree);
+        cuts.push_back(0);
+        for (int r = 1; r < a.gpus; ++r) cuts.push_back(std::max<uint64_t>(n * (uint64_t)r / (uint64_t)a.gpus / 32 * 32, cuts.back() + 1));
+        cuts.push_back(n);
+        if (n < (uint64_t)a.gpus) {
+            fprintf(stderr, "\x1b[31m[ERROR]\x1b[0m --shard-references: fewer references than GPUs\n");
+            return EX_USAGE_;
+        }
+    }
     std::vector<rtx_ctx*> ctxs((size_t)a.gpus, nullptr);
     for (int g = 0; g < a.gpus; ++g) {
         if (rtx_ctx_create(a.gpu + g, &ctxs[(size_t)g]) != 0) {
             fprintf(stderr, "\x1b[31m[ERROR]\x1b[0m %s\n", rtx_last_error(nullptr));
             return EX_TEMPFAIL_;
         }
-        if (rxh_tree_upload(tree, ctxs[(size_t)g], 0, 0) != 0) {
+        if ((sharded ? rxh_tree_upload_sharded(tree, ctxs[(size_t)g], (uint32_t)a.gpus, (uint32_t)g, cuts.data())
+                     : rxh_tree_upload(tree, ctxs[(size_t)g], 0, 0)) != 0) {
             fprintf(stderr, "\x1b[31m[ERROR]\x1b[0m index upload: %s\n", rxh_last_error());
             return EX_TEMPFAIL_;
         }
     }
     int warnings = 0;
     auto t0 = std::chrono::steady_clock::now();
-    int rc = rxh_raxtax_multi(ctxs.data(), ctxs.size(), queries, tree, a.skip_exact_matches, a.raw_confidence, a.batch, send_cb, &w, a.tsv,
-                              log_cb, &w, &warnings);
+    int rc = sharded ? rxh_raxtax_sharded(ctxs.data(), ctxs.size(), queries, tree, a.skip_exact_matches, a.raw_confidence, a.batch, send_cb, &w,
+                                          a.tsv, log_cb, &w, &warnings)
+                     : rxh_raxtax_multi(ctxs.data(), ctxs.size(), queries, tree, a.skip_exact_matches, a.raw_confidence, a.batch, send_cb, &w,
+                                        a.tsv, log_cb, &w, &warnings);
     double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     if (rc != 0) {
         fprintf(stderr, "\x1b[31m[ERROR]\x1b[0m Error while sending results to IO-thread!: %s\n", rxh_last_error());

@@ -1259,6 +1259,173 @@ RXH_API int rxh_merge_shard_results(size_t n_ranks, size_t n_queries, uint32_t m
     }
 }
 
+// raxtax::raxtax over a reference-sharded index held by ONE process: ctxs[r] is shard r (rxh_tree_upload_sharded).  Per chunk: batch
+// to every shard, phase 1, histogram exchange, phase 2, record exchange, phase 3, per-rank downloads, merge, then the same formatting
+// and sending as rxh_raxtax, in query order.  (With one process per GPU the same phases run with NCCL in between: raxtax_b200/dist.py.)
+RXH_API int rxh_raxtax_sharded(rtx_ctx* const* ctxs, size_t n_ctx, const rxh_queries* queries, const rxh_tree* tree_h, int skip_exact_matches,
+                               int raw_confidence, size_t chunk_size, rxh_sender sender, void* sender_user, int tsv, rxh_logger logger,
+                               void* logger_user, int* warnings) {
+    try {
+        if (warnings) *warnings = 0;
+        if (!ctxs || n_ctx == 0 || !queries || !tree_h) throw Error("rxh_raxtax_sharded: no context");
+        const Tree& tree = *tree_h->t;
+        const Queries& qs = *queries->q;
+        const size_t nq = qs.size();
+        const u32 ML = rtx_index_max_levels(ctxs[0]);
+        for (size_t r = 0; r < n_ctx; ++r)
+            if (rtx_index_n_refs(ctxs[r]) != tree.num_tips) throw Error("a context's index does not belong to this tree");
+        if (chunk_size == 0) chunk_size = std::min<size_t>(std::max<size_t>(nq, 1), 8192);
+        struct RankOut {
+            std::vector<u32> begin, first;
+            std::vector<u16> n_kmers;
+            std::vector<u8> nlev;
+            std::vector<double> conf, local, global;
+        };
+        std::vector<RankOut> ro(n_ctx);
+        std::vector<u32> exact_off, exact_ids, ex, m_begin, m_first;
+        std::vector<u8> m_nlev;
+        std::vector<double> m_conf, m_local;
+        std::string primary, tsv_out, msg;
+        bool warned = false;
+        auto dev = [&](int rc, rtx_ctx* c, const char* what) {
+            if (rc) throw Error(std::string(what) + ": " + rtx_last_error(c));
+        };
+        for (size_t c0 = 0; c0 < nq;) {
+            const size_t cn = std::min(chunk_size, nq - c0);
+            exact_off.assign(cn + 1, 0);
+            exact_ids.clear();
+            for (size_t i = 0; i < cn; ++i) {  // tree.sequences.get(query_sequence) (raxtax.rs:42)
+                const size_t q = c0 + i;
+                tree.exact(qs.codes.data() + qs.off[q], (size_t)(qs.off[q + 1] - qs.off[q]), &ex);
+                exact_ids.insert(exact_ids.end(), ex.begin(), ex.end());
+                exact_off[i + 1] = (u32)exact_ids.size();
+            }
+            rtx_batch batch{};
+            batch.n_queries = (u32)cn;
+            batch.seq_offsets = qs.off.data() + c0;
+            batch.seq_codes = qs.codes.data();
+            batch.exact_offsets = exact_off.data();
+            batch.exact_ids = exact_ids.empty() ? nullptr : exact_ids.data();
+            batch.flags = (skip_exact_matches ? RTX_SKIP_EXACT_MATCHES : 0u) | (raw_confidence ? RTX_RAW_CONFIDENCE : 0u);
+            bool too_big = false;
+            for (size_t r = 0; r < n_ctx && !too_big; ++r) {
+                dev(rtx_batch_upload(ctxs[r], &batch), ctxs[r], "rtx_batch_upload");
+                too_big = rtx_batch_sub_batch(ctxs[r]) < cn;  // sharded batches must fit one sub-batch of every shard
+            }
+            if (too_big) {
+                if (chunk_size <= 1) throw Error("rxh_raxtax_sharded: not even one query fits the shards' scratch memory");
+                chunk_size = (chunk_size + 1) / 2;
+                continue;
+            }
+            for (size_t r = 0; r < n_ctx; ++r) dev(rtx_shard_phase1(ctxs[r]), ctxs[r], "rtx_shard_phase1");
+            dev(rtx_shard_exchange_hist_local(ctxs, (uint32_t)n_ctx), ctxs[0], "rtx_shard_exchange_hist_local");
+            for (size_t r = 0; r < n_ctx; ++r) dev(rtx_shard_phase2(ctxs[r]), ctxs[r], "rtx_shard_phase2");
+            dev(rtx_shard_exchange_records_local(ctxs, (uint32_t)n_ctx), ctxs[0], "rtx_shard_exchange_records_local");
+            for (size_t r = 0; r < n_ctx; ++r) dev(rtx_shard_phase3(ctxs[r]), ctxs[r], "rtx_shard_phase3");
+            size_t total = 0;
+            for (size_t r = 0; r < n_ctx; ++r) {
+                RankOut& o = ro[r];
+                o.n_kmers.resize(cn);
+                o.begin.resize(cn + 1);
+                o.global.resize(cn);
+                size_t cap = std::max<size_t>(o.first.size(), cn * 8 + 64);
+                while (true) {
+                    o.first.resize(cap);
+                    o.nlev.resize(cap);
+                    o.conf.resize(cap * ML);
+                    o.local.resize(cap);
+                    rtx_results res{};
+                    res.n_kmers = o.n_kmers.data();
+                    res.result_begin = o.begin.data();
+                    res.global_signal = o.global.data();
+                    res.result_capacity = cap;
+                    res.first_ref = o.first.data();
+                    res.n_levels = o.nlev.data();
+                    res.confidence = o.conf.data();
+                    res.local_signal = o.local.data();
+                    const int rc = rtx_batch_download(ctxs[r], &res);
+                    if (rc == RTX_ERR_INVALID && res.n_results > cap) {
+                        cap = res.n_results + 64;
+                        continue;
+                    }
+                    dev(rc, ctxs[r], "rtx_batch_download");
+                    total += res.n_results;
+                    break;
+                }
+            }
+            // merge the shards' lines per query (order of lineage.rs:93, then the override of raxtax.rs:73-84)
+            std::vector<const u32*> pb(n_ctx), pf(n_ctx);
+            std::vector<const u8*> pn(n_ctx);
+            std::vector<const double*> pc(n_ctx), pl(n_ctx);
+            for (size_t r = 0; r < n_ctx; ++r) {
+                pb[r] = ro[r].begin.data();
+                pf[r] = ro[r].first.data();
+                pn[r] = ro[r].nlev.data();
+                pc[r] = ro[r].conf.data();
+                pl[r] = ro[r].local.data();
+            }
+            const size_t mcap = total + cn;
+            m_begin.resize(cn + 1);
+            m_first.resize(mcap);
+            m_nlev.resize(mcap);
+            m_conf.resize(mcap * ML);
+            m_local.resize(mcap);
+            uint64_t n_out = 0;
+            if (rxh_merge_shard_results(n_ctx, cn, ML, pb.data(), pf.data(), pn.data(), pc.data(), pl.data(), exact_off.data(),
+                                        exact_ids.empty() ? exact_off.data() : exact_ids.data(), tree.ref_levels.data(), skip_exact_matches,
+                                        raw_confidence, m_begin.data(), m_first.data(), m_nlev.data(), m_conf.data(), m_local.data(), mcap, &n_out) != 0)
+                throw Error(g_err);
+            for (size_t i = 0; i < cn; ++i) {
+                const size_t q = c0 + i;
+                if (!skip_exact_matches) {  // the log lines of raxtax.rs:43-53
+                    bool all_equal = true;
+                    std::string first_parent;
+                    for (u32 j = exact_off[i]; j < exact_off[i + 1]; ++j) {
+                        const std::string& l = tree.lineages[exact_ids[j]];
+                        if (logger) {
+                            msg = "Exact sequence match for query " + qs.labels[q] + ": " + l;
+                            logger(logger_user, 3, msg.c_str());
+                        }
+                        const size_t p = l.rfind(',');
+                        if (p == std::string::npos)
+                            throw Error("called `Option::unwrap()` on a `None` value: lineage without ',' (raxtax.rs:49)");
+                        if (j == exact_off[i]) first_parent.assign(l, 0, p);
+                        else if (l.compare(0, p, first_parent) != 0 || p != first_parent.size()) all_equal = false;
+                    }
+                    if (!all_equal) {
+                        if (logger) {
+                            msg = "Exact matches for " + qs.labels[q] + " differ above the leafs of the lineage tree!";
+                            logger(logger_user, 2, msg.c_str());
+                        }
+                        warned = true;
+                    }
+                }
+                primary.clear();
+                tsv_out.clear();
+                std::string seq;
+                if (tsv) seq = decompress_sequence(qs.codes.data() + qs.off[q], (size_t)(qs.off[q + 1] - qs.off[q]));
+                for (u32 r = m_begin[i]; r < m_begin[i + 1]; ++r) {
+                    ResultView rv{&tree.lineages[m_first[r]], m_conf.data() + (size_t)r * ML, m_nlev[r], m_local[r], ro[0].global[i]};
+                    if (r != m_begin[i]) primary += '\n';
+                    output_string(primary, qs.labels[q], rv);
+                    if (tsv) {
+                        if (r != m_begin[i]) tsv_out += '\n';
+                        tsv_string(tsv_out, qs.labels[q], rv, seq);
+                    }
+                }
+                if (sender && sender(sender_user, qs.labels[q].c_str(), primary.c_str(), tsv ? tsv_out.c_str() : nullptr) != 0)
+                    throw Error("sending on a disconnected channel (raxtax.rs:87)");
+            }
+            c0 += cn;
+        }
+        if (warnings) *warnings = warned ? 1 : 0;
+        return 0;
+    } catch (const std::exception& e) {
+        g_err = e.what();
+        return -1;
+    }
+}
+
 RXH_API int rxh_raxtax(rtx_ctx* ctx, const rxh_queries* queries, const rxh_tree* tree_h, int skip_exact_matches, int raw_confidence,
                        size_t chunk_size, rxh_sender sender, void* sender_user, int tsv, rxh_logger logger, void* logger_user, int* warnings) {
     rtx_ctx* one[1] = {ctx};

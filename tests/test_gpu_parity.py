@@ -801,3 +801,29 @@ def test_documented_limits(oracle, ctx):
     with pytest.raises(capi.RtxError) as ei:
         ctx.classify(*_pack(oracle, [synth.BASE_CODES[rng.integers(0, 4, 70000)]]))
     assert ei.value.code == capi.RTX_ERR_UNSUPPORTED
+
+
+@pytest.mark.parametrize("n_shards,skip", [(3, False), (2, True)])
+def test_host_driver_sharded_equals_unsharded(ctx, n_shards, skip):
+    """rxh_raxtax_sharded (all shards driven by one process: phases + the in-process histogram / record exchanges + the merge) sends the
+    lines rxh_raxtax sends for the unsharded index; contexts on the one GPU of the test box stand in for several GPUs."""
+    from raxtax_b200 import dist as rdist
+
+    ds = synth.generate("small", n_queries=150, measure=False)
+    ht = capi.Tree.new(ds.ref_lineages, ds.ref_off, ds.ref_codes)
+    qs = capi.Queries.new(ds.query_labels, ds.query_off, ds.query_codes)
+    ctx.upload_tree(ht)
+    one, logs1, warn1 = capi.raxtax(ctx, qs, ht, skip_exact_matches=skip, tsv=True)
+    cuts = rdist.shard_cuts(ht.num_tips, n_shards)
+    shards = [capi.Context(0) for _ in range(n_shards)]
+    try:
+        for r, c in enumerate(shards):
+            c.upload_tree_sharded(ht, n_shards, r, cuts)
+        many, logs2, warn2 = capi.raxtax(shards, qs, ht, skip_exact_matches=skip, chunk_size=64, tsv=True, sharded=True)
+    finally:
+        for c in shards:
+            c.close()
+    assert [x[0] for x in many] == ds.query_labels
+    same = sum(a == b for a, b in zip(one, many))
+    assert same >= len(one) - 2, [(a, b) for a, b in zip(one, many) if a != b][:2]  # ulp-level ties may fall differently per shard sum
+    assert sorted(logs1) == sorted(logs2) and warn1 == warn2
