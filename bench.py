@@ -1,14 +1,27 @@
 #!/usr/bin/env python
 """bench.py -- queries/sec of the raxtax query-classification hot path on B200 (BASELINE.json metric).
 
-  python bench.py --gpus N --steps K --warmup W                 our CUDA path (one process per GPU under torchrun)
+  python bench.py --gpus N --steps K --warmup W                   our CUDA path (one process per GPU under torchrun)
   python bench.py --impl reference --gpus N --steps K --warmup W  the reference algorithm on the host cores (CPU oracle port)
 
-A "step" is one pass of the hot path (k-mers -> hit counts -> probabilities -> lineage results) over one batch of
-synthetic queries of the workload.  Workload at every N: BASELINE config 2 (100k COI-like 650 bp references x 10k
-queries per GPU; weak scaling: the index is replicated, every rank classifies its own 10k queries, no collective).
-`value` = queries of all ranks / max-over-ranks device time with the batch resident in HBM; `e2e` = the same through
-rtx_classify_batch with pinned HOST buffers (H2D + kernels + D2H inside the timed region).
+A "step" is one pass of the hot path (k-mers -> hit counts -> probabilities -> lineage results) over the workload's queries.
+
+Workloads (--workload, BASELINE.json configs):
+  c3 (default)  1 M COI-like 650 bp references x 200 k queries IN TOTAL, index replicated, the queries split evenly over the N
+                ranks (strong scaling, no data-path collective) -- the configuration the metric's 1/2/4/8 series is quoted on
+  c2            100 k references x 10 k queries per GPU (the single-GPU config; weak scaling when N > 1)
+  c4            500 k 16S-like 1500 bp references x 100 k queries in total, --skip-exact-matches (strong scaling)
+  c5            8 M references sharded over the N ranks, every rank sees every query, NCCL histogram all-reduce + record
+                all-gather inside the device library (bounded query job, see --queries)
+
+Legs of one run, all over the same queries:
+  value            whole-job queries/s with the batch resident in HBM (rtx_batch_run, CUDA events on the context's stream)
+  e2e              the same through the drop-in driver rxh_raxtax (raxtax.rs:14-97): host query arrays in, exact-match lookup,
+                   de-duplication, H2D, kernels, D2H, formatting of every result line and the per-query hand-off to a counting
+                   sender all inside the timed region (host wall clock, barrier on both sides, max over ranks)
+  e2e_device_abi   rtx_classify_batch with page-locked host buffers (the device boundary alone: H2D + kernels + D2H)
+  roofline         the hit-count kernel, from per-launch CUDA events with the kernels serialised
+  cpu_baseline     the CPU oracle port on the host cores over a bounded sample (rank 0, N = 1 only)
 """
 from __future__ import annotations
 
@@ -28,6 +41,9 @@ sys.path.insert(0, ROOT)
 METRIC = "queries/sec (box, device-timed) at 1/2/4/8 B200; hit-count HBM GB/s vs peak"
 UNIT = "queries/s"
 
+# name -> (scaling, skip_exact_matches)
+WORKLOADS = {"c2": ("weak", False), "c3": ("strong", False), "c4": ("strong", True), "c5": ("strong", False)}
+
 
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -40,8 +56,8 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """SM clock and throttle reasons sampled DURING the timed region: NVML polled every ~2 ms from a thread (the timed region of the
-    default run is ~40 ms, too short for `nvidia-smi -lms`); falls back to an nvidia-smi loop when pynvml is missing."""
+    """SM clock and throttle reasons sampled DURING the timed regions: NVML polled every ~10 ms from a thread; falls back to an
+    nvidia-smi loop when pynvml is missing."""
     Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
     def __init__(self, gpu_index):
@@ -77,7 +93,7 @@ class ClockSampler:
                     self.samples.append((float(n.nvmlDeviceGetClockInfo(self.h, n.NVML_CLOCK_SM)), int(n.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))))
                 except Exception:
                     break
-            time.sleep(0.002)
+            time.sleep(0.01)
 
     def start(self):
         if self.nvml is not None:
@@ -105,7 +121,7 @@ class ClockSampler:
                      "sw_thermal_slowdown": getattr(n, "nvmlClocksEventReasonSwThermalSlowdown", 0x20), "sw_power_cap": getattr(n, "nvmlClocksEventReasonSwPowerCap", 0x4)}
             sm = [x[0] for x in self.samples]
             reasons = sorted(k for k, bit in names.items() if any(x[1] & bit for x in self.samples))
-            return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": self.smax, "reasons": reasons, "samples": len(sm), "source": "nvml, 2 ms poll"}
+            return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": self.smax, "reasons": reasons, "samples": len(sm), "source": "nvml, 10 ms poll"}
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.25)
@@ -132,35 +148,100 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm), "source": "nvidia-smi -lms 200"}
 
 
-def make_workload(name, world):
+# ---------------------------------------------------------------------------------------------------------------------
+def load_workload(name, n_queries, rank=0, barrier=None):
+    """The synthetic data set of a BASELINE config (raxtax_b200/synth.py, deterministic).  Generating 1 M references takes ~40 s of
+    numpy, so the arrays are cached under /tmp: the reference arm, our arm and the ranks of a multi-GPU run on one box then share
+    one generation (rank 0 writes, the others wait at the barrier and read)."""
     from raxtax_b200 import synth
 
-    cfg = synth.CONFIGS[name]
-    ds = synth.generate(name, n_queries=cfg[1] * world, measure=False)
-    return ds, cfg[1]
+    path = os.path.join(os.environ.get("RAXTAX_BENCH_CACHE", "/tmp"), f"raxtax_b200_synth_{name}_{n_queries}_v2.npz")
+
+    def from_cache():
+        z = np.load(path, allow_pickle=False)
+        return synth.Dataset(name, bytes(z["lin"]).decode().split("\n"), z["ref_off"], z["ref_codes"], bytes(z["qlab"]).decode().split("\n"),
+                             z["q_off"], z["q_codes"], meta=json.loads(bytes(z["meta"]).decode()))
+
+    ds = None
+    if os.path.exists(path):
+        try:
+            ds = from_cache()
+        except Exception:
+            ds = None
+    if ds is None and rank == 0:
+        ds = synth.generate(name, n_queries=n_queries, measure=False)
+        try:
+            tmp = path + f".{os.getpid()}.tmp.npz"
+            np.savez(tmp, lin=np.frombuffer("\n".join(ds.ref_lineages).encode(), np.uint8), ref_off=ds.ref_off, ref_codes=ds.ref_codes,
+                     qlab=np.frombuffer("\n".join(ds.query_labels).encode(), np.uint8), q_off=ds.query_off, q_codes=ds.query_codes,
+                     meta=np.frombuffer(json.dumps(ds.meta).encode(), np.uint8))
+            os.replace(tmp, path)
+        except Exception:
+            pass
+    if barrier is not None:
+        barrier()
+    if ds is None:
+        try:
+            ds = from_cache()
+        except Exception:
+            ds = synth.generate(name, n_queries=n_queries, measure=False)
+    return ds
 
 
-def cpu_reference_rate(ds, q0, n_sample, threads, full_chunk, skip=False):
-    """The reference algorithm (oracle port of raxtax.rs:14-97, --threads 0 chunking of main.rs:119-124) on host cores."""
-    from oracle import oracle as orc
+def workload_queries(name, world, override=0):
+    """(queries in the whole job, queries per rank, scaling)"""
+    from raxtax_b200 import synth
 
-    ot = orc.Tree.new(ds.ref_lineages, [ds.ref_seq(i) for i in range(ds.n_refs)])
-    off = ds.query_off[q0: q0 + n_sample + 1]
-    codes = ds.query_codes
-    chunk = n_sample if threads == 1 else full_chunk
+    scaling, _ = WORKLOADS[name]
+    base = override or synth.CONFIGS[name][1]
+    if name == "c5":
+        return base, base, "strong"  # every rank sees every query; the references are what is split
+    if scaling == "weak":
+        return base * world, base, scaling
+    per = (base + world - 1) // world
+    return base, per, scaling
 
-    def run():
-        o = ot.classify(off - off[0], codes[int(off[0]): int(off[-1])], skip_exact=skip, threads=threads, chunk_size=chunk)
+
+class CpuReference:
+    """The reference algorithm (oracle port of raxtax.rs:14-97 with the chunked thread fan-out of main.rs:119-124) on host cores,
+    over a bounded sample of the workload's queries."""
+
+    def __init__(self, ds, skip):
+        from oracle import oracle as orc
+
+        import ctypes as C
+
+        self.orc = orc
+        self.ds = ds
+        self.skip = skip
+        blob = "\n".join(ds.ref_lineages).encode()
+        ro = np.ascontiguousarray(ds.ref_off, np.uint64)
+        rc = np.ascontiguousarray(ds.ref_codes, np.uint8)
+        t0 = time.time()
+        self.tree = orc.Tree(orc.lib().orc_tree_new(ds.n_refs, blob, len(blob), ro.ctypes.data_as(C.POINTER(C.c_uint64)), rc.ctypes.data_as(C.POINTER(C.c_uint8))))
+        self.tree_s = time.time() - t0
+
+    def run(self, n, threads, chunk):
+        ds = self.ds
+        off = ds.query_off[: n + 1]
+        o = self.tree.classify(off - off[0], ds.query_codes[int(off[0]): int(off[-1])], skip_exact=self.skip, threads=threads, chunk_size=chunk)
         return o["seconds"]
 
-    return ot, run
-
-
-def cpu_sample_plan(q_total, threads, override=0):
-    """chunk size of the reference for the FULL job (main.rs:119-124) and a bounded sample that keeps every thread busy."""
-    chunk = q_total if threads == 1 else max(100, q_total // (threads * 10) + 1)
-    n = override or min(q_total, 2 * chunk * threads)
-    return n, chunk
+    def plan(self, q_total, threads, seconds_per_step, override=0):
+        """(sample size, chunk): enough queries for ~seconds_per_step of work on all threads, every thread busy; chunks as the
+        reference would cut them for the whole job (main.rs:119-124: max(100, Q / (threads * 10) + 1)) unless the sample is too small
+        for that, in which case the sample is cut evenly (per-query cost does not depend on the chunk size)."""
+        full_chunk = q_total if threads == 1 else max(100, q_total // (threads * 10) + 1)
+        if override:
+            n = min(q_total, override)
+        else:
+            probe = min(q_total, threads * 4)
+            t = self.run(probe, threads, max(1, probe // threads))
+            rate = probe / max(t, 1e-6)
+            n = int(min(q_total, max(threads * 8, rate * seconds_per_step)))
+            n = max(threads, n // threads * threads)
+        chunk = full_chunk if n >= full_chunk * threads else max(1, n // threads)
+        return n, chunk
 
 
 def main():
@@ -169,13 +250,15 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="c2")
-    ap.add_argument("--cpu-sample", type=int, default=0, help="queries in the bounded CPU sample (0 = auto)")
+    ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
+    ap.add_argument("--queries", type=int, default=0, help="queries of the whole job (0 = the config's own number; c5 default: a bounded 131072)")
+    ap.add_argument("--cpu-sample", type=int, default=0, help="queries in the bounded CPU sample (0 = sized for ~20 s / ~6 s per step)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--sub-batch", type=int, default=0, help="RTX_OPT_SUB_BATCH for the timed legs (0 = library default)")
     ap.add_argument("--pipeline", type=int, default=-1, help="RTX_OPT_PIPELINE for the timed legs (-1 = library default)")
+    ap.add_argument("--chunk", type=int, default=0, help="chunk_size of rxh_raxtax in the e2e leg (0 = the driver's default)")
     args = ap.parse_args()
-    args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(min(args.warmup, 1), 1)
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -190,25 +273,38 @@ def main():
         sys.stdout.flush()
         os.write(real_stdout, (json.dumps(line) + "\n").encode())
 
+    from raxtax_b200 import synth
+
+    name = args.workload
+    scaling, skip = WORKLOADS[name]
+    if name == "c5" and not args.queries:
+        args.queries = 131072
+    ref_len, kind = synth.CONFIGS[name][2], synth.CONFIGS[name][3]
+    kind_name = "16S-like" if kind == "16s" else "COI-like"
+
     # ------------------------------------------------------------------------------------------ reference arm
     if args.impl == "reference":
         if rank != 0:
             return 0
-        ds, q_per_gpu = make_workload(args.workload, 1)
-        n_sample, chunk = cpu_sample_plan(q_per_gpu, cores, args.cpu_sample)
-        from raxtax_b200 import synth
-
-        _, run = cpu_reference_rate(ds, 0, n_sample, cores, chunk, skip=args.workload == "c4")
+        q_total, _, _ = workload_queries(name, max(args.gpus, 1), args.queries)
+        ds = load_workload(name, q_total)
+        ref = CpuReference(ds, skip)
+        n_sample, chunk = ref.plan(q_total, cores, 6.0, args.cpu_sample)
         for _ in range(args.warmup):
-            run()
-        secs = [run() for _ in range(args.steps)]
+            ref.run(n_sample, cores, chunk)
+        secs = [ref.run(n_sample, cores, chunk) for _ in range(args.steps)]
         total = float(sum(secs))
         v = n_sample * args.steps / total
         line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-                "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u16/f64",
-                "data": "synthetic", "config": {"workload": f"{args.workload}: {ds.n_refs} refs x {synth.CONFIGS[args.workload][2]} bp, bounded sample of {n_sample} queries per step"},
+                "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "u16/f64",
+                "data": "synthetic",
+                "config": {"workload": f"{name}: {ds.n_refs} {kind_name} refs x {ref_len} bp (6-rank lineages) x {q_total} queries"
+                                       + (", --skip-exact-matches" if skip else "") + f"; CPU arm: bounded sample of {n_sample} queries per step",
+                           "oracle_tree_build_s": round(ref.tree_s, 1)},
                 "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                                 "sample": f"{n_sample} queries of the {args.workload} workload per step, {args.steps} steps, all {cores} host threads"},
+                                 "sample": f"first {n_sample} queries of the {name} workload per step (chunks of {chunk}), {args.steps} steps, all {cores} host threads; "
+                                           "C++ port of raxtax.rs / prob.rs / lineage.rs with flat count-indexed histogram tables (O(1) per reference like the "
+                                           "reference's ahash maps); the Rust reference itself cannot be built in this image (no cargo / rustc)"},
                 "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
         emit(line)
         return 0
@@ -241,12 +337,18 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
         return float(t.item())
 
-    ds, q_per_gpu = make_workload(args.workload, world)
-    from raxtax_b200 import synth
+    if name == "c5":
+        from raxtax_b200 import bench_sharded
 
-    ref_len, kind = synth.CONFIGS[args.workload][2], synth.CONFIGS[args.workload][3]
-    kind_name = "16S-like" if kind == "16s" else "COI-like"
-    skip = args.workload == "c4"  # BASELINE config 4 is the mislabel mode (--skip-exact-matches)
+        line = bench_sharded.run(args, rank, local_rank, world, barrier, max_over_ranks, load_workload, ClockSampler, measured_peaks, METRIC, UNIT)
+        if rank == 0:
+            emit(line)
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    q_total, q_per_rank, scaling = workload_queries(name, world, args.queries)
+    ds = load_workload(name, q_total, rank, barrier)
     t0 = time.time()
     tree = capi.Tree.new(ds.ref_lineages, ds.ref_off, ds.ref_codes)
     t_tree = time.time() - t0
@@ -254,11 +356,13 @@ def main():
     t0 = time.time()
     ctx.upload_tree(tree)
     t_upload = time.time() - t0
-    q0 = rank * q_per_gpu
-    off = (ds.query_off[q0: q0 + q_per_gpu + 1] - ds.query_off[q0]).astype(np.uint64)
-    codes = ds.query_codes[int(ds.query_off[q0]): int(ds.query_off[q0 + q_per_gpu])]
+    q0 = min(rank * q_per_rank, q_total)
+    q1 = min(q0 + q_per_rank, q_total)
+    nq = q1 - q0
+    off = (ds.query_off[q0: q1 + 1] - ds.query_off[q0]).astype(np.uint64)
+    codes = ds.query_codes[int(ds.query_off[q0]): int(ds.query_off[q1])]
     eo, eids = tree.exact_batch(off, codes)
-    # pinned host buffers for the end-to-end leg
+    # pinned host buffers for the device-ABI leg
     pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()
     off_p, codes_p, eo_p, eids_p = pin(off), pin(codes), pin(eo), pin(eids if len(eids) else np.zeros(1, np.uint32))
 
@@ -273,7 +377,6 @@ def main():
     for _ in range(args.warmup):
         ctx.batch_run()
     ctx.synchronize()
-    ctx.set_option(capi.RTX_OPT_PROFILE, 1)
     ctx.profile_reset()
     sampler = ClockSampler(local_rank)
     barrier()
@@ -291,97 +394,159 @@ def main():
     res = ctx.batch_download()
     prof_main = ctx.profile()
     n_results = len(res.first_ref)
-    value = q_per_gpu * world * args.steps / (dev_ms / 1e3)
+    value = q_total * args.steps / (dev_ms / 1e3)
+    sub_batch = ctx.sub_batch
 
-    # ---- per-kernel leg: the same batch with the sub-batch pipeline off, so that every kernel runs alone on the GPU and its
-    # CUDA-event duration is its own (in the pipelined run above hit counting shares the SMs with the other stream's kernels)
+    # ---- per-kernel leg: the same batch with every kernel timed by its own CUDA event pair on the launching stream (the
+    # sub-batch pipeline off, so that every kernel runs alone on the GPU and its duration is its own)
+    reps_k = max(1, min(args.steps, 3))
     ctx.set_option(capi.RTX_OPT_PIPELINE, 0)
     ctx.set_option(capi.RTX_OPT_SUB_BATCH, 0)
+    ctx.set_option(capi.RTX_OPT_PROFILE, 1)
     ctx.batch_upload(off_p, codes_p, eo_p, eids_p, skip_exact=skip)
-    for _ in range(2):
-        ctx.batch_run()
+    ctx.batch_run()
     ctx.profile_reset()
     ser0, ser1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ser0.record(stream)
-    for _ in range(args.steps):
+    for _ in range(reps_k):
         ctx.batch_run()
     ser1.record(stream)
     ctx.synchronize()
-    serial_ms = ser0.elapsed_time(ser1) / args.steps
+    serial_ms = ser0.elapsed_time(ser1) / reps_k
     ctx.batch_download()
     prof = ctx.profile()
+    hit_kernel = ctx.hitcount_kernel_name()
     ctx.set_option(capi.RTX_OPT_PROFILE, 0)
     ctx.set_option(capi.RTX_OPT_PIPELINE, args.pipeline if args.pipeline >= 0 else 0)
     ctx.set_option(capi.RTX_OPT_SUB_BATCH, args.sub_batch)
 
-    # ---- end-to-end leg (host buffers, H2D + kernels + D2H per step) ---------------------------------------------
-    # inputs and result arrays page-locked (rtx_host_alloc), reused from step to step as a long-running caller would
-    res_buf = ctx.pinned_results(q_per_gpu, max(q_per_gpu * 8 + 64, n_results + n_results // 4 + 64))
+    # ---- end-to-end leg: the drop-in driver (rxh_raxtax) over host query arrays, result strings into a counting sender ------
+    queries = capi.Queries.new(ds.query_labels[q0:q1], off, codes)
+    cnt = None
     for _ in range(2):
-        ctx.classify(off_p, codes_p, eo_p, eids_p, skip_exact=skip, out=res_buf)
+        cnt = capi.raxtax_counted(ctx, queries, tree, skip_exact_matches=skip, chunk_size=args.chunk)
+    assert cnt["queries"] == nq, (cnt, nq)
+    assert cnt["lines"] == n_results, f"the driver sent {cnt['lines']} result lines, the device-resident leg produced {n_results}"
     ctx.profile_reset()
     barrier()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        out = ctx.classify(off_p, codes_p, eo_p, eids_p, skip_exact=skip, out=res_buf)
-    e2e_s = max_over_ranks(time.perf_counter() - t0)
+        c2 = capi.raxtax_counted(ctx, queries, tree, skip_exact_matches=skip, chunk_size=args.chunk)
+    e2e_local = time.perf_counter() - t0
+    e2e_s = max_over_ranks(e2e_local)
     barrier()
-    clocks = sampler.stop()  # polled from the start of the device-resident leg to the end of the end-to-end leg (all three timed legs)
+    assert c2["checksum"] == cnt["checksum"] and c2["lines"] == cnt["lines"], "the driver's output changed between steps"
     prof_e2e = ctx.profile()
-    e2e_value = q_per_gpu * world * args.steps / e2e_s
+    e2e_value = q_total * args.steps / e2e_s
+
+    # ---- device-ABI leg (rtx_classify_batch, page-locked input and result buffers reused from step to step) -----------------
+    reps_a = max(1, min(args.steps, 3))
+    res_buf = ctx.pinned_results(nq, max(nq * 8 + 64, n_results + n_results // 4 + 64))
+    ctx.classify(off_p, codes_p, eo_p, eids_p, skip_exact=skip, out=res_buf)
+    ctx.profile_reset()
+    barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(reps_a):
+        out = ctx.classify(off_p, codes_p, eo_p, eids_p, skip_exact=skip, out=res_buf)
+    abi_s = max_over_ranks(time.perf_counter() - t0)
+    barrier()
+    clocks = sampler.stop()  # polled from the start of the device-resident leg to the end of the last timed leg
+    prof_abi = ctx.profile()
     assert len(out.first_ref) == n_results
 
     # ---- roofline of the dominant kernel (hit count) ----------------------------------------------------------
     peak, peak_src = measured_peaks()
     hc = prof["hitcount"]
-    hc_ms = hc["total_ms"] / max(hc["launches"], 1)
-    bytes_per_launch = prof["bitrow_bytes"] / max(hc["launches"], 1)
-    csr_bytes_per_launch = prof["csr_equiv_bytes"] / max(hc["launches"], 1)
-    achieved = bytes_per_launch / (hc_ms * 1e-3) / 1e9 if hc_ms > 0 else 0.0
-    traffic = None
+    n_launch = max(hc["launches"], 1)
+    hc_ms = hc["total_ms"] / n_launch
+    hc_s = hc_ms * 1e-3
+    bitrow_bytes = prof["bitrow_bytes"] / n_launch      # SM-side: every selected row slice once per query + the count vectors
+    csr_bytes = prof["csr_equiv_bytes"] / n_launch      # what the reference's CSR walk would move (SURVEY 8d primary figure)
+    q_per_launch = nq * reps_k / n_launch
+    # compulsory HBM traffic of one launch: the bit matrix once (L2 blocking keeps a tile group's slice on chip while all queries of
+    # the launch pass over it) + the u16 count vector of every query, written once
+    compulsory = ctx.index_bitrow_bytes + q_per_launch * ctx.shard_refs * 2
+    sm_mhz = clocks.get("sm_mhz") or 1965.0
+    n_sms = torch.cuda.get_device_properties(local_rank).multi_processor_count
+    alu_peak = n_sms * 4 * 0.5 * sm_mhz * 1e6  # warp instructions/s the alu pipe (LOP3, IADD3, SHF, PRMT ...) can issue: 0.5 per clock and SMSP
+    tj = {}
     tpath = os.path.join(ROOT, "profiles", "hitcount_traffic.json")
     if os.path.exists(tpath):
         try:
-            tj = json.load(open(tpath))
-            traffic = tj.get("dram_bytes_per_launch") if str(tj.get("workload", "")).startswith(args.workload + ",") else None  # measured on that workload only
+            tj = json.load(open(tpath)).get(name, {})
         except Exception:
-            traffic = None
-    kernel_ms = {k: prof[k]["total_ms"] / args.steps for k in ("kmers", "hitcount", "fixup", "prob", "prefix", "walk")}
-    roofline = {"bound": "hbm", "kernel": "hitcount_bitrows_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": bytes_per_launch,
-                "launch_ms": hc_ms, "timed": "kernels serialized (RTX_OPT_PIPELINE=0), CUDA events around each launch on the launching stream",
-                "serial_ms_per_step": serial_ms, "csr_equivalent": {"bytes_per_launch": csr_bytes_per_launch,
-                                                       "achieved": csr_bytes_per_launch / (hc_ms * 1e-3) / 1e9 if hc_ms > 0 else 0.0,
-                                                       "note": "4*hits+2*N per query: what the reference's CSR walk would move (SURVEY 8d primary figure)"},
-                "kernel_ms_per_step": kernel_ms}
-    if traffic and hc_ms > 0:  # what actually crossed the HBM interface (ncu), next to the algorithmic figure above
-        roofline["dram"] = {"bytes_per_launch": traffic, "gbs": traffic / (hc_ms * 1e-3) / 1e9, "frac_of_peak": traffic / (hc_ms * 1e-3) / 1e9 / peak,
-                            "note": "L2 blocking keeps the bit matrix on chip: the kernel is bound by the SMs' L1 data pipe (80 % of peak, ncu), not by HBM"}
+            tj = {}
+    # ncu figures of one launch of THIS workload (profiles/hitcount_traffic.json, taken with tools/ncu_hitcount.sh), scaled to the
+    # live launch by its row-slice count: instructions and DRAM bytes per row slice are properties of the kernel + data
+    scale = (bitrow_bytes / tj["bitrow_bytes_per_launch"]) if tj.get("bitrow_bytes_per_launch") else None
+    traffic = tj.get("dram_bytes_per_launch") * scale if scale and tj.get("dram_bytes_per_launch") else None
+    alu_inst = tj.get("alu_inst_per_launch") * scale if scale and tj.get("alu_inst_per_launch") else None
+    kernel_ms = {k: prof[k]["total_ms"] / reps_k for k in ("kmers", "hitcount", "fixup", "prob", "prefix", "walk")}
+    roofline = {
+        "kernel": hit_kernel,
+        "bound": "sm (alu-pipe issue: LOP3 carry-save adders; L1 data pipe next) -- NOT hbm: the bit matrix is L2-blocked, see `hbm` and `dram`",
+        "achieved": (alu_inst / hc_s / 1e9) if alu_inst and hc_s > 0 else None, "peak": alu_peak / 1e9, "unit": "G warp-inst/s (alu pipe)",
+        "frac": (alu_inst / hc_s / alu_peak) if alu_inst and hc_s > 0 else None,
+        "traffic": traffic,
+        "launch_ms": hc_ms, "launches_per_step": n_launch / reps_k, "queries_per_launch": q_per_launch,
+        "timed": "kernels serialised, one CUDA event pair per launch on the launching stream (RTX_OPT_PROFILE)",
+        "alu": {"inst_per_launch": alu_inst, "peak_inst_per_s": alu_peak, "sm_mhz": sm_mhz, "n_sms": n_sms,
+                "source": tj.get("source") if alu_inst else "no ncu record for this workload in profiles/hitcount_traffic.json"},
+        "hbm": {"bound": "hbm", "algorithmic_bytes_per_launch": compulsory, "achieved": compulsory / hc_s / 1e9 if hc_s > 0 else None, "peak": peak,
+                "unit": "GB/s", "frac": compulsory / hc_s / 1e9 / peak if hc_s > 0 else None, "peak_source": peak_src,
+                "note": "compulsory traffic: bit matrix once per launch + 2*N bytes of counts per query"},
+        "dram": ({"bytes_per_launch": traffic, "gbs": traffic / hc_s / 1e9, "frac_of_peak": traffic / hc_s / 1e9 / peak,
+                  "source": tj.get("source")} if traffic and hc_s > 0 else None),
+        "sm_side_bytes": {"bitrow_format_bytes_per_launch": bitrow_bytes, "gbs": bitrow_bytes / hc_s / 1e9 if hc_s > 0 else None,
+                          "x_hbm_peak": bitrow_bytes / hc_s / 1e9 / peak if hc_s > 0 else None,
+                          "note": "K_q*row_words*4 + 2*n_pad per query: row slices entering the SMs (served by L2/L1), not an HBM figure"},
+        "csr_equivalent": {"bytes_per_launch": csr_bytes, "gbs": csr_bytes / hc_s / 1e9 if hc_s > 0 else None,
+                           "note": "4*hits+2*N per query: what the reference's CSR walk would move (SURVEY 8d primary figure)"},
+        "serial_ms_per_step": serial_ms, "kernel_ms_per_step": kernel_ms,
+        "kernel_share_of_step": {k: v / serial_ms for k, v in kernel_ms.items()} if serial_ms > 0 else None,
+    }
 
     launches = sum(prof_main[k]["launches"] for k in capi.KERNEL_NAMES)
+    part = "queries split evenly over the ranks" if scaling == "strong" else f"{q_per_rank} queries per GPU"
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32 bit-planes/u16 counts/f64",
+            "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "u32 bit-planes/u16 counts/f64",
             "data": "synthetic",
-            "config": {"workload": f"{args.workload}: {ds.n_refs} {kind_name} refs x {ref_len} bp (6-rank lineages) x {q_per_gpu} queries per GPU, index replicated, queries partitioned"
+            "config": {"workload": f"{name}: {ds.n_refs} {kind_name} refs x {ref_len} bp (6-rank lineages) x {q_total} queries, index replicated, {part}"
                                    + (", --skip-exact-matches" if skip else ""),
+                       "queries_per_rank": nq,
                        "l2": "no flush needed: bit rows %.0f MB + count vectors %.0f MB per step >> 126 MB L2" % (
-                           ctx.index_bytes / 1e6, q_per_gpu * ctx.shard_refs * 2 / 1e6),
-                       "sub_batch": ctx.sub_batch, "pipeline": bool(args.pipeline > 0),
-                       "tree_build_s": round(t_tree, 2), "index_upload_s": round(t_upload, 2), "results_per_step": n_results},
+                           ctx.index_bytes / 1e6, nq * ctx.shard_refs * 2 / 1e6),
+                       "sub_batch": sub_batch, "pipeline": bool(args.pipeline > 0),
+                       "tree_build_s": round(t_tree, 2), "index_upload_s": round(t_upload, 2), "results_per_step": int(sum_over_ranks(n_results))},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": prof_e2e["h2d_bytes"] // args.steps,
-                    "d2h_bytes_per_step": prof_e2e["d2h_bytes"] // args.steps, "ms_per_step": 1e3 * e2e_s / args.steps},
+                    "d2h_bytes_per_step": prof_e2e["d2h_bytes"] // args.steps, "ms_per_step": 1e3 * e2e_s / args.steps,
+                    "through": "rxh_raxtax (drop-in for raxtax::raxtax, raxtax.rs:14-97): pageable host query arrays -> exact-match lookup, de-duplication, "
+                               "H2D, kernels, D2H, formatting of every result line, per-query hand-off to rxh_count_sender / rxh_count_logger",
+                    "result_lines_per_step": cnt["lines"], "result_bytes_per_step": cnt["primary_bytes"], "log_lines_per_step": cnt["log_lines"],
+                    "frac_of_device_resident": e2e_value / value},
+            "e2e_device_abi": {"value": q_total * reps_a / abi_s, "unit": UNIT, "steps": reps_a, "h2d_bytes_per_step": prof_abi["h2d_bytes"] // reps_a,
+                               "d2h_bytes_per_step": prof_abi["d2h_bytes"] // reps_a, "through": "rtx_classify_batch, page-locked host buffers"},
             "gpu_launches": int(launches), "roofline": roofline}
 
     # ---- CPU baseline beside it (rank 0, N = 1 only) -----------------------------------------------------------------
     if world == 1 and not args.no_cpu_baseline:
-        n_sample, chunk = cpu_sample_plan(q_per_gpu, cores, args.cpu_sample)
-        _, run = cpu_reference_rate(ds, 0, n_sample, cores, chunk, skip=skip)
-        run()
-        secs = run()
+        ref = CpuReference(ds, skip)
+        n_sample, chunk = ref.plan(q_total, cores, 20.0, args.cpu_sample)
+        secs = ref.run(n_sample, cores, chunk)
         line["cpu_baseline"] = {"value": n_sample / secs, "unit": UNIT, "cores": cores, "kind": "port",
-                                "sample": f"first {n_sample} queries of the same workload, all {cores} host threads, oracle port of raxtax.rs (Rust reference not buildable here)"}
+                                "sample": f"first {n_sample} queries of the same workload (chunks of {chunk}), all {cores} host threads, {secs:.1f} s; C++ port of "
+                                          "raxtax.rs / prob.rs / lineage.rs with flat count-indexed histogram tables (O(1) per reference like the reference's ahash "
+                                          "maps); the Rust reference cannot be built here (no cargo / rustc)"}
+        # the round-1 statement kept its histogram in an ordered std::map (O(log D) per reference): timed once beside it
+        n_small = max(cores, n_sample // 4 // cores * cores)
+        ref.orc.set_flat_hist(False)
+        s_map = ref.run(n_small, cores, max(1, n_small // cores))
+        ref.orc.set_flat_hist(True)
+        s_flat = ref.run(n_small, cores, max(1, n_small // cores))
+        line["cpu_baseline"]["std_map_variant"] = {"value": n_small / s_map, "flat_value_same_sample": n_small / s_flat, "sample": f"first {n_small} queries"}
     if rank == 0:
         emit(line)
     ctx.close()

@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define RTX_ABI_VERSION 2
+#define RTX_ABI_VERSION 3
 #define RTX_MAX_LEVELS 32 /* deepest lineage (comma-separated ranks) the device tree walk supports */
 #define RTX_MAX_RESULTS_PER_QUERY 256 /* >= the 200 lines a query can produce with the 0.01 cutoff */
 
@@ -128,6 +128,9 @@ uint64_t rtx_index_shard_refs(const rtx_ctx* ctx);   /* references held by this 
 uint32_t rtx_batch_sub_batch(const rtx_ctx* ctx);     /* queries per device sub-batch of the uploaded batch (0 = no batch) */
 uint32_t rtx_index_max_levels(const rtx_ctx* ctx);   /* stride of rtx_results.confidence */
 uint64_t rtx_index_device_bytes(const rtx_ctx* ctx); /* HBM held by the index */
+uint64_t rtx_index_bitrow_bytes(const rtx_ctx* ctx); /* of which: the bit rows (k-mer x reference matrix) */
+/* the hit-count kernel instantiation the last launch used, as ncu names it (measurement records) */
+const char* rtx_hitcount_kernel_name(const rtx_ctx* ctx);
 
 /* ---- query batch (src/raxtax.rs:14-22: `queries: &[(String, Vec<u8>)]` minus the labels) ----------------
  * seq_codes are the 4-bit one-hot codes of parser.rs:11-34.  exact_ids[exact_offsets[q]..exact_offsets[q+1])
@@ -181,6 +184,12 @@ int rtx_classify_batch(rtx_ctx* ctx, const rtx_batch* batch, rtx_results* result
 int rtx_batch_upload(rtx_ctx* ctx, const rtx_batch* batch);
 int rtx_batch_run(rtx_ctx* ctx);
 int rtx_batch_download(rtx_ctx* ctx, rtx_results* results);
+/* Two batch slots per context (0 = default, 1): rtx_batch_slot selects the slot that rtx_batch_upload / _run / _download (and
+ * rtx_classify_batch) act on.  The slots share the context's stream for kernels, but inputs and results move on a separate copy
+ * stream, so a caller can keep the device busy: upload + run slot B while slot A's kernels are still executing, then download A
+ * (waits for A only) while B runs -- see rxh_raxtax in raxtax_host.cpp.  The reference's counterpart is rayon keeping every core
+ * busy with the next chunk (raxtax.rs:35-39). */
+int rtx_batch_slot(rtx_ctx* ctx, int slot);
 
 /* ---- reference-sharded mode (north_star: NCCL all-reduce of the per-query count histograms) -------------
  * Every rank uploads the same batch.  Per batch (which must fit one sub-batch):

@@ -72,19 +72,38 @@ void rxh_queries_arrays(const rxh_queries* q, const uint64_t** seq_offsets, cons
  * sender(user, query_label, primary_results, tsv_results_or_NULL) is called once per query, in query order,
  * from the calling thread (rxh_raxtax; see rxh_raxtax_multi for several GPUs); a non-zero return aborts the run like a failed channel send (raxtax.rs:87).
  * logger(user, level, message) receives the Info / Warn lines the reference writes to raxtax.log
- * (raxtax.rs:46-52): level 2 = Warn, 3 = Info.  chunk_size = queries per device batch (0 = all at once).
+ * (raxtax.rs:46-52): level 2 = Warn, 3 = Info; it is called from the driver threads (serialised with the sender).
+ * chunk_size = queries per device batch (0 = about a quarter of the queries per GPU, between 2048 and 32768).  The driver keeps
+ * two batches in flight per GPU: while one runs, the next is prepared and uploaded and the previous one is formatted and sent,
+ * so results (and a caller's progress file) appear chunk by chunk while the run is going.  A batch that does not fit the device
+ * memory is split in halves and retried.
  * Returns 0, or -1 on error; *warnings (may be NULL) is set when exact matches disagreed above the leaf level
  * (raxtax.rs:49-52, 93-95).
  */
 typedef int (*rxh_sender)(void* user, const char* query_label, const char* primary_results, const char* tsv_results);
 typedef void (*rxh_logger)(void* user, int level, const char* message);
 
+/* A sender / logger pair that only counts (queries, result lines, bytes, an order-independent checksum of the primary strings):
+ * what a benchmark or a test hands to rxh_raxtax as the writer side of the channel.  user = rxh_counts*, zero-initialised by the caller. */
+typedef struct {
+    uint64_t queries, lines, label_bytes, primary_bytes, tsv_bytes, checksum, log_lines, log_bytes, warn_lines;
+} rxh_counts;
+int rxh_count_sender(void* user, const char* query_label, const char* primary_results, const char* tsv_results);
+void rxh_count_logger(void* user, int level, const char* message);
+/* `{:.N}` of an f64 as the result lines print confidences (N = 2) and signals (N = 5) (lineage.rs:17-30): the exact binary value
+ * rounded to nearest, ties to even.  Exposed so that tests can pin the fast path against the C library's conversion. */
+size_t rxh_format_fixed(double value, int precision, char* out, size_t cap);
+
 int rxh_raxtax(rtx_ctx* ctx, const rxh_queries* queries, const rxh_tree* tree, int skip_exact_matches, int raw_confidence,
                size_t chunk_size, rxh_sender sender, void* sender_user, int tsv, rxh_logger logger, void* logger_user, int* warnings);
 
+/* The driver keeps its page-locked result buffers per context between calls (allocating them costs milliseconds and waits for the
+ * device); this frees them.  Call it before rtx_ctx_destroy of a context that was used with rxh_raxtax if the process goes on. */
+void rxh_release_buffers(void);
+
 /* The same over several GPUs of one box (BASELINE config 3: queries partitioned, index replicated, no collective): ctxs[i] each hold
- * the whole index of `tree` (rxh_tree_upload); one host thread per context pulls chunks of chunk_size queries (0 = ~8 chunks per
- * context, >= 4096 queries) from a shared counter, as rayon's par_chunks does for the reference (raxtax.rs:35-39, main.rs:119-124).
+ * the whole index of `tree` (rxh_tree_upload); one driver thread per context pulls chunks of chunk_size queries (0 = ~4 chunks per
+ * context, 2048..32768 queries) from a shared counter, as rayon's par_chunks does for the reference (raxtax.rs:35-39, main.rs:119-124).
  * sender / logger are serialised; queries arrive in completion order (the reference's channel gives no order either). */
 int rxh_raxtax_multi(rtx_ctx* const* ctxs, size_t n_ctx, const rxh_queries* queries, const rxh_tree* tree, int skip_exact_matches,
                      int raw_confidence, size_t chunk_size, rxh_sender sender, void* sender_user, int tsv, rxh_logger logger,

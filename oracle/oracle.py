@@ -101,6 +101,12 @@ def _err():
     return OracleError(lib().orc_last_error().decode())
 
 
+def set_flat_hist(on: bool):
+    """histogram / per-count probability containers of highest_hit_prob_per_reference: flat tables (default, O(1) per reference like
+    the reference's ahash maps) or the ordered std::map of the round-1 statement.  Same results either way."""
+    lib().orc_set_flat_hist(int(bool(on)))
+
+
 def ln_binomial(n, k):
     return lib().orc_ln_binomial(n, k)
 

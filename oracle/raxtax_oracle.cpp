@@ -426,17 +426,34 @@ static std::vector<double> iterative_pmf_ln_row(uint64_t total, uint64_t trials,
 }
 
 // prob.rs:8-103  highest_hit_prob_per_reference
+// The reference keeps the histogram and the per-count probabilities in ahash::HashMaps (prob.rs:13-19,92-95): O(1) per reference,
+// iteration order unspecified.  Two equivalent containers here, both iterated in ascending count order (so that the f64 sums of
+// prob.rs:62-73 are reproducible): an ordered std::map (the original statement, O(log D) per reference) and -- g_flat_hist, the
+// default since round 2 -- a flat table indexed by the u16 count, O(1) per reference like the hash map.  Same values either way;
+// the flat table is what the CPU baseline is timed with, so that the port is not slower than the reference's data structure.
+static int g_flat_hist = 1;
+
 static std::vector<double> highest_hit_prob_per_reference(uint16_t total_num_k_mers, size_t num_trials,
                                                           const uint16_t* sizes, size_t n) {
-    std::map<uint16_t, size_t> counts;  // HashMap<u16,usize> (prob.rs:13-19); ascending iteration here
-    for (size_t i = 0; i < n; ++i) counts[sizes[i]] += 1;
+    std::vector<std::pair<uint16_t, size_t>> counts;  // HashMap<u16,usize> (prob.rs:13-19) as (count, multiplicity), ascending
+    if (g_flat_hist) {
+        std::vector<size_t> tab(65536, 0);
+        for (size_t i = 0; i < n; ++i) tab[sizes[i]] += 1;
+        for (size_t m = 0; m < 65536; ++m)
+            if (tab[m]) counts.emplace_back((uint16_t)m, tab[m]);
+    } else {
+        std::map<uint16_t, size_t> cm;
+        for (size_t i = 0; i < n; ++i) cm[sizes[i]] += 1;
+        counts.assign(cm.begin(), cm.end());
+    }
     // prob.rs:20-23; u64 arithmetic wraps in release builds when K == 0 (0 + 0 - 1)
     uint64_t nn = (uint64_t)total_num_k_mers + (uint64_t)num_trials - 1ull;
     double T = ln_binomial(nn, (uint64_t)num_trials);
-    std::map<uint16_t, double> hp;
-    bool any_full = counts.count(total_num_k_mers) > 0;  // prob.rs:24-26
+    std::vector<std::pair<uint16_t, double>> hp;  // highest_hit_probs: (count, probability), ascending
+    bool any_full = false;  // prob.rs:24-26
+    for (auto& kv : counts) any_full |= kv.first == total_num_k_mers;
     if (any_full) {
-        for (auto& kv : counts) hp[kv.first] = only_last_pmf(total_num_k_mers, num_trials, kv.first, T);
+        for (auto& kv : counts) hp.emplace_back(kv.first, only_last_pmf(total_num_k_mers, num_trials, kv.first, T));
     } else {
         std::vector<std::pair<uint16_t, std::vector<double>>> pmfs;
         for (auto& kv : counts) pmfs.emplace_back(kv.first, iterative_pmf_ln_row(total_num_k_mers, num_trials, kv.first, T));
@@ -467,11 +484,18 @@ static std::vector<double> highest_hit_prob_per_reference(uint16_t total_num_k_m
                 if (c == NEG_INF || pc == NEG_INF) s += 0.0;
                 else s += std::exp(p + pc - c);
             }
-            hp[pmfs[j].first] = s;
+            hp.emplace_back(pmfs[j].first, s);
         }
     }
     std::vector<double> out(n);
-    for (size_t i = 0; i < n; ++i) out[i] = hp[sizes[i]];  // prob.rs:92-95
+    if (g_flat_hist) {  // prob.rs:92-95
+        std::vector<double> tab(65536, 0.0);
+        for (auto& kv : hp) tab[kv.first] = kv.second;
+        for (size_t i = 0; i < n; ++i) out[i] = tab[sizes[i]];
+    } else {
+        std::map<uint16_t, double> hm(hp.begin(), hp.end());
+        for (size_t i = 0; i < n; ++i) out[i] = hm[sizes[i]];
+    }
     double probs_sum = 0.0;
     for (size_t i = 0; i < n; ++i) probs_sum += out[i];  // prob.rs:97
     if (!(probs_sum > 0.0)) throw std::runtime_error("assert probs_sum > 0.0 (prob.rs:98)");
@@ -704,6 +728,10 @@ static int fail(const std::exception& e) {
 }
 
 extern "C" {
+
+// 1 (default): flat count-indexed tables in highest_hit_prob_per_reference; 0: ordered std::map (the round-1 statement)
+void orc_set_flat_hist(int on) { g_flat_hist = on ? 1 : 0; }
+int orc_get_flat_hist(void) { return g_flat_hist; }
 
 const char* orc_last_error() { return g_err.c_str(); }
 

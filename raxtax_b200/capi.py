@@ -29,7 +29,7 @@ KERNEL_NAMES = ["kmers", "hitcount", "fixup", "prob", "index", "walk", "prefix"]
 DEVICE_SYMBOLS = [
     "rtx_abi_version", "rtx_ctx_create", "rtx_ctx_destroy", "rtx_last_error", "rtx_ctx_set_option", "rtx_ctx_stream",
     "rtx_ctx_synchronize", "rtx_host_alloc", "rtx_host_free", "rtx_index_upload", "rtx_index_n_refs", "rtx_index_shard_refs", "rtx_index_max_levels", "rtx_batch_sub_batch",
-    "rtx_index_device_bytes", "rtx_classify_batch", "rtx_batch_upload", "rtx_batch_run", "rtx_batch_download",
+    "rtx_index_device_bytes", "rtx_index_bitrow_bytes", "rtx_hitcount_kernel_name", "rtx_classify_batch", "rtx_batch_upload", "rtx_batch_run", "rtx_batch_download", "rtx_batch_slot",
     "rtx_shard_phase1", "rtx_shard_hist_buffer", "rtx_shard_phase2", "rtx_shard_records_buffers", "rtx_shard_phase3", "rtx_shard_exchange_hist_local", "rtx_shard_exchange_records_local",
     "rtx_profile_reset", "rtx_profile_get",
 ]
@@ -37,7 +37,7 @@ DEVICE_SYMBOLS = [
 HOST_SYMBOLS = [
     "rxh_last_error", "rxh_tree_from_fasta", "rxh_tree_from_bin", "rxh_tree_save_bin", "rxh_queries_skip", "rxh_tree_new", "rxh_tree_free", "rxh_tree_num_tips", "rxh_tree_lineage",
     "rxh_tree_csr", "rxh_tree_build_kmer_map", "rxh_tree_has_kmer_map", "rxh_tree_exact", "rxh_tree_index_desc", "rxh_tree_upload", "rxh_tree_upload_sharded", "rxh_queries_from_fasta", "rxh_queries_new",
-    "rxh_queries_free", "rxh_queries_len", "rxh_queries_label", "rxh_queries_arrays", "rxh_raxtax", "rxh_raxtax_multi", "rxh_raxtax_sharded", "rxh_merge_shard_results", "rxh_exact_batch",
+    "rxh_queries_free", "rxh_queries_len", "rxh_queries_label", "rxh_queries_arrays", "rxh_raxtax", "rxh_raxtax_multi", "rxh_raxtax_sharded", "rxh_merge_shard_results", "rxh_exact_batch", "rxh_count_sender", "rxh_count_logger", "rxh_format_fixed", "rxh_release_buffers",
 ]
 
 
@@ -104,7 +104,9 @@ def device_lib():
     L.rtx_host_alloc.argtypes = [C.c_size_t, C.POINTER(C.c_void_p)]
     L.rtx_host_free.argtypes = [C.c_void_p]
     L.rtx_index_upload.argtypes = [C.c_void_p, C.POINTER(IndexDesc)]
-    for f in ("rtx_index_n_refs", "rtx_index_shard_refs", "rtx_index_device_bytes"):
+    L.rtx_hitcount_kernel_name.restype = C.c_char_p
+    L.rtx_hitcount_kernel_name.argtypes = [C.c_void_p]
+    for f in ("rtx_index_n_refs", "rtx_index_shard_refs", "rtx_index_device_bytes", "rtx_index_bitrow_bytes"):
         getattr(L, f).restype = C.c_uint64
         getattr(L, f).argtypes = [C.c_void_p]
     L.rtx_index_max_levels.restype = C.c_uint32
@@ -114,6 +116,7 @@ def device_lib():
     L.rtx_classify_batch.argtypes = [C.c_void_p, C.POINTER(Batch), C.POINTER(ResultsStruct)]
     L.rtx_batch_upload.argtypes = [C.c_void_p, C.POINTER(Batch)]
     L.rtx_batch_run.argtypes = [C.c_void_p]
+    L.rtx_batch_slot.argtypes = [C.c_void_p, C.c_int]
     L.rtx_batch_download.argtypes = [C.c_void_p, C.POINTER(ResultsStruct)]
     for f in ("rtx_shard_phase1", "rtx_shard_phase2", "rtx_shard_phase3", "rtx_profile_reset"):
         getattr(L, f).argtypes = [C.c_void_p]
@@ -182,6 +185,8 @@ def host_lib():
     L.rxh_merge_shard_results.argtypes = [C.c_size_t, C.c_size_t, C.c_uint32, C.POINTER(u32p), C.POINTER(u32p), C.POINTER(u8p), C.POINTER(f64p),
                                           C.POINTER(f64p), u32p, u32p, u8p, C.c_int, C.c_int, u32p, u32p, u8p, f64p, f64p, C.c_uint64,
                                           C.POINTER(C.c_uint64)]
+    L.rxh_format_fixed.restype = C.c_size_t
+    L.rxh_format_fixed.argtypes = [C.c_double, C.c_int, C.c_char_p, C.c_size_t]
     L.rxh_exact_batch.restype = C.c_uint64
     L.rxh_exact_batch.argtypes = [C.c_void_p, C.c_size_t, u64p, u8p, u32p, u32p, C.c_uint64]
     _host = L
@@ -283,6 +288,18 @@ class Context:
     @property
     def index_bytes(self):
         return device_lib().rtx_index_device_bytes(self._h)
+
+    @property
+    def index_bitrow_bytes(self):
+        return device_lib().rtx_index_bitrow_bytes(self._h)
+
+    def hitcount_kernel_name(self) -> str:
+        return (device_lib().rtx_hitcount_kernel_name(self._h) or b"").decode()
+
+    def batch_slot(self, slot: int):
+        """rtx_batch_slot: the batch slot (0 / 1) that batch_upload / batch_run / batch_download / classify act on."""
+        self._check(device_lib().rtx_batch_slot(self._h, int(slot)))
+        self._slot = int(slot)
 
     def upload_index_arrays(self, n_refs, csr_off, csr_ids, node_lo, node_hi, node_type, child_first, child_count, ref_levels,
                             shard=(0, 0)):
@@ -434,14 +451,16 @@ class Context:
         b, keep = self._make_batch(seq_off, codes, exact_off, exact_ids, flags)
         self._check(device_lib().rtx_batch_upload(self._h, C.byref(b)))
         so = keep[0]
-        self._batch_info = (b.n_queries, int((so[1:] - so[:-1]).max()) if b.n_queries else 0)
+        if not hasattr(self, "_batch_infos"):
+            self._batch_infos = {}
+        self._batch_infos[getattr(self, "_slot", 0)] = (b.n_queries, int((so[1:] - so[:-1]).max()) if b.n_queries else 0)
 
     def batch_run(self):
         self._check(device_lib().rtx_batch_run(self._h))
 
     def batch_download(self, taps=()) -> ClassifyOutput:
         L = device_lib()
-        nq, max_len = self._batch_info
+        nq, max_len = self._batch_infos[getattr(self, "_slot", 0)]
         cap = max(nq * 8 + 64, getattr(self, "_cap_hint", 0))
         while True:
             out, r = self._alloc_results(nq, cap, max_len, taps)
@@ -466,6 +485,38 @@ class Context:
 
 
 # ---------------------------------------------------------------------------------------------------------------
+class Counts(C.Structure):
+    """rxh_counts: what rxh_count_sender / rxh_count_logger accumulate."""
+    _fields_ = [(n, C.c_uint64) for n in ("queries", "lines", "label_bytes", "primary_bytes", "tsv_bytes", "checksum", "log_lines", "log_bytes", "warn_lines")]
+
+    def as_dict(self):
+        return {n: int(getattr(self, n)) for n, _ in self._fields_}
+
+
+def format_fixed(value: float, precision: int) -> str:
+    buf = C.create_string_buffer(512)
+    n = host_lib().rxh_format_fixed(float(value), int(precision), buf, 512)
+    return buf.raw[:n].decode()
+
+
+def raxtax_counted(ctx, queries: "Queries", tree: "Tree", skip_exact_matches=False, raw_confidence=False, chunk_size=0, tsv=False) -> dict:
+    """rxh_raxtax / rxh_raxtax_multi with the library's counting sender and logger (no Python in the loop): returns the counts."""
+    L = host_lib()
+    cnt = Counts()
+    send = C.cast(L.rxh_count_sender, SENDER)
+    log = C.cast(L.rxh_count_logger, LOGGER)
+    warn = C.c_int(0)
+    ctxs = list(ctx) if isinstance(ctx, (list, tuple)) else [ctx]
+    arr = (C.c_void_p * len(ctxs))(*[c._h for c in ctxs])
+    rc = L.rxh_raxtax_multi(arr, len(ctxs), queries._h, tree._h, int(skip_exact_matches), int(raw_confidence), int(chunk_size), send,
+                            C.addressof(cnt), int(tsv), log, C.addressof(cnt), C.byref(warn))
+    if rc != 0:
+        raise _host_err()
+    d = cnt.as_dict()
+    d["warnings"] = bool(warn.value)
+    return d
+
+
 class Tree:
     """raxtax::tree::Tree (tree.rs:36-43) built by the C++ host library."""
 

@@ -16,21 +16,55 @@ struct EventPair {
     int kernel;
 };
 
-struct rtx_ctx {
+// Everything rtx_batch_upload sets up for ONE batch.  A context holds two of these ("slots", rtx_batch_slot): the active one is
+// the BatchState base of rtx_ctx, the other is parked; switching swaps them.  While the kernels of one slot run on `stream`, the
+// other slot can be uploaded (H2D on `stream_cp`) and its predecessor's results downloaded (D2H on `stream_cp` behind the slot's
+// ev_done), so the device never waits for the host between batches.  The large per-sub-batch scratch (counts, prefixes, tables)
+// is shared: only kernels on `stream` touch it and they are ordered by the stream.
+struct BatchState {
+    bool has_batch = false;
+    bool ran = false;
+    BatchView bv{};
+    u32 max_len = 0;
+    u64 total_codes = 0, total_exact = 0;
+    DevBuf d_seq_off, d_codes, d_exact_off, d_exact_ids, d_K, d_kmers, d_rows, d_nrows, d_hist;
+    u32 sub_batch = 0;
+    bool two_slots = false;  // this batch runs with the two-stream sub-batch pipeline
+    // results
+    ResultPool pool{};
+    u32 pool_levels = 0;  // max_levels the pool arrays were sized for
+    DevBuf d_pool_first, d_pool_nlev, d_pool_conf, d_pool_local, d_pool_used, d_res_off, d_res_cnt, d_global, d_status, d_hits;
+    // prob scratch layout of this batch (the buffers themselves are shared between the slots, see bind_scratch)
+    ProbScratch sc{}, sc1{};
+    int prob_slots = 0;
+    size_t prob_smem = 0, prob_big_bytes = 0, prefix_smem = 0;
+    size_t need_counts = 0, need_cbuf = 0, need_preb = 0, need_ptab = 0, need_segoff = 0, need_prob_big = 0;
+    // results in query order (result_scan_kernel / result_gather_kernel)
+    DevBuf d_ord_begin, d_ord_first, d_ord_nlev, d_ord_conf, d_ord_local;
+    int shard_phase = 0;
+    u64 runs_since_download = 0;
+    cudaEvent_t ev_up = nullptr, ev_done = nullptr;  // inputs are on the device / all kernels of the last run have finished
+    bool up_pending = false;                          // ev_up was recorded and no run has waited for it yet
+};
+
+struct rtx_ctx : BatchState {
+    BatchState parked;  // the slot that is not active
+    int cur_slot = 0;
     int device = 0;
     int n_sms = 148;
     cudaStream_t stream = nullptr;
+    cudaStream_t stream_cp = nullptr;  // host <-> device copies of the batch slots
     // sub-batch pipeline: hit counting of sub-batch i+1 (stream) overlaps probabilities / prefix sums / tree walk of sub-batch i
-    // (stream2); the per-sub-batch buffers exist twice ("slots"), events order the two streams
+    // (stream2); the per-sub-batch buffers exist twice, events order the two streams
     cudaStream_t stream2 = nullptr;
     cudaEvent_t ev_hit[2] = {nullptr, nullptr}, ev_post[2] = {nullptr, nullptr};
     bool pipeline_opt = false;  // RTX_OPT_PIPELINE (off: measured 9.95-10.2 ms pipelined against 9.89 ms serial on C2, profiles/r01x_pipeline.txt)
-    bool two_slots = false;    // this batch runs pipelined
     cudaStream_t cur_stream = nullptr;  // what the launch helpers use: stream / slot of the sub-batch being issued
     u16* cur_counts = nullptr;
     bool segmax_valid = false;  // the last hit-count launch left per-segment maxima in cur_sc's aux area
     ProbScratch* cur_sc = nullptr;
     std::string err;
+    std::string hit_kernel;  // the hit-count kernel instantiation of the last launch (rtx_hitcount_kernel_name)
     // options
     int variant = RTX_HITCOUNT_BITROWS;
     int64_t sub_batch_opt = 0;
@@ -50,32 +84,15 @@ struct rtx_ctx {
     u64 mem_free_after_index = 8ull << 30;
     DevBuf d_bitrows, d_rowmap, d_present, d_csr_off, d_csr_ids, d_node_lo, d_node_hi, d_node_type, d_child_first, d_child_count,
         d_node_blo, d_node_bhi, d_bnd_after, d_bnd_rank, d_ref_levels, d_lnfact, d_recs;
-    // batch
-    bool has_batch = false;
-    bool ran = false;
-    BatchView bv{};
-    u32 max_len = 0;
-    u64 total_codes = 0, total_exact = 0;
-    DevBuf d_seq_codes;  // reference sequences while the index is built from them
-    DevBuf d_seq_off, d_codes, d_exact_off, d_exact_ids, d_K, d_kmers, d_rows, d_nrows, d_hist;
+    DevBuf d_seq_codes, d_idx_off;  // reference sequences / their offsets while the index is built from them
+    // per-sub-batch scratch, shared by the two batch slots
     DevBuf d_counts, d_counts1;
-    u32 sub_batch = 0;
-    // results
-    ResultPool pool{};
-    u32 pool_levels = 0;  // max_levels the pool arrays were sized for
-    DevBuf d_pool_first, d_pool_nlev, d_pool_conf, d_pool_local, d_pool_used, d_res_off, d_res_cnt, d_global, d_status, d_hits;
-    // prob scratch
-    ProbScratch sc{}, sc1{};
-    int prob_slots = 0;
-    size_t prob_smem = 0, walk_smem = 0, prefix_smem = 0, bfs_smem = 0, prob_big_bytes = 0;
+    size_t walk_smem = 0, bfs_smem = 0;
     DevBuf d_prob_big;
     DevBuf d_cbuf, d_preb, d_ptab, d_segoff, d_preb1, d_ptab1, d_segoff1;
     // reference-sharded mode
     ShardView sv{};
-    int shard_phase = 0;
     DevBuf d_strad_of_node, d_strad_nodes, d_strad_parent, d_send, d_recv, d_sk, d_sany, d_sbest;
-    // results in query order (result_scan_kernel / result_gather_kernel)
-    DevBuf d_ord_begin, d_ord_first, d_ord_nlev, d_ord_conf, d_ord_local;
     // host staging: one pinned arena (device -> arena by DMA, arena -> caller memory by memcpy unless the caller's memory is pinned itself)
     unsigned char* h_arena = nullptr;
     size_t h_arena_cap = 0, h_arena_used = 0;
@@ -88,7 +105,6 @@ struct rtx_ctx {
     u16* tap_counts_host = nullptr;
     double* tap_probs_host = nullptr;
     u64 tap_prob_stride = 0;
-    u64 runs_since_download = 0;
     // profile
     rtx_profile prof{};
     std::vector<EventPair> events;
@@ -178,12 +194,12 @@ static bool host_ptr_pinned(const void* p) {
 // device -> caller memory: straight DMA when the caller's buffer is pinned, else DMA into the arena and a memcpy after the sync
 static cudaError_t d2h(rtx_ctx* c, void* dst, const void* src, size_t bytes, bool dst_pinned) {
     if (!bytes) return cudaSuccess;
-    if (dst_pinned) return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, c->stream);
+    if (dst_pinned) return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, c->stream_cp);
     const size_t off = (c->h_arena_used + 63) & ~(size_t)63;
     if (off + bytes > c->h_arena_cap) return cudaErrorMemoryAllocation;
     c->h_arena_used = off + bytes;
     c->h_pending.push_back({dst, off, bytes});
-    return cudaMemcpyAsync(c->h_arena + off, src, bytes, cudaMemcpyDeviceToHost, c->stream);
+    return cudaMemcpyAsync(c->h_arena + off, src, bytes, cudaMemcpyDeviceToHost, c->stream_cp);
 }
 static void* arena_take(rtx_ctx* c, size_t bytes) {  // arena space the library reads itself
     const size_t off = (c->h_arena_used + 63) & ~(size_t)63;
@@ -192,7 +208,7 @@ static void* arena_take(rtx_ctx* c, size_t bytes) {  // arena space the library 
     return c->h_arena + off;
 }
 static cudaError_t d2h_finish(rtx_ctx* c) {
-    cudaError_t e = cudaStreamSynchronize(c->stream);
+    cudaError_t e = cudaStreamSynchronize(c->stream_cp);
     if (e != cudaSuccess) return e;
     for (auto& pc : c->h_pending) memcpy(pc.dst, c->h_arena + pc.arena_off, pc.bytes);
     c->h_pending.clear();
@@ -235,9 +251,13 @@ RTX_API int rtx_ctx_create(int device_ordinal, rtx_ctx** out) {
         cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
         e = cudaStreamCreateWithPriority(&c->stream2, cudaStreamNonBlocking, prio_hi);
     }
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->stream_cp, cudaStreamNonBlocking);
     for (int i = 0; i < 2 && e == cudaSuccess; ++i) {
         e = cudaEventCreateWithFlags(&c->ev_hit[i], cudaEventDisableTiming);
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_post[i], cudaEventDisableTiming);
+        BatchState& b = i ? c->parked : static_cast<BatchState&>(*c);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&b.ev_up, cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&b.ev_done, cudaEventDisableTiming);
     }
     if (e != cudaSuccess) {
         std::string m = std::string("stream / event creation: ") + cudaGetErrorString(e);
@@ -276,21 +296,29 @@ RTX_API void rtx_ctx_destroy(rtx_ctx* c) {
     if (c->stream) cudaStreamSynchronize(c->stream);
     if (c->stream2) cudaStreamSynchronize(c->stream2);
     drain_events(c);
+    if (c->stream_cp) cudaStreamSynchronize(c->stream_cp);
     DevBuf* bufs[] = {&c->d_bitrows, &c->d_rowmap, &c->d_present, &c->d_csr_off, &c->d_csr_ids, &c->d_node_lo, &c->d_node_hi,
                       &c->d_node_type, &c->d_child_first, &c->d_child_count, &c->d_node_blo, &c->d_node_bhi, &c->d_bnd_after,
-                      &c->d_bnd_rank, &c->d_ref_levels, &c->d_lnfact, &c->d_seq_off, &c->d_codes, &c->d_exact_off, &c->d_exact_ids,
-                      &c->d_K, &c->d_kmers, &c->d_rows, &c->d_nrows, &c->d_hist, &c->d_counts, &c->d_counts1, &c->d_preb1, &c->d_ptab1, &c->d_segoff1, &c->d_pool_first, &c->d_pool_nlev,
-                      &c->d_pool_conf, &c->d_pool_local, &c->d_pool_used, &c->d_res_off, &c->d_res_cnt, &c->d_global, &c->d_status,
-                      &c->d_hits, &c->d_seq_codes, &c->d_cbuf, &c->d_preb, &c->d_ptab, &c->d_segoff, &c->d_recs, &c->d_strad_of_node, &c->d_strad_nodes, &c->d_strad_parent,
-                      &c->d_send, &c->d_recv, &c->d_sk, &c->d_sany, &c->d_sbest, &c->d_ord_begin, &c->d_ord_first, &c->d_ord_nlev,
-                      &c->d_ord_conf, &c->d_ord_local, &c->d_prob_big};
+                      &c->d_bnd_rank, &c->d_ref_levels, &c->d_lnfact, &c->d_counts, &c->d_counts1, &c->d_preb1, &c->d_ptab1, &c->d_segoff1,
+                      &c->d_seq_codes, &c->d_idx_off, &c->d_cbuf, &c->d_preb, &c->d_ptab, &c->d_segoff, &c->d_recs, &c->d_strad_of_node,
+                      &c->d_strad_nodes, &c->d_strad_parent, &c->d_send, &c->d_recv, &c->d_sk, &c->d_sany, &c->d_sbest, &c->d_prob_big};
     for (DevBuf* b : bufs) b->release();
+    for (int i = 0; i < 2; ++i) {
+        BatchState& s = i ? c->parked : static_cast<BatchState&>(*c);
+        DevBuf* sb[] = {&s.d_seq_off, &s.d_codes, &s.d_exact_off, &s.d_exact_ids, &s.d_K, &s.d_kmers, &s.d_rows, &s.d_nrows, &s.d_hist,
+                        &s.d_pool_first, &s.d_pool_nlev, &s.d_pool_conf, &s.d_pool_local, &s.d_pool_used, &s.d_res_off, &s.d_res_cnt,
+                        &s.d_global, &s.d_status, &s.d_hits, &s.d_ord_begin, &s.d_ord_first, &s.d_ord_nlev, &s.d_ord_conf, &s.d_ord_local};
+        for (DevBuf* b : sb) b->release();
+        if (s.ev_up) cudaEventDestroy(s.ev_up);
+        if (s.ev_done) cudaEventDestroy(s.ev_done);
+    }
     if (c->h_arena) cudaFreeHost(c->h_arena);
     for (int i = 0; i < 2; ++i) {
         if (c->ev_hit[i]) cudaEventDestroy(c->ev_hit[i]);
         if (c->ev_post[i]) cudaEventDestroy(c->ev_post[i]);
     }
     if (c->stream2) cudaStreamDestroy(c->stream2);
+    if (c->stream_cp) cudaStreamDestroy(c->stream_cp);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -352,6 +380,17 @@ RTX_API int rtx_ctx_synchronize(rtx_ctx* ctx) {
     CU(cudaSetDevice(ctx->device));
     CU(cudaStreamSynchronize(ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream2));
+    CU(cudaStreamSynchronize(ctx->stream_cp));
+    return RTX_OK;
+}
+
+RTX_API int rtx_batch_slot(rtx_ctx* ctx, int slot) {
+    if (!ctx) return RTX_ERR_INVALID;
+    REQUIRE(slot == 0 || slot == 1, "rtx_batch_slot: a context has the batch slots 0 and 1");
+    if (slot != ctx->cur_slot) {
+        std::swap(static_cast<BatchState&>(*ctx), ctx->parked);
+        ctx->cur_slot = slot;
+    }
     return RTX_OK;
 }
 
@@ -372,6 +411,8 @@ RTX_API uint64_t rtx_index_shard_refs(const rtx_ctx* c) { return c && c->has_ind
 RTX_API uint32_t rtx_index_max_levels(const rtx_ctx* c) { return c && c->has_index ? c->ix.max_levels : 0; }
 RTX_API uint64_t rtx_index_device_bytes(const rtx_ctx* c) { return c && c->has_index ? c->index_bytes : 0; }
 RTX_API uint32_t rtx_batch_sub_batch(const rtx_ctx* c) { return c && c->has_batch ? c->sub_batch : 0; }
+RTX_API uint64_t rtx_index_bitrow_bytes(const rtx_ctx* c) { return c && c->has_index ? (uint64_t)c->n_rows * c->ix.row_words * 4 : 0; }
+RTX_API const char* rtx_hitcount_kernel_name(const rtx_ctx* c) { return c ? c->hit_kernel.c_str() : ""; }
 
 // ---------------------------------------------------------------------------------------------------------
 // index upload
@@ -417,8 +458,10 @@ RTX_API int rtx_index_upload(rtx_ctx* ctx, const rtx_index_desc* d) {
     REQUIRE(d->node_lo[0] == 0 && d->node_hi[0] == N, "node 0 must be the root with range [0, n_refs)");
     CU(cudaSetDevice(ctx->device));
     CU(cudaStreamSynchronize(ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream_cp));
     ctx->has_index = false;
     ctx->has_batch = false;
+    ctx->parked.has_batch = false;
 
     // ---- tree checks, depth --------------------------------------------------------------------------
     const u32 nn = d->n_nodes;
@@ -474,7 +517,7 @@ RTX_API int rtx_index_upload(rtx_ctx* ctx, const rtx_index_desc* d) {
             max_refs = std::max(max_refs, seq_chunks[c + 1] - seq_chunks[c]);
         }
         CU(ctx->d_seq_codes.ensure(max_codes + 16));
-        CU(ctx->d_seq_off.ensure((max_refs + 1) * 8));
+        CU(ctx->d_idx_off.ensure((max_refs + 1) * 8));
         CU(ctx->d_present.ensure(2048 * 4));
         CU(cudaMemsetAsync(ctx->d_present.p, 0, 2048 * 4, ctx->stream));
     }
@@ -485,7 +528,7 @@ RTX_API int rtx_index_upload(rtx_ctx* ctx, const rtx_index_desc* d) {
         const u64 o0 = d->ref_seq_offsets[r0], bytes_c = d->ref_seq_offsets[r1] - o0;
         reb.resize(r1 - r0 + 1);
         for (u64 r = r0; r <= r1; ++r) reb[r - r0] = d->ref_seq_offsets[r] - o0;
-        cudaError_t e = cudaMemcpyAsync(ctx->d_seq_off.p, reb.data(), reb.size() * 8, cudaMemcpyHostToDevice, ctx->stream);
+        cudaError_t e = cudaMemcpyAsync(ctx->d_idx_off.p, reb.data(), reb.size() * 8, cudaMemcpyHostToDevice, ctx->stream);
         if (e == cudaSuccess && bytes_c) e = cudaMemcpyAsync(ctx->d_seq_codes.p, d->ref_seq_codes + o0, bytes_c, cudaMemcpyHostToDevice, ctx->stream);
         return e;
     };
@@ -494,7 +537,7 @@ RTX_API int rtx_index_upload(rtx_ctx* ctx, const rtx_index_desc* d) {
             CU(seq_chunk_to_device(c));
             {
                 LaunchTimer lt(ctx, RTX_K_INDEX);
-                kmer_presence_kernel<<<ctx->n_sms * 4, 256, 0, ctx->stream>>>(ctx->d_seq_off.as<u64>(), ctx->d_seq_codes.as<u8>(),
+                kmer_presence_kernel<<<ctx->n_sms * 4, 256, 0, ctx->stream>>>(ctx->d_idx_off.as<u64>(), ctx->d_seq_codes.as<u8>(),
                                                                             (u32)(seq_chunks[c + 1] - seq_chunks[c]), ctx->d_present.as<u32>());
             }
             CU(cudaGetLastError());
@@ -581,7 +624,7 @@ RTX_API int rtx_index_upload(rtx_ctx* ctx, const rtx_index_desc* d) {
             CU(seq_chunk_to_device(c));
             {
                 LaunchTimer lt(ctx, RTX_K_INDEX);
-                bitrows_from_seq_kernel<<<ctx->n_sms * 8, 256, 0, ctx->stream>>>(ctx->d_seq_off.as<u64>(), ctx->d_seq_codes.as<u8>(),
+                bitrows_from_seq_kernel<<<ctx->n_sms * 8, 256, 0, ctx->stream>>>(ctx->d_idx_off.as<u64>(), ctx->d_seq_codes.as<u8>(),
                                                                                 (u32)(seq_chunks[c + 1] - seq_chunks[c]), seq_chunks[c] - s0,
                                                                                 ctx->d_rowmap.as<u32>(), ctx->d_bitrows.as<u32>(), row_words);
             }
@@ -589,6 +632,7 @@ RTX_API int rtx_index_upload(rtx_ctx* ctx, const rtx_index_desc* d) {
             CU(cudaStreamSynchronize(ctx->stream));
         }
         ctx->d_seq_codes.release();
+        ctx->d_idx_off.release();
     } else
         CU(upload_vec(ctx->d_csr_off, d->csr_offsets, 65537, nullptr));
     if (nnz) {
@@ -721,6 +765,45 @@ static int ensure_pool(rtx_ctx* ctx, u64 cap) {
     return RTX_OK;
 }
 
+// The per-sub-batch scratch is shared by the two batch slots (only kernels on `stream` touch it, one slot's run after the other's):
+// before a slot's kernels are issued, make the buffers large enough for ITS layout and point its ProbScratch at them -- the other
+// slot's upload may have re-allocated them since.  Growing a buffer goes through cudaFree, which waits for the device.
+static int bind_scratch(rtx_ctx* ctx) {
+    CU(ctx->d_counts.ensure(std::max<size_t>(ctx->need_counts, 1)));
+    CU(ctx->d_cbuf.ensure(std::max<size_t>(ctx->need_cbuf, 1)));
+    CU(ctx->d_preb.ensure(std::max<size_t>(ctx->need_preb, 1)));
+    CU(ctx->d_ptab.ensure(std::max<size_t>(ctx->need_ptab, 1)));
+    CU(ctx->d_segoff.ensure(std::max<size_t>(ctx->need_segoff, 1)));
+    if (ctx->need_prob_big) CU(ctx->d_prob_big.ensure(ctx->need_prob_big));
+    ctx->sc.ptab = ctx->d_ptab.as<double>();
+    ctx->sc.cbuf = ctx->d_cbuf.as<double>();
+    ctx->sc.preb = ctx->d_preb.as<double>();
+    ctx->sc.segoff = ctx->d_segoff.as<double>();
+    ctx->sc.big = ctx->need_prob_big ? ctx->d_prob_big.as<unsigned char>() : nullptr;
+    ctx->sc1 = ctx->sc;
+    if (ctx->two_slots) {
+        CU(ctx->d_counts1.ensure(std::max<size_t>(ctx->need_counts, 1)));
+        CU(ctx->d_preb1.ensure(std::max<size_t>(ctx->need_preb, 1)));
+        CU(ctx->d_ptab1.ensure(std::max<size_t>(ctx->need_ptab, 1)));
+        CU(ctx->d_segoff1.ensure(std::max<size_t>(ctx->need_segoff, 1)));
+        ctx->sc1.preb = ctx->d_preb1.as<double>();
+        ctx->sc1.ptab = ctx->d_ptab1.as<double>();
+        ctx->sc1.segoff = ctx->d_segoff1.as<double>();
+        // the log-CMF scratch is indexed by CTA slot of prob_table_kernel, which only ever runs on stream2: shared
+    }
+    // dynamic shared memory ceilings are per function, not per launch: set them for this slot's layout
+    if (!ctx->prob_big_bytes) CU(cudaFuncSetAttribute(prob_table_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->prob_smem));
+    CU(cudaFuncSetAttribute(prefix_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->prefix_smem));
+    CU(cudaFuncSetAttribute(lineage_walk_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->walk_smem));
+    CU(cudaFuncSetAttribute(lineage_walk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->walk_smem));
+    CU(cudaFuncSetAttribute(lineage_bfs_kernel<kBfsThreadsDefault>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->bfs_smem));
+    CU(cudaFuncSetAttribute(lineage_bfs_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->bfs_smem));
+    ctx->cur_stream = ctx->stream;
+    ctx->cur_counts = ctx->d_counts.as<u16>();
+    ctx->cur_sc = &ctx->sc;
+    return RTX_OK;
+}
+
 RTX_API int rtx_batch_upload(rtx_ctx* ctx, const rtx_batch* batch) {
     if (!ctx) return RTX_ERR_INVALID;
     if (!ctx->has_index) return set_err(ctx, RTX_ERR_NO_INDEX, "rtx_batch_upload: no index uploaded");
@@ -762,6 +845,7 @@ RTX_API int rtx_batch_upload(rtx_ctx* ctx, const rtx_batch* batch) {
     const bool big = smem > 200 * 1024;  // queries beyond ~6.4 kb: the tables of K3 move to global scratch (ProbScratch::big)
     ctx->prob_big_bytes = big ? (smem + 255) & ~(size_t)255 : 0;
     if (big) smem = 0;
+    ctx->sc = ProbScratch{};
     ctx->sc.nprod = nprod;
     ctx->sc.lf_smem = lf_smem;
     ctx->max_len = max_len;
@@ -776,28 +860,32 @@ RTX_API int rtx_batch_upload(rtx_ctx* ctx, const rtx_batch* batch) {
     }
     ctx->total_exact = total_exact;
 
-    // H2D (offsets are rebased to 0 so that callers may pass a window of a larger array)
+    // H2D on the copy stream (offsets are rebased to 0 so that callers may pass a window of a larger array); the kernels of the
+    // slot's next run wait for ev_up, the kernels of the OTHER slot, possibly running right now, are not disturbed
+    cudaStream_t cs = ctx->stream_cp;
     CU(ctx->d_seq_off.ensure((nq + 1) * 8));
     CU(ctx->d_codes.ensure(std::max<u64>(total, 1)));
     if (batch->seq_offsets[0] == 0) {
-        CU(cudaMemcpyAsync(ctx->d_seq_off.p, batch->seq_offsets, (nq + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+        CU(cudaMemcpyAsync(ctx->d_seq_off.p, batch->seq_offsets, (nq + 1) * 8, cudaMemcpyHostToDevice, cs));
     } else {
         std::vector<u64> reb(nq + 1);
         for (u32 q = 0; q <= nq; ++q) reb[q] = batch->seq_offsets[q] - batch->seq_offsets[0];
-        CU(cudaMemcpyAsync(ctx->d_seq_off.p, reb.data(), (nq + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
-        CU(cudaStreamSynchronize(ctx->stream));
+        CU(cudaMemcpyAsync(ctx->d_seq_off.p, reb.data(), (nq + 1) * 8, cudaMemcpyHostToDevice, cs));
+        CU(cudaStreamSynchronize(cs));
     }
-    if (total) CU(cudaMemcpyAsync(ctx->d_codes.p, batch->seq_codes + batch->seq_offsets[0], total, cudaMemcpyHostToDevice, ctx->stream));
+    if (total) CU(cudaMemcpyAsync(ctx->d_codes.p, batch->seq_codes + batch->seq_offsets[0], total, cudaMemcpyHostToDevice, cs));
     ctx->prof.h2d_bytes += (nq + 1) * 8 + total;
     if (batch->exact_offsets) {
         CU(ctx->d_exact_off.ensure((nq + 1) * 4));
         CU(ctx->d_exact_ids.ensure(std::max<u64>(total_exact, 1) * 4));
-        CU(cudaMemcpyAsync(ctx->d_exact_off.p, batch->exact_offsets, (nq + 1) * 4, cudaMemcpyHostToDevice, ctx->stream));
-        if (total_exact) CU(cudaMemcpyAsync(ctx->d_exact_ids.p, batch->exact_ids, total_exact * 4, cudaMemcpyHostToDevice, ctx->stream));
+        CU(cudaMemcpyAsync(ctx->d_exact_off.p, batch->exact_offsets, (nq + 1) * 4, cudaMemcpyHostToDevice, cs));
+        if (total_exact) CU(cudaMemcpyAsync(ctx->d_exact_ids.p, batch->exact_ids, total_exact * 4, cudaMemcpyHostToDevice, cs));
         ctx->prof.h2d_bytes += (nq + 1) * 4 + total_exact * 4;
         bv.exact_off = ctx->d_exact_off.as<u32>();
         bv.exact_ids = ctx->d_exact_ids.as<u32>();
     }
+    CU(cudaEventRecord(ctx->ev_up, cs));
+    ctx->up_pending = true;
     bv.seq_off = ctx->d_seq_off.as<u64>();
     bv.codes = ctx->d_codes.as<u8>();
     bv.kstride = kstride;
@@ -846,8 +934,7 @@ RTX_API int rtx_batch_upload(rtx_ctx* ctx, const rtx_batch* batch) {
     sb = std::min<u64>(std::min<u64>(sb, nq), 65535);
     ctx->sub_batch = (u32)sb;
     ctx->two_slots = may_pipe && nq > sb;
-    CU(ctx->d_counts.ensure(sb * per_query));
-    if (ctx->two_slots) CU(ctx->d_counts1.ensure(sb * per_query));
+    ctx->need_counts = sb * per_query;
 
     // probability kernel scratch
     ctx->prob_smem = smem;
@@ -866,13 +953,8 @@ RTX_API int rtx_batch_upload(rtx_ctx* ctx, const rtx_batch* batch) {
         if (ctx->prefix_smem > 220 * 1024)
             return set_err(ctx, RTX_ERR_UNSUPPORTED, "reference shard too large for the prefix kernel's segment table (more than ~11 M references per GPU): shard the references");
     }
-    CU(cudaFuncSetAttribute(prefix_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->prefix_smem));
     ctx->walk_smem = (size_t)kWalkWarps * WalkSmem::bytes(ctx->ix.max_levels);
-    CU(cudaFuncSetAttribute(lineage_walk_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->walk_smem));
-    CU(cudaFuncSetAttribute(lineage_walk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->walk_smem));
     ctx->bfs_smem = BfsSmem::bytes(ctx->ix.max_levels);
-    CU(cudaFuncSetAttribute(lineage_bfs_kernel<kBfsThreadsDefault>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->bfs_smem));
-    CU(cudaFuncSetAttribute(lineage_bfs_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->bfs_smem));
     ctx->shard_phase = 0;
     int slots = (int)std::min<u64>((u64)ctx->n_sms * occ, sb);
     const u32 tstride = round_up(hstride / 2 + 1, 4);
@@ -880,6 +962,7 @@ RTX_API int rtx_batch_upload(rtx_ctx* ctx, const rtx_batch* batch) {
     ctx->sc.cbuf_stride = (size_t)hstride * tstride;
     ctx->sc.big = nullptr;
     ctx->sc.big_stride = 0;
+    ctx->need_prob_big = 0;
     if (ctx->prob_big_bytes) {
         // long queries: the log-CMF scratch of one CTA slot is hstride x tstride doubles (1 GB at 16 k 8-mers); as many slots as fit a
         // quarter of the free memory (at most 16 GB), at least one
@@ -889,39 +972,26 @@ RTX_API int rtx_batch_upload(rtx_ctx* ctx, const rtx_batch* batch) {
             return set_err(ctx, RTX_ERR_UNSUPPORTED, "query too long: the probability scratch of one query (" + std::to_string(per_slot >> 20) +
                                                          " MB) does not fit a quarter of the free device memory");
         slots = (int)std::max<u64>(1, std::min<u64>((u64)slots, budget / per_slot));
-        CU(ctx->d_prob_big.ensure((size_t)slots * ctx->prob_big_bytes));
-        ctx->sc.big = ctx->d_prob_big.as<unsigned char>();
+        ctx->need_prob_big = (size_t)slots * ctx->prob_big_bytes;
         ctx->sc.big_stride = ctx->prob_big_bytes;
     }
     ctx->prob_slots = slots;
     ctx->sc.preb_stride = round_up(ctx->ix.n_bnd, 4);
-    CU(ctx->d_cbuf.ensure((size_t)slots * ctx->sc.cbuf_stride * 8));
-    CU(ctx->d_preb.ensure((size_t)sb * ctx->sc.preb_stride * 8));
-    CU(ctx->d_ptab.ensure((size_t)sb * hstride * 8));
-    ctx->sc.ptab = ctx->d_ptab.as<double>();
-    ctx->sc.cbuf = ctx->d_cbuf.as<double>();
-    ctx->sc.preb = ctx->d_preb.as<double>();
+    ctx->need_cbuf = (size_t)slots * ctx->sc.cbuf_stride * 8;
+    ctx->need_preb = (size_t)sb * ctx->sc.preb_stride * 8;
+    ctx->need_ptab = (size_t)sb * hstride * 8;
     {   // per query: n_seg segment offsets | u32 aux[2 + n_seg/32] (m_min, skip bitmap; ProbScratch::seg_aux_off)
         const u32 n_seg = (u32)(ctx->ix.n_pad / kPrefixSeg);
         ctx->sc.seg_aux_off = round_up(n_seg, 2);
         ctx->sc.segoff_stride = round_up(ctx->sc.seg_aux_off + 1 + ((n_seg + 31) / 32 + 1) / 2 + (n_seg + 3) / 4, 4);  // + u16 segmax[n_seg]
     }
-    CU(ctx->d_segoff.ensure((size_t)sb * ctx->sc.segoff_stride * 8));
-    ctx->sc.segoff = ctx->d_segoff.as<double>();
-    ctx->sc1 = ctx->sc;
-    if (ctx->two_slots) {
-        CU(ctx->d_preb1.ensure((size_t)sb * ctx->sc.preb_stride * 8));
-        CU(ctx->d_ptab1.ensure((size_t)sb * hstride * 8));
-        CU(ctx->d_segoff1.ensure((size_t)sb * ctx->sc.segoff_stride * 8));
-        ctx->sc1.preb = ctx->d_preb1.as<double>();
-        ctx->sc1.ptab = ctx->d_ptab1.as<double>();
-        ctx->sc1.segoff = ctx->d_segoff1.as<double>();
-        // the log-CMF scratch is indexed by CTA slot of prob_table_kernel, which only ever runs on stream2: shared
-    }
-    ctx->cur_stream = ctx->stream;
-    ctx->cur_counts = ctx->d_counts.as<u16>();
-    ctx->cur_sc = &ctx->sc;
+    ctx->need_segoff = (size_t)sb * ctx->sc.segoff_stride * 8;
     ctx->has_batch = true;
+    int rc = bind_scratch(ctx);  // allocation failures surface here, at upload time
+    if (rc) {
+        ctx->has_batch = false;
+        return rc;
+    }
     return RTX_OK;
 }
 
@@ -960,6 +1030,7 @@ static cudaError_t launch_hitcount(rtx_ctx* c, int q_base, int qb, int nwarps_op
     cudaError_t e = cudaFuncSetAttribute(hitcount_bitrows_kernel<V, NP, PF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     dim3 grid(qb, groups);
+    c->hit_kernel = "hitcount_bitrows_kernel<" + std::to_string(V) + ", " + std::to_string(NP) + ", " + (PF ? "true" : "false") + ">";
     hitcount_bitrows_kernel<V, NP, PF><<<grid, nwarps * 32, smem, c->cur_stream>>>(c->ix, c->bv, c->cur_counts, q_base, tiles_per_cta, n_tiles,
                                                                                  hist_global ? 1 : 0);
     return cudaGetLastError();
@@ -1011,8 +1082,11 @@ static cudaError_t launch_hitcount_group(rtx_ctx* c, int q_base, int qb, int G) 
         c->segmax_valid = true;
         return cudaGetLastError();
     };
-    if (n_chunks > 1) return go(hitcount_group_kernel<V, NP, true, kHitGroupMaxThreads, 1>);
-    if (c->hit_tune == 1) return go(hitcount_group_kernel<V, NP, false, kHitGroupMaxThreads, 1, false>);  // L1 bypass (measured option)
+    const bool lockstep = n_chunks > 1, l1a = lockstep || c->hit_tune != 1;
+    c->hit_kernel = "hitcount_group_kernel<2, " + std::to_string(NP) + ", " + (lockstep ? "true" : "false") + ", " + std::to_string(kHitGroupMaxThreads) +
+                    ", 1, " + (l1a ? "true" : "false") + "> (" + std::to_string(G) + " queries per CTA)";
+    if (lockstep) return go(hitcount_group_kernel<V, NP, true, kHitGroupMaxThreads, 1>);
+    if (!l1a) return go(hitcount_group_kernel<V, NP, false, kHitGroupMaxThreads, 1, false>);  // L1 bypass (measured option)
     return go(hitcount_group_kernel<V, NP, false, kHitGroupMaxThreads, 1>);
 }
 
@@ -1048,6 +1122,7 @@ static int run_phase1(rtx_ctx* ctx, int q_base, int qb) {
         const size_t smem = (size_t)(kCsrTileRefs / 2 + ctx->bv.hstride) * 4;
         CU(cudaFuncSetAttribute(hitcount_csr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         dim3 grid(qb, (unsigned)((ctx->ix.shard_refs + kCsrTileRefs - 1) / kCsrTileRefs));
+        ctx->hit_kernel = "hitcount_csr_kernel";
         hitcount_csr_kernel<<<grid, kCsrThreads, smem, ctx->cur_stream>>>(ctx->ix, ctx->bv, ctx->cur_counts, q_base);
         CU(cudaGetLastError());
     } else {
@@ -1099,12 +1174,27 @@ static int order_results(rtx_ctx* ctx) {
     return RTX_OK;
 }
 
+// before the first kernel of a slot's run: scratch bound to this slot's layout, inputs (H2D on the copy stream) in place
+static int begin_run(rtx_ctx* ctx) {
+    int rc = bind_scratch(ctx);
+    if (rc) return rc;
+    if (ctx->up_pending) {
+        CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_up, 0));
+        ctx->up_pending = false;
+    }
+    return RTX_OK;
+}
+
 static int run_all(rtx_ctx* ctx) {
     BatchView& bv = ctx->bv;
     const u32 nq = bv.n_queries;
     if (nq == 0) return RTX_OK;
     if (ctx->sv.n_shards > 1)
         return set_err(ctx, RTX_ERR_INVALID, "this context holds one shard of a reference-sharded index: use the rtx_shard_phase* calls");
+    {
+        int rc = begin_run(ctx);
+        if (rc) return rc;
+    }
     CU(cudaMemsetAsync(ctx->d_hist.p, 0, (size_t)nq * bv.hstride * 4, ctx->stream));
     CU(cudaMemsetAsync(ctx->d_pool_used.p, 0, 8, ctx->stream));
     CU(cudaMemsetAsync(ctx->d_hits.p, 0, 8, ctx->stream));
@@ -1182,6 +1272,7 @@ static int run_all(rtx_ctx* ctx) {
         int rc = order_results(ctx);
         if (rc) return rc;
     }
+    CU(cudaEventRecord(ctx->ev_done, ctx->stream));
     ctx->prof.queries += nq;
     ctx->runs_since_download += 1;
     ctx->ran = true;
@@ -1212,6 +1303,8 @@ RTX_API int rtx_batch_download(rtx_ctx* ctx, rtx_results* res) {
     }
     REQUIRE(res->result_begin && res->n_kmers && res->global_signal, "result_begin / n_kmers / global_signal must be provided");
     const u32 ML = ctx->ix.max_levels;
+    cudaStream_t cs = ctx->stream_cp;
+    CU(cudaStreamWaitEvent(cs, ctx->ev_done, 0));  // this slot's kernels; the other slot may be running on `stream` meanwhile
     // round 1: per-query metadata through the pinned arena, one synchronisation
     const size_t meta_bytes = 2 * 64 + ((size_t)nq + 1) * 4 + (size_t)nq * (4 + 4 + 2 + 8) + 6 * 64;
     CU(arena_reserve(ctx, meta_bytes));
@@ -1219,11 +1312,11 @@ RTX_API int rtx_batch_download(rtx_ctx* ctx, rtx_results* res) {
     u32* h_begin = (u32*)arena_take(ctx, ((size_t)nq + 1) * 4);
     int* h_status = (int*)arena_take(ctx, (size_t)nq * 4);
     u32* h_nrows = (u32*)arena_take(ctx, (size_t)nq * 4);
-    CU(cudaMemcpyAsync(&h_used[0], ctx->d_pool_used.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
-    CU(cudaMemcpyAsync(&h_used[1], ctx->d_hits.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
-    CU(cudaMemcpyAsync(h_begin, ctx->d_ord_begin.p, ((size_t)nq + 1) * 4, cudaMemcpyDeviceToHost, ctx->stream));
-    CU(cudaMemcpyAsync(h_status, ctx->d_status.p, (size_t)nq * 4, cudaMemcpyDeviceToHost, ctx->stream));
-    CU(cudaMemcpyAsync(h_nrows, ctx->d_nrows.p, (size_t)nq * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaMemcpyAsync(&h_used[0], ctx->d_pool_used.p, 8, cudaMemcpyDeviceToHost, cs));
+    CU(cudaMemcpyAsync(&h_used[1], ctx->d_hits.p, 8, cudaMemcpyDeviceToHost, cs));
+    CU(cudaMemcpyAsync(h_begin, ctx->d_ord_begin.p, ((size_t)nq + 1) * 4, cudaMemcpyDeviceToHost, cs));
+    CU(cudaMemcpyAsync(h_status, ctx->d_status.p, (size_t)nq * 4, cudaMemcpyDeviceToHost, cs));
+    CU(cudaMemcpyAsync(h_nrows, ctx->d_nrows.p, (size_t)nq * 4, cudaMemcpyDeviceToHost, cs));
     CU(d2h(ctx, res->n_kmers, ctx->d_K.p, (size_t)nq * 2, host_ptr_pinned(res->n_kmers)));
     CU(d2h(ctx, res->global_signal, ctx->d_global.p, (size_t)nq * 8, host_ptr_pinned(res->global_signal)));
     CU(d2h_finish(ctx));
@@ -1289,29 +1382,29 @@ RTX_API int rtx_batch_download(rtx_ctx* ctx, rtx_results* res) {
                 "tap_hist_stride too small");
         const u64 w = std::min<u64>(res->tap_hist_stride, bv.hstride);
         CU(cudaMemcpy2DAsync(res->tap_hist, res->tap_hist_stride * 4, ctx->d_hist.p, (size_t)bv.hstride * 4, w * 4, nq, cudaMemcpyDeviceToHost,
-                             ctx->stream));
+                             cs));
         ctx->prof.d2h_bytes += (u64)nq * w * 4;
     }
     if (res->tap_kmers) {
         const u64 w = std::min<u64>(res->tap_kmer_stride, bv.kstride);
         CU(cudaMemcpy2DAsync(res->tap_kmers, res->tap_kmer_stride * 2, ctx->d_kmers.p, (size_t)bv.kstride * 2, w * 2, nq,
-                             cudaMemcpyDeviceToHost, ctx->stream));
+                             cudaMemcpyDeviceToHost, cs));
         ctx->prof.d2h_bytes += (u64)nq * w * 2;
     }
     if (res->tap_probs && !ctx->tap_probs_host) {
         REQUIRE(ctx->sub_batch >= nq, "tap_probs through rtx_batch_download needs the whole batch in one sub-batch; use rtx_classify_batch");
         const u64 w = std::min<u64>(res->tap_prob_stride, bv.hstride);
         CU(cudaMemcpy2DAsync(res->tap_probs, res->tap_prob_stride * 8, ctx->d_ptab.p, (size_t)bv.hstride * 8, w * 8, nq, cudaMemcpyDeviceToHost,
-                             ctx->stream));
+                             cs));
         ctx->prof.d2h_bytes += (u64)nq * w * 8;
     }
     if (res->tap_counts && !ctx->tap_counts_host) {
         REQUIRE(ctx->sub_batch >= nq, "tap_counts through rtx_batch_download needs the whole batch in one sub-batch; use rtx_classify_batch");
         const u64 Ns = ctx->ix.shard_refs;
-        CU(cudaMemcpy2DAsync(res->tap_counts, Ns * 2, ctx->d_counts.p, ctx->ix.n_pad * 2, Ns * 2, nq, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaMemcpy2DAsync(res->tap_counts, Ns * 2, ctx->d_counts.p, ctx->ix.n_pad * 2, Ns * 2, nq, cudaMemcpyDeviceToHost, cs));
         ctx->prof.d2h_bytes += (u64)nq * Ns * 2;
     }
-    CU(cudaStreamSynchronize(ctx->stream));
+    CU(cudaStreamSynchronize(cs));
     return RTX_OK;
 }
 
@@ -1349,6 +1442,8 @@ RTX_API int rtx_shard_phase1(rtx_ctx* ctx) {
     const u32 nq = bv.n_queries;
     ctx->shard_phase = 1;
     if (nq == 0) return RTX_OK;
+    rc = begin_run(ctx);
+    if (rc) return rc;
     CU(cudaMemsetAsync(ctx->d_hist.p, 0, (size_t)nq * bv.hstride * 4, ctx->stream));
     CU(cudaMemsetAsync(ctx->d_pool_used.p, 0, 8, ctx->stream));
     CU(cudaMemsetAsync(ctx->d_hits.p, 0, 8, ctx->stream));
@@ -1437,6 +1532,7 @@ RTX_API int rtx_shard_phase3(rtx_ctx* ctx) {
     ctx->cur_stream = ctx->stream;
     rc = order_results(ctx);
     if (rc) return rc;
+    CU(cudaEventRecord(ctx->ev_done, ctx->stream));
     ctx->prof.queries += nq;
     ctx->runs_since_download += 1;
     ctx->ran = true;
@@ -1521,9 +1617,11 @@ RTX_API int rtx_profile_reset(rtx_ctx* ctx) {
     if (!ctx) return RTX_ERR_INVALID;
     CU(cudaSetDevice(ctx->device));
     CU(cudaStreamSynchronize(ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream_cp));
     drain_events(ctx);
     ctx->prof = rtx_profile{};
     ctx->runs_since_download = 0;
+    ctx->parked.runs_since_download = 0;
     return RTX_OK;
 }
 

@@ -12,9 +12,11 @@
 #include <atomic>
 #include <chrono>
 #include <cmath>
+#include <condition_variable>
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
+#include <deque>
 #include <memory>
 #include <mutex>
 #include <numeric>
@@ -126,35 +128,99 @@ struct Tree {
     std::vector<u32> csr_ids;  // index from the sorted sequences, so the classification path never needs the lists on the host
     bool has_csr = false;
     std::mutex csr_mtx;
-    std::unordered_map<u64, std::vector<u32>> seq_hash;  // sequences (tree.rs:40): hash of codes -> ids, verified on lookup
+    // sequences (tree.rs:40, `HashMap<Vec<u8>, Vec<u32>>`): open addressing over a 64-bit hash of the code bytes; a slot holds the FIRST
+    // reference of a group of identical sequences, the group's other members hang off it in ascending order (ex_next)
+    std::vector<u32> ex_head;  // id + 1, 0 = empty
+    std::vector<u32> ex_tag;   // high half of the hash of the slot's sequence (pre-filter before the memcmp)
+    std::vector<u32> ex_next;  // [num refs] next reference with the same sequence, kNone = last of its group
+    size_t ex_mask = 0;
+    static constexpr u32 kNone = 0xFFFFFFFFu;
     // Inner / Taxon (and non-leaf Sequence) nodes, BFS order, children contiguous
     std::vector<u32> node_lo, node_hi, child_first, child_count;
     std::vector<u8> node_type;
     std::vector<u8> ref_levels;
 
+    // four independent multiply-xor lanes over 32 bytes per round (a single lane is a 7-cycle dependency chain per 8 bytes: at
+    // 650 bytes per query and two hashes per query that alone was a third of the driver's per-query host time)
     static u64 hash_bytes(const u8* p, size_t n) {
-        u64 h = 0x9E3779B97F4A7C15ull ^ (n * 0xff51afd7ed558ccdull);
+        const u64 k0 = 0x9E3779B97F4A7C15ull, k1 = 0xC2B2AE3D27D4EB4Full, k2 = 0x165667B19E3779F9ull, k3 = 0xD6E8FEB86659FD93ull;
+        u64 a = k0 ^ (n * 0xff51afd7ed558ccdull), b = k1, c = k2, d = k3;
+        auto round = [&](const u64* w) {
+            a = (a ^ w[0]) * k1;
+            a ^= a >> 29;
+            b = (b ^ w[1]) * k2;
+            b ^= b >> 29;
+            c = (c ^ w[2]) * k3;
+            c ^= c >> 29;
+            d = (d ^ w[3]) * k0;
+            d ^= d >> 29;
+        };
         size_t i = 0;
-        for (; i + 8 <= n; i += 8) {
-            u64 w;
-            memcpy(&w, p + i, 8);
-            h = (h ^ w) * 0x9FB21C651E98DF25ull;
-            h ^= h >> 29;
+        u64 w[4];
+        for (; i + 32 <= n; i += 32) {
+            memcpy(w, p + i, 32);
+            round(w);
         }
-        u64 tail = 0;
-        for (size_t j = 0; i + j < n; ++j) tail |= (u64)p[i + j] << (8 * j);
-        h = (h ^ tail) * 0xD6E8FEB86659FD93ull;
+        if (i < n) {
+            w[0] = w[1] = w[2] = w[3] = 0;
+            memcpy(w, p + i, n - i);
+            round(w);
+        }
+        u64 h = (a ^ ((b << 17) | (b >> 47))) * k2;
+        h ^= c ^ ((d << 31) | (d >> 33));
+        h *= k1;
         return h ^ (h >> 32);
     }
 
+    bool same_seq(u32 id, const u8* seq, size_t len) const {
+        const size_t l = (size_t)(seq_off[id + 1] - seq_off[id]);
+        return l == len && (len == 0 || memcmp(seq_codes.data() + seq_off[id], seq, len) == 0);
+    }
+    // first reference carrying exactly this sequence, or kNone
+    u32 exact_head(const u8* seq, size_t len, u64 h) const {
+        if (ex_head.empty()) return kNone;
+        const u32 tag = (u32)(h >> 32);
+        for (size_t at = (size_t)h & ex_mask;; at = (at + 1) & ex_mask) {
+            const u32 e = ex_head[at];
+            if (!e) return kNone;
+            if (ex_tag[at] == tag && same_seq(e - 1, seq, len)) return e - 1;
+        }
+    }
     // tree.sequences.get(seq) (raxtax.rs:42)
-    void exact(const u8* seq, size_t len, std::vector<u32>* out) const {
+    void exact(const u8* seq, size_t len, std::vector<u32>* out) const { exact_h(seq, len, hash_bytes(seq, len), out); }
+    void exact_h(const u8* seq, size_t len, u64 h, std::vector<u32>* out) const {
         out->clear();
-        auto it = seq_hash.find(hash_bytes(seq, len));
-        if (it == seq_hash.end()) return;
-        for (u32 id : it->second) {
-            size_t l = (size_t)(seq_off[id + 1] - seq_off[id]);
-            if (l == len && (len == 0 || memcmp(seq_codes.data() + seq_off[id], seq, len) == 0)) out->push_back(id);
+        for (u32 id = exact_head(seq, len, h); id != kNone; id = ex_next[id]) out->push_back(id);
+    }
+    // sequences.entry(sequence).or_default().push(idx) for idx = 0 .. n-1 (tree.rs:109-112)
+    void build_exact() {
+        const size_t n = seq_off.empty() ? 0 : seq_off.size() - 1;
+        size_t cap = 64;
+        while (cap < n * 2) cap <<= 1;
+        ex_head.assign(cap, 0);
+        ex_tag.assign(cap, 0);
+        ex_next.assign(n, kNone);
+        ex_mask = cap - 1;
+        std::vector<u32> tail(n, 0);  // tail[head] = last member of head's group so far
+        for (size_t idx = 0; idx < n; ++idx) {
+            const u8* sp = seq_codes.data() + seq_off[idx];
+            const size_t sl = (size_t)(seq_off[idx + 1] - seq_off[idx]);
+            const u64 h = hash_bytes(sp, sl);
+            const u32 tag = (u32)(h >> 32);
+            for (size_t at = (size_t)h & ex_mask;; at = (at + 1) & ex_mask) {
+                const u32 e = ex_head[at];
+                if (!e) {
+                    ex_head[at] = (u32)idx + 1;
+                    ex_tag[at] = tag;
+                    tail[idx] = (u32)idx;
+                    break;
+                }
+                if (ex_tag[at] == tag && same_seq(e - 1, sp, sl)) {
+                    ex_next[tail[e - 1]] = (u32)idx;
+                    tail[e - 1] = (u32)idx;
+                    break;
+                }
+            }
         }
     }
 };
@@ -334,11 +400,12 @@ static std::unique_ptr<Tree> tree_new(std::vector<std::string> lineages, const u
         const u64 o = seq_off[order[idx]], l = seq_off[order[idx] + 1] - o;
         memcpy(tree->seq_codes.data() + wpos, codes + o, l);
         tree->seq_off[idx] = wpos;
-        tree->seq_hash[Tree::hash_bytes(codes + o, l)].push_back((u32)idx);  // tree.rs:109-112
         wpos += l;
     }
     tree->seq_off[n] = wpos;
-    lap("nodes + sequence hash map");
+    lap("nodes");
+    tree->build_exact();  // tree.rs:109-112
+    lap("sequence map");
     nodes[0].hi = (u32)confidence_idx;  // tree.rs:127
     tree->num_tips = confidence_idx;    // tree.rs:138
     tree->lineages.resize(n);
@@ -436,20 +503,12 @@ static void save_bin(const Tree& t, const char* path) {
     {   // sequences: HashMap<Vec<u8>, Vec<u32>> (tree.rs:40), any order; one entry per distinct sequence
         u64 distinct = 0;
         std::vector<std::vector<u32>> groups;
-        for (const auto& kv : t.seq_hash) {
-            std::vector<u32> ids = kv.second;  // ascending; usually one sequence per bucket, more only on a 64-bit hash collision
-            while (!ids.empty()) {
-                std::vector<u32> same{ids[0]}, rest;
-                const u64 o0 = t.seq_off[ids[0]], l0 = t.seq_off[ids[0] + 1] - o0;
-                for (size_t j = 1; j < ids.size(); ++j) {
-                    const u64 o = t.seq_off[ids[j]], l = t.seq_off[ids[j] + 1] - o;
-                    if (l == l0 && (l == 0 || memcmp(t.seq_codes.data() + o, t.seq_codes.data() + o0, l) == 0)) same.push_back(ids[j]);
-                    else rest.push_back(ids[j]);
-                }
-                groups.push_back(std::move(same));
-                ids.swap(rest);
-                ++distinct;
-            }
+        for (const u32 e : t.ex_head) {
+            if (!e) continue;
+            std::vector<u32> same;
+            for (u32 id = e - 1; id != Tree::kNone; id = t.ex_next[id]) same.push_back(id);  // ascending
+            groups.push_back(std::move(same));
+            ++distinct;
         }
         w.u64v(distinct);
         for (const auto& g : groups) {
@@ -576,8 +635,8 @@ static std::unique_ptr<Tree> load_bin(const u8* data, size_t len) {
         tree->seq_codes.resize(tree->seq_off[n]);
         for (u64 i = 0; i < n; ++i) {
             if (len_of[i]) memcpy(tree->seq_codes.data() + tree->seq_off[i], key_of[i], len_of[i]);
-            tree->seq_hash[Tree::hash_bytes(tree->seq_codes.data() + tree->seq_off[i], len_of[i])].push_back((u32)i);
         }
+        tree->build_exact();
         // k_mer_map
         if (r.u64v() != 65536) throw BinReader::Fail{};
         tree->csr_off.assign(65537, 0);
@@ -981,10 +1040,208 @@ RXH_API uint64_t rxh_exact_batch(const rxh_tree* t, size_t n, const uint64_t* se
     return total;
 }
 
-// raxtax::raxtax (raxtax.rs:14-97).  The reference fans chunks of queries out over the rayon pool (raxtax.rs:35-39); here every
-// context (= GPU, index replicated) has one host thread pulling chunks from a shared counter, with no collective between them;
-// sender and logger are called under one mutex, the lines of a query contiguous, queries in completion order as in the reference.
+// raxtax::raxtax (raxtax.rs:14-97).  The reference fans chunks of queries out over the rayon pool (raxtax.rs:35-39) and a separate
+// writer thread drains the channel (main.rs:126-136).  Here every context (= GPU, index replicated) has one DRIVER thread that pulls
+// chunks from a shared counter and keeps two batches in flight on its device (the two batch slots of rtx_batch_slot): while the
+// kernels of chunk i run, chunk i+1 is de-duplicated, looked up (exact matches), uploaded and queued behind it, and chunk i-1 is
+// formatted by the EMITTER -- the calling thread -- with a few helper threads, then handed to the sender one query at a time.
+// Between the contexts there is no collective; queries arrive in completion order (in query order with one context), the lines of
+// a query contiguous, as in the reference.
 namespace {
+
+// ---- "{:.N}" of an f64 (Rust rounds the exact binary value to nearest, ties to even -- what glibc's %.Nf does too) ---------------
+// Fast path: scale, round, print two integers.  The scaled value carries a relative error of 2^-53, so whenever it sits closer than
+// 1e-6 to a rounding tie -- or is negative, huge or not finite -- the exact (slow) conversion decides.
+static inline char* put_uint(char* p, u64 v) {
+    char tmp[24];
+    int n = 0;
+    do {
+        tmp[n++] = (char)('0' + v % 10);
+        v /= 10;
+    } while (v);
+    while (n) *p++ = tmp[--n];
+    return p;
+}
+static char* put_fixed(char* p, double v, int prec) {
+    static const double pw[] = {1.0, 10.0, 100.0, 1e3, 1e4, 1e5, 1e6};
+    if (prec >= 1 && prec <= 6 && v >= 0.0 && v < 1e9 && !std::signbit(v)) {
+        const double x = v * pw[prec];
+        const double fl = std::floor(x);
+        const double frac = x - fl;
+        if (std::fabs(frac - 0.5) > 1e-6) {
+            const u64 r = (u64)fl + (frac > 0.5 ? 1u : 0u);
+            const u64 scale = (u64)pw[prec];
+            p = put_uint(p, r / scale);
+            *p++ = '.';
+            u64 f = r % scale;
+            for (int i = prec - 1; i >= 0; --i) {
+                p[i] = (char)('0' + f % 10);
+                f /= 10;
+            }
+            return p + prec;
+        }
+    }
+    return p + snprintf(p, 400, "%.*f", prec, v);
+}
+
+// growable char buffer the formatters write into with raw pointers
+struct CharBuf {
+    std::vector<char> v;
+    size_t n = 0;
+    char* reserve(size_t more) {
+        if (n + more > v.size()) v.resize(std::max(v.size() * 2, n + more + 4096));
+        return v.data() + n;
+    }
+    void put(const char* s, size_t len) {
+        memcpy(reserve(len), s, len);
+        n += len;
+    }
+    void put(char c) {
+        *reserve(1) = c;
+        n += 1;
+    }
+    void fixed(double val, int prec) {
+        char* p = reserve(420);
+        n += (size_t)(put_fixed(p, val, prec) - p);
+    }
+};
+
+static void output_line(CharBuf& s, const std::string& label, const ResultView& r) {  // lineage.rs:17-30
+    s.put(label.data(), label.size());
+    s.put('\t');
+    s.put(r.lineage->data(), r.lineage->size());
+    s.put('\t');
+    for (u32 i = 0; i < r.n_levels; ++i) {
+        if (i) s.put(',');
+        s.fixed(r.conf[i], 2);
+    }
+    s.put('\t');
+    s.fixed(r.local, 5);
+    s.put('\t');
+    s.fixed(r.global, 5);
+}
+
+static void tsv_line(CharBuf& s, const std::string& label, const ResultView& r, const std::string& sequence) {  // lineage.rs:32-48
+    s.put(label.data(), label.size());
+    s.put('\t');
+    // itertools::interleave(lineage.split(','), confidences): alternate while both last, then drain the rest
+    const std::string& lin = *r.lineage;
+    size_t start = 0;
+    bool lin_done = false;
+    u32 ci = 0;
+    bool first = true, take_lin = true;
+    while (!lin_done || ci < r.n_levels) {
+        const bool use_lin = take_lin ? !lin_done : !(ci < r.n_levels);
+        if (!first) s.put('\t');
+        first = false;
+        if (use_lin) {
+            const size_t p = lin.find(',', start);
+            if (p == std::string::npos) {
+                s.put(lin.data() + start, lin.size() - start);
+                lin_done = true;
+            } else {
+                s.put(lin.data() + start, p - start);
+                start = p + 1;
+            }
+        } else {
+            s.fixed(r.conf[ci++], 2);
+        }
+        take_lin = !take_lin;
+    }
+    s.put('\t');
+    s.fixed(r.local, 5);
+    s.put('\t');
+    s.fixed(r.global, 5);
+    s.put('\t');
+    s.put(sequence.data(), sequence.size());
+}
+
+// page-locked array from the device library (results land in it by DMA), grown on demand
+template <typename T>
+struct PinnedArr {
+    T* p = nullptr;
+    size_t cap = 0;
+    PinnedArr() = default;
+    PinnedArr(const PinnedArr&) = delete;
+    PinnedArr& operator=(const PinnedArr&) = delete;
+    ~PinnedArr() {
+        if (p) rtx_host_free(p);
+    }
+    void ensure(size_t n) {
+        if (n <= cap) return;
+        rtx_host_free(p);
+        p = nullptr;
+        cap = 0;
+        const size_t want = n + n / 4 + 64;
+        void* q = nullptr;
+        if (rtx_host_alloc(want * sizeof(T), &q) != RTX_OK) throw Error("rtx_host_alloc failed (page-locked result buffers)");
+        p = (T*)q;
+        cap = want;
+    }
+};
+
+// distinct sequences of a chunk: open addressing over (hash, first query with that sequence)
+struct FlatDedup {
+    std::vector<u64> hash;
+    std::vector<u32> slot;  // unique id + 1, 0 = empty
+    size_t mask = 0;
+    void reset(size_t n) {
+        size_t cap = 64;
+        while (cap < n * 2) cap <<= 1;
+        if (slot.size() != cap) {
+            slot.assign(cap, 0);
+            hash.assign(cap, 0);
+        } else std::fill(slot.begin(), slot.end(), 0u);
+        mask = cap - 1;
+    }
+};
+
+struct ChunkJob {
+    size_t c0 = 0, cn = 0, n_uniq = 0;
+    bool compact = false;
+    int dev_slot = 0;
+    std::vector<u32> rep, uniq_first, exact_off, exact_ids;
+    std::vector<u64> u_off, uniq_hash;
+    std::vector<u8> u_codes;
+    PinnedArr<u16> n_kmers;
+    PinnedArr<u32> result_begin, first_ref;
+    PinnedArr<double> global, conf, local;
+    PinnedArr<u8> n_levels;
+    u32 ML = 1;
+    std::atomic<bool> busy{false};  // owned by the pipeline (prep .. emitted)
+};
+
+// The jobs -- above all their page-locked result arrays -- are kept per context between calls of rxh_raxtax: cudaHostAlloc /
+// cudaFreeHost cost milliseconds each and wait for the device, which a caller classifying batch after batch would pay 21 times per
+// call.  rxh_release_buffers() (or the end of the process) frees them.
+struct JobPool {
+    std::mutex mtx;
+    std::unordered_map<rtx_ctx*, std::vector<std::unique_ptr<ChunkJob>>> idle;
+    std::vector<std::unique_ptr<ChunkJob>> take(rtx_ctx* ctx) {
+        std::lock_guard<std::mutex> g(mtx);
+        std::vector<std::unique_ptr<ChunkJob>> v;
+        auto it = idle.find(ctx);
+        if (it != idle.end()) {
+            v = std::move(it->second);
+            idle.erase(it);
+        }
+        while (v.size() < 3) v.emplace_back(new ChunkJob());
+        return v;
+    }
+    void give(rtx_ctx* ctx, std::vector<std::unique_ptr<ChunkJob>> v) {
+        std::lock_guard<std::mutex> g(mtx);
+        idle[ctx] = std::move(v);
+    }
+    void clear() {
+        std::lock_guard<std::mutex> g(mtx);
+        idle.clear();
+    }
+};
+static JobPool& job_pool() {
+    static JobPool* p = new JobPool();  // leaked on purpose: no cudaFreeHost from a static destructor after the CUDA runtime is gone
+    return *p;
+}
+
 struct Worker {
     const Tree& tree;
     const Queries& qs;
@@ -999,173 +1256,473 @@ struct Worker {
     std::atomic<bool> failed{false}, warned{false};
     std::mutex io_mtx{}, err_mtx{};
     std::string err{};
-
-    void run(rtx_ctx* ctx) {
-        try {
-            run_inner(ctx);
-        } catch (const std::exception& e) {
-            failed.store(true);
-            std::lock_guard<std::mutex> g(err_mtx);
-            if (err.empty()) err = e.what();
+    // driver -> emitter
+    std::mutex q_mtx{};
+    std::condition_variable q_cv{}, free_cv{};
+    std::deque<ChunkJob*> ready{};
+    size_t drivers_running = 0;
+    // emitter's helpers
+    struct FormatPart {
+        CharBuf buf;
+        std::vector<size_t> off;  // per query: start of the primary string, start of the tsv string (both NUL-terminated)
+    };
+    std::vector<FormatPart> parts{};
+    std::vector<std::thread> helpers{};
+    std::mutex h_mtx{};
+    std::condition_variable h_cv{}, h_done_cv{};
+    ChunkJob* h_job = nullptr;
+    u64 h_epoch = 0;
+    size_t h_pending = 0;
+    bool h_quit = false;
+    // stage clocks (seconds), printed to stderr at the end of a run when RXH_TIMING is set
+    struct Clock {
+        std::atomic<u64> ns{0};
+        void add(std::chrono::steady_clock::time_point t0) {
+            ns += (u64)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t0).count();
         }
+        double s() const { return (double)ns.load() * 1e-9; }
+    };
+    Clock t_prep{}, t_issue{}, t_collect{}, t_acquire{}, t_format{}, t_send{}, t_emit_wait{};
+    static std::chrono::steady_clock::time_point now() { return std::chrono::steady_clock::now(); }
+
+    void fail(const std::string& what) {
+        failed.store(true);
+        {
+            std::lock_guard<std::mutex> g(err_mtx);
+            if (err.empty()) err = what;
+        }
+        std::lock_guard<std::mutex> g(q_mtx);
+        q_cv.notify_all();
+        free_cv.notify_all();
     }
-    void run_inner(rtx_ctx* ctx) {
-        const u32 ML = rtx_index_max_levels(ctx);
-        if (rtx_index_n_refs(ctx) != tree.num_tips) throw Error("the context's index does not belong to this tree");
-        std::vector<u32> exact_off, exact_ids, first_ref, result_begin;
-        std::vector<u16> n_kmers;
-        std::vector<u8> n_levels;
-        std::vector<double> conf, local, global;
-        std::vector<u32> ex, rep, uniq_first;
-        std::vector<u64> u_off;
-        std::vector<u8> u_codes;
-        std::unordered_map<u64, std::vector<u32>> seen;
-        const bool dedup = getenv("RXH_NO_DEDUP") == nullptr;
-        std::string primary, tsv_out, msg;
-        while (true) {
-            const size_t c0 = next_chunk.fetch_add(1) * chunk_size;
-            if (c0 >= nq || failed.load()) break;
-            const size_t cn = std::min(chunk_size, nq - c0);
-            // Queries with identical sequences (amplicon reads of an abundant taxon) get identical results: the device sees every
-            // distinct sequence of the chunk once, the lines are then written per query label as the reference would (RXH_NO_DEDUP=1
-            // switches this off).  rep[i] = position of query i's sequence among the distinct ones.
-            rep.assign(cn, 0);
-            size_t n_uniq = cn;
-            if (dedup && cn > 1) {
-                seen.clear();
-                uniq_first.clear();
-                for (size_t i = 0; i < cn; ++i) {
-                    const u8* sp = qs.codes.data() + qs.off[c0 + i];
-                    const size_t sl = (size_t)(qs.off[c0 + i + 1] - qs.off[c0 + i]);
-                    auto& bucket = seen[Tree::hash_bytes(sp, sl)];
-                    u32 found = 0xFFFFFFFFu;
-                    for (u32 u : bucket) {
-                        const size_t j = uniq_first[u];
-                        const size_t jl = (size_t)(qs.off[c0 + j + 1] - qs.off[c0 + j]);
-                        if (jl == sl && (sl == 0 || memcmp(qs.codes.data() + qs.off[c0 + j], sp, sl) == 0)) {
-                            found = u;
+
+    // ---- driver side ---------------------------------------------------------------------------------------------------------
+    // de-duplication, exact-match lookup (raxtax.rs:42) and the log lines of raxtax.rs:43-53 for queries [c0, c0 + cn)
+    void prep(ChunkJob& j, size_t c0, size_t cn, FlatDedup& dd, bool dedup) {
+        j.c0 = c0;
+        j.cn = cn;
+        // Queries with identical sequences (amplicon reads of an abundant taxon) get identical results: the device sees every
+        // distinct sequence of the chunk once, the lines are then written per query label as the reference would (RXH_NO_DEDUP=1
+        // switches this off).  rep[i] = position of query i's sequence among the distinct ones.
+        j.rep.resize(cn);
+        j.uniq_first.clear();
+        j.uniq_hash.clear();
+        if (dedup && cn > 1) {
+            dd.reset(cn);
+            for (size_t i = 0; i < cn; ++i) {
+                const u8* sp = qs.codes.data() + qs.off[c0 + i];
+                const size_t sl = (size_t)(qs.off[c0 + i + 1] - qs.off[c0 + i]);
+                const u64 h = Tree::hash_bytes(sp, sl);
+                size_t at = (size_t)(h ^ (h >> 31)) & dd.mask;
+                u32 found = 0xFFFFFFFFu;
+                while (dd.slot[at]) {
+                    if (dd.hash[at] == h) {
+                        const size_t k = j.uniq_first[dd.slot[at] - 1];
+                        const size_t kl = (size_t)(qs.off[c0 + k + 1] - qs.off[c0 + k]);
+                        if (kl == sl && (sl == 0 || memcmp(qs.codes.data() + qs.off[c0 + k], sp, sl) == 0)) {
+                            found = dd.slot[at] - 1;
                             break;
                         }
                     }
-                    if (found == 0xFFFFFFFFu) {
-                        found = (u32)uniq_first.size();
-                        uniq_first.push_back((u32)i);
-                        bucket.push_back(found);
-                    }
-                    rep[i] = found;
+                    at = (at + 1) & dd.mask;
                 }
-                n_uniq = uniq_first.size();
-            }
-            const bool compact = n_uniq < cn;
-            if (compact) {  // the distinct sequences, contiguous
-                u_off.assign(1, 0);
-                u_codes.clear();
-                for (size_t u = 0; u < n_uniq; ++u) {
-                    const size_t q = c0 + uniq_first[u];
-                    u_codes.insert(u_codes.end(), qs.codes.begin() + (ptrdiff_t)qs.off[q], qs.codes.begin() + (ptrdiff_t)qs.off[q + 1]);
-                    u_off.push_back(u_codes.size());
+                if (found == 0xFFFFFFFFu) {
+                    found = (u32)j.uniq_first.size();
+                    j.uniq_first.push_back((u32)i);
+                    j.uniq_hash.push_back(h);
+                    dd.slot[at] = found + 1;
+                    dd.hash[at] = h;
                 }
-            } else {
-                for (size_t i = 0; i < cn; ++i) rep[i] = (u32)i;
+                j.rep[i] = found;
             }
-            exact_off.assign(n_uniq + 1, 0);
-            exact_ids.clear();
-            for (size_t u = 0; u < n_uniq; ++u) {  // tree.sequences.get(query_sequence) (raxtax.rs:42), once per distinct sequence
-                const size_t q = c0 + (compact ? uniq_first[u] : u);
-                tree.exact(qs.codes.data() + qs.off[q], (size_t)(qs.off[q + 1] - qs.off[q]), &ex);
-                exact_ids.insert(exact_ids.end(), ex.begin(), ex.end());
-                exact_off[u + 1] = (u32)exact_ids.size();
+            j.n_uniq = j.uniq_first.size();
+        } else {
+            j.n_uniq = cn;
+        }
+        j.compact = j.n_uniq < cn;
+        if (j.compact) {  // the distinct sequences, contiguous
+            j.u_off.assign(1, 0);
+            j.u_codes.clear();
+            for (size_t u = 0; u < j.n_uniq; ++u) {
+                const size_t q = c0 + j.uniq_first[u];
+                j.u_codes.insert(j.u_codes.end(), qs.codes.begin() + (ptrdiff_t)qs.off[q], qs.codes.begin() + (ptrdiff_t)qs.off[q + 1]);
+                j.u_off.push_back(j.u_codes.size());
             }
-            for (size_t i = 0; i < cn; ++i) {  // the log lines of raxtax.rs:43-53, per query
-                const size_t q = c0 + i;
-                ex.assign(exact_ids.begin() + exact_off[rep[i]], exact_ids.begin() + exact_off[rep[i] + 1]);
-                if (!skip_exact_matches) {  // raxtax.rs:43-53
-                    bool all_equal = true;
-                    std::string first_parent;
-                    for (size_t j = 0; j < ex.size(); ++j) {
-                        const std::string& l = tree.lineages[ex[j]];
-                        if (logger) {
-                            msg = "Exact sequence match for query " + qs.labels[q] + ": " + l;
-                            std::lock_guard<std::mutex> g(io_mtx);
-                            logger(logger_user, 3, msg.c_str());
-                        }
-                        size_t p = l.rfind(',');
-                        if (p == std::string::npos)
-                            throw Error("called `Option::unwrap()` on a `None` value: lineage without ',' (raxtax.rs:49)");
-                        if (j == 0) first_parent.assign(l, 0, p);
-                        else if (l.compare(0, p, first_parent) != 0 || p != first_parent.size()) all_equal = false;
-                    }
-                    if (!all_equal) {
-                        if (logger) {
-                            msg = "Exact matches for " + qs.labels[q] + " differ above the leafs of the lineage tree!";
-                            std::lock_guard<std::mutex> g(io_mtx);
-                            logger(logger_user, 2, msg.c_str());
-                        }
-                        warned.store(true);
-                    }
-                }
-            }
-            rtx_batch batch{};
-            batch.n_queries = (u32)n_uniq;
-            batch.seq_offsets = compact ? u_off.data() : qs.off.data() + c0;
-            batch.seq_codes = compact ? u_codes.data() : qs.codes.data();
-            batch.exact_offsets = exact_off.data();
-            batch.exact_ids = exact_ids.empty() ? nullptr : exact_ids.data();
-            batch.flags = (skip_exact_matches ? RTX_SKIP_EXACT_MATCHES : 0u) | (raw_confidence ? RTX_RAW_CONFIDENCE : 0u);
-            // the device batch API wants seq_codes to be the base the offsets index into
-            rtx_results res{};
-            n_kmers.resize(n_uniq);
-            result_begin.resize(n_uniq + 1);
-            global.resize(n_uniq);
-            size_t cap = std::max<size_t>(first_ref.size(), n_uniq * 8 + 64);
-            while (true) {
-                first_ref.resize(cap);
-                n_levels.resize(cap);
-                conf.resize(cap * ML);
-                local.resize(cap);
-                res = rtx_results{};
-                res.n_kmers = n_kmers.data();
-                res.result_begin = result_begin.data();
-                res.global_signal = global.data();
-                res.result_capacity = cap;
-                res.first_ref = first_ref.data();
-                res.n_levels = n_levels.data();
-                res.confidence = conf.data();
-                res.local_signal = local.data();
-                int rc = rtx_classify_batch(ctx, &batch, &res);
-                if (rc == RTX_ERR_INVALID && res.n_results > cap) {
-                    cap = res.n_results + 64;
-                    continue;
-                }
-                if (rc) throw Error(std::string("rtx_classify_batch: ") + rtx_last_error(ctx));
-                break;
-            }
-            for (size_t i = 0; i < cn; ++i) {  // utils::get_results / get_results_tsv (raxtax.rs:85-87)
-                const size_t q = c0 + i;
-                primary.clear();
-                tsv_out.clear();
-                std::string seq;
-                if (tsv) seq = decompress_sequence(qs.codes.data() + qs.off[q], (size_t)(qs.off[q + 1] - qs.off[q]));
-                const u32 u = rep[i];
-                for (u32 r = result_begin[u]; r < result_begin[u + 1]; ++r) {
-                    ResultView rv{&tree.lineages[first_ref[r]], conf.data() + (size_t)r * ML, n_levels[r], local[r], global[u]};
-                    if (r != result_begin[u]) primary += '\n';
-                    output_string(primary, qs.labels[q], rv);
-                    if (tsv) {
-                        if (r != result_begin[u]) tsv_out += '\n';
-                        tsv_string(tsv_out, qs.labels[q], rv, seq);
-                    }
-                }
-                if (sender) {
+        } else {
+            for (size_t i = 0; i < cn; ++i) j.rep[i] = (u32)i;
+        }
+        j.exact_off.assign(j.n_uniq + 1, 0);
+        j.exact_ids.clear();
+        const bool have_hash = j.uniq_hash.size() == j.n_uniq;
+        for (size_t u = 0; u < j.n_uniq; ++u) {  // tree.sequences.get(query_sequence) (raxtax.rs:42), once per distinct sequence
+            const size_t q = c0 + (have_hash ? j.uniq_first[u] : u);
+            const u8* sp = qs.codes.data() + qs.off[q];
+            const size_t sl = (size_t)(qs.off[q + 1] - qs.off[q]);
+            for (u32 id = tree.exact_head(sp, sl, have_hash ? j.uniq_hash[u] : Tree::hash_bytes(sp, sl)); id != Tree::kNone; id = tree.ex_next[id])
+                j.exact_ids.push_back(id);
+            j.exact_off[u + 1] = (u32)j.exact_ids.size();
+        }
+        if (skip_exact_matches || j.exact_ids.empty()) return;
+        std::string msg, first_parent;
+        for (size_t i = 0; i < cn; ++i) {  // the log lines of raxtax.rs:43-53, per query
+            const size_t q = c0 + i;
+            const u32 e0 = j.exact_off[j.rep[i]], e1 = j.exact_off[j.rep[i] + 1];
+            bool all_equal = true;
+            for (u32 e = e0; e < e1; ++e) {
+                const std::string& l = tree.lineages[j.exact_ids[e]];
+                if (logger) {
+                    msg = "Exact sequence match for query " + qs.labels[q] + ": " + l;
                     std::lock_guard<std::mutex> g(io_mtx);
-                    if (sender(sender_user, qs.labels[q].c_str(), primary.c_str(), tsv ? tsv_out.c_str() : nullptr) != 0)
-                        throw Error("sending on a disconnected channel (raxtax.rs:87)");
+                    logger(logger_user, 3, msg.c_str());
                 }
+                const size_t p = l.rfind(',');
+                if (p == std::string::npos) throw Error("called `Option::unwrap()` on a `None` value: lineage without ',' (raxtax.rs:49)");
+                if (e == e0) first_parent.assign(l, 0, p);
+                else if (l.compare(0, p, first_parent) != 0 || p != first_parent.size()) all_equal = false;
+            }
+            if (!all_equal) {
+                if (logger) {
+                    msg = "Exact matches for " + qs.labels[q] + " differ above the leafs of the lineage tree!";
+                    std::lock_guard<std::mutex> g(io_mtx);
+                    logger(logger_user, 2, msg.c_str());
+                }
+                warned.store(true);
             }
         }
     }
+
+    static bool is_oom(rtx_ctx* ctx) { return strstr(rtx_last_error(ctx), "out of memory") != nullptr; }
+
+    // H2D + all kernels of the job, queued behind whatever the device is doing; returns false when device memory ran out
+    bool issue(rtx_ctx* ctx, ChunkJob& j, int dev_slot) {
+        rtx_batch batch{};
+        batch.n_queries = (u32)j.n_uniq;
+        batch.seq_offsets = j.compact ? j.u_off.data() : qs.off.data() + j.c0;
+        batch.seq_codes = j.compact ? j.u_codes.data() : qs.codes.data();
+        batch.exact_offsets = j.exact_off.data();
+        batch.exact_ids = j.exact_ids.empty() ? nullptr : j.exact_ids.data();
+        batch.flags = (skip_exact_matches ? RTX_SKIP_EXACT_MATCHES : 0u) | (raw_confidence ? RTX_RAW_CONFIDENCE : 0u);
+        j.dev_slot = dev_slot;
+        if (rtx_batch_slot(ctx, dev_slot)) throw Error(std::string("rtx_batch_slot: ") + rtx_last_error(ctx));
+        int rc = rtx_batch_upload(ctx, &batch);
+        if (rc == RTX_ERR_CUDA && is_oom(ctx)) return false;
+        if (rc) throw Error(std::string("rtx_batch_upload: ") + rtx_last_error(ctx));
+        rc = rtx_batch_run(ctx);
+        if (rc == RTX_ERR_CUDA && is_oom(ctx)) return false;
+        if (rc) throw Error(std::string("rtx_batch_run: ") + rtx_last_error(ctx));
+        return true;
+    }
+
+    // waits for the job's kernels, D2H into its page-locked arrays.  The result lines stay on the device until they fit: a too
+    // small capacity only repeats the copy, never the kernels.
+    void collect(rtx_ctx* ctx, ChunkJob& j) {
+        if (rtx_batch_slot(ctx, j.dev_slot)) throw Error(std::string("rtx_batch_slot: ") + rtx_last_error(ctx));
+        const u32 ML = rtx_index_max_levels(ctx);
+        j.ML = ML;
+        j.n_kmers.ensure(j.n_uniq);
+        j.result_begin.ensure(j.n_uniq + 1);
+        j.global.ensure(j.n_uniq);
+        size_t cap = std::max<size_t>(j.first_ref.cap, j.n_uniq * 8 + 64);
+        while (true) {
+            j.first_ref.ensure(cap);
+            j.n_levels.ensure(cap);
+            j.conf.ensure(cap * ML);
+            j.local.ensure(cap);
+            cap = std::min(std::min(j.first_ref.cap, j.n_levels.cap), std::min(j.conf.cap / ML, j.local.cap));
+            rtx_results res{};
+            res.n_kmers = j.n_kmers.p;
+            res.result_begin = j.result_begin.p;
+            res.global_signal = j.global.p;
+            res.result_capacity = cap;
+            res.first_ref = j.first_ref.p;
+            res.n_levels = j.n_levels.p;
+            res.confidence = j.conf.p;
+            res.local_signal = j.local.p;
+            const int rc = rtx_batch_download(ctx, &res);
+            if (rc == RTX_ERR_INVALID && res.n_results > cap) {
+                cap = res.n_results + 64;
+                continue;
+            }
+            if (rc) throw Error(std::string("rtx_batch_download: ") + rtx_last_error(ctx));
+            break;
+        }
+    }
+
+    void hand_over(ChunkJob* j) {
+        std::lock_guard<std::mutex> g(q_mtx);
+        ready.push_back(j);
+        q_cv.notify_all();
+    }
+
+    ChunkJob* acquire(std::vector<std::unique_ptr<ChunkJob>>& jobs) {
+        std::unique_lock<std::mutex> g(q_mtx);
+        while (true) {
+            for (auto& j : jobs)
+                if (!j->busy.load()) {
+                    j->busy.store(true);
+                    return j.get();
+                }
+            if (failed.load()) return nullptr;
+            free_cv.wait(g);
+        }
+    }
+
+    void drive(rtx_ctx* ctx) {
+        try {
+            drive_inner(ctx);
+        } catch (const std::exception& e) {
+            fail(e.what());
+        }
+        std::lock_guard<std::mutex> g(q_mtx);
+        --drivers_running;
+        q_cv.notify_all();
+    }
+
+    void drive_inner(rtx_ctx* ctx) {
+        if (rtx_index_n_refs(ctx) != tree.num_tips) throw Error("the context's index does not belong to this tree");
+        const bool dedup = getenv("RXH_NO_DEDUP") == nullptr;
+        std::vector<std::unique_ptr<ChunkJob>> jobs = job_pool().take(ctx);
+        struct Return {
+            rtx_ctx* ctx;
+            std::vector<std::unique_ptr<ChunkJob>>& jobs;
+            ~Return() { job_pool().give(ctx, std::move(jobs)); }
+        } ret{ctx, jobs};
+        FlatDedup dd;
+        ChunkJob* inflight = nullptr;
+        int dev_slot = 0;
+        std::vector<std::pair<size_t, size_t>> todo;  // ranges of this thread's current chunk (split further when memory runs out)
+        while (true) {
+            if (todo.empty()) {
+                const size_t c0 = next_chunk.fetch_add(1) * chunk_size;
+                if (c0 >= nq || failed.load()) break;
+                todo.emplace_back(c0, std::min(chunk_size, nq - c0));
+            }
+            const std::pair<size_t, size_t> range = todo.back();
+            todo.pop_back();
+            auto t0 = now();
+            ChunkJob* j = acquire(jobs);
+            t_acquire.add(t0);
+            if (!j) break;
+            t0 = now();
+            prep(*j, range.first, range.second, dd, dedup);
+            t_prep.add(t0);
+            t0 = now();
+            const bool issued = issue(ctx, *j, dev_slot);
+            t_issue.add(t0);
+            if (!issued) {
+                // the batch does not fit the device next to the index: drain, then classify it in two halves
+                j->busy.store(false);
+                if (inflight) {
+                    collect(ctx, *inflight);
+                    hand_over(inflight);
+                    inflight = nullptr;
+                }
+                if (range.second <= 1) throw Error(std::string("not even one query fits the device memory: ") + rtx_last_error(ctx));
+                const size_t h = range.second / 2;
+                todo.emplace_back(range.first + h, range.second - h);
+                todo.emplace_back(range.first, h);
+                continue;
+            }
+            dev_slot ^= 1;
+            if (inflight) {
+                t0 = now();
+                collect(ctx, *inflight);
+                t_collect.add(t0);
+                hand_over(inflight);
+            }
+            inflight = j;
+        }
+        if (inflight) {
+            auto t0 = now();
+            collect(ctx, *inflight);
+            t_collect.add(t0);
+            hand_over(inflight);
+        }
+        // the jobs (and their page-locked arrays) must outlive the emitter's use of them
+        std::unique_lock<std::mutex> g(q_mtx);
+        while (true) {
+            bool any = false;
+            for (auto& j : jobs) any |= j->busy.load();
+            if (!any) break;
+            free_cv.wait(g);
+        }
+    }
+
+    // ---- emitter side --------------------------------------------------------------------------------------------------------
+    // utils::get_results / get_results_tsv (raxtax.rs:85-87) for the queries [i0, i1) of a job
+    void format_range(const ChunkJob& j, size_t i0, size_t i1, FormatPart& out) const {
+        out.buf.n = 0;
+        out.off.clear();
+        const u32 ML = j.ML;
+        std::string seq;
+        for (size_t i = i0; i < i1; ++i) {
+            const size_t q = j.c0 + i;
+            const u32 u = j.rep[i];
+            const u32 r0 = j.result_begin.p[u], r1 = j.result_begin.p[u + 1];
+            out.off.push_back(out.buf.n);
+            for (u32 r = r0; r < r1; ++r) {
+                const ResultView rv{&tree.lineages[j.first_ref.p[r]], j.conf.p + (size_t)r * ML, j.n_levels.p[r], j.local.p[r], j.global.p[u]};
+                if (r != r0) out.buf.put('\n');
+                output_line(out.buf, qs.labels[q], rv);
+            }
+            out.buf.put('\0');
+            out.off.push_back(out.buf.n);
+            if (tsv) {
+                seq = decompress_sequence(qs.codes.data() + qs.off[q], (size_t)(qs.off[q + 1] - qs.off[q]));
+                for (u32 r = r0; r < r1; ++r) {
+                    const ResultView rv{&tree.lineages[j.first_ref.p[r]], j.conf.p + (size_t)r * ML, j.n_levels.p[r], j.local.p[r], j.global.p[u]};
+                    if (r != r0) out.buf.put('\n');
+                    tsv_line(out.buf, qs.labels[q], rv, seq);
+                }
+                out.buf.put('\0');
+            }
+        }
+    }
+    static void part_range(size_t cn, size_t n_parts, size_t k, size_t* i0, size_t* i1) {
+        *i0 = cn * k / n_parts;
+        *i1 = cn * (k + 1) / n_parts;
+    }
+    void helper_main(size_t k) {
+        u64 seen = 0;
+        while (true) {
+            ChunkJob* j;
+            {
+                std::unique_lock<std::mutex> g(h_mtx);
+                h_cv.wait(g, [&] { return h_quit || h_epoch != seen; });
+                if (h_quit) return;
+                seen = h_epoch;
+                j = h_job;
+            }
+            size_t i0, i1;
+            part_range(j->cn, parts.size(), k, &i0, &i1);
+            try {
+                format_range(*j, i0, i1, parts[k]);
+            } catch (const std::exception& e) {
+                fail(e.what());
+            }
+            std::lock_guard<std::mutex> g(h_mtx);
+            if (--h_pending == 0) h_done_cv.notify_all();
+        }
+    }
+    void emit(ChunkJob& j) {
+        const size_t n_parts = parts.size();
+        if (n_parts > 1) {
+            std::lock_guard<std::mutex> g(h_mtx);
+            h_job = &j;
+            h_pending = n_parts - 1;
+            ++h_epoch;
+            h_cv.notify_all();
+        }
+        size_t i0, i1;
+        auto t0 = now();
+        part_range(j.cn, n_parts, 0, &i0, &i1);
+        format_range(j, i0, i1, parts[0]);
+        if (n_parts > 1) {
+            std::unique_lock<std::mutex> g(h_mtx);
+            h_done_cv.wait(g, [&] { return h_pending == 0; });
+        }
+        t_format.add(t0);
+        if (!sender || failed.load()) return;
+        t0 = now();
+        struct SendClock {
+            Clock& c;
+            std::chrono::steady_clock::time_point t0;
+            ~SendClock() { c.add(t0); }
+        } sc{t_send, t0};
+        std::lock_guard<std::mutex> g(io_mtx);
+        for (size_t k = 0; k < n_parts; ++k) {
+            part_range(j.cn, n_parts, k, &i0, &i1);
+            const FormatPart& fp = parts[k];
+            const char* base = fp.buf.v.data();
+            for (size_t i = i0; i < i1; ++i) {
+                const size_t o = (i - i0) * 2;
+                if (sender(sender_user, qs.labels[j.c0 + i].c_str(), base + fp.off[o], tsv ? base + fp.off[o + 1] : nullptr) != 0)
+                    throw Error("sending on a disconnected channel (raxtax.rs:87)");
+            }
+        }
+    }
+
+    void run(rtx_ctx* const* ctxs, size_t n_ctx) {
+        size_t n_helpers = 0;
+        if (const char* e = getenv("RXH_FORMAT_THREADS")) n_helpers = (size_t)std::max(0, atoi(e) - 1);
+        else n_helpers = std::min<size_t>(3, std::max<size_t>(1, std::thread::hardware_concurrency() / 8));
+        if (nq < 512) n_helpers = 0;
+        parts.resize(n_helpers + 1);
+        for (size_t k = 1; k <= n_helpers; ++k) helpers.emplace_back([this, k] { helper_main(k); });
+        drivers_running = n_ctx;
+        std::vector<std::thread> drivers;
+        for (size_t i = 0; i < n_ctx; ++i) drivers.emplace_back([this, ctx = ctxs[i]] { drive(ctx); });
+        while (true) {  // the calling thread is the writer side of the channel (main.rs:126-136)
+            ChunkJob* j = nullptr;
+            {
+                auto t0 = now();
+                std::unique_lock<std::mutex> g(q_mtx);
+                q_cv.wait(g, [&] { return !ready.empty() || drivers_running == 0; });
+                t_emit_wait.add(t0);
+                if (ready.empty()) break;
+                j = ready.front();
+                ready.pop_front();
+            }
+            if (!failed.load()) {
+                try {
+                    emit(*j);
+                } catch (const std::exception& e) {
+                    fail(e.what());
+                }
+            }
+            std::lock_guard<std::mutex> g(q_mtx);
+            j->busy.store(false);
+            free_cv.notify_all();
+        }
+        for (auto& t : drivers) t.join();
+        {
+            std::lock_guard<std::mutex> g(h_mtx);
+            h_quit = true;
+            h_cv.notify_all();
+        }
+        for (auto& t : helpers) t.join();
+        if (getenv("RXH_TIMING"))
+            fprintf(stderr, "[rxh raxtax] %zu queries, %zu ctx, chunk %zu, %zu format threads | drivers: acquire %.4f prep %.4f issue %.4f collect %.4f | "
+                            "emitter: wait %.4f format %.4f send %.4f s\n", nq, n_ctx, chunk_size, parts.size(), t_acquire.s(), t_prep.s(), t_issue.s(),
+                    t_collect.s(), t_emit_wait.s(), t_format.s(), t_send.s());
+    }
 };
 }  // namespace
+
+// sender / logger that only count: what a benchmark hands to rxh_raxtax so that formatting, ordering and the per-query hand-off are
+// all inside the timed region without a file system or an interpreter behind them
+RXH_API int rxh_count_sender(void* user, const char* query_label, const char* primary_results, const char* tsv_results) {
+    rxh_counts* c = (rxh_counts*)user;
+    if (!c) return 0;
+    c->queries += 1;
+    c->label_bytes += strlen(query_label);
+    const size_t n = strlen(primary_results);
+    c->primary_bytes += n;
+    uint64_t lines = n ? 1 : 0;
+    for (const char* p = primary_results; (p = (const char*)memchr(p, '\n', (size_t)(primary_results + n - p))) != nullptr; ++p) ++lines;
+    c->lines += lines;
+    c->checksum += Tree::hash_bytes((const u8*)primary_results, n);  // a sum of per-query hashes: independent of the arrival order
+    if (tsv_results) c->tsv_bytes += strlen(tsv_results);
+    return 0;
+}
+RXH_API void rxh_release_buffers(void) { job_pool().clear(); }
+
+RXH_API size_t rxh_format_fixed(double value, int precision, char* out, size_t cap) {
+    char buf[448];
+    if (precision < 0 || precision > 17) return 0;
+    const size_t n = (size_t)(put_fixed(buf, value, precision) - buf);
+    if (n + 1 > cap) return 0;
+    memcpy(out, buf, n);
+    out[n] = '\0';
+    return n;
+}
+RXH_API void rxh_count_logger(void* user, int level, const char* message) {
+    rxh_counts* c = (rxh_counts*)user;
+    if (!c) return;
+    c->log_lines += 1;
+    c->log_bytes += strlen(message);
+    if (level == 2) c->warn_lines += 1;
+}
 
 RXH_API int rxh_raxtax_multi(rtx_ctx* const* ctxs, size_t n_ctx, const rxh_queries* queries, const rxh_tree* tree_h, int skip_exact_matches,
                              int raw_confidence, size_t chunk_size, rxh_sender sender, void* sender_user, int tsv, rxh_logger logger,
@@ -1176,16 +1733,14 @@ RXH_API int rxh_raxtax_multi(rtx_ctx* const* ctxs, size_t n_ctx, const rxh_queri
         return -1;
     }
     const size_t nq = queries->q->size();
-    if (chunk_size == 0) {  // one chunk per context and pass when there is one context; else ~8 chunks per context, at least 4096 queries
-        chunk_size = n_ctx == 1 ? std::max<size_t>(nq, 1) : std::max<size_t>(4096, (nq + n_ctx * 8 - 1) / (n_ctx * 8));
+    if (chunk_size == 0) {
+        // ~4 chunks per context so that the pipeline (upload | kernels | formatting) has something to overlap and results, the
+        // progress file with them, appear while the run is going; bounded above so that the per-batch device arrays (~15 KB per
+        // 1.5 kb query) stay small next to the index, and below so that the index is not re-read from HBM for a handful of queries
+        chunk_size = std::min<size_t>(32768, std::max<size_t>(2048, (nq + n_ctx * 4 - 1) / (n_ctx * 4)));
     }
     Worker w{*tree_h->t, *queries->q, nq, chunk_size, skip_exact_matches, raw_confidence, tsv, sender, sender_user, logger, logger_user};
-    if (n_ctx == 1) w.run(ctxs[0]);
-    else {
-        std::vector<std::thread> th;
-        for (size_t i = 0; i < n_ctx; ++i) th.emplace_back([&w, ctx = ctxs[i]] { w.run(ctx); });
-        for (auto& t : th) t.join();
-    }
+    w.run(ctxs, n_ctx);
     if (warnings) *warnings = w.warned.load() ? 1 : 0;
     if (w.failed.load()) {
         g_err = w.err;

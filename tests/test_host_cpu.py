@@ -31,7 +31,7 @@ def test_device_abi_exports_every_declared_symbol():
     for n in names:
         assert hasattr(lib, n), n
     lib.rtx_abi_version.restype = C.c_int
-    assert lib.rtx_abi_version() == 2
+    assert lib.rtx_abi_version() == 3
 
 
 def test_host_abi_exports_every_declared_symbol():
@@ -257,3 +257,16 @@ def test_cli_only_db_writes_the_reference_database_and_checkpoint(tmp_path):
     ao, ai = a.csr()
     bo, bi = b.csr()
     assert np.array_equal(ao, bo) and np.array_equal(ai, bi)
+
+
+def test_fixed_point_formatting_matches_libc():
+    """rxh_format_fixed (the fast path behind every confidence and signal of a result line, lineage.rs:17-30) prints what "%.Nf"
+    prints: the exact binary value rounded to nearest, ties to even -- Rust's `{:.N}`."""
+    rng = np.random.default_rng(7)
+    vals = [0.0, 1.0, 0.125, 0.375, 0.005, 0.015, 0.025, 0.995, 0.999995, 0.0000049999, 1.41421356, 0.5, 0.25, 1e-9, 123456.789, -0.0, -1.5,
+            float("inf"), float("nan"), 1e12, 0.004999999999999999, 0.105, 2.675, 0.000005, 0.000015, 999999999.999999]
+    r = rng.random(20000)
+    vals += list(r) + list(np.round(r, 2)) + list(np.round(r, 5) + 0.5e-5) + list(np.round(r, 2) + 0.005) + list(r * 1.5)
+    for v in vals:
+        for prec in (2, 5):
+            assert capi.format_fixed(v, prec) == "%.*f" % (prec, v), (v, prec)
