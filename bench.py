@@ -254,6 +254,7 @@ def main():
     ap.add_argument("--queries", type=int, default=0, help="queries of the whole job (0 = the config's own number; c5 default: a bounded 131072)")
     ap.add_argument("--cpu-sample", type=int, default=0, help="queries in the bounded CPU sample (0 = sized for ~20 s / ~6 s per step)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-sharded", action="store_true", help="skip the reference-sharded check leg of a multi-GPU run")
     ap.add_argument("--sub-batch", type=int, default=0, help="RTX_OPT_SUB_BATCH for the timed legs (0 = library default)")
     ap.add_argument("--pipeline", type=int, default=-1, help="RTX_OPT_PIPELINE for the timed legs (-1 = library default)")
     ap.add_argument("--chunk", type=int, default=0, help="chunk_size of rxh_raxtax in the e2e leg (0 = the driver's default)")
@@ -530,6 +531,17 @@ def main():
             "e2e_device_abi": {"value": q_total * reps_a / abi_s, "unit": UNIT, "steps": reps_a, "h2d_bytes_per_step": prof_abi["h2d_bytes"] // reps_a,
                                "d2h_bytes_per_step": prof_abi["d2h_bytes"] // reps_a, "through": "rtx_classify_batch, page-locked host buffers"},
             "gpu_launches": int(launches), "roofline": roofline}
+
+    # ---- reference-sharded check (N > 1): the same references cut into N shards, NCCL collectives inside the device library ------
+    if world > 1 and not args.no_sharded:
+        from raxtax_b200 import bench_sharded
+
+        n_sh = min(16384, q_per_rank)  # rank 0's slice starts at query 0: its unsharded results above are the expected lines
+        rec = bench_sharded.sharded_leg(ctx, tree, ds, n_sh, rank, world, max(1, min(args.steps, 5)), skip, dist, barrier, max_over_ranks,
+                                        expect=res if rank == 0 else None)
+        if rank == 0:
+            assert rec["identical_to_unsharded"], "reference-sharded run differs from the unsharded one"
+        line["sharded"] = rec
 
     # ---- CPU baseline beside it (rank 0, N = 1 only) -----------------------------------------------------------------
     if world == 1 and not args.no_cpu_baseline:

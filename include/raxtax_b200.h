@@ -75,6 +75,7 @@ const char* rtx_last_error(const rtx_ctx* ctx); /* ctx may be NULL: error of the
 int rtx_ctx_set_option(rtx_ctx* ctx, int option, int64_t value);
 /* the CUDA stream (cudaStream_t) all of this context's work is issued on; lets a caller record its own events */
 void* rtx_ctx_stream(rtx_ctx* ctx);
+int rtx_ctx_device(const rtx_ctx* ctx); /* the CUDA device ordinal the context was created on */
 int rtx_ctx_synchronize(rtx_ctx* ctx);
 /* Page-locked host memory for batch inputs and result arrays.  Optional: every call accepts ordinary memory (results then pass
  * through the context's own pinned staging arena and one memcpy); buffers from rtx_host_alloc -- or registered by the caller with
@@ -217,13 +218,37 @@ int rtx_shard_phase3(rtx_ctx* ctx);
 int rtx_shard_exchange_hist_local(rtx_ctx* const* ctxs, uint32_t n);
 int rtx_shard_exchange_records_local(rtx_ctx* const* ctxs, uint32_t n);
 
+/* ---- reference-sharded mode over NCCL, inside the library ------------------------------------------------
+ * One rank = one context = one GPU (processes under torchrun / MPI, or threads of one process).  rtx_comm_unique_id (any one rank;
+ * the 128 bytes reach the others out of band) + rtx_comm_init on every rank build the communicator; the index is uploaded as
+ * shard `rank` of `nranks` (rtx_index_desc.n_shards / shard_rank / shard_cuts).  Then per batch, on EVERY rank with the same batch:
+ *   rtx_batch_upload
+ *   rtx_shard_run     k-mers, then per sub-batch: local hit counts | ncclAllReduce(ncclUint32, ncclSum) of the sub-batch's histogram
+ *                     rows (in place; the exchange prob.rs:62-73 forces: the product over ALL references) | P(count), local prefixes,
+ *                     straddler records | ncclAllGather of the records | combine + tree walk.  Two scratch slots: the collectives and
+ *                     the tail kernels of sub-batch i run on a second stream under the hit counting of sub-batch i+1.
+ *   rtx_shard_gather  the ranks' result lines -> root (ncclSend / ncclRecv), merged on the root's device in the order of
+ *                     lineage.rs:93, then the one-exact-match override (raxtax.rs:73-84)
+ *   rtx_batch_download  root: the final lines of the batch, exactly what an unsharded context returns; other ranks: no lines
+ * rtx_shard_classify = the four in one call.  libnccl.so.2 is bound at run time (the copy already loaded into the process wins);
+ * without it rtx_comm_* fail with RTX_ERR_UNSUPPORTED and everything else works. */
+#define RTX_COMM_UNIQUE_ID_BYTES 128
+int rtx_comm_unique_id(void* out /* RTX_COMM_UNIQUE_ID_BYTES */);
+int rtx_comm_init(rtx_ctx* ctx, const void* unique_id, int rank, int nranks);
+int rtx_comm_destroy(rtx_ctx* ctx);
+int rtx_shard_run(rtx_ctx* ctx);
+int rtx_shard_gather(rtx_ctx* ctx, int root);
+int rtx_shard_classify(rtx_ctx* ctx, const rtx_batch* batch, rtx_results* results, int root);
+
 /* ---- measurement ---------------------------------------------------------------------------------------- */
 typedef struct {
     uint64_t launches;   /* kernel launches since the last reset */
     double total_ms;     /* sum of CUDA-event durations (only with RTX_OPT_PROFILE) */
 } rtx_kernel_stat;
 
-enum { RTX_K_KMERS = 0, RTX_K_HITCOUNT = 1, RTX_K_FIXUP = 2, RTX_K_PROB = 3, RTX_K_INDEX = 4, RTX_K_WALK = 5, RTX_K_PREFIX = 6, RTX_K_COUNT = 7 };
+enum { RTX_K_KMERS = 0, RTX_K_HITCOUNT = 1, RTX_K_FIXUP = 2, RTX_K_PROB = 3, RTX_K_INDEX = 4, RTX_K_WALK = 5, RTX_K_PREFIX = 6,
+       RTX_K_ALLREDUCE = 7 /* histogram all-reduce */, RTX_K_ALLGATHER = 8 /* straddler records, result offsets */,
+       RTX_K_SHARD = 9 /* record / combine / merge kernels */, RTX_K_GATHER = 10 /* result lines -> root */, RTX_K_COUNT = 11 };
 
 typedef struct {
     rtx_kernel_stat kernel[RTX_K_COUNT];
@@ -232,6 +257,7 @@ typedef struct {
     uint64_t bitrow_bytes;     /* bytes of bit rows + count vectors the hit-count launches had to move */
     uint64_t csr_equiv_bytes;  /* 4*hits + 2*N per query: the reference data structure's traffic */
     uint64_t h2d_bytes, d2h_bytes;
+    uint64_t allreduce_bytes, allgather_bytes, gather_bytes; /* payload of the collectives (reference-sharded mode over NCCL) */
 } rtx_profile;
 
 int rtx_profile_reset(rtx_ctx* ctx);

@@ -18,7 +18,7 @@ DEVICE_LIB = os.path.join(PKG, "libraxtax_b200.so")
 HOST_LIB = os.path.join(PKG, "libraxtax_host.so")
 CLI_BIN = os.path.join(PKG, "raxtax")
 
-NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC", "-ldl",
               "-shared"]
 
 

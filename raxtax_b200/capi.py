@@ -23,14 +23,15 @@ RTX_SKIP_EXACT_MATCHES, RTX_RAW_CONFIDENCE = 1, 2
 RTX_HITCOUNT_BITROWS, RTX_HITCOUNT_CSR = 0, 1
 RTX_OPT_HITCOUNT_VARIANT, RTX_OPT_SUB_BATCH, RTX_OPT_KEEP_CSR, RTX_OPT_PROFILE, RTX_OPT_HITCOUNT_TUNE, RTX_OPT_HITCOUNT_MAX_TILES = 1, 2, 3, 4, 5, 6
 RTX_OPT_HITCOUNT_GROUP, RTX_OPT_HITCOUNT_CHUNKS, RTX_OPT_WALK_VARIANT, RTX_OPT_WALK_LOG_CAP, RTX_OPT_PIPELINE = 7, 8, 9, 10, 11
-KERNEL_NAMES = ["kmers", "hitcount", "fixup", "prob", "index", "walk", "prefix"]
+KERNEL_NAMES = ["kmers", "hitcount", "fixup", "prob", "index", "walk", "prefix", "allreduce", "allgather", "shard", "gather"]
 
 # every symbol include/raxtax_b200.h declares
 DEVICE_SYMBOLS = [
-    "rtx_abi_version", "rtx_ctx_create", "rtx_ctx_destroy", "rtx_last_error", "rtx_ctx_set_option", "rtx_ctx_stream",
+    "rtx_abi_version", "rtx_ctx_create", "rtx_ctx_destroy", "rtx_last_error", "rtx_ctx_set_option", "rtx_ctx_stream", "rtx_ctx_device",
     "rtx_ctx_synchronize", "rtx_host_alloc", "rtx_host_free", "rtx_index_upload", "rtx_index_n_refs", "rtx_index_shard_refs", "rtx_index_max_levels", "rtx_batch_sub_batch",
     "rtx_index_device_bytes", "rtx_index_bitrow_bytes", "rtx_hitcount_kernel_name", "rtx_classify_batch", "rtx_batch_upload", "rtx_batch_run", "rtx_batch_download", "rtx_batch_slot",
     "rtx_shard_phase1", "rtx_shard_hist_buffer", "rtx_shard_phase2", "rtx_shard_records_buffers", "rtx_shard_phase3", "rtx_shard_exchange_hist_local", "rtx_shard_exchange_records_local",
+    "rtx_comm_unique_id", "rtx_comm_init", "rtx_comm_destroy", "rtx_shard_run", "rtx_shard_gather", "rtx_shard_classify",
     "rtx_profile_reset", "rtx_profile_get",
 ]
 # every symbol include/raxtax_host.h declares
@@ -65,8 +66,9 @@ class KernelStat(C.Structure):
 
 
 class Profile(C.Structure):
-    _fields_ = [("kernel", KernelStat * 7), ("queries", C.c_uint64), ("hits", C.c_uint64), ("bitrow_bytes", C.c_uint64),
-                ("csr_equiv_bytes", C.c_uint64), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64)]
+    _fields_ = [("kernel", KernelStat * 11), ("queries", C.c_uint64), ("hits", C.c_uint64), ("bitrow_bytes", C.c_uint64),
+                ("csr_equiv_bytes", C.c_uint64), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64), ("allreduce_bytes", C.c_uint64),
+                ("allgather_bytes", C.c_uint64), ("gather_bytes", C.c_uint64)]
 
 
 SENDER = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_char_p, C.c_char_p, C.c_char_p)
@@ -122,6 +124,12 @@ def device_lib():
         getattr(L, f).argtypes = [C.c_void_p]
     L.rtx_shard_hist_buffer.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]
     L.rtx_shard_records_buffers.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64), C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]
+    L.rtx_comm_unique_id.argtypes = [C.c_char_p]
+    L.rtx_comm_init.argtypes = [C.c_void_p, C.c_char_p, C.c_int, C.c_int]
+    L.rtx_comm_destroy.argtypes = [C.c_void_p]
+    L.rtx_shard_run.argtypes = [C.c_void_p]
+    L.rtx_shard_gather.argtypes = [C.c_void_p, C.c_int]
+    L.rtx_shard_classify.argtypes = [C.c_void_p, C.POINTER(Batch), C.POINTER(ResultsStruct), C.c_int]
     L.rtx_shard_exchange_hist_local.argtypes = [C.POINTER(C.c_void_p), C.c_uint32]
     L.rtx_shard_exchange_records_local.argtypes = [C.POINTER(C.c_void_p), C.c_uint32]
     L.rtx_profile_get.argtypes = [C.c_void_p, C.POINTER(Profile)]
@@ -344,6 +352,27 @@ class Context:
         self._check(device_lib().rtx_shard_records_buffers(self._h, C.byref(sp), C.byref(sb), C.byref(rp), C.byref(rb)))
         return (sp.value or 0, int(sb.value)), (rp.value or 0, int(rb.value))
 
+    # ---- reference-sharded mode over NCCL inside the library --------------------------------------------------
+    @staticmethod
+    def comm_unique_id() -> bytes:
+        buf = C.create_string_buffer(128)
+        rc = device_lib().rtx_comm_unique_id(buf)
+        if rc != 0:
+            raise RtxError(rc, device_lib().rtx_last_error(None).decode())
+        return buf.raw
+
+    def comm_init(self, unique_id: bytes, rank: int, nranks: int):
+        self._check(device_lib().rtx_comm_init(self._h, unique_id, int(rank), int(nranks)))
+
+    def comm_destroy(self):
+        self._check(device_lib().rtx_comm_destroy(self._h))
+
+    def shard_run(self):
+        self._check(device_lib().rtx_shard_run(self._h))
+
+    def shard_gather(self, root: int = 0):
+        self._check(device_lib().rtx_shard_gather(self._h, int(root)))
+
     # ---- batches -------------------------------------------------------------------------------------------
     def _make_batch(self, seq_off, codes, exact_off, exact_ids, flags):
         b = Batch()
@@ -424,8 +453,10 @@ class Context:
         out.confidence, out.local_signal = out.confidence[:n], out.local_signal[:n]
         return out
 
-    def classify(self, seq_off, codes, exact_off=None, exact_ids=None, skip_exact=False, raw_conf=False, taps=(), out=None) -> ClassifyOutput:
-        """rtx_classify_batch: H2D + kernels + D2H in one call.  out = pinned_results(...) reuses page-locked result buffers."""
+    def classify(self, seq_off, codes, exact_off=None, exact_ids=None, skip_exact=False, raw_conf=False, taps=(), out=None, shard_root=None) -> ClassifyOutput:
+        """rtx_classify_batch: H2D + kernels + D2H in one call.  out = pinned_results(...) reuses page-locked result buffers.
+        shard_root = r: rtx_shard_classify instead (reference-sharded mode over NCCL, every rank calls it with the same batch; the
+        final lines come back on rank r, nothing on the others)."""
         L = device_lib()
         flags = (RTX_SKIP_EXACT_MATCHES if skip_exact else 0) | (RTX_RAW_CONFIDENCE if raw_conf else 0)
         b, keep = self._make_batch(seq_off, codes, exact_off, exact_ids, flags)
@@ -436,7 +467,14 @@ class Context:
         reuse = out
         while True:
             out, r = self._alloc_results(nq, cap, max_len, taps, reuse)
-            rc = L.rtx_classify_batch(self._h, C.byref(b), C.byref(r))
+            if shard_root is None:
+                rc = L.rtx_classify_batch(self._h, C.byref(b), C.byref(r))
+            else:
+                rc = L.rtx_shard_classify(self._h, C.byref(b), C.byref(r), int(shard_root))
+                if rc == RTX_ERR_INVALID and r.n_results > r.result_capacity:  # the batch is resident and merged: only the copy is repeated
+                    cap = int(r.n_results) + 64
+                    out, r = self._alloc_results(nq, cap, max_len, taps, None)
+                    rc = L.rtx_batch_download(self._h, C.byref(r))
             if rc == RTX_ERR_INVALID and r.n_results > r.result_capacity and reuse is not None:
                 raise ValueError(f"pinned result buffers too small: {int(r.n_results)} result lines, capacity {int(r.result_capacity)}")
             if rc == RTX_ERR_INVALID and r.n_results > cap:
@@ -480,7 +518,8 @@ class Context:
         self._check(device_lib().rtx_profile_get(self._h, C.byref(p)))
         d = {n: dict(launches=int(p.kernel[i].launches), total_ms=float(p.kernel[i].total_ms)) for i, n in enumerate(KERNEL_NAMES)}
         d.update(queries=int(p.queries), hits=int(p.hits), bitrow_bytes=int(p.bitrow_bytes), csr_equiv_bytes=int(p.csr_equiv_bytes),
-                 h2d_bytes=int(p.h2d_bytes), d2h_bytes=int(p.d2h_bytes))
+                 h2d_bytes=int(p.h2d_bytes), d2h_bytes=int(p.d2h_bytes), allreduce_bytes=int(p.allreduce_bytes),
+                 allgather_bytes=int(p.allgather_bytes), gather_bytes=int(p.gather_bytes))
         return d
 
 

@@ -1831,6 +1831,103 @@ __global__ void __launch_bounds__(256) result_gather_kernel(ResultPool pool, con
 }
 
 // =========================================================================================================
+// Reference-sharded mode, on the root after the result gather: per query the lines of ALL ranks -- each rank's already in the order of
+// lineage.rs:93 -- merged into that order (confidence vectors descending lexicographically, on an equal prefix the longer vector
+// first, then first reference ascending), followed by the one-exact-match override (raxtax.rs:73-84), which needs the best line of
+// all ranks and is therefore left out by the ranks' own walks.  g_* hold the ranks' lines back to back (rank r at rank_off[r]),
+// all_begin[r][q] the ranks' per-query offsets.
+// =========================================================================================================
+struct MergeView {
+    const u32* all_begin;  // [n_ranks][nq + 1]
+    const u32* rank_off;   // [n_ranks + 1] first line of rank r in g_*
+    const u32* g_first;
+    const u8* g_nlev;
+    const double* g_conf;  // [lines][ML]
+    const double* g_local;
+    u32 n_ranks, nq, ML, pad;
+};
+
+__device__ __forceinline__ bool merge_override(const BatchView& b, u32 q) {
+    if ((b.flags & (RTX_RAW_CONFIDENCE | RTX_SKIP_EXACT_MATCHES)) || b.exact_off == nullptr) return false;
+    return b.exact_off[q + 1] - b.exact_off[q] == 1u;
+}
+
+// merged line count per query -> pool.res_cnt (result_scan_kernel then turns it into the offsets of the merged arrays)
+__global__ void __launch_bounds__(256) shard_merge_count_kernel(MergeView mv, BatchView b, ResultPool pool) {
+    const u32 q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= mv.nq) return;
+    u32 tot = 0;
+    for (u32 r = 0; r < mv.n_ranks; ++r) {
+        const u32* ab = mv.all_begin + (size_t)r * (mv.nq + 1);
+        tot += ab[q + 1] - ab[q];
+    }
+    if (tot == 0) pool.status[q] = kQEmptyResult;  // raxtax.rs:72
+    else if (tot > RTX_MAX_RESULTS_PER_QUERY) pool.status[q] = kQTooManyResults;
+    pool.res_cnt[q] = tot == 0 ? 0u : (merge_override(b, q) ? 1u : tot);
+}
+
+// one warp per query: rank sort of the query's lines (a handful; at most RTX_MAX_RESULTS_PER_QUERY)
+__global__ void __launch_bounds__(256) shard_merge_write_kernel(MergeView mv, BatchView b, IndexView ix, const u32* __restrict__ ord_begin,
+                                                                 u32* __restrict__ o_first, u8* __restrict__ o_nlev, double* __restrict__ o_conf,
+                                                                 double* __restrict__ o_local) {
+    const u32 q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (q >= mv.nq) return;
+    const u32 ML = mv.ML, R = mv.n_ranks;
+    u32 tot = 0;
+    for (u32 r = 0; r < R; ++r) {
+        const u32* ab = mv.all_begin + (size_t)r * (mv.nq + 1);
+        tot += ab[q + 1] - ab[q];
+    }
+    if (tot == 0 || tot > RTX_MAX_RESULTS_PER_QUERY) return;
+    // i-th line of the query over the ranks in rank order -> index into g_*
+    auto line_at = [&](u32 i) -> u32 {
+        for (u32 r = 0; r < R; ++r) {
+            const u32* ab = mv.all_begin + (size_t)r * (mv.nq + 1);
+            const u32 n = ab[q + 1] - ab[q];
+            if (i < n) return mv.rank_off[r] + ab[q] + i;
+            i -= n;
+        }
+        return 0u;
+    };
+    // does line x come before line y?
+    auto before = [&](u32 x, u32 y) -> bool {
+        const u32 nx = mv.g_nlev[x], ny = mv.g_nlev[y];
+        for (u32 lev = 0; lev < ML; ++lev) {
+            const bool hx = lev < nx, hy = lev < ny;
+            if (!hx && !hy) break;
+            if (hx != hy) return hx;  // equal prefix: the longer vector first
+            const long long kx = llround(mv.g_conf[(size_t)x * ML + lev] * 100.0), ky = llround(mv.g_conf[(size_t)y * ML + lev] * 100.0);
+            if (kx != ky) return kx > ky;
+        }
+        const u32 fx = mv.g_first[x], fy = mv.g_first[y];
+        return fx != fy ? fx < fy : x < y;
+    };
+    const bool ovr = merge_override(b, q);
+    const u32 dst = ord_begin[q];
+    for (u32 i = lane; i < tot; i += 32) {
+        const u32 x = line_at(i);
+        u32 pos = 0;
+        for (u32 k = 0; k < tot; ++k) {
+            if (k == i) continue;
+            pos += before(line_at(k), x) ? 1u : 0u;
+        }
+        if (!ovr) {
+            o_first[dst + pos] = mv.g_first[x];
+            o_nlev[dst + pos] = mv.g_nlev[x];
+            o_local[dst + pos] = mv.g_local[x];
+            for (u32 lev = 0; lev < ML; ++lev) o_conf[(size_t)(dst + pos) * ML + lev] = mv.g_conf[(size_t)x * ML + lev];
+        } else if (pos == 0) {  // signals of the best computed line, lineage and 1.0s of the exact match (raxtax.rs:73-84)
+            const u32 id = b.exact_ids[b.exact_off[q]];
+            const u32 n = ix.ref_levels[id];
+            o_first[dst] = id;
+            o_nlev[dst] = (u8)n;
+            o_local[dst] = mv.g_local[x];
+            for (u32 lev = 0; lev < ML; ++lev) o_conf[(size_t)dst * ML + lev] = lev < n ? 1.0 : 0.0;
+        }
+    }
+}
+
+// =========================================================================================================
 // K5 (level-synchronous form, the default for unsharded indexes).  The depth-first walker above follows one chain of
 // dependent loads per 32 children it looks at; taxonomies have nodes with thousands of children, so even a query with a
 // single result line evaluates ~2 500 children (80 dependent round trips), and a query with a flat probability profile

@@ -1,6 +1,9 @@
 // rtx_api.cu -- C ABI (include/raxtax_b200.h) of the sm_100a query-classification library.
 // Host-side orchestration only: validation, HBM layout, kernel launches, result ordering.  No CPU compute path.
 
+#include <dlfcn.h>
+#include <nccl.h>  // types and prototypes only: libnccl is bound at run time (see the NCCL section below)
+
 #include <algorithm>
 #include <cmath>
 #include <cstring>
@@ -45,6 +48,10 @@ struct BatchState {
     u64 runs_since_download = 0;
     cudaEvent_t ev_up = nullptr, ev_done = nullptr;  // inputs are on the device / all kernels of the last run have finished
     bool up_pending = false;                          // ev_up was recorded and no run has waited for it yet
+    // reference-sharded mode over NCCL
+    bool sub_batch_agreed = false;  // the ranks settled on one sub-batch size for this batch
+    bool merged = false;            // rtx_shard_gather ran: d_ord_* hold the merged lines (root) / nothing (other ranks)
+    u64 merged_lines = 0;
 };
 
 struct rtx_ctx : BatchState {
@@ -93,6 +100,10 @@ struct rtx_ctx : BatchState {
     // reference-sharded mode
     ShardView sv{};
     DevBuf d_strad_of_node, d_strad_nodes, d_strad_parent, d_send, d_recv, d_sk, d_sany, d_sbest;
+    // ... over NCCL (rtx_comm_init): exchange buffers per scratch slot, gather buffers of the root
+    void* comm = nullptr;  // ncclComm_t
+    int comm_rank = 0, comm_size = 0;
+    DevBuf d_agree, d_send_s[2], d_recv_s[2], d_sk_s[2], d_sany_s[2], d_sbest_s[2], d_all_begin, d_rank_off, d_g_first, d_g_nlev, d_g_conf, d_g_local;
     // host staging: one pinned arena (device -> arena by DMA, arena -> caller memory by memcpy unless the caller's memory is pinned itself)
     unsigned char* h_arena = nullptr;
     size_t h_arena_cap = 0, h_arena_used = 0;
@@ -297,6 +308,13 @@ RTX_API void rtx_ctx_destroy(rtx_ctx* c) {
     if (c->stream2) cudaStreamSynchronize(c->stream2);
     drain_events(c);
     if (c->stream_cp) cudaStreamSynchronize(c->stream_cp);
+    rtx_comm_destroy(c);
+    for (int i = 0; i < 2; ++i) {
+        DevBuf* xb[] = {&c->d_send_s[i], &c->d_recv_s[i], &c->d_sk_s[i], &c->d_sany_s[i], &c->d_sbest_s[i]};
+        for (DevBuf* b : xb) b->release();
+    }
+    DevBuf* gb[] = {&c->d_agree, &c->d_all_begin, &c->d_rank_off, &c->d_g_first, &c->d_g_nlev, &c->d_g_conf, &c->d_g_local};
+    for (DevBuf* b : gb) b->release();
     DevBuf* bufs[] = {&c->d_bitrows, &c->d_rowmap, &c->d_present, &c->d_csr_off, &c->d_csr_ids, &c->d_node_lo, &c->d_node_hi,
                       &c->d_node_type, &c->d_child_first, &c->d_child_count, &c->d_node_blo, &c->d_node_bhi, &c->d_bnd_after,
                       &c->d_bnd_rank, &c->d_ref_levels, &c->d_lnfact, &c->d_counts, &c->d_counts1, &c->d_preb1, &c->d_ptab1, &c->d_segoff1,
@@ -374,6 +392,7 @@ RTX_API int rtx_ctx_set_option(rtx_ctx* ctx, int option, int64_t value) {
 }
 
 RTX_API void* rtx_ctx_stream(rtx_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+RTX_API int rtx_ctx_device(const rtx_ctx* ctx) { return ctx ? ctx->device : -1; }
 
 RTX_API int rtx_ctx_synchronize(rtx_ctx* ctx) {
     if (!ctx) return RTX_ERR_INVALID;
@@ -925,7 +944,8 @@ RTX_API int rtx_batch_upload(rtx_ctx* ctx, const rtx_batch* batch) {
     u64 sb = (u64)ctx->sub_batch_opt;
     if (!sb) {
         const u64 mem_free = ctx->mem_free_after_index;  // sampled once per index upload (cudaMemGetInfo costs ~1 ms per call)
-        const u64 budget = std::min<u64>(std::max<u64>(mem_free / 4, 2ull << 30), 48ull << 30);
+        u64 budget = std::min<u64>(std::max<u64>(mem_free / 4, 2ull << 30), 48ull << 30);
+        if (ctx->comm != nullptr && ctx->sv.n_shards > 1) budget = std::min<u64>(budget, std::max<u64>(mem_free / 5, 1ull << 30));  // two scratch slots
         const u64 scratch_per_query = per_query + ((u64)round_up(ctx->ix.n_bnd, 4) + ctx->ix.n_pad / kPrefixSeg + ctx->ix.n_pad / kPrefixSeg / 64 + ctx->ix.n_pad / kPrefixSeg / 4 + 8 + hstride) * 8;
         sb = std::max<u64>(1, budget / scratch_per_query);
     }
@@ -933,7 +953,9 @@ RTX_API int rtx_batch_upload(rtx_ctx* ctx, const rtx_batch* batch) {
     if (!ctx->sub_batch_opt && may_pipe && nq >= 4096) sb = std::min<u64>(sb, std::max<u64>(1024, (nq + 3) / 4));  // >= 4 pipeline stages
     sb = std::min<u64>(std::min<u64>(sb, nq), 65535);
     ctx->sub_batch = (u32)sb;
-    ctx->two_slots = may_pipe && nq > sb;
+    ctx->two_slots = (may_pipe && nq > sb) || (ctx->comm != nullptr && ctx->sv.n_shards > 1 && nq > 1);
+    ctx->sub_batch_agreed = false;
+    ctx->merged = false;
     ctx->need_counts = sb * per_query;
 
     // probability kernel scratch
@@ -1320,7 +1342,7 @@ RTX_API int rtx_batch_download(rtx_ctx* ctx, rtx_results* res) {
     CU(d2h(ctx, res->n_kmers, ctx->d_K.p, (size_t)nq * 2, host_ptr_pinned(res->n_kmers)));
     CU(d2h(ctx, res->global_signal, ctx->d_global.p, (size_t)nq * 8, host_ptr_pinned(res->global_signal)));
     CU(d2h_finish(ctx));
-    const unsigned long long used = h_used[0], hits = h_used[1];
+    const unsigned long long used = ctx->merged ? (unsigned long long)h_begin[nq] : h_used[0], hits = h_used[1];
     ctx->prof.d2h_bytes += 16 + 4 + (u64)nq * (3 * 4 + 2 + 8);
     {
         // every run since the last download processed this same batch: account them all
@@ -1346,6 +1368,8 @@ RTX_API int rtx_batch_download(rtx_ctx* ctx, rtx_results* res) {
             default: return set_err(ctx, RTX_ERR_CUDA, "query " + std::to_string(q) + ": unknown device status");
         }
     }
+    if (pool_overflow && ctx->merged)
+        return set_err(ctx, RTX_ERR_CUDA, "result pool overflow after rtx_shard_gather (the gather sizes the pools of all ranks before merging)");
     if (pool_overflow) {
         // grow the pool and redo the whole batch once (counts of earlier sub-batches are gone)
         int rc = ensure_pool(ctx, used + used / 4 + 1024);
@@ -1537,6 +1561,383 @@ RTX_API int rtx_shard_phase3(rtx_ctx* ctx) {
     ctx->runs_since_download += 1;
     ctx->ran = true;
     return RTX_OK;
+}
+
+// =========================================================================================================
+// Reference-sharded mode over NCCL (BASELINE config 5; north_star: "an NCCL-over-NVLink allreduce of the small per-query count
+// histograms and a gather of the above-threshold hits").  One rank = one context = one GPU; the ranks may be processes (torchrun,
+// MPI) or threads of one process.  The exchange prob.rs:62-73 forces -- cmf_prod_components needs the count histogram over ALL
+// references -- is an in-place ncclAllReduce(ncclUint32, ncclSum) on the sub-batch's rows of the histogram buffer; the straddler
+// records travel by ncclAllGather; the result lines reach the root by ncclSend / ncclRecv and are merged there on the device.
+// libnccl is bound at run time (dlopen: the copy a host framework already loaded, else the system's), so that the library has no
+// link-time dependency for the single-GPU and query-partitioned cases.
+// =========================================================================================================
+namespace {
+struct NcclApi {
+    void* lib = nullptr;
+    std::string err;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+    bool ok() const { return lib != nullptr && err.empty(); }
+};
+
+NcclApi load_nccl() {
+    NcclApi a;
+    const char* names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char* n : names) {  // the copy already in the process (e.g. the one a Python framework bundles) wins
+        a.lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL | RTLD_NOLOAD);
+        if (a.lib) break;
+    }
+    for (const char* n : names) {
+        if (a.lib) break;
+        a.lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+    }
+    if (!a.lib) {
+        a.err = std::string("libnccl.so.2 not found: ") + (dlerror() ? dlerror() : "");
+        return a;
+    }
+    auto sym = [&](const char* n) -> void* {
+        void* p = dlsym(a.lib, n);
+        if (!p && a.err.empty()) a.err = std::string("libnccl lacks ") + n;
+        return p;
+    };
+    a.GetUniqueId = (decltype(a.GetUniqueId))sym("ncclGetUniqueId");
+    a.CommInitRank = (decltype(a.CommInitRank))sym("ncclCommInitRank");
+    a.CommDestroy = (decltype(a.CommDestroy))sym("ncclCommDestroy");
+    a.AllReduce = (decltype(a.AllReduce))sym("ncclAllReduce");
+    a.AllGather = (decltype(a.AllGather))sym("ncclAllGather");
+    a.Send = (decltype(a.Send))sym("ncclSend");
+    a.Recv = (decltype(a.Recv))sym("ncclRecv");
+    a.GroupStart = (decltype(a.GroupStart))sym("ncclGroupStart");
+    a.GroupEnd = (decltype(a.GroupEnd))sym("ncclGroupEnd");
+    a.GetErrorString = (decltype(a.GetErrorString))sym("ncclGetErrorString");
+    return a;
+}
+NcclApi& nccl() {
+    static NcclApi api = load_nccl();
+    return api;
+}
+}  // namespace
+
+#define NC(call)                                                                                                                  \
+    do {                                                                                                                          \
+        ncclResult_t r__ = (call);                                                                                                \
+        if (r__ != ncclSuccess) return set_err(ctx, RTX_ERR_CUDA, std::string(#call) + ": " + nccl().GetErrorString(r__));        \
+    } while (0)
+
+RTX_API int rtx_comm_unique_id(void* out) {
+    rtx_ctx* ctx = nullptr;
+    if (!out) return set_err(nullptr, RTX_ERR_INVALID, "rtx_comm_unique_id: out is NULL");
+    if (!nccl().ok()) return set_err(nullptr, RTX_ERR_UNSUPPORTED, "NCCL unavailable: " + nccl().err);
+    ncclUniqueId id;
+    NC(nccl().GetUniqueId(&id));
+    static_assert(sizeof(id) == RTX_COMM_UNIQUE_ID_BYTES, "ncclUniqueId size");
+    memcpy(out, &id, sizeof id);
+    return RTX_OK;
+}
+
+RTX_API int rtx_comm_init(rtx_ctx* ctx, const void* unique_id, int rank, int nranks) {
+    if (!ctx) return RTX_ERR_INVALID;
+    REQUIRE(unique_id != nullptr && nranks >= 1 && rank >= 0 && rank < nranks, "rtx_comm_init: bad rank / nranks / id");
+    if (!nccl().ok()) return set_err(ctx, RTX_ERR_UNSUPPORTED, "NCCL unavailable: " + nccl().err);
+    CU(cudaSetDevice(ctx->device));
+    if (ctx->comm) {
+        nccl().CommDestroy((ncclComm_t)ctx->comm);
+        ctx->comm = nullptr;
+    }
+    ncclUniqueId id;
+    memcpy(&id, unique_id, sizeof id);
+    ncclComm_t comm = nullptr;
+    NC(nccl().CommInitRank(&comm, nranks, id, rank));
+    ctx->comm = comm;
+    ctx->comm_rank = rank;
+    ctx->comm_size = nranks;
+    return RTX_OK;
+}
+
+RTX_API int rtx_comm_destroy(rtx_ctx* ctx) {
+    if (!ctx) return RTX_ERR_INVALID;
+    if (ctx->comm) {
+        cudaSetDevice(ctx->device);
+        cudaStreamSynchronize(ctx->stream);
+        cudaStreamSynchronize(ctx->stream2);
+        nccl().CommDestroy((ncclComm_t)ctx->comm);
+        ctx->comm = nullptr;
+    }
+    ctx->comm_size = 0;
+    return RTX_OK;
+}
+
+static int comm_precheck(rtx_ctx* ctx, const char* who) {
+    if (!ctx) return RTX_ERR_INVALID;
+    if (!ctx->comm) return set_err(ctx, RTX_ERR_INVALID, std::string(who) + ": no communicator (rtx_comm_init)");
+    if ((int)ctx->sv.n_shards != ctx->comm_size || (int)ctx->sv.rank != ctx->comm_rank)
+        return set_err(ctx, RTX_ERR_INVALID, std::string(who) + ": the index must be uploaded as shard `rank` of `nranks` shards of the communicator");
+    if (!ctx->has_batch) return set_err(ctx, RTX_ERR_INVALID, std::string(who) + ": no batch uploaded");
+    return RTX_OK;
+}
+
+// All phases of the uploaded batch.  The batch is cut into sub-batches (the same cut on every rank: the smallest of the ranks'
+// own choices) that alternate between two scratch slots: hit counting of sub-batch i+1 runs on `stream` while the histogram
+// all-reduce, the probability / prefix / record kernels, the record all-gather and the tree walk of sub-batch i run on `stream2`.
+RTX_API int rtx_shard_run(rtx_ctx* ctx) {
+    int rc = comm_precheck(ctx, "rtx_shard_run");
+    if (rc) return rc;
+    CU(cudaSetDevice(ctx->device));
+    BatchView& bv = ctx->bv;
+    const u32 nq = bv.n_queries;
+    ncclComm_t comm = (ncclComm_t)ctx->comm;
+    ctx->merged = false;
+    // the ranks agree on the sub-batch size (each sized its own from its free memory) -- once per upload
+    if (!ctx->sub_batch_agreed) {
+        CU(ctx->d_agree.ensure(8));
+        const u32 mine = nq ? ctx->sub_batch : 0xFFFFFFFFu;
+        CU(cudaMemcpyAsync(ctx->d_agree.p, &mine, 4, cudaMemcpyHostToDevice, ctx->stream));
+        NC(nccl().AllReduce(ctx->d_agree.p, ctx->d_agree.p, 1, ncclUint32, ncclMin, comm, ctx->stream));
+        u32 agreed = 0;
+        CU(cudaMemcpyAsync(&agreed, ctx->d_agree.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+        if (nq) ctx->sub_batch = std::max(1u, std::min(agreed, ctx->sub_batch));
+        ctx->sub_batch_agreed = true;
+    }
+    if (nq == 0) {
+        ctx->shard_phase = 3;
+        ctx->ran = true;
+        return RTX_OK;
+    }
+    const u32 sb = ctx->sub_batch;
+    const bool pipe = ctx->two_slots && nq > sb;
+    rc = begin_run(ctx);
+    if (rc) return rc;
+    const size_t S = ctx->sv.n_strad;
+    const u32 R = ctx->sv.n_shards;
+    const int n_slots = pipe ? 2 : 1;
+    for (int s = 0; s < n_slots; ++s) {  // exchange buffers per scratch slot, sized for one sub-batch
+        CU(ctx->d_send_s[s].ensure(std::max<size_t>(1, (size_t)sb * S) * sizeof(ShardRec)));
+        CU(ctx->d_recv_s[s].ensure(std::max<size_t>(1, (size_t)sb * S) * sizeof(ShardRec) * R));
+        CU(ctx->d_sk_s[s].ensure(std::max<size_t>(1, (size_t)sb * S)));
+        CU(ctx->d_sany_s[s].ensure(std::max<size_t>(1, (size_t)sb * S)));
+        CU(ctx->d_sbest_s[s].ensure(std::max<size_t>(1, (size_t)sb * S) * 4));
+    }
+    CU(cudaMemsetAsync(ctx->d_hist.p, 0, (size_t)nq * bv.hstride * 4, ctx->stream));
+    CU(cudaMemsetAsync(ctx->d_pool_used.p, 0, 8, ctx->stream));
+    CU(cudaMemsetAsync(ctx->d_hits.p, 0, 8, ctx->stream));
+    {
+        LaunchTimer lt(ctx, RTX_K_KMERS);
+        kmers_kernel<<<nq, kKmerThreads, 0, ctx->stream>>>(ctx->ix, bv);
+        CU(cudaGetLastError());
+    }
+    u32 i_sub = 0;
+    for (u32 q0 = 0; q0 < nq; q0 += sb, ++i_sub) {
+        const int qb = (int)std::min<u32>(sb, nq - q0);
+        const int slot = pipe ? (int)(i_sub & 1u) : 0;
+        ctx->cur_counts = slot ? ctx->d_counts1.as<u16>() : ctx->d_counts.as<u16>();
+        ctx->cur_sc = slot ? &ctx->sc1 : &ctx->sc;
+        ctx->cur_stream = ctx->stream;
+        if (pipe && i_sub >= 2) CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_post[slot], 0));  // the slot's previous tenant is done
+        rc = run_phase1(ctx, (int)q0, qb);
+        if (rc) return rc;
+        if ((bv.flags & RTX_SKIP_EXACT_MATCHES) && bv.exact_off) {
+            LaunchTimer lt(ctx, RTX_K_FIXUP);
+            fixup_exact_kernel<<<(qb + 127) / 128, 128, 0, ctx->stream>>>(ctx->ix, bv, ctx->cur_counts, (int)q0, qb);
+            CU(cudaGetLastError());
+        }
+        if (pipe) {
+            CU(cudaEventRecord(ctx->ev_hit[slot], ctx->stream));
+            ctx->cur_stream = ctx->stream2;
+            CU(cudaStreamWaitEvent(ctx->stream2, ctx->ev_hit[slot], 0));
+        }
+        cudaStream_t st = ctx->cur_stream;
+        {   // prob.rs:62-73 needs the histogram over all references
+            LaunchTimer lt(ctx, RTX_K_ALLREDUCE);
+            u32* h = ctx->d_hist.as<u32>() + (size_t)q0 * bv.hstride;
+            NC(nccl().AllReduce(h, h, (size_t)qb * bv.hstride, ncclUint32, ncclSum, comm, st));
+            ctx->prof.allreduce_bytes += (u64)qb * bv.hstride * 4;
+        }
+        rc = launch_prob(ctx, (int)q0, qb);
+        if (rc) return rc;
+        ShardView sv = ctx->sv;
+        sv.send = ctx->d_send_s[slot].as<ShardRec>();
+        sv.recv = ctx->d_recv_s[slot].as<ShardRec>();
+        sv.sk = ctx->d_sk_s[slot].as<u8>();
+        sv.sany = ctx->d_sany_s[slot].as<u8>();
+        sv.sbest = ctx->d_sbest_s[slot].as<u32>();
+        if (S) {
+            {
+                LaunchTimer lt(ctx, RTX_K_SHARD);
+                const long long warps = (long long)qb * (long long)S;
+                shard_records_kernel<<<(unsigned)((warps * 32 + 127) / 128), 128, 0, st>>>(ctx->ix, ctx->d_recs.as<NodeRec>(), *ctx->cur_sc, sv, qb);
+                CU(cudaGetLastError());
+            }
+            {
+                LaunchTimer lt(ctx, RTX_K_ALLGATHER);
+                NC(nccl().AllGather(sv.send, (void*)sv.recv, (size_t)qb * S * sizeof(ShardRec), ncclUint8, comm, st));
+                ctx->prof.allgather_bytes += (u64)qb * S * sizeof(ShardRec) * R;
+            }
+            {
+                LaunchTimer lt(ctx, RTX_K_SHARD);
+                shard_combine_kernel<<<(qb + 127) / 128, 128, 0, st>>>(sv, ctx->d_recs.as<NodeRec>(), qb);
+                CU(cudaGetLastError());
+            }
+        }
+        {
+            LaunchTimer lt(ctx, RTX_K_WALK);
+            lineage_walk_kernel<true><<<(qb + kWalkWarps - 1) / kWalkWarps, kWalkWarps * 32, ctx->walk_smem, st>>>(
+                ctx->ix, ctx->d_recs.as<NodeRec>(), bv, ctx->pool, *ctx->cur_sc, sv, (int)q0, qb, 0);
+            CU(cudaGetLastError());
+        }
+        if (pipe) CU(cudaEventRecord(ctx->ev_post[slot], ctx->stream2));
+    }
+    if (pipe) {
+        CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_post[0], 0));
+        if (i_sub >= 2) CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_post[1], 0));
+    }
+    ctx->cur_stream = ctx->stream;
+    ctx->cur_counts = ctx->d_counts.as<u16>();
+    ctx->cur_sc = &ctx->sc;
+    rc = order_results(ctx);
+    if (rc) return rc;
+    CU(cudaEventRecord(ctx->ev_done, ctx->stream));
+    ctx->shard_phase = 3;
+    ctx->prof.queries += nq;
+    ctx->runs_since_download += 1;
+    ctx->ran = true;
+    return RTX_OK;
+}
+
+// The ranks' result lines -> root, merged there (shard_merge_*_kernel): afterwards rtx_batch_download returns the batch's final lines
+// on the root and no lines on the other ranks.
+RTX_API int rtx_shard_gather(rtx_ctx* ctx, int root) {
+    int rc = comm_precheck(ctx, "rtx_shard_gather");
+    if (rc) return rc;
+    REQUIRE(root >= 0 && root < ctx->comm_size, "rtx_shard_gather: bad root");
+    if (!ctx->ran) return set_err(ctx, RTX_ERR_INVALID, "rtx_shard_gather: nothing was run");
+    CU(cudaSetDevice(ctx->device));
+    const u32 nq = ctx->bv.n_queries;
+    const u32 R = (u32)ctx->comm_size, ML = ctx->ix.max_levels;
+    const bool is_root = ctx->comm_rank == root;
+    ncclComm_t comm = (ncclComm_t)ctx->comm;
+    cudaStream_t st = ctx->stream;
+    if (nq == 0) {
+        ctx->merged = true;
+        ctx->merged_lines = 0;
+        return RTX_OK;
+    }
+    // a result pool that overflowed on ANY rank is grown there and the batch re-run on ALL ranks (the collectives need everybody)
+    CU(ctx->d_agree.ensure(16));
+    for (int attempt = 0;; ++attempt) {
+        unsigned long long h[2] = {0, 0}, g[2] = {0, 0};
+        CU(cudaMemcpyAsync(&h[0], ctx->d_pool_used.p, 8, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        h[1] = h[0] > ctx->pool.cap ? 1ull : 0ull;
+        CU(cudaMemcpyAsync(ctx->d_agree.p, h, 16, cudaMemcpyHostToDevice, st));
+        NC(nccl().AllReduce(ctx->d_agree.p, ctx->d_agree.p, 2, ncclUint64, ncclMax, comm, st));
+        CU(cudaMemcpyAsync(g, ctx->d_agree.p, 16, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        if (!g[1]) break;
+        if (attempt >= 2) return set_err(ctx, RTX_ERR_CUDA, "rtx_shard_gather: the result pool keeps overflowing");
+        if (h[1]) {
+            rc = ensure_pool(ctx, h[0] + h[0] / 4 + 1024);
+            if (rc) return rc;
+        }
+        rc = rtx_shard_run(ctx);
+        if (rc) return rc;
+    }
+    // every rank's per-query offsets everywhere (4 bytes per query and rank), then the totals on the host
+    CU(ctx->d_all_begin.ensure((size_t)R * (nq + 1) * 4));
+    {
+        LaunchTimer lt(ctx, RTX_K_ALLGATHER);
+        NC(nccl().AllGather(ctx->d_ord_begin.p, ctx->d_all_begin.p, (size_t)nq + 1, ncclUint32, comm, st));
+        ctx->prof.allgather_bytes += (u64)R * (nq + 1) * 4;
+    }
+    std::vector<u32> tot(R), off(R + 1, 0);
+    CU(cudaMemcpy2DAsync(tot.data(), 4, ctx->d_all_begin.as<u32>() + nq, (size_t)(nq + 1) * 4, 4, R, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    for (u32 r = 0; r < R; ++r) off[r + 1] = off[r] + tot[r];
+    const u64 all = off[R];
+    const u32 mine = tot[ctx->comm_rank];
+    if (is_root) {
+        CU(ctx->d_g_first.ensure(std::max<u64>(all, 1) * 4));
+        CU(ctx->d_g_nlev.ensure(std::max<u64>(all, 1)));
+        CU(ctx->d_g_conf.ensure(std::max<u64>(all, 1) * ML * 8));
+        CU(ctx->d_g_local.ensure(std::max<u64>(all, 1) * 8));
+        CU(ctx->d_rank_off.ensure((R + 1) * 4));
+        CU(cudaMemcpyAsync(ctx->d_rank_off.p, off.data(), (R + 1) * 4, cudaMemcpyHostToDevice, st));
+    }
+    {
+        LaunchTimer lt(ctx, RTX_K_GATHER);
+        NC(nccl().GroupStart());
+        if (!is_root) {
+            if (mine) {
+                NC(nccl().Send(ctx->d_ord_first.p, (size_t)mine * 4, ncclUint8, root, comm, st));
+                NC(nccl().Send(ctx->d_ord_nlev.p, (size_t)mine, ncclUint8, root, comm, st));
+                NC(nccl().Send(ctx->d_ord_conf.p, (size_t)mine * ML * 8, ncclUint8, root, comm, st));
+                NC(nccl().Send(ctx->d_ord_local.p, (size_t)mine * 8, ncclUint8, root, comm, st));
+            }
+        } else {
+            for (u32 r = 0; r < R; ++r) {
+                if ((int)r == root || !tot[r]) continue;
+                NC(nccl().Recv(ctx->d_g_first.as<u32>() + off[r], (size_t)tot[r] * 4, ncclUint8, (int)r, comm, st));
+                NC(nccl().Recv(ctx->d_g_nlev.as<u8>() + off[r], (size_t)tot[r], ncclUint8, (int)r, comm, st));
+                NC(nccl().Recv(ctx->d_g_conf.as<double>() + (size_t)off[r] * ML, (size_t)tot[r] * ML * 8, ncclUint8, (int)r, comm, st));
+                NC(nccl().Recv(ctx->d_g_local.as<double>() + off[r], (size_t)tot[r] * 8, ncclUint8, (int)r, comm, st));
+            }
+        }
+        NC(nccl().GroupEnd());
+        ctx->prof.gather_bytes += is_root ? (all - mine) * (4 + 1 + 8 + (u64)ML * 8) : (u64)mine * (4 + 1 + 8 + (u64)ML * 8);
+    }
+    if (!is_root) {
+        CU(cudaMemsetAsync(ctx->d_ord_begin.p, 0, ((size_t)nq + 1) * 4, st));
+        CU(cudaEventRecord(ctx->ev_done, st));
+        ctx->merged = true;
+        ctx->merged_lines = 0;
+        return RTX_OK;
+    }
+    if (mine) {  // the root's own lines take their place among the gathered ones
+        CU(cudaMemcpyAsync(ctx->d_g_first.as<u32>() + off[root], ctx->d_ord_first.p, (size_t)mine * 4, cudaMemcpyDeviceToDevice, st));
+        CU(cudaMemcpyAsync(ctx->d_g_nlev.as<u8>() + off[root], ctx->d_ord_nlev.p, (size_t)mine, cudaMemcpyDeviceToDevice, st));
+        CU(cudaMemcpyAsync(ctx->d_g_conf.as<double>() + (size_t)off[root] * ML, ctx->d_ord_conf.p, (size_t)mine * ML * 8, cudaMemcpyDeviceToDevice, st));
+        CU(cudaMemcpyAsync(ctx->d_g_local.as<double>() + off[root], ctx->d_ord_local.p, (size_t)mine * 8, cudaMemcpyDeviceToDevice, st));
+    }
+    // the merged lines go where the root's own were: those arrays are sized for the pool's capacity
+    if (all > ctx->pool.cap) {
+        rc = ensure_pool(ctx, all + all / 4 + 1024);
+        if (rc) return rc;
+    }
+    MergeView mv{ctx->d_all_begin.as<u32>(), ctx->d_rank_off.as<u32>(), ctx->d_g_first.as<u32>(), ctx->d_g_nlev.as<u8>(), ctx->d_g_conf.as<double>(),
+                 ctx->d_g_local.as<double>(), R, nq, ML, 0};
+    {
+        LaunchTimer lt(ctx, RTX_K_SHARD);
+        shard_merge_count_kernel<<<(nq + 255) / 256, 256, 0, st>>>(mv, ctx->bv, ctx->pool);
+        CU(cudaGetLastError());
+        result_scan_kernel<<<1, kScanThreads, 0, st>>>(ctx->pool, ctx->d_ord_begin.as<u32>(), nq);
+        CU(cudaGetLastError());
+        shard_merge_write_kernel<<<(nq + 7) / 8, 256, 0, st>>>(mv, ctx->bv, ctx->ix, ctx->d_ord_begin.as<u32>(), ctx->d_ord_first.as<u32>(),
+                                                              ctx->d_ord_nlev.as<u8>(), ctx->d_ord_conf.as<double>(), ctx->d_ord_local.as<double>());
+        CU(cudaGetLastError());
+    }
+    CU(cudaEventRecord(ctx->ev_done, st));
+    ctx->merged = true;
+    ctx->merged_lines = ~0ull;  // read from ord_begin[nq] by the download
+    return RTX_OK;
+}
+
+RTX_API int rtx_shard_classify(rtx_ctx* ctx, const rtx_batch* batch, rtx_results* results, int root) {
+    if (!ctx) return RTX_ERR_INVALID;
+    REQUIRE(results != nullptr, "results is NULL");
+    int rc = rtx_batch_upload(ctx, batch);
+    if (rc == RTX_OK) rc = rtx_shard_run(ctx);
+    if (rc == RTX_OK) rc = rtx_shard_gather(ctx, root);
+    if (rc == RTX_OK) rc = rtx_batch_download(ctx, results);
+    return rc;
 }
 
 // ---- in-process exchange between the shards of one process (stand-ins for ncclAllReduce / ncclAllGather) ---------------------

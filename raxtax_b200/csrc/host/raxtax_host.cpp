@@ -1283,6 +1283,8 @@ struct Worker {
         double s() const { return (double)ns.load() * 1e-9; }
     };
     Clock t_prep{}, t_issue{}, t_collect{}, t_acquire{}, t_format{}, t_send{}, t_emit_wait{};
+    std::chrono::steady_clock::time_point t_start{}, t_first_issue{}, t_last_collect{};
+    std::atomic<bool> first_issued{false};
     static std::chrono::steady_clock::time_point now() { return std::chrono::steady_clock::now(); }
 
     void fail(const std::string& what) {
@@ -1298,7 +1300,7 @@ struct Worker {
 
     // ---- driver side ---------------------------------------------------------------------------------------------------------
     // de-duplication, exact-match lookup (raxtax.rs:42) and the log lines of raxtax.rs:43-53 for queries [c0, c0 + cn)
-    void prep(ChunkJob& j, size_t c0, size_t cn, FlatDedup& dd, bool dedup) {
+    void prep(ChunkJob& j, size_t c0, size_t cn, FlatDedup& dd, bool dedup, bool log = true) {
         j.c0 = c0;
         j.cn = cn;
         // Queries with identical sequences (amplicon reads of an abundant taxon) get identical results: the device sees every
@@ -1362,7 +1364,7 @@ struct Worker {
                 j.exact_ids.push_back(id);
             j.exact_off[u + 1] = (u32)j.exact_ids.size();
         }
-        if (skip_exact_matches || j.exact_ids.empty()) return;
+        if (skip_exact_matches || j.exact_ids.empty() || !log) return;
         std::string msg, first_parent;
         for (size_t i = 0; i < cn; ++i) {  // the log lines of raxtax.rs:43-53, per query
             const size_t q = c0 + i;
@@ -1509,6 +1511,7 @@ struct Worker {
             t0 = now();
             const bool issued = issue(ctx, *j, dev_slot);
             t_issue.add(t0);
+            if (!first_issued.exchange(true)) t_first_issue = now();
             if (!issued) {
                 // the batch does not fit the device next to the index: drain, then classify it in two halves
                 j->busy.store(false);
@@ -1536,6 +1539,7 @@ struct Worker {
             auto t0 = now();
             collect(ctx, *inflight);
             t_collect.add(t0);
+            t_last_collect = now();
             hand_over(inflight);
         }
         // the jobs (and their page-locked arrays) must outlive the emitter's use of them
@@ -1546,6 +1550,65 @@ struct Worker {
             if (!any) break;
             free_cv.wait(g);
         }
+    }
+
+    // Reference-sharded mode over NCCL: ctx is rank `rank` of `n_ranks` (index uploaded with rxh_tree_upload_sharded, communicator
+    // set up).  Every rank walks the same chunks in the same order -- the collectives inside rtx_shard_run / rtx_shard_gather need
+    // all of them -- and prepares the same batch; rank 0 gets the merged lines, writes the log lines and feeds the emitter.
+    void drive_sharded(rtx_ctx* ctx, int rank) {
+        try {
+            if (rtx_index_n_refs(ctx) != tree.num_tips) throw Error("a context's index does not belong to this tree");
+            const bool dedup = getenv("RXH_NO_DEDUP") == nullptr;
+            std::vector<std::unique_ptr<ChunkJob>> jobs = job_pool().take(ctx);
+            struct Return {
+                rtx_ctx* ctx;
+                std::vector<std::unique_ptr<ChunkJob>>& jobs;
+                ~Return() { job_pool().give(ctx, std::move(jobs)); }
+            } ret{ctx, jobs};
+            FlatDedup dd;
+            for (size_t c0 = 0; c0 < nq && !failed.load(); c0 += chunk_size) {
+                auto t0 = now();
+                ChunkJob* j = acquire(jobs);
+                t_acquire.add(t0);
+                if (!j) break;
+                t0 = now();
+                prep(*j, c0, std::min(chunk_size, nq - c0), dd, dedup, rank == 0);
+                t_prep.add(t0);
+                t0 = now();
+                rtx_batch batch{};
+                batch.n_queries = (u32)j->n_uniq;
+                batch.seq_offsets = j->compact ? j->u_off.data() : qs.off.data() + j->c0;
+                batch.seq_codes = j->compact ? j->u_codes.data() : qs.codes.data();
+                batch.exact_offsets = j->exact_off.data();
+                batch.exact_ids = j->exact_ids.empty() ? nullptr : j->exact_ids.data();
+                batch.flags = (skip_exact_matches ? RTX_SKIP_EXACT_MATCHES : 0u) | (raw_confidence ? RTX_RAW_CONFIDENCE : 0u);
+                j->dev_slot = 0;
+                if (rtx_batch_slot(ctx, 0) || rtx_batch_upload(ctx, &batch)) throw Error(std::string("rtx_batch_upload: ") + rtx_last_error(ctx));
+                if (rtx_shard_run(ctx)) throw Error(std::string("rtx_shard_run: ") + rtx_last_error(ctx));
+                if (rtx_shard_gather(ctx, 0)) throw Error(std::string("rtx_shard_gather: ") + rtx_last_error(ctx));
+                t_issue.add(t0);
+                if (rank == 0) {
+                    t0 = now();
+                    collect(ctx, *j);
+                    t_collect.add(t0);
+                    hand_over(j);
+                } else {
+                    j->busy.store(false);
+                }
+            }
+            std::unique_lock<std::mutex> g(q_mtx);
+            while (true) {
+                bool any = false;
+                for (auto& j : jobs) any |= j->busy.load();
+                if (!any) break;
+                free_cv.wait(g);
+            }
+        } catch (const std::exception& e) {
+            fail(e.what());
+        }
+        std::lock_guard<std::mutex> g(q_mtx);
+        --drivers_running;
+        q_cv.notify_all();
     }
 
     // ---- emitter side --------------------------------------------------------------------------------------------------------
@@ -1642,7 +1705,9 @@ struct Worker {
         }
     }
 
-    void run(rtx_ctx* const* ctxs, size_t n_ctx) {
+    void run(rtx_ctx* const* ctxs, size_t n_ctx, bool sharded = false) {
+        t_start = now();
+        t_first_issue = t_last_collect = t_start;
         size_t n_helpers = 0;
         if (const char* e = getenv("RXH_FORMAT_THREADS")) n_helpers = (size_t)std::max(0, atoi(e) - 1);
         else n_helpers = std::min<size_t>(3, std::max<size_t>(1, std::thread::hardware_concurrency() / 8));
@@ -1651,7 +1716,10 @@ struct Worker {
         for (size_t k = 1; k <= n_helpers; ++k) helpers.emplace_back([this, k] { helper_main(k); });
         drivers_running = n_ctx;
         std::vector<std::thread> drivers;
-        for (size_t i = 0; i < n_ctx; ++i) drivers.emplace_back([this, ctx = ctxs[i]] { drive(ctx); });
+        for (size_t i = 0; i < n_ctx; ++i) {
+            if (sharded) drivers.emplace_back([this, ctx = ctxs[i], i] { drive_sharded(ctx, (int)i); });
+            else drivers.emplace_back([this, ctx = ctxs[i]] { drive(ctx); });
+        }
         while (true) {  // the calling thread is the writer side of the channel (main.rs:126-136)
             ChunkJob* j = nullptr;
             {
@@ -1683,8 +1751,10 @@ struct Worker {
         for (auto& t : helpers) t.join();
         if (getenv("RXH_TIMING"))
             fprintf(stderr, "[rxh raxtax] %zu queries, %zu ctx, chunk %zu, %zu format threads | drivers: acquire %.4f prep %.4f issue %.4f collect %.4f | "
-                            "emitter: wait %.4f format %.4f send %.4f s\n", nq, n_ctx, chunk_size, parts.size(), t_acquire.s(), t_prep.s(), t_issue.s(),
-                    t_collect.s(), t_emit_wait.s(), t_format.s(), t_send.s());
+                            "emitter: wait %.4f format %.4f send %.4f | wall %.4f (first batch issued after %.4f, last results on the host %.4f before the end) s\n",
+                    nq, n_ctx, chunk_size, parts.size(), t_acquire.s(), t_prep.s(), t_issue.s(), t_collect.s(), t_emit_wait.s(), t_format.s(), t_send.s(),
+                    std::chrono::duration<double>(now() - t_start).count(), std::chrono::duration<double>(t_first_issue - t_start).count(),
+                    std::chrono::duration<double>(now() - t_last_collect).count());
     }
 };
 }  // namespace
@@ -1829,6 +1899,33 @@ RXH_API int rxh_raxtax_sharded(rtx_ctx* const* ctxs, size_t n_ctx, const rxh_que
         const u32 ML = rtx_index_max_levels(ctxs[0]);
         for (size_t r = 0; r < n_ctx; ++r)
             if (rtx_index_n_refs(ctxs[r]) != tree.num_tips) throw Error("a context's index does not belong to this tree");
+        {
+            // every shard on its own GPU: the exchanges are NCCL collectives inside the device library (rtx_shard_run / rtx_shard_gather),
+            // one driver thread per rank.  Several shards on one GPU (tests, a database too large for the GPUs at hand): NCCL does not
+            // take two ranks on one device, the exchanges below are staged through page-locked host memory instead.
+            bool distinct = n_ctx > 1;
+            for (size_t a = 0; a < n_ctx && distinct; ++a)
+                for (size_t b = a + 1; b < n_ctx; ++b) distinct &= rtx_ctx_device(ctxs[a]) != rtx_ctx_device(ctxs[b]);
+            if (distinct && getenv("RXH_SHARD_NO_NCCL") == nullptr) {
+                unsigned char uid[RTX_COMM_UNIQUE_ID_BYTES];
+                if (rtx_comm_unique_id(uid)) throw Error(std::string("rtx_comm_unique_id: ") + rtx_last_error(nullptr));
+                std::vector<int> rcs(n_ctx, 0);
+                {
+                    std::vector<std::thread> th;  // ncclCommInitRank blocks until every rank has joined
+                    for (size_t r = 0; r < n_ctx; ++r) th.emplace_back([&, r] { rcs[r] = rtx_comm_init(ctxs[r], uid, (int)r, (int)n_ctx); });
+                    for (auto& t : th) t.join();
+                }
+                for (size_t r = 0; r < n_ctx; ++r)
+                    if (rcs[r]) throw Error(std::string("rtx_comm_init: ") + rtx_last_error(ctxs[r]));
+                if (chunk_size == 0) chunk_size = std::min<size_t>(32768, std::max<size_t>(2048, (nq + 3) / 4));
+                Worker w{tree, qs, nq, chunk_size, skip_exact_matches, raw_confidence, tsv, sender, sender_user, logger, logger_user};
+                w.run(ctxs, n_ctx, true);
+                for (size_t r = 0; r < n_ctx; ++r) rtx_comm_destroy(ctxs[r]);
+                if (warnings) *warnings = w.warned.load() ? 1 : 0;
+                if (w.failed.load()) throw Error(w.err);
+                return 0;
+            }
+        }
         if (chunk_size == 0) chunk_size = std::min<size_t>(std::max<size_t>(nq, 1), 8192);
         struct RankOut {
             std::vector<u32> begin, first;

@@ -1,0 +1,113 @@
+"""Reference-sharded mode over NCCL inside the device library (rtx_comm_init / rtx_shard_run / rtx_shard_gather): needs >= 2 GPUs
+(NCCL does not accept two ranks on one device), so it is skipped on the single-GPU test box and run with `gpurun --gpus N`.
+One thread per GPU drives one rank, as the C++ host driver does; the ranks could equally be processes."""
+import threading
+
+import numpy as np
+import pytest
+
+from raxtax_b200 import capi, synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _n_gpus():
+    import torch
+
+    return torch.cuda.device_count()
+
+
+def _run_ranks(n, fn):
+    errs, outs = [None] * n, [None] * n
+
+    def body(r):
+        try:
+            outs[r] = fn(r)
+        except BaseException as e:  # noqa: BLE001
+            errs[r] = e
+
+    th = [threading.Thread(target=body, args=(r,)) for r in range(n)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join(timeout=600)
+    for e in errs:
+        if e is not None:
+            raise e
+    return outs
+
+
+@pytest.mark.parametrize("skip,raw,sub_batch", [(False, False, 0), (True, False, 300), (False, True, 777)])
+def test_nccl_sharded_equals_unsharded(skip, raw, sub_batch):
+    n = min(_n_gpus(), 8)
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs")
+    ds = synth.generate("c2", n_refs=24_000, n_queries=2_304, measure=False)
+    ht = capi.Tree.new(ds.ref_lineages, ds.ref_off, ds.ref_codes)
+    eo, eids = ht.exact_batch(ds.query_off, ds.query_codes)
+    c0 = capi.Context(0)
+    c0.upload_tree(ht)
+    want = c0.classify(ds.query_off, ds.query_codes, eo, eids, skip_exact=skip, raw_conf=raw)
+    c0.close()
+    N = ht.num_tips
+    cuts = np.array([0] + sorted(int(x) for x in np.random.default_rng(5).choice(np.arange(1, N), n - 1, replace=False)) + [N], np.uint64)
+    uid = capi.Context.comm_unique_id()
+
+    def rank(r):
+        c = capi.Context(r)
+        try:
+            c.comm_init(uid, r, n)
+            c.upload_tree_sharded(ht, n, r, cuts)
+            c.set_option(capi.RTX_OPT_SUB_BATCH, sub_batch)
+            outs = []
+            for _ in range(2):  # twice: buffers, communicator and agreed sub-batch size are reused
+                outs.append(c.classify(ds.query_off, ds.query_codes, eo, eids, skip_exact=skip, raw_conf=raw, shard_root=0))
+            prof = c.profile()
+            return outs, prof
+        finally:
+            c.close()
+
+    res = _run_ranks(n, rank)
+    for r in range(1, n):
+        for o in res[r][0]:
+            assert int(o.result_begin[-1]) == 0 and len(o.first_ref) == 0
+    prof0 = res[0][1]
+    assert prof0["allreduce"]["launches"] >= 2 and prof0["allreduce_bytes"] > 0 and prof0["gather"]["launches"] >= 2
+    for got in res[0][0]:
+        assert np.array_equal(got.result_begin, want.result_begin)
+        assert np.array_equal(got.n_kmers, want.n_kmers)
+        assert np.array_equal(got.first_ref, want.first_ref) and np.array_equal(got.n_levels, want.n_levels)
+        lev = np.arange(want.confidence.shape[1])[None, :] < want.n_levels[:, None]  # entries beyond a line's levels are unspecified
+        assert np.array_equal(got.confidence[lev], want.confidence[lev])
+        assert np.max(np.abs(got.local_signal - want.local_signal)) <= 1e-12
+        assert np.max(np.abs(got.global_signal - want.global_signal)) <= 1e-9
+
+
+@pytest.mark.parametrize("skip", [False, True])
+def test_host_driver_sharded_over_nccl_equals_unsharded(skip):
+    """rxh_raxtax_sharded with every shard on its own GPU (driver threads + NCCL inside the device library) sends the strings the
+    unsharded driver sends, in query order."""
+    n = min(_n_gpus(), 8)
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs")
+    ds = synth.generate("c2", n_refs=12_000, n_queries=1_500, measure=False)
+    ht = capi.Tree.new(ds.ref_lineages, ds.ref_off, ds.ref_codes)
+    qs = capi.Queries.new(ds.query_labels, ds.query_off, ds.query_codes)
+    c0 = capi.Context(0)
+    c0.upload_tree(ht)
+    want, logs_w, warn_w = capi.raxtax(c0, qs, ht, skip_exact_matches=skip, tsv=True)
+    c0.close()
+    N = ht.num_tips
+    cuts = np.array([N * r // n for r in range(n)] + [N], np.uint64)
+    ctxs = [capi.Context(r) for r in range(n)]
+    try:
+        for r, c in enumerate(ctxs):
+            c.upload_tree_sharded(ht, n, r, cuts)
+        for chunk in (0, 400):
+            got, logs, warn = capi.raxtax(ctxs, qs, ht, skip_exact_matches=skip, chunk_size=chunk, tsv=True, sharded=True)
+            assert [g[0] for g in got] == ds.query_labels
+            assert got == want, f"chunk {chunk}"
+            assert sorted(logs) == sorted(logs_w) and warn == warn_w
+    finally:
+        for c in ctxs:
+            c.close()
