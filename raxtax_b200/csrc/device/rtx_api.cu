@@ -382,8 +382,8 @@ RTX_API int rtx_ctx_set_option(rtx_ctx* ctx, int option, int64_t value) {
             ctx->hit_chunks = (int)value;
             return RTX_OK;
         case RTX_OPT_HITCOUNT_TUNE:
-            REQUIRE(value == 1 || (value >= 0 && value < 1000 && (value % 10 == 0 || value % 10 == 2 || value % 10 == 4)),
-                    "bad hit-count tuning word");  // 1: query-group kernel with L1-bypassing row loads
+            REQUIRE((value >= 0 && value <= 4) || (value >= 10 && value < 1000 && (value % 10 == 0 || value % 10 == 2 || value % 10 == 4)),
+                    "bad hit-count tuning word");  // 1..4: load form of the query-group kernel (launch_hitcount_group); >= 10: single-query kernel geometry
             ctx->hit_tune = (int)value;
             return RTX_OK;
         default:
@@ -1104,10 +1104,15 @@ static cudaError_t launch_hitcount_group(rtx_ctx* c, int q_base, int qb, int G) 
         c->segmax_valid = true;
         return cudaGetLastError();
     };
-    const bool lockstep = n_chunks > 1, l1a = lockstep || c->hit_tune != 1;
+    // hit_tune: 0 default, 1 = .v2 row loads that bypass the L1, 2 = .v2 row loads through the L1 (the round-1 kernel),
+    // 3 = one-line loads (lane words l and l + 32) through the L1, 4 = one-line loads that bypass the L1
+    const int mode = c->hit_tune ? c->hit_tune : 2;
+    const bool lockstep = n_chunks > 1, l1a = lockstep || mode == 2 || mode == 3, split = !lockstep && (mode == 3 || mode == 4);
     c->hit_kernel = "hitcount_group_kernel<2, " + std::to_string(NP) + ", " + (lockstep ? "true" : "false") + ", " + std::to_string(kHitGroupMaxThreads) +
-                    ", 1, " + (l1a ? "true" : "false") + "> (" + std::to_string(G) + " queries per CTA)";
+                    ", 1, " + (l1a ? "true" : "false") + ", " + (split ? "true" : "false") + "> (" + std::to_string(G) + " queries per CTA)";
     if (lockstep) return go(hitcount_group_kernel<V, NP, true, kHitGroupMaxThreads, 1>);
+    if (split) return l1a ? go(hitcount_group_kernel<V, NP, false, kHitGroupMaxThreads, 1, true, true>)
+                          : go(hitcount_group_kernel<V, NP, false, kHitGroupMaxThreads, 1, false, true>);
     if (!l1a) return go(hitcount_group_kernel<V, NP, false, kHitGroupMaxThreads, 1, false>);  // L1 bypass (measured option)
     return go(hitcount_group_kernel<V, NP, false, kHitGroupMaxThreads, 1>);
 }
@@ -1126,7 +1131,7 @@ static cudaError_t launch_hitcount_tuned(rtx_ctx* c, int q_base, int qb, u32 kma
         if (kmax < (1u << 13)) return launch_hitcount_group<13>(c, q_base, qb, G);
         return launch_hitcount_group<16>(c, q_base, qb, G);
     }
-    const int tune = c->hit_tune ? c->hit_tune : 12;  // default: 2 words per lane, register double buffering
+    const int tune = c->hit_tune >= 10 ? c->hit_tune : 12;  // default: 2 words per lane, register double buffering
     const int V = tune % 10 ? tune % 10 : 4;
     const bool PF = (tune / 10) % 10 != 0;
     const int nwarps = tune / 100;

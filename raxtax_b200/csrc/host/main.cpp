@@ -63,7 +63,8 @@ void usage() {
             "      --shard-references               With --gpus N: every GPU holds 1/N of the references (databases too large to\n"
             "                                       replicate) instead of the whole index\n"
             "      --batch <N>                      Queries per device batch [default: all]\n"
-            "  -v / -q                              More / less output\n");
+            "  -v, --verbose...                     Increase logging verbosity (repeatable: -vv)\n"
+            "  -q, --quiet...                       Decrease logging verbosity (repeatable: -qq)\n");
 }
 
 bool read_file(const std::string& path, std::string* out) {  // utils::get_reader (utils.rs:42-60): gz by extension; gzopen also reads plain files
@@ -79,13 +80,31 @@ bool read_file(const std::string& path, std::string* out) {  // utils::get_reade
 struct Writers {
     FILE *primary = nullptr, *tsv = nullptr, *log = nullptr, *progress = nullptr;
     int verbosity = 3;
+    std::string pending_labels;  // labels whose result lines are written but possibly still in a stdio buffer
+    size_t pending_n = 0;
+    bool failed = false;
+
+    // The reference writes unbuffered Files in the order result, then progress (main.rs:128-134): the progress file can never run
+    // ahead of the output.  Here the streams are block-buffered, so the labels are held back until the result lines they stand for
+    // have been flushed; a kill at any point leaves raxtax.ckp listing only queries whose lines are complete in raxtax.out / .tsv
+    // (lines of queries not yet listed are what check_incomplete_output removes on resume).
+    bool commit() {
+        if (pending_n == 0) return !failed;
+        if ((tsv && fflush(tsv) != 0) || fflush(primary) != 0) failed = true;
+        if (!failed && (fwrite(pending_labels.data(), 1, pending_labels.size(), progress) != pending_labels.size() || fflush(progress) != 0)) failed = true;
+        pending_labels.clear();
+        pending_n = 0;
+        return !failed;
+    }
 };
 
 int send_cb(void* user, const char* label, const char* primary, const char* tsv) {  // writer thread body (main.rs:128-134)
     Writers* w = (Writers*)user;
-    if (w->tsv && tsv) fprintf(w->tsv, "%s\n", tsv);
-    if (fprintf(w->primary, "%s\n", primary) < 0) return 1;
-    fprintf(w->progress, "%s\n", label);
+    if (w->tsv && tsv && (fputs(tsv, w->tsv) < 0 || fputc('\n', w->tsv) == EOF)) return 1;
+    if (fputs(primary, w->primary) < 0 || fputc('\n', w->primary) == EOF) return 1;
+    w->pending_labels += label;
+    w->pending_labels += '\n';
+    if (++w->pending_n >= 256 && !w->commit()) return 1;
     return 0;
 }
 
@@ -107,10 +126,29 @@ bool is_dir(const std::string& p) {
     struct stat st;
     return stat(p.c_str(), &st) == 0 && S_ISDIR(st.st_mode);
 }
-std::string absolute(const std::string& p) {  // std::path::absolute: no symlink resolution, no existence check
-    std::error_code ec;
-    auto a = std::filesystem::absolute(p, ec);
-    return ec ? p : a.lexically_normal().string();
+// std::path::absolute (Unix): the path joined onto the working directory when relative, `.` components and repeated separators
+// dropped, `..` KEPT, no symlink resolution, no existence check -- the string raxtax.json's fingerprint compares (io.rs:23-45)
+std::string absolute(const std::string& p) {
+    std::string full = p;
+    if (p.empty() || p[0] != '/') {
+        std::error_code ec;
+        const auto cwd = std::filesystem::current_path(ec);
+        if (ec) return p;
+        full = cwd.string() + "/" + p;
+    }
+    std::string out;
+    size_t i = 0;
+    while (i < full.size()) {
+        while (i < full.size() && full[i] == '/') ++i;
+        size_t j = i;
+        while (j < full.size() && full[j] != '/') ++j;
+        if (j > i && !(j - i == 1 && full[i] == '.')) {
+            out += '/';
+            out.append(full, i, j - i);
+        }
+        i = j;
+    }
+    return out.empty() ? "/" : out;
 }
 bool read_raw(const std::string& path, std::string* out) {
     FILE* f = fopen(path.c_str(), "rb");
@@ -203,9 +241,30 @@ bool json_find(const std::string& j, const char* key, std::string* raw) {
                     case 'r': o += '\r'; break;
                     case 't': o += '\t'; break;
                     case 'u':
-                        if (p + 4 < j.size()) {
-                            o += (char)strtol(j.substr(p + 1, 4).c_str(), nullptr, 16);
+                        if (p + 4 < j.size()) {  // \uXXXX, a surrogate pair for code points beyond the BMP -> UTF-8
+                            unsigned long cp = strtoul(j.substr(p + 1, 4).c_str(), nullptr, 16);
                             p += 4;
+                            if (cp >= 0xD800 && cp < 0xDC00 && p + 6 < j.size() && j[p + 1] == '\\' && j[p + 2] == 'u') {
+                                const unsigned long lo = strtoul(j.substr(p + 3, 4).c_str(), nullptr, 16);
+                                if (lo >= 0xDC00 && lo < 0xE000) {
+                                    cp = 0x10000 + ((cp - 0xD800) << 10) + (lo - 0xDC00);
+                                    p += 6;
+                                }
+                            }
+                            if (cp < 0x80) o += (char)cp;
+                            else if (cp < 0x800) {
+                                o += (char)(0xC0 | (cp >> 6));
+                                o += (char)(0x80 | (cp & 0x3F));
+                            } else if (cp < 0x10000) {
+                                o += (char)(0xE0 | (cp >> 12));
+                                o += (char)(0x80 | ((cp >> 6) & 0x3F));
+                                o += (char)(0x80 | (cp & 0x3F));
+                            } else {
+                                o += (char)(0xF0 | (cp >> 18));
+                                o += (char)(0x80 | ((cp >> 12) & 0x3F));
+                                o += (char)(0x80 | ((cp >> 6) & 0x3F));
+                                o += (char)(0x80 | (cp & 0x3F));
+                            }
                         }
                         break;
                     default: o += j[p];
@@ -291,8 +350,10 @@ int main(int argc, char** argv) {
         else if (s == "--gpus") a.gpus = std::max(1, atoi(val("--gpus")));
         else if (s == "--shard-references") a.shard_refs = true;
         else if (s == "--batch") a.batch = (size_t)atoll(val("--batch"));
-        else if (s == "-v") a.verbosity = 4;
-        else if (s == "-q") a.verbosity = 2;
+        else if (s == "--verbose") a.verbosity = std::min(5, a.verbosity + 1);  // clap_verbosity_flag::Verbosity<InfoLevel> (io.rs:152-153)
+        else if (s == "--quiet") a.verbosity = std::max(0, a.verbosity - 1);
+        else if (s.size() >= 2 && s[0] == '-' && s.find_first_not_of('v', 1) == std::string::npos) a.verbosity = std::min(5, a.verbosity + (int)s.size() - 1);  // -v, -vv, ...
+        else if (s.size() >= 2 && s[0] == '-' && s.find_first_not_of('q', 1) == std::string::npos) a.verbosity = std::max(0, a.verbosity - ((int)s.size() - 1));
         else if (s == "-h" || s == "--help") {
             usage();
             return 0;
@@ -488,6 +549,10 @@ int main(int argc, char** argv) {
                      : rxh_raxtax_multi(ctxs.data(), ctxs.size(), queries, tree, a.skip_exact_matches, a.raw_confidence, a.batch, send_cb, &w,
                                         a.tsv, log_cb, &w, &warnings);
     double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    if (!w.commit() && rc == 0) {  // the labels still held back: results first, then progress
+        fprintf(stderr, "\x1b[31m[ERROR]\x1b[0m Could not write the result files\n");
+        return EX_IOERR_;
+    }
     if (rc != 0) {
         fprintf(stderr, "\x1b[31m[ERROR]\x1b[0m Error while sending results to IO-thread!: %s\n", rxh_last_error());
         return EX_TEMPFAIL_;

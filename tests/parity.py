@@ -17,7 +17,14 @@ CONF_TOL = 1e-6
 
 
 def oracle_tree_from_ds(orc, ds):
-    return orc.Tree.new(ds.ref_lineages, [ds.ref_seq(i) for i in range(ds.n_refs)])
+    """orc.Tree over a synthetic data set, handing the packed arrays straight to the C side (a Python list of a million sequences
+    takes longer to build than the tree)."""
+    import ctypes as C
+
+    blob = "\n".join(ds.ref_lineages).encode()
+    off = np.ascontiguousarray(ds.ref_off, np.uint64)
+    codes = np.ascontiguousarray(ds.ref_codes if len(ds.ref_codes) else np.zeros(1, np.uint8), np.uint8)
+    return orc.Tree(orc.lib().orc_tree_new(ds.n_refs, blob, len(blob), off.ctypes.data_as(C.POINTER(C.c_uint64)), codes.ctypes.data_as(C.POINTER(C.c_uint8))))
 
 
 def hist_from_counts(counts_row, K):
@@ -132,3 +139,48 @@ def compare_batch(orc_out, dev_out, n_queries, checker=None, probs=None):
         else:
             bad.append(q)
     return ok, tol, bad
+
+
+# ---- text level: the strings the host driver / the CLI write, against the oracle's ------------------------------------------
+def results_from_text(lines, first_ref_of_lineage):
+    """raxtax.out lines of one query (`label \\t lineage \\t c1,c2,.. \\t local \\t global`, lineage.rs:17-30) -> the tuples
+    TolerantChecker.acceptable takes."""
+    out = []
+    for l in lines:
+        f = l.split("\t")
+        out.append((first_ref_of_lineage[f[1]], np.array([float(x) for x in f[2].split(",")]), float(f[3]), float(f[4])))
+    return out
+
+
+def assert_text_parity(got_by_query, exp_by_query, orc_out, ot, max_tolerated_frac=0.05, what=""):
+    """got / exp: per query, the list of its raxtax.out lines.  Every query whose lines differ from the oracle's must be one of the
+    outcomes the reference itself could have produced (TolerantChecker: fallback ties, rounding boundaries); returns their number."""
+    assert len(got_by_query) == len(exp_by_query)
+    lin = ot.lineages
+    first = {}
+    for i, l in enumerate(lin):
+        first.setdefault(l, i)
+    checker = TolerantChecker(ot.flatten(), ot.num_tips)
+    tolerated, bad = 0, []
+    for q, (g, e) in enumerate(zip(got_by_query, exp_by_query)):
+        if g == e:
+            continue
+        dev = results_from_text(g, first)
+        ora = orc_out["results"].for_query(q)
+        if checker.acceptable(orc_out["probs"][q], dev, ora):
+            tolerated += 1
+        else:
+            bad.append(q)
+    assert not bad, f"{what}: {len(bad)} queries differ from the oracle's text beyond tie / rounding tolerance, first {bad[:5]}: got {got_by_query[bad[0]]} expected {exp_by_query[bad[0]]}"
+    assert tolerated <= max(1, int(max_tolerated_frac * len(exp_by_query))), f"{what}: {tolerated} of {len(exp_by_query)} queries needed tolerance"
+    print(f"{what}: {len(exp_by_query) - tolerated} of {len(exp_by_query)} queries identical text, {tolerated} within tie / rounding tolerance")
+    return tolerated
+
+
+def lines_by_query(text, labels):
+    """raxtax.out text -> per query (in the order of `labels`) its lines; the lines of a query are contiguous (raxtax.rs:85-88)."""
+    by = {l: [] for l in labels}
+    for line in text.split("\n"):
+        if line:
+            by[line.split("\t", 1)[0]].append(line)
+    return [by[l] for l in labels]

@@ -255,10 +255,9 @@ def test_diptera_sample_self_classification(oracle, ctx):
         golden = os.path.join(GOLDEN, "diptera_sample.skip.out" if skip else "diptera_sample.default.out")
         qs = capi.Queries.from_fasta(text)
         sent, _, _ = capi.raxtax(ctx, qs, ht, skip_exact_matches=skip)
-        got = "\n".join(s[1] for s in sent) + "\n"
-        exp = open(golden).read()
-        same = sum(a == b for a, b in zip(got.split("\n"), exp.split("\n")))
-        assert same >= 0.98 * len(exp.split("\n")), "raxtax.out lines vs golden"
+        # every query whose lines differ from the golden text must be a documented tie / rounding-boundary case (tests/parity.py)
+        parity.assert_text_parity([s[1].split("\n") for s in sent], parity.lines_by_query(open(golden).read(), labels), o, ot,
+                                  what=f"diptera sample vs golden ({'skip' if skip else 'default'})")
 
 
 # ---- edge cases ---------------------------------------------------------------------------------------------------------
@@ -345,16 +344,16 @@ def test_c2_scale_properties(ctx):
     assert n_override > 0
 
 
-@pytest.mark.parametrize("cfg,nq,skip", [("c3", 192, False), ("c4", 96, True)])
+@pytest.mark.parametrize("cfg,nq,skip", [("c3", 256, False), ("c4", 256, True)])
 def test_full_scale_configs(oracle, ctx, cfg, nq, skip):
     """BASELINE configs 3 (1 M COI refs) and 4 (500 k 16S-like 1500 bp refs, --skip-exact-matches) at their full reference
-    counts: size-independent properties of every query, then full parity of the first 48 queries against the CPU oracle
-    built over the same references (RTX_FULL_ORACLE=0 skips the oracle part; it costs 20-60 s of host time per config)."""
+    counts: size-independent properties of every query, then full parity of all 256 queries against the CPU oracle built over
+    the same references, on all host cores (RTX_FULL_ORACLE=0 skips the oracle part; it costs ~1-2 min of host time per config)."""
     ds = synth.generate(cfg, n_queries=nq, measure=False)
     ht, eo, eids, dev, _ = _check_scale_properties(ctx, ds, skip=skip)
     assert ht.num_tips == synth.CONFIGS[cfg][0]
     if os.environ.get("RTX_FULL_ORACLE", "1") != "0":
-        n = 48
+        n = nq
         ot = parity.oracle_tree_from_ds(oracle, ds)
         q_off = ds.query_off[: n + 1]
         q_codes = ds.query_codes[: int(q_off[-1])]
@@ -364,7 +363,7 @@ def test_full_scale_configs(oracle, ctx, cfg, nq, skip):
         checker = parity.TolerantChecker(ot.flatten(), ot.num_tips)
         ok, tol, bad = parity.compare_batch(o, dev, n, checker, o["probs"])
         assert not bad, f"{len(bad)} queries differ from the oracle at full scale, first {bad[:3]}"
-        assert tol <= max(1, n // 10)
+        assert tol <= max(1, n // 20)
         print(f"{cfg}: {ok} of {n} queries identical to the oracle at N = {ht.num_tips}, {tol} within tie/rounding tolerance")
 
 
@@ -407,7 +406,7 @@ def test_reference_sharded_matches_oracle(oracle, n_shards, skip, raw):
 
 
 # ---- the raxtax command-line binary: unchanged CLI flags and output files ---------------------------------
-def test_cli_binary_writes_reference_format_files(tmp_path):
+def test_cli_binary_writes_reference_format_files(oracle, tmp_path):
     import subprocess
 
     from raxtax_b200 import _build
@@ -421,7 +420,12 @@ def test_cli_binary_writes_reference_format_files(tmp_path):
         out = (prefix / "raxtax.out").read_text().split("\n")
         exp = open(os.path.join(GOLDEN, golden)).read().split("\n")
         assert len(out) == len(exp)
-        assert sum(a == b for a, b in zip(out, exp)) >= 0.98 * len(exp)
+        text = open(fasta).read()
+        ot = oracle.Tree.from_fasta(text)
+        labels, q_off, q_codes = oracle.parse_queries(text)
+        o = ot.classify(q_off, q_codes, skip_exact=skip, threads=4, chunk_size=16, want_probs=True)
+        parity.assert_text_parity(parity.lines_by_query("\n".join(out), labels), parity.lines_by_query("\n".join(exp), labels), o, ot,
+                                  what=f"CLI raxtax.out vs golden ({'skip' if skip else 'default'})")
         tsv = (prefix / "raxtax.tsv").read_text().split("\n")
         assert len(tsv) == len(exp) and tsv[0].count("\t") == 15  # label + 6 x (rank, conf) + 2 signals + sequence
         assert len((prefix / "raxtax.ckp").read_text().splitlines()) == 400

@@ -27,6 +27,11 @@ ctx.batch_upload(ds.query_off, ds.query_codes, eo, eids)
 OPT = {"G": capi.RTX_OPT_HITCOUNT_GROUP, "C": capi.RTX_OPT_HITCOUNT_CHUNKS, "T": capi.RTX_OPT_HITCOUNT_TUNE, "M": capi.RTX_OPT_HITCOUNT_MAX_TILES,
        "S": capi.RTX_OPT_SUB_BATCH, "W": capi.RTX_OPT_WALK_VARIANT}
 ref = None
+ref_counts = None
+n_chk = min(192, ds.n_queries)
+chk_off = ds.query_off[: n_chk + 1]
+chk_codes = ds.query_codes[: int(chk_off[-1])]
+chk_eo, chk_eids = tree.exact_batch(chk_off, chk_codes)
 for cfg in configs:
     f = {k: int(v) for k, v in re.findall(r"([GCTMSW])(\d+)", cfg)}
     for k, o in OPT.items():
@@ -45,6 +50,10 @@ for cfg in configs:
         ref = out.hist.copy()
     ms = p["hitcount"]["total_ms"] / 3  # per pass over the whole batch (a pass is several launches when sub-batched)
     gbs = p["bitrow_bytes"] / 3 / ms / 1e6
-    print(json.dumps(dict(cfg=cfg, hitcount_ms=round(ms, 3), bitrow_GBps=round(gbs, 1), prob_ms=round(p["prob"]["total_ms"] / 3, 3),
+    small = ctx.classify(chk_off, chk_codes, chk_eo, chk_eids, taps=("counts",))  # the count vectors themselves (the layout inside a tile is the kernel's business)
+    if ref_counts is None:
+        ref_counts = small.counts.copy()
+    counts_same = bool(np.array_equal(small.counts, ref_counts))
+    print(json.dumps(dict(cfg=cfg, kernel=ctx.hitcount_kernel_name(), counts_identical=counts_same, hitcount_ms=round(ms, 3), bitrow_GBps=round(gbs, 1), prob_ms=round(p["prob"]["total_ms"] / 3, 3),
                           prefix_ms=round(p["prefix"]["total_ms"] / 3, 3), walk_ms=round(p["walk"]["total_ms"] / 3, 3),
                           hist_identical=bool(np.array_equal(out.hist, ref)))), flush=True)
