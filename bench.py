@@ -463,7 +463,7 @@ def main():
     n_launch = max(hc["launches"], 1)
     hc_ms = hc["total_ms"] / n_launch
     hc_s = hc_ms * 1e-3
-    bitrow_bytes = prof["bitrow_bytes"] / n_launch      # SM-side: every selected row slice once per query + the count vectors
+    bitrow_bytes = prof["bitrow_bytes"] / n_launch      # SM side: every selected bit-row slice once per query + the count vectors
     csr_bytes = prof["csr_equiv_bytes"] / n_launch      # what the reference's CSR walk would move (SURVEY 8d primary figure)
     q_per_launch = nq * reps_k / n_launch
     # compulsory HBM traffic of one launch: the bit matrix once (L2 blocking keeps a tile group's slice on chip while all queries of
@@ -471,38 +471,44 @@ def main():
     compulsory = ctx.index_bitrow_bytes + q_per_launch * ctx.shard_refs * 2
     sm_mhz = clocks.get("sm_mhz") or 1965.0
     n_sms = torch.cuda.get_device_properties(local_rank).multi_processor_count
-    alu_peak = n_sms * 4 * 0.5 * sm_mhz * 1e6  # warp instructions/s the alu pipe (LOP3, IADD3, SHF, PRMT ...) can issue: 0.5 per clock and SMSP
-    tj = {}
+    tj_all = {}
     tpath = os.path.join(ROOT, "profiles", "hitcount_traffic.json")
     if os.path.exists(tpath):
         try:
-            tj = json.load(open(tpath)).get(name, {})
+            tj_all = json.load(open(tpath))
         except Exception:
-            tj = {}
-    # ncu figures of one launch of THIS workload (profiles/hitcount_traffic.json, taken with tools/ncu_hitcount.sh), scaled to the
-    # live launch by its row-slice count: instructions and DRAM bytes per row slice are properties of the kernel + data
+            tj_all = {}
+    tj = tj_all.get(name, {})
+    dp = tj_all.get("datapath", {})
+    # The limiter ncu names is the SM's memory front end, not HBM: the kernel streams scattered 256-byte slices of L2-resident bit rows
+    # through the L1 (fill + read-out).  Its ceiling is MEASURED: the same access pattern with no arithmetic at all
+    # (tools/micro/smem_tma_probe.cu, profiles/r2_datapath_probe.txt), in bytes per clock and SM.
+    path_bpc = float(dp.get("ldg_scattered_256B_slices_B_per_clk_per_SM", 71.2))
+    path_peak = path_bpc * n_sms * sm_mhz * 1e6 / 1e9  # GB/s at the clock sampled during the run
+    achieved = bitrow_bytes / hc_s / 1e9 if hc_s > 0 else 0.0
+    # ncu figures of one launch of THIS workload (profiles/hitcount_traffic.json), DRAM bytes scaled to the live launch by its row-slice bytes
     scale = (bitrow_bytes / tj["bitrow_bytes_per_launch"]) if tj.get("bitrow_bytes_per_launch") else None
-    traffic = tj.get("dram_bytes_per_launch") * scale if scale and tj.get("dram_bytes_per_launch") else None
-    alu_inst = tj.get("alu_inst_per_launch") * scale if scale and tj.get("alu_inst_per_launch") else None
+    traffic = tj["dram_bytes_per_launch"] * scale if scale and tj.get("dram_bytes_per_launch") else None
     kernel_ms = {k: prof[k]["total_ms"] / reps_k for k in ("kmers", "hitcount", "fixup", "prob", "prefix", "walk")}
     roofline = {
         "kernel": hit_kernel,
-        "bound": "sm (alu-pipe issue: LOP3 carry-save adders; L1 data pipe next) -- NOT hbm: the bit matrix is L2-blocked, see `hbm` and `dram`",
-        "achieved": (alu_inst / hc_s / 1e9) if alu_inst and hc_s > 0 else None, "peak": alu_peak / 1e9, "unit": "G warp-inst/s (alu pipe)",
-        "frac": (alu_inst / hc_s / alu_peak) if alu_inst and hc_s > 0 else None,
+        "bound": "sm-l1 (L2 -> L1 fill -> register path of scattered 256-byte bit-row slices; ncu: L1 data pipe %s %%, alu pipe %s %%, DRAM %s of peak) -- "
+                 "not hbm: the bit matrix is L2-blocked, see `hbm` and `dram`" % (tj.get("l1_data_pipe_pct", "?"), tj.get("alu_pipe_pct", "?"),
+                                                                                   ("%.0f %%" % (100 * traffic / hc_s / 1e9 / peak)) if traffic and hc_s > 0 else "?"),
+        "achieved": achieved, "peak": path_peak, "unit": "GB/s", "frac": achieved / path_peak if path_peak > 0 else None,
+        "peak_source": "measured ceiling of the path: %.1f B/clk/SM x %d SMs x %.0f MHz (%s)" % (path_bpc, n_sms, sm_mhz, dp.get("source", "default")),
+        "algorithmic_bytes_per_launch": bitrow_bytes,
+        "algorithmic_bytes_note": "K_q * row_words * 4 + 2 * n_pad per query (DESIGN 4): every selected bit-row slice enters an SM once per query",
         "traffic": traffic,
         "launch_ms": hc_ms, "launches_per_step": n_launch / reps_k, "queries_per_launch": q_per_launch,
         "timed": "kernels serialised, one CUDA event pair per launch on the launching stream (RTX_OPT_PROFILE)",
-        "alu": {"inst_per_launch": alu_inst, "peak_inst_per_s": alu_peak, "sm_mhz": sm_mhz, "n_sms": n_sms,
-                "source": tj.get("source") if alu_inst else "no ncu record for this workload in profiles/hitcount_traffic.json"},
+        "ncu": {k: tj.get(k) for k in ("kernel_symbol", "launch_ms_ncu", "alu_pipe_pct", "l1_data_pipe_pct", "lts_pct", "l1_hit_pct", "l2_hit_pct", "warps_active_pct",
+                                       "registers", "source")} if tj else None,
         "hbm": {"bound": "hbm", "algorithmic_bytes_per_launch": compulsory, "achieved": compulsory / hc_s / 1e9 if hc_s > 0 else None, "peak": peak,
                 "unit": "GB/s", "frac": compulsory / hc_s / 1e9 / peak if hc_s > 0 else None, "peak_source": peak_src,
                 "note": "compulsory traffic: bit matrix once per launch + 2*N bytes of counts per query"},
         "dram": ({"bytes_per_launch": traffic, "gbs": traffic / hc_s / 1e9, "frac_of_peak": traffic / hc_s / 1e9 / peak,
-                  "source": tj.get("source")} if traffic and hc_s > 0 else None),
-        "sm_side_bytes": {"bitrow_format_bytes_per_launch": bitrow_bytes, "gbs": bitrow_bytes / hc_s / 1e9 if hc_s > 0 else None,
-                          "x_hbm_peak": bitrow_bytes / hc_s / 1e9 / peak if hc_s > 0 else None,
-                          "note": "K_q*row_words*4 + 2*n_pad per query: row slices entering the SMs (served by L2/L1), not an HBM figure"},
+                  "x_compulsory": traffic / compulsory, "source": tj.get("source")} if traffic and hc_s > 0 else None),
         "csr_equivalent": {"bytes_per_launch": csr_bytes, "gbs": csr_bytes / hc_s / 1e9 if hc_s > 0 else None,
                            "note": "4*hits+2*N per query: what the reference's CSR walk would move (SURVEY 8d primary figure)"},
         "serial_ms_per_step": serial_ms, "kernel_ms_per_step": kernel_ms,

@@ -12,7 +12,10 @@ KEYS = ['gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum
         'smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio', 'smsp__average_warps_issue_stalled_wait_per_issue_active.ratio',
         'smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio', 'smsp__average_warps_issue_stalled_mio_throttle_per_issue_active.ratio',
         'smsp__average_warps_issue_stalled_lg_throttle_per_issue_active.ratio', 'smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio',
-        'launch__shared_mem_per_block_dynamic', 'sm__cycles_elapsed.max']
+        'launch__shared_mem_per_block_dynamic', 'sm__cycles_elapsed.max', 'smsp__inst_executed_pipe_alu.sum', 'smsp__inst_executed_pipe_fma.sum',
+        'smsp__inst_executed_pipe_lsu.sum', 'sm__inst_executed_pipe_alu.sum', 'l1tex__data_pipe_lsu_wavefronts.sum', 'l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed',
+        'l1tex__t_sector_hit_rate.pct', 'l1tex__m_xbar2l1tex_read_bytes.sum', 'lts__t_bytes.sum', 'sm__cycles_active.avg', 'smsp__cycles_active.avg',
+        'l1tex__t_requests_pipe_lsu_mem_global_op_ld.sum', 'l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum']
 
 
 def raw(rep):
