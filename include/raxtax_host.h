@@ -37,6 +37,11 @@ rxh_tree* rxh_tree_new(size_t n, const char* lineage_blob, size_t blob_len, cons
  * parser::parse_reference_fasta_file does, parser.rs:37-44); a loaded tree carries its k_mer_map, which is then what the
  * device index is built from.  rxh_tree_save_bin = Tree::save_to_file.  32-bit ids only (not the `huge_db` feature). */
 rxh_tree* rxh_tree_from_bin(const void* data, size_t len);
+/* parser::parse_reference_fasta_file (parser.rs:37-44): the file is loaded as a binary database if it deserialises as one
+ * (*was_database = 1), else parsed as FASTA, plain or gz -- in blocks that are read / decompressed on one thread while the previous
+ * block is parsed on all the others, so that the text is never held in memory as a whole.  rxh_queries_from_file likewise
+ * (parser.rs:108-115, without the skip filter: rxh_queries_skip). */
+rxh_tree* rxh_tree_from_file(const char* path, int* was_database);
 int rxh_tree_save_bin(const rxh_tree* t, const char* path);
 void rxh_tree_free(rxh_tree* t);
 size_t rxh_tree_num_tips(const rxh_tree* t);
@@ -59,6 +64,7 @@ int rxh_tree_upload_sharded(const rxh_tree* t, rtx_ctx* ctx, uint32_t n_shards, 
 
 /* ---- queries ----------------------------------------------------------------------------------------------- */
 rxh_queries* rxh_queries_from_fasta(const char* text, size_t len);
+rxh_queries* rxh_queries_from_file(const char* path);
 rxh_queries* rxh_queries_new(size_t n, const char* label_blob, size_t blob_len, const uint64_t* seq_offsets, const uint8_t* seq_codes);
 /* drop the queries whose label is listed ('\n'-separated, the content of raxtax.ckp): parse_query_fasta_str's queries_to_skip
  * filter (parser.rs:108-115,150-153) */

@@ -48,7 +48,7 @@ def build_host(force=False):
     if force or _stale(HOST_LIB, HOST_SRC + hdr + [DEVICE_LIB]):
         cxx = os.environ.get("CXX", "g++")
         cmd = [cxx, "-O3", "-std=c++17", "-fPIC", "-shared", "-Wall", "-Wextra", "-I", INC, "-o", HOST_LIB] + HOST_SRC + [
-            "-L", PKG, "-lraxtax_b200", "-Wl,-rpath,$ORIGIN"]
+            "-L", PKG, "-lraxtax_b200", "-lz", "-lpthread", "-Wl,-rpath,$ORIGIN"]
         subprocess.check_call(cmd)
     return HOST_LIB
 

@@ -36,7 +36,7 @@ DEVICE_SYMBOLS = [
 ]
 # every symbol include/raxtax_host.h declares
 HOST_SYMBOLS = [
-    "rxh_last_error", "rxh_tree_from_fasta", "rxh_tree_from_bin", "rxh_tree_save_bin", "rxh_queries_skip", "rxh_tree_new", "rxh_tree_free", "rxh_tree_num_tips", "rxh_tree_lineage",
+    "rxh_last_error", "rxh_tree_from_fasta", "rxh_tree_from_file", "rxh_queries_from_file", "rxh_tree_from_bin", "rxh_tree_save_bin", "rxh_queries_skip", "rxh_tree_new", "rxh_tree_free", "rxh_tree_num_tips", "rxh_tree_lineage",
     "rxh_tree_csr", "rxh_tree_build_kmer_map", "rxh_tree_has_kmer_map", "rxh_tree_exact", "rxh_tree_index_desc", "rxh_tree_upload", "rxh_tree_upload_sharded", "rxh_queries_from_fasta", "rxh_queries_new",
     "rxh_queries_free", "rxh_queries_len", "rxh_queries_label", "rxh_queries_arrays", "rxh_raxtax", "rxh_raxtax_multi", "rxh_raxtax_sharded", "rxh_merge_shard_results", "rxh_exact_batch", "rxh_count_sender", "rxh_count_logger", "rxh_format_fixed", "rxh_release_buffers",
 ]
@@ -149,6 +149,10 @@ def host_lib():
     L.rxh_last_error.restype = C.c_char_p
     L.rxh_tree_from_fasta.restype = C.c_void_p
     L.rxh_tree_from_fasta.argtypes = [C.c_char_p, C.c_size_t]
+    L.rxh_tree_from_file.restype = C.c_void_p
+    L.rxh_tree_from_file.argtypes = [C.c_char_p, C.POINTER(C.c_int)]
+    L.rxh_queries_from_file.restype = C.c_void_p
+    L.rxh_queries_from_file.argtypes = [C.c_char_p]
     L.rxh_tree_from_bin.restype = C.c_void_p
     L.rxh_tree_from_bin.argtypes = [C.c_char_p, C.c_size_t]
     L.rxh_tree_save_bin.argtypes = [C.c_void_p, C.c_char_p]
@@ -570,6 +574,12 @@ class Tree:
         return cls(host_lib().rxh_tree_from_fasta(b, len(b)))
 
     @classmethod
+    def from_file(cls, path: str):  # parser::parse_reference_fasta_file (parser.rs:37-44) -> (tree, was_database)
+        was = C.c_int(0)
+        t = cls(host_lib().rxh_tree_from_file(path.encode(), C.byref(was)))
+        return t, bool(was.value)
+
+    @classmethod
     def from_bin(cls, data: bytes):  # Tree::load_from_file (tree.rs:154-164); None when the bytes are not a database
         h = host_lib().rxh_tree_from_bin(data, len(data))
         return cls(h) if h else None
@@ -678,6 +688,10 @@ class Queries:
     def from_fasta(cls, text: str) -> "Queries":
         b = text.encode()
         return cls(host_lib().rxh_queries_from_fasta(b, len(b)))
+
+    @classmethod
+    def from_file(cls, path: str) -> "Queries":  # parser::parse_query_fasta_file (plain or gz, streamed)
+        return cls(host_lib().rxh_queries_from_file(path.encode()))
 
     @classmethod
     def new(cls, labels, seq_off, codes) -> "Queries":

@@ -13,7 +13,6 @@
 // Exit codes follow main.rs: 73 CANTCREAT, 66 NOINPUT, 74 IOERR, 75 TEMPFAIL, 0 OK.
 
 #include <sys/stat.h>
-#include <zlib.h>
 
 #include <algorithm>
 #include <chrono>
@@ -65,16 +64,6 @@ void usage() {
             "      --batch <N>                      Queries per device batch [default: all]\n"
             "  -v, --verbose...                     Increase logging verbosity (repeatable: -vv)\n"
             "  -q, --quiet...                       Decrease logging verbosity (repeatable: -qq)\n");
-}
-
-bool read_file(const std::string& path, std::string* out) {  // utils::get_reader (utils.rs:42-60): gz by extension; gzopen also reads plain files
-    gzFile f = gzopen(path.c_str(), "rb");
-    if (!f) return false;
-    char buf[1 << 16];
-    int n;
-    while ((n = gzread(f, buf, sizeof buf)) > 0) out->append(buf, (size_t)n);
-    gzclose(f);
-    return n == 0;
 }
 
 struct Writers {
@@ -160,14 +149,6 @@ bool read_raw(const std::string& path, std::string* out) {
     fclose(f);
     return ok;
 }
-bool gz_by_extension(const std::string& path) {  // utils::get_reader (utils.rs:42-60)
-    const size_t dot = path.rfind('.');
-    if (dot == std::string::npos || path.find('/', dot) != std::string::npos) return false;
-    std::string ext = path.substr(dot + 1);
-    for (auto& c : ext) c = (char)tolower((unsigned char)c);
-    return ext == "gz" || ext == "gzip";
-}
-
 // io::FileFingerprint (io.rs:23-45)
 struct Fingerprint {
     std::string path;
@@ -451,25 +432,14 @@ int main(int argc, char** argv) {
     rxh_tree* tree = nullptr;
     bool store_db = false;
     {
-        std::string raw;
-        if (!read_raw(ckp.db.path, &raw)) {
-            fprintf(stderr, "\x1b[31m[ERROR]\x1b[0m Failed to parse %s: cannot read file\n", ckp.db.path.c_str());
+        if (a.verbosity >= 3) fprintf(stderr, "[INFO ] Trying to read from database file...\n");
+        int was_database = 0;
+        tree = rxh_tree_from_file(ckp.db.path.c_str(), &was_database);  // parser::parse_reference_fasta_file (parser.rs:37-44)
+        if (!tree) {
+            fprintf(stderr, "\x1b[31m[ERROR]\x1b[0m Failed to parse %s: %s\n", ckp.db.path.c_str(), rxh_last_error());
             return EX_NOINPUT_;
         }
-        if (a.verbosity >= 3) fprintf(stderr, "[INFO ] Trying to read from database file...\n");
-        tree = rxh_tree_from_bin(raw.data(), raw.size());
-        if (!tree) {
-            store_db = true;
-            std::string text;
-            if (gz_by_extension(ckp.db.path)) {
-                if (!read_file(ckp.db.path, &text)) text.clear();
-            } else text.swap(raw);
-            tree = rxh_tree_from_fasta(text.data(), text.size());
-            if (!tree) {
-                fprintf(stderr, "\x1b[31m[ERROR]\x1b[0m Failed to parse %s: %s\n", ckp.db.path.c_str(), rxh_last_error());
-                return EX_NOINPUT_;
-            }
-        }
+        store_db = !was_database;
     }
     std::string created_db;
     if (store_db && !a.skip_db) {  // main.rs:73-98, Args::get_db_output (io.rs:269-286)
@@ -499,17 +469,11 @@ int main(int argc, char** argv) {
     if (a.only_db) return EX_OK_;
 
     // ---- parser::parse_query_fasta_file with the processed queries skipped (main.rs:104-117) ------------------------------
-    std::string q_text;
-    if (!read_file(a.query_file, &q_text)) {
-        fprintf(stderr, "\x1b[31m[ERROR]\x1b[0m Failed to parse %s: cannot read file\n", a.query_file.c_str());
-        return EX_NOINPUT_;
-    }
-    rxh_queries* queries = rxh_queries_from_fasta(q_text.data(), q_text.size());
+    rxh_queries* queries = rxh_queries_from_file(a.query_file.c_str());
     if (!queries) {
         fprintf(stderr, "\x1b[31m[ERROR]\x1b[0m Failed to parse %s: %s\n", a.query_file.c_str(), rxh_last_error());
         return EX_NOINPUT_;
     }
-    std::string().swap(q_text);
     if (!ckp.processed.empty()) {
         std::string blob;
         for (const auto& l : ckp.processed) blob += l + "\n";

@@ -17,6 +17,7 @@
 #include <cstdio>
 #include <cstring>
 #include <deque>
+#include <exception>
 #include <memory>
 #include <mutex>
 #include <numeric>
@@ -25,6 +26,9 @@
 #include <thread>
 #include <unordered_map>
 #include <vector>
+
+#include <sys/stat.h>
+#include <zlib.h>
 
 #include "raxtax_host.h"
 
@@ -38,6 +42,38 @@ typedef uint64_t u64;
 struct Error : std::runtime_error {
     using std::runtime_error::runtime_error;
 };
+
+// ---- threads ----------------------------------------------------------------------------------------------------------------
+static size_t host_threads() {
+    if (const char* e = getenv("RXH_THREADS")) return (size_t)std::max(1, atoi(e));
+    return std::min<size_t>(16, std::max<size_t>(1, std::thread::hardware_concurrency()));
+}
+// fn(task) for task = 0 .. n-1 on up to host_threads() threads (tasks handed out through a counter); the first exception is re-thrown
+template <typename F>
+static void parallel_for(size_t n, F&& fn) {
+    const size_t T = std::min(host_threads(), n);
+    if (T <= 1) {
+        for (size_t i = 0; i < n; ++i) fn(i);
+        return;
+    }
+    std::atomic<size_t> next{0};
+    std::exception_ptr err;
+    std::mutex err_mtx;
+    std::vector<std::thread> th;
+    for (size_t t = 0; t < T; ++t)
+        th.emplace_back([&] {
+            for (size_t i; (i = next.fetch_add(1)) < n;) {
+                try {
+                    fn(i);
+                } catch (...) {
+                    std::lock_guard<std::mutex> g(err_mtx);
+                    if (!err) err = std::current_exception();
+                }
+            }
+        });
+    for (auto& t : th) t.join();
+    if (err) std::rethrow_exception(err);
+}
 
 // ---- parser.rs:11-34 ------------------------------------------------------------------------------------------
 struct DnaTable {
@@ -192,6 +228,7 @@ struct Tree {
         out->clear();
         for (u32 id = exact_head(seq, len, h); id != kNone; id = ex_next[id]) out->push_back(id);
     }
+    void hash_all(std::vector<u64>& hashes) const;  // hash of every reference sequence, in parallel
     // sequences.entry(sequence).or_default().push(idx) for idx = 0 .. n-1 (tree.rs:109-112)
     void build_exact() {
         const size_t n = seq_off.empty() ? 0 : seq_off.size() - 1;
@@ -202,10 +239,12 @@ struct Tree {
         ex_next.assign(n, kNone);
         ex_mask = cap - 1;
         std::vector<u32> tail(n, 0);  // tail[head] = last member of head's group so far
+        std::vector<u64> hashes(n);
+        hash_all(hashes);
         for (size_t idx = 0; idx < n; ++idx) {
             const u8* sp = seq_codes.data() + seq_off[idx];
             const size_t sl = (size_t)(seq_off[idx + 1] - seq_off[idx]);
-            const u64 h = hash_bytes(sp, sl);
+            const u64 h = hashes[idx];
             const u32 tag = (u32)(h >> 32);
             for (size_t at = (size_t)h & ex_mask;; at = (at + 1) & ex_mask) {
                 const u32 e = ex_head[at];
@@ -224,6 +263,15 @@ struct Tree {
         }
     }
 };
+
+void Tree::hash_all(std::vector<u64>& hashes) const {
+    const size_t n = hashes.size(), blocks = (n + 16383) / 16384;
+    parallel_for(blocks, [&](size_t b) {
+        const size_t hi = std::min(n, (b + 1) * 16384);
+        for (size_t idx = b * 16384; idx < hi; ++idx)
+            hashes[idx] = hash_bytes(seq_codes.data() + seq_off[idx], (size_t)(seq_off[idx + 1] - seq_off[idx]));
+    });
+}
 
 template <typename F>
 static inline void for_each_kmer(const u8* s, size_t n, F&& f);
@@ -329,7 +377,19 @@ static std::unique_ptr<Tree> tree_new(std::vector<std::string> lineages, const u
     };
     std::vector<u32> order(n);
     std::iota(order.begin(), order.end(), 0u);
-    std::stable_sort(order.begin(), order.end(), [&](u32 a, u32 b) { return lineages[a].compare(lineages[b]) < 0; });  // tree.rs:54
+    {   // tree.rs:54: stable sort by lineage -- runs sorted in parallel, then merged pairwise (std::inplace_merge is stable)
+        auto less = [&](u32 a, u32 b) { return lineages[a].compare(lineages[b]) < 0; };
+        size_t runs = 1;
+        while (runs < host_threads() && n / (runs * 2) >= 65536) runs *= 2;
+        std::vector<size_t> cut(runs + 1);
+        for (size_t r = 0; r <= runs; ++r) cut[r] = n * r / runs;
+        parallel_for(runs, [&](size_t r) { std::stable_sort(order.begin() + (ptrdiff_t)cut[r], order.begin() + (ptrdiff_t)cut[r + 1], less); });
+        for (size_t w = 1; w < runs; w *= 2)
+            parallel_for(runs / (2 * w), [&](size_t k) {
+                const size_t lo = cut[2 * w * k], mid = cut[2 * w * k + w], hi = cut[2 * w * k + 2 * w];
+                std::inplace_merge(order.begin() + (ptrdiff_t)lo, order.begin() + (ptrdiff_t)mid, order.begin() + (ptrdiff_t)hi, less);
+            });
+    }
 
     lap("stable sort by lineage");
     std::vector<BNode> nodes;
@@ -338,13 +398,26 @@ static std::unique_ptr<Tree> tree_new(std::vector<std::string> lineages, const u
     size_t confidence_idx = 0;
     tree->seq_off.assign(n + 1, 0);
     tree->ref_levels.resize(n);
-    {
-        u64 total = 0;
-        for (size_t i = 0; i < n; ++i) total += seq_off[order[i] + 1] - seq_off[order[i]];
-        tree->seq_codes.resize(total);
+    for (size_t i = 0; i < n; ++i) tree->seq_off[i + 1] = tree->seq_off[i] + (seq_off[order[i] + 1] - seq_off[order[i]]);
+    tree->seq_codes.resize(tree->seq_off[n]);
+    {   // the sequences in sorted order (tree.rs:109-112 keeps them as the keys of `sequences`)
+        const size_t blocks = (n + 16383) / 16384;
+        parallel_for(blocks, [&](size_t b) {
+            const size_t hi = std::min(n, (b + 1) * 16384);
+            for (size_t idx = b * 16384; idx < hi; ++idx) {
+                const u64 o = seq_off[order[idx]], l = seq_off[order[idx] + 1] - o;
+                if (l) memcpy(tree->seq_codes.data() + tree->seq_off[idx], codes + o, l);
+            }
+        });
     }
-    std::vector<std::string> levels;
-    u64 wpos = 0;
+    lap("sequences copied");
+    struct LevelView {
+        const char* p;
+        size_t n;
+        bool equals(const std::string& s) const { return s.size() == n && (n == 0 || memcmp(s.data(), p, n) == 0); }
+        std::string str() const { return std::string(p, n); }
+    };
+    std::vector<LevelView> levels;
     for (size_t idx = 0; idx < n; ++idx) {  // tree.rs:56-126
         const std::string& lineage = lineages[order[idx]];
         levels.clear();
@@ -353,10 +426,10 @@ static std::unique_ptr<Tree> tree_new(std::vector<std::string> lineages, const u
             while (true) {
                 size_t p = lineage.find(',', start);
                 if (p == std::string::npos) {
-                    levels.emplace_back(lineage, start);
+                    levels.push_back(LevelView{lineage.data() + start, lineage.size() - start});
                     break;
                 }
-                levels.emplace_back(lineage, start, p - start);
+                levels.push_back(LevelView{lineage.data() + start, p - start});
                 start = p + 1;
             }
         }
@@ -365,13 +438,13 @@ static std::unique_ptr<Tree> tree_new(std::vector<std::string> lineages, const u
         const size_t last_level = levels.size() - 1;
         u32 cur = 0;
         for (size_t level = 0; level < levels.size(); ++level) {
-            const std::string& label = levels[level];
+            const LevelView& label = levels[level];
             const u8 nt = level == last_level ? 1 : 0;
             BNode& c = nodes[cur];
             bool need_new = true;
             u32 next = 0;
             if (c.trailing_seq) {  // last child is the Sequence leaf carrying this node's own label (tree.rs:102-106)
-                if (c.label == label) {
+                if (label.equals(c.label)) {
                     // degenerate lineage (a rank repeats its parent's label): the reference walks INTO the Sequence node
                     BNode s{c.label, c.hi - 1, c.hi, 2, {}, false};
                     next = (u32)nodes.size();
@@ -382,11 +455,11 @@ static std::unique_ptr<Tree> tree_new(std::vector<std::string> lineages, const u
                 }
             } else if (!c.children.empty()) {
                 next = c.children.back();
-                if (nodes[next].label == label) need_new = false;
+                if (label.equals(nodes[next].label)) need_new = false;
             }
             if (need_new) {
                 next = (u32)nodes.size();
-                nodes.push_back(BNode{label, (u32)confidence_idx, (u32)confidence_idx + 1, nt, {}, false});
+                nodes.push_back(BNode{label.str(), (u32)confidence_idx, (u32)confidence_idx + 1, nt, {}, false});
                 nodes[cur].children.push_back(next);
                 nodes[cur].trailing_seq = false;
             }
@@ -396,13 +469,7 @@ static std::unique_ptr<Tree> tree_new(std::vector<std::string> lineages, const u
         }
         nodes[cur].trailing_seq = true;  // add_child(Sequence(label, ci-1)) (tree.rs:102-106)
         nodes[cur].hi = (u32)confidence_idx;  // tree.rs:107
-
-        const u64 o = seq_off[order[idx]], l = seq_off[order[idx] + 1] - o;
-        memcpy(tree->seq_codes.data() + wpos, codes + o, l);
-        tree->seq_off[idx] = wpos;
-        wpos += l;
     }
-    tree->seq_off[n] = wpos;
     lap("nodes");
     tree->build_exact();  // tree.rs:109-112
     lap("sequence map");
@@ -669,40 +736,225 @@ static std::unique_ptr<Tree> load_bin(const u8* data, size_t len) {
     }
 }
 
+// ---- FASTA parsing (parser.rs:46-154), by blocks and in parallel --------------------------------------------------------------
+// The reference reads the whole file into a String and walks its lines on one thread.  Here the text arrives in blocks (a whole
+// buffer, or what a gz / plain reader has produced so far), every block is cut at header lines into pieces that are parsed in
+// parallel, and the per-record rules of the reference are applied to the pieces' records in file order afterwards:
+//   references (parser.rs:46-105): every header contributes a label; a sequence is pushed at the NEXT header only if it is not empty,
+//   the last one unconditionally; more labels than sequences is the "does not match" error
+//   queries (parser.rs:117-154): a record whose sequence is empty is dropped, label included, unless it is the last one
+struct FastaPiece {
+    std::vector<std::string> labels;  // lineage (references) or the whole header line after '>' (queries), one per header
+    std::vector<u64> lens;            // codes that follow that header inside the piece
+    std::vector<u8> codes;
+    std::string error;                // what the serial parser would have raised first inside this piece
+    bool headless_codes = false;      // sequence lines before the piece's first header (only the very first piece can have them)
+};
+
+static void parse_piece(const char* b0, const char* e0, bool reference, FastaPiece& out) {
+    LineReader lr(b0, (size_t)(e0 - b0));
+    const char *b, *e;
+    out.codes.reserve((size_t)(e0 - b0));
+    try {
+        while (lr.next(&b, &e)) {
+            if (*b == '>') {
+                if (reference) {
+                    std::string lineage;
+                    if (!capture_tax(b + 1, e, &lineage)) throw Error("Unexpected taxonomical annotation detected in label " + std::string(b + 1, e));
+                    out.labels.push_back(std::move(lineage));
+                } else {
+                    out.labels.emplace_back(b + 1, e);
+                }
+                out.lens.push_back(0);
+            } else {
+                if (out.lens.empty()) {
+                    out.headless_codes = true;
+                    return;  // "Not a valid FASTA file": decided by the caller (only possible in the first piece)
+                }
+                const size_t before = out.codes.size();
+                append_codes(out.codes, b, e);
+                out.lens.back() += out.codes.size() - before;
+            }
+        }
+    } catch (const std::exception& ex) {
+        out.error = ex.what();
+    }
+}
+
+struct FastaAccumulator {
+    const bool reference;
+    bool any_line = false;
+    std::vector<std::string> labels;  // one per header so far
+    std::vector<u64> lens;
+    std::vector<u8> codes;
+    std::vector<FastaPiece> pieces;  // kept between blocks: their buffers are reused instead of being mapped and faulted in again
+    explicit FastaAccumulator(bool ref) : reference(ref) {}
+
+    // [b, e) starts at a header line (or at the start of the file) and ends at a record boundary (or at the end of the file)
+    void add_block(const char* b, const char* e) {
+        if (b >= e) return;
+        // cut at "\n>" into pieces of ~4 MB
+        std::vector<const char*> cut{b};
+        size_t target = 4u << 20;
+        if (const char* ev = getenv("RXH_FASTA_PIECE")) target = (size_t)std::max(1, atoi(ev));  // test hook
+        const char* p = b;
+        while ((size_t)(e - p) > target) {
+            const char* q = p + target;
+            const char* hit = nullptr;
+            while (q < e) {
+                const char* nl = (const char*)memchr(q, '\n', (size_t)(e - q));
+                if (!nl || nl + 1 >= e) break;
+                if (nl[1] == '>') {
+                    hit = nl + 1;
+                    break;
+                }
+                q = nl + 1;
+            }
+            if (!hit) break;
+            cut.push_back(hit);
+            p = hit;
+        }
+        cut.push_back(e);
+        const size_t n_pieces = cut.size() - 1;
+        if (pieces.size() < n_pieces) pieces.resize(n_pieces);
+        parallel_for(n_pieces, [&](size_t i) {
+            FastaPiece& pc = pieces[i];
+            pc.labels.clear();
+            pc.lens.clear();
+            pc.codes.clear();
+            pc.error.clear();
+            pc.headless_codes = false;
+            parse_piece(cut[i], cut[i + 1], reference, pc);
+        });
+        std::vector<size_t> at(n_pieces + 1, codes.size());
+        for (size_t i = 0; i < n_pieces; ++i) {
+            FastaPiece& pc = pieces[i];
+            if (pc.headless_codes) {
+                if (labels.empty() && i == 0) throw Error("Not a valid FASTA file");
+                throw Error("internal: FASTA block does not start at a header");
+            }
+            if (!pc.error.empty()) throw Error(pc.error);
+            if (!pc.labels.empty() || !pc.codes.empty()) any_line = true;
+            for (auto& l : pc.labels) labels.push_back(std::move(l));
+            lens.insert(lens.end(), pc.lens.begin(), pc.lens.end());
+            at[i + 1] = at[i] + pc.codes.size();
+        }
+        if (codes.capacity() < at.back()) codes.reserve(std::max(at.back(), codes.capacity() * 2));
+        codes.resize(at.back());
+        parallel_for(n_pieces, [&](size_t i) {
+            if (!pieces[i].codes.empty()) memcpy(codes.data() + at[i], pieces[i].codes.data(), pieces[i].codes.size());
+        });
+    }
+};
+
+// whole text in memory
+static void accumulate_text(FastaAccumulator& acc, const char* text, size_t len) {
+    if (len == 0) throw Error("File is empty");
+    acc.add_block(text, text + len);
+    if (acc.labels.empty()) throw Error("Not a valid FASTA file");  // no header line at all (the reference panics indexing lines[0])
+}
+
+// gz (by content: gzopen reads plain files as they are) or plain file, block by block: the reader thread decompresses the next block
+// while the previous one is parsed
+static void accumulate_file(FastaAccumulator& acc, const std::string& path) {
+    gzFile f = gzopen(path.c_str(), "rb");
+    if (!f) throw Error("cannot read file");
+    gzbuffer(f, 1u << 20);
+    {   // room for the codes up front: the file's size when it is plain text, a guess of 4x when it is compressed
+        struct stat st;
+        if (stat(path.c_str(), &st) == 0 && st.st_size > 0) acc.codes.reserve((size_t)st.st_size * (gzdirect(f) ? 1 : 4));
+    }
+    size_t block = 48u << 20;
+    if (const char* e = getenv("RXH_FASTA_BLOCK")) block = (size_t)std::max(16, atoi(e));  // test hook: tiny blocks exercise the carry logic
+    std::string carry, next;
+    bool eof = false, read_err = false;
+    auto read_block = [&](std::string& dst) {  // appends up to `block` bytes
+        const size_t at = dst.size();
+        dst.resize(at + block);
+        size_t got = 0;
+        while (got < block) {
+            const int n = gzread(f, &dst[at + got], (unsigned)std::min<size_t>(block - got, 1u << 30));
+            if (n < 0) {
+                read_err = true;
+                break;
+            }
+            if (n == 0) {
+                eof = true;
+                break;
+            }
+            got += (size_t)n;
+        }
+        dst.resize(at + got);
+    };
+    const bool timing = getenv("RXH_TIMING") != nullptr;
+    auto tp0 = std::chrono::steady_clock::now();
+    double t_parse = 0.0, t_wait = 0.0, t_shift = 0.0;
+    read_block(carry);
+    bool any = !carry.empty();
+    while (true) {
+        std::thread reader;
+        next.clear();
+        if (!eof && !read_err) reader = std::thread([&] { read_block(next); });
+        // parse carry up to its last record boundary; at the end of the file all of it
+        size_t split = carry.size();
+        const bool last = eof && !reader.joinable();
+        if (!last) {
+            split = 0;
+            for (size_t p = carry.size(); p-- > 1;)
+                if (carry[p] == '>' && carry[p - 1] == '\n') {
+                    split = p;
+                    break;
+                }
+        }
+        std::exception_ptr perr;
+        auto tp1 = std::chrono::steady_clock::now();
+        try {
+            if (split > 0) acc.add_block(carry.data(), carry.data() + split);
+        } catch (...) {
+            perr = std::current_exception();
+        }
+        auto tp2 = std::chrono::steady_clock::now();
+        t_parse += std::chrono::duration<double>(tp2 - tp1).count();
+        if (reader.joinable()) reader.join();
+        auto tp3 = std::chrono::steady_clock::now();
+        t_wait += std::chrono::duration<double>(tp3 - tp2).count();
+        if (perr) {
+            gzclose(f);
+            std::rethrow_exception(perr);
+        }
+        if (last) break;
+        carry.erase(0, split);
+        any = any || !next.empty();
+        carry += next;
+        t_shift += std::chrono::duration<double>(std::chrono::steady_clock::now() - tp3).count();
+    }
+    gzclose(f);
+    if (timing)
+        fprintf(stderr, "[rxh fasta] %zu headers, %.1f MB of codes: total %.3f s (parsing blocks %.3f, waiting for the reader %.3f, moving the carry %.3f)\n",
+                acc.labels.size(), acc.codes.size() / 1e6, std::chrono::duration<double>(std::chrono::steady_clock::now() - tp0).count(), t_parse, t_wait, t_shift);
+    if (read_err) throw Error("cannot read file");
+    if (!any) throw Error("File is empty");
+    if (acc.labels.empty()) throw Error("Not a valid FASTA file");
+}
+
+static std::unique_ptr<Tree> tree_from_accumulator(FastaAccumulator& acc) {
+    const size_t H = acc.labels.size();
+    std::vector<u64> off{0};
+    off.reserve(H + 1);
+    u64 pos = 0;
+    for (size_t i = 0; i < H; ++i) {
+        pos += acc.lens[i];
+        if (acc.lens[i] > 0 || i + 1 == H) off.push_back(pos);  // !current_sequence.is_empty() at the next header; the last one always
+    }
+    if (H != off.size() - 1) throw Error("Number of sequences does not match number of labels");
+    return tree_new(std::move(acc.labels), off.data(), acc.codes.data());
+}
+
 // parser.rs:46-105
 static std::unique_ptr<Tree> parse_reference_fasta_str(const char* text, size_t len) {
-    if (len == 0) throw Error("File is empty");
-    LineReader lr(text, len);
-    const char *b, *e;
-    std::vector<std::string> labels;
-    std::vector<u64> off{0};
-    std::vector<u8> codes;
-    bool first = true, have_current = false;
-    u64 cur_start = 0;
-    while (lr.next(&b, &e)) {
-        if (first) {
-            if (*b != '>') throw Error("Not a valid FASTA file");
-            first = false;
-        }
-        if (*b == '>') {
-            std::string lineage;
-            if (!capture_tax(b + 1, e, &lineage))
-                throw Error("Unexpected taxonomical annotation detected in label " + std::string(b + 1, e));
-            labels.push_back(std::move(lineage));
-            if (codes.size() > cur_start) {  // !current_sequence.is_empty()
-                off.push_back(codes.size());
-                cur_start = codes.size();
-            }
-            have_current = true;
-        } else {
-            append_codes(codes, b, e);
-        }
-    }
-    if (first) throw Error("Not a valid FASTA file");  // the reference indexes lines[0] and panics on an all-blank file
-    (void)have_current;
-    off.push_back(codes.size());  // sequences.push(current_sequence)
-    if (labels.size() != off.size() - 1) throw Error("Number of sequences does not match number of labels");
-    return tree_new(std::move(labels), off.data(), codes.data());
+    FastaAccumulator acc(true);
+    accumulate_text(acc, text, len);
+    return tree_from_accumulator(acc);
 }
 
 struct Queries {
@@ -712,36 +964,27 @@ struct Queries {
     size_t size() const { return labels.size(); }
 };
 
-// parser.rs:117-154 (queries_to_skip is applied by the caller that owns the checkpoint)
-static std::unique_ptr<Queries> parse_query_fasta_str(const char* text, size_t len) {
-    if (len == 0) throw Error("File is empty");
-    LineReader lr(text, len);
-    const char *b, *e;
+static std::unique_ptr<Queries> queries_from_accumulator(FastaAccumulator& acc) {
     auto q = std::make_unique<Queries>();
+    const size_t H = acc.labels.size();
     q->off.push_back(0);
-    bool first = true;
-    std::string cur_label;
-    u64 cur_start = 0;
-    while (lr.next(&b, &e)) {
-        if (first) {
-            if (*b != '>') throw Error("Not a valid FASTA file");
-            first = false;
-        }
-        if (*b == '>') {
-            if (q->codes.size() > cur_start) {  // push the finished record; empty records are silently merged (parser.rs:138-141)
-                q->labels.push_back(cur_label);
-                q->off.push_back(q->codes.size());
-                cur_start = q->codes.size();
-            }
-            cur_label.assign(b + 1, e);
-        } else {
-            append_codes(q->codes, b, e);
+    u64 pos = 0;
+    for (size_t i = 0; i < H; ++i) {
+        pos += acc.lens[i];
+        if (acc.lens[i] > 0 || i + 1 == H) {  // empty records are silently merged into the next one (parser.rs:138-141); the last is pushed as is
+            q->labels.push_back(std::move(acc.labels[i]));
+            q->off.push_back(pos);
         }
     }
-    if (first) throw Error("Not a valid FASTA file");
-    q->labels.push_back(cur_label);  // queries.push(current_query)
-    q->off.push_back(q->codes.size());
+    q->codes = std::move(acc.codes);
     return q;
+}
+
+// parser.rs:117-154 (queries_to_skip is applied by the caller that owns the checkpoint)
+static std::unique_ptr<Queries> parse_query_fasta_str(const char* text, size_t len) {
+    FastaAccumulator acc(false);
+    accumulate_text(acc, text, len);
+    return queries_from_accumulator(acc);
 }
 
 // the closing filter of parser.rs:150-153: drop the queries whose label a checkpoint lists as processed
@@ -869,6 +1112,57 @@ RXH_API rxh_tree* rxh_tree_from_fasta(const char* text, size_t len) {
     try {
         auto h = new rxh_tree();
         h->t = parse_reference_fasta_str(text, len);
+        return h;
+    } catch (const std::exception& e) {
+        g_err = e.what();
+        return nullptr;
+    }
+}
+
+// parser::parse_reference_fasta_file (parser.rs:37-44): a binary database if the whole file deserialises as one, else FASTA (plain or
+// gz).  A bincode image of Tree starts with the root node's label, the string "root" behind its u64 length: only such a file is read
+// in one piece and tried as a database; everything else streams through the block parser without ever being held as one string.
+RXH_API rxh_tree* rxh_tree_from_file(const char* path, int* was_database) {
+    if (was_database) *was_database = 0;
+    try {
+        FILE* f = fopen(path, "rb");
+        if (!f) throw Error("cannot read file");
+        unsigned char head[12];
+        const size_t got = fread(head, 1, sizeof head, f);
+        static const unsigned char kBinHead[12] = {4, 0, 0, 0, 0, 0, 0, 0, 'r', 'o', 'o', 't'};
+        if (got == sizeof head && memcmp(head, kBinHead, sizeof head) == 0) {
+            std::string raw((const char*)head, got);
+            char buf[1 << 16];
+            size_t n;
+            while ((n = fread(buf, 1, sizeof buf, f)) > 0) raw.append(buf, n);
+            fclose(f);
+            auto t = load_bin((const u8*)raw.data(), raw.size());
+            if (t) {
+                if (was_database) *was_database = 1;
+                auto h = new rxh_tree();
+                h->t = std::move(t);
+                return h;
+            }
+        } else {
+            fclose(f);
+        }
+        FastaAccumulator acc(true);
+        accumulate_file(acc, path);
+        auto h = new rxh_tree();
+        h->t = tree_from_accumulator(acc);
+        return h;
+    } catch (const std::exception& e) {
+        g_err = e.what();
+        return nullptr;
+    }
+}
+
+RXH_API rxh_queries* rxh_queries_from_file(const char* path) {  // parser::parse_query_fasta_file (parser.rs:108-115) minus the skip filter
+    try {
+        FastaAccumulator acc(false);
+        accumulate_file(acc, path);
+        auto h = new rxh_queries();
+        h->q = queries_from_accumulator(acc);
         return h;
     } catch (const std::exception& e) {
         g_err = e.what();

@@ -270,3 +270,64 @@ def test_fixed_point_formatting_matches_libc():
     for v in vals:
         for prec in (2, 5):
             assert capi.format_fixed(v, prec) == "%.*f" % (prec, v), (v, prec)
+
+
+def _tree_arrays(t):
+    d = capi.IndexDesc()
+    capi.host_lib().rxh_tree_index_desc(t._h, C.byref(d))
+    nn, n = d.n_nodes, d.n_refs
+    g = lambda p, k: np.ctypeslib.as_array(p, (k,)).copy()
+    off = g(d.ref_seq_offsets, n + 1)
+    return (g(d.node_lo, nn), g(d.node_hi, nn), g(d.node_type, nn), g(d.child_first, nn), g(d.child_count, nn), g(d.ref_levels, n), off,
+            g(d.ref_seq_codes, int(off[-1])) if off[-1] else np.zeros(0, np.uint8))
+
+
+@pytest.mark.parametrize("block,piece", [(None, None), ("64", "1"), ("1000", "200"), ("100000", "3000")])
+def test_streamed_fasta_files_equal_in_memory_parse(tmp_path, monkeypatch, block, piece):
+    """rxh_tree_from_file / rxh_queries_from_file (plain and gz, read in blocks, blocks cut into pieces parsed in parallel) give what
+    the one-string parsers give; tiny blocks and pieces force every record across a block / piece boundary."""
+    import gzip
+
+    ds = synth.generate("tiny", measure=False)
+    ref_txt = ds.ref_fasta().replace("\n>", "\n\n; a comment line\n   \n>", 3)  # blank / comment lines are dropped (parser.rs:53-57)
+    q_txt = ds.query_fasta()
+    want_t = capi.Tree.from_fasta(ref_txt)
+    want_q = capi.Queries.from_fasta(q_txt)
+    if block:
+        monkeypatch.setenv("RXH_FASTA_BLOCK", block)
+        monkeypatch.setenv("RXH_FASTA_PIECE", piece)
+    for gz in (False, True):
+        rp, qp = tmp_path / ("r.fasta" + (".gz" if gz else "")), tmp_path / ("q.fasta" + (".gz" if gz else ""))
+        (gzip.open if gz else open)(rp, "wt").write(ref_txt)
+        (gzip.open if gz else open)(qp, "wt").write(q_txt)
+        t, was_db = capi.Tree.from_file(str(rp))
+        assert not was_db and t.lineages == want_t.lineages
+        for a, b in zip(_tree_arrays(t), _tree_arrays(want_t)):
+            assert np.array_equal(a, b)
+        q = capi.Queries.from_file(str(qp))
+        assert q.labels == want_q.labels
+        for a, b in zip(q.arrays(), want_q.arrays()):
+            assert np.array_equal(a, b)
+    # a binary database is recognised by content and loaded as such
+    binp = tmp_path / "db.bin"
+    want_t.save_bin(str(binp))
+    t, was_db = capi.Tree.from_file(str(binp))
+    assert was_db and t.lineages == want_t.lineages
+
+
+def test_streamed_fasta_errors_match_the_parsers(tmp_path):
+    cases = [("", "File is empty"), ("ACGT\n>x;tax=a,b;\nACGT", "Not a valid FASTA"), (">x;tax=a,b;\nACGU", "Unexpected character"),
+             (">x;taxon=a,b\nACGT", "taxonomical annotation"), (">x;tax=a,b;\n>y;tax=a,c;\nACGT", "does not match"), ("\n  \n;c\n", "Not a valid FASTA")]
+    for i, (text, msg) in enumerate(cases):
+        p = tmp_path / f"e{i}.fasta"
+        p.write_text(text)
+        with pytest.raises(capi.HostError, match=msg):
+            capi.Tree.from_file(str(p))
+    with pytest.raises(capi.HostError, match="cannot read file"):
+        capi.Tree.from_file(str(tmp_path / "missing.fasta"))
+    # queries: empty records are merged into the next one, the last record is kept even when empty (parser.rs:138-147)
+    p = tmp_path / "q.fasta"
+    p.write_text(">a\n>b\nACGT\n>c\n")
+    q = capi.Queries.from_file(str(p))
+    assert q.labels == ["b", "c"] and list(q.arrays()[0]) == [0, 4, 4]
+    assert capi.Queries.from_fasta(">a\n>b\nACGT\n>c\n").labels == ["b", "c"]
