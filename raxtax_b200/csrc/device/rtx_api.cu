@@ -1122,7 +1122,10 @@ static cudaError_t launch_hitcount_tuned(rtx_ctx* c, int q_base, int qb, u32 kma
     int G = c->hit_group;  // 0 = default
     const bool force_group = G == 101;
     if (force_group) G = 1;
-    if (G == 0) G = 4;
+    // queries per CTA: 4 on indexes of a few GB, 16 on large ones -- measured (profiles/r2_hitcount_group_by_index_size.txt): on 1 M x 650 bp
+    // references (8.2 GB of bit rows) 16 queries per CTA are 5.8 % faster than 4 (more rows shared through the L1, less L2 traffic), on
+    // 100 k references (0.8 GB) and on 500 k x 1500 bp (4.1 GB) they are 1-5 % slower
+    if (G == 0) G = ((u64)c->n_rows * c->ix.row_words * 4 >= (6ull << 30)) ? 16 : 4;
     while (G > 1 && (size_t)G * (c->bv.kstride + c->bv.hstride) * 4 > 150 * 1024) G /= 2;  // long queries: smaller groups
     if ((G > 1 || force_group) && qb >= G) {
         if (kmax < (1u << 8)) return launch_hitcount_group<8>(c, q_base, qb, G);
