@@ -132,7 +132,54 @@ def _assign_parents(n_child, n_parent, rng, skew=1.2):
     return par
 
 
+def generate_clades(name, n_clades, n_refs=None, n_queries=None, seed=None) -> Dataset:
+    """A large reference set as `n_clades` diverged copies of one base set of n_refs / n_clades references: clade c carries the base
+    lineages under its own phylum labels and the base sequences with 4 % of the bases substituted (so that no sequence is shared
+    between clades and the 8-mer sharing across clades is that of distant relatives).  8 M references by the full hierarchical model
+    take ~5 minutes and 20 GB of temporaries; this takes the base set's time plus a few seconds per clade.  Queries: the base set's
+    query mix, each query assigned to a random clade and mutated like that clade's references where it copies one."""
+    cfg = CONFIGS[name]
+    n_refs = n_refs or cfg[0]
+    n_queries = cfg[1] if n_queries is None else n_queries
+    seed = SEED_BASE + CONFIG_SEED[name] if seed is None else seed
+    base = generate(name, n_refs=n_refs // n_clades, n_queries=n_queries, length=cfg[2], kind=cfg[3], seed=seed, measure=False)
+    rng = np.random.default_rng(seed + 7919)
+    cum = np.cumsum(COMPOSITION)
+    ref_parts, lin, lens = [], [], (base.ref_off[1:] - base.ref_off[:-1]).astype(np.int64)
+    # substitution pattern per clade: a fixed set of alignment columns re-drawn (a clade-specific "ancestral" change), applied to
+    # every sequence of the clade alike, references and the queries derived from them -- exact copies stay exact copies
+    col_sub = [None] * n_clades
+    pos_in_seq = (np.arange(len(base.ref_codes), dtype=np.int64) - np.repeat(base.ref_off[:-1].astype(np.int64), lens))
+    for c in range(n_clades):
+        codes = base.ref_codes.copy()
+        if c:
+            cols = rng.random(cfg[2]) < 0.04
+            new_base = BASE_CODES[np.searchsorted(cum, rng.random(cfg[2])).clip(0, 3)]
+            col_sub[c] = (cols, new_base)
+            hit = cols[pos_in_seq] & (codes < 15) & np.isin(codes, BASE_CODES)
+            codes[hit] = new_base[pos_in_seq[hit]]
+        ref_parts.append(codes)
+        lin += [l if c == 0 else l.replace("p:P", f"p:X{c}P", 1) for l in base.ref_lineages]
+    ref_codes = np.concatenate(ref_parts)
+    ref_off = np.zeros(len(lin) + 1, np.uint64)
+    ref_off[1:] = np.cumsum(np.tile(lens, n_clades))
+    # queries
+    q_codes = base.query_codes.copy()
+    q_lens = (base.query_off[1:] - base.query_off[:-1]).astype(np.int64)
+    q_clade = rng.integers(0, n_clades, base.n_queries)
+    q_pos = (np.arange(len(q_codes), dtype=np.int64) - np.repeat(base.query_off[:-1].astype(np.int64), q_lens))
+    q_of = np.repeat(q_clade, q_lens)
+    for c in range(1, n_clades):
+        cols, new_base = col_sub[c]
+        hit = (q_of == c) & cols[np.minimum(q_pos, cfg[2] - 1)] & np.isin(q_codes, BASE_CODES)
+        q_codes[hit] = new_base[q_pos[hit]]
+    meta = dict(base.meta, n_refs=len(lin), n_clades=n_clades, note="clade copies of a base set (synth.generate_clades)")
+    return Dataset(name, lin, ref_off, ref_codes, base.query_labels, base.query_off, q_codes, meta=meta)
+
+
 def generate(name="c2", n_refs=None, n_queries=None, length=None, kind=None, seed=None, measure=True) -> Dataset:
+    if name == "c5" and n_refs is None and length is None and kind is None:
+        return generate_clades("c5", 8, n_queries=n_queries, seed=seed)
     cfg = CONFIGS.get(name)
     if cfg is not None:
         n_refs = n_refs or cfg[0]
