@@ -52,9 +52,12 @@ typedef enum {
     RTX_OPT_SUB_BATCH = 2,      /* queries per device sub-batch (0 = auto) */
     RTX_OPT_KEEP_CSR = 3,       /* keep the CSR postings resident after building bit rows (needed for variant CSR) */
     RTX_OPT_PROFILE = 4,        /* record a CUDA event pair around every kernel launch (rtx_profile_get) */
-    RTX_OPT_HITCOUNT_TUNE = 5,  /* bit-row kernel geometry: V + 10*prefetch + 100*warps_per_cta, 0 = library default */
+    RTX_OPT_HITCOUNT_TUNE = 5,  /* 0 = library default; 1..4 = row-load form of the query-group kernel (1: .v2 loads bypassing the L1,
+                                   2: .v2 through the L1 = default, 3: one-line loads through the L1, 4: one-line loads bypassing it);
+                                   >= 10 = single-query kernel geometry: V + 10*prefetch + 100*warps_per_cta */
     RTX_OPT_HITCOUNT_MAX_TILES = 6, /* warp tiles (32*V words each) per CTA; fewer = more reference tile groups (L2 blocking); 0 = default */
-    RTX_OPT_HITCOUNT_GROUP = 7,     /* queries per CTA (one per warp) of the query-group bit-row kernel: 0 = library default (4),
+    RTX_OPT_HITCOUNT_GROUP = 7,     /* queries per CTA (one per warp) of the query-group bit-row kernel: 0 = library default (4; 16 when the
+                                       bit rows exceed 6 GB),
                                        1 = single-query kernel (one warp per reference tile), 2..16 = group size, 101 = group kernel with 1 */
     RTX_OPT_HITCOUNT_CHUNKS = 8,    /* row-id chunks the warps of a group cross in lockstep (block barrier per chunk) so that shared rows
                                        hit the L1; 0 or 1 = no lockstep (default, fastest measured) */

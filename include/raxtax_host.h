@@ -116,9 +116,13 @@ int rxh_raxtax_multi(rtx_ctx* const* ctxs, size_t n_ctx, const rxh_queries* quer
                      void* logger_user, int* warnings);
 
 /* raxtax::raxtax over a reference-sharded index (BASELINE config 5: databases too large to replicate) with all shards driven by this
- * process: ctxs[r] holds shard r of n_ctx (rxh_tree_upload_sharded, any mix of devices).  Lines are sent in query order from the
- * calling thread.  chunk_size = queries per sharded batch (0 = up to 8192; halved automatically until a batch fits one sub-batch
- * of every shard). */
+ * process: ctxs[r] holds shard r of n_ctx (rxh_tree_upload_sharded).  When every shard sits on its own GPU the contexts are joined into
+ * an NCCL communicator and one driver thread per rank calls rtx_shard_run / rtx_shard_gather (histogram all-reduce, record all-gather
+ * and the gather + merge of the result lines all inside the device library); rank 0's lines feed the same writer side as rxh_raxtax.
+ * Several shards on one GPU (NCCL does not take two ranks on one device; RXH_SHARD_NO_NCCL=1 forces this path): phase by phase with the
+ * exchanges staged through pinned host memory and the merge on the host.  Lines are sent in query order from the calling thread.
+ * chunk_size = queries per sharded batch (0 = a quarter of the queries, 2048..32768, over NCCL; up to 8192 on the staged path, halved
+ * automatically until a batch fits one sub-batch of every shard). */
 int rxh_raxtax_sharded(rtx_ctx* const* ctxs, size_t n_ctx, const rxh_queries* queries, const rxh_tree* tree, int skip_exact_matches,
                        int raw_confidence, size_t chunk_size, rxh_sender sender, void* sender_user, int tsv, rxh_logger logger,
                        void* logger_user, int* warnings);
