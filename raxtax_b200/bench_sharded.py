@@ -41,14 +41,26 @@ def sharded_leg(ctx, tree, ds, n_queries, rank, world, steps, skip, dist, barrie
     out = None
     for _ in range(2):
         out = ctx.classify(off_p, codes_p, eo_p, eids_p, skip_exact=skip, shard_root=0)
-    same = None
+    n_diff = None
     if expect is not None and rank == 0:
-        n = int(expect.result_begin[n_queries])
-        lev = np.arange(expect.confidence.shape[1])[None, :] < expect.n_levels[:n, None]
-        same = bool(np.array_equal(out.result_begin, expect.result_begin[: n_queries + 1]) and np.array_equal(out.first_ref, expect.first_ref[:n])
-                    and np.array_equal(out.n_levels, expect.n_levels[:n]) and np.array_equal(out.confidence[lev], expect.confidence[:n][lev])
-                    and np.max(np.abs(out.local_signal - expect.local_signal[:n]), initial=0.0) <= 1e-9
-                    and np.max(np.abs(out.global_signal - expect.global_signal[:n_queries]), initial=0.0) <= 1e-9)
+        # per query: the same lines (first reference, levels, confidences bit for bit, signals to 1e-9) as the unsharded context gave.
+        # Queries whose probability profile is exactly flat (K = 0: every node confidence is size/N, sitting ON rounding boundaries and
+        # exact ties) may legitimately differ -- the sharded sums add the same numbers in another order (tools/shard_diff.py judges such
+        # queries against the CPU restatement: both outcomes acceptable); they are counted, not hidden.
+        eb, gb = expect.result_begin[: n_queries + 1].astype(np.int64), out.result_begin.astype(np.int64)
+        bad = (gb[1:] - gb[:-1]) != (eb[1:] - eb[:-1])
+        ok_q = np.nonzero(~bad)[0]
+        if len(ok_q):
+            cnt = (eb[1:] - eb[:-1])[ok_q]
+            qi = np.repeat(ok_q, cnt)                                   # query of every compared line
+            k = np.arange(len(qi)) - np.repeat(np.cumsum(cnt) - cnt, cnt)  # position of the line within its query
+            ei, gi = eb[qi] + k, gb[qi] + k
+            lev = np.arange(expect.confidence.shape[1])[None, :] < expect.n_levels[ei][:, None]
+            line_ok = ((out.first_ref[gi] == expect.first_ref[ei]) & (out.n_levels[gi] == expect.n_levels[ei])
+                       & np.all((out.confidence[gi] == expect.confidence[ei]) | ~lev, axis=1) & (np.abs(out.local_signal[gi] - expect.local_signal[ei]) <= 1e-9))
+            bad[np.unique(qi[~line_ok])] = True
+        bad |= np.abs(out.global_signal - expect.global_signal[:n_queries]) > 1e-9
+        n_diff = int(bad.sum())
     ctx.set_option(capi.RTX_OPT_PROFILE, 1)
     ctx.classify(off_p, codes_p, eo_p, eids_p, skip_exact=skip, shard_root=0)
     ctx.profile_reset()
@@ -79,7 +91,9 @@ def sharded_leg(ctx, tree, ds, n_queries, rank, world, steps, skip, dist, barrie
            "collective_bytes_per_step_rank0": {"allreduce": prof["allreduce_bytes"] // reps_p, "allgather": prof["allgather_bytes"] // reps_p,
                                                "gather": prof["gather_bytes"] // reps_p},
            "h2d_bytes_per_step": prof_t["h2d_bytes"] // steps, "d2h_bytes_per_step": prof_t["d2h_bytes"] // steps, "gpu_launches": int(launches),
-           "identical_to_unsharded": same}
+           "queries_differing_from_unsharded": n_diff,
+           "identical_note": "compared line by line with rank 0's unsharded results of the same queries; flat-profile (K = 0) queries sit on exact "
+                             "ties / rounding boundaries and may differ (DESIGN 2, tools/shard_diff.py)"}
     return rec
 
 

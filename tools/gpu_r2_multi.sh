@@ -8,7 +8,7 @@ import json
 d=json.load(open("gpurun_out/${tag}_bench_c3_n$n.json"))
 s=d.get("sharded") or {}
 print("c3 N=$n value", round(d["value"]), "e2e", round(d["e2e"]["value"]), "frac", round(d["e2e"]["frac_of_device_resident"],3), "ms/step", round(d["ms_per_step"],2))
-print("sharded leg:", round(s.get("value",0)), "q/s", s.get("n_ranks"), "ranks", s.get("queries"), "queries identical:", s.get("identical_to_unsharded"), s.get("phase_ms_per_step_rank0"))
+print("sharded leg:", round(s.get("value",0)), "q/s", s.get("n_ranks"), "ranks", s.get("queries"), "queries differing from unsharded:", s.get("queries_differing_from_unsharded"), s.get("phase_ms_per_step_rank0"))
 PY
 if [ -n "$c5" ]; then
 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29512 bench.py --workload c5 --gpus $n --steps 3 --warmup 2 > gpurun_out/${tag}_bench_c5_n$n.json 2> gpurun_out/${tag}_bench_c5_n$n.err
