@@ -331,3 +331,23 @@ def test_streamed_fasta_errors_match_the_parsers(tmp_path):
     q = capi.Queries.from_file(str(p))
     assert q.labels == ["b", "c"] and list(q.arrays()[0]) == [0, 4, 4]
     assert capi.Queries.from_fasta(">a\n>b\nACGT\n>c\n").labels == ["b", "c"]
+
+
+def test_bench_strong_scaling_slices_cover_the_job_once():
+    """bench.py's partition of the default workload: every query of the job belongs to exactly one rank, at every N."""
+    import bench
+
+    for name in ("c3", "c4"):
+        for world in (1, 2, 3, 4, 8):
+            q_total, per, scaling = bench.workload_queries(name, world)
+            assert scaling == "strong" and q_total == synth.CONFIGS[name][1]
+            seen = 0
+            for rank in range(world):
+                q0 = min(rank * per, q_total)
+                q1 = min(q0 + per, q_total)
+                assert q0 == seen
+                seen = q1
+            assert seen == q_total
+    q_total, per, scaling = bench.workload_queries("c2", 4)
+    assert scaling == "weak" and per == synth.CONFIGS["c2"][1] and q_total == 4 * per
+    assert bench.workload_queries("c5", 8, 131072) == (131072, 131072, "strong")  # sharded references: every rank sees every query

@@ -8,17 +8,19 @@ import tempfile
 import time
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from raxtax_b200 import _build, synth
+import bench
+from raxtax_b200 import _build
 
 name = sys.argv[1] if len(sys.argv) > 1 else "c2"
 extra = sys.argv[2:]
-ds = synth.generate(name, measure=False)
+ds = bench.load_workload(name, bench.workload_queries(name, 1)[0])
+only_first = os.environ.get("CLI_WALL_ONLY_SKIP_DB") == "1"  # large sets: skip the two runs that write / read the multi-GB .bin
 with tempfile.TemporaryDirectory() as d:
     refs, qs = os.path.join(d, "refs.fasta"), os.path.join(d, "queries.fasta")
     open(refs, "w").write(ds.ref_fasta())
     open(qs, "w").write(ds.query_fasta())
     rows = []
-    for label, flags in (("fasta database, --skip-db", ["--skip-db"]), ("fasta database, writes the .bin", []), ("the .bin as database", None)):
+    for label, flags in (("fasta database, --skip-db", ["--skip-db"]), ("fasta database, writes the .bin", []), ("the .bin as database", None))[: 1 if only_first else 3]:
         prefix = os.path.join(d, "out_" + str(len(rows)))
         db = refs if flags is not None else os.path.join(d, "out_1", "refs.bin")
         cmd = [_build.CLI_BIN, "-d", db, "-i", qs, "-o", prefix, "--tsv"] + (flags or []) + extra
