@@ -1520,6 +1520,7 @@ struct JobPool {
             idle.erase(it);
         }
         while (v.size() < 3) v.emplace_back(new ChunkJob());
+        for (auto& j : v) j->busy.store(false);  // a run that failed half-way may have left its jobs marked
         return v;
     }
     void give(rtx_ctx* ctx, std::vector<std::unique_ptr<ChunkJob>> v) {
