@@ -79,7 +79,7 @@ void rxh_queries_arrays(const rxh_queries* q, const uint64_t** seq_offsets, cons
  * from the calling thread (rxh_raxtax; see rxh_raxtax_multi for several GPUs); a non-zero return aborts the run like a failed channel send (raxtax.rs:87).
  * logger(user, level, message) receives the Info / Warn lines the reference writes to raxtax.log
  * (raxtax.rs:46-52): level 2 = Warn, 3 = Info; it is called from the driver threads (serialised with the sender).
- * chunk_size = queries per device batch (0 = about a quarter of the queries per GPU, between 2048 and 32768).  The driver keeps
+ * chunk_size = queries per device batch (0 = about an eighth of the queries per GPU, between 1024 and 32768).  The driver keeps
  * two batches in flight per GPU: while one runs, the next is prepared and uploaded and the previous one is formatted and sent,
  * so results (and a caller's progress file) appear chunk by chunk while the run is going.  A batch that does not fit the device
  * memory is split in halves and retried.
@@ -108,8 +108,8 @@ int rxh_raxtax(rtx_ctx* ctx, const rxh_queries* queries, const rxh_tree* tree, i
 void rxh_release_buffers(void);
 
 /* The same over several GPUs of one box (BASELINE config 3: queries partitioned, index replicated, no collective): ctxs[i] each hold
- * the whole index of `tree` (rxh_tree_upload); one driver thread per context pulls chunks of chunk_size queries (0 = ~4 chunks per
- * context, 2048..32768 queries) from a shared counter, as rayon's par_chunks does for the reference (raxtax.rs:35-39, main.rs:119-124).
+ * the whole index of `tree` (rxh_tree_upload); one driver thread per context pulls chunks of chunk_size queries (0 = ~8 chunks per
+ * context, 1024..32768 queries) from a shared counter, as rayon's par_chunks does for the reference (raxtax.rs:35-39, main.rs:119-124).
  * sender / logger are serialised; queries arrive in completion order (the reference's channel gives no order either). */
 int rxh_raxtax_multi(rtx_ctx* const* ctxs, size_t n_ctx, const rxh_queries* queries, const rxh_tree* tree, int skip_exact_matches,
                      int raw_confidence, size_t chunk_size, rxh_sender sender, void* sender_user, int tsv, rxh_logger logger,

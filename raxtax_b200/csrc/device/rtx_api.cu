@@ -22,9 +22,20 @@ struct EventPair {
 // Everything rtx_batch_upload sets up for ONE batch.  A context holds two of these ("slots", rtx_batch_slot): the active one is
 // the BatchState base of rtx_ctx, the other is parked; switching swaps them.  While the kernels of one slot run on `stream`, the
 // other slot can be uploaded (H2D on `stream_cp`) and its predecessor's results downloaded (D2H on `stream_cp` behind the slot's
-// ev_done), so the device never waits for the host between batches.  The large per-sub-batch scratch (counts, prefixes, tables)
-// is shared: only kernels on `stream` touch it and they are ordered by the stream.
+// ev_done), so the device never waits for the host between batches.  Every slot has its own compute stream and its own per-sub-batch
+// scratch (counts, prefixes, tables): the hit counting of the batch in one slot starts as soon as the hit counting of the batch in the
+// other slot is through (ev_k2) and so runs under that batch's probability / prefix / walk kernels, whose tails (persistent CTAs, one
+// CTA per query) leave most of the GPU idle -- what makes small batches cost no more than their share of a large one.
 struct BatchState {
+    cudaStream_t stream = nullptr;
+    // sub-batch pipeline: hit counting of sub-batch i+1 (stream) overlaps probabilities / prefix sums / tree walk of sub-batch i
+    // (stream2); the per-sub-batch buffers exist twice, events order the two streams
+    cudaStream_t stream2 = nullptr;
+    cudaEvent_t ev_hit[2] = {nullptr, nullptr}, ev_post[2] = {nullptr, nullptr};
+    cudaEvent_t ev_k2 = nullptr;  // the last hit-count launch of the slot's current run has finished
+    bool k2_recorded = false;
+    // per-sub-batch scratch
+    DevBuf d_counts, d_counts1, d_prob_big, d_cbuf, d_preb, d_ptab, d_segoff, d_preb1, d_ptab1, d_segoff1;
     bool has_batch = false;
     bool ran = false;
     BatchView bv{};
@@ -59,12 +70,7 @@ struct rtx_ctx : BatchState {
     int cur_slot = 0;
     int device = 0;
     int n_sms = 148;
-    cudaStream_t stream = nullptr;
     cudaStream_t stream_cp = nullptr;  // host <-> device copies of the batch slots
-    // sub-batch pipeline: hit counting of sub-batch i+1 (stream) overlaps probabilities / prefix sums / tree walk of sub-batch i
-    // (stream2); the per-sub-batch buffers exist twice, events order the two streams
-    cudaStream_t stream2 = nullptr;
-    cudaEvent_t ev_hit[2] = {nullptr, nullptr}, ev_post[2] = {nullptr, nullptr};
     bool pipeline_opt = false;  // RTX_OPT_PIPELINE (off: measured 9.95-10.2 ms pipelined against 9.89 ms serial on C2, profiles/r01x_pipeline.txt)
     cudaStream_t cur_stream = nullptr;  // what the launch helpers use: stream / slot of the sub-batch being issued
     u16* cur_counts = nullptr;
@@ -92,11 +98,7 @@ struct rtx_ctx : BatchState {
     DevBuf d_bitrows, d_rowmap, d_present, d_csr_off, d_csr_ids, d_node_lo, d_node_hi, d_node_type, d_child_first, d_child_count,
         d_node_blo, d_node_bhi, d_bnd_after, d_bnd_rank, d_ref_levels, d_lnfact, d_recs;
     DevBuf d_seq_codes, d_idx_off;  // reference sequences / their offsets while the index is built from them
-    // per-sub-batch scratch, shared by the two batch slots
-    DevBuf d_counts, d_counts1;
     size_t walk_smem = 0, bfs_smem = 0;
-    DevBuf d_prob_big;
-    DevBuf d_cbuf, d_preb, d_ptab, d_segoff, d_preb1, d_ptab1, d_segoff1;
     // reference-sharded mode
     ShardView sv{};
     DevBuf d_strad_of_node, d_strad_nodes, d_strad_parent, d_send, d_recv, d_sk, d_sany, d_sbest;
@@ -256,19 +258,21 @@ RTX_API int rtx_ctx_create(int device_ordinal, rtx_ctx** out) {
     rtx_ctx* c = new rtx_ctx();
     c->device = device_ordinal;
     c->n_sms = prop.multiProcessorCount;
-    e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
-    if (e == cudaSuccess) {  // the second stream carries the short kernels behind hit counting: its CTAs go first whenever an SM frees up
-        int prio_lo = 0, prio_hi = 0;
-        cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
-        e = cudaStreamCreateWithPriority(&c->stream2, cudaStreamNonBlocking, prio_hi);
-    }
-    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->stream_cp, cudaStreamNonBlocking);
+    e = cudaStreamCreateWithFlags(&c->stream_cp, cudaStreamNonBlocking);
+    int prio_lo = 0, prio_hi = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
     for (int i = 0; i < 2 && e == cudaSuccess; ++i) {
-        e = cudaEventCreateWithFlags(&c->ev_hit[i], cudaEventDisableTiming);
-        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&c->ev_post[i], cudaEventDisableTiming);
         BatchState& b = i ? c->parked : static_cast<BatchState&>(*c);
+        e = cudaStreamCreateWithFlags(&b.stream, cudaStreamNonBlocking);
+        // the second stream carries the short kernels behind hit counting: its CTAs go first whenever an SM frees up
+        if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&b.stream2, cudaStreamNonBlocking, prio_hi);
+        for (int k = 0; k < 2 && e == cudaSuccess; ++k) {
+            e = cudaEventCreateWithFlags(&b.ev_hit[k], cudaEventDisableTiming);
+            if (e == cudaSuccess) e = cudaEventCreateWithFlags(&b.ev_post[k], cudaEventDisableTiming);
+        }
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&b.ev_up, cudaEventDisableTiming);
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&b.ev_done, cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&b.ev_k2, cudaEventDisableTiming);
     }
     if (e != cudaSuccess) {
         std::string m = std::string("stream / event creation: ") + cudaGetErrorString(e);
@@ -304,8 +308,11 @@ RTX_API int rtx_ctx_create(int device_ordinal, rtx_ctx** out) {
 RTX_API void rtx_ctx_destroy(rtx_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
-    if (c->stream) cudaStreamSynchronize(c->stream);
-    if (c->stream2) cudaStreamSynchronize(c->stream2);
+    for (int i = 0; i < 2; ++i) {
+        BatchState& s = i ? c->parked : static_cast<BatchState&>(*c);
+        if (s.stream) cudaStreamSynchronize(s.stream);
+        if (s.stream2) cudaStreamSynchronize(s.stream2);
+    }
     drain_events(c);
     if (c->stream_cp) cudaStreamSynchronize(c->stream_cp);
     rtx_comm_destroy(c);
@@ -317,27 +324,28 @@ RTX_API void rtx_ctx_destroy(rtx_ctx* c) {
     for (DevBuf* b : gb) b->release();
     DevBuf* bufs[] = {&c->d_bitrows, &c->d_rowmap, &c->d_present, &c->d_csr_off, &c->d_csr_ids, &c->d_node_lo, &c->d_node_hi,
                       &c->d_node_type, &c->d_child_first, &c->d_child_count, &c->d_node_blo, &c->d_node_bhi, &c->d_bnd_after,
-                      &c->d_bnd_rank, &c->d_ref_levels, &c->d_lnfact, &c->d_counts, &c->d_counts1, &c->d_preb1, &c->d_ptab1, &c->d_segoff1,
-                      &c->d_seq_codes, &c->d_idx_off, &c->d_cbuf, &c->d_preb, &c->d_ptab, &c->d_segoff, &c->d_recs, &c->d_strad_of_node,
-                      &c->d_strad_nodes, &c->d_strad_parent, &c->d_send, &c->d_recv, &c->d_sk, &c->d_sany, &c->d_sbest, &c->d_prob_big};
+                      &c->d_bnd_rank, &c->d_ref_levels, &c->d_lnfact, &c->d_seq_codes, &c->d_idx_off, &c->d_recs, &c->d_strad_of_node,
+                      &c->d_strad_nodes, &c->d_strad_parent, &c->d_send, &c->d_recv, &c->d_sk, &c->d_sany, &c->d_sbest};
     for (DevBuf* b : bufs) b->release();
     for (int i = 0; i < 2; ++i) {
         BatchState& s = i ? c->parked : static_cast<BatchState&>(*c);
         DevBuf* sb[] = {&s.d_seq_off, &s.d_codes, &s.d_exact_off, &s.d_exact_ids, &s.d_K, &s.d_kmers, &s.d_rows, &s.d_nrows, &s.d_hist,
                         &s.d_pool_first, &s.d_pool_nlev, &s.d_pool_conf, &s.d_pool_local, &s.d_pool_used, &s.d_res_off, &s.d_res_cnt,
-                        &s.d_global, &s.d_status, &s.d_hits, &s.d_ord_begin, &s.d_ord_first, &s.d_ord_nlev, &s.d_ord_conf, &s.d_ord_local};
+                        &s.d_global, &s.d_status, &s.d_hits, &s.d_ord_begin, &s.d_ord_first, &s.d_ord_nlev, &s.d_ord_conf, &s.d_ord_local,
+                        &s.d_counts, &s.d_counts1, &s.d_prob_big, &s.d_cbuf, &s.d_preb, &s.d_ptab, &s.d_segoff, &s.d_preb1, &s.d_ptab1, &s.d_segoff1};
         for (DevBuf* b : sb) b->release();
         if (s.ev_up) cudaEventDestroy(s.ev_up);
         if (s.ev_done) cudaEventDestroy(s.ev_done);
+        if (s.ev_k2) cudaEventDestroy(s.ev_k2);
+        for (int k = 0; k < 2; ++k) {
+            if (s.ev_hit[k]) cudaEventDestroy(s.ev_hit[k]);
+            if (s.ev_post[k]) cudaEventDestroy(s.ev_post[k]);
+        }
+        if (s.stream2) cudaStreamDestroy(s.stream2);
+        if (s.stream) cudaStreamDestroy(s.stream);
     }
     if (c->h_arena) cudaFreeHost(c->h_arena);
-    for (int i = 0; i < 2; ++i) {
-        if (c->ev_hit[i]) cudaEventDestroy(c->ev_hit[i]);
-        if (c->ev_post[i]) cudaEventDestroy(c->ev_post[i]);
-    }
-    if (c->stream2) cudaStreamDestroy(c->stream2);
     if (c->stream_cp) cudaStreamDestroy(c->stream_cp);
-    if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
 
@@ -399,6 +407,8 @@ RTX_API int rtx_ctx_synchronize(rtx_ctx* ctx) {
     CU(cudaSetDevice(ctx->device));
     CU(cudaStreamSynchronize(ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream2));
+    CU(cudaStreamSynchronize(ctx->parked.stream));
+    CU(cudaStreamSynchronize(ctx->parked.stream2));
     CU(cudaStreamSynchronize(ctx->stream_cp));
     return RTX_OK;
 }
@@ -477,6 +487,9 @@ RTX_API int rtx_index_upload(rtx_ctx* ctx, const rtx_index_desc* d) {
     REQUIRE(d->node_lo[0] == 0 && d->node_hi[0] == N, "node 0 must be the root with range [0, n_refs)");
     CU(cudaSetDevice(ctx->device));
     CU(cudaStreamSynchronize(ctx->stream));
+    CU(cudaStreamSynchronize(ctx->parked.stream));
+    CU(cudaStreamSynchronize(ctx->stream2));
+    CU(cudaStreamSynchronize(ctx->parked.stream2));
     CU(cudaStreamSynchronize(ctx->stream_cp));
     ctx->has_index = false;
     ctx->has_batch = false;
@@ -750,8 +763,11 @@ RTX_API int rtx_index_upload(rtx_ctx* ctx, const rtx_index_desc* d) {
     ctx->n_rows = n_rows;
     ctx->index_bytes = bytes;
     {
-        DevBuf* scratch[] = {&ctx->d_counts, &ctx->d_counts1, &ctx->d_preb, &ctx->d_preb1, &ctx->d_segoff, &ctx->d_segoff1, &ctx->d_ptab, &ctx->d_ptab1, &ctx->d_cbuf};
-        for (DevBuf* b : scratch) b->release();  // sized for the previous index
+        for (int i = 0; i < 2; ++i) {  // sized for the previous index
+            BatchState& st = i ? ctx->parked : static_cast<BatchState&>(*ctx);
+            DevBuf* scratch[] = {&st.d_counts, &st.d_counts1, &st.d_preb, &st.d_preb1, &st.d_segoff, &st.d_segoff1, &st.d_ptab, &st.d_ptab1, &st.d_cbuf};
+            for (DevBuf* b : scratch) b->release();
+        }
         size_t mem_free = 0, mem_total = 0;
         if (cudaMemGetInfo(&mem_free, &mem_total) != cudaSuccess) mem_free = 8ull << 30;
         ctx->mem_free_after_index = mem_free;
@@ -784,9 +800,8 @@ static int ensure_pool(rtx_ctx* ctx, u64 cap) {
     return RTX_OK;
 }
 
-// The per-sub-batch scratch is shared by the two batch slots (only kernels on `stream` touch it, one slot's run after the other's):
-// before a slot's kernels are issued, make the buffers large enough for ITS layout and point its ProbScratch at them -- the other
-// slot's upload may have re-allocated them since.  Growing a buffer goes through cudaFree, which waits for the device.
+// Before a slot's kernels are issued: its per-sub-batch scratch large enough for the batch's layout, its ProbScratch pointed at it, the
+// per-function shared-memory ceilings set for this layout.  Growing a buffer goes through cudaFree, which waits for the device.
 static int bind_scratch(rtx_ctx* ctx) {
     CU(ctx->d_counts.ensure(std::max<size_t>(ctx->need_counts, 1)));
     CU(ctx->d_cbuf.ensure(std::max<size_t>(ctx->need_cbuf, 1)));
@@ -1212,6 +1227,10 @@ static int begin_run(rtx_ctx* ctx) {
         CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_up, 0));
         ctx->up_pending = false;
     }
+    // two hit-count kernels side by side would only halve each other's L2 share: this batch's kernels start when the hit counting of
+    // the batch in the other slot is through, i.e. under that batch's tail kernels
+    if (ctx->parked.k2_recorded) CU(cudaStreamWaitEvent(ctx->stream, ctx->parked.ev_k2, 0));
+    ctx->k2_recorded = false;
     return RTX_OK;
 }
 
@@ -1251,6 +1270,10 @@ static int run_all(rtx_ctx* ctx) {
             LaunchTimer lt(ctx, RTX_K_FIXUP);
             fixup_exact_kernel<<<(qb + 127) / 128, 128, 0, ctx->cur_stream>>>(ctx->ix, bv, ctx->cur_counts, (int)q0, qb);
             CU(cudaGetLastError());
+        }
+        if (q0 + ctx->sub_batch >= nq) {  // the run's last hit-count launch: the batch in the other slot may start counting behind it
+            CU(cudaEventRecord(ctx->ev_k2, ctx->stream));
+            ctx->k2_recorded = true;
         }
         if (pipe) {
             CU(cudaEventRecord(ctx->ev_hit[slot], ctx->stream));
@@ -2026,6 +2049,7 @@ RTX_API int rtx_profile_reset(rtx_ctx* ctx) {
     if (!ctx) return RTX_ERR_INVALID;
     CU(cudaSetDevice(ctx->device));
     CU(cudaStreamSynchronize(ctx->stream));
+    CU(cudaStreamSynchronize(ctx->parked.stream));
     CU(cudaStreamSynchronize(ctx->stream_cp));
     drain_events(ctx);
     ctx->prof = rtx_profile{};
@@ -2038,6 +2062,7 @@ RTX_API int rtx_profile_get(rtx_ctx* ctx, rtx_profile* out) {
     if (!ctx || !out) return RTX_ERR_INVALID;
     CU(cudaSetDevice(ctx->device));
     CU(cudaStreamSynchronize(ctx->stream));
+    CU(cudaStreamSynchronize(ctx->parked.stream));
     drain_events(ctx);
     *out = ctx->prof;
     return RTX_OK;

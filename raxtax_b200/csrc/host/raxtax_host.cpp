@@ -1963,7 +1963,8 @@ struct Worker {
         }
     }
     void emit(ChunkJob& j) {
-        const size_t n_parts = parts.size();
+        // the helpers are worth their wake-up (two condition-variable round trips, ~0.1 ms) only on chunks of several thousand queries
+        const size_t n_parts = j.cn >= 6144 ? parts.size() : 1;
         if (n_parts > 1) {
             std::lock_guard<std::mutex> g(h_mtx);
             h_job = &j;
@@ -2006,7 +2007,7 @@ struct Worker {
         size_t n_helpers = 0;
         if (const char* e = getenv("RXH_FORMAT_THREADS")) n_helpers = (size_t)std::max(0, atoi(e) - 1);
         else n_helpers = std::min<size_t>(3, std::max<size_t>(1, std::thread::hardware_concurrency() / 8));
-        if (nq < 512) n_helpers = 0;
+        if (nq < 512 || chunk_size < 6144) n_helpers = 0;  // emit() only fans chunks of >= 6144 queries out
         parts.resize(n_helpers + 1);
         for (size_t k = 1; k <= n_helpers; ++k) helpers.emplace_back([this, k] { helper_main(k); });
         drivers_running = n_ctx;
@@ -2099,10 +2100,10 @@ RXH_API int rxh_raxtax_multi(rtx_ctx* const* ctxs, size_t n_ctx, const rxh_queri
     }
     const size_t nq = queries->q->size();
     if (chunk_size == 0) {
-        // ~4 chunks per context so that the pipeline (upload | kernels | formatting) has something to overlap and results, the
+        // ~8 chunks per context so that the pipeline (upload | kernels | formatting) has something to overlap and results, the
         // progress file with them, appear while the run is going; bounded above so that the per-batch device arrays (~15 KB per
         // 1.5 kb query) stay small next to the index, and below so that the index is not re-read from HBM for a handful of queries
-        chunk_size = std::min<size_t>(32768, std::max<size_t>(2048, (nq + n_ctx * 4 - 1) / (n_ctx * 4)));
+        chunk_size = std::min<size_t>(32768, std::max<size_t>(1024, (nq + n_ctx * 8 - 1) / (n_ctx * 8)));
     }
     Worker w{*tree_h->t, *queries->q, nq, chunk_size, skip_exact_matches, raw_confidence, tsv, sender, sender_user, logger, logger_user};
     w.run(ctxs, n_ctx);
