@@ -1976,6 +1976,22 @@ __global__ void __launch_bounds__(256) shard_merge_write_kernel(MergeView mv, Ba
 // =========================================================================================================
 constexpr u32 kBfsEntries = 512;   // significant nodes + fallback chain nodes of one query
 constexpr u32 kBfsFrontier = 256;  // nodes of one level / simultaneously active fallback chains
+// Large frontiers.  Taxonomies have giant nodes (a genus with 75 k species, an order with thousands of families), and enumerating the
+// children of every frontier node made a flat-profile query test 250 k children per walk and even a one-line query 30-86 k.
+//   * Significant children (lineage.rs:126-149) are found by a mass-pruned search instead: a run of children whose total probability
+//     mass stays below 0.005 cannot contain a child with round(conf * 100) != 0, so a warp cuts a run into 32 sub-runs, reads the 33
+//     prefix values at their ends and keeps the sub-runs that reach the floor; runs of at most kBfsLeaf children ("pairs": node +
+//     child run) are then evaluated child by child exactly as before.  Disjoint runs of mass >= 0.005: at most 200 per round.
+//   * The fallback arg-max (lineage.rs:156-164) has no such bound -- every child of a chain head has to be looked at -- except for a
+//     query that kept few 512-reference segments (K4's mass cut): children wholly inside dropped segments are exactly 0, and the
+//     runs that overlap a kept segment are found by binary search over the head's sorted child ranges (bfs_build_pairs).
+constexpr u32 kBfsKept = 128;                         // more kept segments than this: the arg-max looks at every child (flat profiles)
+constexpr u32 kBfsPairs = 512;                        // >= kBfsFrontier + max(kBfsKept, 200)
+constexpr u32 kBfsPairMin = 768;                      // frontiers with fewer children are enumerated as before
+constexpr u32 kBfsSmallNode = 48;                     // arg-max pairs: a node with so few children is one pair, no search
+constexpr u32 kBfsLeaf = 64;                          // search: runs this short are evaluated child by child
+constexpr u32 kBfsQueue = 256;                        // search: runs in flight per round
+constexpr double kBfsMassFloor = 0.004999;            // a child is significant from 0.005 on; the margin covers the rounding of the sums
 constexpr int kBfsThreadsDefault = 256;  // CTA size of lineage_bfs_kernel (template parameter: RTX_OPT_WALK_VARIANT 2 runs 128)
 
 struct BfsSmem {
@@ -1985,21 +2001,31 @@ struct BfsSmem {
     u32* ent_cc;               // [E] child_count | type << 30
     u32* ent_lo;               // [E]
     u32* ent_size;             // [E]
-    u32* fr_off;               // [F + 1]
+    u32* fr_off;               // [P + 1] offsets of the flattened children, per frontier node or per pair
     u32* besti;                // [F]
+    u32* pair_a;               // [P] first child of the pair's run
+    u32* pair_b;               // [P] one past its last child
+    u32* pbase;                // [F + 1] first pair of a frontier node
+    u32* kept;                 // [kBfsKept] kept segments, ascending
+    u32* q_a;                  // [2][kBfsQueue] search runs (current / next round): first child,
+    u32* q_b;                  // [2][kBfsQueue] one past the last child,
     u16* ent_parent;           // [E]
     u16* list_a;               // [F] fallback heads / active chains (current)
     u16* list_b;               // [F] active chains (next)
     u16* res_ent;              // [R]
     u16* order;                // [R]
+    u16* pair_own;             // [P] frontier position of the pair's node
+    u16* pj0;                  // [F] first kept segment under a frontier node
+    u16* q_own;                // [2][kBfsQueue] frontier position of the run's node
     u8* ent_k;                 // [E]
     u8* ent_depth;             // [E]
     u8* ent_any;               // [E]
     u8* res_k;                 // [R][ML]
-    static constexpr u32 E = kBfsEntries, F = kBfsFrontier, R = RTX_MAX_RESULTS_PER_QUERY;
+    static constexpr u32 E = kBfsEntries, F = kBfsFrontier, R = RTX_MAX_RESULTS_PER_QUERY, P = kBfsPairs;
     __host__ __device__ static size_t bytes(u32 ML) {
-        size_t b = (size_t)F * 8 + (size_t)R * 8 + (size_t)E * 16 + (size_t)(F + 1) * 4 + (size_t)F * 4 + (size_t)E * 2 + (size_t)F * 4 + (size_t)R * 4 +
-                   (size_t)E * 3 + (size_t)R * ML;
+        size_t b = (size_t)F * 8 + (size_t)R * 8 + (size_t)E * 16 + (size_t)(P + 1) * 4 + (size_t)F * 4 + (size_t)P * 8 + (size_t)(F + 1) * 4 +
+                   (size_t)kBfsKept * 4 + (size_t)kBfsQueue * 20 + (size_t)E * 2 + (size_t)F * 4 + (size_t)R * 4 + (size_t)P * 2 + (size_t)F * 2 + (size_t)E * 3 +
+                   (size_t)R * ML;
         return (b + 64 + 15) & ~(size_t)15;
     }
     __device__ BfsSmem(unsigned char* base, u32 ML) {
@@ -2010,13 +2036,22 @@ struct BfsSmem {
         ent_lo = ent_cc + E;
         ent_size = ent_lo + E;
         fr_off = ent_size + E;
-        besti = fr_off + F + 1;
-        ent_parent = reinterpret_cast<u16*>(besti + F);
+        besti = fr_off + P + 1;
+        pair_a = besti + F;
+        pair_b = pair_a + P;
+        pbase = pair_b + P;
+        kept = pbase + F + 1;
+        q_a = kept + kBfsKept;
+        q_b = q_a + 2 * kBfsQueue;
+        ent_parent = reinterpret_cast<u16*>(q_b + 2 * kBfsQueue);
         list_a = ent_parent + E;
         list_b = list_a + F;
         res_ent = list_b + F;
         order = res_ent + R;
-        ent_k = reinterpret_cast<u8*>(order + R);
+        pair_own = order + R;
+        pj0 = pair_own + P;
+        q_own = pj0 + F;
+        ent_k = reinterpret_cast<u8*>(q_own + 2 * kBfsQueue);
         ent_depth = ent_k + E;
         ent_any = ent_depth + E;
         res_k = ent_any + E;
@@ -2047,13 +2082,224 @@ __device__ __forceinline__ u32 bfs_owner(const u32* __restrict__ fr_off, u32 n, 
     return lo;
 }
 
+// first index in the ascending list `a[0..n)` whose value is >= key
+__device__ __forceinline__ u32 bfs_lower_bound(const u32* __restrict__ a, u32 n, u32 key) {
+    u32 lo = 0, hi = n;
+    while (lo < hi) {
+        const u32 mid = (lo + hi) >> 1;
+        if (a[mid] < key) lo = mid + 1;
+        else hi = mid;
+    }
+    return lo;
+}
+
+// Sparse expansion of `n` frontier nodes (log entries given by index list or by a contiguous range): the pairs (node, kept segment
+// under it) with the run of the node's children that overlaps the segment -> pair_own / pair_a, fr_off[0..P] = offsets of the runs in
+// the flattened child list.  Runs of one node are clipped against their predecessor, so no child appears twice.  Children are sorted
+// and disjoint (tree.rs:77-107), their [lo, lo + size) are read from the node records.  Block-wide (four barriers); returns P.
+template <int kBfsThreads>
+__device__ u32 bfs_build_pairs(const BfsSmem& w, const NodeRec* __restrict__ recs, u32 n, u32 range_begin, const u16* __restrict__ list,
+                               u32 n_kept, int tid) {
+    const int lane = tid & 31, warp = tid >> 5;
+    for (u32 i = tid; i < n; i += kBfsThreads) {
+        const u32 e = list ? (u32)list[i] : range_begin + i;
+        const u32 cc = w.ent_cc[e] & 0x3FFFFFFFu;
+        const u32 lo = w.ent_lo[e], hi = lo + w.ent_size[e];
+        const u32 j0 = bfs_lower_bound(w.kept, n_kept, lo / kPrefixSeg);
+        const u32 j1 = bfs_lower_bound(w.kept, n_kept, (hi + kPrefixSeg - 1) / kPrefixSeg);
+        u32 np = (cc == 0 || j1 <= j0) ? 0u : j1 - j0;
+        if (cc <= kBfsSmallNode) np = min(np, 1u);
+        w.pj0[i] = (u16)j0;
+        w.besti[i] = np;  // (the fallback rounds initialise besti behind this call)
+    }
+    __syncthreads();
+    if (warp == 0) {
+        u32 running = 0;
+        for (u32 bb = 0; bb < n; bb += 32) {
+            const u32 i = bb + lane;
+            const u32 c = (i < n) ? w.besti[i] : 0u;
+            const u32 inc = warp_scan_incl(c, lane);
+            if (i < n) w.pbase[i] = running + inc - c;
+            running += __shfl_sync(kFullMask, inc, 31);
+        }
+        if (lane == 0) w.pbase[n] = running;
+    }
+    __syncthreads();
+    const u32 P = w.pbase[n];
+    for (u32 t = tid; t < 2 * P; t += kBfsThreads) {
+        const u32 p = t >> 1, upper = t & 1u;
+        const u32 i = bfs_owner(w.pbase, n, p);
+        const u32 e = list ? (u32)list[i] : range_begin + i;
+        const u32 cf = w.ent_cf[e], cc = w.ent_cc[e] & 0x3FFFFFFFu;
+        u32 val;
+        if (cc <= kBfsSmallNode) {
+            val = upper ? cc : 0u;
+        } else {
+            const u32 seg = w.kept[(u32)w.pj0[i] + (p - w.pbase[i])];
+            // lower: first child that ends behind the segment's first reference; upper: first child that starts behind its last one
+            const u64 key = upper ? ((u64)seg + 1u) * kPrefixSeg : (u64)seg * kPrefixSeg;
+            u32 lo = 0, hi = cc;
+            while (lo < hi) {
+                const u32 mid = (lo + hi) >> 1;
+                const uint2 ls = *reinterpret_cast<const uint2*>(&recs[cf + mid].lo);  // lo, size
+                const bool right = upper ? ((u64)ls.x >= key) : ((u64)ls.x + ls.y > key);
+                if (right) hi = mid;
+                else lo = mid + 1;
+            }
+            val = lo;
+        }
+        if (upper) {
+            w.pair_b[p] = val;
+        } else {
+            w.pair_a[p] = val;
+            w.pair_own[p] = (u16)i;
+        }
+    }
+    __syncthreads();
+    if (warp == 0) {
+        u32 running = 0;
+        for (u32 bb = 0; bb < P; bb += 32) {
+            const u32 p = bb + lane;
+            u32 a = 0, c = 0;
+            if (p < P) {
+                a = w.pair_a[p];
+                if (p > 0 && w.pair_own[p - 1] == w.pair_own[p]) a = max(a, w.pair_b[p - 1]);  // pair_b ascends within a node
+                const u32 bx = w.pair_b[p];
+                c = bx > a ? bx - a : 0u;
+            }
+            const u32 inc = warp_scan_incl(c, lane);
+            __syncwarp();
+            if (p < P) {
+                w.pair_a[p] = a;
+                w.fr_off[p] = running + inc - c;
+            }
+            running += __shfl_sync(kFullMask, inc, 31);
+        }
+        if (lane == 0) w.fr_off[P] = running;
+    }
+    __syncthreads();
+    return P;
+}
+
+// probability mass in front of child j of a node (j == cc: behind its last child), from the boundary prefixes (see node_conf)
+__device__ __forceinline__ double bfs_child_prefix(const NodeRec* __restrict__ recs, u32 cf, u32 cc, u32 j, const double* __restrict__ preb,
+                                                   const double* __restrict__ segoff, const u32* __restrict__ skipw) {
+    const bool end = j >= cc;
+    const NodeRec* r = recs + cf + (end ? cc - 1u : j);
+    const uint2 bb = *reinterpret_cast<const uint2*>(&r->blo), ss = *reinterpret_cast<const uint2*>(&r->slo);
+    const u32 bi = end ? bb.y : bb.x, si = end ? ss.y : ss.x;
+    const double pv = preb[bi];
+    const bool sk = (skipw[si >> 5] >> (si & 31)) & 1u;
+    return segoff[si] + (sk ? 0.0 : pv);
+}
+
+// Mass-pruned search for the child runs of `n` frontier nodes (log entries range_begin ..) that can hold a significant child ->
+// pair_own / pair_a, fr_off[0..P].  ctr: three shared counters (pairs, runs of this round, runs of the next).  Block-wide; returns P,
+// or ~0u when a list overflowed (the caller hands the query to the depth-first walker).
+template <int kBfsThreads>
+__device__ u32 bfs_search_pairs(const BfsSmem& w, const NodeRec* __restrict__ recs, const double* __restrict__ preb, const double* __restrict__ segoff,
+                                const u32* __restrict__ skipw, u32 n, u32 range_begin, u32* ctr, int tid) {
+    constexpr int kBfsWarps = kBfsThreads / 32;
+    const int lane = tid & 31, warp = tid >> 5;
+    const u32 lt_mask = (1u << lane) - 1u;
+    if (tid < 4) ctr[tid] = 0u;  // [3]: overflow
+    __syncthreads();
+    for (u32 bb = 0; bb < n; bb += kBfsThreads) {  // small nodes are one pair each, the others start as one run
+        const u32 i = bb + tid;
+        const u32 cc = (i < n) ? (w.ent_cc[range_begin + i] & 0x3FFFFFFFu) : 0u;
+        const bool small = cc != 0 && cc <= kBfsLeaf, big = cc > kBfsLeaf;
+        const u32 ms = __ballot_sync(kFullMask, small), mb = __ballot_sync(kFullMask, big);
+        u32 ps = 0, pb = 0;
+        if (lane == 0) {
+            if (ms) ps = atomicAdd(&ctr[0], (u32)__popc(ms));
+            if (mb) pb = atomicAdd(&ctr[1], (u32)__popc(mb));
+        }
+        ps = __shfl_sync(kFullMask, ps, 0);
+        pb = __shfl_sync(kFullMask, pb, 0);
+        if (ps + __popc(ms) > kBfsPairs || pb + __popc(mb) > kBfsQueue) {
+            if (lane == 0) ctr[3] = 1u;
+        } else if (small) {
+            const u32 pos = ps + __popc(ms & lt_mask);
+            w.pair_own[pos] = (u16)i;
+            w.pair_a[pos] = 0u;
+            w.pair_b[pos] = cc;
+        } else if (big) {
+            const u32 pos = pb + __popc(mb & lt_mask);
+            w.q_own[pos] = (u16)i;
+            w.q_a[pos] = 0u;
+            w.q_b[pos] = cc;
+        }
+    }
+    __syncthreads();
+    u32 cur = 0;
+    while (true) {  // block-uniform
+        const u32 n_in = ctr[1 + cur];
+        if (n_in == 0 || ctr[3]) break;
+        const u32 nxt = cur ^ 1u;
+        for (u32 it = warp; it < n_in; it += kBfsWarps) {
+            const u32 own = w.q_own[cur * kBfsQueue + it], a = w.q_a[cur * kBfsQueue + it], b = w.q_b[cur * kBfsQueue + it];
+            const u32 e = range_begin + own;
+            const u32 cf = w.ent_cf[e], cc = w.ent_cc[e] & 0x3FFFFFFFu;
+            const u32 step = (b - a + 31u) / 32u;
+            const u32 sa = min(a + (u32)lane * step, b), sb = min(sa + step, b);
+            const double v0 = bfs_child_prefix(recs, cf, cc, sa, preb, segoff, skipw);
+            double v1 = __shfl_down_sync(kFullMask, v0, 1);
+            if (lane == 31) v1 = bfs_child_prefix(recs, cf, cc, sb, preb, segoff, skipw);
+            const bool keep = sa < sb && (v1 - v0) >= kBfsMassFloor;
+            const bool leaf = keep && sb - sa <= kBfsLeaf, more = keep && !leaf;
+            const u32 ml = __ballot_sync(kFullMask, leaf), mm = __ballot_sync(kFullMask, more);
+            u32 pl = 0, pm = 0;
+            if (lane == 0) {
+                if (ml) pl = atomicAdd(&ctr[0], (u32)__popc(ml));
+                if (mm) pm = atomicAdd(&ctr[1 + nxt], (u32)__popc(mm));
+            }
+            pl = __shfl_sync(kFullMask, pl, 0);
+            pm = __shfl_sync(kFullMask, pm, 0);
+            if (pl + __popc(ml) > kBfsPairs || pm + __popc(mm) > kBfsQueue) {
+                if (lane == 0) ctr[3] = 1u;
+            } else if (leaf) {
+                const u32 pos = pl + __popc(ml & lt_mask);
+                w.pair_own[pos] = (u16)own;
+                w.pair_a[pos] = sa;
+                w.pair_b[pos] = sb;
+            } else if (more) {
+                const u32 pos = nxt * kBfsQueue + pm + __popc(mm & lt_mask);
+                w.q_own[pos] = (u16)own;
+                w.q_a[pos] = sa;
+                w.q_b[pos] = sb;
+            }
+        }
+        __syncthreads();
+        if (tid == 0) ctr[1 + cur] = 0u;
+        cur = nxt;
+        __syncthreads();
+    }
+    if (ctr[3]) return ~0u;
+    const u32 P = ctr[0];
+    if (warp == 0) {
+        u32 running = 0;
+        for (u32 bb = 0; bb < P; bb += 32) {
+            const u32 p = bb + lane;
+            const u32 c = (p < P) ? w.pair_b[p] - w.pair_a[p] : 0u;
+            const u32 inc = warp_scan_incl(c, lane);
+            if (p < P) w.fr_off[p] = running + inc - c;
+            running += __shfl_sync(kFullMask, inc, 31);
+        }
+        if (lane == 0) w.fr_off[P] = running;
+    }
+    __syncthreads();
+    return P;
+}
+
 template <int kBfsThreads>
 __global__ void __launch_bounds__(kBfsThreads)  // (a 6-CTA/SM bound, 40 registers with small spills, measured the same 0.89 ms)
     lineage_bfs_kernel(IndexView ix, const NodeRec* __restrict__ recs, BatchView b, ResultPool pool, ProbScratch sc, int q_base, int q_count,
-                       u32 entry_cap) {
+                       u32 entry_cap, int sparse) {
     constexpr int kBfsWarps = kBfsThreads / 32;
     extern __shared__ __align__(16) unsigned char bsm_raw[];
     __shared__ u32 s_log_n, s_n_res, s_n_fb, s_n_next, s_retry, s_retry_cls;  // s_retry_cls: raised while sorting a frontier (see the level loop)
+    __shared__ u32 s_n_kept;  // kept segments of a sparse query, 0 = the arg-max looks at every child
+    __shared__ u32 s_ctr[4], s_slow;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int ql = blockIdx.x;
     if (ql >= q_count) return;
@@ -2087,14 +2333,50 @@ __global__ void __launch_bounds__(kBfsThreads)  // (a 6-CTA/SM bound, 40 registe
             s_retry = 0;
             s_retry_cls = 0;
         }
+        if (warp == 0) {  // the kept segments (K4's skip bitmap, complemented), in ascending order, if they are few
+            const u32 n_seg = (u32)(ix.n_pad / kPrefixSeg), n_words = (n_seg + 31u) / 32u;
+            u32 running = 0;
+            bool few = sparse != 0;
+            for (u32 bb = 0; bb < n_words && few; bb += 32) {
+                const u32 wi = bb + lane;
+                u32 kw = 0;
+                if (wi < n_words) {
+                    kw = ~skipw[wi];
+                    if (wi * 32u + 32u > n_seg) kw &= (1u << (n_seg - wi * 32u)) - 1u;  // (n_seg is not a multiple of 32 here)
+                }
+                const u32 c = __popc(kw);
+                const u32 inc = warp_scan_incl(c, lane);
+                const u32 tot = __shfl_sync(kFullMask, inc, 31);
+                if (running + tot > kBfsKept) {
+                    few = false;
+                } else {
+                    u32 pos = running + inc - c;
+                    while (kw) {
+                        w.kept[pos++] = wi * 32u + (u32)__ffs(kw) - 1u;
+                        kw &= kw - 1u;
+                    }
+                    running += tot;
+                }
+            }
+            if (lane == 0) s_n_kept = few ? running : 0u;
+        }
         __syncthreads();
+        const u32 n_kept = s_n_kept;
         // ---- significant nodes, level by level (lineage.rs:126-149).  Two barriers per level: the child offsets of the current
         // frontier (warp 0) are computed in the same phase in which the previous frontier is sorted into result lines and
         // fallback heads (its ent_any flags are final since the barrier behind the evaluation that set them).  Each phase has its
         // own overflow flag -- s_retry_cls is written before the first barrier and read behind it, s_retry between the barriers and
         // read behind the second -- so that no warp can test a flag another warp is raising in the same phase -------------
         u32 lvl_begin = 0, lvl_end = 1, prev_begin = 0, prev_end = 0;
+#ifdef RTX_WALK_TRACE
+        const long long tr_t0 = clock64();
+        long long tr_lvl_t[12];
+        u32 tr_lvl_tot[12], tr_lvl_nf[12], tr_nl = 0, tr_fb_children = 0, tr_fb_rounds = 0, tr_fb_heads = 0;
+#endif
         while (true) {
+#ifdef RTX_WALK_TRACE
+            const long long tr_a = clock64();
+#endif
             const bool have = lvl_begin < lvl_end;
             const u32 nf = lvl_end - lvl_begin;
             if (have && warp == 0) bfs_child_offsets(w, nf, lvl_begin, nullptr, lane);
@@ -2126,7 +2408,16 @@ __global__ void __launch_bounds__(kBfsThreads)  // (a 6-CTA/SM bound, 40 registe
             }
             __syncthreads();
             if (!have || s_retry_cls) break;
-            const u32 total = w.fr_off[nf];
+            u32 total = w.fr_off[nf], n_own = nf;
+            const bool pairs = sparse != 0 && total >= kBfsPairMin;  // block-uniform
+            if (pairs) {
+                n_own = bfs_search_pairs<kBfsThreads>(w, recs, preb, segoff, skipw, nf, lvl_begin, s_ctr, tid);
+                if (n_own == ~0u) {  // (every thread sees the same return value)
+                    if (tid == 0) s_retry = 1;
+                    break;
+                }
+                total = w.fr_off[n_own];
+            }
             for (u32 base = (u32)warp * 64; base < total; base += kBfsWarps * 64) {  // two chunks of 32 children in flight per warp
                 u32 kk[2], ee[2];
                 NodeRec cr[2];
@@ -2136,8 +2427,9 @@ __global__ void __launch_bounds__(kBfsThreads)  // (a 6-CTA/SM bound, 40 registe
                     ee[u] = 0;
                     cr[u] = NodeRec{0, 0, 0, 0, 0, 0, 0, 0};
                     if (idx < total) {
-                        ee[u] = lvl_begin + bfs_owner(w.fr_off, nf, idx);
-                        cr[u] = recs[w.ent_cf[ee[u]] + (idx - w.fr_off[ee[u] - lvl_begin])];
+                        const u32 o = bfs_owner(w.fr_off, n_own, idx);
+                        ee[u] = lvl_begin + (pairs ? (u32)w.pair_own[o] : o);
+                        cr[u] = recs[w.ent_cf[ee[u]] + (pairs ? w.pair_a[o] : 0u) + (idx - w.fr_off[o])];
                     }
                 }
 #pragma unroll
@@ -2173,6 +2465,14 @@ __global__ void __launch_bounds__(kBfsThreads)  // (a 6-CTA/SM bound, 40 registe
                 }
             }
             __syncthreads();
+#ifdef RTX_WALK_TRACE
+            if (tr_nl < 12) {
+                tr_lvl_t[tr_nl] = clock64() - tr_a;
+                tr_lvl_tot[tr_nl] = total;
+                tr_lvl_nf[tr_nl] = nf | (pairs ? 0x80000000u : 0u);
+                ++tr_nl;
+            }
+#endif
             if (s_retry) break;
             prev_begin = lvl_begin;
             prev_end = lvl_end;
@@ -2190,31 +2490,114 @@ __global__ void __launch_bounds__(kBfsThreads)  // (a 6-CTA/SM bound, 40 registe
         u16* cur = w.list_a;
         u16* nxt = w.list_b;
         u32 n_ch = s_retry ? 0u : s_n_fb;
+#ifdef RTX_WALK_TRACE
+        const long long tr_t1 = clock64();
+        tr_fb_heads = n_ch;
+#endif
         while (n_ch > 0) {  // block-uniform
             if (warp == 0) bfs_child_offsets(w, n_ch, 0, cur, lane);
-            for (u32 i = tid; i < n_ch; i += kBfsThreads) {
-                w.best[i] = 0ull;
-                w.besti[i] = 0u;
-            }
             if (tid == 0) s_n_next = 0;
             __syncthreads();
-            const u32 total = w.fr_off[n_ch];
-            for (u32 idx = tid; idx < total; idx += kBfsThreads) {  // pass A: the largest child confidence of every chain head
-                const u32 c = bfs_owner(w.fr_off, n_ch, idx);
-                const NodeRec cr = recs[w.ent_cf[cur[c]] + (idx - w.fr_off[c])];
-                const double v = fmax(node_conf(preb, segoff, skipw, cr), 0.0);
-                atomicMax(&w.best[c], (unsigned long long)__double_as_longlong(v));  // non-negative doubles order like their bits
+            u32 total = w.fr_off[n_ch], n_own = n_ch;
+            const bool pairs = n_kept != 0 && total >= kBfsPairMin;  // block-uniform
+            if (pairs) {
+                n_own = bfs_build_pairs<kBfsThreads>(w, recs, n_ch, 0, cur, n_kept, tid);
+                total = w.fr_off[n_own];
+            }
+            for (u32 i = tid; i < n_ch; i += kBfsThreads) {
+                w.best[i] = 0ull;
+                w.besti[i] = 0u;  // 1 + child index of the chain's last "record" (below); bit 31: the chain takes the second pass
+            }
+            if (tid == 0) s_slow = 0;
+#ifdef RTX_WALK_TRACE
+            tr_fb_children += total;
+            ++tr_fb_rounds;
+#endif
+            __syncthreads();
+            // max_by(partial_cmp): the LAST maximal child wins (lineage.rs:156-164); children tied in exact arithmetic (same hit counts)
+            // differ only by rounding noise of the prefix sums, so values within 1e-12 relative of the maximum count as maximal.
+            // One pass: a child within the tolerance of the running maximum of its chain is a "record"; every child within the
+            // tolerance of the FINAL maximum is one (the running maximum only grows), so the record with the largest index is the
+            // answer if it passes the final test itself -- else (values in the 1e-12 band right below the tolerance: practically
+            // never) the chain is scanned a second time.  A warp whose 32 children belong to one chain (the giant nodes that carry the
+            // cost) reduces first and touches shared memory twice.
+            for (u32 base = 0; base < total; base += 2 * kBfsThreads) {  // two children per lane in flight
+                bool valid[2];
+                u32 c[2], ci[2];
+                NodeRec cr[2];
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    const u32 idx = base + u * kBfsThreads + tid;
+                    valid[u] = idx < total;
+                    c[u] = 0;
+                    ci[u] = 0;
+                    cr[u] = NodeRec{0, 0, 0, 0, 0, 0, 0, 0};
+                    if (valid[u]) {
+                        const u32 o = bfs_owner(w.fr_off, n_own, idx);
+                        c[u] = pairs ? (u32)w.pair_own[o] : o;
+                        ci[u] = (pairs ? w.pair_a[o] : 0u) + (idx - w.fr_off[o]);
+                        cr[u] = recs[w.ent_cf[cur[c[u]]] + ci[u]];
+                    }
+                }
+                double vv[2];
+#pragma unroll
+                for (int u = 0; u < 2; ++u) vv[u] = valid[u] ? fmax(node_conf(preb, segoff, skipw, cr[u]), 0.0) : 0.0;
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    const double v = vv[u];
+                    const u32 vm = __ballot_sync(kFullMask, valid[u]);
+                    if (vm == 0u) continue;  // warp-uniform
+                    const u32 c0 = __shfl_sync(kFullMask, c[u], __ffs(vm) - 1);
+                    if (__all_sync(kFullMask, !valid[u] || c[u] == c0)) {
+                        double vmax = v;  // (invalid lanes hold 0.0, the smallest admissible value)
+#pragma unroll
+                        for (int o2 = 16; o2 > 0; o2 >>= 1) vmax = fmax(vmax, __shfl_xor_sync(kFullMask, vmax, o2));
+                        unsigned long long old = 0ull;
+                        if (lane == 0) old = atomicMax(&w.best[c0], (unsigned long long)__double_as_longlong(vmax));  // non-negative doubles order like their bits
+                        old = __shfl_sync(kFullMask, old, 0);
+                        const double run = fmax(__longlong_as_double((long long)old), vmax);
+                        const bool rec = valid[u] && v >= run - fabs(run) * 1e-12;
+                        const u32 r = __reduce_max_sync(kFullMask, rec ? ci[u] + 1u : 0u);
+                        if (lane == 0 && r) atomicMax(&w.besti[c0], r);
+                    } else if (valid[u]) {
+                        const unsigned long long old = atomicMax(&w.best[c[u]], (unsigned long long)__double_as_longlong(v));
+                        const double run = fmax(__longlong_as_double((long long)old), v);
+                        if (v >= run - fabs(run) * 1e-12) atomicMax(&w.besti[c[u]], ci[u] + 1u);
+                    }
+                }
             }
             __syncthreads();
-            for (u32 idx = tid; idx < total; idx += kBfsThreads) {  // pass B: the LAST child within 1e-12 relative of the maximum
-                const u32 c = bfs_owner(w.fr_off, n_ch, idx);
-                const u32 ci = idx - w.fr_off[c];
-                const NodeRec cr = recs[w.ent_cf[cur[c]] + ci];
-                const double v = fmax(node_conf(preb, segoff, skipw, cr), 0.0);
-                const double bestv = __longlong_as_double((long long)w.best[c]);
-                if (v >= bestv - fabs(bestv) * 1e-12) atomicMax(&w.besti[c], ci);
+            for (u32 i = tid; i < n_ch; i += kBfsThreads) {  // does the last record pass the final test?
+                const u32 head = cur[i];
+                const u32 hcc = w.ent_cc[head] & 0x3FFFFFFFu;
+                const double bestv = __longlong_as_double((long long)w.best[i]);
+                if (w.best[i] == 0ull || w.besti[i] == 0u) {
+                    // no child above 0: all of them tie and the last one wins (the children outside the kept segments, which the
+                    // sparse expansion does not look at, are exactly 0 as well)
+                    w.besti[i] = hcc;
+                } else {
+                    const NodeRec cr = recs[w.ent_cf[head] + w.besti[i] - 1u];
+                    const double v = fmax(node_conf(preb, segoff, skipw, cr), 0.0);
+                    if (!(v >= bestv - fabs(bestv) * 1e-12)) {
+                        w.besti[i] = 0x80000000u;
+                        s_slow = 1u;
+                    }
+                }
             }
             __syncthreads();
+            if (s_slow) {  // block-uniform; second pass over the marked chains: the LAST child within 1e-12 relative of the maximum
+                for (u32 idx = tid; idx < total; idx += kBfsThreads) {
+                    const u32 o = bfs_owner(w.fr_off, n_own, idx);
+                    const u32 c = pairs ? (u32)w.pair_own[o] : o;
+                    if (!(w.besti[c] & 0x80000000u)) continue;
+                    const u32 ci = (pairs ? w.pair_a[o] : 0u) + (idx - w.fr_off[o]);
+                    const NodeRec cr = recs[w.ent_cf[cur[c]] + ci];
+                    const double v = fmax(node_conf(preb, segoff, skipw, cr), 0.0);
+                    const double bestv = __longlong_as_double((long long)w.best[c]);
+                    if (v >= bestv - fabs(bestv) * 1e-12) atomicMax(&w.besti[c], 0x80000000u | (ci + 1u));
+                }
+                __syncthreads();
+            }
             for (u32 bb = 0; bb < n_ch; bb += kBfsThreads) {  // one new log entry (0.01) per chain; Inner nodes stay active
                 const u32 i = bb + tid;
                 const bool valid = i < n_ch;
@@ -2222,6 +2605,8 @@ __global__ void __launch_bounds__(kBfsThreads)  // (a 6-CTA/SM bound, 40 registe
                 u32 head = 0;
                 if (valid) {
                     head = cur[i];
+                    const u32 b1 = w.besti[i] & 0x7FFFFFFFu;  // 1 + index of the chosen child
+                    w.besti[i] = b1 ? b1 - 1u : 0u;
                     br = recs[w.ent_cf[head] + w.besti[i]];
                 }
                 const bool go_on = valid && (br.cc_type >> 30) == 0;
@@ -2260,6 +2645,17 @@ __global__ void __launch_bounds__(kBfsThreads)  // (a 6-CTA/SM bound, 40 registe
             __syncthreads();
         }
         const bool retry = s_retry != 0;
+#ifdef RTX_WALK_TRACE
+        if (tid == 0) {
+            const long long tr_t2 = clock64();
+            if (tr_t2 - tr_t0 > 200000 || (q % 97) == 0) {
+                printf("TR q %d kept %u retry %d res %u lvl_clk %lld fb_clk %lld heads %u rounds %u fbch %u |", q, n_kept, (int)retry, s_n_res, tr_t1 - tr_t0, tr_t2 - tr_t1,
+                       tr_fb_heads, tr_fb_rounds, tr_fb_children);
+                for (u32 i = 0; i < tr_nl; ++i) printf(" L%u nf %u%s ch %u clk %lld", i, tr_lvl_nf[i] & 0xFFFFu, (tr_lvl_nf[i] >> 31) ? "p" : "", tr_lvl_tot[i], tr_lvl_t[i]);
+                printf("\n");
+            }
+        }
+#endif
         n_res = retry ? 0u : s_n_res;
         // ---- confidence vectors and local signals of the result lines (lineage.rs:95-102, utils.rs:91-105) -------------
         bool too_deep = false;

@@ -374,7 +374,7 @@ RTX_API int rtx_ctx_set_option(rtx_ctx* ctx, int option, int64_t value) {
             ctx->pipeline_opt = value != 0;
             return RTX_OK;
         case RTX_OPT_WALK_VARIANT:
-            REQUIRE(value >= 0 && value <= 2, "unknown walk variant");  // 2: level-synchronous walk with 128-thread CTAs
+            REQUIRE(value >= 0 && value <= 3, "unknown walk variant");  // 2: level-synchronous walk with 128-thread CTAs, 3: without the sparse expansion
             ctx->walk_variant = (int)value;
             return RTX_OK;
         case RTX_OPT_WALK_LOG_CAP:
@@ -1286,14 +1286,14 @@ static int run_all(rtx_ctx* ctx) {
         }
         {
             LaunchTimer lt(ctx, RTX_K_WALK);
-            if (ctx->walk_variant == 0 || ctx->walk_variant == 2) {  // level-synchronous walk, then the depth-first walker for the queries it handed back
+            if (ctx->walk_variant != 1) {  // level-synchronous walk, then the depth-first walker for the queries it handed back
                 const u32 cap = ctx->walk_log_cap ? (u32)ctx->walk_log_cap : kBfsEntries;
                 if (ctx->walk_variant == 2)
                     lineage_bfs_kernel<128><<<qb, 128, ctx->bfs_smem, ctx->cur_stream>>>(ctx->ix, ctx->d_recs.as<NodeRec>(), bv, ctx->pool,
-                                                                                         *ctx->cur_sc, (int)q0, qb, cap);
+                                                                                         *ctx->cur_sc, (int)q0, qb, cap, 1);
                 else
                     lineage_bfs_kernel<kBfsThreadsDefault><<<qb, kBfsThreadsDefault, ctx->bfs_smem, ctx->cur_stream>>>(
-                        ctx->ix, ctx->d_recs.as<NodeRec>(), bv, ctx->pool, *ctx->cur_sc, (int)q0, qb, cap);
+                        ctx->ix, ctx->d_recs.as<NodeRec>(), bv, ctx->pool, *ctx->cur_sc, (int)q0, qb, cap, ctx->walk_variant == 3 ? 0 : 1);
                 CU(cudaGetLastError());
             }
             lineage_walk_kernel<false><<<(qb + kWalkWarps - 1) / kWalkWarps, kWalkWarps * 32, ctx->walk_smem, ctx->cur_stream>>>(
