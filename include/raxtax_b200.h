@@ -63,7 +63,8 @@ typedef enum {
                                        hit the L1; 0 or 1 = no lockstep (default, fastest measured) */
     RTX_OPT_WALK_VARIANT = 9,       /* tree walk: 0 = level-synchronous kernel + depth-first retry of overflowing queries (default),
                                        1 = depth-first walker only, 2 = level-synchronous with 128-thread CTAs, 3 = level-synchronous
-                                       without the sparse expansion of large frontiers (every child of a frontier node is evaluated) */
+                                       without the large-frontier paths (every child of a frontier node is evaluated), 4 = test hook:
+                                       those paths (mass-pruned search, arg-max over the kept segments) forced on every frontier */
     RTX_OPT_PIPELINE = 11,          /* 1: batches of >= 4096 queries are cut into >= 4 sub-batches and hit counting of sub-batch i+1 overlaps
                                        probabilities / prefix sums / tree walk of sub-batch i on a second, higher-priority stream;
                                        0 (default) = serial: on B200 the overlap only recovers what the shorter launches lose */

@@ -2017,6 +2017,7 @@ struct BfsSmem {
     u16* pair_own;             // [P] frontier position of the pair's node
     u16* pj0;                  // [F] first kept segment under a frontier node
     u16* q_own;                // [2][kBfsQueue] frontier position of the run's node
+    u16* ent_sj;               // [E] sharded walk: 1 + straddler index of the node, 0 = it lies inside this shard
     u8* ent_k;                 // [E]
     u8* ent_depth;             // [E]
     u8* ent_any;               // [E]
@@ -2024,7 +2025,7 @@ struct BfsSmem {
     static constexpr u32 E = kBfsEntries, F = kBfsFrontier, R = RTX_MAX_RESULTS_PER_QUERY, P = kBfsPairs;
     __host__ __device__ static size_t bytes(u32 ML) {
         size_t b = (size_t)F * 8 + (size_t)R * 8 + (size_t)E * 16 + (size_t)(P + 1) * 4 + (size_t)F * 4 + (size_t)P * 8 + (size_t)(F + 1) * 4 +
-                   (size_t)kBfsKept * 4 + (size_t)kBfsQueue * 20 + (size_t)E * 2 + (size_t)F * 4 + (size_t)R * 4 + (size_t)P * 2 + (size_t)F * 2 + (size_t)E * 3 +
+                   (size_t)kBfsKept * 4 + (size_t)kBfsQueue * 20 + (size_t)E * 4 + (size_t)F * 4 + (size_t)R * 4 + (size_t)P * 2 + (size_t)F * 2 + (size_t)E * 3 +
                    (size_t)R * ML;
         return (b + 64 + 15) & ~(size_t)15;
     }
@@ -2051,7 +2052,8 @@ struct BfsSmem {
         pair_own = order + R;
         pj0 = pair_own + P;
         q_own = pj0 + F;
-        ent_k = reinterpret_cast<u8*>(q_own + 2 * kBfsQueue);
+        ent_sj = q_own + 2 * kBfsQueue;
+        ent_k = reinterpret_cast<u8*>(ent_sj + E);
         ent_depth = ent_k + E;
         ent_any = ent_depth + E;
         res_k = ent_any + E;
@@ -2059,12 +2061,14 @@ struct BfsSmem {
 };
 
 // warp 0: exclusive prefix of the child counts of `n` log entries (given by index list or by a contiguous range) -> fr_off[0..n]
-__device__ __forceinline__ void bfs_child_offsets(const BfsSmem& w, u32 n, u32 range_begin, const u16* __restrict__ list, int lane) {
+// (skip_strad: entries of straddling nodes count no children -- fallback rounds of the sharded walk)
+__device__ __forceinline__ void bfs_child_offsets(const BfsSmem& w, u32 n, u32 range_begin, const u16* __restrict__ list, int lane,
+                                                  bool skip_strad = false) {
     u32 running = 0;
     for (u32 bb = 0; bb < n; bb += 32) {
         const u32 i = bb + lane;
         const u32 e = (i < n) ? (list ? (u32)list[i] : range_begin + i) : 0u;
-        const u32 c = (i < n) ? (w.ent_cc[e] & 0x3FFFFFFFu) : 0u;
+        const u32 c = (i < n && !(skip_strad && w.ent_sj[e])) ? (w.ent_cc[e] & 0x3FFFFFFFu) : 0u;
         const u32 inc = warp_scan_incl(c, lane);
         if (i < n) w.fr_off[i] = running + inc - c;
         running += __shfl_sync(kFullMask, inc, 31);
@@ -2097,18 +2101,19 @@ __device__ __forceinline__ u32 bfs_lower_bound(const u32* __restrict__ a, u32 n,
 // under it) with the run of the node's children that overlaps the segment -> pair_own / pair_a, fr_off[0..P] = offsets of the runs in
 // the flattened child list.  Runs of one node are clipped against their predecessor, so no child appears twice.  Children are sorted
 // and disjoint (tree.rs:77-107), their [lo, lo + size) are read from the node records.  Block-wide (four barriers); returns P.
+// (shard_begin: first reference of this shard -- segments count local references; skip_strad as in bfs_child_offsets)
 template <int kBfsThreads>
 __device__ u32 bfs_build_pairs(const BfsSmem& w, const NodeRec* __restrict__ recs, u32 n, u32 range_begin, const u16* __restrict__ list,
-                               u32 n_kept, int tid) {
+                               u32 n_kept, int tid, u32 shard_begin, bool skip_strad, u32 small_node) {
     const int lane = tid & 31, warp = tid >> 5;
     for (u32 i = tid; i < n; i += kBfsThreads) {
         const u32 e = list ? (u32)list[i] : range_begin + i;
-        const u32 cc = w.ent_cc[e] & 0x3FFFFFFFu;
-        const u32 lo = w.ent_lo[e], hi = lo + w.ent_size[e];
+        const u32 cc = (skip_strad && w.ent_sj[e]) ? 0u : (w.ent_cc[e] & 0x3FFFFFFFu);
+        const u32 lo = w.ent_lo[e] - shard_begin, hi = lo + w.ent_size[e];  // (nodes inside the shard)
         const u32 j0 = bfs_lower_bound(w.kept, n_kept, lo / kPrefixSeg);
         const u32 j1 = bfs_lower_bound(w.kept, n_kept, (hi + kPrefixSeg - 1) / kPrefixSeg);
         u32 np = (cc == 0 || j1 <= j0) ? 0u : j1 - j0;
-        if (cc <= kBfsSmallNode) np = min(np, 1u);
+        if (cc <= small_node) np = min(np, 1u);
         w.pj0[i] = (u16)j0;
         w.besti[i] = np;  // (the fallback rounds initialise besti behind this call)
     }
@@ -2132,12 +2137,12 @@ __device__ u32 bfs_build_pairs(const BfsSmem& w, const NodeRec* __restrict__ rec
         const u32 e = list ? (u32)list[i] : range_begin + i;
         const u32 cf = w.ent_cf[e], cc = w.ent_cc[e] & 0x3FFFFFFFu;
         u32 val;
-        if (cc <= kBfsSmallNode) {
+        if (cc <= small_node) {
             val = upper ? cc : 0u;
         } else {
             const u32 seg = w.kept[(u32)w.pj0[i] + (p - w.pbase[i])];
             // lower: first child that ends behind the segment's first reference; upper: first child that starts behind its last one
-            const u64 key = upper ? ((u64)seg + 1u) * kPrefixSeg : (u64)seg * kPrefixSeg;
+            const u64 key = (u64)shard_begin + (upper ? ((u64)seg + 1u) * kPrefixSeg : (u64)seg * kPrefixSeg);
             u32 lo = 0, hi = cc;
             while (lo < hi) {
                 const u32 mid = (lo + hi) >> 1;
@@ -2194,40 +2199,91 @@ __device__ __forceinline__ double bfs_child_prefix(const NodeRec* __restrict__ r
 }
 
 // Mass-pruned search for the child runs of `n` frontier nodes (log entries range_begin ..) that can hold a significant child ->
-// pair_own / pair_a, fr_off[0..P].  ctr: three shared counters (pairs, runs of this round, runs of the next).  Block-wide; returns P,
-// or ~0u when a list overflowed (the caller hands the query to the depth-first walker).
-template <int kBfsThreads>
+// pair_own / pair_a, fr_off[0..P].  ctr: four shared counters (pairs, runs of this round, runs of the next, overflow).  Block-wide;
+// returns P, or ~0u when a list overflowed (the caller hands the query to the depth-first walker).
+// SH (reference-sharded walk): the prefixes only know this shard's references.  Of a large node's children those that touch the shard
+// [sh_lo, sh_hi) are found by binary search; the first and the last of them may straddle a cut (their confidence comes from the
+// combined records) and are always looked at, the ones in between lie inside the shard and are searched by mass.
+template <int kBfsThreads, bool SH>
 __device__ u32 bfs_search_pairs(const BfsSmem& w, const NodeRec* __restrict__ recs, const double* __restrict__ preb, const double* __restrict__ segoff,
-                                const u32* __restrict__ skipw, u32 n, u32 range_begin, u32* ctr, int tid) {
+                                const u32* __restrict__ skipw, u32 n, u32 range_begin, u32* ctr, int tid, u64 sh_lo, u64 sh_hi, u32 leaf_len) {
     constexpr int kBfsWarps = kBfsThreads / 32;
     const int lane = tid & 31, warp = tid >> 5;
     const u32 lt_mask = (1u << lane) - 1u;
-    if (tid < 4) ctr[tid] = 0u;  // [3]: overflow
+    if (tid < 4) ctr[tid] = 0u;
     __syncthreads();
     for (u32 bb = 0; bb < n; bb += kBfsThreads) {  // small nodes are one pair each, the others start as one run
         const u32 i = bb + tid;
         const u32 cc = (i < n) ? (w.ent_cc[range_begin + i] & 0x3FFFFFFFu) : 0u;
-        const bool small = cc != 0 && cc <= kBfsLeaf, big = cc > kBfsLeaf;
-        const u32 ms = __ballot_sync(kFullMask, small), mb = __ballot_sync(kFullMask, big);
-        u32 ps = 0, pb = 0;
+        u32 np = 0, nq = 0, pa[2] = {0u, 0u}, pb[2] = {0u, 0u}, qa = 0, qb = 0;
+        if (cc != 0 && cc <= leaf_len) {
+            np = 1;
+            pb[0] = cc;
+        } else if (cc != 0) {
+            u32 ta = 0, tb = cc;
+            if (SH) {
+                const u32 cf = w.ent_cf[range_begin + i];
+                u32 lo = 0, hi = cc;
+                while (lo < hi) {  // first child that ends behind the shard's first reference
+                    const u32 mid = (lo + hi) >> 1;
+                    const uint2 ls = *reinterpret_cast<const uint2*>(&recs[cf + mid].lo);
+                    if ((u64)ls.x + ls.y > sh_lo) hi = mid;
+                    else lo = mid + 1;
+                }
+                ta = lo;
+                hi = cc;
+                while (lo < hi) {  // first child that starts behind its last one
+                    const u32 mid = (lo + hi) >> 1;
+                    const uint2 ls = *reinterpret_cast<const uint2*>(&recs[cf + mid].lo);
+                    if ((u64)ls.x >= sh_hi) hi = mid;
+                    else lo = mid + 1;
+                }
+                tb = lo;
+            }
+            if (tb > ta && (tb - ta <= leaf_len)) {
+                np = 1;
+                pa[0] = ta;
+                pb[0] = tb;
+            } else if (tb > ta) {
+                if (SH) {
+                    np = 2;
+                    pa[0] = ta;
+                    pb[0] = ta + 1;
+                    pa[1] = tb - 1;
+                    pb[1] = tb;
+                    ++ta;
+                    --tb;
+                }
+                nq = 1;
+                qa = ta;
+                qb = tb;
+            }
+        }
+        const u32 pinc = warp_scan_incl(np, lane);
+        const u32 ptot = __shfl_sync(kFullMask, pinc, 31);
+        const u32 mb = __ballot_sync(kFullMask, nq != 0);
+        u32 ps = 0, pq = 0;
         if (lane == 0) {
-            if (ms) ps = atomicAdd(&ctr[0], (u32)__popc(ms));
-            if (mb) pb = atomicAdd(&ctr[1], (u32)__popc(mb));
+            if (ptot) ps = atomicAdd(&ctr[0], ptot);
+            if (mb) pq = atomicAdd(&ctr[1], (u32)__popc(mb));
         }
         ps = __shfl_sync(kFullMask, ps, 0);
-        pb = __shfl_sync(kFullMask, pb, 0);
-        if (ps + __popc(ms) > kBfsPairs || pb + __popc(mb) > kBfsQueue) {
+        pq = __shfl_sync(kFullMask, pq, 0);
+        if (ps + ptot > kBfsPairs || pq + __popc(mb) > kBfsQueue) {
             if (lane == 0) ctr[3] = 1u;
-        } else if (small) {
-            const u32 pos = ps + __popc(ms & lt_mask);
-            w.pair_own[pos] = (u16)i;
-            w.pair_a[pos] = 0u;
-            w.pair_b[pos] = cc;
-        } else if (big) {
-            const u32 pos = pb + __popc(mb & lt_mask);
-            w.q_own[pos] = (u16)i;
-            w.q_a[pos] = 0u;
-            w.q_b[pos] = cc;
+        } else {
+            const u32 pos = ps + pinc - np;
+            for (u32 k = 0; k < np; ++k) {
+                w.pair_own[pos + k] = (u16)i;
+                w.pair_a[pos + k] = pa[k];
+                w.pair_b[pos + k] = pb[k];
+            }
+            if (nq) {
+                const u32 qp = pq + __popc(mb & lt_mask);
+                w.q_own[qp] = (u16)i;
+                w.q_a[qp] = qa;
+                w.q_b[qp] = qb;
+            }
         }
     }
     __syncthreads();
@@ -2246,7 +2302,7 @@ __device__ u32 bfs_search_pairs(const BfsSmem& w, const NodeRec* __restrict__ re
             double v1 = __shfl_down_sync(kFullMask, v0, 1);
             if (lane == 31) v1 = bfs_child_prefix(recs, cf, cc, sb, preb, segoff, skipw);
             const bool keep = sa < sb && (v1 - v0) >= kBfsMassFloor;
-            const bool leaf = keep && sb - sa <= kBfsLeaf, more = keep && !leaf;
+            const bool leaf = keep && sb - sa <= leaf_len, more = keep && !leaf;
             const u32 ml = __ballot_sync(kFullMask, leaf), mm = __ballot_sync(kFullMask, more);
             u32 pl = 0, pm = 0;
             if (lane == 0) {
@@ -2291,10 +2347,14 @@ __device__ u32 bfs_search_pairs(const BfsSmem& w, const NodeRec* __restrict__ re
     return P;
 }
 
-template <int kBfsThreads>
+// SH: the reference-sharded walk (see lineage_walk_kernel<true> for the rules): a child that straddles a shard cut takes its confidence
+// from the combined records, a child inside another shard is left to its owner; a straddling node learns from the combined flags whether
+// it has a significant child / whether a line is pushed below it, and is reported by the rank that holds its first reference; a fallback
+// chain follows the combined best child through straddling nodes and ends where it leaves the shard.
+template <int kBfsThreads, bool SH>
 __global__ void __launch_bounds__(kBfsThreads)  // (a 6-CTA/SM bound, 40 registers with small spills, measured the same 0.89 ms)
-    lineage_bfs_kernel(IndexView ix, const NodeRec* __restrict__ recs, BatchView b, ResultPool pool, ProbScratch sc, int q_base, int q_count,
-                       u32 entry_cap, int sparse) {
+    lineage_bfs_kernel(IndexView ix, const NodeRec* __restrict__ recs, BatchView b, ResultPool pool, ProbScratch sc, ShardView sv, int q_base,
+                       int q_count, u32 entry_cap, int sparse) {
     constexpr int kBfsWarps = kBfsThreads / 32;
     extern __shared__ __align__(16) unsigned char bsm_raw[];
     __shared__ u32 s_log_n, s_n_res, s_n_fb, s_n_next, s_retry, s_retry_cls;  // s_retry_cls: raised while sorting a frontier (see the level loop)
@@ -2313,12 +2373,19 @@ __global__ void __launch_bounds__(kBfsThreads)  // (a 6-CTA/SM bound, 40 registe
     const double* __restrict__ segoff = sc.segoff + (size_t)ql * sc.segoff_stride;
     const u32* __restrict__ skipw = seg_aux(sc, ql) + 2;
     const u32 lt_mask = (1u << lane) - 1u;
+    const u64 sh_lo = ix.shard_begin, sh_hi = ix.shard_begin + ix.shard_refs;
+    auto inside = [&](const NodeRec& r) { return (u64)r.lo >= sh_lo && (u64)r.lo + r.size <= sh_hi; };
+    auto owned = [&](u32 lo) { return (u64)lo >= sh_lo && (u64)lo < sh_hi; };  // this rank reports a straddling node that starts here
+    const size_t srow = SH ? (size_t)ql * sv.n_strad : 0;
+    // sparse == 2 (test hook): the large-frontier paths run on every frontier, with runs of two children
+    const u32 pair_min = sparse == 2 ? 0u : kBfsPairMin, leaf_len = sparse == 2 ? 2u : kBfsLeaf, small_node = sparse == 2 ? 2u : kBfsSmallNode;
     int status = pool.status[q];
 
     u32 n_res = 0;
     if (status == kQOk) {  // block-uniform
         if (tid == 0) {
             const NodeRec root = recs[0];
+            w.ent_sj[0] = SH ? (u16)(sv.strad_of_node[0] + 1) : (u16)0;
             w.ent_cf[0] = root.child_first;
             w.ent_cc[0] = root.cc_type;
             w.ent_lo[0] = root.lo;
@@ -2386,10 +2453,17 @@ __global__ void __launch_bounds__(kBfsThreads)  // (a 6-CTA/SM bound, 40 registe
                 const u32 i = bb + tid;
                 bool is_res = false, is_fb = false;
                 const u32 e = prev_begin + i;
-                if (i < pn && !w.ent_any[e]) {
+                if (i < pn) {
+                    bool any_sig = w.ent_any[e] != 0, pushed = any_sig, mine = true;
+                    if (SH && w.ent_sj[e]) {
+                        const u32 sa = sv.sany[srow + w.ent_sj[e] - 1u];
+                        any_sig = any_sig || (sa & 1u);
+                        pushed = pushed || (sa & 2u);
+                        mine = owned(w.ent_lo[e]);
+                    }
                     const u32 type = w.ent_cc[e] >> 30;
-                    is_fb = type == 0;
-                    is_res = type == 1 && e != 0;  // the root never reports itself
+                    is_fb = type == 0 && !any_sig;
+                    is_res = type == 1 && e != 0 && !pushed && mine;  // the root never reports itself
                 }
                 const u32 mr = __ballot_sync(kFullMask, is_res), mf = __ballot_sync(kFullMask, is_fb);
                 u32 pr = 0, pf = 0;
@@ -2409,9 +2483,9 @@ __global__ void __launch_bounds__(kBfsThreads)  // (a 6-CTA/SM bound, 40 registe
             __syncthreads();
             if (!have || s_retry_cls) break;
             u32 total = w.fr_off[nf], n_own = nf;
-            const bool pairs = sparse != 0 && total >= kBfsPairMin;  // block-uniform
+            const bool pairs = sparse != 0 && total >= pair_min;  // block-uniform
             if (pairs) {
-                n_own = bfs_search_pairs<kBfsThreads>(w, recs, preb, segoff, skipw, nf, lvl_begin, s_ctr, tid);
+                n_own = bfs_search_pairs<kBfsThreads, SH>(w, recs, preb, segoff, skipw, nf, lvl_begin, s_ctr, tid, sh_lo, sh_hi, leaf_len);
                 if (n_own == ~0u) {  // (every thread sees the same return value)
                     if (tid == 0) s_retry = 1;
                     break;
@@ -2420,22 +2494,31 @@ __global__ void __launch_bounds__(kBfsThreads)  // (a 6-CTA/SM bound, 40 registe
             }
             for (u32 base = (u32)warp * 64; base < total; base += kBfsWarps * 64) {  // two chunks of 32 children in flight per warp
                 u32 kk[2], ee[2];
+                int sj[2];
                 NodeRec cr[2];
 #pragma unroll
                 for (int u = 0; u < 2; ++u) {
                     const u32 idx = base + u * 32 + lane;
                     ee[u] = 0;
+                    sj[u] = -1;
                     cr[u] = NodeRec{0, 0, 0, 0, 0, 0, 0, 0};
                     if (idx < total) {
                         const u32 o = bfs_owner(w.fr_off, n_own, idx);
                         ee[u] = lvl_begin + (pairs ? (u32)w.pair_own[o] : o);
-                        cr[u] = recs[w.ent_cf[ee[u]] + (pairs ? w.pair_a[o] : 0u) + (idx - w.fr_off[o])];
+                        const u32 cn = w.ent_cf[ee[u]] + (pairs ? w.pair_a[o] : 0u) + (idx - w.fr_off[o]);
+                        cr[u] = recs[cn];
+                        if (SH) sj[u] = sv.strad_of_node[cn];
                     }
                 }
 #pragma unroll
                 for (int u = 0; u < 2; ++u) {
                     const u32 idx = base + u * 32 + lane;
-                    kk[u] = (idx < total) ? (u32)round(node_conf(preb, segoff, skipw, cr[u]) * 100.0) : 0u;  // f64::round (lineage.rs:129)
+                    kk[u] = 0u;
+                    if (idx < total) {
+                        if (SH && sj[u] >= 0) kk[u] = sv.sk[srow + sj[u]];  // combined over the ranks
+                        else if (!SH || inside(cr[u])) kk[u] = (u32)round(node_conf(preb, segoff, skipw, cr[u]) * 100.0);  // f64::round (lineage.rs:129)
+                        // children inside another shard are walked by their owner
+                    }
                 }
 #pragma unroll
                 for (int u = 0; u < 2; ++u) {
@@ -2457,6 +2540,7 @@ __global__ void __launch_bounds__(kBfsThreads)  // (a 6-CTA/SM bound, 40 registe
                             w.ent_depth[pos] = (u8)(w.ent_depth[ee[u]] + 1);
                             w.ent_any[pos] = 0;
                             w.ent_any[ee[u]] = 1;
+                            w.ent_sj[pos] = (u16)(sj[u] + 1);
                             // a significant Sequence node (it has children, or it would not be in the tree) may push nothing, and
                             // its Taxon parent is then reported after all (lineage.rs:143-149): the depth-first walker tracks that
                             if ((cr[u].cc_type >> 30) == 2u) s_retry = 1;
@@ -2495,13 +2579,13 @@ __global__ void __launch_bounds__(kBfsThreads)  // (a 6-CTA/SM bound, 40 registe
         tr_fb_heads = n_ch;
 #endif
         while (n_ch > 0) {  // block-uniform
-            if (warp == 0) bfs_child_offsets(w, n_ch, 0, cur, lane);
+            if (warp == 0) bfs_child_offsets(w, n_ch, 0, cur, lane, SH);
             if (tid == 0) s_n_next = 0;
             __syncthreads();
             u32 total = w.fr_off[n_ch], n_own = n_ch;
-            const bool pairs = n_kept != 0 && total >= kBfsPairMin;  // block-uniform
+            const bool pairs = n_kept != 0 && total >= pair_min;  // block-uniform
             if (pairs) {
-                n_own = bfs_build_pairs<kBfsThreads>(w, recs, n_ch, 0, cur, n_kept, tid);
+                n_own = bfs_build_pairs<kBfsThreads>(w, recs, n_ch, 0, cur, n_kept, tid, (u32)sh_lo, SH, small_node);
                 total = w.fr_off[n_own];
             }
             for (u32 i = tid; i < n_ch; i += kBfsThreads) {
@@ -2571,7 +2655,11 @@ __global__ void __launch_bounds__(kBfsThreads)  // (a 6-CTA/SM bound, 40 registe
                 const u32 head = cur[i];
                 const u32 hcc = w.ent_cc[head] & 0x3FFFFFFFu;
                 const double bestv = __longlong_as_double((long long)w.best[i]);
-                if (w.best[i] == 0ull || w.besti[i] == 0u) {
+                if (SH && w.ent_sj[head]) {
+                    // the best child of a straddling node was decided from all ranks' records
+                    const u32 bn = sv.sbest[srow + w.ent_sj[head] - 1u];
+                    w.besti[i] = bn >= w.ent_cf[head] ? bn - w.ent_cf[head] + 1u : 1u;
+                } else if (w.best[i] == 0ull || w.besti[i] == 0u) {
                     // no child above 0: all of them tie and the last one wins (the children outside the kept segments, which the
                     // sparse expansion does not look at, are exactly 0 as well)
                     w.besti[i] = hcc;
@@ -2600,17 +2688,26 @@ __global__ void __launch_bounds__(kBfsThreads)  // (a 6-CTA/SM bound, 40 registe
             }
             for (u32 bb = 0; bb < n_ch; bb += kBfsThreads) {  // one new log entry (0.01) per chain; Inner nodes stay active
                 const u32 i = bb + tid;
-                const bool valid = i < n_ch;
                 NodeRec br = NodeRec{0, 0, 0, 0, 0, 0, 0, 0};
                 u32 head = 0;
-                if (valid) {
+                int bsj = -1;
+                bool here = true, mine = true;  // sharded: does the chain go on / end on this rank?
+                if (i < n_ch) {
                     head = cur[i];
                     const u32 b1 = w.besti[i] & 0x7FFFFFFFu;  // 1 + index of the chosen child
                     w.besti[i] = b1 ? b1 - 1u : 0u;
-                    br = recs[w.ent_cf[head] + w.besti[i]];
+                    const u32 bn = w.ent_cf[head] + w.besti[i];
+                    br = recs[bn];
+                    if (SH) {
+                        bsj = sv.strad_of_node[bn];
+                        here = bsj >= 0 || inside(br);  // else the chain continues in another rank's shard
+                        mine = bsj >= 0 ? owned(br.lo) : here;
+                    }
                 }
-                const bool go_on = valid && (br.cc_type >> 30) == 0;
-                const bool done = valid && !go_on;
+                const bool is_inner = (br.cc_type >> 30) == 0;
+                const bool go_on = i < n_ch && is_inner && here;
+                const bool done = i < n_ch && !is_inner && mine;
+                const bool valid = go_on || done;
                 const u32 mv = __ballot_sync(kFullMask, valid), mg = __ballot_sync(kFullMask, go_on), md = __ballot_sync(kFullMask, done);
                 u32 pv = 0, pg = 0, pd = 0;
                 if (lane == 0) {
@@ -2633,6 +2730,7 @@ __global__ void __launch_bounds__(kBfsThreads)  // (a 6-CTA/SM bound, 40 registe
                     w.ent_k[pos] = 1;  // 1.0 / rounding_factor
                     w.ent_depth[pos] = (u8)(w.ent_depth[head] + 1);
                     w.ent_any[pos] = 0;
+                    w.ent_sj[pos] = (u16)(bsj + 1);
                     if (go_on) nxt[pg + __popc(mg & lt_mask)] = (u16)pos;
                     else w.res_ent[pd + __popc(md & lt_mask)] = (u16)pos;
                 }
@@ -2689,7 +2787,7 @@ __global__ void __launch_bounds__(kBfsThreads)  // (a 6-CTA/SM bound, 40 registe
             if (lane == 0) w.res_local[r] = sqrt(s2);
         }
         if (__syncthreads_or(too_deep ? 1 : 0) || retry) status = kQWalkRetry;
-        else if (n_res == 0) status = kQEmptyResult;  // assert!(!eval_res.is_empty()) raxtax.rs:72
+        else if (n_res == 0 && !SH) status = kQEmptyResult;  // assert!(!eval_res.is_empty()) raxtax.rs:72 (sharded: checked after the merge)
     }
     if (status == kQWalkRetry) {  // lineage_walk_kernel<false> redoes this query
         if (tid == 0) pool.status[q] = status;
@@ -2724,8 +2822,8 @@ __global__ void __launch_bounds__(kBfsThreads)  // (a 6-CTA/SM bound, 40 registe
     u32 n_out = (status == kQOk) ? n_res : 0;
     bool ovr = false;
     u32 ovr_idx = 0;
-    if (status == kQOk && !(b.flags & RTX_RAW_CONFIDENCE) && !(b.flags & RTX_SKIP_EXACT_MATCHES) && b.exact_off) {
-        if (b.exact_off[q + 1] - b.exact_off[q] == 1) {
+    if (!SH && status == kQOk && !(b.flags & RTX_RAW_CONFIDENCE) && !(b.flags & RTX_SKIP_EXACT_MATCHES) && b.exact_off) {
+        if (b.exact_off[q + 1] - b.exact_off[q] == 1) {  // sharded: the caller applies the override after merging the ranks
             ovr = true;
             ovr_idx = b.exact_ids[b.exact_off[q]];
             n_out = 1;

@@ -374,7 +374,7 @@ RTX_API int rtx_ctx_set_option(rtx_ctx* ctx, int option, int64_t value) {
             ctx->pipeline_opt = value != 0;
             return RTX_OK;
         case RTX_OPT_WALK_VARIANT:
-            REQUIRE(value >= 0 && value <= 3, "unknown walk variant");  // 2: level-synchronous walk with 128-thread CTAs, 3: without the sparse expansion
+            REQUIRE(value >= 0 && value <= 4, "unknown walk variant");  // 2: 128-thread CTAs, 3: without the large-frontier paths, 4: with them forced
             ctx->walk_variant = (int)value;
             return RTX_OK;
         case RTX_OPT_WALK_LOG_CAP:
@@ -830,8 +830,9 @@ static int bind_scratch(rtx_ctx* ctx) {
     CU(cudaFuncSetAttribute(prefix_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->prefix_smem));
     CU(cudaFuncSetAttribute(lineage_walk_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->walk_smem));
     CU(cudaFuncSetAttribute(lineage_walk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->walk_smem));
-    CU(cudaFuncSetAttribute(lineage_bfs_kernel<kBfsThreadsDefault>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->bfs_smem));
-    CU(cudaFuncSetAttribute(lineage_bfs_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->bfs_smem));
+    CU(cudaFuncSetAttribute(lineage_bfs_kernel<kBfsThreadsDefault, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->bfs_smem));
+    CU(cudaFuncSetAttribute(lineage_bfs_kernel<kBfsThreadsDefault, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->bfs_smem));
+    CU(cudaFuncSetAttribute(lineage_bfs_kernel<128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->bfs_smem));
     ctx->cur_stream = ctx->stream;
     ctx->cur_counts = ctx->d_counts.as<u16>();
     ctx->cur_sc = &ctx->sc;
@@ -1234,6 +1235,23 @@ static int begin_run(rtx_ctx* ctx) {
     return RTX_OK;
 }
 
+// tree walk of one shard's part of the tree: the level-synchronous kernel, then the depth-first walker for the queries it handed back
+// (RTX_OPT_WALK_VARIANT 1: depth-first walker only, as in round 1)
+static int launch_shard_walk(rtx_ctx* ctx, const ShardView& sv, const ProbScratch& sc, int q0, int qb, cudaStream_t st) {
+    LaunchTimer lt(ctx, RTX_K_WALK);
+    const bool bfs = ctx->walk_variant != 1;
+    if (bfs) {
+        const u32 cap = ctx->walk_log_cap ? (u32)ctx->walk_log_cap : kBfsEntries;
+        lineage_bfs_kernel<kBfsThreadsDefault, true><<<qb, kBfsThreadsDefault, ctx->bfs_smem, st>>>(
+            ctx->ix, ctx->d_recs.as<NodeRec>(), ctx->bv, ctx->pool, sc, sv, q0, qb, cap, ctx->walk_variant == 3 ? 0 : ctx->walk_variant == 4 ? 2 : 1);
+        CU(cudaGetLastError());
+    }
+    lineage_walk_kernel<true><<<(qb + kWalkWarps - 1) / kWalkWarps, kWalkWarps * 32, ctx->walk_smem, st>>>(
+        ctx->ix, ctx->d_recs.as<NodeRec>(), ctx->bv, ctx->pool, sc, sv, q0, qb, bfs ? 1 : 0);
+    CU(cudaGetLastError());
+    return RTX_OK;
+}
+
 static int run_all(rtx_ctx* ctx) {
     BatchView& bv = ctx->bv;
     const u32 nq = bv.n_queries;
@@ -1289,11 +1307,12 @@ static int run_all(rtx_ctx* ctx) {
             if (ctx->walk_variant != 1) {  // level-synchronous walk, then the depth-first walker for the queries it handed back
                 const u32 cap = ctx->walk_log_cap ? (u32)ctx->walk_log_cap : kBfsEntries;
                 if (ctx->walk_variant == 2)
-                    lineage_bfs_kernel<128><<<qb, 128, ctx->bfs_smem, ctx->cur_stream>>>(ctx->ix, ctx->d_recs.as<NodeRec>(), bv, ctx->pool,
-                                                                                         *ctx->cur_sc, (int)q0, qb, cap, 1);
+                    lineage_bfs_kernel<128, false><<<qb, 128, ctx->bfs_smem, ctx->cur_stream>>>(ctx->ix, ctx->d_recs.as<NodeRec>(), bv, ctx->pool,
+                                                                                                *ctx->cur_sc, ShardView{}, (int)q0, qb, cap, 1);
                 else
-                    lineage_bfs_kernel<kBfsThreadsDefault><<<qb, kBfsThreadsDefault, ctx->bfs_smem, ctx->cur_stream>>>(
-                        ctx->ix, ctx->d_recs.as<NodeRec>(), bv, ctx->pool, *ctx->cur_sc, (int)q0, qb, cap, ctx->walk_variant == 3 ? 0 : 1);
+                    lineage_bfs_kernel<kBfsThreadsDefault, false><<<qb, kBfsThreadsDefault, ctx->bfs_smem, ctx->cur_stream>>>(
+                        ctx->ix, ctx->d_recs.as<NodeRec>(), bv, ctx->pool, *ctx->cur_sc, ShardView{}, (int)q0, qb, cap,
+                        ctx->walk_variant == 3 ? 0 : ctx->walk_variant == 4 ? 2 : 1);
                 CU(cudaGetLastError());
             }
             lineage_walk_kernel<false><<<(qb + kWalkWarps - 1) / kWalkWarps, kWalkWarps * 32, ctx->walk_smem, ctx->cur_stream>>>(
@@ -1578,12 +1597,8 @@ RTX_API int rtx_shard_phase3(rtx_ctx* ctx) {
         shard_combine_kernel<<<(nq + 127) / 128, 128, 0, ctx->stream>>>(ctx->sv, ctx->d_recs.as<NodeRec>(), (int)nq);
         CU(cudaGetLastError());
     }
-    {
-        LaunchTimer lt(ctx, RTX_K_WALK);
-        lineage_walk_kernel<true><<<(nq + kWalkWarps - 1) / kWalkWarps, kWalkWarps * 32, ctx->walk_smem, ctx->stream>>>(
-            ctx->ix, ctx->d_recs.as<NodeRec>(), bv, ctx->pool, ctx->sc, ctx->sv, 0, (int)nq, 0);
-        CU(cudaGetLastError());
-    }
+    rc = launch_shard_walk(ctx, ctx->sv, ctx->sc, 0, (int)nq, ctx->stream);
+    if (rc) return rc;
     ctx->cur_stream = ctx->stream;
     rc = order_results(ctx);
     if (rc) return rc;
@@ -1819,12 +1834,8 @@ RTX_API int rtx_shard_run(rtx_ctx* ctx) {
                 CU(cudaGetLastError());
             }
         }
-        {
-            LaunchTimer lt(ctx, RTX_K_WALK);
-            lineage_walk_kernel<true><<<(qb + kWalkWarps - 1) / kWalkWarps, kWalkWarps * 32, ctx->walk_smem, st>>>(
-                ctx->ix, ctx->d_recs.as<NodeRec>(), bv, ctx->pool, *ctx->cur_sc, sv, (int)q0, qb, 0);
-            CU(cudaGetLastError());
-        }
+        rc = launch_shard_walk(ctx, sv, *ctx->cur_sc, (int)q0, qb, st);
+        if (rc) return rc;
         if (pipe) CU(cudaEventRecord(ctx->ev_post[slot], ctx->stream2));
     }
     if (pipe) {

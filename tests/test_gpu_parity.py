@@ -614,7 +614,7 @@ def test_random_shapes_walk_variants_and_shards(oracle, ctx, seed):
     ctx.upload_tree(ht)
     outs = []
     try:
-        for variant, cap in ((0, 0), (1, 0), (0, 4)):
+        for variant, cap in ((0, 0), (1, 0), (0, 4), (3, 0), (4, 0)):  # 3 / 4: large-frontier paths of the level-synchronous walk off / forced
             ctx.set_option(capi.RTX_OPT_WALK_VARIANT, variant)
             ctx.set_option(capi.RTX_OPT_WALK_LOG_CAP, cap)
             outs.append(ctx.classify(q_off, q_codes, eo, eids, skip_exact=skip))
@@ -633,6 +633,7 @@ def test_random_shapes_walk_variants_and_shards(oracle, ctx, seed):
     try:
         for r, c in enumerate(ctxs):
             c.upload_tree_sharded(ht, n_shards, r, cuts)
+            c.set_option(capi.RTX_OPT_WALK_VARIANT, (0, 4, 1)[seed % 3])  # sharded walk: default, large-frontier paths forced, depth-first only
         ref_levels = ht.index_arrays()["ref_levels"]
         merged, per_rank = rdist.classify_sharded_local(ctxs, q_off, q_codes, eo, eids, ref_levels, skip_exact=skip, taps=("counts",))
     finally:
@@ -692,9 +693,95 @@ def test_random_mid_size_against_oracle(oracle, ctx, seed):
     r_off, r_codes = _pack(oracle, refs)
     q_off, q_codes = _pack(oracle, queries)
     skip, variant = bool(seed & 1), (capi.RTX_HITCOUNT_CSR if seed % 5 == 4 else capi.RTX_HITCOUNT_BITROWS)
-    o, dev, ot, _ = _run_both(oracle, ctx, (lineages, r_off, r_codes, q_off, q_codes), skip=skip, sub_batch=int(seed % 4) * 7, variant=variant)
+    ctx.set_option(capi.RTX_OPT_WALK_VARIANT, 4 if seed % 3 == 1 else 0)  # every third case: the walk's large-frontier paths forced
+    try:
+        o, dev, ot, _ = _run_both(oracle, ctx, (lineages, r_off, r_codes, q_off, q_codes), skip=skip, sub_batch=int(seed % 4) * 7, variant=variant)
+    finally:
+        ctx.set_option(capi.RTX_OPT_WALK_VARIANT, 0)
     _assert_integer_parity(o, dev, len(queries))
     _assert_result_parity(o, dev, ot, len(queries), max_tolerated_frac=1.0)
+
+
+@pytest.mark.parametrize("n_shards,skip", [(1, False), (3, False), (4, True)])
+def test_giant_nodes_walk_paths(oracle, ctx, n_shards, skip):
+    """A taxonomy with giant nodes (one genus holding thousands of species, one family holding hundreds of genera), so that the
+    level-synchronous walk takes its large-frontier paths at their production thresholds -- mass-pruned search for significant
+    children, fallback arg-max over the kept segments / in one pass -- unsharded (against the dense expansion, the depth-first
+    walker and the oracle) and reference-sharded with cuts inside the giant nodes (against the oracle)."""
+    from raxtax_b200 import dist as rdist
+
+    rng = np.random.default_rng(77)
+    L = 120
+    root = synth.BASE_CODES[rng.integers(0, 4, L)]
+
+    def mutate(s, rate):
+        t = s.copy()
+        m = rng.random(L) < rate
+        t[m] = synth.BASE_CODES[rng.integers(0, 4, int(m.sum()))]
+        return t
+
+    lineages, refs = [], []
+    fam_seq = [mutate(root, 0.15) for _ in range(3)]
+    for f in range(3):
+        n_gen = (900, 3, 1)[f]
+        for g in range(n_gen):
+            gs = mutate(fam_seq[f], 0.08)
+            n_spe = 3000 if (f == 1 and g == 0) else (1200 if (f == 0 and g == 7) else int(rng.integers(1, 4)))
+            for sp in range(n_spe):
+                ss = mutate(gs, 0.05)
+                for _ in range(int(rng.integers(1, 3))):
+                    lineages.append(f"p:P,f:F{f},g:G{f}_{g},s:S{f}_{g}_{sp}")
+                    refs.append(mutate(ss, 0.01))
+    order = rng.permutation(len(refs))
+    lineages = [lineages[i] for i in order]
+    refs = [refs[i] for i in order]
+    queries = []
+    for _ in range(120):
+        r = rng.random()
+        base = refs[int(rng.integers(0, len(refs)))]
+        if r < 0.3:
+            queries.append(base.copy())
+        elif r < 0.6:
+            queries.append(mutate(base, 0.02))
+        elif r < 0.85:
+            queries.append(mutate(base, 0.25))  # flat profiles: fallback chains through the giant nodes
+        else:
+            queries.append(synth.BASE_CODES[rng.integers(0, 4, int(rng.integers(0, L)))])
+    r_off, r_codes = _pack(oracle, refs)
+    q_off, q_codes = _pack(oracle, queries)
+    ht = capi.Tree.new(lineages, r_off, r_codes)
+    eo, eids = ht.exact_batch(q_off, q_codes)
+    ot = oracle.Tree.new(lineages, [np.asarray(r, np.uint8) for r in refs])
+    o = ot.classify(q_off, q_codes, skip_exact=skip, threads=os.cpu_count() or 4, chunk_size=8, want_counts=True, want_probs=True)
+    if n_shards == 1:
+        ctx.upload_tree(ht)
+        outs = []
+        try:
+            for variant in (0, 3, 1, 4):
+                ctx.set_option(capi.RTX_OPT_WALK_VARIANT, variant)
+                outs.append(ctx.classify(q_off, q_codes, eo, eids, skip_exact=skip, taps=("counts",)))
+        finally:
+            ctx.set_option(capi.RTX_OPT_WALK_VARIANT, 0)
+        for o2 in outs[1:]:
+            assert _same_outputs(outs[0], o2)
+        assert np.array_equal(outs[0].counts, o["counts"])
+        _assert_result_parity(o, outs[0], ot, len(queries), max_tolerated_frac=1.0)
+        return
+    n = ht.num_tips
+    cuts = np.array([0] + [int(n * (i + 0.37) / n_shards) for i in range(n_shards - 1)] + [n], np.uint64)
+    ref_levels = ht.index_arrays()["ref_levels"]
+    for variant in (0, 1):
+        ctxs = [capi.Context(0) for _ in range(n_shards)]
+        try:
+            for r, c in enumerate(ctxs):
+                c.upload_tree_sharded(ht, n_shards, r, cuts)
+                c.set_option(capi.RTX_OPT_WALK_VARIANT, variant)
+            merged, per_rank = rdist.classify_sharded_local(ctxs, q_off, q_codes, eo, eids, ref_levels, skip_exact=skip, taps=("counts",))
+        finally:
+            for c in ctxs:
+                c.close()
+        assert np.array_equal(np.concatenate([x.counts for x in per_rank], axis=1), o["counts"])
+        _assert_result_parity(o, merged, ot, len(queries), max_tolerated_frac=1.0)
 
 
 def test_host_driver_dedups_identical_queries(ctx):
