@@ -1376,50 +1376,155 @@ __device__ bool seq_subtree_pushes(const NodeRec* __restrict__ recs, const doubl
     return false;
 }
 
-// one warp per (query, straddler)
+// One warp per (query, straddler): the straddler's probability mass inside this shard and, of its children that lie wholly inside the
+// shard, how many are significant / push a line and which one is the largest (last one within 1e-12 relative of the maximum, as in
+// lineage.rs:156-164; the ranks' records are combined by shard_combine_kernel).
+//   * Only the children that touch the shard are looked at (binary search over the sorted child ranges).
+//   * One pass: the last "record" (a child within the tolerance of the running maximum) is the answer if it passes the final test, see
+//     the fallback rounds of lineage_bfs_kernel; else the run is scanned again.
+//   * A query that kept few 512-reference segments under the straddler (K4's mass cut) only evaluates the children that overlap
+//     them; all others are exactly 0 -- they only matter when nothing is above 0, and then the last child wins.
+constexpr u32 kRecKept = 32;        // at most this many kept segments under a straddler for the sparse scan
+constexpr u32 kRecSparseMin = 128;  // children touching the shard, below which everything is evaluated
+
 __global__ void __launch_bounds__(128) shard_records_kernel(IndexView ix, const NodeRec* __restrict__ recs, ProbScratch sc, ShardView sv, int q_count) {
-    const int lane = threadIdx.x & 31;
+    __shared__ u32 s_kept[4][kRecKept];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (w >= (long long)q_count * sv.n_strad) return;
     const int ql = (int)(w / sv.n_strad), j = (int)(w % sv.n_strad);
     const double* __restrict__ preb = sc.preb + (size_t)ql * sc.preb_stride;
     const double* __restrict__ segoff = sc.segoff + (size_t)ql * sc.segoff_stride;
     const u32* __restrict__ skipw = seg_aux(sc, ql) + 2;
+    const u64 sh_lo = ix.shard_begin, sh_hi = ix.shard_begin + ix.shard_refs;
     const u32 node = sv.strad_nodes[j];
     const NodeRec nr = recs[node];
     const u32 cf = nr.child_first, cc = nr.cc_type & 0x3FFFFFFFu;
+    auto child_lo_size = [&](u32 ci) { return *reinterpret_cast<const uint2*>(&recs[cf + ci].lo); };
+    // children [ta, tb) touch the shard
+    u32 ta = 0, tb = cc;
+    if (cc > 32) {
+        ta = warp_first_true(0u, cc, lane, [&](u32 x) { const uint2 ls = child_lo_size(x); return (u64)ls.x + ls.y > sh_lo; });
+        tb = warp_first_true(ta, cc, lane, [&](u32 x) { return (u64)child_lo_size(x).x >= sh_hi; });
+    }
     double best = -CUDART_INF;
-    u32 n_sig = 0, n_push = 0;  // significant inside children; those of them below which a result line is pushed
-    for (u32 cb = 0; cb < cc; cb += 32) {
-        const u32 ci = cb + lane;
-        if (ci < cc && sv.strad_of_node[cf + ci] < 0 && node_inside(ix, cf + ci)) {
-            const NodeRec cr = recs[cf + ci];
-            const double v = node_conf(preb, segoff, skipw, cr);
-            best = fmax(best, v);
-            if ((u32)round(v * 100.0) != 0) {
-                ++n_sig;
-                n_push += ((cr.cc_type >> 30) != 2u) || seq_subtree_pushes(recs, preb, segoff, skipw, cr);
+    u32 n_sig = 0, n_push = 0;  // significant inside children; those of them below which a result line is pushed (per lane)
+    u32 last_rec = 0, last_valid = 0;  // 1 + child index (warp-uniform)
+    auto conf_of = [&](u32 ci, bool& valid) {
+        const NodeRec cr = recs[cf + ci];
+        valid = sv.strad_of_node[cf + ci] < 0 && (u64)cr.lo >= sh_lo && (u64)cr.lo + cr.size <= sh_hi;
+        return cr;
+    };
+    auto scan_run = [&](u32 a, u32 b2) {
+        for (u32 cb = a; cb < b2; cb += 32) {
+            const u32 ci = cb + lane;
+            bool valid = false;
+            double v = -CUDART_INF;
+            if (ci < b2) {
+                const NodeRec cr = conf_of(ci, valid);
+                if (valid) {
+                    v = node_conf(preb, segoff, skipw, cr);
+                    if ((u32)round(v * 100.0) != 0) {
+                        ++n_sig;
+                        n_push += ((cr.cc_type >> 30) != 2u) || seq_subtree_pushes(recs, preb, segoff, skipw, cr);
+                    }
+                }
+            }
+            const u32 vm = __ballot_sync(kFullMask, valid);
+            if (vm == 0u) continue;
+            double vmax = v;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) vmax = fmax(vmax, __shfl_xor_sync(kFullMask, vmax, o));
+            best = fmax(best, vmax);
+            const bool rec = valid && v >= best - fabs(best) * 1e-12;
+            const u32 r = __reduce_max_sync(kFullMask, rec ? ci + 1u : 0u);
+            if (r) last_rec = r;
+            last_valid = cb + 32u - (u32)__clz(vm);  // 1 + index of the chunk's last valid child (chunks ascend)
+        }
+    };
+    // the kept segments under the part of the straddler that lies in this shard
+    bool sparse = false;
+    u32 n_kept = 0;
+    if (tb - ta > kRecSparseMin) {
+        const u64 llo = (u64)nr.lo > sh_lo ? (u64)nr.lo - sh_lo : 0ull;
+        const u64 lhi = min((u64)nr.lo + nr.size, sh_hi) - sh_lo;
+        const u32 s0 = (u32)(llo / kPrefixSeg), s1 = (u32)((lhi + kPrefixSeg - 1) / kPrefixSeg);  // segments [s0, s1)
+        sparse = true;
+        for (u32 wb = s0 >> 5; wb * 32u < s1 && sparse; wb += 32) {
+            const u32 wi = wb + lane;
+            u32 kw = 0;
+            if (wi * 32u < s1) {
+                kw = ~skipw[wi];
+                if (wi * 32u < s0) kw &= ~((1u << (s0 - wi * 32u)) - 1u);
+                if (wi * 32u + 32u > s1) kw &= (1u << (s1 - wi * 32u)) - 1u;
+            }
+            const u32 c = __popc(kw);
+            const u32 inc = warp_scan_incl(c, lane);
+            const u32 tot = __shfl_sync(kFullMask, inc, 31);
+            if (n_kept + tot > kRecKept) {
+                sparse = false;
+            } else {
+                u32 pos = n_kept + inc - c;
+                while (kw) {
+                    s_kept[wib][pos++] = wi * 32u + (u32)__ffs(kw) - 1u;
+                    kw &= kw - 1u;
+                }
+                n_kept += tot;
             }
         }
+        __syncwarp();
+    }
+    if (sparse) {
+        u32 cursor = ta;
+        for (u32 k = 0; k < n_kept && cursor < tb; ++k) {
+            const u64 key_lo = sh_lo + (u64)s_kept[wib][k] * kPrefixSeg, key_hi = key_lo + kPrefixSeg;
+            const u32 a = warp_first_true(cursor, tb, lane, [&](u32 x) { const uint2 ls = child_lo_size(x); return (u64)ls.x + ls.y > key_lo; });
+            const u32 b2 = warp_first_true(a, tb, lane, [&](u32 x) { return (u64)child_lo_size(x).x >= key_hi; });
+            scan_run(a, b2);
+            cursor = max(cursor, b2);
+        }
+        if (!(best > 0.0)) {  // nothing above 0 among the evaluated children: the others are exactly 0, all tie, the last valid child wins
+            bool v1 = false, v2 = false;
+            if (tb > ta) conf_of(tb - 1, v1);
+            if (tb > ta + 1) conf_of(tb - 2, v2);
+            const u32 lv = v1 ? tb : (v2 ? tb - 1 : 0u);
+            if (lv) {
+                best = fmax(best, 0.0);
+                last_rec = lv;
+            }
+            last_valid = 0;  // (no second pass)
+        }
+    } else {
+        scan_run(ta, tb);
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
-        best = fmax(best, __shfl_xor_sync(kFullMask, best, o));
         n_sig += __shfl_xor_sync(kFullMask, n_sig, o);
         n_push += __shfl_xor_sync(kFullMask, n_push, o);
     }
     u32 besti = 0;
-    if (best > -CUDART_INF) {
+    if (best > -CUDART_INF && last_rec) {
         const double thr = best - fabs(best) * 1e-12;
-        for (u32 cb = 0; cb < cc; cb += 32) {
-            const u32 ci = cb + lane;
-            if (ci < cc && sv.strad_of_node[cf + ci] < 0 && node_inside(ix, cf + ci)) {
-                const NodeRec cr = recs[cf + ci];
-                if (node_conf(preb, segoff, skipw, cr) >= thr) besti = cf + ci;
-            }
+        bool ok = true;
+        if (last_valid) {  // does the last record pass the final test?
+            bool valid;
+            const NodeRec cr = conf_of(last_rec - 1u, valid);
+            ok = node_conf(preb, segoff, skipw, cr) >= thr;
         }
+        if (ok) {
+            besti = cf + last_rec - 1u;
+        } else {  // (values in the 1e-12 band right below the tolerance: practically never) second pass
+            for (u32 cb = ta; cb < tb; cb += 32) {
+                const u32 ci = cb + lane;
+                if (ci < tb) {
+                    bool valid;
+                    const NodeRec cr = conf_of(ci, valid);
+                    if (valid && node_conf(preb, segoff, skipw, cr) >= thr) besti = cf + ci;
+                }
+            }
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) besti = max(besti, __shfl_xor_sync(kFullMask, besti, o));
+            for (int o = 16; o > 0; o >>= 1) besti = max(besti, __shfl_xor_sync(kFullMask, besti, o));
+        }
     }
     if (lane == 0) {
         ShardRec r;
