@@ -381,6 +381,16 @@ __device__ __forceinline__ void merge_carries_v(u32 (&pl)[V][NP], const u32 (&ea
     for (int v = 0; v < V; ++v) merge_carries<NP>(pl[v], ea[v], eb[v]);
 }
 
+// The count vectors (2 * N bytes per query, tens of GB per launch) are written once and read back much later, if at all: streaming
+// stores (evict-first) keep them from pushing the L2-blocked slice of the bit matrix out of the L2.
+__device__ __forceinline__ void store_counts(uint4* p, const uint4& v) {
+#ifdef RTX_COUNTS_PLAIN_STORE
+    *p = v;
+#else
+    __stcs(p, v);
+#endif
+}
+
 template <int V, int NP, bool PF>
 __global__ void __launch_bounds__(kHitThreads)
     hitcount_bitrows_kernel(IndexView ix, BatchView b, u16* __restrict__ counts, int q_base, int tiles_per_cta, int n_tiles, int hist_global) {
@@ -462,7 +472,7 @@ __global__ void __launch_bounds__(kHitThreads)
                 const u64 ref0 = (u64)(word0 + v) * 32;
                 uint4* dst = reinterpret_cast<uint4*>(qcounts + ref0);
 #pragma unroll
-                for (int i = 0; i < 4; ++i) dst[i] = make_uint4(out[4 * i], out[4 * i + 1], out[4 * i + 2], out[4 * i + 3]);
+                for (int i = 0; i < 4; ++i) store_counts(dst + i, make_uint4(out[4 * i], out[4 * i + 1], out[4 * i + 2], out[4 * i + 3]));
                 if (ref0 + 32 <= ix.shard_refs) {
 #pragma unroll
                     for (int i = 0; i < 16; ++i) {
@@ -641,7 +651,7 @@ __global__ void __launch_bounds__(MAX_THREADS, CTAS_PER_SM)
                 const u64 ref0 = (u64)(word0 + v * kWordStep) * 32;
                 uint4* dst = reinterpret_cast<uint4*>(qcounts + ref0);
 #pragma unroll
-                for (int i = 0; i < 4; ++i) dst[i] = make_uint4(out[4 * i], out[4 * i + 1], out[4 * i + 2], out[4 * i + 3]);
+                for (int i = 0; i < 4; ++i) store_counts(dst + i, make_uint4(out[4 * i], out[4 * i + 1], out[4 * i + 2], out[4 * i + 3]));
                 if (ref0 + 32 <= ix.shard_refs) {
 #pragma unroll
                     for (int i = 0; i < 16; ++i) {
@@ -791,14 +801,17 @@ struct ProbScratch {
     double* cbuf;        // [slots][cbuf_stride] r_m[i] = pmf_m(i) / cmf_m(i) of the slow branch, row d = distinct count d
     size_t cbuf_stride;  // = hstride * tstride doubles
     u32 tstride;         // doubles per cbuf row ( >= max t + 1 )
-    double* preb;        // [sub-batch queries][preb_stride] prefix sums of normalised probabilities at node boundaries, relative
-    size_t preb_stride;  //   to the start of the 512-reference segment the boundary belongs to
+    double* blk;         // [sub-batch queries][blk_stride] prefix sum of the normalised probabilities at the start of every block of 8
+    size_t blk_stride;   //   references, relative to the start of the block's 512-reference segment (K4 -> walk)
+    const u16* counts;   // [sub-batch queries][counts_stride] the slot's count vectors (K2 -> K4, walk)
+    size_t counts_stride;
+    u32 hstride;         // stride of ptab
     double* segoff;      // [sub-batch queries][segoff_stride] prefix sum at the start of every 512-reference segment
     size_t segoff_stride;
     u32 seg_aux_off;     // per query, behind the segment offsets (in doubles): u32 aux[] = { m_min, 0, skip bitmap words ..., u16 segmax[n_seg] }
                          //   segmax (K2 -> K4): largest count of every 512-reference segment
                          //   m_min (K3 -> K4): counts below it carry < kMassCut of the probability mass altogether and are taken as 0
-                         //   skip bit s (K4 -> walk): no reference of segment s reaches m_min; its boundary prefixes were not written
+                         //   skip bit s (K4 -> walk): no reference of segment s reaches m_min; its block prefixes were not written
     double* ptab;        // [sub-batch queries][hstride] normalised P(m), direct-indexed by count (K3 -> K4)
     int nprod;           // kProbWarps: one partial prod array per warp; 1: a single array updated with shared-memory atomics
     int lf_smem;         // 1: ln n! staged in shared memory, 0: read from HBM/L2 (very long queries)
@@ -839,20 +852,64 @@ struct ProbSmem {
 
 // node record: one 16-byte load gives everything the walk needs about a child
 struct __align__(16) NodeRec {
-    u32 blo, bhi;      // boundary indices of [lo, hi) clamped to the shard
+    u32 blo, bhi;      // [lo, hi) clamped to the shard, as local reference positions
     u32 child_first;
     u32 cc_type;       // child_count | node_type << 30
-    u32 slo, shi;      // prefix segment the boundary blo / bhi belongs to (segment of the reference in front of it)
+    u32 slo, shi;      // prefix segments of the references in front of blo / bhi
     u32 lo, size;      // node_lo and node_hi - node_lo (global reference ids, not clamped to the shard)
 };
 
-// confidence of a node = sum of the normalised probabilities of its references (lineage.rs:114-117)
-// Boundaries inside a skipped segment (see ProbScratch::seg_aux_off) sit at relative prefix 0; their preb slots hold stale data.
-__device__ __forceinline__ double node_conf(const double* __restrict__ preb, const double* __restrict__ segoff, const u32* __restrict__ skipw,
-                                            const NodeRec& r) {
-    const double ph = preb[r.bhi], pl = preb[r.blo];  // both loads are issued before the bitmap words are known
-    const bool sh = (skipw[r.shi >> 5] >> (r.shi & 31)) & 1u, sl = (skipw[r.slo >> 5] >> (r.slo & 31)) & 1u;
-    return (segoff[r.shi] - segoff[r.slo]) + ((sh ? 0.0 : ph) - (sl ? 0.0 : pl));
+// One query's view of what K4 left behind.  The prefix sums of lineage.rs:61-77 are not materialised per reference (8 * N bytes per
+// query) nor per node boundary (5.6 MB per query on 1 M references, which made K4 HBM-write-bound on flat profiles): K4 stores one
+// value per 32 references, and whoever needs the mass in front of a position adds the up to 32 values P(count[r]) in between.
+struct MassView {
+    const double* __restrict__ blk;
+    const double* __restrict__ segoff;
+    const u32* __restrict__ skipw;
+    const u16* __restrict__ counts;
+    const double* __restrict__ ptab;
+};
+__device__ __forceinline__ const u32* seg_aux(const ProbScratch& sc, int ql);
+__device__ __forceinline__ MassView mass_view(const ProbScratch& sc, int ql) {
+    return MassView{sc.blk + (size_t)ql * sc.blk_stride, sc.segoff + (size_t)ql * sc.segoff_stride, seg_aux(sc, ql) + 2,
+                    sc.counts + (size_t)ql * sc.counts_stride, sc.ptab + (size_t)ql * sc.hstride};
+}
+__device__ __forceinline__ bool seg_skipped(const MassView& m, u32 s) { return (m.skipw[s >> 5] >> (s & 31)) & 1u; }
+constexpr u32 kBlkRefs = 8;  // references per stored prefix value
+// mass of the local references in front of position p, relative to the start of segment s = segment of reference p - 1 (0 for p == 0)
+__device__ __forceinline__ double mass_rel(const MassView& m, u32 p, u32 s) {
+    if (p == 0u || seg_skipped(m, s)) return 0.0;  // a skipped segment holds no mass (and no block prefixes)
+    const u32 last = p - 1u, k = last & 7u;
+    const uint4 c = *reinterpret_cast<const uint4*>(m.counts + (last & ~7u));  // the eight counts of the block, one 16-byte load
+    double v = m.blk[last >> 3];
+    v += m.ptab[c.x & 0xFFFFu];
+    if (k >= 1) v += m.ptab[c.x >> 16];
+    if (k >= 2) v += m.ptab[c.y & 0xFFFFu];
+    if (k >= 3) v += m.ptab[c.y >> 16];
+    if (k >= 4) v += m.ptab[c.z & 0xFFFFu];
+    if (k >= 5) v += m.ptab[c.z >> 16];
+    if (k >= 6) v += m.ptab[c.w & 0xFFFFu];
+    if (k >= 7) v += m.ptab[c.w >> 16];
+    return v;
+}
+// confidence of a node = sum of the normalised probabilities of its references (lineage.rs:114-117).  r.blo / r.bhi: the node's
+// local reference range (clamped to the shard), r.slo / r.shi: the segments of the references in front of them.
+__device__ __forceinline__ double node_conf(const MassView& m, const NodeRec& r) {
+    const u32 n = r.bhi - r.blo;
+    if (n <= 4u) {  // a few references (at most two segments): their probabilities themselves, in order
+        if (n == 0u) return 0.0;
+        const u32 sa = r.blo >> 9, sb = (r.bhi - 1u) >> 9;  // kPrefixSeg == 512
+        const bool ka = !seg_skipped(m, sa), kb = !seg_skipped(m, sb);
+        u32 c[4];
+#pragma unroll
+        for (u32 i = 0; i < 4; ++i) c[i] = i < n ? (u32)m.counts[r.blo + i] : 0u;
+        double v = 0.0;
+#pragma unroll
+        for (u32 i = 0; i < 4; ++i)
+            if (i < n && (((r.blo + i) >> 9) == sa ? ka : kb)) v += m.ptab[c[i]];
+        return v;
+    }
+    return (m.segoff[r.shi] - m.segoff[r.slo]) + (mass_rel(m, r.bhi, r.shi) - mass_rel(m, r.blo, r.slo));
 }
 __device__ __forceinline__ const u32* seg_aux(const ProbScratch& sc, int ql) {
     return reinterpret_cast<const u32*>(sc.segoff + (size_t)ql * sc.segoff_stride + sc.seg_aux_off);
@@ -1172,22 +1229,25 @@ __global__ void __launch_bounds__(kProbThreads, 4)
 }
 
 // =========================================================================================================
-// K4: prefix sums of the normalised probabilities at node boundaries (lineage.rs:61-77,114-117).
+// K4: prefix sums of the normalised probabilities (lineage.rs:61-77,114-117), kept per block of 8 references.
 //
 // One CTA per query, ONE barrier-free pass over the count vector in 512-reference segments (one segment = one warp
-// iteration, 16 references per lane): thread-serial + warp scan of P(count[r]); the values at the node boundaries of the
-// segment -- relative to the segment start -- are compacted in a per-warp staging buffer and stored with coalesced
-// 8-byte lanes; the segment total goes to shared memory.  After the pass one block-wide exclusive scan turns the totals
-// into segment offsets (a few KB per query).  A node confidence is then
-//     (segoff[seg(hi)] - segoff[seg(lo)]) + (preb[bhi] - preb[blo])                                   (node_conf)
-// so no warp ever waits for another one and the P(m) table is gathered exactly once per reference (the gathers from
-// shared memory are what bounds this kernel: l1tex 97 % in the two-pass version).
-// dynamic smem: double Ptab[hstride] | double segtot[n_seg (even)] | double stage[kPrefixWarps][kPrefixSeg]
+// iteration, 16 references per lane): thread-serial + warp scan of P(count[r]); the running sum at the start of every block of 8
+// references -- two per lane, relative to the segment start -- is stored (64 values, 512 bytes per segment; round 1 stored the
+// value at every node boundary, ~2.9 KB per segment on 1 M references, which made this kernel HBM-write-bound on flat profiles:
+// 12.1 -> 6.2 ms per 20 k queries), the segment total goes to shared memory.  After the pass one block-wide exclusive scan turns the
+// totals into segment offsets (a few KB per query).  The mass in front of a reference is then segoff[segment] + blk[block] + the up
+// to 8 values P(count[r]) in between (mass_rel: one 16-byte load of the block's counts), and a node confidence
+//     (segoff[seg(hi)] - segoff[seg(lo)]) + (rel(hi) - rel(lo))                                        (node_conf)
+// -- or, for a node of at most 4 references, the sum of their probabilities themselves.  No warp ever waits for another one and the
+// P(m) table is gathered exactly once per reference here.
+// dynamic smem: double Ptab[hstride] | double segtot[n_seg (even)] | u32 skip bitmap words
 // =========================================================================================================
 constexpr int kPrefixThreads = 256;
 constexpr int kPrefixWarps = kPrefixThreads / 32;
 constexpr int kPrefixPer = 16;
 constexpr u32 kPrefixSeg = 32 * kPrefixPer;  // 512 references; n_pad (a multiple of 4096) is a whole number of segments
+static_assert(kPrefixSeg == 512, "node_conf / mass_rel shift by 9");
 
 __device__ __forceinline__ void prefix_gather(double (&v)[kPrefixPer], const double* __restrict__ Ptab, const uint4& c0, const uint4& c1,
                                               u64 r0, u64 Ns) {
@@ -1218,8 +1278,7 @@ __global__ void __launch_bounds__(kPrefixThreads)
     const u32 n_seg = (u32)(ix.n_pad / kPrefixSeg);
     const bool ptab_global = sc.big != nullptr;  // very long queries: P(m) is gathered from the global table (L2) instead of a shared-memory copy
     double* segtot = reinterpret_cast<double*>(xsm_raw) + (ptab_global ? 0u : b.hstride);
-    double* stage = segtot + ((n_seg + 1u) & ~1u) + (size_t)warp * kPrefixSeg;
-    double* stage_end = segtot + ((n_seg + 1u) & ~1u) + (size_t)kPrefixWarps * kPrefixSeg;  // u32 skip bitmap words behind the staging area
+    double* stage_end = segtot + ((n_seg + 1u) & ~1u);  // u32 skip bitmap words behind the segment totals
     const u32 K = b.K[q];
     const double* __restrict__ gp = sc.ptab + (size_t)ql * b.hstride;
     const double* __restrict__ Ptab = gp;
@@ -1230,7 +1289,7 @@ __global__ void __launch_bounds__(kPrefixThreads)
     }
     __syncthreads();
     const u16* __restrict__ qcounts = counts + (size_t)ql * ix.n_pad;
-    double* __restrict__ preb = sc.preb + (size_t)ql * sc.preb_stride;
+    double* __restrict__ blk = sc.blk + (size_t)ql * sc.blk_stride;
     const u64 Ns = ix.shard_refs;
     u32* __restrict__ aux = const_cast<u32*>(seg_aux(sc, ql));
     const u32 mmin2 = aux[0] * 0x10001u;  // m_min in both half-words
@@ -1265,8 +1324,6 @@ __global__ void __launch_bounds__(kPrefixThreads)
             }
             continue;
         }
-        const u32 word = ix.bnd_after[r0 >> 5];
-        const u32 rank0 = ix.bnd_rank[s * (kPrefixSeg / 32)];  // boundaries before this segment
         {   // does any reference of the segment reach m_min?  (padding references have count 0; m_min == 0 keeps everything)
             const u32 mx = __vmaxu2(__vmaxu2(__vmaxu2(x0.x, x0.y), __vmaxu2(x0.z, x0.w)), __vmaxu2(__vmaxu2(x1.x, x1.y), __vmaxu2(x1.z, x1.w)));
             if (!__any_sync(kFullMask, __vcmpgeu2(mx, mmin2) != 0u)) {
@@ -1284,19 +1341,8 @@ __global__ void __launch_bounds__(kPrefixThreads)
         const double inc = warp_scan_incl(v[kPrefixPer - 1], lane);
         const double offs = inc - v[kPrefixPer - 1];
         if (lane == 31) segtot[s] = inc;
-        const u32 bits = (r0 < Ns) ? ((word >> (u32)(r0 & 31)) & 0xFFFFu) : 0u;
-        const u32 nb = __popc(bits);
-        const u32 pinc = warp_scan_incl(nb, lane);
-        const u32 total_b = __shfl_sync(kFullMask, pinc, 31);
-        u32 pos = pinc - nb;
-#pragma unroll
-        for (int k = 0; k < kPrefixPer; ++k) {
-            if (bits & (1u << k)) stage[pos++] = offs + v[k];
-        }
-        __syncwarp();
-        double* __restrict__ dst = preb + 1u + rank0;
-        for (u32 i = lane; i < total_b; i += 32) dst[i] = stage[i];
-        __syncwarp();
+        // the running sum at the start of every block of 8 references (two per lane), relative to the segment start
+        *reinterpret_cast<double2*>(blk + (size_t)s * (kPrefixSeg / kBlkRefs) + 2 * lane) = make_double2(offs, offs + v[7]);
     }
     __syncthreads();
     // ---- exclusive scan of the segment totals -> segment offsets -------------------------------------------------
@@ -1318,7 +1364,6 @@ __global__ void __launch_bounds__(kPrefixThreads)
             run += segtot[i];
         }
     }
-    if (tid == 0) preb[0] = 0.0;
     for (u32 i = tid; i < (n_seg + 31u) / 32u; i += kPrefixThreads) aux[2 + i] = skipw_s[i];
 }
 
@@ -1354,8 +1399,7 @@ __device__ __forceinline__ bool node_inside(const IndexView& ix, u32 node) {
 // Does the subtree of a significant Sequence node push a result line (lineage.rs:126-149)?  Its Taxon / Inner children do as soon as
 // they are significant; Sequence children (a rank repeating its parent's label again) are followed.  The node lies inside the shard,
 // hence so does its whole subtree.  Rare path (degenerate lineages), one lane.
-__device__ bool seq_subtree_pushes(const NodeRec* __restrict__ recs, const double* __restrict__ preb, const double* __restrict__ segoff,
-                                   const u32* __restrict__ skipw, const NodeRec& s) {
+__device__ bool seq_subtree_pushes(const NodeRec* __restrict__ recs, const MassView& mv, const NodeRec& s) {
     u32 st_cf[8], st_cc[8];
     int sp = 1;
     st_cf[0] = s.child_first;
@@ -1365,7 +1409,7 @@ __device__ bool seq_subtree_pushes(const NodeRec* __restrict__ recs, const doubl
         const u32 cf = st_cf[sp], cc = st_cc[sp];
         for (u32 i = 0; i < cc; ++i) {
             const NodeRec c = recs[cf + i];
-            if ((u32)round(node_conf(preb, segoff, skipw, c) * 100.0) == 0u) continue;
+            if ((u32)round(node_conf(mv, c) * 100.0) == 0u) continue;
             if ((c.cc_type >> 30) != 2u) return true;
             if (sp >= 8) return true;  // deeper than any sane lineage: be conservative
             st_cf[sp] = c.child_first;
@@ -1393,9 +1437,7 @@ __global__ void __launch_bounds__(128) shard_records_kernel(IndexView ix, const 
     const long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (w >= (long long)q_count * sv.n_strad) return;
     const int ql = (int)(w / sv.n_strad), j = (int)(w % sv.n_strad);
-    const double* __restrict__ preb = sc.preb + (size_t)ql * sc.preb_stride;
-    const double* __restrict__ segoff = sc.segoff + (size_t)ql * sc.segoff_stride;
-    const u32* __restrict__ skipw = seg_aux(sc, ql) + 2;
+    const MassView mv = mass_view(sc, ql);
     const u64 sh_lo = ix.shard_begin, sh_hi = ix.shard_begin + ix.shard_refs;
     const u32 node = sv.strad_nodes[j];
     const NodeRec nr = recs[node];
@@ -1423,10 +1465,10 @@ __global__ void __launch_bounds__(128) shard_records_kernel(IndexView ix, const 
             if (ci < b2) {
                 const NodeRec cr = conf_of(ci, valid);
                 if (valid) {
-                    v = node_conf(preb, segoff, skipw, cr);
+                    v = node_conf(mv, cr);
                     if ((u32)round(v * 100.0) != 0) {
                         ++n_sig;
-                        n_push += ((cr.cc_type >> 30) != 2u) || seq_subtree_pushes(recs, preb, segoff, skipw, cr);
+                        n_push += ((cr.cc_type >> 30) != 2u) || seq_subtree_pushes(recs, mv, cr);
                     }
                 }
             }
@@ -1454,7 +1496,7 @@ __global__ void __launch_bounds__(128) shard_records_kernel(IndexView ix, const 
             const u32 wi = wb + lane;
             u32 kw = 0;
             if (wi * 32u < s1) {
-                kw = ~skipw[wi];
+                kw = ~mv.skipw[wi];
                 if (wi * 32u < s0) kw &= ~((1u << (s0 - wi * 32u)) - 1u);
                 if (wi * 32u + 32u > s1) kw &= (1u << (s1 - wi * 32u)) - 1u;
             }
@@ -1509,7 +1551,7 @@ __global__ void __launch_bounds__(128) shard_records_kernel(IndexView ix, const 
         if (last_valid) {  // does the last record pass the final test?
             bool valid;
             const NodeRec cr = conf_of(last_rec - 1u, valid);
-            ok = node_conf(preb, segoff, skipw, cr) >= thr;
+            ok = node_conf(mv, cr) >= thr;
         }
         if (ok) {
             besti = cf + last_rec - 1u;
@@ -1519,7 +1561,7 @@ __global__ void __launch_bounds__(128) shard_records_kernel(IndexView ix, const 
                 if (ci < tb) {
                     bool valid;
                     const NodeRec cr = conf_of(ci, valid);
-                    if (valid && node_conf(preb, segoff, skipw, cr) >= thr) besti = cf + ci;
+                    if (valid && node_conf(mv, cr) >= thr) besti = cf + ci;
                 }
             }
 #pragma unroll
@@ -1528,7 +1570,7 @@ __global__ void __launch_bounds__(128) shard_records_kernel(IndexView ix, const 
     }
     if (lane == 0) {
         ShardRec r;
-        r.mass = node_conf(preb, segoff, skipw, nr);
+        r.mass = node_conf(mv, nr);
         r.best = best;
         r.best_child = besti;
         r.n_sig = min(n_sig, 0xFFFFu) | (min(n_push, 0xFFFFu) << 16);
@@ -1641,9 +1683,7 @@ __global__ void __launch_bounds__(kWalkWarps * 32)
     const u32 ML = ix.max_levels;
     WalkSmem ws(wsm_raw + (size_t)warp * WalkSmem::bytes(ML), ML);
     const double Nd = (double)ix.n_refs;
-    const double* __restrict__ preb = sc.preb + (size_t)ql * sc.preb_stride;
-    const double* __restrict__ segoff = sc.segoff + (size_t)ql * sc.segoff_stride;
-    const u32* __restrict__ skipw = seg_aux(sc, ql) + 2;
+    const MassView mv = mass_view(sc, ql);
     int status = retry_only ? (int)kQOk : pool.status[q];
 
     u32 n_res = 0;
@@ -1675,10 +1715,10 @@ __global__ void __launch_bounds__(kWalkWarps * 32)
                     if (SH) {
                         const int sj = sv.strad_of_node[cf + ci];
                         if (sj >= 0) k = sv.sk[(size_t)ql * sv.n_strad + sj];  // combined over the ranks
-                        else if (node_inside(ix, cf + ci)) k = (u32)round((node_conf(preb, segoff, skipw, cr)) * 100.0);
+                        else if (node_inside(ix, cf + ci)) k = (u32)round((node_conf(mv, cr)) * 100.0);
                         // children inside another shard are walked by their owner
                     } else {
-                        k = (u32)round((node_conf(preb, segoff, skipw, cr)) * 100.0);  // f64::round, half away from zero (lineage.rs:129)
+                        k = (u32)round((node_conf(mv, cr)) * 100.0);  // f64::round, half away from zero (lineage.rs:129)
                     }
                 }
                 const u32 mask = __ballot_sync(kFullMask, k != 0);
@@ -1765,7 +1805,7 @@ __global__ void __launch_bounds__(kWalkWarps * 32)
                             const u32 ci = cb + lane;
                             if (ci < cur_cc) {
                                 const NodeRec cr = recs[cur_cf + ci];
-                                const double v = node_conf(preb, segoff, skipw, cr);
+                                const double v = node_conf(mv, cr);
                                 if (cb == 0) {
                                     cv0 = v;
                                     cr0 = cr;
@@ -1782,7 +1822,7 @@ __global__ void __launch_bounds__(kWalkWarps * 32)
                             const u32 ci = cb + lane;
                             if (ci < cur_cc) {
                                 const NodeRec cr = recs[cur_cf + ci];
-                                if (node_conf(preb, segoff, skipw, cr) >= thr) besti = ci;
+                                if (node_conf(mv, cr) >= thr) besti = ci;
                             }
                         }
 #pragma unroll
@@ -2098,6 +2138,8 @@ constexpr u32 kBfsLeaf = 64;                          // search: runs this short
 constexpr u32 kBfsQueue = 256;                        // search: runs in flight per round
 constexpr double kBfsMassFloor = 0.004999;            // a child is significant from 0.005 on; the margin covers the rounding of the sums
 constexpr int kBfsThreadsDefault = 256;  // CTA size of lineage_bfs_kernel (template parameter: RTX_OPT_WALK_VARIANT 2 runs 128)
+constexpr u32 kBfsPtabSmemMax = 16384;   // the query's P(m) table is staged behind BfsSmem when it fits (K <= 2047), see bfs_ptab_smem
+__host__ __device__ inline size_t bfs_ptab_smem(u32 hstride) { return (size_t)hstride * 8 <= kBfsPtabSmemMax ? (size_t)hstride * 8 : 0; }
 
 struct BfsSmem {
     unsigned long long* best;  // [F] arg-max value (bits of a non-negative double)
@@ -2291,16 +2333,13 @@ __device__ u32 bfs_build_pairs(const BfsSmem& w, const NodeRec* __restrict__ rec
     return P;
 }
 
-// probability mass in front of child j of a node (j == cc: behind its last child), from the boundary prefixes (see node_conf)
-__device__ __forceinline__ double bfs_child_prefix(const NodeRec* __restrict__ recs, u32 cf, u32 cc, u32 j, const double* __restrict__ preb,
-                                                   const double* __restrict__ segoff, const u32* __restrict__ skipw) {
+// probability mass in front of child j of a node (j == cc: behind its last child), see node_conf
+__device__ __forceinline__ double bfs_child_prefix(const NodeRec* __restrict__ recs, u32 cf, u32 cc, u32 j, const MassView& mv) {
     const bool end = j >= cc;
     const NodeRec* r = recs + cf + (end ? cc - 1u : j);
     const uint2 bb = *reinterpret_cast<const uint2*>(&r->blo), ss = *reinterpret_cast<const uint2*>(&r->slo);
-    const u32 bi = end ? bb.y : bb.x, si = end ? ss.y : ss.x;
-    const double pv = preb[bi];
-    const bool sk = (skipw[si >> 5] >> (si & 31)) & 1u;
-    return segoff[si] + (sk ? 0.0 : pv);
+    const u32 p = end ? bb.y : bb.x, si = end ? ss.y : ss.x;
+    return mv.segoff[si] + mass_rel(mv, p, si);
 }
 
 // Mass-pruned search for the child runs of `n` frontier nodes (log entries range_begin ..) that can hold a significant child ->
@@ -2310,8 +2349,8 @@ __device__ __forceinline__ double bfs_child_prefix(const NodeRec* __restrict__ r
 // [sh_lo, sh_hi) are found by binary search; the first and the last of them may straddle a cut (their confidence comes from the
 // combined records) and are always looked at, the ones in between lie inside the shard and are searched by mass.
 template <int kBfsThreads, bool SH>
-__device__ u32 bfs_search_pairs(const BfsSmem& w, const NodeRec* __restrict__ recs, const double* __restrict__ preb, const double* __restrict__ segoff,
-                                const u32* __restrict__ skipw, u32 n, u32 range_begin, u32* ctr, int tid, u64 sh_lo, u64 sh_hi, u32 leaf_len) {
+__device__ u32 bfs_search_pairs(const BfsSmem& w, const NodeRec* __restrict__ recs, const MassView& mv, u32 n, u32 range_begin, u32* ctr, int tid,
+                                u64 sh_lo, u64 sh_hi, u32 leaf_len) {
     constexpr int kBfsWarps = kBfsThreads / 32;
     const int lane = tid & 31, warp = tid >> 5;
     const u32 lt_mask = (1u << lane) - 1u;
@@ -2403,9 +2442,9 @@ __device__ u32 bfs_search_pairs(const BfsSmem& w, const NodeRec* __restrict__ re
             const u32 cf = w.ent_cf[e], cc = w.ent_cc[e] & 0x3FFFFFFFu;
             const u32 step = (b - a + 31u) / 32u;
             const u32 sa = min(a + (u32)lane * step, b), sb = min(sa + step, b);
-            const double v0 = bfs_child_prefix(recs, cf, cc, sa, preb, segoff, skipw);
+            const double v0 = bfs_child_prefix(recs, cf, cc, sa, mv);
             double v1 = __shfl_down_sync(kFullMask, v0, 1);
-            if (lane == 31) v1 = bfs_child_prefix(recs, cf, cc, sb, preb, segoff, skipw);
+            if (lane == 31) v1 = bfs_child_prefix(recs, cf, cc, sb, mv);
             const bool keep = sa < sb && (v1 - v0) >= kBfsMassFloor;
             const bool leaf = keep && sb - sa <= leaf_len, more = keep && !leaf;
             const u32 ml = __ballot_sync(kFullMask, leaf), mm = __ballot_sync(kFullMask, more);
@@ -2474,9 +2513,13 @@ __global__ void __launch_bounds__(kBfsThreads)  // (a 6-CTA/SM bound, 40 registe
     constexpr u32 F = BfsSmem::F, R = BfsSmem::R;
     const u32 E = min(BfsSmem::E, entry_cap);  // a smaller cap only serves the tests of the retry path
     const double Nd = (double)ix.n_refs;
-    const double* __restrict__ preb = sc.preb + (size_t)ql * sc.preb_stride;
-    const double* __restrict__ segoff = sc.segoff + (size_t)ql * sc.segoff_stride;
-    const u32* __restrict__ skipw = seg_aux(sc, ql) + 2;
+    MassView mv = mass_view(sc, ql);
+    if (bfs_ptab_smem(b.hstride)) {  // the gathers of node_conf / mass_rel then come from shared memory (visible behind the first barrier below)
+        double* ptab_s = reinterpret_cast<double*>(bsm_raw + BfsSmem::bytes(ML));
+        const u32 K1 = (u32)b.K[q] + 1u;
+        for (u32 m = tid; m < K1; m += kBfsThreads) ptab_s[m] = mv.ptab[m];
+        mv.ptab = ptab_s;
+    }
     const u32 lt_mask = (1u << lane) - 1u;
     const u64 sh_lo = ix.shard_begin, sh_hi = ix.shard_begin + ix.shard_refs;
     auto inside = [&](const NodeRec& r) { return (u64)r.lo >= sh_lo && (u64)r.lo + r.size <= sh_hi; };
@@ -2513,7 +2556,7 @@ __global__ void __launch_bounds__(kBfsThreads)  // (a 6-CTA/SM bound, 40 registe
                 const u32 wi = bb + lane;
                 u32 kw = 0;
                 if (wi < n_words) {
-                    kw = ~skipw[wi];
+                    kw = ~mv.skipw[wi];
                     if (wi * 32u + 32u > n_seg) kw &= (1u << (n_seg - wi * 32u)) - 1u;  // (n_seg is not a multiple of 32 here)
                 }
                 const u32 c = __popc(kw);
@@ -2590,7 +2633,7 @@ __global__ void __launch_bounds__(kBfsThreads)  // (a 6-CTA/SM bound, 40 registe
             u32 total = w.fr_off[nf], n_own = nf;
             const bool pairs = sparse != 0 && total >= pair_min;  // block-uniform
             if (pairs) {
-                n_own = bfs_search_pairs<kBfsThreads, SH>(w, recs, preb, segoff, skipw, nf, lvl_begin, s_ctr, tid, sh_lo, sh_hi, leaf_len);
+                n_own = bfs_search_pairs<kBfsThreads, SH>(w, recs, mv, nf, lvl_begin, s_ctr, tid, sh_lo, sh_hi, leaf_len);
                 if (n_own == ~0u) {  // (every thread sees the same return value)
                     if (tid == 0) s_retry = 1;
                     break;
@@ -2621,7 +2664,7 @@ __global__ void __launch_bounds__(kBfsThreads)  // (a 6-CTA/SM bound, 40 registe
                     kk[u] = 0u;
                     if (idx < total) {
                         if (SH && sj[u] >= 0) kk[u] = sv.sk[srow + sj[u]];  // combined over the ranks
-                        else if (!SH || inside(cr[u])) kk[u] = (u32)round(node_conf(preb, segoff, skipw, cr[u]) * 100.0);  // f64::round (lineage.rs:129)
+                        else if (!SH || inside(cr[u])) kk[u] = (u32)round(node_conf(mv, cr[u]) * 100.0);  // f64::round (lineage.rs:129)
                         // children inside another shard are walked by their owner
                     }
                 }
@@ -2730,7 +2773,7 @@ __global__ void __launch_bounds__(kBfsThreads)  // (a 6-CTA/SM bound, 40 registe
                 }
                 double vv[2];
 #pragma unroll
-                for (int u = 0; u < 2; ++u) vv[u] = valid[u] ? fmax(node_conf(preb, segoff, skipw, cr[u]), 0.0) : 0.0;
+                for (int u = 0; u < 2; ++u) vv[u] = valid[u] ? fmax(node_conf(mv, cr[u]), 0.0) : 0.0;
 #pragma unroll
                 for (int u = 0; u < 2; ++u) {
                     const double v = vv[u];
@@ -2770,7 +2813,7 @@ __global__ void __launch_bounds__(kBfsThreads)  // (a 6-CTA/SM bound, 40 registe
                     w.besti[i] = hcc;
                 } else {
                     const NodeRec cr = recs[w.ent_cf[head] + w.besti[i] - 1u];
-                    const double v = fmax(node_conf(preb, segoff, skipw, cr), 0.0);
+                    const double v = fmax(node_conf(mv, cr), 0.0);
                     if (!(v >= bestv - fabs(bestv) * 1e-12)) {
                         w.besti[i] = 0x80000000u;
                         s_slow = 1u;
@@ -2785,7 +2828,7 @@ __global__ void __launch_bounds__(kBfsThreads)  // (a 6-CTA/SM bound, 40 registe
                     if (!(w.besti[c] & 0x80000000u)) continue;
                     const u32 ci = (pairs ? w.pair_a[o] : 0u) + (idx - w.fr_off[o]);
                     const NodeRec cr = recs[w.ent_cf[cur[c]] + ci];
-                    const double v = fmax(node_conf(preb, segoff, skipw, cr), 0.0);
+                    const double v = fmax(node_conf(mv, cr), 0.0);
                     const double bestv = __longlong_as_double((long long)w.best[c]);
                     if (v >= bestv - fabs(bestv) * 1e-12) atomicMax(&w.besti[c], 0x80000000u | (ci + 1u));
                 }

@@ -636,7 +636,7 @@ RTX_API int rtx_index_upload(rtx_ctx* ctx, const rtx_index_desc* d) {
         std::vector<NodeRec> recs(nn);
         auto seg_of = [&](u64 pos) -> u32 { return pos > s0 ? (u32)((pos - s0 - 1) / kPrefixSeg) : 0u; };  // segment of the reference in front of pos
         for (u32 i = 0; i < nn; ++i)
-            recs[i] = NodeRec{blo[i], bhi[i], d->child_first[i], d->child_count[i] | ((u32)d->node_type[i] << 30),
+            recs[i] = NodeRec{(u32)(clampu(d->node_lo[i]) - s0), (u32)(clampu(d->node_hi[i]) - s0), d->child_first[i], d->child_count[i] | ((u32)d->node_type[i] << 30),
                               seg_of(clampu(d->node_lo[i])), seg_of(clampu(d->node_hi[i])), d->node_lo[i], d->node_hi[i] - d->node_lo[i]};
         CU(upload_vec(ctx->d_recs, recs.data(), nn, &bytes));
     }
@@ -811,7 +811,10 @@ static int bind_scratch(rtx_ctx* ctx) {
     if (ctx->need_prob_big) CU(ctx->d_prob_big.ensure(ctx->need_prob_big));
     ctx->sc.ptab = ctx->d_ptab.as<double>();
     ctx->sc.cbuf = ctx->d_cbuf.as<double>();
-    ctx->sc.preb = ctx->d_preb.as<double>();
+    ctx->sc.blk = ctx->d_preb.as<double>();
+    ctx->sc.counts = ctx->d_counts.as<u16>();
+    ctx->sc.counts_stride = (size_t)ctx->ix.n_pad;
+    ctx->sc.hstride = ctx->bv.hstride;
     ctx->sc.segoff = ctx->d_segoff.as<double>();
     ctx->sc.big = ctx->need_prob_big ? ctx->d_prob_big.as<unsigned char>() : nullptr;
     ctx->sc1 = ctx->sc;
@@ -820,7 +823,8 @@ static int bind_scratch(rtx_ctx* ctx) {
         CU(ctx->d_preb1.ensure(std::max<size_t>(ctx->need_preb, 1)));
         CU(ctx->d_ptab1.ensure(std::max<size_t>(ctx->need_ptab, 1)));
         CU(ctx->d_segoff1.ensure(std::max<size_t>(ctx->need_segoff, 1)));
-        ctx->sc1.preb = ctx->d_preb1.as<double>();
+        ctx->sc1.blk = ctx->d_preb1.as<double>();
+        ctx->sc1.counts = ctx->d_counts1.as<u16>();
         ctx->sc1.ptab = ctx->d_ptab1.as<double>();
         ctx->sc1.segoff = ctx->d_segoff1.as<double>();
         // the log-CMF scratch is indexed by CTA slot of prob_table_kernel, which only ever runs on stream2: shared
@@ -953,7 +957,7 @@ RTX_API int rtx_batch_upload(rtx_ctx* ctx, const rtx_batch* batch) {
         if (rc) return rc;
     }
 
-    // sub-batch: the per-query scratch (count vector, boundary prefixes, segment offsets, P(m) table) of one sub-batch may take a
+    // sub-batch: the per-query scratch (count vector, block prefixes, segment offsets, P(m) table) of one sub-batch may take a
     // quarter of the memory that is free now, at most 48 GB and at least 2 GiB -- large sub-batches amortise the launch tails of
     // the walk and probability kernels (C3: 1 069 queries per sub-batch at the old fixed 2 GiB, ~6 000 now)
     const u64 per_query = ctx->ix.n_pad * 2;
@@ -962,7 +966,7 @@ RTX_API int rtx_batch_upload(rtx_ctx* ctx, const rtx_batch* batch) {
         const u64 mem_free = ctx->mem_free_after_index;  // sampled once per index upload (cudaMemGetInfo costs ~1 ms per call)
         u64 budget = std::min<u64>(std::max<u64>(mem_free / 4, 2ull << 30), 48ull << 30);
         if (ctx->comm != nullptr && ctx->sv.n_shards > 1) budget = std::min<u64>(budget, std::max<u64>(mem_free / 5, 1ull << 30));  // two scratch slots
-        const u64 scratch_per_query = per_query + ((u64)round_up(ctx->ix.n_bnd, 4) + ctx->ix.n_pad / kPrefixSeg + ctx->ix.n_pad / kPrefixSeg / 64 + ctx->ix.n_pad / kPrefixSeg / 4 + 8 + hstride) * 8;
+        const u64 scratch_per_query = per_query + ((u64)ctx->ix.n_pad / kBlkRefs + ctx->ix.n_pad / kPrefixSeg + ctx->ix.n_pad / kPrefixSeg / 64 + ctx->ix.n_pad / kPrefixSeg / 4 + 8 + hstride) * 8;
         sb = std::max<u64>(1, budget / scratch_per_query);
     }
     const bool may_pipe = ctx->pipeline_opt && ctx->sv.n_shards <= 1;
@@ -986,13 +990,13 @@ RTX_API int rtx_batch_upload(rtx_ctx* ctx, const rtx_batch* batch) {
     if (occ < 1) return set_err(ctx, RTX_ERR_CUDA, "prob_table_kernel does not fit on an SM");
     {
         const size_t n_seg = ctx->ix.n_pad / kPrefixSeg;
-        ctx->prefix_smem = ((ctx->prob_big_bytes ? (size_t)0 : (size_t)hstride) + ((n_seg + 1) & ~(size_t)1) + (size_t)kPrefixWarps * kPrefixSeg) * 8 +
+        ctx->prefix_smem = ((ctx->prob_big_bytes ? (size_t)0 : (size_t)hstride) + ((n_seg + 1) & ~(size_t)1)) * 8 +
                            ((n_seg + 31) / 32) * 4 + 16;
         if (ctx->prefix_smem > 220 * 1024)
             return set_err(ctx, RTX_ERR_UNSUPPORTED, "reference shard too large for the prefix kernel's segment table (more than ~11 M references per GPU): shard the references");
     }
     ctx->walk_smem = (size_t)kWalkWarps * WalkSmem::bytes(ctx->ix.max_levels);
-    ctx->bfs_smem = BfsSmem::bytes(ctx->ix.max_levels);
+    ctx->bfs_smem = BfsSmem::bytes(ctx->ix.max_levels) + bfs_ptab_smem(hstride);
     ctx->shard_phase = 0;
     int slots = (int)std::min<u64>((u64)ctx->n_sms * occ, sb);
     const u32 tstride = round_up(hstride / 2 + 1, 4);
@@ -1014,9 +1018,9 @@ RTX_API int rtx_batch_upload(rtx_ctx* ctx, const rtx_batch* batch) {
         ctx->sc.big_stride = ctx->prob_big_bytes;
     }
     ctx->prob_slots = slots;
-    ctx->sc.preb_stride = round_up(ctx->ix.n_bnd, 4);
+    ctx->sc.blk_stride = (size_t)ctx->ix.n_pad / kBlkRefs;  // one value per block of references
     ctx->need_cbuf = (size_t)slots * ctx->sc.cbuf_stride * 8;
-    ctx->need_preb = (size_t)sb * ctx->sc.preb_stride * 8;
+    ctx->need_preb = (size_t)sb * ctx->sc.blk_stride * 8;
     ctx->need_ptab = (size_t)sb * hstride * 8;
     {   // per query: n_seg segment offsets | u32 aux[2 + n_seg/32] (m_min, skip bitmap; ProbScratch::seg_aux_off)
         const u32 n_seg = (u32)(ctx->ix.n_pad / kPrefixSeg);
