@@ -878,10 +878,11 @@ __device__ __forceinline__ bool seg_skipped(const MassView& m, u32 s) { return (
 constexpr u32 kBlkRefs = 8;  // references per stored prefix value
 // mass of the local references in front of position p, relative to the start of segment s = segment of reference p - 1 (0 for p == 0)
 __device__ __forceinline__ double mass_rel(const MassView& m, u32 p, u32 s) {
-    if (p == 0u || seg_skipped(m, s)) return 0.0;  // a skipped segment holds no mass (and no block prefixes)
-    const u32 last = p - 1u, k = last & 7u;
+    // (the loads are issued before the skip bit is known: one dependent round trip less on the walk's critical path)
+    const u32 last = p ? p - 1u : 0u, k = last & 7u;
     const uint4 c = *reinterpret_cast<const uint4*>(m.counts + (last & ~7u));  // the eight counts of the block, one 16-byte load
     double v = m.blk[last >> 3];
+    if (p == 0u || seg_skipped(m, s)) return 0.0;  // a skipped segment holds no mass (and stale block prefixes)
     v += m.ptab[c.x & 0xFFFFu];
     if (k >= 1) v += m.ptab[c.x >> 16];
     if (k >= 2) v += m.ptab[c.y & 0xFFFFu];
@@ -2140,6 +2141,8 @@ constexpr double kBfsMassFloor = 0.004999;            // a child is significant 
 constexpr int kBfsThreadsDefault = 256;  // CTA size of lineage_bfs_kernel (template parameter: RTX_OPT_WALK_VARIANT 2 runs 128)
 constexpr u32 kBfsPtabSmemMax = 16384;   // the query's P(m) table is staged behind BfsSmem when it fits (K <= 2047), see bfs_ptab_smem
 __host__ __device__ inline size_t bfs_ptab_smem(u32 hstride) { return (size_t)hstride * 8 <= kBfsPtabSmemMax ? (size_t)hstride * 8 : 0; }
+// ... and so is its skip bitmap (one bit per 512-reference segment)
+__host__ __device__ inline size_t bfs_skip_smem(u64 n_pad) { return (size_t)(((n_pad / 512 + 31) / 32 * 4 + 15) & ~(u64)15); }
 
 struct BfsSmem {
     unsigned long long* best;  // [F] arg-max value (bits of a non-negative double)
@@ -2520,6 +2523,13 @@ __global__ void __launch_bounds__(kBfsThreads)  // (a 6-CTA/SM bound, 40 registe
         for (u32 m = tid; m < K1; m += kBfsThreads) ptab_s[m] = mv.ptab[m];
         mv.ptab = ptab_s;
     }
+    {
+        u32* skip_s = reinterpret_cast<u32*>(bsm_raw + BfsSmem::bytes(ML) + bfs_ptab_smem(b.hstride));
+        const u32 n_words = (u32)((ix.n_pad / kPrefixSeg + 31) / 32);
+        for (u32 i = tid; i < n_words; i += kBfsThreads) skip_s[i] = mv.skipw[i];
+        mv.skipw = skip_s;
+    }
+    __syncthreads();  // (block-uniform: the tables are read by warp 0 right below)
     const u32 lt_mask = (1u << lane) - 1u;
     const u64 sh_lo = ix.shard_begin, sh_hi = ix.shard_begin + ix.shard_refs;
     auto inside = [&](const NodeRec& r) { return (u64)r.lo >= sh_lo && (u64)r.lo + r.size <= sh_hi; };

@@ -996,7 +996,7 @@ RTX_API int rtx_batch_upload(rtx_ctx* ctx, const rtx_batch* batch) {
             return set_err(ctx, RTX_ERR_UNSUPPORTED, "reference shard too large for the prefix kernel's segment table (more than ~11 M references per GPU): shard the references");
     }
     ctx->walk_smem = (size_t)kWalkWarps * WalkSmem::bytes(ctx->ix.max_levels);
-    ctx->bfs_smem = BfsSmem::bytes(ctx->ix.max_levels) + bfs_ptab_smem(hstride);
+    ctx->bfs_smem = BfsSmem::bytes(ctx->ix.max_levels) + bfs_ptab_smem(hstride) + bfs_skip_smem(ctx->ix.n_pad);
     ctx->shard_phase = 0;
     int slots = (int)std::min<u64>((u64)ctx->n_sms * occ, sb);
     const u32 tstride = round_up(hstride / 2 + 1, 4);
