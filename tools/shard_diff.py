@@ -1,7 +1,7 @@
 """Why a reference-sharded run can differ from the unsharded one: the same queries of a workload through N shards on ONE GPU (staged
 exchanges, the same kernels as the NCCL path) and through an unsharded context; every differing query is printed and judged against the
 CPU oracle with the tolerant checker (fallback ties / rounding boundaries, tests/parity.py).
-usage: python tools/shard_diff.py c3 8 16384"""
+usage: python tools/shard_diff.py c3 8 16384   |   python tools/shard_diff.py c2:12000:1500 8 1500"""
 import os
 import sys
 
@@ -15,8 +15,15 @@ from raxtax_b200 import dist as rdist
 name = sys.argv[1] if len(sys.argv) > 1 else "c3"
 n_shards = int(sys.argv[2]) if len(sys.argv) > 2 else 8
 nq = int(sys.argv[3]) if len(sys.argv) > 3 else 16384
-q_total, _, _ = bench.workload_queries(name, 1)
-ds = bench.load_workload(name, q_total)
+if ":" in name:  # name:n_refs:n_queries -- a reduced data set, e.g. c2:12000:1500 (tests/test_gpu_nccl.py)
+    from raxtax_b200 import synth
+
+    name, n_refs, n_q = name.split(":")
+    ds = synth.generate(name, n_refs=int(n_refs), n_queries=int(n_q), measure=False)
+    nq = min(nq, ds.n_queries)
+else:
+    q_total, _, _ = bench.workload_queries(name, 1)
+    ds = bench.load_workload(name, q_total)
 tree = capi.Tree.new(ds.ref_lineages, ds.ref_off, ds.ref_codes)
 off = np.ascontiguousarray(ds.query_off[: nq + 1], np.uint64)
 codes = ds.query_codes[: int(off[-1])]
