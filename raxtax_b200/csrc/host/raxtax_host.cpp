@@ -1548,6 +1548,8 @@ struct Worker {
     rxh_logger logger;
     void* logger_user;
     std::atomic<size_t> next_chunk{0};
+    std::vector<size_t> chunk_begin{};  // query-partitioned drivers: chunk i = [chunk_begin[i], chunk_begin[i + 1])
+    bool ramp = false;                  // the chunk size was left to the library: small chunks at both ends of the job (plan_chunks)
     std::atomic<bool> failed{false}, warned{false};
     std::mutex io_mtx{}, err_mtx{};
     std::string err{};
@@ -1790,9 +1792,9 @@ struct Worker {
         std::vector<std::pair<size_t, size_t>> todo;  // ranges of this thread's current chunk (split further when memory runs out)
         while (true) {
             if (todo.empty()) {
-                const size_t c0 = next_chunk.fetch_add(1) * chunk_size;
-                if (c0 >= nq || failed.load()) break;
-                todo.emplace_back(c0, std::min(chunk_size, nq - c0));
+                const size_t ci = next_chunk.fetch_add(1);
+                if (ci + 1 >= chunk_begin.size() || failed.load()) break;
+                todo.emplace_back(chunk_begin[ci], chunk_begin[ci + 1] - chunk_begin[ci]);
             }
             const std::pair<size_t, size_t> range = todo.back();
             todo.pop_back();
@@ -2001,8 +2003,34 @@ struct Worker {
         }
     }
 
+    // The first chunk of a context is prepared (hashed, de-duplicated, looked up) before its device has anything to do, and the last
+    // one is formatted and sent after the device is through: with eight equal chunks that is a quarter of a chunk's host work on
+    // either side of the job (12 + 16 ms of a 1.17 s C3 job, profiles/r2y_e2e_probe_c3.txt).  When the chunk size is the library's
+    // choice the job starts and ends with chunks of an eighth, a quarter and a half of it -- one set per context.
+    void plan_chunks(size_t n_ctx) {
+        chunk_begin.assign(1, 0);
+        std::vector<size_t> steps;
+        for (size_t c = std::max<size_t>(1024, chunk_size / 8); c < chunk_size; c *= 2) steps.push_back(c);
+        size_t edge = 0;
+        for (size_t c : steps) edge += c * n_ctx;
+        if (!ramp || steps.empty() || nq < 2 * edge + 2 * n_ctx * chunk_size) {
+            for (size_t c = chunk_size; c < nq; c += chunk_size) chunk_begin.push_back(c);
+            chunk_begin.push_back(nq);
+            return;
+        }
+        size_t pos = 0;
+        for (size_t c : steps)
+            for (size_t k = 0; k < n_ctx; ++k) chunk_begin.push_back(pos += c);
+        const size_t mid_end = nq - edge;
+        while (pos + chunk_size < mid_end) chunk_begin.push_back(pos += chunk_size);
+        if (pos < mid_end) chunk_begin.push_back(pos = mid_end);
+        for (size_t i = steps.size(); i-- > 0;)
+            for (size_t k = 0; k < n_ctx; ++k) chunk_begin.push_back(pos += steps[i]);
+    }
+
     void run(rtx_ctx* const* ctxs, size_t n_ctx, bool sharded = false) {
         t_start = now();
+        if (!sharded) plan_chunks(n_ctx);
         t_first_issue = t_last_collect = t_start;
         size_t n_helpers = 0;
         if (const char* e = getenv("RXH_FORMAT_THREADS")) n_helpers = (size_t)std::max(0, atoi(e) - 1);
@@ -2099,6 +2127,7 @@ RXH_API int rxh_raxtax_multi(rtx_ctx* const* ctxs, size_t n_ctx, const rxh_queri
         return -1;
     }
     const size_t nq = queries->q->size();
+    const bool ramp = chunk_size == 0;
     if (chunk_size == 0) {
         // ~8 chunks per context so that the pipeline (upload | kernels | formatting) has something to overlap and results, the
         // progress file with them, appear while the run is going; bounded above so that the per-batch device arrays (~15 KB per
@@ -2106,6 +2135,7 @@ RXH_API int rxh_raxtax_multi(rtx_ctx* const* ctxs, size_t n_ctx, const rxh_queri
         chunk_size = std::min<size_t>(32768, std::max<size_t>(1024, (nq + n_ctx * 8 - 1) / (n_ctx * 8)));
     }
     Worker w{*tree_h->t, *queries->q, nq, chunk_size, skip_exact_matches, raw_confidence, tsv, sender, sender_user, logger, logger_user};
+    w.ramp = ramp;
     w.run(ctxs, n_ctx);
     if (warnings) *warnings = w.warned.load() ? 1 : 0;
     if (w.failed.load()) {
