@@ -91,11 +91,6 @@ struct IndexView {
     const u8* node_type;
     const u32* child_first;
     const u32* child_count;
-    const u32* node_blo;  // index of node_lo in the sorted boundary list (valid when the boundary lies in this shard)
-    const u32* node_bhi;
-    const u32* bnd_after;  // bitmap over local refs: bit r set iff a node boundary sits right after local ref r
-    const u32* bnd_rank;   // [row_words] number of set bits in bnd_after words before word w
-    u32 n_bnd;             // number of boundaries inside this shard, incl. local position 0
     u32 n_nodes;
     u32 max_levels;
     const u8* ref_levels;  // [n_refs]

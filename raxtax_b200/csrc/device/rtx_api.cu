@@ -96,7 +96,7 @@ struct rtx_ctx : BatchState {
     u64 index_bytes = 0;
     u64 mem_free_after_index = 8ull << 30;
     DevBuf d_bitrows, d_rowmap, d_present, d_csr_off, d_csr_ids, d_node_lo, d_node_hi, d_node_type, d_child_first, d_child_count,
-        d_node_blo, d_node_bhi, d_bnd_after, d_bnd_rank, d_ref_levels, d_lnfact, d_recs;
+        d_ref_levels, d_lnfact, d_recs;
     DevBuf d_seq_codes, d_idx_off;  // reference sequences / their offsets while the index is built from them
     size_t walk_smem = 0, bfs_smem = 0;
     // reference-sharded mode
@@ -323,8 +323,7 @@ RTX_API void rtx_ctx_destroy(rtx_ctx* c) {
     DevBuf* gb[] = {&c->d_agree, &c->d_all_begin, &c->d_rank_off, &c->d_g_first, &c->d_g_nlev, &c->d_g_conf, &c->d_g_local};
     for (DevBuf* b : gb) b->release();
     DevBuf* bufs[] = {&c->d_bitrows, &c->d_rowmap, &c->d_present, &c->d_csr_off, &c->d_csr_ids, &c->d_node_lo, &c->d_node_hi,
-                      &c->d_node_type, &c->d_child_first, &c->d_child_count, &c->d_node_blo, &c->d_node_bhi, &c->d_bnd_after,
-                      &c->d_bnd_rank, &c->d_ref_levels, &c->d_lnfact, &c->d_seq_codes, &c->d_idx_off, &c->d_recs, &c->d_strad_of_node,
+                      &c->d_node_type, &c->d_child_first, &c->d_child_count, &c->d_ref_levels, &c->d_lnfact, &c->d_seq_codes, &c->d_idx_off, &c->d_recs, &c->d_strad_of_node,
                       &c->d_strad_nodes, &c->d_strad_parent, &c->d_send, &c->d_recv, &c->d_sk, &c->d_sany, &c->d_sbest};
     for (DevBuf* b : bufs) b->release();
     for (int i = 0; i < 2; ++i) {
@@ -597,36 +596,8 @@ RTX_API int rtx_index_upload(rtx_ctx* ctx, const rtx_index_desc* d) {
     }
     CU(upload_vec(ctx->d_rowmap, rowmap.data(), 65536, &bytes));
 
-    // ---- node boundaries ---------------------------------------------------------------------------------
-    std::vector<u32> bnd_after(row_words, 0), bnd_rank(row_words, 0), blo(nn), bhi(nn);
+    // ---- lineage tree ------------------------------------------------------------------------------------
     auto clampu = [&](u64 x) { return std::min(std::max(x, s0), s1); };
-    auto mark = [&](u64 pos) {
-        if (pos > s0) {
-            u64 r = pos - s0 - 1;
-            bnd_after[r >> 5] |= 1u << (r & 31);
-        }
-    };
-    mark(s1);
-    for (u32 i = 0; i < nn; ++i) {
-        mark(clampu(d->node_lo[i]));
-        mark(clampu(d->node_hi[i]));
-    }
-    u32 run = 0;
-    for (u32 w = 0; w < row_words; ++w) {
-        bnd_rank[w] = run;
-        run += (u32)__builtin_popcount(bnd_after[w]);
-    }
-    const u32 n_bnd = run + 1;
-    auto bidx = [&](u64 pos) -> u32 {
-        if (pos == s0) return 0;
-        u64 r = pos - s0 - 1;
-        u32 w = bnd_after[r >> 5];
-        return 1u + bnd_rank[r >> 5] + (u32)__builtin_popcount(w & ((1u << (r & 31)) - 1u));
-    };
-    for (u32 i = 0; i < nn; ++i) {
-        blo[i] = bidx(clampu(d->node_lo[i]));
-        bhi[i] = bidx(clampu(d->node_hi[i]));
-    }
     CU(upload_vec(ctx->d_node_lo, d->node_lo, nn, &bytes));
     CU(upload_vec(ctx->d_node_hi, d->node_hi, nn, &bytes));
     CU(upload_vec(ctx->d_node_type, d->node_type, nn, &bytes));
@@ -640,10 +611,6 @@ RTX_API int rtx_index_upload(rtx_ctx* ctx, const rtx_index_desc* d) {
                               seg_of(clampu(d->node_lo[i])), seg_of(clampu(d->node_hi[i])), d->node_lo[i], d->node_hi[i] - d->node_lo[i]};
         CU(upload_vec(ctx->d_recs, recs.data(), nn, &bytes));
     }
-    CU(upload_vec(ctx->d_node_blo, blo.data(), nn, &bytes));
-    CU(upload_vec(ctx->d_node_bhi, bhi.data(), nn, &bytes));
-    CU(upload_vec(ctx->d_bnd_after, bnd_after.data(), row_words, &bytes));
-    CU(upload_vec(ctx->d_bnd_rank, bnd_rank.data(), row_words, &bytes));
     CU(upload_vec(ctx->d_ref_levels, d->ref_levels, N, &bytes));
 
     // ---- bit rows -----------------------------------------------------------------------------------------
@@ -752,11 +719,6 @@ RTX_API int rtx_index_upload(rtx_ctx* ctx, const rtx_index_desc* d) {
     ix.node_type = ctx->d_node_type.as<u8>();
     ix.child_first = ctx->d_child_first.as<u32>();
     ix.child_count = ctx->d_child_count.as<u32>();
-    ix.node_blo = ctx->d_node_blo.as<u32>();
-    ix.node_bhi = ctx->d_node_bhi.as<u32>();
-    ix.bnd_after = ctx->d_bnd_after.as<u32>();
-    ix.bnd_rank = ctx->d_bnd_rank.as<u32>();
-    ix.n_bnd = n_bnd;
     ix.n_nodes = nn;
     ix.max_levels = max_levels;
     ix.ref_levels = ctx->d_ref_levels.as<u8>();
