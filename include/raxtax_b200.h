@@ -201,7 +201,7 @@ int rtx_batch_slot(rtx_ctx* ctx, int slot);
  * Every rank uploads the same batch.  Per batch (which must fit one sub-batch):
  *   rtx_shard_phase1      k-mers, local hit counts, local histograms
  *   [all-reduce SUM, in place, of the hist buffer: uint32 [n_queries * hist_stride]]     <- the only O(Q*K) exchange
- *   rtx_shard_phase2      P(count) from the global histogram, local boundary prefixes, one record per
+ *   rtx_shard_phase2      P(count) from the global histogram, local block prefixes, one record per
  *                         (query, straddling node): local mass, local best child, local significant children
  *   [all-gather of the records buffer: send_bytes from every rank -> recv = n_shards * send_bytes, rank order]
  *   rtx_shard_phase3      combines the records, walks the part of the tree this rank owns

@@ -100,6 +100,12 @@ void rxh_count_logger(void* user, int level, const char* message);
  * rounded to nearest, ties to even.  Exposed so that tests can pin the fast path against the C library's conversion. */
 size_t rxh_format_fixed(double value, int precision, char* out, size_t cap);
 
+/* The chunks rxh_raxtax / rxh_raxtax_multi cut a job of n_queries into for n_ctx contexts (the reference's par_chunks, raxtax.rs:35-39,
+ * main.rs:119-124): chunk i = [begins[i], begins[i + 1]).  chunk_size 0 = the library's choice (about eight chunks per context, smaller
+ * ones at both ends of the job so that the host work before the first launch and behind the last one is short).  Writes at most cap
+ * values, returns how many there are.  Exposed for tests. */
+size_t rxh_plan_chunks(size_t n_queries, size_t n_ctx, size_t chunk_size, size_t* begins, size_t cap);
+
 int rxh_raxtax(rtx_ctx* ctx, const rxh_queries* queries, const rxh_tree* tree, int skip_exact_matches, int raw_confidence,
                size_t chunk_size, rxh_sender sender, void* sender_user, int tsv, rxh_logger logger, void* logger_user, int* warnings);
 

@@ -38,7 +38,7 @@ DEVICE_SYMBOLS = [
 HOST_SYMBOLS = [
     "rxh_last_error", "rxh_tree_from_fasta", "rxh_tree_from_file", "rxh_queries_from_file", "rxh_tree_from_bin", "rxh_tree_save_bin", "rxh_queries_skip", "rxh_tree_new", "rxh_tree_free", "rxh_tree_num_tips", "rxh_tree_lineage",
     "rxh_tree_csr", "rxh_tree_build_kmer_map", "rxh_tree_has_kmer_map", "rxh_tree_exact", "rxh_tree_index_desc", "rxh_tree_upload", "rxh_tree_upload_sharded", "rxh_queries_from_fasta", "rxh_queries_new",
-    "rxh_queries_free", "rxh_queries_len", "rxh_queries_label", "rxh_queries_arrays", "rxh_raxtax", "rxh_raxtax_multi", "rxh_raxtax_sharded", "rxh_merge_shard_results", "rxh_exact_batch", "rxh_count_sender", "rxh_count_logger", "rxh_format_fixed", "rxh_release_buffers",
+    "rxh_queries_free", "rxh_queries_len", "rxh_queries_label", "rxh_queries_arrays", "rxh_raxtax", "rxh_raxtax_multi", "rxh_raxtax_sharded", "rxh_merge_shard_results", "rxh_exact_batch", "rxh_count_sender", "rxh_count_logger", "rxh_format_fixed", "rxh_release_buffers", "rxh_plan_chunks",
 ]
 
 
@@ -199,6 +199,8 @@ def host_lib():
                                           C.POINTER(C.c_uint64)]
     L.rxh_format_fixed.restype = C.c_size_t
     L.rxh_format_fixed.argtypes = [C.c_double, C.c_int, C.c_char_p, C.c_size_t]
+    L.rxh_plan_chunks.restype = C.c_size_t
+    L.rxh_plan_chunks.argtypes = [C.c_size_t, C.c_size_t, C.c_size_t, C.POINTER(C.c_size_t), C.c_size_t]
     L.rxh_exact_batch.restype = C.c_uint64
     L.rxh_exact_batch.argtypes = [C.c_void_p, C.c_size_t, u64p, u8p, u32p, u32p, C.c_uint64]
     _host = L
@@ -534,6 +536,14 @@ class Counts(C.Structure):
 
     def as_dict(self):
         return {n: int(getattr(self, n)) for n, _ in self._fields_}
+
+
+def plan_chunks(n_queries: int, n_ctx: int = 1, chunk_size: int = 0) -> list:
+    """rxh_plan_chunks: the chunk boundaries the host driver uses (chunk_size 0 = the library's choice)."""
+    n = host_lib().rxh_plan_chunks(n_queries, n_ctx, chunk_size, None, 0)
+    buf = (C.c_size_t * n)()
+    host_lib().rxh_plan_chunks(n_queries, n_ctx, chunk_size, buf, n)
+    return list(buf)
 
 
 def format_fixed(value: float, precision: int) -> str:

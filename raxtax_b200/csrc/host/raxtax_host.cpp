@@ -1537,6 +1537,41 @@ static JobPool& job_pool() {
     return *p;
 }
 
+// The first chunk of a context is prepared (hashed, de-duplicated, looked up) before its device has anything to do, and the last
+// one is formatted and sent after the device is through: with eight equal chunks that is a quarter of a chunk's host work on
+// either side of the job (12 + 16 ms of a 1.17 s C3 job, profiles/r2y_e2e_probe_c3.txt).  When the chunk size is the library's
+// choice (`ramp`) the job starts and ends with chunks of an eighth, a quarter and a half of it -- one set per context.
+// -> chunk i = [begin[i], begin[i + 1]), begin.back() == nq
+static std::vector<size_t> plan_chunk_begins(size_t nq, size_t n_ctx, size_t chunk_size, bool ramp) {
+    std::vector<size_t> begin(1, 0);
+    if (nq == 0) return begin;
+    chunk_size = std::max<size_t>(1, chunk_size);
+    n_ctx = std::max<size_t>(1, n_ctx);
+    std::vector<size_t> steps;
+    for (size_t c = std::max<size_t>(1024, chunk_size / 8); c < chunk_size; c *= 2) steps.push_back(c);
+    size_t edge = 0;
+    for (size_t c : steps) edge += c * n_ctx;
+    if (!ramp || steps.empty() || nq < 2 * edge + 2 * n_ctx * chunk_size) {
+        for (size_t c = chunk_size; c < nq; c += chunk_size) begin.push_back(c);
+        begin.push_back(nq);
+        return begin;
+    }
+    size_t pos = 0;
+    for (size_t c : steps)
+        for (size_t k = 0; k < n_ctx; ++k) begin.push_back(pos += c);
+    const size_t mid_end = nq - edge;
+    const size_t n_head = begin.size();
+    while (pos + chunk_size < mid_end) begin.push_back(pos += chunk_size);
+    if (pos < mid_end) {  // the rest of the middle part: a chunk of its own, or -- a full launch sequence for a few queries does not pay -- part of the last one
+        if (mid_end - pos < chunk_size / 2 && begin.size() > n_head) begin.back() = mid_end;
+        else begin.push_back(mid_end);
+        pos = mid_end;
+    }
+    for (size_t i = steps.size(); i-- > 0;)
+        for (size_t k = 0; k < n_ctx; ++k) begin.push_back(pos += steps[i]);
+    return begin;
+}
+
 struct Worker {
     const Tree& tree;
     const Queries& qs;
@@ -2003,30 +2038,7 @@ struct Worker {
         }
     }
 
-    // The first chunk of a context is prepared (hashed, de-duplicated, looked up) before its device has anything to do, and the last
-    // one is formatted and sent after the device is through: with eight equal chunks that is a quarter of a chunk's host work on
-    // either side of the job (12 + 16 ms of a 1.17 s C3 job, profiles/r2y_e2e_probe_c3.txt).  When the chunk size is the library's
-    // choice the job starts and ends with chunks of an eighth, a quarter and a half of it -- one set per context.
-    void plan_chunks(size_t n_ctx) {
-        chunk_begin.assign(1, 0);
-        std::vector<size_t> steps;
-        for (size_t c = std::max<size_t>(1024, chunk_size / 8); c < chunk_size; c *= 2) steps.push_back(c);
-        size_t edge = 0;
-        for (size_t c : steps) edge += c * n_ctx;
-        if (!ramp || steps.empty() || nq < 2 * edge + 2 * n_ctx * chunk_size) {
-            for (size_t c = chunk_size; c < nq; c += chunk_size) chunk_begin.push_back(c);
-            chunk_begin.push_back(nq);
-            return;
-        }
-        size_t pos = 0;
-        for (size_t c : steps)
-            for (size_t k = 0; k < n_ctx; ++k) chunk_begin.push_back(pos += c);
-        const size_t mid_end = nq - edge;
-        while (pos + chunk_size < mid_end) chunk_begin.push_back(pos += chunk_size);
-        if (pos < mid_end) chunk_begin.push_back(pos = mid_end);
-        for (size_t i = steps.size(); i-- > 0;)
-            for (size_t k = 0; k < n_ctx; ++k) chunk_begin.push_back(pos += steps[i]);
-    }
+    void plan_chunks(size_t n_ctx) { chunk_begin = plan_chunk_begins(nq, n_ctx, chunk_size, ramp); }
 
     void run(rtx_ctx* const* ctxs, size_t n_ctx, bool sharded = false) {
         t_start = now();
@@ -2118,6 +2130,22 @@ RXH_API void rxh_count_logger(void* user, int level, const char* message) {
     if (level == 2) c->warn_lines += 1;
 }
 
+// ~8 chunks per context so that the pipeline (upload | kernels | formatting) has something to overlap and results, the progress file
+// with them, appear while the run is going; bounded above so that the per-batch device arrays (~15 KB per 1.5 kb query) stay small
+// next to the index, and below so that the index is not re-read from HBM for a handful of queries
+static size_t default_chunk_size(size_t nq, size_t n_ctx) {
+    return std::min<size_t>(32768, std::max<size_t>(1024, (nq + n_ctx * 8 - 1) / (n_ctx * 8)));
+}
+
+RXH_API size_t rxh_plan_chunks(size_t n_queries, size_t n_ctx, size_t chunk_size, size_t* begins, size_t cap) {
+    n_ctx = std::max<size_t>(1, n_ctx);
+    const bool ramp = chunk_size == 0;
+    if (ramp) chunk_size = default_chunk_size(n_queries, n_ctx);
+    const std::vector<size_t> b = plan_chunk_begins(n_queries, n_ctx, chunk_size, ramp);
+    for (size_t i = 0; i < b.size() && i < cap; ++i) begins[i] = b[i];
+    return b.size();
+}
+
 RXH_API int rxh_raxtax_multi(rtx_ctx* const* ctxs, size_t n_ctx, const rxh_queries* queries, const rxh_tree* tree_h, int skip_exact_matches,
                              int raw_confidence, size_t chunk_size, rxh_sender sender, void* sender_user, int tsv, rxh_logger logger,
                              void* logger_user, int* warnings) {
@@ -2128,12 +2156,7 @@ RXH_API int rxh_raxtax_multi(rtx_ctx* const* ctxs, size_t n_ctx, const rxh_queri
     }
     const size_t nq = queries->q->size();
     const bool ramp = chunk_size == 0;
-    if (chunk_size == 0) {
-        // ~8 chunks per context so that the pipeline (upload | kernels | formatting) has something to overlap and results, the
-        // progress file with them, appear while the run is going; bounded above so that the per-batch device arrays (~15 KB per
-        // 1.5 kb query) stay small next to the index, and below so that the index is not re-read from HBM for a handful of queries
-        chunk_size = std::min<size_t>(32768, std::max<size_t>(1024, (nq + n_ctx * 8 - 1) / (n_ctx * 8)));
-    }
+    if (chunk_size == 0) chunk_size = default_chunk_size(nq, n_ctx);
     Worker w{*tree_h->t, *queries->q, nq, chunk_size, skip_exact_matches, raw_confidence, tsv, sender, sender_user, logger, logger_user};
     w.ramp = ramp;
     w.run(ctxs, n_ctx);

@@ -351,3 +351,23 @@ def test_bench_strong_scaling_slices_cover_the_job_once():
     q_total, per, scaling = bench.workload_queries("c2", 4)
     assert scaling == "weak" and per == synth.CONFIGS["c2"][1] and q_total == 4 * per
     assert bench.workload_queries("c5", 8, 131072) == (131072, 131072, "strong")  # sharded references: every rank sees every query
+
+
+def test_chunk_plan_covers_every_query_once():
+    """rxh_plan_chunks (the driver's par_chunks, raxtax.rs:35-39): consecutive, non-empty chunks that cover [0, n) exactly; an explicit
+    chunk size is kept as given; the library's own choice starts and ends every context's share of the job with small chunks."""
+    for nq in (0, 1, 7, 999, 1024, 1025, 4096, 10_000, 25_000, 99_999, 200_000, 1_000_000):
+        for n_ctx in (1, 2, 8):
+            for cs in (0, 1, 64, 1000, 32768):
+                b = capi.plan_chunks(nq, n_ctx, cs)
+                assert b[0] == 0 and b[-1] == nq
+                sizes = [b[i + 1] - b[i] for i in range(len(b) - 1)]
+                assert all(x > 0 for x in sizes) and sum(sizes) == nq
+                if cs:
+                    assert all(x == cs for x in sizes[:-1]) and (not sizes or sizes[-1] <= cs)
+                elif sizes:
+                    assert max(sizes) <= 32768 * 3 // 2
+    sizes = np.diff(capi.plan_chunks(200_000, 1, 0))
+    assert sizes[0] < sizes[len(sizes) // 2] and sizes[-1] < sizes[len(sizes) // 2] and sizes[0] >= 1024
+    sizes8 = np.diff(capi.plan_chunks(200_000, 8, 0))
+    assert len(set(sizes8[:8])) == 1 and len(set(sizes8[-8:])) == 1  # one small first and last chunk per context
