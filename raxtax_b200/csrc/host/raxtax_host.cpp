@@ -154,12 +154,30 @@ static bool capture_tax(const char* b, const char* e, std::string* out) {
     }
 }
 
+// std::vector::resize zero-fills: for the sorted copy of the sequences (650 MB per million 650 bp references) that is a single-threaded
+// pass over memory the parallel copy behind it overwrites entirely.  With this allocator resize leaves the bytes alone.
+template <typename T>
+struct DefaultInitAlloc : std::allocator<T> {
+    template <typename U>
+    struct rebind {
+        using other = DefaultInitAlloc<U>;
+    };
+    template <typename U>
+    void construct(U* p) noexcept {
+        ::new (static_cast<void*>(p)) U;
+    }
+    template <typename U, typename... A>
+    void construct(U* p, A&&... a) {
+        ::new (static_cast<void*>(p)) U(std::forward<A>(a)...);
+    }
+};
+
 // ---- Tree (tree.rs:36-43) in flat form --------------------------------------------------------------------------
 struct Tree {
     size_t num_tips = 0;
     std::vector<std::string> lineages;  // sorted (tree.rs:128-131)
     std::vector<u64> seq_off;           // sorted sequences, 4-bit codes
-    std::vector<u8> seq_codes;
+    std::vector<u8, DefaultInitAlloc<u8>> seq_codes;
     std::vector<u64> csr_off;  // k_mer_map (tree.rs:41): 65537 offsets.  Built on first use (ensure_csr): the device builds its own
     std::vector<u32> csr_ids;  // index from the sorted sequences, so the classification path never needs the lists on the host
     bool has_csr = false;
@@ -411,72 +429,187 @@ static std::unique_ptr<Tree> tree_new(std::vector<std::string> lineages, const u
         });
     }
     lap("sequences copied");
-    struct LevelView {
-        const char* p;
-        size_t n;
-        bool equals(const std::string& s) const { return s.size() == n && (n == 0 || memcmp(s.data(), p, n) == 0); }
-        std::string str() const { return std::string(p, n); }
-    };
-    std::vector<LevelView> levels;
-    for (size_t idx = 0; idx < n; ++idx) {  // tree.rs:56-126
-        const std::string& lineage = lineages[order[idx]];
-        levels.clear();
+    // the lineages in sorted order (tree.rs:128-131) before the node walk reads them: the walk then goes through them front to back
+    // instead of chasing order[] into the input
+    tree->lineages.resize(n);
+    {
+        const size_t blocks = (n + 16383) / 16384;
+        parallel_for(blocks, [&](size_t b) {
+            const size_t hi = std::min(n, (b + 1) * 16384);
+            for (size_t idx = b * 16384; idx < hi; ++idx) tree->lineages[idx] = std::move(lineages[order[idx]]);
+        });
+    }
+    lap("lineages in sorted order");
+    // ---- nodes (tree.rs:56-126).  The references are sorted and the reference compares a level's label with the LAST child only
+    // (tree.rs:77-96), so which nodes a reference creates is decided by the lineage right before it alone: it re-uses that one's nodes on
+    // the leading levels the two share and opens new ones below; when the previous lineage is a prefix of this one, level-wise, its final
+    // node still has the implicit Sequence leaf as last child (tree.rs:102-106), and a next level repeating that node's label walks INTO
+    // the leaf.  That makes the string work -- levels, shared levels, the repeated-label test -- independent per reference (parallel);
+    // what is left for the sequential pass is integer bookkeeping: node ids in creation order, child lists, ranges.
+    // RXH_TREE_WALK=1 runs the level-by-level walk of round 1 instead (kept as the statement the tests compare with).
+    if (getenv("RXH_TREE_WALK") == nullptr) {
+        std::vector<u8> n_lev(n), n_shared(n), degenerate(n);
+        std::atomic<bool> too_deep{false};
         {
-            size_t start = 0;
-            while (true) {
-                size_t p = lineage.find(',', start);
-                if (p == std::string::npos) {
-                    levels.push_back(LevelView{lineage.data() + start, lineage.size() - start});
-                    break;
+            const size_t blocks = (n + 16383) / 16384;
+            parallel_for(blocks, [&](size_t b) {
+                const size_t hi = std::min(n, (b + 1) * 16384);
+                for (size_t idx = b * 16384; idx < hi; ++idx) {
+                    const std::string& cur = tree->lineages[idx];
+                    const size_t levels = (size_t)std::count(cur.begin(), cur.end(), ',') + 1;
+                    if (levels > 255) {
+                        too_deep.store(true);
+                        continue;
+                    }
+                    n_lev[idx] = (u8)levels;
+                    tree->ref_levels[idx] = (u8)levels;
+                    size_t shared = 0;
+                    bool deg = false;
+                    if (idx > 0) {
+                        const std::string& prev = tree->lineages[idx - 1];
+                        const size_t m = std::min(prev.size(), cur.size());
+                        size_t k = 0, last_comma = std::string::npos;  // the last comma inside the common part
+                        while (k < m && prev[k] == cur[k]) {
+                            if (cur[k] == ',') {
+                                ++shared;
+                                last_comma = k;
+                            }
+                            ++k;
+                        }
+                        if (k == m && prev.size() == cur.size()) {
+                            ++shared;  // the same lineage again
+                        } else if (k == prev.size() && k < cur.size() && cur[k] == ',') {
+                            ++shared;  // the previous lineage is a prefix of this one, level-wise: its final node is on this one's path
+                            // label of the previous lineage's last level (= this one's level shared - 1) against this one's next level
+                            const size_t a0 = last_comma == std::string::npos ? 0 : last_comma + 1, a1 = k;
+                            const size_t b0 = k + 1;
+                            size_t b1 = cur.find(',', b0);
+                            if (b1 == std::string::npos) b1 = cur.size();
+                            deg = (a1 - a0) == (b1 - b0) && cur.compare(a0, a1 - a0, cur, b0, b1 - b0) == 0;
+                        }
+                    }
+                    n_shared[idx] = (u8)std::min<size_t>(shared, 255);
+                    degenerate[idx] = deg ? 1 : 0;
                 }
-                levels.push_back(LevelView{lineage.data() + start, p - start});
-                start = p + 1;
-            }
+            });
         }
-        if (levels.size() > 255) throw Error("lineage with more than 255 ranks");
-        tree->ref_levels[idx] = (u8)levels.size();
-        const size_t last_level = levels.size() - 1;
-        u32 cur = 0;
-        for (size_t level = 0; level < levels.size(); ++level) {
-            const LevelView& label = levels[level];
-            const u8 nt = level == last_level ? 1 : 0;
-            BNode& c = nodes[cur];
-            bool need_new = true;
-            u32 next = 0;
-            if (c.trailing_seq) {  // last child is the Sequence leaf carrying this node's own label (tree.rs:102-106)
-                if (label.equals(c.label)) {
-                    // degenerate lineage (a rank repeats its parent's label): the reference walks INTO the Sequence node
-                    BNode s{c.label, c.hi - 1, c.hi, 2, {}, false};
+        if (too_deep.load()) throw Error("lineage with more than 255 ranks");
+        std::vector<u32> path;  // node of every level of the previous reference
+        for (size_t idx = 0; idx < n; ++idx) {
+            const size_t levels = n_lev[idx];
+            const size_t shared = std::min<size_t>(std::min<size_t>(n_shared[idx], path.size()), levels);
+            for (size_t l = shared; l < path.size(); ++l) nodes[path[l]].hi = (u32)idx;  // the previous reference's nodes below the shared levels end here
+            path.resize(levels);
+            for (size_t level = shared; level < levels; ++level) {
+                const u32 parent = level == 0 ? 0u : path[level - 1];
+                const u32 id = (u32)nodes.size();
+                if (level == shared && degenerate[idx])
+                    nodes.push_back(BNode{std::string(), (u32)idx - 1, (u32)idx, 2, {}, false});  // the Sequence leaf of the reference before (tree.rs:102-106)
+                else
+                    nodes.push_back(BNode{std::string(), (u32)idx, (u32)idx + 1, (u8)(level == levels - 1 ? 1 : 0), {}, false});
+                nodes[parent].children.push_back(id);
+                nodes[parent].trailing_seq = false;
+                path[level] = id;
+            }
+            nodes[path[levels - 1]].trailing_seq = true;  // add_child(Sequence(label, ci-1)) (tree.rs:102-106)
+            confidence_idx += 1;
+        }
+        for (size_t l = 0; l < path.size(); ++l) nodes[path[l]].hi = (u32)n;
+    } else {
+        struct LevelView {
+            const char* p;
+            size_t n;
+            bool equals(const std::string& s) const { return s.size() == n && (n == 0 || memcmp(s.data(), p, n) == 0); }
+            std::string str() const { return std::string(p, n); }
+        };
+        std::vector<LevelView> levels;
+        // The references arrive sorted, so a lineage shares its leading levels with the one before it, and on those levels the walk of
+        // tree.rs:77-96 finds "the last child carries my label" -- the node the previous reference went through (it is still the last
+        // child: everything added since went below it, and a node with children never has a trailing Sequence leaf).  Those levels only
+        // extend the node ranges; label comparisons and the split at ',' start at the first level that differs.
+        std::vector<u32> path;       // node of every level of the previous reference
+        const std::string* prev = nullptr;
+        for (size_t idx = 0; idx < n; ++idx) {  // tree.rs:56-126
+            const std::string& lineage = tree->lineages[idx];
+            if (idx + 8 < n) __builtin_prefetch(tree->lineages[idx + 8].data());
+            size_t shared = 0;  // leading levels equal to the previous lineage's
+            if (prev) {
+                const size_t m = std::min(prev->size(), lineage.size());
+                size_t k = 0;
+                while (k < m && (*prev)[k] == lineage[k]) ++k;
+                const bool whole = k == m && prev->size() == lineage.size();  // the same lineage again
+                for (size_t j = 0; j < k; ++j)
+                    if (lineage[j] == ',') ++shared;
+                if (whole || (k == prev->size() && k < lineage.size() && lineage[k] == ','))
+                    ++shared;  // the same lineage again / the previous one is a strict prefix of this one, level-wise (variable depth)
+                shared = std::min(shared, path.size());
+            }
+            levels.clear();
+            {
+                size_t start = 0;
+                while (true) {
+                    size_t p = lineage.find(',', start);
+                    if (p == std::string::npos) {
+                        levels.push_back(LevelView{lineage.data() + start, lineage.size() - start});
+                        break;
+                    }
+                    levels.push_back(LevelView{lineage.data() + start, p - start});
+                    start = p + 1;
+                }
+            }
+            if (levels.size() > 255) throw Error("lineage with more than 255 ranks");
+            tree->ref_levels[idx] = (u8)levels.size();
+            const size_t last_level = levels.size() - 1;
+            shared = std::min(shared, levels.size());
+            path.resize(levels.size());
+            u32 cur = 0;
+            for (size_t level = 0; level < levels.size(); ++level) {
+                if (level < shared) {  // the previous reference's node of this level: only its range grows (tree.rs:95-96)
+                    nodes[cur].hi = (u32)confidence_idx + 1;
+                    if (level == last_level) confidence_idx += 1;
+                    cur = path[level];
+                    continue;
+                }
+                const LevelView& label = levels[level];
+                const u8 nt = level == last_level ? 1 : 0;
+                BNode& c = nodes[cur];
+                bool need_new = true;
+                u32 next = 0;
+                if (c.trailing_seq) {  // last child is the Sequence leaf carrying this node's own label (tree.rs:102-106)
+                    if (label.equals(c.label)) {
+                        // degenerate lineage (a rank repeats its parent's label): the reference walks INTO the Sequence node
+                        BNode s{c.label, c.hi - 1, c.hi, 2, {}, false};
+                        next = (u32)nodes.size();
+                        nodes.push_back(std::move(s));
+                        nodes[cur].children.push_back(next);
+                        nodes[cur].trailing_seq = false;
+                        need_new = false;
+                    }
+                } else if (!c.children.empty()) {
+                    next = c.children.back();
+                    if (label.equals(nodes[next].label)) need_new = false;
+                }
+                if (need_new) {
                     next = (u32)nodes.size();
-                    nodes.push_back(std::move(s));
+                    nodes.push_back(BNode{label.str(), (u32)confidence_idx, (u32)confidence_idx + 1, nt, {}, false});
                     nodes[cur].children.push_back(next);
                     nodes[cur].trailing_seq = false;
-                    need_new = false;
                 }
-            } else if (!c.children.empty()) {
-                next = c.children.back();
-                if (label.equals(nodes[next].label)) need_new = false;
+                nodes[cur].hi = (u32)confidence_idx + 1;
+                if (level == last_level) confidence_idx += 1;
+                cur = next;
+                path[level] = cur;
             }
-            if (need_new) {
-                next = (u32)nodes.size();
-                nodes.push_back(BNode{label.str(), (u32)confidence_idx, (u32)confidence_idx + 1, nt, {}, false});
-                nodes[cur].children.push_back(next);
-                nodes[cur].trailing_seq = false;
-            }
-            nodes[cur].hi = (u32)confidence_idx + 1;
-            if (level == last_level) confidence_idx += 1;
-            cur = next;
+            nodes[cur].trailing_seq = true;  // add_child(Sequence(label, ci-1)) (tree.rs:102-106)
+            nodes[cur].hi = (u32)confidence_idx;  // tree.rs:107
+            prev = &lineage;
         }
-        nodes[cur].trailing_seq = true;  // add_child(Sequence(label, ci-1)) (tree.rs:102-106)
-        nodes[cur].hi = (u32)confidence_idx;  // tree.rs:107
     }
     lap("nodes");
     tree->build_exact();  // tree.rs:109-112
     lap("sequence map");
     nodes[0].hi = (u32)confidence_idx;  // tree.rs:127
     tree->num_tips = confidence_idx;    // tree.rs:138
-    tree->lineages.resize(n);
-    for (size_t i = 0; i < n; ++i) tree->lineages[i] = std::move(lineages[order[i]]);
 
     if (eager_csr) build_csr(*tree);  // tree.rs:114-123,134-137; otherwise on first use
     lap(eager_csr ? "k_mer_map (CSR), 2 passes" : "k_mer_map deferred");

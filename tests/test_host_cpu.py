@@ -371,3 +371,52 @@ def test_chunk_plan_covers_every_query_once():
     assert sizes[0] < sizes[len(sizes) // 2] and sizes[-1] < sizes[len(sizes) // 2] and sizes[0] >= 1024
     sizes8 = np.diff(capi.plan_chunks(200_000, 8, 0))
     assert len(set(sizes8[:8])) == 1 and len(set(sizes8[-8:])) == 1  # one small first and last chunk per context
+
+
+def test_host_tree_matches_oracle_on_random_degenerate_lineages(oracle):
+    """Tree::new (tree.rs:47-140) on lineages drawn from a tiny label alphabet: repeated labels along a lineage, lineages that are
+    prefixes of others (variable depth), empty levels, many identical lineages -- the cases in which the host's shared-prefix walk could
+    part from the reference's "compare with the last child only" rule."""
+    rng = np.random.default_rng(123)
+    labels = ["a", "b", "ab", "", "a,", "c"]
+    for case in range(60):
+        n = int(rng.integers(1, 70))
+        lineages = []
+        for _ in range(n):
+            depth = int(rng.integers(1, 6))
+            lin = ",".join(labels[int(rng.integers(0, 4 if case % 2 else 3))].rstrip(",") for _ in range(depth))
+            lineages.append(lin)
+            if rng.random() < 0.3:
+                lineages.append(lin)  # the same lineage again (several Sequence leaves under one taxon)
+        seqs = [synth.BASE_CODES[rng.integers(0, 4, int(rng.integers(8, 24)))] for _ in lineages]
+        off, codes = oracle.pack_sequences(seqs)
+        _compare_tree(oracle.Tree.new(lineages, seqs), capi.Tree.new(lineages, off, codes))
+
+
+def test_tree_build_pairwise_equals_level_walk(oracle):
+    """The node tree built from consecutive lineage pairs (parallel string work + an integer pass, the default) is the tree the
+    level-by-level walk of tree.rs:56-126 builds (RXH_TREE_WALK=1), on degenerate random lineages and on a synthetic set."""
+    rng = np.random.default_rng(321)
+    labels = ["a", "b", "ab", "", "c", "a!"]
+    cases = []
+    for case in range(80):
+        lineages = []
+        for _ in range(int(rng.integers(1, 120))):
+            lin = ",".join(labels[int(rng.integers(0, 3 + case % 4))] for _ in range(int(rng.integers(1, 6))))
+            lineages += [lin] * int(rng.integers(1, 4))
+        rng.shuffle(lineages)
+        cases.append(lineages)
+    ds = synth.generate("small", n_queries=1, measure=False)
+    cases.append(list(ds.ref_lineages))
+    for lineages in cases:
+        seqs = [synth.BASE_CODES[rng.integers(0, 4, 12)] for _ in lineages]
+        off, codes = oracle.pack_sequences(seqs)
+        a = capi.Tree.new(lineages, off, codes).index_arrays()
+        os.environ["RXH_TREE_WALK"] = "1"
+        try:
+            b = capi.Tree.new(lineages, off, codes).index_arrays()
+        finally:
+            del os.environ["RXH_TREE_WALK"]
+        assert a.keys() == b.keys()
+        for k in a:
+            assert np.array_equal(a[k], b[k]), k
