@@ -98,7 +98,27 @@ static inline u8 map_dna_char(char ch) {
     return v;
 }
 // one sequence line appended to a code vector: table translation in bulk, the (rare) bad character found afterwards
-static inline void append_codes(std::vector<u8>& codes, const char* b, const char* e) {
+// std::vector::resize zero-fills: for the code bytes of a FASTA file and the sorted copy of the sequences (650 MB per million 650 bp
+// references, written three times on the way from the text to the Tree) that is a pass over memory the real writer behind it overwrites
+// entirely.  With this allocator resize leaves the bytes alone.
+template <typename T>
+struct DefaultInitAlloc : std::allocator<T> {
+    template <typename U>
+    struct rebind {
+        using other = DefaultInitAlloc<U>;
+    };
+    template <typename U>
+    void construct(U* p) noexcept {
+        ::new (static_cast<void*>(p)) U;
+    }
+    template <typename U, typename... A>
+    void construct(U* p, A&&... a) {
+        ::new (static_cast<void*>(p)) U(std::forward<A>(a)...);
+    }
+};
+using ByteVec = std::vector<u8, DefaultInitAlloc<u8>>;
+
+static inline void append_codes(ByteVec& codes, const char* b, const char* e) {
     const size_t at = codes.size(), n = (size_t)(e - b);
     codes.resize(at + n);
     u8* out = codes.data() + at;
@@ -154,30 +174,12 @@ static bool capture_tax(const char* b, const char* e, std::string* out) {
     }
 }
 
-// std::vector::resize zero-fills: for the sorted copy of the sequences (650 MB per million 650 bp references) that is a single-threaded
-// pass over memory the parallel copy behind it overwrites entirely.  With this allocator resize leaves the bytes alone.
-template <typename T>
-struct DefaultInitAlloc : std::allocator<T> {
-    template <typename U>
-    struct rebind {
-        using other = DefaultInitAlloc<U>;
-    };
-    template <typename U>
-    void construct(U* p) noexcept {
-        ::new (static_cast<void*>(p)) U;
-    }
-    template <typename U, typename... A>
-    void construct(U* p, A&&... a) {
-        ::new (static_cast<void*>(p)) U(std::forward<A>(a)...);
-    }
-};
-
 // ---- Tree (tree.rs:36-43) in flat form --------------------------------------------------------------------------
 struct Tree {
     size_t num_tips = 0;
     std::vector<std::string> lineages;  // sorted (tree.rs:128-131)
     std::vector<u64> seq_off;           // sorted sequences, 4-bit codes
-    std::vector<u8, DefaultInitAlloc<u8>> seq_codes;
+    ByteVec seq_codes;
     std::vector<u64> csr_off;  // k_mer_map (tree.rs:41): 65537 offsets.  Built on first use (ensure_csr): the device builds its own
     std::vector<u32> csr_ids;  // index from the sorted sequences, so the classification path never needs the lists on the host
     bool has_csr = false;
@@ -879,7 +881,7 @@ static std::unique_ptr<Tree> load_bin(const u8* data, size_t len) {
 struct FastaPiece {
     std::vector<std::string> labels;  // lineage (references) or the whole header line after '>' (queries), one per header
     std::vector<u64> lens;            // codes that follow that header inside the piece
-    std::vector<u8> codes;
+    ByteVec codes;
     std::string error;                // what the serial parser would have raised first inside this piece
     bool headless_codes = false;      // sequence lines before the piece's first header (only the very first piece can have them)
 };
@@ -919,7 +921,7 @@ struct FastaAccumulator {
     bool any_line = false;
     std::vector<std::string> labels;  // one per header so far
     std::vector<u64> lens;
-    std::vector<u8> codes;
+    ByteVec codes;
     std::vector<FastaPiece> pieces;  // kept between blocks: their buffers are reused instead of being mapped and faulted in again
     explicit FastaAccumulator(bool ref) : reference(ref) {}
 
@@ -1025,13 +1027,10 @@ static void accumulate_file(FastaAccumulator& acc, const std::string& path) {
     read_block(carry);
     bool any = !carry.empty();
     while (true) {
-        std::thread reader;
-        next.clear();
-        if (!eof && !read_err) reader = std::thread([&] { read_block(next); });
-        // parse carry up to its last record boundary; at the end of the file all of it
+        // parse carry up to its last record boundary; at the end of the file (or after a read error, reported below) all of it
+        const bool more = !eof && !read_err;
         size_t split = carry.size();
-        const bool last = eof && !reader.joinable();
-        if (!last) {
+        if (more) {
             split = 0;
             for (size_t p = carry.size(); p-- > 1;)
                 if (carry[p] == '>' && carry[p - 1] == '\n') {
@@ -1039,8 +1038,18 @@ static void accumulate_file(FastaAccumulator& acc, const std::string& path) {
                     break;
                 }
         }
+        // the reader thread puts the next block behind the unparsed rest of this one (less than a record, unless the block holds no
+        // header at all), so that the text is not shifted a second time
+        std::thread reader;
+        auto tp0b = std::chrono::steady_clock::now();
+        next.clear();
+        if (more) {
+            next.assign(carry, split, std::string::npos);
+            reader = std::thread([&] { read_block(next); });
+        }
         std::exception_ptr perr;
         auto tp1 = std::chrono::steady_clock::now();
+        t_shift += std::chrono::duration<double>(tp1 - tp0b).count();
         try {
             if (split > 0) acc.add_block(carry.data(), carry.data() + split);
         } catch (...) {
@@ -1055,11 +1064,9 @@ static void accumulate_file(FastaAccumulator& acc, const std::string& path) {
             gzclose(f);
             std::rethrow_exception(perr);
         }
-        if (last) break;
-        carry.erase(0, split);
-        any = any || !next.empty();
-        carry += next;
-        t_shift += std::chrono::duration<double>(std::chrono::steady_clock::now() - tp3).count();
+        if (!more) break;
+        carry.swap(next);
+        any = any || !carry.empty();
     }
     gzclose(f);
     if (timing)
@@ -1093,7 +1100,7 @@ static std::unique_ptr<Tree> parse_reference_fasta_str(const char* text, size_t 
 struct Queries {
     std::vector<std::string> labels;
     std::vector<u64> off;
-    std::vector<u8> codes;
+    ByteVec codes;
     size_t size() const { return labels.size(); }
 };
 
